@@ -1,0 +1,175 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY.  Regenerates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference and `make -C oracle ref`):
+    python oracle/make_golden.py
+
+Every fixture holds an input configuration (as the reference's generators / its own `MD` wrote it) and the
+reference's outputs on it:
+  * per-term accelerations / potentials / dPotentials, cell ids and linked-list order from
+    oracle/_ref/ref_harness (which calls the reference headers: CellOpt, Blob::do*Force, ...),
+  * for the `traj_*` entries the state written by the reference `MD` executable itself
+    (OMP_NUM_THREADS=1, so the Langevin noise is the single MT19937 stream MTRand(seed)) after K steps.
+The reference ships no golden vectors of its own; these are "outputs of the reference
+run here".
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import orc  # noqa: E402
+
+REF = os.path.join(HERE, "_ref")
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+ENV1 = dict(os.environ, OMP_NUM_THREADS="1")
+
+
+def run(cmd, cwd):
+    subprocess.run(cmd, cwd=cwd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=ENV1)
+
+
+def run_md(cwd, m, name, nsteps):
+    """run the reference MD for nsteps from m (dict); returns the dict it stored at its last step.
+    The reference stores inside iteration endInt, after Verlet::first and before the new forces
+    (MD.cpp:373-381), so the returned state is {x after first(), v at the half kick}."""
+    m = dict(m)
+    t0 = m["initialTime"]
+    start = int(t0 / m["deltaT"] + 1e-7)
+    end = start + nsteps
+    m["finalTime"] = end * m["deltaT"]
+    m["measureInterval"] = 1e6
+    # store only at the final step: i % storeint == 0 for i in (start, end] only at i == end when storeint == end
+    m["storeInterval"] = end * m["deltaT"]
+    orc.write_mpd(os.path.join(cwd, name + ".mpd"), m)
+    run([os.path.join(REF, "MD"), name], cwd)
+    return orc.read_mpd(os.path.join(cwd, name + ".mpd"))
+
+
+def harness(cwd, name, scale=None):
+    cmd = [os.path.join(REF, "ref_harness"), "dump", name, name + ".bin"]
+    if scale is not None:
+        cmd += [repr(float(s)) for s in scale]
+    run(cmd, cwd)
+    return orc.read_dump(os.path.join(cwd, name + ".bin"))
+
+
+def pack(m, g, extra=None):
+    d = {"nTypes": m["nTypes"], "box": np.array(m["size"]), "cutoff": m["cutoff"], "deltaT": m["deltaT"],
+         "gamma": m["gamma"], "temperature": m["initialTemp"], "seed": m["seed"], "initialTime": m["initialTime"],
+         "deltaLXY": m.get("deltaLXY", 0.0), "tension": m.get("tension", 0.0),
+         "xyz": m["xyz"], "vel": m["vel"], "type": m["type"], "fC": m["twoBodyFconst"], "uC": m["twoBodyUconst"],
+         "nmol": len(m["molecules"])}
+    for k, mol in enumerate(m["molecules"]):
+        d[f"mol{k}_type"] = mol["type"]
+        d[f"mol{k}_bonds"] = mol["bonds"]
+        d[f"mol{k}_const"] = mol["constants"]
+    for key in ("scale", "cell_id", "cell_next", "nCells_nFull", "fullCells", "a_pair", "U_pair", "dU_pair",
+                "U_mol", "dU_mol", "kinetic"):
+        if key in g:
+            d["ref_" + key] = g[key]
+    for k in range(len(m["molecules"])):
+        d[f"ref_a_mol{k}"] = g[f"a_mol{k}"]
+    if extra:
+        d.update(extra)
+    return d
+
+
+def traj(cwd, m, name, nsteps):
+    f = run_md(cwd, m, name, nsteps)
+    return {"traj_steps": nsteps, "traj_xyz": f["xyz"], "traj_vel": f["vel"], "traj_box": np.array(f["size"]),
+            "traj_time": f["initialTime"]}, f
+
+
+def save(name, d):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(f"{name}: N={len(d['xyz'])} nmol={d['nmol']} -> {os.path.getsize(os.path.join(OUT, name + '.npz')) // 1024} KiB")
+
+
+def main():
+    tmp = tempfile.mkdtemp(prefix="golden_")
+    try:
+        # ---- liposome, 300 lipids (CHAIN only; box 400^3 -> 8e6 cells, 0.01% occupied)
+        run([os.path.join(REF, "liposome"), "lipo", "42", "300", "3.45"], tmp)
+        m = orc.read_mpd(os.path.join(tmp, "lipo.mpd"))
+        t, eq = traj(tmp, m, "lipo_run", 24)
+        save("lipo_t0", pack(m, harness(tmp, "lipo"), t))
+        _, eq = traj(tmp, m, "lipo_run", 150)
+        orc.write_mpd(os.path.join(tmp, "lipo_eq.mpd"), eq)
+        t, _ = traj(tmp, eq, "lipo_run2", 16)  # restart path: initialTime != 0 (MD.cpp:274-308)
+        save("lipo_eq", pack(eq, harness(tmp, "lipo_eq", (0.9993, 0.9993, 1.0 / 0.9993 ** 2)), t))
+
+        # ---- explicit BOND + BEND lists equivalent to the CHAIN (list code paths, system.h:1880-2040)
+        mb = dict(eq)
+        ch = eq["molecules"][0]
+        start, nch, ln = [int(x) for x in ch["bonds"][0]]
+        bonds = np.array([[s + l, s + l + 1] for s in range(start, start + nch * ln, ln) for l in range(ln - 1)], np.int32)
+        bends = np.array([[s + l, s + l + 1, s + l + 2] for s in range(start, start + nch * ln, ln) for l in range(ln - 2)], np.int32)
+        mb["molecules"] = [{"type": orc.BOND, "constants": ch["constants"][:2], "bonds": bonds},
+                           {"type": orc.BEND, "constants": ch["constants"][2:], "bonds": bends}]
+        mb["nMolecules"] = 2
+        orc.write_mpd(os.path.join(tmp, "bondbend.mpd"), mb)
+        save("bondbend", pack(mb, harness(tmp, "bondbend")))
+
+        # ---- flat bilayer, fully periodic small box (pairs across the boundary), MC box moves with tension
+        run([os.path.join(REF, "bilayer"), "bl", "99", "600", "3.11", "0", "0", "0", "0"], tmp)
+        m = orc.read_mpd(os.path.join(tmp, "bl.mpd"))
+        m["tension"] = 0.5
+        orc.write_mpd(os.path.join(tmp, "bl.mpd"), m)
+        t, _ = traj(tmp, m, "bl_run", 24)  # MC trials at i = 8, 16, 24
+        save("bilayer_t0", pack(m, harness(tmp, "bl"), t))
+        _, eq = traj(tmp, m, "bl_run", 200)
+        orc.write_mpd(os.path.join(tmp, "bl_eq.mpd"), eq)
+        t, _ = traj(tmp, eq, "bl_run2", 16)
+        save("bilayer_eq", pack(eq, harness(tmp, "bl_eq", (1.0004, 1.0004, 1.0 / 1.0004 ** 2)), t))
+
+        # ---- liposome + cytoskeleton: CHAIN(3) + CHAIN(6) + BOND anchors
+        run([os.path.join(REF, "lipoCyto"), "lc", "4321", "-6", "0", "800", "3.45", "0", "6", "1"], tmp)
+        m = orc.read_mpd(os.path.join(tmp, "lc.mpd"))
+        _, eq = traj(tmp, m, "lc_run", 100)
+        orc.write_mpd(os.path.join(tmp, "lc_eq.mpd"), eq)
+        save("lipocyto_eq", pack(eq, harness(tmp, "lc_eq")))
+
+        # ---- vesicle + continuum-sphere bead (BEAD molecule, 8 types).  The generator starts the bead out of range
+        # (SURVEY 8c), so pull it onto the outer leaflet.
+        run([os.path.join(REF, "continuumSphereAndLiposome"), "cs", "1234", "1200", "3.45", "3", "-6", "40", "5.88",
+             "0", "1", "0", "2.0"], tmp)
+        m = orc.read_mpd(os.path.join(tmp, "cs.mpd"))
+        b = int(m["molecules"][1]["bonds"][0, 0])
+        m["xyz"][b, 2] -= 2.2
+        orc.write_mpd(os.path.join(tmp, "bead1.mpd"), m)
+        t, _ = traj(tmp, m, "bead1_run", 16)  # covers the double mass division quirk (MD.cpp:340-355, :480-494)
+        save("bead1", pack(m, harness(tmp, "bead1"), t))
+
+        # two beads in one BEAD molecule, close to each other and to the membrane (bead-bead term + exclusion quirk Q7)
+        m2 = dict(m)
+        m2["xyz"] = np.vstack([m["xyz"], m["xyz"][b] + np.array([4.6, 0.3, -0.4])])
+        m2["vel"] = np.vstack([m["vel"], [0.1, -0.2, 0.05]])
+        m2["type"] = np.append(m["type"], m["type"][b]).astype(np.int32)
+        m2["nParticles"] = m["nParticles"] + 1
+        m2["molecules"] = [m["molecules"][0], {"type": orc.BEAD, "constants": m["molecules"][1]["constants"],
+                                               "bonds": np.array([[b], [b + 1]], np.int32)}]
+        orc.write_mpd(os.path.join(tmp, "bead2.mpd"), m2)
+        t, _ = traj(tmp, m2, "bead2_run", 8)
+        save("bead2", pack(m2, harness(tmp, "bead2"), t))
+
+        # ---- MT19937 known answers (MersenneTwister.h) for the barostat / reference-noise streams
+        run([os.path.join(REF, "ref_harness"), "mt", "5000", "64", "mt.bin"], tmp)
+        g = orc.read_dump(os.path.join(tmp, "mt.bin"))
+        run([os.path.join(REF, "ref_harness"), "mt", "42", "64", "mt2.bin"], tmp)
+        g2 = orc.read_dump(os.path.join(tmp, "mt2.bin"))
+        np.savez_compressed(os.path.join(OUT, "mt19937.npz"), seed5000_rand53=g["rand53"],
+                            seed5000_u32=g["randInt"].view(np.uint32), seed42_rand53=g2["rand53"],
+                            seed42_u32=g2["randInt"].view(np.uint32))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
