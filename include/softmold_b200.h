@@ -1,0 +1,220 @@
+/*
+ * softmold_b200.h -- C ABI of the B200-native SoftMold MD timestep (libsoftmold_b200.so).
+ *
+ * The reference (LaradjiSoftMatter/SoftMold) has no plugin / FFI seam: its hot path is the set of C++ template
+ * objects that `MD.cpp` instantiates and drives once per timestep.  This ABI replaces exactly those seams, one
+ * entry point per reference interface (file:line relative to the reference root is cited on each), so a maintainer
+ * can swap the objects for calls into this library (INTEGRATION.md shows the binding), and our own drop-in `MD`
+ * host driver (softmold_b200/csrc/md_main.cpp) uses nothing else.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++ / torch types; every call returns int (SMD_OK == 0) and never throws;
+ *    smd_last_error(ctx) returns the text of the last failure on that context (smd_last_error(NULL): create errors).
+ *  - the caller owns every host buffer; the library owns all device memory; one context per GPU; calls on one
+ *    context are not thread-safe (same as the reference objects, which borrow raw pointers into Blob).
+ *  - host particle arrays are in the ORIGINAL particle order of the .mpd file: positions [n][3] doubles, types
+ *    [n] int32, velocities / accelerations [n][3] doubles.  (Device storage is cell-sorted; the library permutes.)
+ *  - all arithmetic is IEEE FP64 ("dtype f64"); cell and neighbour membership is bit-exact with the reference.
+ *  - there is NO CPU fallback: every compute entry point fails with SMD_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SOFTMOLD_B200_H
+#define SOFTMOLD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMD_ABI_VERSION 1
+
+enum {
+	SMD_OK = 0,
+	SMD_ERR_ARG = 1,      /* bad argument / call order */
+	SMD_ERR_CUDA = 2,     /* CUDA runtime failure or no usable device */
+	SMD_ERR_CELL = 3,     /* particle outside the box / moved more than one cell per step / cell overflow
+	                         (the reference: `throw 0` at cellOpt.h:541-552, :775-779, system.h:452-469) */
+	SMD_ERR_IO = 4,       /* .mpd / output file problems */
+	SMD_ERR_UNSUPPORTED = 5
+};
+
+/* molecule type ids, identical to the reference enum (include/algorithms/molecules.h:6-40) */
+enum { SMD_MOL_BOND = 6, SMD_MOL_BEND = 7, SMD_MOL_CHAIN = 8, SMD_MOL_BEAD = 9, SMD_MOL_BALL = 19 };
+
+/* energy / force terms.  Bit masks select terms in smd_compute_forces; indices address out_terms[] arrays. */
+enum { SMD_TERM_PAIR = 0, SMD_TERM_CHAIN = 1, SMD_TERM_BOND = 2, SMD_TERM_BEND = 3, SMD_TERM_BEAD = 4,
+       SMD_TERM_BALL = 5, SMD_NTERMS = 8 };
+#define SMD_MASK(term) (1u << (term))
+#define SMD_MASK_LANGEVIN (1u << 16)
+#define SMD_MASK_ALL_MOLECULES (SMD_MASK(SMD_TERM_CHAIN) | SMD_MASK(SMD_TERM_BOND) | SMD_MASK(SMD_TERM_BEND) | \
+                                SMD_MASK(SMD_TERM_BEAD) | SMD_MASK(SMD_TERM_BALL))
+#define SMD_MASK_ALL (SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_ALL_MOLECULES | SMD_MASK_LANGEVIN)
+
+/* Langevin noise source */
+enum {
+	SMD_NOISE_PHILOX = 0,   /* Philox4x32-10 keyed (seed, step, particle): the product default */
+	SMD_NOISE_EXTERNAL = 1  /* uniforms supplied by the host with smd_set_noise (parity runs against the reference's
+	                           MT19937 stream, algorithms/langevin.h:125-130) */
+};
+
+typedef struct smd_ctx smd_ctx;
+
+/* Everything CellOpt / Verlet / Langevin take in their constructors:
+ *   CellOpt::initialize  include/algorithms/cellOpt.h:153-227   (p, a, Fconst, Uconst, nParticles, nTypes, size, wrap, cutoff)
+ *   Verlet ctor          include/algorithms/verlet.h:21-23       (p, a, v, nParticles, size, dt, wrap, aP)
+ *   Langevin::initialize include/algorithms/langevin.h:110-135   (a, v, p, nParticles, gamma, dt, seed)            */
+typedef struct smd_desc {
+	int32_t abi_version;     /* SMD_ABI_VERSION */
+	int32_t n_particles;
+	int32_t n_types;
+	int32_t device;          /* CUDA device ordinal */
+	double box[3];           /* `size` */
+	double cutoff;           /* `cutoff` (rc) */
+	double dt;               /* `deltaT` */
+	double gamma;            /* `gamma` */
+	double temperature;      /* `initialTemp` */
+	uint64_t seed;           /* `seed` */
+	int32_t noise;           /* SMD_NOISE_* */
+	int32_t track_unwrapped; /* keep the unwrapped copy aP used for diffusion (MD.cpp:96-105, verlet.h:318-330) */
+	int32_t rank, nranks;    /* slab decomposition (0,1 for a single GPU) */
+	int32_t reserved[8];
+} smd_desc;
+
+int smd_abi_version(void);
+const char *smd_last_error(const smd_ctx *ctx);
+
+/* number of CUDA devices this process can use; 0 (and SMD_ERR_CUDA from smd_create) when there is none */
+int smd_device_count(void);
+
+int smd_create(const smd_desc *desc, smd_ctx **out);
+int smd_destroy(smd_ctx *ctx);
+
+/* twoBodyFconst / twoBodyUconst, 6*nTypes^2 doubles each, row = type1*nTypes+type2
+ * (Blob::getTwoBodyFconst/Uconst, include/system.h:256-257; layout include/potentials/laradjiRevalee.h:103-108,143-148) */
+int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double *uC);
+
+/* Blob::getPositions / getVelocities (include/system.h:247-249).  vel may be NULL (zeros). Resets the step state. */
+int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t *type, const double *vel);
+
+/* molecule records, in the order of the .mpd file (the bead list of a BEAD molecule depends on that order,
+ * include/system.h:2053-2070).  Constants as in MD.h:58-66:
+ *   CHAIN  c[4] = {r0, kBond, cosTheta0, kBend}, blocks[n][3] = {start, nChains, length}   (system.h:1782-1866)
+ *   BOND   c[2] = {r0, k},           ij[n][2]                                                 (system.h:1880-1934)
+ *   BEND   c[2] = {cosTheta0, k},    ijk[n][3]                                                (system.h:1975-2040)
+ *   BEAD   C[22*nTypes^2],           idx[n]                                                   (system.h:2043-2212)
+ *   BALL   c[2] = {r0, k},           cj[n][2] = {centre, j}                                   (system.h:1936-1971) */
+int smd_add_chain(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[4]);
+int smd_add_bonds(smd_ctx *ctx, int32_t n, const int32_t *ij, const double c[2]);
+int smd_add_bends(smd_ctx *ctx, int32_t n, const int32_t *ijk, const double c[2]);
+int smd_add_beads(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C);
+int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const double c[2]);
+
+/* temperature may be ramped by the driver (MD.cpp:369-371) */
+int smd_set_temperature(smd_ctx *ctx, double temperature);
+
+/* uniforms in [0,1) for the NEXT Langevin evaluation, u[n][3] in original particle order, consumed once
+ * (SMD_NOISE_EXTERNAL only).  Replaces MTRand::rand53 draws of Langevin::compute, algorithms/langevin.h:284-331. */
+int smd_set_noise(smd_ctx *ctx, const double *u);
+
+/* CellOpt::build (cellOpt.h:510-710): bin the current positions into the reference's cell grid and sort. */
+int smd_build_cells(smd_ctx *ctx);
+
+/* a = 0, then accumulate the selected terms on the current configuration:
+ *   SMD_TERM_PAIR   CellOpt::build + computeForce            cellOpt.h:510-926, MD.h:795-848
+ *   SMD_TERM_CHAIN..BALL   Blob::do*Force for every molecule of that kind   system.h:1782-2212
+ *   SMD_MASK_LANGEVIN      Langevin::compute(temperature)     algorithms/langevin.h:232-331
+ * `step` is the MD iteration index (Philox counter).  This is what MD.cpp:186-262 does before its loop. */
+int smd_compute_forces(smd_ctx *ctx, uint32_t term_mask, int64_t step);
+
+/* Finish an interrupted half kick after loading a checkpoint with initialTime != 0 (MD.cpp:274-308):
+ * bead mass division + Verlet::second. */
+int smd_resume(smd_ctx *ctx);
+
+/* nsteps iterations i = first_step .. first_step+nsteps-1 of the loop MD.cpp:335-511 without store / measure /
+ * box moves: bead mass division, Verlet::first, a=0, Langevin, build, pair + molecule forces, bead mass division,
+ * Verlet::second.  Asynchronous: returns after enqueueing; any later call that reads results synchronises. */
+int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps);
+
+/* the two halves of one iteration, for drivers that store a checkpoint in the middle (MD.cpp:373-381) */
+int smd_step_begin(smd_ctx *ctx, int64_t step);   /* bead mass division, Verlet::first, a = 0   (MD.cpp:340-366) */
+int smd_step_end(smd_ctx *ctx, int64_t step);     /* Langevin ... Verlet::second                (MD.cpp:410-511) */
+
+/* CellOpt::computePotential (cellOpt.h:928-1041) + Blob::do*Potential (system.h:2487-3167) as summed by
+ * dataExtraction::compute (dataExtraction.h:839-990).  out_terms[SMD_NTERMS], indexed by SMD_TERM_*. */
+int smd_potential(smd_ctx *ctx, double *out_terms);
+
+/* Kinetic::compute, include/algorithms/dataCollection.h:666-674 */
+int smd_kinetic(smd_ctx *ctx, double *out);
+
+/* CellOpt::computeDPotential (cellOpt.h:1043-1180) + Blob::do*DPotential (system.h:3280-3757) for the proposed
+ * component-wise scaling of the box (MD.cpp:608-675).  out_terms[SMD_NTERMS]. */
+int smd_dpotential(smd_ctx *ctx, const double scale[3], double *out_terms);
+
+/* accepted box move: p *= scale, CellOpt::resize / Verlet::resize / setSize (MD.cpp:697-712, cellOpt.h:1525-1570) */
+int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3]);
+
+/* One Metropolis box-move trial exactly as MD.cpp:589-721 given the two rand53 draws the reference takes from
+ * MTRand randNum(seed): u_fluct (:595) and u_accept (:688).  Returns accepted (0/1), the total dPotential incl.
+ * tension*dA, and the box after the trial. */
+int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, double u_fluct, double u_accept,
+                    int32_t *accepted, double *dU_total, double box_out[3]);
+
+/* read back (original particle order).  Any pointer may be NULL. */
+int smd_get_particles(smd_ctx *ctx, double *xyz, int32_t *type, double *vel);
+int smd_get_forces(smd_ctx *ctx, double *acc);
+int smd_get_unwrapped(smd_ctx *ctx, double *xyz);
+int smd_get_box(smd_ctx *ctx, double box[3]);
+
+/* cell membership as the reference computes it (cellOpt.h:530-556): key of every particle, and the particles of
+ * every occupied cell in the reference's list order (descending particle index, cellOpt.h:572-585).
+ * n_cells_xyz[3] = nCells.  cell_key / cell_rank are [n]: rank = position of the particle in its cell's list. */
+int smd_get_cell_ids(smd_ctx *ctx, int32_t n_cells_xyz[3], int32_t *cell_key, int32_t *cell_rank);
+
+/* number of in-range pairs (r^2 < rc^2), and per-particle neighbour counts [n] (may be NULL) */
+int smd_count_pairs(smd_ctx *ctx, int64_t *total, int32_t *per_particle);
+
+/* wait for all enqueued work; reports deferred device-side errors (SMD_ERR_CELL) */
+int smd_synchronize(smd_ctx *ctx);
+
+/* device pointers of the resident state for zero-copy interop (torch / NCCL plumbing): sorted order!
+ *   which: 0 positions {x,y,z,type-bits}[n] (32 B records), 1 velocities SoA [3][cap], 2 accelerations SoA [3][cap],
+ *          3 original index of each slot int32[n] */
+int smd_device_ptr(smd_ctx *ctx, int32_t which, void **ptr, size_t *bytes);
+
+/* CUDA stream (cudaStream_t) all work of this context is enqueued on, for event timing by the caller */
+int smd_stream(smd_ctx *ctx, void **stream);
+
+/* counters: kernels launched since creation, cell rebuilds */
+int smd_stats(smd_ctx *ctx, int64_t *kernel_launches, int64_t *rebuilds);
+
+/* ------------------------------------------------------------------ host-side file boundary (no GPU needed)
+ * `.mpd` reader / writer with the semantics of Script<T,Blob>::read/write + Blob::input/output
+ * (include/fileFormats/scriptFormat.h:64-95, include/system.h:589-1749). */
+typedef struct smd_mpd smd_mpd;
+
+int smd_mpd_read(const char *name_without_ext, smd_mpd **out, char *err, size_t errlen);
+int smd_mpd_write(const smd_mpd *m, const char *name_without_ext, char *err, size_t errlen);
+void smd_mpd_free(smd_mpd *m);
+
+/* scalar commands by their .mpd name ("gamma", "initialTemp", "seed", "nTypes", "deltaLXY", "tension", ...);
+ * present = 0 when the command was not in the file (then *value is the reference default) */
+int smd_mpd_get_scalar(const smd_mpd *m, const char *command, double *value, int32_t *present);
+int smd_mpd_set_scalar(smd_mpd *m, const char *command, double value);
+int smd_mpd_get_size(const smd_mpd *m, double size[3]);
+int smd_mpd_set_size(smd_mpd *m, const double size[3]);
+/* borrowed pointers into the object, valid until smd_mpd_free: xyz [n][3], type [n], vel [n][3] */
+int smd_mpd_particles(smd_mpd *m, int32_t *n, double **xyz, int32_t **type, double **vel);
+int smd_mpd_pair_tables(smd_mpd *m, int32_t *n_types, double **fC, double **uC);
+int smd_mpd_n_molecules(const smd_mpd *m);
+/* molecule k: type, number of bond records, ints per record, borrowed pointers to records and constants */
+int smd_mpd_molecule(smd_mpd *m, int32_t k, int32_t *type, int32_t *n_records, int32_t *record_width,
+                     int32_t **records, int32_t *n_constants, double **constants);
+
+/* convenience: create a context from a parsed file (tables, particles, molecules all set) */
+int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, int32_t track_unwrapped, smd_ctx **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,385 @@
+"""ctypes binding of libsoftmold_b200.so (C ABI: include/softmold_b200.h).
+
+This is plumbing for tests and bench.py; the product is the shared library and the `MD_b200` host driver.  There is
+no CPU fallback anywhere: if the library is missing this module raises at import of the symbols, and every compute
+call raises SoftMoldError when no B200-class device is usable."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsoftmold_b200.so")
+
+SMD_OK, SMD_ERR_ARG, SMD_ERR_CUDA, SMD_ERR_CELL, SMD_ERR_IO, SMD_ERR_UNSUPPORTED = range(6)
+MOL_BOND, MOL_BEND, MOL_CHAIN, MOL_BEAD, MOL_BALL = 6, 7, 8, 9, 19
+TERM_PAIR, TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL, NTERMS = 0, 1, 2, 3, 4, 5, 8
+MASK_LANGEVIN = 1 << 16
+MASK_ALL_MOLECULES = sum(1 << t for t in (TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL))
+MASK_ALL = (1 << TERM_PAIR) | MASK_ALL_MOLECULES | MASK_LANGEVIN
+NOISE_PHILOX, NOISE_EXTERNAL = 0, 1
+ABI_VERSION = 1
+
+# every symbol include/softmold_b200.h declares
+SYMBOLS = [
+    "smd_abi_version", "smd_last_error", "smd_device_count", "smd_create", "smd_destroy", "smd_set_pair_tables",
+    "smd_set_particles", "smd_add_chain", "smd_add_bonds", "smd_add_bends", "smd_add_beads", "smd_add_ball",
+    "smd_set_temperature", "smd_set_noise", "smd_build_cells", "smd_compute_forces", "smd_resume", "smd_step",
+    "smd_step_begin", "smd_step_end", "smd_potential", "smd_kinetic", "smd_dpotential", "smd_rescale",
+    "smd_mc_box_move", "smd_get_particles", "smd_get_forces", "smd_get_unwrapped", "smd_get_box", "smd_get_cell_ids",
+    "smd_count_pairs", "smd_synchronize", "smd_device_ptr", "smd_stream", "smd_stats", "smd_mpd_read", "smd_mpd_write",
+    "smd_mpd_free", "smd_mpd_get_scalar", "smd_mpd_set_scalar", "smd_mpd_get_size", "smd_mpd_set_size",
+    "smd_mpd_particles", "smd_mpd_pair_tables", "smd_mpd_n_molecules", "smd_mpd_molecule", "smd_create_from_mpd",
+]
+
+
+class SoftMoldError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"softmold_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Desc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_particles", C.c_int32), ("n_types", C.c_int32), ("device", C.c_int32),
+                ("box", C.c_double * 3), ("cutoff", C.c_double), ("dt", C.c_double), ("gamma", C.c_double),
+                ("temperature", C.c_double), ("seed", C.c_uint64), ("noise", C.c_int32), ("track_unwrapped", C.c_int32),
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved", C.c_int32 * 8)]
+
+
+_lib = None
+
+
+def lib():
+    """load the shared library; raises (loudly) when it has not been built"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(softmold_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for s in SYMBOLS:
+            getattr(L, s)
+        L.smd_last_error.restype = C.c_char_p
+        L.smd_last_error.argtypes = [C.c_void_p]
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.smd_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
+        L.smd_destroy.argtypes = [vp]
+        L.smd_set_pair_tables.argtypes = [vp, vp, vp]
+        L.smd_set_particles.argtypes = [vp, vp, vp, vp]
+        L.smd_add_chain.argtypes = [vp, i32, vp, vp]
+        L.smd_add_bonds.argtypes = [vp, i32, vp, vp]
+        L.smd_add_bends.argtypes = [vp, i32, vp, vp]
+        L.smd_add_beads.argtypes = [vp, i32, vp, vp]
+        L.smd_add_ball.argtypes = [vp, i32, vp, vp]
+        L.smd_set_temperature.argtypes = [vp, dbl]
+        L.smd_set_noise.argtypes = [vp, vp]
+        L.smd_build_cells.argtypes = [vp]
+        L.smd_compute_forces.argtypes = [vp, C.c_uint32, i64]
+        L.smd_resume.argtypes = [vp]
+        L.smd_step.argtypes = [vp, i64, i32]
+        L.smd_step_begin.argtypes = [vp, i64]
+        L.smd_step_end.argtypes = [vp, i64]
+        L.smd_potential.argtypes = [vp, vp]
+        L.smd_kinetic.argtypes = [vp, dp]
+        L.smd_dpotential.argtypes = [vp, vp, vp]
+        L.smd_rescale.argtypes = [vp, vp, vp]
+        L.smd_mc_box_move.argtypes = [vp, dbl, dbl, dbl, dbl, ip, dp, vp]
+        L.smd_get_particles.argtypes = [vp, vp, vp, vp]
+        L.smd_get_forces.argtypes = [vp, vp]
+        L.smd_get_unwrapped.argtypes = [vp, vp]
+        L.smd_get_box.argtypes = [vp, vp]
+        L.smd_get_cell_ids.argtypes = [vp, vp, vp, vp]
+        L.smd_count_pairs.argtypes = [vp, C.POINTER(i64), vp]
+        L.smd_synchronize.argtypes = [vp]
+        L.smd_device_ptr.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.smd_stream.argtypes = [vp, C.POINTER(vp)]
+        L.smd_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+        L.smd_mpd_read.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_size_t]
+        L.smd_mpd_write.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.smd_mpd_free.argtypes = [vp]
+        L.smd_mpd_free.restype = None
+        L.smd_mpd_get_scalar.argtypes = [vp, C.c_char_p, dp, ip]
+        L.smd_mpd_set_scalar.argtypes = [vp, C.c_char_p, dbl]
+        L.smd_mpd_get_size.argtypes = [vp, vp]
+        L.smd_mpd_set_size.argtypes = [vp, vp]
+        L.smd_mpd_particles.argtypes = [vp, ip, C.POINTER(dp), C.POINTER(ip), C.POINTER(dp)]
+        L.smd_mpd_pair_tables.argtypes = [vp, ip, C.POINTER(dp), C.POINTER(dp)]
+        L.smd_mpd_n_molecules.argtypes = [vp]
+        L.smd_mpd_molecule.argtypes = [vp, i32, ip, ip, ip, C.POINTER(ip), ip, C.POINTER(dp)]
+        L.smd_create_from_mpd.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+        _lib = L
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One simulation resident on one GPU.  Method names follow the C ABI (smd_*), whose entry points in turn replace
+    the reference's CellOpt / Verlet / Langevin / Blob::do* seams (see include/softmold_b200.h)."""
+
+    def __init__(self, n_particles, n_types, box, cutoff, dt, gamma, temperature, seed, device=0,
+                 noise=NOISE_PHILOX, track_unwrapped=False, _handle=None):
+        self.L = lib()
+        self.n = int(n_particles)
+        self.n_types = int(n_types)
+        if _handle is not None:
+            self.h = _handle
+            return
+        d = Desc()
+        d.abi_version = ABI_VERSION
+        d.n_particles, d.n_types, d.device = self.n, self.n_types, device
+        d.box = (C.c_double * 3)(*[float(x) for x in box])
+        d.cutoff, d.dt, d.gamma, d.temperature = float(cutoff), float(dt), float(gamma), float(temperature)
+        d.seed, d.noise, d.track_unwrapped = int(seed), int(noise), int(bool(track_unwrapped))
+        d.rank, d.nranks = 0, 1
+        h = C.c_void_p()
+        rc = self.L.smd_create(C.byref(d), C.byref(h))
+        if rc:
+            raise SoftMoldError(rc, self.L.smd_last_error(None).decode())
+        self.h = h
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.smd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise SoftMoldError(rc, self.L.smd_last_error(self.h).decode())
+
+    @classmethod
+    def from_dict(cls, m, device=0, noise=NOISE_PHILOX, track_unwrapped=False):
+        """m: dict with the .mpd fields (as oracle.orc.read_mpd / load_golden produce them)"""
+        ctx = cls(m["nParticles"], m["nTypes"], m["size"], m["cutoff"], m["deltaT"], m["gamma"], m["initialTemp"],
+                  m["seed"], device=device, noise=noise, track_unwrapped=track_unwrapped)
+        ctx.set_pair_tables(m["twoBodyFconst"], m["twoBodyUconst"])
+        ctx.set_particles(m["xyz"], m["type"], m["vel"])
+        for mol in m["molecules"]:
+            ctx.add_molecule(mol["type"], mol["bonds"], mol["constants"])
+        return ctx
+
+    # -- setup
+    def set_pair_tables(self, fC, uC):
+        fC, uC = _f64(fC), _f64(uC)
+        assert fC.size == 6 * self.n_types ** 2 and uC.size == fC.size
+        self._ck(self.L.smd_set_pair_tables(self.h, _ptr(fC), _ptr(uC)))
+
+    def set_particles(self, xyz, typ, vel=None):
+        xyz, typ = _f64(xyz), _i32(typ)
+        assert xyz.shape == (self.n, 3) and typ.shape == (self.n,)
+        vel = None if vel is None else _f64(vel)
+        self._ck(self.L.smd_set_particles(self.h, _ptr(xyz), _ptr(typ), _ptr(vel)))
+
+    def add_molecule(self, mtype, records, constants):
+        r, c = _i32(records), _f64(constants)
+        n = len(r)
+        f = {MOL_CHAIN: self.L.smd_add_chain, MOL_BOND: self.L.smd_add_bonds, MOL_BEND: self.L.smd_add_bends,
+             MOL_BEAD: self.L.smd_add_beads, MOL_BALL: self.L.smd_add_ball}.get(int(mtype))
+        if f is None:
+            raise SoftMoldError(SMD_ERR_UNSUPPORTED, f"molecule type {mtype} is outside the hot path")
+        self._ck(f(self.h, n, _ptr(r), _ptr(c)))
+
+    def set_temperature(self, T):
+        self._ck(self.L.smd_set_temperature(self.h, float(T)))
+
+    def set_noise(self, u):
+        u = _f64(u)
+        assert u.shape == (self.n, 3)
+        self._ck(self.L.smd_set_noise(self.h, _ptr(u)))
+
+    # -- compute
+    def build_cells(self):
+        self._ck(self.L.smd_build_cells(self.h))
+
+    def compute_forces(self, mask=MASK_ALL, step=0):
+        self._ck(self.L.smd_compute_forces(self.h, mask, step))
+
+    def resume(self):
+        self._ck(self.L.smd_resume(self.h))
+
+    def step(self, first_step, nsteps=1):
+        self._ck(self.L.smd_step(self.h, first_step, nsteps))
+
+    def step_begin(self, step):
+        self._ck(self.L.smd_step_begin(self.h, step))
+
+    def step_end(self, step):
+        self._ck(self.L.smd_step_end(self.h, step))
+
+    def potential(self):
+        out = np.zeros(NTERMS)
+        self._ck(self.L.smd_potential(self.h, _ptr(out)))
+        return out
+
+    def kinetic(self):
+        v = C.c_double()
+        self._ck(self.L.smd_kinetic(self.h, C.byref(v)))
+        return v.value
+
+    def dpotential(self, scale):
+        out, s = np.zeros(NTERMS), _f64(scale)
+        self._ck(self.L.smd_dpotential(self.h, _ptr(s), _ptr(out)))
+        return out
+
+    def rescale(self, scale, new_box):
+        s, b = _f64(scale), _f64(new_box)
+        self._ck(self.L.smd_rescale(self.h, _ptr(s), _ptr(b)))
+
+    def mc_box_move(self, deltaLXY, tension, u_fluct, u_accept):
+        acc, dU, box = C.c_int32(), C.c_double(), np.zeros(3)
+        self._ck(self.L.smd_mc_box_move(self.h, deltaLXY, tension, u_fluct, u_accept, C.byref(acc), C.byref(dU), _ptr(box)))
+        return bool(acc.value), dU.value, box
+
+    # -- read back
+    def get_particles(self):
+        xyz, typ, vel = np.zeros((self.n, 3)), np.zeros(self.n, np.int32), np.zeros((self.n, 3))
+        self._ck(self.L.smd_get_particles(self.h, _ptr(xyz), _ptr(typ), _ptr(vel)))
+        return xyz, typ, vel
+
+    def get_forces(self):
+        a = np.zeros((self.n, 3))
+        self._ck(self.L.smd_get_forces(self.h, _ptr(a)))
+        return a
+
+    def get_unwrapped(self):
+        a = np.zeros((self.n, 3))
+        self._ck(self.L.smd_get_unwrapped(self.h, _ptr(a)))
+        return a
+
+    def get_box(self):
+        b = np.zeros(3)
+        self._ck(self.L.smd_get_box(self.h, _ptr(b)))
+        return b
+
+    def get_cell_ids(self):
+        nc, key, rank = np.zeros(3, np.int32), np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        self._ck(self.L.smd_get_cell_ids(self.h, _ptr(nc), _ptr(key), _ptr(rank)))
+        return nc, key, rank
+
+    def count_pairs(self, per_particle=True):
+        tot = C.c_int64()
+        per = np.zeros(self.n, np.int32) if per_particle else None
+        self._ck(self.L.smd_count_pairs(self.h, C.byref(tot), _ptr(per)))
+        return tot.value, per
+
+    def synchronize(self):
+        self._ck(self.L.smd_synchronize(self.h))
+
+    def stream(self):
+        s = C.c_void_p()
+        self._ck(self.L.smd_stream(self.h, C.byref(s)))
+        return s.value
+
+    def stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.L.smd_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class Mpd:
+    """`.mpd` file object (host side, no GPU needed): smd_mpd_* of the C ABI."""
+
+    SCALARS = ["gamma", "initialTemp", "finalTemp", "seed", "nTypes", "nMolecules", "nParticles", "periodic", "cutoff",
+               "initialTime", "finalTime", "deltaT", "storeInterval", "measureInterval", "deltaLXY", "removeSolvent",
+               "tempStepInterval", "tension"]
+
+    def __init__(self, name):
+        self.L = lib()
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = self.L.smd_mpd_read(os.fsencode(name), C.byref(h), err, len(err))
+        if rc:
+            raise SoftMoldError(rc, err.value.decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.smd_mpd_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def write(self, name):
+        err = C.create_string_buffer(1024)
+        rc = self.L.smd_mpd_write(self.h, os.fsencode(name), err, len(err))
+        if rc:
+            raise SoftMoldError(rc, err.value.decode())
+
+    def scalar(self, cmd):
+        v, p = C.c_double(), C.c_int32()
+        if self.L.smd_mpd_get_scalar(self.h, cmd.encode(), C.byref(v), C.byref(p)):
+            raise KeyError(cmd)
+        return v.value, bool(p.value)
+
+    def set_scalar(self, cmd, value):
+        if self.L.smd_mpd_set_scalar(self.h, cmd.encode(), float(value)):
+            raise KeyError(cmd)
+
+    def size(self):
+        s = np.zeros(3)
+        self.L.smd_mpd_get_size(self.h, _ptr(s))
+        return s
+
+    def to_dict(self):
+        """same shape as oracle.orc.read_mpd (copies)"""
+        m = {"molecules": []}
+        for k in self.SCALARS:
+            v, present = self.scalar(k)
+            if present:
+                m[k] = int(v) if k in ("seed", "nTypes", "nMolecules", "nParticles", "periodic") else v
+        m["size"] = list(self.size())
+        n = C.c_int32()
+        xyz, typ, vel = C.POINTER(C.c_double)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_double)()
+        self.L.smd_mpd_particles(self.h, C.byref(n), C.byref(xyz), C.byref(typ), C.byref(vel))
+        n = n.value
+        m["xyz"] = np.ctypeslib.as_array(xyz, (n, 3)).copy() if n else np.zeros((0, 3))
+        m["type"] = np.ctypeslib.as_array(typ, (n,)).copy() if n else np.zeros(0, np.int32)
+        m["vel"] = np.ctypeslib.as_array(vel, (n, 3)).copy() if n else np.zeros((0, 3))
+        nT = C.c_int32()
+        fC, uC = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+        self.L.smd_mpd_pair_tables(self.h, C.byref(nT), C.byref(fC), C.byref(uC))
+        if fC:
+            m["twoBodyFconst"] = np.ctypeslib.as_array(fC, (6 * nT.value ** 2,)).copy()
+            m["twoBodyUconst"] = np.ctypeslib.as_array(uC, (6 * nT.value ** 2,)).copy()
+        for k in range(self.L.smd_mpd_n_molecules(self.h)):
+            t, nr, w, nc = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            rec, cst = C.POINTER(C.c_int32)(), C.POINTER(C.c_double)()
+            self.L.smd_mpd_molecule(self.h, k, C.byref(t), C.byref(nr), C.byref(w), C.byref(rec), C.byref(nc), C.byref(cst))
+            r = np.ctypeslib.as_array(rec, (nr.value, w.value)).copy() if nr.value else np.zeros((0, w.value), np.int32)
+            c = np.ctypeslib.as_array(cst, (nc.value,)).copy() if nc.value else np.zeros(0)
+            m["molecules"].append({"type": t.value, "bonds": r, "constants": c})
+        return m
+
+    def create_context(self, device=0, noise=NOISE_PHILOX, track_unwrapped=False):
+        h = C.c_void_p()
+        rc = self.L.smd_create_from_mpd(self.h, device, noise, int(bool(track_unwrapped)), C.byref(h))
+        if rc:
+            msg = self.L.smd_last_error(h if h else None).decode()
+            if h:
+                self.L.smd_destroy(h)
+            raise SoftMoldError(rc, msg)
+        n, _ = self.scalar("nParticles")
+        nT, _ = self.scalar("nTypes")
+        return Context(int(n), int(nT), None, None, None, None, None, None, _handle=h)

@@ -1,0 +1,842 @@
+// libsoftmold_b200.so -- C ABI implementation (include/softmold_b200.h) on top of the sm_100a kernels.
+// Host-side orchestration only; there is no CPU compute path: without a usable CUDA device every compute entry
+// point returns SMD_ERR_CUDA.
+#include <cmath>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include "smd_kernels.cuh"
+
+using namespace smd;
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                          \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) {                                                                          \
+			ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+			return SMD_ERR_CUDA;                                                                          \
+		}                                                                                                 \
+	} while (0)
+
+#define REQUIRE(cond, msg)                                                                                \
+	do {                                                                                                  \
+		if (!(cond)) { ctx->err = (msg); return SMD_ERR_ARG; }                                            \
+	} while (0)
+
+static inline int nblk(long long n, int tpb) { return (int)std::max<long long>(1, (n + tpb - 1) / tpb); }
+
+#define LAUNCH(kernel, grid, block, smem, ...)                                                            \
+	do {                                                                                                  \
+		kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                                    \
+		ctx->launches++;                                                                                  \
+	} while (0)
+
+static const int MAX_PARTIALS = 1 << 20;
+
+extern "C" int smd_abi_version(void) { return SMD_ABI_VERSION; }
+
+extern "C" const char *smd_last_error(const smd_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int smd_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+static void set_geom(smd_ctx *ctx, const double box[3])
+{
+	Geom &g = ctx->geom;
+	for (int d = 0; d < 3; d++) {
+		g.box[d] = box[d];
+		g.nc[d] = (int)(box[d] / ctx->desc.cutoff);   // cellOpt.h:194-196 / :1529-1531
+		g.cs[d] = box[d] / g.nc[d];                   // cellOpt.h:207-209 / :1560-1562
+	}
+	g.rc2 = ctx->desc.cutoff * ctx->desc.cutoff;
+}
+
+static int check_geom(smd_ctx *ctx)
+{
+	const Geom &g = ctx->geom;
+	for (int d = 0; d < 3; d++) {
+		if (g.nc[d] < 3) {
+			ctx->err = "box shorter than 3 cells along an axis: the reference's half stencil double-counts there; unsupported";
+			return SMD_ERR_UNSUPPORTED;
+		}
+	}
+	if (g.nc[0] > 2048 || g.nc[1] > 2048 || g.nc[2] > 1024) {
+		ctx->err = "cell grid exceeds 2048 x 2048 x 1024 cells";
+		return SMD_ERR_UNSUPPORTED;
+	}
+	return SMD_OK;
+}
+
+extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
+{
+	if (!desc || !out) { g_create_error = "null argument"; return SMD_ERR_ARG; }
+	if (desc->abi_version != SMD_ABI_VERSION) { g_create_error = "ABI version mismatch"; return SMD_ERR_ARG; }
+	if (desc->n_particles < 0 || desc->n_types <= 0 || desc->cutoff <= 0 || desc->dt <= 0) {
+		g_create_error = "invalid descriptor (n_particles, n_types, cutoff, dt)";
+		return SMD_ERR_ARG;
+	}
+	int ndev = smd_device_count();
+	if (ndev <= 0 || desc->device < 0 || desc->device >= ndev) {
+		g_create_error = "no usable CUDA device (this library has no CPU fallback)";
+		return SMD_ERR_CUDA;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, desc->device) != cudaSuccess || prop.major < 10) {
+		g_create_error = "device is not sm_100 class";
+		return SMD_ERR_CUDA;
+	}
+	smd_ctx *ctx = new smd_ctx();
+	ctx->desc = *desc;
+	ctx->N = desc->n_particles;
+	ctx->nT = desc->n_types;
+	ctx->cap = ((std::max(ctx->N, 1) + 255) / 256) * 256;
+	ctx->temperature = desc->temperature;
+	ctx->device = desc->device;
+	ctx->cur = 0; ctx->wdata = 0; ctx->wnext = 0;
+	ctx->cells_valid = false;
+	ctx->tables_set = ctx->particles_set = false;
+	ctx->noise_ready = false;
+	ctx->acc_live = false;
+	ctx->n_molecules = 0;
+	ctx->launches = ctx->rebuilds = 0;
+	set_geom(ctx, desc->box);
+	int rc = check_geom(ctx);
+	if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
+
+#define CKC(call)                                                                                         \
+	do {                                                                                                  \
+		cudaError_t e_ = (call);                                                                          \
+		if (e_ != cudaSuccess) {                                                                          \
+			g_create_error = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+			delete ctx;                                                                                   \
+			return SMD_ERR_CUDA;                                                                          \
+		}                                                                                                 \
+	} while (0)
+	CKC(cudaSetDevice(ctx->device));
+	CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	size_t cap = ctx->cap;
+	for (int b = 0; b < 2; b++) {
+		CKC(cudaMalloc(&ctx->pos[b], cap * sizeof(Particle)));
+		CKC(cudaMalloc(&ctx->vel[b], 3 * cap * sizeof(double)));
+		CKC(cudaMalloc(&ctx->gid[b], cap * sizeof(int)));
+		ctx->unw[b] = nullptr;
+		if (desc->track_unwrapped) CKC(cudaMalloc(&ctx->unw[b], 3 * cap * sizeof(double)));
+		CKC(cudaMalloc(&ctx->win[b], WIN_WORDS * sizeof(int)));
+		CKC(cudaMemset(ctx->win[b], 0, WIN_WORDS * sizeof(int)));
+	}
+	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
+	CKC(cudaMemset(ctx->acc, 0, 3 * cap * sizeof(double)));
+	CKC(cudaMalloc(&ctx->acc2, 3 * cap * sizeof(double)));
+	CKC(cudaMalloc(&ctx->slot_of, cap * sizeof(int)));
+	// dense offset table over the occupied window of the reference grid; capacity = whole grid up to 64 Mi cells
+	long long total = (long long)ctx->geom.nc[0] * ctx->geom.nc[1] * ctx->geom.nc[2];
+	ctx->cellcap = std::min<long long>(std::max<long long>(2 * total, 1 << 16), 64ll << 20);
+	CKC(cudaMalloc(&ctx->count, (ctx->cellcap + 1) * sizeof(int)));
+	CKC(cudaMemset(ctx->count, 0, (ctx->cellcap + 1) * sizeof(int)));
+	CKC(cudaMalloc(&ctx->start, (ctx->cellcap + 1) * sizeof(int)));
+	CKC(cudaMalloc(&ctx->cursor, (ctx->cellcap + 1) * sizeof(int)));
+	CKC(cudaMalloc(&ctx->blockSums, SCAN_BLOCKS * sizeof(int)));
+	CKC(cudaMalloc(&ctx->cellOfSlot, cap * sizeof(int)));
+	CKC(cudaMalloc(&ctx->order, cap * sizeof(int)));
+	CKC(cudaMalloc(&ctx->bbox, 6 * sizeof(int)));
+	int bb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+	CKC(cudaMemcpy(ctx->bbox, bb, sizeof bb, cudaMemcpyHostToDevice));
+	CKC(cudaMalloc(&ctx->errflag, sizeof(int)));
+	CKC(cudaMemset(ctx->errflag, 0, sizeof(int)));
+	CKC(cudaMalloc(&ctx->fC, 6 * ctx->nT * ctx->nT * sizeof(double)));
+	CKC(cudaMalloc(&ctx->uC, 6 * ctx->nT * ctx->nT * sizeof(double)));
+	CKC(cudaMalloc(&ctx->noise, 3 * cap * sizeof(double)));
+	CKC(cudaMalloc(&ctx->partials, MAX_PARTIALS * sizeof(double)));
+	CKC(cudaMalloc(&ctx->scalars, 64 * sizeof(double)));
+	CKC(cudaMalloc(&ctx->icount, cap * sizeof(int)));
+	CKC(cudaMalloc(&ctx->stage, 3 * cap * sizeof(double) * 2));
+	CKC(cudaMalloc(&ctx->istage, 2 * cap * sizeof(int)));
+	CKC(cudaMallocHost(&ctx->h_pinned, 64 * sizeof(double)));
+#undef CKC
+	if (6 * ctx->nT * ctx->nT * sizeof(double) > 40000) {
+		g_create_error = "too many particle types for the shared-memory pair table";
+		smd_destroy(ctx);
+		return SMD_ERR_UNSUPPORTED;
+	}
+	*out = ctx;
+	return SMD_OK;
+}
+
+extern "C" int smd_destroy(smd_ctx *ctx)
+{
+	if (!ctx) return SMD_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (int b = 0; b < 2; b++) {
+		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]); cudaFree(ctx->win[b]);
+	}
+	cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
+	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
+	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
+	cudaFree(ctx->icount); cudaFree(ctx->stage); cudaFree(ctx->istage);
+	cudaFreeHost(ctx->h_pinned);
+	for (auto &b : ctx->bonds) cudaFree(b.d_ij);
+	for (auto &b : ctx->bends) cudaFree(b.d_ijk);
+	for (auto &b : ctx->balls) cudaFree(b.d_cj);
+	for (auto &b : ctx->beads) { cudaFree(b.d_beads); cudaFree(b.d_C); }
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return SMD_OK;
+}
+
+static int check_device_errors(smd_ctx *ctx)
+{
+	int flag = 0;
+	CK(cudaMemcpyAsync(&flag, ctx->errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaGetLastError());
+	if (flag) {
+		ctx->err = "device-side cell error:";
+		if (flag & ERR_OUT_OF_BOX) ctx->err += " particle outside the box or NaN position (reference: 'cell placement is on boundary', cellOpt.h:541-552)";
+		if (flag & ERR_WINDOW) ctx->err += " particle moved more than one cell in a step";
+		if (flag & ERR_WINDOW_CAP) ctx->err += " occupied cell window exceeds the offset-table capacity";
+		return SMD_ERR_CELL;
+	}
+	return SMD_OK;
+}
+
+extern "C" int smd_synchronize(smd_ctx *ctx)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	return check_device_errors(ctx);
+}
+
+extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double *uC)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(fC && uC, "null table");
+	CK(cudaSetDevice(ctx->device));
+	size_t bytes = 6 * (size_t)ctx->nT * ctx->nT * sizeof(double);
+	CK(cudaMemcpyAsync(ctx->fC, fC, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->uC, uC, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->tables_set = true;
+	return SMD_OK;
+}
+
+// recompute the occupied-cell window from scratch (after set_particles or a box move)
+static int refresh_window(smd_ctx *ctx)
+{
+	LAUNCH(k_bbox, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], ctx->geom, ctx->bbox, ctx->errflag);
+	LAUNCH(k_window_init, 1, 1, 0, ctx->bbox, ctx->win[ctx->wnext], ctx->geom, ctx->cellcap, ctx->errflag);
+	ctx->cells_valid = false;
+	return SMD_OK;
+}
+
+extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t *type, const double *vel)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(xyz && type, "null positions / types");
+	CK(cudaSetDevice(ctx->device));
+	int N = ctx->N;
+	// the reference refuses out-of-box particles at load (system.h:452-469)
+	for (int i = 0; i < N; i++)
+		for (int d = 0; d < 3; d++) {
+			double x = xyz[3 * i + d];
+			if (!(x >= 0 && x <= ctx->geom.box[d])) {
+				char buf[128];
+				snprintf(buf, sizeof buf, "%c position of particle %d is out of bounds.", "XYZ"[d], i);
+				ctx->err = buf;
+				return SMD_ERR_CELL;
+			}
+		}
+	for (int i = 0; i < N; i++)
+		if (type[i] < 0 || type[i] >= ctx->nT) { ctx->err = "particle type out of range"; return SMD_ERR_ARG; }
+	double *sx = ctx->stage, *sv = ctx->stage + 3 * (size_t)ctx->cap;
+	CK(cudaMemcpyAsync(sx, xyz, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->istage, type, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+	if (vel) CK(cudaMemcpyAsync(sv, vel, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->cur = 0;
+	LAUNCH(k_import_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, sx, ctx->istage, vel ? sv : nullptr, ctx->pos[0], ctx->vel[0],
+	       ctx->unw[0], ctx->gid[0], ctx->slot_of);
+	CK(cudaMemsetAsync(ctx->acc, 0, 3 * (size_t)ctx->cap * sizeof(double), ctx->stream));
+	ctx->acc_live = false;
+	refresh_window(ctx);
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->particles_set = true;
+	ctx->noise_ready = false;
+	return SMD_OK;
+}
+
+static int check_index(smd_ctx *ctx, const int32_t *v, size_t n, const char *what)
+{
+	for (size_t i = 0; i < n; i++)
+		if (v[i] < 0 || v[i] >= ctx->N) {
+			ctx->err = std::string(what) + " index out of bounds";   // Blob::errorChecking, system.h:483-545
+			return SMD_ERR_ARG;
+		}
+	return SMD_OK;
+}
+
+extern "C" int smd_add_chain(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[4])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n_blocks >= 0 && (blocks || n_blocks == 0) && c, "bad CHAIN arguments");
+	for (int j = 0; j < n_blocks; j++) {
+		ChainBlock cb;
+		cb.start = blocks[3 * j]; cb.nChains = blocks[3 * j + 1]; cb.len = blocks[3 * j + 2];
+		long long end = (long long)cb.start + (long long)cb.nChains * cb.len;
+		REQUIRE(cb.start >= 0 && cb.nChains >= 0 && end <= ctx->N, "CHAIN Molecule is out of bounds!");
+		REQUIRE(cb.len >= 3, "CHAIN length below 3 is undefined in the reference (system.h:1834-1836)");
+		for (int k = 0; k < 4; k++) cb.c[k] = c[k];
+		ctx->chains.push_back(cb);
+	}
+	ctx->n_molecules++;
+	return SMD_OK;
+}
+
+template <class L>
+static int upload_list(smd_ctx *ctx, const int32_t *v, size_t n, int **dptr)
+{
+	*dptr = nullptr;
+	if (n == 0) return SMD_OK;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMalloc(dptr, n * sizeof(int)));
+	CK(cudaMemcpy(*dptr, v, n * sizeof(int), cudaMemcpyHostToDevice));
+	return SMD_OK;
+}
+
+extern "C" int smd_add_bonds(smd_ctx *ctx, int32_t n, const int32_t *ij, const double c[2])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (ij || n == 0) && c, "bad BOND arguments");
+	int rc = check_index(ctx, ij, 2 * (size_t)n, "BOND Molecule");
+	if (rc) return rc;
+	BondList b;
+	b.n = n; b.c[0] = c[0]; b.c[1] = c[1];
+	rc = upload_list<int>(ctx, ij, 2 * (size_t)n, &b.d_ij);
+	if (rc) return rc;
+	ctx->bonds.push_back(b);
+	ctx->n_molecules++;
+	return SMD_OK;
+}
+
+extern "C" int smd_add_bends(smd_ctx *ctx, int32_t n, const int32_t *ijk, const double c[2])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (ijk || n == 0) && c, "bad BEND arguments");
+	int rc = check_index(ctx, ijk, 3 * (size_t)n, "BEND Molecule");
+	if (rc) return rc;
+	BendList b;
+	b.n = n; b.c[0] = c[0]; b.c[1] = c[1];
+	rc = upload_list<int>(ctx, ijk, 3 * (size_t)n, &b.d_ijk);
+	if (rc) return rc;
+	ctx->bends.push_back(b);
+	ctx->n_molecules++;
+	return SMD_OK;
+}
+
+extern "C" int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const double c[2])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	(void)n; (void)cj; (void)c;
+	ctx->err = "BALL molecules are not implemented yet";
+	return SMD_ERR_UNSUPPORTED;
+}
+
+// rebuild the assembled bead lists: molecule i sees its own beads followed by those of every later BEAD molecule
+static int rebuild_bead_lists(smd_ctx *ctx)
+{
+	CK(cudaSetDevice(ctx->device));
+	for (size_t i = 0; i < ctx->beads.size(); i++) {
+		std::vector<int> all;
+		for (size_t j = i; j < ctx->beads.size(); j++) all.insert(all.end(), ctx->beads[j].own.begin(), ctx->beads[j].own.end());
+		BeadMol &b = ctx->beads[i];
+		if (b.d_beads) cudaFree(b.d_beads);
+		b.d_beads = nullptr;
+		b.nAll = (int)all.size();
+		if (!all.empty()) {
+			CK(cudaMalloc(&b.d_beads, all.size() * sizeof(int)));
+			CK(cudaMemcpy(b.d_beads, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice));
+		}
+	}
+	return SMD_OK;
+}
+
+extern "C" int smd_add_beads(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (idx || n == 0) && C, "bad BEAD arguments");
+	int rc = check_index(ctx, idx, (size_t)n, "BEAD Molecule");
+	if (rc) return rc;
+	CK(cudaSetDevice(ctx->device));
+	BeadMol b;
+	b.nOwn = n; b.nAll = n; b.d_beads = nullptr; b.d_C = nullptr;
+	b.radius = C[4];   // BEADRADIUS, MD.h:53
+	b.mol_index = ctx->n_molecules;
+	b.own.assign(idx, idx + n);
+	size_t nc = 22 * (size_t)ctx->nT * ctx->nT;
+	CK(cudaMalloc(&b.d_C, nc * sizeof(double)));
+	CK(cudaMemcpy(b.d_C, C, nc * sizeof(double), cudaMemcpyHostToDevice));
+	ctx->beads.push_back(b);
+	ctx->n_molecules++;
+	return rebuild_bead_lists(ctx);
+}
+
+extern "C" int smd_set_temperature(smd_ctx *ctx, double temperature)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	ctx->temperature = temperature;
+	return SMD_OK;
+}
+
+extern "C" int smd_set_noise(smd_ctx *ctx, const double *u)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(u, "null noise");
+	REQUIRE(ctx->desc.noise == SMD_NOISE_EXTERNAL, "context was not created with SMD_NOISE_EXTERNAL");
+	CK(cudaSetDevice(ctx->device));
+	// the previous Langevin kernel may still be reading the buffer: stream order takes care of it
+	CK(cudaMemcpyAsync(ctx->noise, u, 3 * (size_t)ctx->N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));   // host buffer may be reused by the caller
+	ctx->noise_ready = true;
+	return SMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cell build
+static int build_cells(smd_ctx *ctx)
+{
+	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1;
+	// bin into the window derived by the previous build (or by refresh_window); k_scan2 derives the next one
+	int w = ctx->wnext;
+	int *win = ctx->win[w], *win_next = ctx->win[w ^ 1];
+	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, N, ctx->pos[cur], ctx->geom, win, ctx->count, ctx->cellOfSlot, ctx->bbox, ctx->errflag);
+	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, win, ctx->blockSums);
+	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, win_next, ctx->geom, ctx->cellcap, ctx->errflag);
+	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, win, ctx->blockSums, ctx->start, ctx->cursor, N);
+	LAUNCH(k_place, nblk(N, TPB), TPB, 0, N, ctx->cellOfSlot, ctx->cursor, ctx->order);
+	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[cur], ctx->pos[nxt],
+	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
+	       ctx->gid[nxt], ctx->slot_of);
+	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
+	ctx->cur = nxt;
+	ctx->wdata = w;
+	ctx->wnext = w ^ 1;
+	ctx->cells_valid = true;
+	ctx->rebuilds++;
+	return SMD_OK;
+}
+
+// the window the CURRENT sorted order / start[] refer to
+static inline int *cur_win(smd_ctx *ctx) { return ctx->win[ctx->wdata]; }
+
+extern "C" int smd_build_cells(smd_ctx *ctx)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->particles_set, "smd_set_particles first");
+	CK(cudaSetDevice(ctx->device));
+	if (ctx->cells_valid) return SMD_OK;
+	return build_cells(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ force terms
+static int pair_smem(smd_ctx *ctx) { return 6 * ctx->nT * ctx->nT * (int)sizeof(double); }
+
+// NOTE on acc[]: a build permutes pos / vel / gid but not acc (it is zeroed or recomputed right after every
+// build in the reference's loop order), so forces are always evaluated as: [build] -> zero -> terms.
+static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
+{
+	const Particle *pos = ctx->pos[ctx->cur];
+	if (mask & SMD_MASK(SMD_TERM_CHAIN))
+		for (auto &cb : ctx->chains)
+			if (cb.nChains > 0)
+				LAUNCH(k_chain<0>, nblk(cb.nChains, TPB), TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, cb, ctx->acc, nullptr, 1.0, 1.0, 1.0);
+	if (mask & SMD_MASK(SMD_TERM_BOND))
+		for (auto &b : ctx->bonds)
+			if (b.n > 0)
+				LAUNCH(k_bond<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+	if (mask & SMD_MASK(SMD_TERM_BEND))
+		for (auto &b : ctx->bends)
+			if (b.n > 0)
+				LAUNCH(k_bend<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+	if (mask & SMD_MASK(SMD_TERM_BEAD))
+		for (auto &b : ctx->beads) {
+			if (b.nOwn <= 0) continue;
+			LAUNCH(k_beadbead<0>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius,
+			       ctx->acc, nullptr, 1.0, 1.0, 1.0);
+			LAUNCH(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
+			       b.d_beads, b.d_C, b.nOwn <= 20 ? 1 : 0, ctx->acc, nullptr, 1.0, 1.0, 1.0);
+		}
+	return SMD_OK;
+}
+
+static int bead_mass_divide(smd_ctx *ctx)
+{
+	for (auto &b : ctx->beads) {
+		if (b.nOwn <= 0) continue;
+		double mass = (4.0) * M_PI * b.radius * b.radius;   // MD.cpp:346
+		LAUNCH(k_bead_mass, nblk(b.nOwn, 64), 64, 0, b.nOwn, ctx->cap, b.d_beads, ctx->slot_of, mass, ctx->acc);
+	}
+	return SMD_OK;
+}
+
+static int add_langevin(smd_ctx *ctx, int64_t step)
+{
+	double sigma = sqrt((6.0 * ctx->temperature * ctx->desc.gamma) / ctx->desc.dt);   // langevin.h:235
+	const double *ext = nullptr;
+	if (ctx->desc.noise == SMD_NOISE_EXTERNAL) {
+		REQUIRE(ctx->noise_ready, "SMD_NOISE_EXTERNAL: call smd_set_noise before every Langevin evaluation");
+		ext = ctx->noise;
+		ctx->noise_ready = false;
+	}
+	LAUNCH(k_langevin, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->cap, ctx->vel[ctx->cur], ctx->acc, ctx->gid[ctx->cur], ctx->desc.gamma, sigma,
+	       ctx->desc.seed, (uint64_t)step, ext);
+	return SMD_OK;
+}
+
+static int ready(smd_ctx *ctx)
+{
+	REQUIRE(ctx->particles_set, "smd_set_particles first");
+	REQUIRE(ctx->tables_set, "smd_set_pair_tables first");
+	CK(cudaSetDevice(ctx->device));
+	return SMD_OK;
+}
+
+static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first)
+{
+	int N = ctx->N;
+	// CellOpt::build: always rebuilt (the reference rebuilds every step, MD.cpp:412)
+	ctx->acc_live = false;   // about to be overwritten: no need to carry it through the build
+	if (!ctx->cells_valid) build_cells(ctx);
+	LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);
+	ctx->acc_live = true;
+	int rc;
+	if (langevin_first && (mask & SMD_MASK_LANGEVIN))
+		if ((rc = add_langevin(ctx, step))) return rc;
+	if (mask & SMD_MASK(SMD_TERM_PAIR))
+		LAUNCH(k_pair<PAIR_FORCE>, nblk(N, TPB), TPB, pair_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start,
+		       cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->acc, nullptr, nullptr, 1.0, 1.0, 1.0);
+	if (!langevin_first && (mask & SMD_MASK_LANGEVIN))
+		if ((rc = add_langevin(ctx, step))) return rc;
+	return add_molecule_forces(ctx, mask);
+}
+
+extern "C" int smd_compute_forces(smd_ctx *ctx, uint32_t term_mask, int64_t step)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	int rc = ready(ctx);
+	if (rc) return rc;
+	// MD.cpp:192-262: pair, thermostat, molecules
+	rc = forces(ctx, term_mask, step, false);
+	return rc;
+}
+
+extern "C" int smd_resume(smd_ctx *ctx)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	int rc = ready(ctx);
+	if (rc) return rc;
+	bead_mass_divide(ctx);
+	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);
+	return SMD_OK;
+}
+
+extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	(void)step;
+	int rc = ready(ctx);
+	if (rc) return rc;
+	int N = ctx->N;
+	bead_mass_divide(ctx);                                                         // MD.cpp:340-355
+	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
+	       ctx->desc.dt);                                                          // MD.cpp:356
+	LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);                  // MD.cpp:357-366
+	ctx->acc_live = false;
+	ctx->cells_valid = false;
+	return SMD_OK;
+}
+
+extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	int rc = ready(ctx);
+	if (rc) return rc;
+	// MD.cpp:410-478: thermostat, build, pair, molecules
+	rc = forces(ctx, SMD_MASK_ALL, step, true);
+	if (rc) return rc;
+	bead_mass_divide(ctx);                                                         // MD.cpp:480-494
+	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);   // :511
+	return SMD_OK;
+}
+
+extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->desc.noise != SMD_NOISE_EXTERNAL || nsteps <= 1, "external noise: one step per smd_set_noise");
+	for (int k = 0; k < nsteps; k++) {
+		int rc = smd_step_begin(ctx, first_step + k);
+		if (rc) return rc;
+		rc = smd_step_end(ctx, first_step + k);
+		if (rc) return rc;
+	}
+	return SMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ energies
+static int finish_sum(smd_ctx *ctx, int nparts, int slot, double factor)
+{
+	LAUNCH(k_final_sum, 1, 256, 0, nparts, ctx->partials, ctx->scalars, slot, factor);
+	return SMD_OK;
+}
+
+// MODE 1 potential, 2 dPotential; results accumulate on the host per term
+template <int MODE>
+static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
+{
+	int rc = ready(ctx);
+	if (rc) return rc;
+	int N = ctx->N;
+	if (!ctx->cells_valid) build_cells(ctx);   // dataExtraction::compute rebuilds its own CellOpt (dataExtraction.h:839-841)
+	double sx = scale ? scale[0] : 1.0, sy = scale ? scale[1] : 1.0, sz = scale ? scale[2] : 1.0;
+	const Particle *pos = ctx->pos[ctx->cur];
+	std::vector<int> term_of_slot;
+	int slot = 0;
+	auto push = [&](int term) { term_of_slot.push_back(term); return slot++; };
+	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + 2 * ctx->beads.size() <= 64, "too many molecule records for one energy call");
+	{
+		int nb = nblk(N, TPB);
+		LAUNCH(k_pair<(MODE == 1 ? PAIR_POTENTIAL : PAIR_DPOTENTIAL)>, nb, TPB, pair_smem(ctx), N, ctx->cap, pos, ctx->gid[ctx->cur], ctx->start,
+		       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, nullptr, ctx->partials, nullptr, sx, sy, sz);
+		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
+	}
+	for (auto &cb : ctx->chains) {
+		if (cb.nChains <= 0) continue;
+		int nb = nblk(cb.nChains, TPB);
+		LAUNCH(k_chain<MODE>, nb, TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, cb, nullptr, ctx->partials, sx, sy, sz);
+		finish_sum(ctx, nb, push(SMD_TERM_CHAIN), 1.0);
+	}
+	for (auto &b : ctx->bonds) {
+		if (b.n <= 0) continue;
+		int nb = nblk(b.n, TPB);
+		LAUNCH(k_bond<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz);
+		finish_sum(ctx, nb, push(SMD_TERM_BOND), 1.0);
+	}
+	for (auto &b : ctx->bends) {
+		if (b.n <= 0) continue;
+		int nb = nblk(b.n, TPB);
+		LAUNCH(k_bend<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz);
+		finish_sum(ctx, nb, push(SMD_TERM_BEND), 1.0);
+	}
+	for (auto &b : ctx->beads) {
+		if (b.nOwn <= 0) continue;
+		LAUNCH(k_beadbead<MODE>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius, nullptr,
+		       ctx->partials, sx, sy, sz);
+		finish_sum(ctx, 1, push(SMD_TERM_BEAD), 1.0);
+		int nb = nblk(N, TPB);
+		LAUNCH(k_bead<MODE>, nb, TPB, 0, N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, 0,
+		       nullptr, ctx->partials, sx, sy, sz);
+		finish_sum(ctx, nb, push(SMD_TERM_BEAD), 1.0);
+	}
+	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, slot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	rc = check_device_errors(ctx);
+	if (rc) return rc;
+	for (int t = 0; t < SMD_NTERMS; t++) out_terms[t] = 0;
+	for (int k = 0; k < slot; k++) out_terms[term_of_slot[k]] += ctx->h_pinned[k];
+	return SMD_OK;
+}
+
+extern "C" int smd_potential(smd_ctx *ctx, double *out_terms)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(out_terms, "null output");
+	return energy_terms<1>(ctx, nullptr, out_terms);
+}
+
+extern "C" int smd_dpotential(smd_ctx *ctx, const double scale[3], double *out_terms)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(out_terms && scale, "null argument");
+	return energy_terms<2>(ctx, scale, out_terms);
+}
+
+extern "C" int smd_kinetic(smd_ctx *ctx, double *out)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(out && ctx->particles_set, "bad call");
+	CK(cudaSetDevice(ctx->device));
+	int nb = std::min(nblk(ctx->N, 256), 1024);
+	LAUNCH(k_kinetic, nb, 256, 0, ctx->N, ctx->cap, ctx->vel[ctx->cur], ctx->partials);
+	finish_sum(ctx, nb, 0, 1.0);
+	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	int rc = check_device_errors(ctx);
+	if (rc) return rc;
+	*out = ctx->h_pinned[0];
+	return SMD_OK;
+}
+
+extern "C" int smd_count_pairs(smd_ctx *ctx, int64_t *total, int32_t *per_particle)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	int rc = ready(ctx);
+	if (rc) return rc;
+	int N = ctx->N;
+	if (!ctx->cells_valid) build_cells(ctx);
+	int nb = nblk(N, TPB);
+	LAUNCH(k_pair<PAIR_COUNT>, nb, TPB, pair_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom,
+	       ctx->nT, ctx->fC, nullptr, ctx->partials, ctx->icount, 1.0, 1.0, 1.0);
+	finish_sum(ctx, nb, 0, 1.0);
+	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	if (per_particle) {
+		LAUNCH(k_export_int, nblk(N, TPB), TPB, 0, N, ctx->icount, ctx->gid[ctx->cur], ctx->istage);
+		CK(cudaMemcpyAsync(per_particle, ctx->istage, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	rc = check_device_errors(ctx);
+	if (rc) return rc;
+	if (total) *total = (int64_t)llround(ctx->h_pinned[0]) / 2;
+	return SMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ box moves
+extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(scale && new_box && ctx->particles_set, "bad call");
+	CK(cudaSetDevice(ctx->device));
+	Geom old = ctx->geom;
+	set_geom(ctx, new_box);
+	int rc = check_geom(ctx);
+	long long total = (long long)ctx->geom.nc[0] * ctx->geom.nc[1] * ctx->geom.nc[2];
+	if (!rc && total > ctx->cellcap) { ctx->err = "box grew beyond the cell-table capacity"; rc = SMD_ERR_UNSUPPORTED; }
+	if (rc) { ctx->geom = old; return rc; }
+	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], scale[0], scale[1], scale[2]);
+	refresh_window(ctx);
+	return SMD_OK;
+}
+
+extern "C" int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, double u_fluct, double u_accept, int32_t *accepted,
+                               double *dU_total, double box_out[3])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	// MD.cpp:591-613
+	double size[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
+	double oldSize[3] = {size[0], size[1], size[2]};
+	double fl[3];
+	fl[0] = deltaLXY * (2.0 * u_fluct - 1.0);
+	fl[1] = fl[0];
+	fl[2] = (size[0] * size[1]) / ((size[0] + fl[0]) * (size[1] + fl[1]));
+	size[0] += fl[0]; size[1] += fl[1]; size[2] *= fl[2];
+	double aSize[3] = {size[0] / oldSize[0], size[1] / oldSize[1], size[2] / oldSize[2]};
+	double terms[SMD_NTERMS];
+	int rc = smd_dpotential(ctx, aSize, terms);
+	if (rc) return rc;
+	// MD.cpp:615-675: pair first, then the molecules in file order (we sum by kind; FP64 sum order differs only)
+	double dPotential = 0;
+	for (int t = 0; t < SMD_NTERMS; t++) dPotential += terms[t];
+	if (tension != 0) dPotential += tension * ((size[0] * size[1]) - (oldSize[0] * oldSize[1]));   // :677-678
+	double D = exp(dPotential / ctx->temperature);                                                    // :683-687
+	int acc = (D >= u_accept || -dPotential <= 0) ? 1 : 0;                                            // :695
+	if (acc) {
+		rc = smd_rescale(ctx, aSize, size);
+		if (rc) return rc;
+	}
+	if (accepted) *accepted = acc;
+	if (dU_total) *dU_total = dPotential;
+	if (box_out) for (int d = 0; d < 3; d++) box_out[d] = ctx->geom.box[d];
+	return SMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ read back
+extern "C" int smd_get_particles(smd_ctx *ctx, double *xyz, int32_t *type, double *vel)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->particles_set, "smd_set_particles first");
+	CK(cudaSetDevice(ctx->device));
+	int N = ctx->N;
+	double *sx = ctx->stage, *sv = ctx->stage + 3 * (size_t)ctx->cap;
+	LAUNCH(k_export_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->gid[ctx->cur], xyz ? sx : nullptr,
+	       type ? ctx->istage : nullptr, vel ? sv : nullptr);
+	if (xyz) CK(cudaMemcpyAsync(xyz, sx, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	if (type) CK(cudaMemcpyAsync(type, ctx->istage, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	if (vel) CK(cudaMemcpyAsync(vel, sv, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	return check_device_errors(ctx);
+}
+
+extern "C" int smd_get_forces(smd_ctx *ctx, double *acc)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(acc && ctx->particles_set, "bad call");
+	CK(cudaSetDevice(ctx->device));
+	int N = ctx->N;
+	LAUNCH(k_export_soa3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc, ctx->gid[ctx->cur], ctx->stage);
+	CK(cudaMemcpyAsync(acc, ctx->stage, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	return check_device_errors(ctx);
+}
+
+extern "C" int smd_get_unwrapped(smd_ctx *ctx, double *xyz)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(xyz && ctx->particles_set && ctx->unw[0], "unwrapped positions are not tracked");
+	CK(cudaSetDevice(ctx->device));
+	int N = ctx->N;
+	LAUNCH(k_export_soa3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->stage);
+	CK(cudaMemcpyAsync(xyz, ctx->stage, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	return check_device_errors(ctx);
+}
+
+extern "C" int smd_get_box(smd_ctx *ctx, double box[3])
+{
+	if (!ctx || !box) return SMD_ERR_ARG;
+	for (int d = 0; d < 3; d++) box[d] = ctx->geom.box[d];
+	return SMD_OK;
+}
+
+extern "C" int smd_get_cell_ids(smd_ctx *ctx, int32_t n_cells_xyz[3], int32_t *cell_key, int32_t *cell_rank)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(cell_key && cell_rank, "null output");
+	int rc = ready(ctx);
+	if (rc) return rc;
+	if (!ctx->cells_valid) build_cells(ctx);
+	int N = ctx->N;
+	int *key = ctx->istage, *rank = ctx->istage + ctx->cap;
+	LAUNCH(k_export_cells, nblk(N, TPB), TPB, 0, N, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom, key, rank);
+	CK(cudaMemcpyAsync(cell_key, key, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(cell_rank, rank, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	if (n_cells_xyz) for (int d = 0; d < 3; d++) n_cells_xyz[d] = ctx->geom.nc[d];
+	return check_device_errors(ctx);
+}
+
+extern "C" int smd_device_ptr(smd_ctx *ctx, int32_t which, void **ptr, size_t *bytes)
+{
+	if (!ctx || !ptr) return SMD_ERR_ARG;
+	size_t b = 0;
+	switch (which) {
+	case 0: *ptr = ctx->pos[ctx->cur]; b = (size_t)ctx->N * sizeof(Particle); break;
+	case 1: *ptr = ctx->vel[ctx->cur]; b = 3 * (size_t)ctx->cap * sizeof(double); break;
+	case 2: *ptr = ctx->acc; b = 3 * (size_t)ctx->cap * sizeof(double); break;
+	case 3: *ptr = ctx->gid[ctx->cur]; b = (size_t)ctx->N * sizeof(int); break;
+	default: ctx->err = "unknown buffer"; return SMD_ERR_ARG;
+	}
+	if (bytes) *bytes = b;
+	return SMD_OK;
+}
+
+extern "C" int smd_stream(smd_ctx *ctx, void **stream)
+{
+	if (!ctx || !stream) return SMD_ERR_ARG;
+	*stream = (void *)ctx->stream;
+	return SMD_OK;
+}
+
+extern "C" int smd_stats(smd_ctx *ctx, int64_t *kernel_launches, int64_t *rebuilds)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	if (kernel_launches) *kernel_launches = ctx->launches;
+	if (rebuilds) *rebuilds = ctx->rebuilds;
+	return SMD_OK;
+}

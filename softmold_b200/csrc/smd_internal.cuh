@@ -1,0 +1,111 @@
+// Internal definitions shared by the CUDA translation units of libsoftmold_b200.so.
+// Compiled for sm_100a only, with --fmad=false: the reference is g++ -O3 on baseline x86-64 (no FMA), and cell /
+// neighbour membership has to be bit-exact with it, so no multiply-add may be contracted anywhere in this library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/softmold_b200.h"
+
+namespace smd {
+
+// One particle record, 32 B, 32 B aligned: the device twin of the reference's position<T> {x,y,z,int type}
+// (include/algorithms/dataTypes.h:183-351).  The 4 spare bytes carry the particle's cell coordinates in the
+// reference grid, packed 11/11/10 bits (x,y,z), filled by the binning kernel.
+struct __align__(32) Particle {
+	double x, y, z;
+	int type;
+	unsigned cell;
+};
+
+__host__ __device__ inline unsigned pack_cell(int cx, int cy, int cz) { return (unsigned)cx | ((unsigned)cy << 11) | ((unsigned)cz << 22); }
+__host__ __device__ inline void unpack_cell(unsigned c, int &cx, int &cy, int &cz) { cx = c & 2047u; cy = (c >> 11) & 2047u; cz = c >> 22; }
+
+// geometry passed by value to kernels (changes only through host-driven box moves)
+struct Geom {
+	double box[3];
+	double cs[3];   // cell size  = box / nc          (cellOpt.h:207-209)
+	int nc[3];      // cells per axis = int(box / rc) (cellOpt.h:194-196)
+	double rc2;     // cutoff^2
+};
+
+// device-resident active window of the cell grid: the bounding box of occupied cells dilated by one cell.
+// win[0..2] origin, win[3..5] extent, win[6] number of cells in the window.
+enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_WORDS = 8 };
+
+enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW = 2, ERR_WINDOW_CAP = 4, ERR_NAN = 8 };
+
+struct ChainBlock { int start, nChains, len; double c[4]; };
+struct BondList { int n; int *d_ij; double c[2]; };
+struct BendList { int n; int *d_ijk; double c[2]; };
+struct BallList { int n; int *d_cj; double c[2]; };
+struct BeadMol {
+	int nOwn, nAll;        // beads of this molecule / of the list assembled from molecules j >= i (system.h:2053-2070)
+	int *d_beads;          // [nAll] original particle indices, own beads first
+	double *d_C;           // [22*nT*nT]
+	double radius;         // C[BEADRADIUS=4]
+	int mol_index;         // position in the molecule list (file order)
+	std::vector<int> own;  // host copy of own bead indices
+};
+
+} // namespace smd
+
+struct smd_ctx {
+	smd_desc desc;
+	int N, nT, cap;
+	smd::Geom geom;
+	double temperature;
+	std::string err;
+	cudaStream_t stream;
+	int device;
+
+	// resident particle state, cell-sorted ("slot" order); double-buffered for the per-step reorder
+	smd::Particle *pos[2];
+	double *vel[2];   // SoA [3][cap]
+	double *unw[2];   // SoA [3][cap] unwrapped positions (optional)
+	int *gid[2];      // original index of slot
+	int cur;
+	double *acc;      // SoA [3][cap]
+	double *acc2;     // alternate buffer for builds that must carry live accelerations along
+	bool acc_live;    // acc holds forces a later kick still needs
+	int *slot_of;     // [N] slot of original index
+
+	// cell grid
+	long long cellcap;
+	int *count, *start, *cursor, *blockSums;
+	int *cellOfSlot, *order;
+	int *win[2];      // window descriptors (device), ping-pong
+	int wdata, wnext; // window start[] refers to / window the next build bins into
+	int *bbox;        // [6] min xyz, max xyz accumulators
+	int *errflag;
+	bool cells_valid;  // sorted order + start[] describe the current positions
+
+	// pair tables
+	double *fC, *uC;
+	bool tables_set, particles_set;
+
+	// molecules
+	std::vector<smd::ChainBlock> chains;
+	std::vector<smd::BondList> bonds;
+	std::vector<smd::BendList> bends;
+	std::vector<smd::BallList> balls;
+	std::vector<smd::BeadMol> beads;
+	int n_molecules;
+
+	// noise
+	double *noise;     // [N][3] original order, external uniforms
+	bool noise_ready;
+
+	// scratch
+	double *partials;  // block partial sums
+	double *scalars;   // small device result buffer
+	int *icount;       // per-particle int scratch
+	double *stage;     // [N][3] staging in original order
+	int *istage;       // [N]
+	double *h_pinned;  // pinned host scratch (scalars)
+
+	long long launches, rebuilds;
+};

@@ -1,0 +1,999 @@
+// Device kernels of the SoftMold MD timestep for sm_100a.  Included by smd_core.cu only.
+// All FP64; compiled with --fmad=false (see smd_internal.cuh).  Reference citations are file:line relative to the
+// reference root.
+#pragma once
+#include "smd_internal.cuh"
+
+namespace smd {
+
+constexpr int TPB = 128;          // threads per block for per-particle kernels
+constexpr int SCAN_BLOCKS = 256;  // fixed grid of the 3-phase cell-offset scan
+constexpr int SCAN_TPB = 256;
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// deterministic block sum (result valid in thread 0); blockDim.x multiple of 32, <= 1024
+__device__ __forceinline__ double block_sum(double v)
+{
+	__shared__ double sh[32];
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	v = warp_sum(v);
+	__syncthreads();
+	if (lane == 0) sh[w] = v;
+	__syncthreads();
+	int nw = (blockDim.x + 31) >> 5;
+	v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+	if (w == 0) v = warp_sum(v);
+	return v;
+}
+
+__device__ __forceinline__ Particle load_particle(const Particle *p)
+{
+	// two 16-byte loads of one aligned 32-byte record (one sector)
+	const double2 *q = reinterpret_cast<const double2 *>(p);
+	double2 a = q[0], b = q[1];
+	Particle r;
+	r.x = a.x; r.y = a.y; r.z = b.x;
+	long long w = __double_as_longlong(b.y);
+	r.type = (int)(w & 0xffffffffll);
+	r.cell = (unsigned)((unsigned long long)w >> 32);
+	return r;
+}
+
+__device__ __forceinline__ void store_particle(Particle *p, const Particle &r)
+{
+	double2 *q = reinterpret_cast<double2 *>(p);
+	long long w = ((long long)(unsigned long long)r.cell << 32) | (unsigned)r.type;
+	q[0] = make_double2(r.x, r.y);
+	q[1] = make_double2(r.z, __longlong_as_double(w));
+}
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+// Counter-based noise keyed on (seed, step, particle): spec in DESIGN.md, restated in oracle/oracle.c.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4])
+{
+#pragma unroll
+	for (int r = 0; r < 10; r++) {
+		uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+		uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+		uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+		c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+		k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+	}
+	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+	return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void philox_uniform3(uint64_t seed, uint64_t step, uint32_t id, double u[3])
+{
+	uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ 0x5D0F7A3Bu;
+	uint32_t w[4], x[4];
+	philox4x32_10(id, (uint32_t)step, (uint32_t)(step >> 32), 0u, k0, k1, w);
+	philox4x32_10(id, (uint32_t)step, (uint32_t)(step >> 32), 1u, k0, k1, x);
+	u[0] = u53(w[0], w[1]);
+	u[1] = u53(w[2], w[3]);
+	u[2] = u53(x[0], x[1]);
+}
+
+// ------------------------------------------------------------------------------------------------ integrator
+// Verlet::first, algorithms/verlet.h:288-356: v += a*dt/2 ; p += v*dt ; aP += v*dt (type != 0 only) ; wrap with
+// strict > L and < 0 for every particle.  In place, slot order.
+__global__ void __launch_bounds__(TPB) k_verlet_first(int N, int cap, Particle *pos, double *vel, const double *acc, double *unw,
+                                                      Geom g, double dt)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	Particle p = load_particle(pos + s);
+	double h = 0.5 * dt;
+	if (p.type != 0) {
+		double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
+		vx += (acc[s] * h); vy += (acc[cap + s] * h); vz += (acc[2 * cap + s] * h);
+		vel[s] = vx; vel[cap + s] = vy; vel[2 * cap + s] = vz;
+		p.x += vx * dt; p.y += vy * dt; p.z += vz * dt;
+		if (unw) {
+			unw[s] += vx * dt; unw[cap + s] += vy * dt; unw[2 * cap + s] += vz * dt;
+		}
+	}
+	if (p.x > g.box[0]) p.x -= g.box[0];
+	if (p.x < 0) p.x += g.box[0];
+	if (p.y > g.box[1]) p.y -= g.box[1];
+	if (p.y < 0) p.y += g.box[1];
+	if (p.z > g.box[2]) p.z -= g.box[2];
+	if (p.z < 0) p.z += g.box[2];
+	store_particle(pos + s, p);
+}
+
+// Verlet::second, algorithms/verlet.h:463-477
+__global__ void __launch_bounds__(TPB) k_verlet_second(int N, int cap, const Particle *pos, double *vel, const double *acc, double dt)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	if (pos[s].type == 0) return;
+	double h = 0.5 * dt;
+	vel[s] += (acc[s] * h);
+	vel[cap + s] += (acc[cap + s] * h);
+	vel[2 * cap + s] += (acc[2 * cap + s] * h);
+}
+
+__global__ void __launch_bounds__(TPB) k_zero3(int N, int cap, double *a)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	a[s] = 0; a[cap + s] = 0; a[2 * cap + s] = 0;
+}
+
+// Langevin::compute scalar-gamma branch, algorithms/langevin.h:284-331: a += -g v + sigma (2u-1)
+__global__ void __launch_bounds__(TPB) k_langevin(int N, int cap, const double *vel, double *acc, const int *gid, double gamma,
+                                                  double sigma, uint64_t seed, uint64_t step, const double *ext_noise)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	int id = gid[s];
+	double u[3];
+	if (ext_noise) {
+		u[0] = ext_noise[3 * id]; u[1] = ext_noise[3 * id + 1]; u[2] = ext_noise[3 * id + 2];
+	} else {
+		philox_uniform3(seed, step, (uint32_t)id, u);
+	}
+#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		double psi = 2.0 * u[c] - 1.0;
+		acc[c * cap + s] += (-gamma * vel[c * cap + s] + sigma * psi);
+	}
+}
+
+// Kinetic::compute, algorithms/dataCollection.h:666-674: sum (vx^2+vy^2+vz^2)/2
+__global__ void __launch_bounds__(256) k_kinetic(int N, int cap, const double *vel, double *partials)
+{
+	double e = 0;
+	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < N; s += gridDim.x * blockDim.x) {
+		double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
+		e += ((vx * vx + vy * vy + vz * vz) / 2.0);
+	}
+	e = block_sum(e);
+	if (threadIdx.x == 0) partials[blockIdx.x] = e;
+}
+
+// final deterministic reduction of `n` partials into out[slot]
+__global__ void __launch_bounds__(256) k_final_sum(int n, const double *partials, double *out, int slot, double factor)
+{
+	double e = 0;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) e += partials[i];
+	e = block_sum(e);
+	if (threadIdx.x == 0) out[slot] = e * factor;
+}
+
+// accepted box move: p *= aSize (MD.cpp:697-707)
+__global__ void __launch_bounds__(TPB) k_rescale(int N, Particle *pos, double sx, double sy, double sz)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	Particle p = load_particle(pos + s);
+	p.x *= sx; p.y *= sy; p.z *= sz;
+	store_particle(pos + s, p);
+}
+
+// ------------------------------------------------------------------------------------------------ cell list
+// CellOpt::build, cellOpt.h:510-710.  The reference grid is nc = int(L/rc), cell size L/nc, key from int(p/cs) with
+// the upper-edge clamp (:530-556).  We keep a dense offset table only over the occupied window of that grid.
+
+__device__ __forceinline__ bool cell_coords(const Particle &p, const Geom &g, int &cx, int &cy, int &cz)
+{
+	cx = (int)(p.x / g.cs[0]); cy = (int)(p.y / g.cs[1]); cz = (int)(p.z / g.cs[2]);
+	cx = (cx >= g.nc[0]) ? cx - 1 : cx;   // "correction for older systems", cellOpt.h:537-539
+	cy = (cy >= g.nc[1]) ? cy - 1 : cy;
+	cz = (cz >= g.nc[2]) ? cz - 1 : cz;
+	// the reference would index out of bounds here (ERRORS_ENABLED: throw 0, cellOpt.h:541-552)
+	return !(cx < 0 || cy < 0 || cz < 0 || cx >= g.nc[0] || cy >= g.nc[1] || cz >= g.nc[2]) &&
+	       p.x == p.x && p.y == p.y && p.z == p.z;
+}
+
+// bounding box of occupied cells (used after set_particles / a box move; steady state tracks it inside k_bin)
+__global__ void __launch_bounds__(TPB) k_bbox(int N, const Particle *pos, Geom g, int *bbox, int *errflag)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+	if (s < N) {
+		Particle p = load_particle(pos + s);
+		int c[3];
+		if (!cell_coords(p, g, c[0], c[1], c[2])) atomicOr(errflag, ERR_OUT_OF_BOX);
+		else
+			for (int d = 0; d < 3; d++) { lo[d] = c[d]; hi[d] = c[d]; }
+	}
+	for (int d = 0; d < 3; d++) {
+		int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
+		if ((threadIdx.x & 31) == 0 && l != INT_MAX) { atomicMin(bbox + d, l); atomicMax(bbox + 3 + d, h); }
+	}
+}
+
+// window = bbox dilated by one cell, clamped to the grid; resets the accumulators
+__device__ __forceinline__ void window_from_bbox(int *bbox, int *win, const Geom &g, long long cellcap, int *errflag)
+{
+	long long n = 1;
+	for (int d = 0; d < 3; d++) {
+		int lo = bbox[d], hi = bbox[3 + d];
+		if (lo == INT_MAX) { lo = 0; hi = 0; }
+		lo = max(lo - 1, 0);
+		hi = min(hi + 1, g.nc[d] - 1);
+		win[WIN_ORG + d] = lo;
+		win[WIN_DIM + d] = hi - lo + 1;
+		n *= (hi - lo + 1);
+		bbox[d] = INT_MAX; bbox[3 + d] = INT_MIN;
+	}
+	if (n > cellcap) { atomicOr(errflag, ERR_WINDOW_CAP); n = 0; }
+	win[WIN_NCELLS] = (int)n;
+}
+
+__global__ void k_window_init(int *bbox, int *win, Geom g, long long cellcap, int *errflag)
+{
+	window_from_bbox(bbox, win, g, cellcap, errflag);
+}
+
+// pass 1 of the counting sort: key of every particle, histogram over the window, bbox for the next window.
+// Warp-aggregated: lanes sharing a cell elect a leader that issues one atomicAdd for the group.
+__global__ void __launch_bounds__(TPB) k_bin(int N, Particle *pos, Geom g, const int *win, int *count, int *cellOfSlot, int *bbox,
+                                             int *errflag)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+	int local = -1;
+	if (s < N) {
+		Particle p = load_particle(pos + s);
+		int c[3];
+		bool ok = cell_coords(p, g, c[0], c[1], c[2]);
+		if (!ok) {
+			atomicOr(errflag, ERR_OUT_OF_BOX);
+			for (int d = 0; d < 3; d++) c[d] = min(max(c[d], 0), g.nc[d] - 1);
+		}
+		int l[3];
+		bool inside = true;
+		for (int d = 0; d < 3; d++) {
+			l[d] = c[d] - win[WIN_ORG + d];
+			if (l[d] < 0 || l[d] >= win[WIN_DIM + d]) { inside = false; l[d] = min(max(l[d], 0), win[WIN_DIM + d] - 1); }
+			lo[d] = hi[d] = c[d];
+		}
+		if (!inside) atomicOr(errflag, ERR_WINDOW);
+		local = l[0] + win[WIN_DIM] * (l[1] + win[WIN_DIM + 1] * l[2]);
+		p.cell = pack_cell(c[0], c[1], c[2]);
+		store_particle(pos + s, p);
+		cellOfSlot[s] = local;
+	}
+	unsigned active = __ballot_sync(0xffffffffu, local >= 0);
+	if (local >= 0) {
+		unsigned peers = __match_any_sync(active, local);
+		int leader = __ffs(peers) - 1;
+		if ((int)(threadIdx.x & 31) == leader) atomicAdd(count + local, __popc(peers));
+	}
+	for (int d = 0; d < 3; d++) {
+		int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
+		if ((threadIdx.x & 31) == 0 && l != INT_MAX) { atomicMin(bbox + d, l); atomicMax(bbox + 3 + d, h); }
+	}
+}
+
+// 3-phase exclusive scan of count[0..ncells) with a fixed grid (ncells lives on the device)
+__device__ __forceinline__ void scan_chunk(int ncells, int &b0, int &b1)
+{
+	int chunk = (ncells + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
+	chunk = (chunk + SCAN_TPB - 1) / SCAN_TPB * SCAN_TPB;
+	long long a = (long long)blockIdx.x * chunk;
+	b0 = (int)min(a, (long long)ncells);
+	b1 = (int)min(a + chunk, (long long)ncells);
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int *win, int *blockSums)
+{
+	int b0, b1;
+	scan_chunk(win[WIN_NCELLS], b0, b1);
+	int sum = 0;
+	for (int i = b0 + threadIdx.x; i < b1; i += SCAN_TPB) sum += count[i];
+	__shared__ int sh[SCAN_TPB / 32];
+	sum = __reduce_add_sync(0xffffffffu, sum);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int t = 0;
+		for (int w = 0; w < SCAN_TPB / 32; w++) t += sh[w];
+		blockSums[blockIdx.x] = t;
+	}
+}
+
+// single block: exclusive scan of the block sums; thread 0 also derives the NEXT step's window from the bbox
+// accumulated by k_bin (particles move less than one cell per step, so bbox +- 1 cell contains them next step)
+__global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox, int *win_next, Geom g, long long cellcap, int *errflag)
+{
+	__shared__ int sh[SCAN_BLOCKS];
+	int v = blockSums[threadIdx.x];
+	sh[threadIdx.x] = v;
+	__syncthreads();
+	for (int o = 1; o < SCAN_BLOCKS; o <<= 1) {
+		int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+		__syncthreads();
+		sh[threadIdx.x] += t;
+		__syncthreads();
+	}
+	blockSums[threadIdx.x] = sh[threadIdx.x] - v;
+	if (threadIdx.x == 0) window_from_bbox(bbox, win_next, g, cellcap, errflag);
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *win, const int *blockSums, int *start, int *cursor, int N)
+{
+	int ncells = win[WIN_NCELLS];
+	int b0, b1;
+	scan_chunk(ncells, b0, b1);
+	__shared__ int sh[SCAN_TPB / 32];
+	__shared__ int carry_sh;
+	if (threadIdx.x == 0) carry_sh = blockSums[blockIdx.x];
+	__syncthreads();
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int base = b0; base < b1; base += SCAN_TPB) {
+		int i = base + threadIdx.x;
+		int v = (i < b1) ? count[i] : 0;
+		int inc = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += t;
+		}
+		if (lane == 31) sh[w] = inc;
+		__syncthreads();
+		int woff = 0, total = 0;
+		for (int k = 0; k < SCAN_TPB / 32; k++) {
+			int t = sh[k];
+			if (k < w) woff += t;
+			total += t;
+		}
+		int carry = carry_sh;
+		int ex = carry + woff + inc - v;
+		if (i < b1) { start[i] = ex; cursor[i] = ex; count[i] = 0; }
+		__syncthreads();
+		if (threadIdx.x == 0) carry_sh = carry + total;
+		__syncthreads();
+	}
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) start[ncells] = N;
+}
+
+// pass 2: claim a position inside the cell's range (arbitrary order, fixed by k_reorder)
+__global__ void __launch_bounds__(TPB) k_place(int N, const int *cellOfSlot, int *cursor, int *order)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	int q = atomicAdd(cursor + cellOfSlot[s], 1);
+	order[q] = s;
+}
+
+// pass 3: final slot = cell start + rank by DESCENDING original index, which is exactly the order of the
+// reference's head-inserted linked list (cellOpt.h:572-585) and makes the sort deterministic; move the records.
+__global__ void __launch_bounds__(TPB) k_reorder(int N, int cap, const int *order, const int *cellOfSlot, const int *start,
+                                                 const Particle *pos_in, Particle *pos_out, const double *vel_in, double *vel_out,
+                                                 const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
+                                                 const int *gid_in, int *gid_out, int *slot_of)
+{
+	int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= N) return;
+	int s = order[q];
+	int c = cellOfSlot[s];
+	int b = start[c], e = start[c + 1];
+	int g = gid_in[s];
+	int rank = 0;
+	for (int k = b; k < e; k++) rank += (gid_in[order[k]] > g);
+	int t = b + rank;
+	Particle p = load_particle(pos_in + s);
+	store_particle(pos_out + t, p);
+	vel_out[t] = vel_in[s]; vel_out[cap + t] = vel_in[cap + s]; vel_out[2 * cap + t] = vel_in[2 * cap + s];
+	if (unw_in) { unw_out[t] = unw_in[s]; unw_out[cap + t] = unw_in[cap + s]; unw_out[2 * cap + t] = unw_in[2 * cap + s]; }
+	if (acc_in) { acc_out[t] = acc_in[s]; acc_out[cap + t] = acc_in[cap + s]; acc_out[2 * cap + t] = acc_in[2 * cap + s]; }
+	gid_out[t] = g;
+	slot_of[g] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ pair engine
+// MD.h:795-848 Force<T>, MD.h:895-930 Potential<T>
+
+__device__ __forceinline__ int pair_branch(double dr, const double *fc)
+{
+	// int(dr / fC[cindex]) * 3 (MD.h:822).  For dr < 2 rm the quotient's integer part is decided exactly by
+	// comparisons (IEEE division is monotone and dr < rm => fl(dr/rm) < 1, dr < 2rm => fl(dr/rm) < 2), so the
+	// division only runs in the never-used region dr >= 2 rm.
+	double rm = fc[0];
+	if (dr < rm) return 0;
+	if (dr < rm + rm) return 3;
+	return ((int)(dr / rm)) * 3;
+}
+
+__device__ __forceinline__ double pair_force_mag(double dr2, int t1, int t2, int nT, const double *fC, int ntab)
+{
+	double dr = sqrt(dr2);
+	int ci = 6 * (t1 * nT + t2);
+	ci += pair_branch(dr, fC + ci);
+	ci = min(ci, ntab - 3);   // the reference reads past its table for dr >= 3 rm in the last row; stay in bounds
+	double m = fC[ci] - dr;
+	return ((fC[ci + 1] - fC[ci + 2] * m) * m) / dr;
+}
+
+__device__ __forceinline__ double pair_potential_val(double dr2, int t1, int t2, int nT, const double *uC)
+{
+	double dr = sqrt(dr2);
+	int ci = 6 * (t1 * nT + t2);
+	double u;
+	if (dr <= uC[ci]) {
+		u = uC[ci] - dr;
+		u = uC[ci + 1] * u * u + uC[ci + 2];
+	} else {
+		u = uC[ci + 3] - dr;
+		u = u * u * (uC[ci + 4] - u * uC[ci + 5]);
+	}
+	return u;
+}
+
+enum PairMode { PAIR_FORCE = 0, PAIR_POTENTIAL = 1, PAIR_DPOTENTIAL = 2, PAIR_COUNT = 3 };
+
+// One thread per particle (slot).  The reference walks a half stencil (13 forward cells, cellOpt.h:715) with
+// Newton's third law under per-cell locks; here every particle gathers its own force from the full 27-cell stencil:
+// no atomics, deterministic, and each pair term is BIT-IDENTICAL to the reference's because
+//   * d = p1 - p2 is exactly antisymmetric, so evaluating a pair from either end gives the same |d|^2 and magnitude;
+//   * for a neighbour cell reached across the periodic boundary the reference adds +-L to the NEIGHBOUR particle
+//     of the HOME cell before subtracting (cellOpt.h:811-821,846-848).  We reproduce that orientation: a forward
+//     offset shifts the neighbour, a backward offset means the neighbour's cell is the home cell and WE get shifted;
+//   * the constant row is picked in the reference's orientation (type of the home / later-loaded particle first).
+// PAIR_POTENTIAL / PAIR_DPOTENTIAL visit every pair once (forward cells + lower index first in the own cell) and
+// reduce per block.  tab = fC for force, uC otherwise (staged in shared memory).
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
+                                              const int *__restrict__ start, const int *__restrict__ win, Geom g, int nT,
+                                              const double *__restrict__ tab, double *__restrict__ acc, double *__restrict__ partials,
+                                              int *__restrict__ icount, double sx, double sy, double sz)
+{
+	extern __shared__ double s_tab[];
+	int ntab = 6 * nT * nT;
+	for (int k = threadIdx.x; k < ntab; k += blockDim.x) s_tab[k] = tab[k];
+	__syncthreads();
+
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	double ax = 0, ay = 0, az = 0, usum = 0;
+	int cnt = 0;
+	if (i < N) {
+		Particle pi = load_particle(pos + i);
+		int cx, cy, cz;
+		unpack_cell(pi.cell, cx, cy, cz);
+		int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
+		int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
+		for (int oz = -1; oz <= 1; oz++) {
+			int nz = cz + oz;
+			double Sz = 0;
+			if (nz < 0) { nz += g.nc[2]; Sz = -g.box[2]; }
+			if (nz >= g.nc[2]) { nz -= g.nc[2]; Sz = g.box[2]; }
+			int lz = nz - w2;
+			if (lz < 0 || lz >= d2) continue;
+			for (int oy = -1; oy <= 1; oy++) {
+				int ny = cy + oy;
+				double Sy = 0;
+				if (ny < 0) { ny += g.nc[1]; Sy = -g.box[1]; }
+				if (ny >= g.nc[1]) { ny -= g.nc[1]; Sy = g.box[1]; }
+				int ly = ny - w1;
+				if (ly < 0 || ly >= d1) continue;
+				for (int ox = -1; ox <= 1; ox++) {
+					int nx = cx + ox;
+					double Sx = 0;
+					if (nx < 0) { nx += g.nc[0]; Sx = -g.box[0]; }
+					if (nx >= g.nc[0]) { nx -= g.nc[0]; Sx = g.box[0]; }
+					int lx = nx - w0;
+					if (lx < 0 || lx >= d0) continue;
+					bool self = (ox == 0 && oy == 0 && oz == 0);
+					// forward offsets of cellOpt.h:715
+					bool fwd = (oz == 1) || (oz == 0 && (ox == 1 || (ox == 0 && oy == 1)));
+					if (MODE == PAIR_POTENTIAL || MODE == PAIR_DPOTENTIAL)
+						if (!self && !fwd) continue;
+					int c = lx + d0 * (ly + d1 * lz);
+					int jb = start[c], je = start[c + 1];
+					bool shifted = (Sx != 0) || (Sy != 0) || (Sz != 0);
+					// backward: the neighbour's cell is home and shifts US by the opposite image vector
+					double bx = pi.x - Sx, by = pi.y - Sy, bz = pi.z - Sz;
+					for (int j = jb; j < je; j++) {
+						if (self && j == i) continue;
+						Particle pj = load_particle(pos + j);
+						double dx, dy, dz;
+						if (!shifted || self) {
+							dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
+						} else if (fwd) {
+							dx = pi.x - (pj.x + Sx); dy = pi.y - (pj.y + Sy); dz = pi.z - (pj.z + Sz);
+						} else {
+							dx = -(pj.x - bx); dy = -(pj.y - by); dz = -(pj.z - bz);
+						}
+						double dr2 = dx * dx + dy * dy + dz * dz;
+						if (MODE == PAIR_COUNT) {
+							cnt += (dr2 < g.rc2);
+							continue;
+						}
+						// am I the reference's p1 (home cell; in the own cell the later-loaded = lower original index,
+						// i.e. the HIGHER slot because a cell's slots are sorted by descending original index)?
+						bool home = self ? (i > j) : fwd;
+						if (MODE == PAIR_POTENTIAL || MODE == PAIR_DPOTENTIAL)
+							if (!home) continue;
+						int t1 = home ? pi.type : pj.type, t2 = home ? pj.type : pi.type;
+						if (MODE == PAIR_FORCE) {
+							if (dr2 < g.rc2) {
+								double m = pair_force_mag(dr2, t1, t2, nT, s_tab, ntab);
+								ax += dx * m; ay += dy * m; az += dz * m;
+							}
+						} else if (MODE == PAIR_POTENTIAL) {
+							if (dr2 < g.rc2) usum += pair_potential_val(dr2, t1, t2, nT, s_tab);
+						} else {
+							// cellOpt.h:1097-1107 / :1161-1171: old - new with both (shifted) positions scaled
+							double uo = (dr2 < g.rc2) ? pair_potential_val(dr2, t1, t2, nT, s_tab) : 0.0;
+							double qx = pj.x, qy = pj.y, qz = pj.z;
+							if (shifted && !self) { qx += Sx; qy += Sy; qz += Sz; }
+							double ex = pi.x * sx - qx * sx, ey = pi.y * sy - qy * sy, ez = pi.z * sz - qz * sz;
+							double er2 = ex * ex + ey * ey + ez * ez;
+							double un = (er2 < g.rc2) ? pair_potential_val(er2, t1, t2, nT, s_tab) : 0.0;
+							usum += (uo - un);
+						}
+					}
+				}
+			}
+		}
+		if (MODE == PAIR_FORCE) {
+			acc[i] += ax; acc[cap + i] += ay; acc[2 * cap + i] += az;
+		}
+		if (MODE == PAIR_COUNT) icount[i] = cnt;
+	}
+	if (MODE == PAIR_POTENTIAL || MODE == PAIR_DPOTENTIAL) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+	if (MODE == PAIR_COUNT) {
+		double c = block_sum((double)cnt);
+		if (threadIdx.x == 0) partials[blockIdx.x] = c;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ bonded terms
+// minimum image per component with strict compares, system.h:1809-1817
+__device__ __forceinline__ void min_image(double &dx, double &dy, double &dz, const Geom &g)
+{
+	if (dx > g.box[0] / 2.0) dx -= g.box[0];
+	if (dx < -g.box[0] / 2.0) dx += g.box[0];
+	if (dy > g.box[1] / 2.0) dy -= g.box[1];
+	if (dy < -g.box[1] / 2.0) dy += g.box[1];
+	if (dz > g.box[2] / 2.0) dz -= g.box[2];
+	if (dz < -g.box[2] / 2.0) dz += g.box[2];
+}
+
+struct V3 { double x, y, z; };
+
+__device__ __forceinline__ V3 diff_mi(const Particle &a, const Particle &b, const Geom &g)
+{
+	V3 d = {a.x - b.x, a.y - b.y, a.z - b.z};
+	min_image(d.x, d.y, d.z, g);
+	return d;
+}
+
+// MD.h:384-403 harmonicF: returns f with a1 += f, a2 -= f
+__device__ __forceinline__ V3 harmonic_f(V3 d, double r0, double k)
+{
+	double dr = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+	double m = dr - r0;
+	m = -m * k / dr;
+	V3 f = {d.x * m, d.y * m, d.z * m};
+	return f;
+}
+
+// MD.h:422-431 harmonicP
+__device__ __forceinline__ double harmonic_p(V3 d, double r0, double k)
+{
+	double dr = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+	double u = dr - r0;
+	return 0.5 * k * u * u;
+}
+
+// MD.h:683-723 bendF: a1 += fa ; a2 += (fb - fa) ; a3 -= fb
+__device__ __forceinline__ void bend_f(V3 da, V3 db, double c0, double k, V3 &fa, V3 &fb)
+{
+	double dra = sqrt(da.x * da.x + da.y * da.y + da.z * da.z);
+	double drb = sqrt(db.x * db.x + db.y * db.y + db.z * db.z);
+	da.x /= dra; da.y /= dra; da.z /= dra;
+	db.x /= drb; db.y /= drb; db.z /= drb;
+	double ct = (da.x * db.x) + (da.y * db.y) + (da.z * db.z);
+	double m = c0 - ct;
+	m *= k;
+	fa.x = m * (db.x - (da.x * ct)) / dra; fb.x = m * (da.x - (db.x * ct)) / drb;
+	fa.y = m * (db.y - (da.y * ct)) / dra; fb.y = m * (da.y - (db.y * ct)) / drb;
+	fa.z = m * (db.z - (da.z * ct)) / dra; fb.z = m * (da.z - (db.z * ct)) / drb;
+}
+
+// MD.h:769-789 bendP
+__device__ __forceinline__ double bend_p(V3 da, V3 db, double c0, double k)
+{
+	double dra = sqrt(da.x * da.x + da.y * da.y + da.z * da.z);
+	double drb = sqrt(db.x * db.x + db.y * db.y + db.z * db.z);
+	da.x /= dra; da.y /= dra; da.z /= dra;
+	db.x /= drb; db.y /= drb; db.z /= drb;
+	double ct = (da.x * db.x) + (da.y * db.y) + (da.z * db.z);
+	double u = c0 - ct;
+	return k * u * u * 0.5;
+}
+
+__device__ __forceinline__ V3 scaled(V3 d, double sx, double sy, double sz)
+{
+	V3 r = {d.x * sx, d.y * sy, d.z * sz};
+	return r;
+}
+
+// CHAIN blocks, one thread per chain, same triplet order as Blob::doChainForce (system.h:1782-1866) /
+// doChainPotential (:2487-2568) / doChainDPotential (:3280-3384).  Chains are disjoint, so the force variant
+// updates acc[] without atomics; each particle's chain terms are summed in the reference's order.
+// MODE 0 force, 1 potential, 2 dPotential.
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_chain(int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                               ChainBlock cb, double *acc, double *partials, double sx, double sy, double sz)
+{
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0;
+	if (k < cb.nChains) {
+		int base = cb.start + k * cb.len;
+		int s1 = slot_of[base], s2 = slot_of[base + 1];
+		Particle p1 = load_particle(pos + s1), p2 = load_particle(pos + s2);
+		V3 a1 = {0, 0, 0}, a2 = {0, 0, 0};
+		for (int l = 0; l <= cb.len - 3; l++) {
+			bool tail = (l == cb.len - 3);
+			int s3 = slot_of[base + l + 2];
+			Particle p3 = load_particle(pos + s3);
+			V3 da = diff_mi(p1, p2, g), db = diff_mi(p2, p3, g);
+			V3 a3 = {0, 0, 0};
+			if (MODE == 0) {
+				V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
+				a1.x += f.x; a1.y += f.y; a1.z += f.z;
+				a2.x -= f.x; a2.y -= f.y; a2.z -= f.z;
+				if (tail) {
+					V3 f2 = harmonic_f(db, cb.c[0], cb.c[1]);
+					a2.x += f2.x; a2.y += f2.y; a2.z += f2.z;
+					a3.x -= f2.x; a3.y -= f2.y; a3.z -= f2.z;
+				}
+				V3 fa, fb;
+				bend_f(da, db, cb.c[2], cb.c[3], fa, fb);
+				a1.x += fa.x; a1.y += fa.y; a1.z += fa.z;
+				a2.x += (fb.x - fa.x); a2.y += (fb.y - fa.y); a2.z += (fb.z - fa.z);
+				a3.x -= fb.x; a3.y -= fb.y; a3.z -= fb.z;
+				// particle 1 of this triplet is complete
+				acc[s1] += a1.x; acc[cap + s1] += a1.y; acc[2 * cap + s1] += a1.z;
+				if (tail) {
+					acc[s2] += a2.x; acc[cap + s2] += a2.y; acc[2 * cap + s2] += a2.z;
+					acc[s3] += a3.x; acc[cap + s3] += a3.y; acc[2 * cap + s3] += a3.z;
+				}
+			} else if (MODE == 1) {
+				usum += harmonic_p(da, cb.c[0], cb.c[1]);
+				if (tail) usum += harmonic_p(db, cb.c[0], cb.c[1]);
+				usum += bend_p(da, db, cb.c[2], cb.c[3]);
+			} else {
+				double uo = harmonic_p(da, cb.c[0], cb.c[1]);
+				if (tail) uo += harmonic_p(db, cb.c[0], cb.c[1]);
+				uo += bend_p(da, db, cb.c[2], cb.c[3]);
+				V3 ea = scaled(da, sx, sy, sz), eb = scaled(db, sx, sy, sz);
+				double un = harmonic_p(ea, cb.c[0], cb.c[1]);
+				if (tail) un += harmonic_p(eb, cb.c[0], cb.c[1]);
+				un += bend_p(ea, eb, cb.c[2], cb.c[3]);
+				usum += (uo - un);
+			}
+			s1 = s2; s2 = s3; p1 = p2; p2 = p3; a1 = a2; a2 = a3;
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// explicit BOND list (system.h:1880-1934, :2717-2747, :3398-3435); one thread per bond, FP64 atomics for the force
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_bond(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                              const int *__restrict__ ij, double r0, double kk, double *acc, double *partials,
+                                              double sx, double sy, double sz)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0;
+	if (b < nb) {
+		int s1 = slot_of[ij[2 * b]], s2 = slot_of[ij[2 * b + 1]];
+		V3 d = diff_mi(load_particle(pos + s1), load_particle(pos + s2), g);
+		if (MODE == 0) {
+			V3 f = harmonic_f(d, r0, kk);
+			atomicAdd(acc + s1, f.x); atomicAdd(acc + cap + s1, f.y); atomicAdd(acc + 2 * cap + s1, f.z);
+			atomicAdd(acc + s2, -f.x); atomicAdd(acc + cap + s2, -f.y); atomicAdd(acc + 2 * cap + s2, -f.z);
+		} else if (MODE == 1) {
+			usum = harmonic_p(d, r0, kk);
+		} else {
+			double uo = harmonic_p(d, r0, kk);
+			usum = uo - harmonic_p(scaled(d, sx, sy, sz), r0, kk);
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// explicit BEND list (system.h:1975-2040, :2781-2822, :3476-3527)
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_bend(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                              const int *__restrict__ ijk, double c0, double kk, double *acc, double *partials,
+                                              double sx, double sy, double sz)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0;
+	if (b < nb) {
+		int s1 = slot_of[ijk[3 * b]], s2 = slot_of[ijk[3 * b + 1]], s3 = slot_of[ijk[3 * b + 2]];
+		Particle p2 = load_particle(pos + s2);
+		V3 da = diff_mi(load_particle(pos + s1), p2, g), db = diff_mi(p2, load_particle(pos + s3), g);
+		if (MODE == 0) {
+			V3 fa, fb;
+			bend_f(da, db, c0, kk, fa, fb);
+			atomicAdd(acc + s1, fa.x); atomicAdd(acc + cap + s1, fa.y); atomicAdd(acc + 2 * cap + s1, fa.z);
+			atomicAdd(acc + s2, fb.x - fa.x); atomicAdd(acc + cap + s2, fb.y - fa.y); atomicAdd(acc + 2 * cap + s2, fb.z - fa.z);
+			atomicAdd(acc + s3, -fb.x); atomicAdd(acc + cap + s3, -fb.y); atomicAdd(acc + 2 * cap + s3, -fb.z);
+		} else if (MODE == 1) {
+			usum = bend_p(da, db, c0, kk);
+		} else {
+			double uo = bend_p(da, db, c0, kk);
+			usum = uo - bend_p(scaled(da, sx, sy, sz), scaled(db, sx, sy, sz), c0, kk);
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ BEAD molecule
+// continuum-sphere bead terms, MD.h:165-382
+
+__device__ __forceinline__ double bead_mag(double dr2, const double *C, double cut2)
+{
+	double mag = 0;
+	double rminD = C[4] + C[5];
+	double rminD2 = rminD * rminD;
+	if (rminD2 <= dr2 && dr2 < cut2) {
+		double dr = sqrt(dr2);
+		double E = C[0] - dr, E2 = E * E, E3 = E * E2;
+		mag = 2.0 * (0.4 * E3 + C[1] * E2 + C[2] * E) / (dr);
+		mag += 4.0 * E2 + 8.0 * C[1] * E + 6.0 * C[2];
+		mag *= (E2 * C[3]) / (dr * dr);
+	} else if (dr2 < rminD2) {
+		double dr = sqrt(dr2);
+		double B = rminD - dr, B2 = B * B, B3 = B2 * B, B4 = B2 * B2;
+		mag = (B4 * C[6] + B3 * C[7] + B2 * C[8] + B * C[9] + C[10]) / (dr);
+		mag += (4.0 * B3 * C[6] + 3.0 * B2 * C[7] + 2.0 * B * C[8] + C[9]);
+		mag /= dr * dr;
+	}
+	return mag;
+}
+
+__device__ __forceinline__ double bead_pot(double dr2, const double *C, double cut2)
+{
+	double u = 0;
+	double rminD = C[4] + C[5];
+	double rminD2 = rminD * rminD;
+	if (rminD2 <= dr2 && dr2 < cut2) {
+		double dr = sqrt(dr2);
+		double E = C[0] - dr, E2 = E * E, E3 = E * E2;
+		u = 2.0 * E3 * (0.4 * E2 + C[1] * E + C[2]) * C[3] / (dr);
+	} else if (dr2 < rminD2) {
+		double dr = sqrt(dr2);
+		double B = rminD - dr, B2 = B * B, B3 = B2 * B, B4 = B2 * B2;
+		u = (B4 * C[6] + B3 * C[7] + B2 * C[8] + B * C[9] + C[10]) / (dr);
+	}
+	return u;
+}
+
+__device__ __forceinline__ double beadbead_mag(double dr2, const double *C, double cut2)
+{
+	const double *K = C + 11;   // BEADBEADOFFSET, MD.h:51
+	double mag = 0;
+	double rminD = K[0], rminD2 = rminD * rminD;
+	if (rminD2 <= dr2 && dr2 < cut2) {
+		double dr = sqrt(dr2);
+		double E = K[1] - dr, E2 = E * E, E3 = E * E2;
+		mag = E3 * (6.0 * K[2] * E2 + 5.0 * K[3] * E + 4.0 * K[4] + (K[2] * E3 + K[3] * E2 + K[4] * E) / dr) / (dr * dr);
+	} else if (dr2 < rminD2) {
+		double dr = sqrt(dr2);
+		double B = rminD - dr, B2 = B * B, B3 = B2 * B, B4 = B2 * B2, B5 = B2 * B3;
+		mag = 5.0 * B4 * K[5] + 4.0 * B3 * K[6] + 3.0 * B2 * K[7] + 2.0 * B * K[8] + K[9];
+		mag += (B5 * K[5] + B4 * K[6] + B3 * K[7] + B2 * K[8] + B * K[9] + K[10]) / (dr);
+		mag /= dr * dr;
+	}
+	return mag;
+}
+
+__device__ __forceinline__ double beadbead_pot(double dr2, const double *C, double cut2)
+{
+	const double *K = C + 11;
+	double u = 0;
+	double rminD = K[0], rminD2 = rminD * rminD;
+	if (rminD2 <= dr2 && dr2 < cut2) {
+		double dr = sqrt(dr2);
+		double E = K[1] - dr, E2 = E * E, E4 = E2 * E2;
+		u = E4 * (K[2] * E2 + K[3] * E + K[4]) / dr;
+	} else if (dr2 < rminD2) {
+		double dr = sqrt(dr2);
+		double B = rminD - dr, B2 = B * B, B3 = B2 * B, B4 = B2 * B2, B5 = B2 * B3;
+		u = (B5 * K[5] + B4 * K[6] + B3 * K[7] + B2 * K[8] + B * K[9] + K[10]) / (dr);
+	}
+	return u;
+}
+
+// bead-bead pairs of one BEAD molecule: j over own beads, k > j over the assembled list (system.h:2074-2098).
+// A handful of pairs: one block, thread per (j,k).
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_beadbead(int nOwn, int nAll, int cap, const Particle *__restrict__ pos,
+                                                  const int *__restrict__ slot_of, Geom g, int nT, const int *__restrict__ beads,
+                                                  const double *__restrict__ C, double R, double *acc, double *partials,
+                                                  double sx, double sy, double sz)
+{
+	double usum = 0;
+	for (int t = threadIdx.x; t < nOwn * nAll; t += blockDim.x) {
+		int j = t / nAll, k = t % nAll;
+		if (k <= j) continue;
+		int s1 = slot_of[beads[j]], s2 = slot_of[beads[k]];
+		Particle p1 = load_particle(pos + s1), p2 = load_particle(pos + s2);
+		V3 d = diff_mi(p1, p2, g);
+		double cut = R + R + 2.0;
+		cut *= cut;
+		const double *Cr = C + 22 * (p1.type * nT + p2.type);
+		double dr2 = d.x * d.x + d.y * d.y + d.z * d.z;
+		if (MODE == 0) {
+			double m = beadbead_mag(dr2, Cr, cut);
+			double fx = d.x * m, fy = d.y * m, fz = d.z * m;
+			atomicAdd(acc + s1, fx); atomicAdd(acc + cap + s1, fy); atomicAdd(acc + 2 * cap + s1, fz);
+			atomicAdd(acc + s2, -fx); atomicAdd(acc + cap + s2, -fy); atomicAdd(acc + 2 * cap + s2, -fz);
+		} else if (MODE == 1) {
+			usum += beadbead_pot(dr2, Cr, cut);
+		} else {
+			double uo = beadbead_pot(dr2, Cr, cut);
+			V3 e = scaled(d, sx, sy, sz);
+			usum += (uo - beadbead_pot(e.x * e.x + e.y * e.y + e.z * e.z, Cr, cut));
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[0] = usum;
+	}
+}
+
+// bead - particle terms: one thread per particle, loop over the molecule's own beads (system.h:2165-2210 brute-force
+// branch; the hash-cell branch :2105-2164 visits the same pairs).  excl_all: the force excludes every own bead when
+// nOwn <= 20 and only the bead itself otherwise; potential / dPotential always exclude only the bead itself (Q7).
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_bead(int N, int nOwn, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
+                                              const int *__restrict__ slot_of, Geom g, int nT, const int *__restrict__ beads,
+                                              const double *__restrict__ C, int excl_all, double *acc, double *partials,
+                                              double sx, double sy, double sz)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	bool live = s < N;
+	Particle p;
+	int id = -1;
+	if (live) { p = load_particle(pos + s); id = gid[s]; }
+	double cut2 = C[0] * C[0];   // (R + rc)^2 from row 0, system.h:2100-2101
+	double usum = 0;
+	double ax = 0, ay = 0, az = 0;
+	bool own = false;
+	if (live && excl_all)
+		for (int e = 0; e < nOwn; e++) own |= (beads[e] == id);
+	for (int j = 0; j < nOwn; j++) {
+		int bs = slot_of[beads[j]];
+		Particle pb = load_particle(pos + bs);
+		double fx = 0, fy = 0, fz = 0;
+		bool hit = false;
+		if (live && bs != s && !own) {
+			V3 d = diff_mi(pb, p, g);
+			double dr2 = d.x * d.x + d.y * d.y + d.z * d.z;
+			const double *Cr = C + 22 * (pb.type * nT + p.type);
+			if (MODE == 0) {
+				double m = bead_mag(dr2, Cr, cut2);
+				if (m != 0) {
+					fx = d.x * m; fy = d.y * m; fz = d.z * m;
+					ax -= fx; ay -= fy; az -= fz;
+					hit = true;
+				}
+			} else if (MODE == 1) {
+				usum += bead_pot(dr2, Cr, cut2);
+			} else {
+				double uo = bead_pot(dr2, Cr, cut2);
+				V3 e = scaled(d, sx, sy, sz);
+				usum += (uo - bead_pot(e.x * e.x + e.y * e.y + e.z * e.z, Cr, cut2));
+			}
+		}
+		if (MODE == 0) {
+			// reaction on the bead: reduce over the block only when somebody touched it
+			if (__syncthreads_or(hit)) {
+				double rx = block_sum(fx), ry = block_sum(fy), rz = block_sum(fz);
+				if (threadIdx.x == 0) { atomicAdd(acc + bs, rx); atomicAdd(acc + cap + bs, ry); atomicAdd(acc + 2 * cap + bs, rz); }
+			}
+		}
+	}
+	if (MODE == 0) {
+		if (live && (ax != 0 || ay != 0 || az != 0)) {
+			atomicAdd(acc + s, ax); atomicAdd(acc + cap + s, ay); atomicAdd(acc + 2 * cap + s, az);
+		}
+	} else {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// a[bead] /= 4 pi R^2 (MD.cpp:340-355, :480-494)
+__global__ void k_bead_mass(int n, int cap, const int *__restrict__ beads, const int *__restrict__ slot_of, double mass, double *acc)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	int s = slot_of[beads[j]];
+	acc[s] /= mass; acc[cap + s] /= mass; acc[2 * cap + s] /= mass;
+}
+
+// ------------------------------------------------------------------------------------------------ gather / scatter to original order
+__global__ void __launch_bounds__(TPB) k_export_particles(int N, int cap, const Particle *pos, const double *vel, const int *gid,
+                                                          double *xyz, int *type, double *v)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	int g = gid[s];
+	Particle p = load_particle(pos + s);
+	if (xyz) { xyz[3 * g] = p.x; xyz[3 * g + 1] = p.y; xyz[3 * g + 2] = p.z; }
+	if (type) type[g] = p.type;
+	if (v) { v[3 * g] = vel[s]; v[3 * g + 1] = vel[cap + s]; v[3 * g + 2] = vel[2 * cap + s]; }
+}
+
+__global__ void __launch_bounds__(TPB) k_export_soa3(int N, int cap, const double *a, const int *gid, double *out)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	int g = gid[s];
+	out[3 * g] = a[s]; out[3 * g + 1] = a[cap + s]; out[3 * g + 2] = a[2 * cap + s];
+}
+
+__global__ void __launch_bounds__(TPB) k_export_int(int N, const int *v, const int *gid, int *out)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	out[gid[s]] = v[s];
+}
+
+__global__ void __launch_bounds__(TPB) k_import_particles(int N, int cap, const double *xyz, const int *type, const double *v,
+                                                          Particle *pos, double *vel, double *unw, int *gid, int *slot_of)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	Particle p;
+	p.x = xyz[3 * s]; p.y = xyz[3 * s + 1]; p.z = xyz[3 * s + 2];
+	p.type = type[s];
+	p.cell = 0;
+	store_particle(pos + s, p);
+	vel[s] = v ? v[3 * s] : 0.0; vel[cap + s] = v ? v[3 * s + 1] : 0.0; vel[2 * cap + s] = v ? v[3 * s + 2] : 0.0;
+	if (unw) { unw[s] = p.x; unw[cap + s] = p.y; unw[2 * cap + s] = p.z; }
+	gid[s] = s;
+	slot_of[s] = s;
+}
+
+// reference cell key and rank inside the cell's list, per original index
+__global__ void __launch_bounds__(TPB) k_export_cells(int N, const Particle *pos, const int *gid,
+                                                      const int *start, const int *win, Geom g, int *key, int *rank)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	int cx, cy, cz;
+	unpack_cell(pos[s].cell, cx, cy, cz);
+	int id = gid[s];
+	key[id] = cx + cy * g.nc[0] + cz * g.nc[0] * g.nc[1];
+	int c = (cx - win[WIN_ORG]) + win[WIN_DIM] * ((cy - win[WIN_ORG + 1]) + win[WIN_DIM + 1] * (cz - win[WIN_ORG + 2]));
+	rank[id] = s - start[c];
+}
+
+} // namespace smd

@@ -1,0 +1,231 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against
+  (1) the golden vectors produced by the UNMODIFIED reference (tests/golden/*.npz), and
+  (2) the oracle (oracle/oracle.c) on the same seeded inputs.
+Tolerances are the north star's: forces <= 1e-5 relative, energies <= 1e-7 relative (FP64), cell / neighbour
+membership bit-exact.  In practice the pair terms are bit-identical and only the summation order differs, so the
+observed errors sit around 1e-14; the asserts below use the stated bounds with an extra tight check where the
+design promises more."""
+import numpy as np
+import pytest
+
+import softmold_b200 as sm
+from conftest import CASES, golden_path
+
+pytestmark = pytest.mark.gpu
+
+F_RTOL = 1e-5   # per-particle force, relative to max|F| of the term
+E_RTOL = 1e-7   # energies
+
+
+def rel_force_err(a, ref):
+    scale = np.abs(ref).max()
+    return np.abs(a - ref).max() / (scale if scale > 0 else 1.0)
+
+
+def close_energy(x, ref, scale=None):
+    s = max(abs(ref), abs(scale) if scale is not None else 0.0, 1e-300)
+    return abs(x - ref) / s
+
+
+@pytest.fixture(scope="module")
+def contexts(orc):
+    cache = {}
+
+    def get(case, **kw):
+        key = (case, tuple(sorted(kw.items())))
+        if key not in cache:
+            m, ref = orc.load_golden(golden_path(case))
+            cache[key] = (sm.Context.from_dict(m, **kw), m, ref)
+        return cache[key]
+
+    yield get
+    for ctx, _, _ in cache.values():
+        ctx.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cell_membership_bit_exact(contexts, case):
+    ctx, m, ref = contexts(case)
+    nc, key, rank = ctx.get_cell_ids()
+    assert list(nc) == list(ref["nCells_nFull"][:3])
+    assert np.array_equal(key, ref["cell_id"])                       # cellOpt.h:530-556
+    # list order of every cell = the reference's head-inserted linked list (descending index)
+    nxt = ref["cell_next"]
+    n = len(key)
+    expect_rank = np.zeros(n, np.int32)
+    heads = {}
+    for i in range(n):          # head of a cell = largest index in it
+        heads[key[i]] = i
+    for c, h in heads.items():
+        r, i = 0, h
+        while i != -1:
+            expect_rank[i] = r
+            r += 1
+            i = nxt[i]
+    assert np.array_equal(rank, expect_rank)
+    assert len(heads) == ref["nCells_nFull"][3]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_neighbour_membership_bit_exact(contexts, orc, case):
+    ctx, m, ref = contexts(case)
+    tot, per = ctx.count_pairs()
+    otot, oper = orc.pair_count(m["xyz"], m["type"], m["nTypes"], m["size"], m["cutoff"], per_particle=True)
+    assert tot == otot
+    assert np.array_equal(per, oper)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_pair_force_potential_dpotential(contexts, case):
+    ctx, m, ref = contexts(case)
+    ctx.compute_forces(mask=1 << sm.TERM_PAIR)
+    a = ctx.get_forces()
+    ra = ref["a_pair"].reshape(-1, 3)
+    err = rel_force_err(a, ra)
+    assert err <= F_RTOL
+    assert err <= 1e-12, err            # identical pair terms, only the summation order differs
+    U = ctx.potential()
+    assert close_energy(U[sm.TERM_PAIR], ref["U_pair"][0]) <= E_RTOL
+    assert close_energy(U[sm.TERM_PAIR], ref["U_pair"][0]) <= 1e-12
+    dU = ctx.dpotential(ref["scale"])
+    # dU is a sum of many cancelling terms: the natural scale is the potential it is a difference of
+    assert close_energy(dU[sm.TERM_PAIR], ref["dU_pair"][0]) <= 1e-7
+    assert abs(dU[sm.TERM_PAIR] - ref["dU_pair"][0]) <= 1e-12 * abs(ref["U_pair"][0]) + 1e-9 * abs(ref["dU_pair"][0])
+    assert close_energy(ctx.kinetic(), ref["kinetic"][0]) <= 1e-13
+
+
+TERM_OF = {sm.MOL_CHAIN: sm.TERM_CHAIN, sm.MOL_BOND: sm.TERM_BOND, sm.MOL_BEND: sm.TERM_BEND, sm.MOL_BEAD: sm.TERM_BEAD}
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_molecule_terms(contexts, case):
+    ctx, m, ref = contexts(case)
+    U, dU = ctx.potential(), ctx.dpotential(ref["scale"])
+    by_term_a, by_term_U, by_term_dU = {}, {}, {}
+    for k, mol in enumerate(m["molecules"]):
+        t = TERM_OF[mol["type"]]
+        by_term_a[t] = by_term_a.get(t, 0) + ref[f"a_mol{k}"].reshape(-1, 3)
+        by_term_U[t] = by_term_U.get(t, 0) + ref["U_mol"][k]
+        by_term_dU[t] = by_term_dU.get(t, 0) + ref["dU_mol"][k]
+    for t in by_term_a:
+        ctx.compute_forces(mask=1 << t)
+        a = ctx.get_forces()
+        err = rel_force_err(a, by_term_a[t])
+        assert err <= F_RTOL, (case, t, err)
+        assert err <= 1e-11, (case, t, err)
+        assert close_energy(U[t], by_term_U[t], scale=ref["U_pair"][0] * 1e-6) <= E_RTOL, (case, t, U[t], by_term_U[t])
+        assert abs(dU[t] - by_term_dU[t]) <= 1e-7 * max(abs(by_term_dU[t]), 1e-6 * abs(by_term_U[t]), 1e-12), (case, t)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_total_force_matches_oracle_with_philox_noise(contexts, orc, case):
+    """all terms + Langevin with the counter-based noise, against the oracle's restatement of the same spec"""
+    ctx, m, ref = contexts(case)
+    step = 12345
+    ctx.compute_forces(mask=sm.MASK_ALL, step=step)
+    a = ctx.get_forces()
+    S = orc.System(m, noise="philox")
+    S.init(step)
+    err = rel_force_err(a, S.acc)
+    assert err <= 1e-11, err
+
+
+def test_philox_uniforms_bit_exact(orc):
+    """a = -g v + sigma (2u-1) with v = 0 and only the Langevin term isolates the uniforms"""
+    n = 4096
+    rng = np.random.default_rng(3)
+    box = [40.0, 40.0, 40.0]
+    xyz = rng.random((n, 3)) * 40
+    typ = np.ones(n, np.int32)
+    gamma, dt, T, seed = 1.0, 0.02, 3.0, 0x123456789ABCDEF
+    ctx = sm.Context(n, 2, box, 2.0, dt, gamma, T, seed)
+    ctx.set_pair_tables(np.zeros(24), np.zeros(24))
+    ctx.set_particles(xyz, typ, np.zeros((n, 3)))
+    for step in (0, 7, 2 ** 33 + 5):
+        ctx.compute_forces(mask=sm.MASK_LANGEVIN, step=step)
+        a = ctx.get_forces()
+        u = orc.philox_uniforms(seed, step, n)
+        sigma = np.sqrt((6.0 * T * gamma) / dt)
+        expect = -gamma * 0.0 + sigma * (2.0 * u - 1.0)
+        assert np.array_equal(a, expect)
+    ctx.close()
+    # sanity of the stream itself
+    u = orc.philox_uniforms(seed, 1, 200000)
+    assert abs(u.mean() - 0.5) < 2e-3 and abs(u.var() - 1 / 12) < 1e-3 and u.min() >= 0 and u.max() < 1
+
+
+@pytest.mark.parametrize("case", ["lipo_t0", "lipo_eq", "bilayer_t0", "bilayer_eq", "bead1", "bead2"])
+def test_trajectory_matches_reference_md(contexts, orc, case):
+    """The whole loop of MD.cpp for K steps against the state the reference `MD` executable wrote (one thread):
+    Langevin noise = the reference's MT19937 stream fed through smd_set_noise, MC box moves with tension driven by
+    the reference's second MT19937 stream, bead mass quirk, restart path."""
+    m, ref = orc.load_golden(golden_path(case))
+    ctx = sm.Context.from_dict(m, noise=sm.NOISE_EXTERNAL)
+    n, K = m["nParticles"], int(ref["traj_steps"])
+    lang = orc.mt_rand53(m["seed"], 3 * n * (K + 2)).reshape(-1, n, 3)
+    mc = orc.mt_rand53(m["seed"], 2 * (K // 8 + 2))
+    start = int(m["initialTime"] / m["deltaT"] + 1e-7)
+    draw = 0
+    ctx.set_noise(lang[draw]); draw += 1
+    ctx.compute_forces(mask=sm.MASK_ALL, step=start)
+    if m["initialTime"] != 0:
+        ctx.resume()
+    trials = 0
+    for i in range(start, start + K):
+        ctx.step_begin(i)
+        ctx.set_noise(lang[draw]); draw += 1
+        ctx.step_end(i)
+        if i % 8 == 0 and i != 0 and m.get("deltaLXY", 0) != 0:
+            ctx.mc_box_move(m["deltaLXY"], m.get("tension", 0.0), mc[2 * trials], mc[2 * trials + 1])
+            trials += 1
+    ctx.step_begin(start + K)
+    xyz, _, vel = ctx.get_particles()
+    box = ctx.get_box()
+    ctx.close()
+    np.testing.assert_allclose(box, ref["traj_box"], rtol=1e-13)
+    # 15 significant digits of text in the reference's file + chaotic growth of the 1e-16 summation-order noise
+    assert np.abs(xyz - ref["traj_xyz"]).max() <= 1e-9
+    assert np.abs(vel - ref["traj_vel"]).max() <= 1e-8
+
+
+def test_trajectory_vs_oracle_philox_long(orc):
+    """100 steps with the product's own noise against the oracle running the same Philox spec"""
+    m, _ = orc.load_golden(golden_path("bilayer_eq"))
+    ctx = sm.Context.from_dict(m)
+    S = orc.System(m, noise="philox")
+    start = 0
+    m["initialTime"] = 0.0
+    S.init(start)
+    ctx.compute_forces(mask=sm.MASK_ALL, step=start)
+    K = 100
+    ctx.step(start, K)
+    for i in range(start, start + K):
+        S.s.deltaLXY = 0.0
+        S.step(i)
+    xyz, _, vel = ctx.get_particles()
+    assert np.abs(xyz - S.xyz).max() <= 1e-7
+    assert np.abs(vel - S.vel).max() <= 1e-6
+    launches, rebuilds = ctx.stats()
+    assert rebuilds >= K and launches > 0
+    ctx.close()
+
+
+def test_errors_are_loud(orc):
+    m, _ = orc.load_golden(golden_path("lipo_t0"))
+    bad = dict(m)
+    bad["xyz"] = m["xyz"].copy()
+    bad["xyz"][5, 0] = 401.0
+    with pytest.raises(sm.SoftMoldError, match="X position of particle 5 is out of bounds"):
+        sm.Context.from_dict(bad)
+    ctx = sm.Context.from_dict(m)
+    with pytest.raises(sm.SoftMoldError):
+        ctx.add_molecule(sm.MOL_BOND, np.array([[0, 10 ** 6]], np.int32), [1.0, 1.0])
+    # blow the system up: a huge velocity carries a particle across many cells in one step
+    xyz, typ, vel = ctx.get_particles()
+    vel[0] = [5000.0, 0, 0]
+    ctx.set_particles(xyz, typ, vel)
+    ctx.compute_forces()
+    ctx.step(0, 2)
+    with pytest.raises(sm.SoftMoldError, match="cell"):
+        ctx.synchronize()
+    ctx.close()
