@@ -100,7 +100,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->cap = ((std::max(ctx->N, 1) + 255) / 256) * 256;
 	ctx->temperature = desc->temperature;
 	ctx->device = desc->device;
-	ctx->cur = 0; ctx->wdata = 0; ctx->wnext = 0;
+	ctx->cur = 0;
 	ctx->cells_valid = false;
 	ctx->tables_set = ctx->particles_set = false;
 	ctx->noise_ready = false;
@@ -129,9 +129,9 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 		CKC(cudaMalloc(&ctx->gid[b], cap * sizeof(int)));
 		ctx->unw[b] = nullptr;
 		if (desc->track_unwrapped) CKC(cudaMalloc(&ctx->unw[b], 3 * cap * sizeof(double)));
-		CKC(cudaMalloc(&ctx->win[b], WIN_WORDS * sizeof(int)));
-		CKC(cudaMemset(ctx->win[b], 0, WIN_WORDS * sizeof(int)));
 	}
+	CKC(cudaMalloc(&ctx->win, WIN_WORDS * sizeof(int)));
+	CKC(cudaMemset(ctx->win, 0, WIN_WORDS * sizeof(int)));
 	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
 	CKC(cudaMemset(ctx->acc, 0, 3 * cap * sizeof(double)));
 	CKC(cudaMalloc(&ctx->acc2, 3 * cap * sizeof(double)));
@@ -176,9 +176,9 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for (int b = 0; b < 2; b++) {
-		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]); cudaFree(ctx->win[b]);
+		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]);
 	}
-	cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
+	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
 	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
 	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
 	cudaFree(ctx->icount); cudaFree(ctx->stage); cudaFree(ctx->istage);
@@ -201,7 +201,6 @@ static int check_device_errors(smd_ctx *ctx)
 	if (flag) {
 		ctx->err = "device-side cell error:";
 		if (flag & ERR_OUT_OF_BOX) ctx->err += " particle outside the box or NaN position (reference: 'cell placement is on boundary', cellOpt.h:541-552)";
-		if (flag & ERR_WINDOW) ctx->err += " particle moved more than one cell in a step";
 		if (flag & ERR_WINDOW_CAP) ctx->err += " occupied cell window exceeds the offset-table capacity";
 		return SMD_ERR_CELL;
 	}
@@ -228,11 +227,11 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 	return SMD_OK;
 }
 
-// recompute the occupied-cell window from scratch (after set_particles or a box move)
-static int refresh_window(smd_ctx *ctx)
+// tag every particle with its cell and accumulate the occupied bounding box (after set_particles / a box move;
+// the steady state does this inside k_verlet_first)
+static int retag_cells(smd_ctx *ctx)
 {
-	LAUNCH(k_bbox, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], ctx->geom, ctx->bbox, ctx->errflag);
-	LAUNCH(k_window_init, 1, 1, 0, ctx->bbox, ctx->win[ctx->wnext], ctx->geom, ctx->cellcap, ctx->errflag);
+	LAUNCH(k_tag_cells, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], ctx->geom, ctx->bbox, ctx->errflag);
 	ctx->cells_valid = false;
 	return SMD_OK;
 }
@@ -265,7 +264,7 @@ extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t 
 	       ctx->unw[0], ctx->gid[0], ctx->slot_of);
 	CK(cudaMemsetAsync(ctx->acc, 0, 3 * (size_t)ctx->cap * sizeof(double), ctx->stream));
 	ctx->acc_live = false;
-	refresh_window(ctx);
+	retag_cells(ctx);
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->particles_set = true;
 	ctx->noise_ready = false;
@@ -411,28 +410,24 @@ extern "C" int smd_set_noise(smd_ctx *ctx, const double *u)
 static int build_cells(smd_ctx *ctx)
 {
 	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1;
-	// bin into the window derived by the previous build (or by refresh_window); k_scan2 derives the next one
-	int w = ctx->wnext;
-	int *win = ctx->win[w], *win_next = ctx->win[w ^ 1];
-	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, N, ctx->pos[cur], ctx->geom, win, ctx->count, ctx->cellOfSlot, ctx->bbox, ctx->errflag);
-	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, win, ctx->blockSums);
-	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, win_next, ctx->geom, ctx->cellcap, ctx->errflag);
-	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, win, ctx->blockSums, ctx->start, ctx->cursor, N);
+	// particles were tagged with their cell (and bbox[] accumulated) by whoever moved them last
+	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, N, ctx->pos[cur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot);
+	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
+	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, ctx->win, ctx->geom, ctx->cellcap, ctx->errflag);
+	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N);
 	LAUNCH(k_place, nblk(N, TPB), TPB, 0, N, ctx->cellOfSlot, ctx->cursor, ctx->order);
 	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[cur], ctx->pos[nxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
 	       ctx->gid[nxt], ctx->slot_of);
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
-	ctx->wdata = w;
-	ctx->wnext = w ^ 1;
 	ctx->cells_valid = true;
 	ctx->rebuilds++;
 	return SMD_OK;
 }
 
 // the window the CURRENT sorted order / start[] refer to
-static inline int *cur_win(smd_ctx *ctx) { return ctx->win[ctx->wdata]; }
+static inline int *cur_win(smd_ctx *ctx) { return ctx->win; }
 
 extern "C" int smd_build_cells(smd_ctx *ctx)
 {
@@ -554,7 +549,7 @@ extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
 	int N = ctx->N;
 	bead_mass_divide(ctx);                                                         // MD.cpp:340-355
 	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
-	       ctx->desc.dt);                                                          // MD.cpp:356
+	       ctx->desc.dt, ctx->bbox, ctx->errflag);                                 // MD.cpp:356
 	LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);                  // MD.cpp:357-366
 	ctx->acc_live = false;
 	ctx->cells_valid = false;
@@ -714,7 +709,7 @@ extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new
 	if (!rc && total > ctx->cellcap) { ctx->err = "box grew beyond the cell-table capacity"; rc = SMD_ERR_UNSUPPORTED; }
 	if (rc) { ctx->geom = old; return rc; }
 	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], scale[0], scale[1], scale[2]);
-	refresh_window(ctx);
+	retag_cells(ctx);
 	return SMD_OK;
 }
 

@@ -32,11 +32,11 @@ struct Geom {
 	double rc2;     // cutoff^2
 };
 
-// device-resident active window of the cell grid: the bounding box of occupied cells dilated by one cell.
+// device-resident active window of the cell grid: the bounding box of occupied cells plus one cell each side.
 // win[0..2] origin, win[3..5] extent, win[6] number of cells in the window.
 enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_WORDS = 8 };
 
-enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW = 2, ERR_WINDOW_CAP = 4, ERR_NAN = 8 };
+enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW_CAP = 4 };
 
 struct ChainBlock { int start, nChains, len; double c[4]; };
 struct BondList { int n; int *d_ij; double c[2]; };
@@ -77,8 +77,7 @@ struct smd_ctx {
 	long long cellcap;
 	int *count, *start, *cursor, *blockSums;
 	int *cellOfSlot, *order;
-	int *win[2];      // window descriptors (device), ping-pong
-	int wdata, wnext; // window start[] refers to / window the next build bins into
+	int *win;         // window descriptor of the current sorted order (device)
 	int *bbox;        // [6] min xyz, max xyz accumulators
 	int *errflag;
 	bool cells_valid;  // sorted order + start[] describe the current positions

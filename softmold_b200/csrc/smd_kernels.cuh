@@ -89,29 +89,38 @@ __device__ __forceinline__ void philox_uniform3(uint64_t seed, uint64_t step, ui
 // ------------------------------------------------------------------------------------------------ integrator
 // Verlet::first, algorithms/verlet.h:288-356: v += a*dt/2 ; p += v*dt ; aP += v*dt (type != 0 only) ; wrap with
 // strict > L and < 0 for every particle.  In place, slot order.
+// It also does the first half of CellOpt::build for the new positions (cellOpt.h:530-556): the cell coordinates of
+// the reference grid are packed into the record and the bounding box of occupied cells is accumulated for the
+// counting sort that follows (tag_cell below).
+__device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, int *errflag, bool live);
+
 __global__ void __launch_bounds__(TPB) k_verlet_first(int N, int cap, Particle *pos, double *vel, const double *acc, double *unw,
-                                                      Geom g, double dt)
+                                                      Geom g, double dt, int *bbox, int *errflag)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= N) return;
-	Particle p = load_particle(pos + s);
-	double h = 0.5 * dt;
-	if (p.type != 0) {
-		double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
-		vx += (acc[s] * h); vy += (acc[cap + s] * h); vz += (acc[2 * cap + s] * h);
-		vel[s] = vx; vel[cap + s] = vy; vel[2 * cap + s] = vz;
-		p.x += vx * dt; p.y += vy * dt; p.z += vz * dt;
-		if (unw) {
-			unw[s] += vx * dt; unw[cap + s] += vy * dt; unw[2 * cap + s] += vz * dt;
+	bool live = s < N;
+	Particle p;
+	if (live) {
+		p = load_particle(pos + s);
+		double h = 0.5 * dt;
+		if (p.type != 0) {
+			double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
+			vx += (acc[s] * h); vy += (acc[cap + s] * h); vz += (acc[2 * cap + s] * h);
+			vel[s] = vx; vel[cap + s] = vy; vel[2 * cap + s] = vz;
+			p.x += vx * dt; p.y += vy * dt; p.z += vz * dt;
+			if (unw) {
+				unw[s] += vx * dt; unw[cap + s] += vy * dt; unw[2 * cap + s] += vz * dt;
+			}
 		}
+		if (p.x > g.box[0]) p.x -= g.box[0];
+		if (p.x < 0) p.x += g.box[0];
+		if (p.y > g.box[1]) p.y -= g.box[1];
+		if (p.y < 0) p.y += g.box[1];
+		if (p.z > g.box[2]) p.z -= g.box[2];
+		if (p.z < 0) p.z += g.box[2];
 	}
-	if (p.x > g.box[0]) p.x -= g.box[0];
-	if (p.x < 0) p.x += g.box[0];
-	if (p.y > g.box[1]) p.y -= g.box[1];
-	if (p.y < 0) p.y += g.box[1];
-	if (p.z > g.box[2]) p.z -= g.box[2];
-	if (p.z < 0) p.z += g.box[2];
-	store_particle(pos + s, p);
+	tag_cell(p, g, bbox, errflag, live);
+	if (live) store_particle(pos + s, p);
 }
 
 // Verlet::second, algorithms/verlet.h:463-477
@@ -199,17 +208,19 @@ __device__ __forceinline__ bool cell_coords(const Particle &p, const Geom &g, in
 	       p.x == p.x && p.y == p.y && p.z == p.z;
 }
 
-// bounding box of occupied cells (used after set_particles / a box move; steady state tracks it inside k_bin)
-__global__ void __launch_bounds__(TPB) k_bbox(int N, const Particle *pos, Geom g, int *bbox, int *errflag)
+// cell coordinates of p in the reference grid -> packed into the record; bounding box of occupied cells -> bbox[6]
+// (warp-reduced, then one atomicMin/Max per warp).  Must be called by all 32 lanes.
+__device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, int *errflag, bool live)
 {
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
-	if (s < N) {
-		Particle p = load_particle(pos + s);
+	if (live) {
 		int c[3];
-		if (!cell_coords(p, g, c[0], c[1], c[2])) atomicOr(errflag, ERR_OUT_OF_BOX);
-		else
-			for (int d = 0; d < 3; d++) { lo[d] = c[d]; hi[d] = c[d]; }
+		if (!cell_coords(p, g, c[0], c[1], c[2])) {
+			atomicOr(errflag, ERR_OUT_OF_BOX);
+			for (int d = 0; d < 3; d++) c[d] = min(max(c[d], 0), g.nc[d] - 1);
+		}
+		for (int d = 0; d < 3; d++) lo[d] = hi[d] = c[d];
+		p.cell = pack_cell(c[0], c[1], c[2]);
 	}
 	for (int d = 0; d < 3; d++) {
 		int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
@@ -217,56 +228,52 @@ __global__ void __launch_bounds__(TPB) k_bbox(int N, const Particle *pos, Geom g
 	}
 }
 
-// window = bbox dilated by one cell, clamped to the grid; resets the accumulators
-__device__ __forceinline__ void window_from_bbox(int *bbox, int *win, const Geom &g, long long cellcap, int *errflag)
+// stand-alone tagging pass (after set_particles / a box move; the steady state does it inside k_verlet_first)
+__global__ void __launch_bounds__(TPB) k_tag_cells(int N, Particle *pos, Geom g, int *bbox, int *errflag)
 {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	bool live = s < N;
+	Particle p;
+	if (live) p = load_particle(pos + s);
+	tag_cell(p, g, bbox, errflag, live);
+	if (live) store_particle(pos + s, p);
+}
+
+// The offset table covers only the occupied window of the reference grid: the exact bounding box of the cells
+// tagged above, plus one empty cell on each side so that stencil look-ups of boundary cells stay inside the table.
+// Every kernel of the build derives it from bbox[] with this one function; k_scan2 publishes it in win[] for the
+// kernels that run after the build and re-arms bbox[].
+struct Window { int org[3], dim[3]; int ncells; };
+
+__device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long long cellcap)
+{
+	Window w;
 	long long n = 1;
 	for (int d = 0; d < 3; d++) {
 		int lo = bbox[d], hi = bbox[3 + d];
 		if (lo == INT_MAX) { lo = 0; hi = 0; }
 		lo = max(lo - 1, 0);
 		hi = min(hi + 1, g.nc[d] - 1);
-		win[WIN_ORG + d] = lo;
-		win[WIN_DIM + d] = hi - lo + 1;
-		n *= (hi - lo + 1);
-		bbox[d] = INT_MAX; bbox[3 + d] = INT_MIN;
+		w.org[d] = lo;
+		w.dim[d] = hi - lo + 1;
+		n *= w.dim[d];
 	}
-	if (n > cellcap) { atomicOr(errflag, ERR_WINDOW_CAP); n = 0; }
-	win[WIN_NCELLS] = (int)n;
+	w.ncells = (n > cellcap) ? 0 : (int)n;   // over capacity: flagged by k_scan2, nothing is binned
+	return w;
 }
 
-__global__ void k_window_init(int *bbox, int *win, Geom g, long long cellcap, int *errflag)
-{
-	window_from_bbox(bbox, win, g, cellcap, errflag);
-}
-
-// pass 1 of the counting sort: key of every particle, histogram over the window, bbox for the next window.
-// Warp-aggregated: lanes sharing a cell elect a leader that issues one atomicAdd for the group.
-__global__ void __launch_bounds__(TPB) k_bin(int N, Particle *pos, Geom g, const int *win, int *count, int *cellOfSlot, int *bbox,
-                                             int *errflag)
+// pass 1 of the counting sort: histogram over the window.  Warp-aggregated: lanes sharing a cell elect a leader
+// that issues one atomicAdd for the group.
+__global__ void __launch_bounds__(TPB) k_bin(int N, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
+                                             int *cellOfSlot)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+	Window w = window_of(bbox, g, cellcap);
 	int local = -1;
-	if (s < N) {
-		Particle p = load_particle(pos + s);
-		int c[3];
-		bool ok = cell_coords(p, g, c[0], c[1], c[2]);
-		if (!ok) {
-			atomicOr(errflag, ERR_OUT_OF_BOX);
-			for (int d = 0; d < 3; d++) c[d] = min(max(c[d], 0), g.nc[d] - 1);
-		}
-		int l[3];
-		bool inside = true;
-		for (int d = 0; d < 3; d++) {
-			l[d] = c[d] - win[WIN_ORG + d];
-			if (l[d] < 0 || l[d] >= win[WIN_DIM + d]) { inside = false; l[d] = min(max(l[d], 0), win[WIN_DIM + d] - 1); }
-			lo[d] = hi[d] = c[d];
-		}
-		if (!inside) atomicOr(errflag, ERR_WINDOW);
-		local = l[0] + win[WIN_DIM] * (l[1] + win[WIN_DIM + 1] * l[2]);
-		p.cell = pack_cell(c[0], c[1], c[2]);
-		store_particle(pos + s, p);
+	if (s < N && w.ncells > 0) {
+		int cx, cy, cz;
+		unpack_cell(pos[s].cell, cx, cy, cz);
+		local = (cx - w.org[0]) + w.dim[0] * ((cy - w.org[1]) + w.dim[1] * (cz - w.org[2]));
 		cellOfSlot[s] = local;
 	}
 	unsigned active = __ballot_sync(0xffffffffu, local >= 0);
@@ -274,10 +281,6 @@ __global__ void __launch_bounds__(TPB) k_bin(int N, Particle *pos, Geom g, const
 		unsigned peers = __match_any_sync(active, local);
 		int leader = __ffs(peers) - 1;
 		if ((int)(threadIdx.x & 31) == leader) atomicAdd(count + local, __popc(peers));
-	}
-	for (int d = 0; d < 3; d++) {
-		int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
-		if ((threadIdx.x & 31) == 0 && l != INT_MAX) { atomicMin(bbox + d, l); atomicMax(bbox + 3 + d, h); }
 	}
 }
 
@@ -291,10 +294,10 @@ __device__ __forceinline__ void scan_chunk(int ncells, int &b0, int &b1)
 	b1 = (int)min(a + chunk, (long long)ncells);
 }
 
-__global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int *win, int *blockSums)
+__global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int *bbox, Geom g, long long cellcap, int *blockSums)
 {
 	int b0, b1;
-	scan_chunk(win[WIN_NCELLS], b0, b1);
+	scan_chunk(window_of(bbox, g, cellcap).ncells, b0, b1);
 	int sum = 0;
 	for (int i = b0 + threadIdx.x; i < b1; i += SCAN_TPB) sum += count[i];
 	__shared__ int sh[SCAN_TPB / 32];
@@ -308,9 +311,8 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int 
 	}
 }
 
-// single block: exclusive scan of the block sums; thread 0 also derives the NEXT step's window from the bbox
-// accumulated by k_bin (particles move less than one cell per step, so bbox +- 1 cell contains them next step)
-__global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox, int *win_next, Geom g, long long cellcap, int *errflag)
+// single block: exclusive scan of the block sums; thread 0 publishes the window and re-arms the bbox accumulators
+__global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox, int *win, Geom g, long long cellcap, int *errflag)
 {
 	__shared__ int sh[SCAN_BLOCKS];
 	int v = blockSums[threadIdx.x];
@@ -323,7 +325,13 @@ __global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox
 		__syncthreads();
 	}
 	blockSums[threadIdx.x] = sh[threadIdx.x] - v;
-	if (threadIdx.x == 0) window_from_bbox(bbox, win_next, g, cellcap, errflag);
+	if (threadIdx.x == 0) {
+		Window w = window_of(bbox, g, cellcap);
+		for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = w.org[d]; win[WIN_DIM + d] = w.dim[d]; }
+		win[WIN_NCELLS] = w.ncells;
+		if (w.ncells == 0) atomicOr(errflag, ERR_WINDOW_CAP);
+		for (int d = 0; d < 3; d++) { bbox[d] = INT_MAX; bbox[3 + d] = INT_MIN; }
+	}
 }
 
 __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *win, const int *blockSums, int *start, int *cursor, int N)

@@ -220,12 +220,19 @@ def test_errors_are_loud(orc):
     ctx = sm.Context.from_dict(m)
     with pytest.raises(sm.SoftMoldError):
         ctx.add_molecule(sm.MOL_BOND, np.array([[0, 10 ** 6]], np.int32), [1.0, 1.0])
-    # blow the system up: a huge velocity carries a particle across many cells in one step
+    # a particle crossing many cells in one step is fine (cells are rebuilt from scratch, as in the reference) ...
     xyz, typ, vel = ctx.get_particles()
-    vel[0] = [5000.0, 0, 0]
+    vel[0] = [3000.0, 0, 0]
+    ctx.set_particles(xyz, typ, vel)
+    ctx.compute_forces()
+    ctx.step(0, 1)
+    ctx.synchronize()
+    # ... but one that leaves the box even after the single wrap of Verlet::first makes the reference index out of
+    # bounds (cellOpt.h:541-552); here it is a loud error
+    vel[0] = [1e5, 0, 0]
     ctx.set_particles(xyz, typ, vel)
     ctx.compute_forces()
     ctx.step(0, 2)
-    with pytest.raises(sm.SoftMoldError, match="cell"):
+    with pytest.raises(sm.SoftMoldError, match="outside the box"):
         ctx.synchronize()
     ctx.close()
