@@ -188,6 +188,26 @@ int smd_stream(smd_ctx *ctx, void **stream);
 /* counters: kernels launched since creation, cell rebuilds */
 int smd_stats(smd_ctx *ctx, int64_t *kernel_launches, int64_t *rebuilds);
 
+/* Per-phase device timing with CUDA events recorded on the context's stream around the kernels of each phase of
+ * the timestep (the reference only prints wall seconds per measure interval, MD.cpp:527-532).
+ * smd_profile(ctx, mask): bit p enables phase p; 0 disables; accumulators are reset.
+ * smd_profile_read synchronises and returns accumulated milliseconds and bracket counts per phase. */
+enum { SMD_PHASE_INTEGRATE1 = 0,  /* bead mass, Verlet::first (+ cell tagging), a = 0   MD.cpp:340-366 */
+       SMD_PHASE_BUILD = 1,       /* CellOpt::build                                     MD.cpp:412     */
+       SMD_PHASE_PAIR = 2,        /* CellOpt::computeForce                              MD.cpp:413     */
+       SMD_PHASE_MOLECULES = 3,   /* Blob::do*Force                                     MD.cpp:414-509 */
+       SMD_PHASE_LANGEVIN = 4,    /* Langevin::compute                                  MD.cpp:410     */
+       SMD_PHASE_INTEGRATE2 = 5,  /* Verlet::second                                     MD.cpp:511     */
+       SMD_PHASE_STEP = 6,        /* one whole smd_step_begin + smd_step_end                           */
+       SMD_NPHASES = 8 };
+int smd_profile(smd_ctx *ctx, uint32_t phase_mask);
+int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPHASES]);
+
+/* FP64 pipe peak of the context's device in TFLOP/s, measured with a dependency-chain micro-kernel: with fused
+ * multiply-add, and with separate multiply + add (what this library issues: it is compiled without contraction to
+ * stay bit-exact with the reference's x86-64 build).  Roofline denominator for the pair kernel. */
+int smd_fp64_peak(smd_ctx *ctx, double *fma_tflops, double *muladd_tflops);
+
 /* ------------------------------------------------------------------ host-side file boundary (no GPU needed)
  * `.mpd` reader / writer with the semantics of Script<T,Blob>::read/write + Blob::input/output
  * (include/fileFormats/scriptFormat.h:64-95, include/system.h:589-1749). */

@@ -173,13 +173,43 @@ static int cmd_mt(int argc, char **argv)
 	return 0;
 }
 
-// phases: time the reference's own Verlet / Langevin / CellOpt / do*Force in MD.cpp:335-511 order,
-// no file I/O, for <nsteps> steps. Prints one line: N nsteps seconds threads.
+// phases: time the reference's own Verlet / Langevin / CellOpt / do*Force in MD.cpp:335-511 order, no file I/O.
+//   ref_harness phases name nsteps [warmup_reps timed_reps]
+// Each rep is <nsteps> MD iterations.  Prints one line per timed rep: N nsteps seconds threads.
+static void molecule_forces(Blob<double> &S)
+{
+	// the molecule switch of MD.cpp:414-478 for the molecule kinds on the hot path
+	for (int k = 0; k < S.readNMolecules(); k++) {
+		int t = S.getMolecule()[k].readType();
+		if (t == CHAIN) S.doChainForce(k);
+		else if (t == BOND) S.doBondForce(k);
+		else if (t == BEND) S.doBendForce(k);
+		else if (t == BEAD) S.doBeadForce(k);
+	}
+}
+
+static void bead_mass(Blob<double> &S)
+{
+	// MD.cpp:340-355 / :480-494
+	threeVector<double> *acc = S.getAccelerations();
+	for (int k = 0; k < S.readNMolecules(); k++) {
+		molecule<double, fourVector<int> > &m = S.getMolecule()[k];
+		if (m.readType() != BEAD) continue;
+		double r = m.getConstants()[BEADRADIUS];
+		double mass = 4.0 * M_PI * r * r;
+		for (int j = 0; j < m.readNBond(); j++) {
+			int idx = m.getBonds()[j].s[0];
+			acc[idx].x /= mass; acc[idx].y /= mass; acc[idx].z /= mass;
+		}
+	}
+}
+
 static int cmd_phases(int argc, char **argv)
 {
-	if (argc < 4) { fprintf(stderr, "usage: ref_harness phases name nsteps\n"); return 2; }
+	if (argc < 4) { fprintf(stderr, "usage: ref_harness phases name nsteps [warmup_reps timed_reps]\n"); return 2; }
 	const char *name = argv[2];
 	int nsteps = atoi(argv[3]);
+	int warm = argc > 4 ? atoi(argv[4]) : 0, reps = argc > 5 ? atoi(argv[5]) : 1;
 	Blob<double> S;
 	Script<double, Blob<double> > io(name, std::ios::in, &S);
 	io.read();
@@ -197,25 +227,23 @@ static int cmd_phases(int argc, char **argv)
 	pair.build();
 	pair.computeForce();
 	thermostat.compute(S.readInitialTemp());
-	for (int k = 0; k < S.readNMolecules(); k++)
-		if (S.getMolecule()[k].readType() == CHAIN) S.doChainForce(k);
-		else if (S.getMolecule()[k].readType() == BOND) S.doBondForce(k);
-		else if (S.getMolecule()[k].readType() == BEND) S.doBendForce(k);
-	double t0 = omp_get_wtime();
-	for (int i = 0; i < nsteps; i++) {
-		integrate.first();
-		for (int k = 0; k < n; k++) { acc[k].x = 0; acc[k].y = 0; acc[k].z = 0; }
-		thermostat.compute(S.readInitialTemp());
-		pair.build();
-		pair.computeForce();
-		for (int k = 0; k < S.readNMolecules(); k++)
-			if (S.getMolecule()[k].readType() == CHAIN) S.doChainForce(k);
-			else if (S.getMolecule()[k].readType() == BOND) S.doBondForce(k);
-			else if (S.getMolecule()[k].readType() == BEND) S.doBendForce(k);
-		integrate.second();
+	molecule_forces(S);
+	for (int rep = 0; rep < warm + reps; rep++) {
+		double t0 = omp_get_wtime();
+		for (int i = 0; i < nsteps; i++) {
+			bead_mass(S);
+			integrate.first();
+			for (int k = 0; k < n; k++) { acc[k].x = 0; acc[k].y = 0; acc[k].z = 0; }
+			thermostat.compute(S.readInitialTemp());
+			pair.build();
+			pair.computeForce();
+			molecule_forces(S);
+			bead_mass(S);
+			integrate.second();
+		}
+		double t1 = omp_get_wtime();
+		if (rep >= warm) { printf("%d %d %.6f %d\n", n, nsteps, t1 - t0, omp_get_max_threads()); fflush(stdout); }
 	}
-	double t1 = omp_get_wtime();
-	printf("%d %d %.6f %d\n", n, nsteps, t1 - t0, omp_get_max_threads());
 	return 0;
 }
 

@@ -6,4 +6,4 @@ There is no CPU fallback: `capi.lib()` raises when the library has not been buil
 when no B200-class GPU is usable."""
 from .capi import (Context, Mpd, SoftMoldError, lib, LIB_PATH, SYMBOLS, MASK_ALL, MASK_ALL_MOLECULES, MASK_LANGEVIN,  # noqa: F401
                    TERM_PAIR, TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL, NTERMS, NOISE_PHILOX,
-                   NOISE_EXTERNAL, MOL_BOND, MOL_BEND, MOL_CHAIN, MOL_BEAD, MOL_BALL)
+                   NOISE_EXTERNAL, MOL_BOND, MOL_BEND, MOL_CHAIN, MOL_BEAD, MOL_BALL, PHASES)

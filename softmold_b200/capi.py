@@ -27,7 +27,7 @@ SYMBOLS = [
     "smd_set_temperature", "smd_set_noise", "smd_build_cells", "smd_compute_forces", "smd_resume", "smd_step",
     "smd_step_begin", "smd_step_end", "smd_potential", "smd_kinetic", "smd_dpotential", "smd_rescale",
     "smd_mc_box_move", "smd_get_particles", "smd_get_forces", "smd_get_unwrapped", "smd_get_box", "smd_get_cell_ids",
-    "smd_count_pairs", "smd_synchronize", "smd_device_ptr", "smd_stream", "smd_stats", "smd_mpd_read", "smd_mpd_write",
+    "smd_count_pairs", "smd_synchronize", "smd_device_ptr", "smd_stream", "smd_stats", "smd_profile", "smd_profile_read", "smd_fp64_peak", "smd_mpd_read", "smd_mpd_write",
     "smd_mpd_free", "smd_mpd_get_scalar", "smd_mpd_set_scalar", "smd_mpd_get_size", "smd_mpd_set_size",
     "smd_mpd_particles", "smd_mpd_pair_tables", "smd_mpd_n_molecules", "smd_mpd_molecule", "smd_create_from_mpd",
 ]
@@ -95,6 +95,9 @@ def lib():
         L.smd_device_ptr.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.smd_stream.argtypes = [vp, C.POINTER(vp)]
         L.smd_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+        L.smd_profile.argtypes = [vp, C.c_uint32]
+        L.smd_profile_read.argtypes = [vp, vp, vp]
+        L.smd_fp64_peak.argtypes = [vp, dp, dp]
         L.smd_mpd_read.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_size_t]
         L.smd_mpd_write.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
         L.smd_mpd_free.argtypes = [vp]
@@ -249,8 +252,13 @@ class Context:
         return bool(acc.value), dU.value, box
 
     # -- read back
-    def get_particles(self):
-        xyz, typ, vel = np.zeros((self.n, 3)), np.zeros(self.n, np.int32), np.zeros((self.n, 3))
+    def get_particles(self, out=None):
+        """out: optional (xyz, type, vel) preallocated C-contiguous arrays (e.g. pinned host memory); an entry may be
+        None to skip that read-back"""
+        if out is None:
+            xyz, typ, vel = np.zeros((self.n, 3)), np.zeros(self.n, np.int32), np.zeros((self.n, 3))
+        else:
+            xyz, typ, vel = out
         self._ck(self.L.smd_get_particles(self.h, _ptr(xyz), _ptr(typ), _ptr(vel)))
         return xyz, typ, vel
 
@@ -288,10 +296,30 @@ class Context:
         self._ck(self.L.smd_stream(self.h, C.byref(s)))
         return s.value
 
+    def profile(self, phases=None):
+        """enable device timing of the named phases (PHASES), all when None, none when []"""
+        mask = 0
+        for p in (PHASES if phases is None else phases):
+            mask |= 1 << PHASES.index(p)
+        self._ck(self.L.smd_profile(self.h, mask))
+
+    def profile_read(self):
+        ms, cnt = np.zeros(8), np.zeros(8, np.int64)
+        self._ck(self.L.smd_profile_read(self.h, _ptr(ms), _ptr(cnt)))
+        return {p: (float(ms[i]), int(cnt[i])) for i, p in enumerate(PHASES)}
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.smd_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def stats(self):
         a, b = C.c_int64(), C.c_int64()
         self._ck(self.L.smd_stats(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+PHASES = ["integrate1", "build", "pair", "molecules", "langevin", "integrate2", "step"]
 
 
 class Mpd:

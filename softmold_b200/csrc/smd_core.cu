@@ -37,6 +37,67 @@ static inline int nblk(long long n, int tpb) { return (int)std::max<long long>(1
 
 static const int MAX_PARTIALS = 1 << 20;
 
+// ------------------------------------------------------------------------------------------------ phase timing
+static cudaEvent_t prof_event(smd_ctx *ctx)
+{
+	cudaEvent_t e;
+	if (!ctx->prof_free.empty()) { e = ctx->prof_free.back(); ctx->prof_free.pop_back(); return e; }
+	cudaEventCreate(&e);
+	return e;
+}
+
+static void prof_drain(smd_ctx *ctx)
+{
+	if (ctx->prof_pending.empty()) return;
+	cudaEventSynchronize(ctx->prof_pending.back().e1);
+	for (auto &sp : ctx->prof_pending) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { ctx->prof_ms[sp.phase] += ms; ctx->prof_count[sp.phase]++; }
+		ctx->prof_free.push_back(sp.e0);
+		ctx->prof_free.push_back(sp.e1);
+	}
+	ctx->prof_pending.clear();
+}
+
+// RAII bracket: records an event pair around the launches of one phase when that phase is enabled
+struct ProfScope {
+	smd_ctx *ctx; int phase; cudaEvent_t e0; bool on;
+	ProfScope(smd_ctx *c, int ph) : ctx(c), phase(ph), e0(nullptr), on((c->prof_mask >> ph) & 1u)
+	{
+		if (on) { e0 = prof_event(ctx); cudaEventRecord(e0, ctx->stream); }
+	}
+	~ProfScope()
+	{
+		if (!on) return;
+		cudaEvent_t e1 = prof_event(ctx);
+		cudaEventRecord(e1, ctx->stream);
+		ctx->prof_pending.push_back({phase, e0, e1});
+		if (ctx->prof_pending.size() >= 16384) prof_drain(ctx);
+	}
+};
+
+extern "C" int smd_profile(smd_ctx *ctx, uint32_t phase_mask)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	prof_drain(ctx);
+	for (int p = 0; p < SMD_NPHASES; p++) { ctx->prof_ms[p] = 0; ctx->prof_count[p] = 0; }
+	ctx->prof_mask = phase_mask;
+	return SMD_OK;
+}
+
+extern "C" int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPHASES])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	cudaSetDevice(ctx->device);
+	prof_drain(ctx);
+	for (int p = 0; p < SMD_NPHASES; p++) {
+		if (ms) ms[p] = ctx->prof_ms[p];
+		if (count) count[p] = ctx->prof_count[p];
+	}
+	return SMD_OK;
+}
+
 extern "C" int smd_abi_version(void) { return SMD_ABI_VERSION; }
 
 extern "C" const char *smd_last_error(const smd_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -187,6 +248,8 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto &b : ctx->bends) cudaFree(b.d_ijk);
 	for (auto &b : ctx->balls) cudaFree(b.d_cj);
 	for (auto &b : ctx->beads) { cudaFree(b.d_beads); cudaFree(b.d_C); }
+	prof_drain(ctx);
+	for (auto e : ctx->prof_free) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 	return SMD_OK;
@@ -506,17 +569,24 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 	int N = ctx->N;
 	// CellOpt::build: always rebuilt (the reference rebuilds every step, MD.cpp:412)
 	ctx->acc_live = false;   // about to be overwritten: no need to carry it through the build
-	if (!ctx->cells_valid) build_cells(ctx);
+	if (!ctx->cells_valid) { ProfScope ps(ctx, SMD_PHASE_BUILD); build_cells(ctx); }
 	LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);
 	ctx->acc_live = true;
 	int rc;
-	if (langevin_first && (mask & SMD_MASK_LANGEVIN))
+	if (langevin_first && (mask & SMD_MASK_LANGEVIN)) {
+		ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
 		if ((rc = add_langevin(ctx, step))) return rc;
-	if (mask & SMD_MASK(SMD_TERM_PAIR))
+	}
+	if (mask & SMD_MASK(SMD_TERM_PAIR)) {
+		ProfScope ps(ctx, SMD_PHASE_PAIR);
 		LAUNCH(k_pair<PAIR_FORCE>, nblk(N, TPB), TPB, pair_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start,
 		       cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->acc, nullptr, nullptr, 1.0, 1.0, 1.0);
-	if (!langevin_first && (mask & SMD_MASK_LANGEVIN))
+	}
+	if (!langevin_first && (mask & SMD_MASK_LANGEVIN)) {
+		ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
 		if ((rc = add_langevin(ctx, step))) return rc;
+	}
+	ProfScope ps(ctx, SMD_PHASE_MOLECULES);
 	return add_molecule_forces(ctx, mask);
 }
 
@@ -547,6 +617,7 @@ extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
 	int rc = ready(ctx);
 	if (rc) return rc;
 	int N = ctx->N;
+	ProfScope ps(ctx, SMD_PHASE_INTEGRATE1);
 	bead_mass_divide(ctx);                                                         // MD.cpp:340-355
 	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
 	       ctx->desc.dt, ctx->bbox, ctx->errflag);                                 // MD.cpp:356
@@ -564,7 +635,8 @@ extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
 	// MD.cpp:410-478: thermostat, build, pair, molecules
 	rc = forces(ctx, SMD_MASK_ALL, step, true);
 	if (rc) return rc;
-	bead_mass_divide(ctx);                                                         // MD.cpp:480-494
+	{ ProfScope ps(ctx, SMD_PHASE_MOLECULES); bead_mass_divide(ctx); }             // MD.cpp:480-494
+	ProfScope ps(ctx, SMD_PHASE_INTEGRATE2);
 	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);   // :511
 	return SMD_OK;
 }
@@ -574,6 +646,7 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(ctx->desc.noise != SMD_NOISE_EXTERNAL || nsteps <= 1, "external noise: one step per smd_set_noise");
 	for (int k = 0; k < nsteps; k++) {
+		ProfScope ps(ctx, SMD_PHASE_STEP);
 		int rc = smd_step_begin(ctx, first_step + k);
 		if (rc) return rc;
 		rc = smd_step_end(ctx, first_step + k);
@@ -825,6 +898,40 @@ extern "C" int smd_stream(smd_ctx *ctx, void **stream)
 {
 	if (!ctx || !stream) return SMD_ERR_ARG;
 	*stream = (void *)ctx->stream;
+	return SMD_OK;
+}
+
+extern "C" int smd_fp64_peak(smd_ctx *ctx, double *fma_tflops, double *muladd_tflops)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, ctx->device));
+	int blocks = prop.multiProcessorCount * 8, iters = 4096;
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0));
+	CK(cudaEventCreate(&e1));
+	double res[2] = {0, 0};
+	for (int mode = 0; mode < 2; mode++) {
+		float best = 1e30f;
+		for (int rep = 0; rep < 4; rep++) {
+			CK(cudaEventRecord(e0, ctx->stream));
+			if (mode == 0) k_fp64_peak<1><<<blocks, 256, 0, ctx->stream>>>(iters, 0.999999, 1e-7, ctx->scalars);
+			else k_fp64_peak<0><<<blocks, 256, 0, ctx->stream>>>(iters, 0.999999, 1e-7, ctx->scalars);
+			ctx->launches++;
+			CK(cudaEventRecord(e1, ctx->stream));
+			CK(cudaEventSynchronize(e1));
+			float ms = 0;
+			CK(cudaEventElapsedTime(&ms, e0, e1));
+			if (rep > 0 && ms < best) best = ms;
+		}
+		double flop = (double)blocks * 256.0 * iters * 8.0 * 2.0;   // mul + add per element, fused or not
+		res[mode] = flop / (best * 1e-3) * 1e-12;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (fma_tflops) *fma_tflops = res[0];
+	if (muladd_tflops) *muladd_tflops = res[1];
 	return SMD_OK;
 }
 

@@ -107,4 +107,12 @@ struct smd_ctx {
 	double *h_pinned;  // pinned host scratch (scalars)
 
 	long long launches, rebuilds;
+
+	// per-phase event timing (smd_profile)
+	struct ProfSpan { int phase; cudaEvent_t e0, e1; };
+	uint32_t prof_mask = 0;
+	std::vector<ProfSpan> prof_pending;
+	std::vector<cudaEvent_t> prof_free;
+	double prof_ms[SMD_NPHASES] = {0};
+	long long prof_count[SMD_NPHASES] = {0};
 };

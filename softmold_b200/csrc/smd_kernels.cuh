@@ -946,6 +946,29 @@ __global__ void k_bead_mass(int n, int cap, const int *__restrict__ beads, const
 	acc[s] /= mass; acc[cap + s] /= mass; acc[2 * cap + s] /= mass;
 }
 
+// ------------------------------------------------------------------------------------------------ FP64 pipe peak
+// Roofline denominator for the pair kernel, measured on the device it runs on: 8 independent dependency chains per
+// thread of either DFMA (FUSED = 1, the pipe's nominal peak, 2 flop per instruction) or DMUL + DADD (FUSED = 0, what
+// this library may issue: no contraction allowed, 1 flop per instruction).
+template <int FUSED>
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double a, double b, double *out)
+{
+	double x[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++) x[k] = (double)(threadIdx.x + k) * 1e-3;
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			if (FUSED) x[k] = __fma_rn(x[k], a, b);
+			else x[k] = __dadd_rn(__dmul_rn(x[k], a), b);
+		}
+	}
+	double s = 0;
+#pragma unroll
+	for (int k = 0; k < 8; k++) s += x[k];
+	if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------------------ gather / scatter to original order
 __global__ void __launch_bounds__(TPB) k_export_particles(int N, int cap, const Particle *pos, const double *vel, const int *gid,
                                                           double *xyz, int *type, double *v)
