@@ -118,6 +118,29 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 		g.cs[d] = box[d] / g.nc[d];                   // cellOpt.h:207-209 / :1560-1562
 	}
 	g.rc2 = ctx->desc.cutoff * ctx->desc.cutoff;
+	// FP32 prefilter threshold of k_pair_force2: absolute coordinates (and image shifts) up to maxL carry a rounding
+	// error of maxL * 2^-24 each; a difference of two of them plus its own rounding stays below 4 of those, so
+	// |r2_32 - r2_64| < 2 * sqrt(3) * rc * 4 * maxL * 2^-24 + (FP32 rounding of the squares).  32 * rc * that ulp
+	// covers it several times over.
+	double maxL = std::max(box[0], std::max(box[1], box[2]));
+	double margin = 32.0 * ctx->desc.cutoff * maxL * (1.0 / 16777216.0) + 1e-5 * g.rc2;
+	ctx->pgeo.thr32 = nextafterf((float)(g.rc2 + margin), INFINITY);
+	ctx->pgeo.margin32 = nextafterf((float)margin, INFINITY);
+	ctx->pgeo.slack32 = (float)(8.0 * maxL * (1.0 / 16777216.0) + 1e-6 * ctx->desc.cutoff);
+	for (int d = 0; d < 3; d++) ctx->pgeo.cs32[d] = (float)g.cs[d];
+}
+
+// per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
+static int upload_acut(smd_ctx *ctx)
+{
+	if (ctx->acut_raw.empty()) return SMD_OK;
+	std::vector<float> a(ctx->nT);
+	for (int t = 0; t < ctx->nT; t++)
+		a[t] = ctx->acut_raw[t] < 0 ? -1.0f : std::min(ctx->acut_raw[t] + ctx->pgeo.margin32, ctx->pgeo.thr32);
+	cudaError_t e = cudaMemcpyAsync(ctx->acut, a.data(), a.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e != cudaSuccess) { ctx->err = std::string("upload_acut: ") + cudaGetErrorString(e); return SMD_ERR_CUDA; }
+	return SMD_OK;
 }
 
 static int check_geom(smd_ctx *ctx)
@@ -191,6 +214,10 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 		ctx->unw[b] = nullptr;
 		if (desc->track_unwrapped) CKC(cudaMalloc(&ctx->unw[b], 3 * cap * sizeof(double)));
 	}
+	CKC(cudaMalloc(&ctx->pos32, (cap + 4) * sizeof(float4)));   // + overhang of the 4-wide candidate loads
+	CKC(cudaMemset(ctx->pos32, 0, (cap + 4) * sizeof(float4)));
+	CKC(cudaMalloc(&ctx->acut, (size_t)ctx->nT * sizeof(float)));
+	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->win, WIN_WORDS * sizeof(int)));
 	CKC(cudaMemset(ctx->win, 0, WIN_WORDS * sizeof(int)));
 	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
@@ -222,6 +249,18 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->istage, 2 * cap * sizeof(int)));
 	CKC(cudaMallocHost(&ctx->h_pinned, 64 * sizeof(double)));
 #undef CKC
+	{
+		int smem = PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) + (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned);
+		cudaError_t e1 = cudaFuncSetAttribute(k_pair_force2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 != cudaSuccess) {
+			g_create_error = std::string("cudaFuncSetAttribute(k_pair_force2): ") + cudaGetErrorString(e1);
+			smd_destroy(ctx);
+			return SMD_ERR_CUDA;
+		}
+	}
 	if (6 * ctx->nT * ctx->nT * sizeof(double) > 40000) {
 		g_create_error = "too many particle types for the shared-memory pair table";
 		smd_destroy(ctx);
@@ -239,6 +278,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (int b = 0; b < 2; b++) {
 		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]);
 	}
+	cudaFree(ctx->pos32); cudaFree(ctx->acut); cudaFree(ctx->ptab);
 	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
 	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
 	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
@@ -285,8 +325,55 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 	size_t bytes = 6 * (size_t)ctx->nT * ctx->nT * sizeof(double);
 	CK(cudaMemcpyAsync(ctx->fC, fC, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->uC, uC, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	{
+		// phase-1 class cutoff per type and the padded phase-2 table of k_pair_force2 (see there)
+		int nT = ctx->nT;
+		auto row = [&](int a, int b) { return fC + 6 * (a * nT + b); };
+		auto zero_tail = [&](const double *r) { return r[4] == 0.0 && r[5] == 0.0 && ctx->desc.cutoff <= 2.0 * r[0] && r[0] > 0; };
+		auto zero_core = [&](const double *r) { return r[1] == 0.0 && r[2] == 0.0; };
+		ctx->acut_raw.assign(nT, -1.0f);
+		for (int a = 0; a < nT; a++)
+			for (int b = 0; b < nT; b++) {
+				const double *r1 = row(a, b), *r2 = row(b, a);   // looked up in either orientation
+				float c = INFINITY;
+				if (zero_tail(r1) && zero_tail(r2)) {
+					double rm = std::max(r1[0], r2[0]);
+					c = nextafterf((float)(rm * rm), INFINITY);
+					if (zero_core(r1) && zero_core(r2)) c = -1.0f;
+				}
+				ctx->acut_raw[a] = std::max(ctx->acut_raw[a], c);
+			}
+		// smallest double whose correctly rounded square root is >= v
+		auto sq_threshold = [](double v) {
+			double x = v * v;
+			while (x > 0 && sqrt(x) >= v) x = nextafter(x, 0.0);
+			while (sqrt(x) < v) x = nextafter(x, INFINITY);
+			return x;
+		};
+		std::vector<double> pt((size_t)PTAB_STRIDE * nT * nT, 0.0);
+		for (int k = 0; k < nT * nT; k++) {
+			const double *r = fC + 6 * k;
+			double *o = pt.data() + (size_t)PTAB_STRIDE * k;
+			o[0] = r[0] > 0 ? sq_threshold(r[0]) : 0.0;
+			o[1] = r[0] > 0 ? sq_threshold(r[0] + r[0]) : 0.0;
+			o[2] = r[0]; o[3] = r[1]; o[4] = r[2];
+			o[6] = r[3]; o[7] = r[4]; o[8] = r[5];
+		}
+		CK(cudaMemcpyAsync(ctx->ptab, pt.data(), pt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		int rc = upload_acut(ctx);
+		if (rc) return rc;
+	}
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->tables_set = true;
+	// the reference looks rows up in the order (home particle, neighbour); every shipped generator
+	// writes symmetric tables, which lets the pair kernel skip the orientation logic.  Asymmetric tables still work.
+	ctx->tables_symmetric = true;
+	for (int a = 0; a < ctx->nT; a++)
+		for (int b = 0; b < a; b++)
+			for (int k = 0; k < 6; k++)
+				if (fC[6 * (a * ctx->nT + b) + k] != fC[6 * (b * ctx->nT + a) + k] || uC[6 * (a * ctx->nT + b) + k] != uC[6 * (b * ctx->nT + a) + k])
+					ctx->tables_symmetric = false;
 	return SMD_OK;
 }
 
@@ -481,7 +568,7 @@ static int build_cells(smd_ctx *ctx)
 	LAUNCH(k_place, nblk(N, TPB), TPB, 0, N, ctx->cellOfSlot, ctx->cursor, ctx->order);
 	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[cur], ctx->pos[nxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
-	       ctx->gid[nxt], ctx->slot_of);
+	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut);
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
 	ctx->cells_valid = true;
@@ -564,27 +651,59 @@ static int ready(smd_ctx *ctx)
 	return SMD_OK;
 }
 
+static int pair_force_smem(smd_ctx *ctx)
+{
+	return PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) + (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned);
+}
+
 static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first)
 {
 	int N = ctx->N;
 	// CellOpt::build: always rebuilt (the reference rebuilds every step, MD.cpp:412)
 	ctx->acc_live = false;   // about to be overwritten: no need to carry it through the build
 	if (!ctx->cells_valid) { ProfScope ps(ctx, SMD_PHASE_BUILD); build_cells(ctx); }
-	LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);
-	ctx->acc_live = true;
 	int rc;
-	if (langevin_first && (mask & SMD_MASK_LANGEVIN)) {
-		ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
-		if ((rc = add_langevin(ctx, step))) return rc;
-	}
-	if (mask & SMD_MASK(SMD_TERM_PAIR)) {
+	LangevinArgs lg = {};
+	bool pair = mask & SMD_MASK(SMD_TERM_PAIR), lang = mask & SMD_MASK_LANGEVIN;
+	if (langevin_first && lang && pair) {
+		// steady-state step (MD.cpp:357-413): a = 0, thermostat, pair force in ONE kernel
+		if (ctx->desc.noise == SMD_NOISE_EXTERNAL) {
+			REQUIRE(ctx->noise_ready, "SMD_NOISE_EXTERNAL: call smd_set_noise before every Langevin evaluation");
+			lg.ext_noise = ctx->noise;
+			ctx->noise_ready = false;
+		}
+		lg.gamma = ctx->desc.gamma;
+		lg.sigma = sqrt((6.0 * ctx->temperature * ctx->desc.gamma) / ctx->desc.dt);   // langevin.h:235
+		lg.seed = ctx->desc.seed; lg.step = (uint64_t)step;
+		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
 		ProfScope ps(ctx, SMD_PHASE_PAIR);
-		LAUNCH(k_pair<PAIR_FORCE>, nblk(N, TPB), TPB, pair_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start,
-		       cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->acc, nullptr, nullptr, 1.0, 1.0, 1.0);
-	}
-	if (!langevin_first && (mask & SMD_MASK_LANGEVIN)) {
-		ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
-		if ((rc = add_langevin(ctx, step))) return rc;
+		if (ctx->tables_symmetric)
+			LAUNCH((k_pair_force2<true, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+		else
+			LAUNCH((k_pair_force2<true, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+		ctx->acc_live = true;
+	} else {
+		LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);
+		ctx->acc_live = true;
+		if (langevin_first && lang) {
+			ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
+			if ((rc = add_langevin(ctx, step))) return rc;
+		}
+		if (pair) {
+			ProfScope ps(ctx, SMD_PHASE_PAIR);
+			if (ctx->tables_symmetric)
+				LAUNCH((k_pair_force2<false, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+			else
+				LAUNCH((k_pair_force2<false, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+		}
+		if (!langevin_first && lang) {
+			ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
+			if ((rc = add_langevin(ctx, step))) return rc;
+		}
 	}
 	ProfScope ps(ctx, SMD_PHASE_MOLECULES);
 	return add_molecule_forces(ctx, mask);
@@ -621,7 +740,7 @@ extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
 	bead_mass_divide(ctx);                                                         // MD.cpp:340-355
 	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
 	       ctx->desc.dt, ctx->bbox, ctx->errflag);                                 // MD.cpp:356
-	LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);                  // MD.cpp:357-366
+	// a = 0 (MD.cpp:357-366) is folded into the force evaluation that follows: it overwrites a[]
 	ctx->acc_live = false;
 	ctx->cells_valid = false;
 	return SMD_OK;
@@ -780,7 +899,8 @@ extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new
 	int rc = check_geom(ctx);
 	long long total = (long long)ctx->geom.nc[0] * ctx->geom.nc[1] * ctx->geom.nc[2];
 	if (!rc && total > ctx->cellcap) { ctx->err = "box grew beyond the cell-table capacity"; rc = SMD_ERR_UNSUPPORTED; }
-	if (rc) { ctx->geom = old; return rc; }
+	if (rc) { set_geom(ctx, old.box); return rc; }
+	if ((rc = upload_acut(ctx))) return rc;
 	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], scale[0], scale[1], scale[2]);
 	retag_cells(ctx);
 	return SMD_OK;

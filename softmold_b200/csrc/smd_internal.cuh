@@ -38,6 +38,13 @@ enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_WORDS = 8 };
 
 enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW_CAP = 4 };
 
+struct PairGeo {            // phase-1 constants of k_pair_force2
+	float thr32;            // rc^2 + FP32 rounding margin
+	float margin32;         // that margin
+	float slack32;          // FP32 rounding of a coordinate difference against a cell face
+	float cs32[3];          // cell size
+};
+
 struct ChainBlock { int start, nChains, len; double c[4]; };
 struct BondList { int n; int *d_ij; double c[2]; };
 struct BendList { int n; int *d_ijk; double c[2]; };
@@ -64,6 +71,11 @@ struct smd_ctx {
 
 	// resident particle state, cell-sorted ("slot" order); double-buffered for the per-step reorder
 	smd::Particle *pos[2];
+	float4 *pos32;    // FP32 mirror {x,y,z,type} of pos[cur], written by the reorder (phase 1 of the pair force kernel)
+	float *acut;      // [nT] FP32 phase-1 class cutoff per type, margin included (see k_pair_force2)
+	double *ptab;     // [nT*nT][PTAB_STRIDE] padded force table + exact branch thresholds
+	std::vector<float> acut_raw;   // host: rm^2 / +inf / -1 per type, before the margin
+	smd::PairGeo pgeo; // rc^2 + FP32 rounding margin etc. for that phase
 	double *vel[2];   // SoA [3][cap]
 	double *unw[2];   // SoA [3][cap] unwrapped positions (optional)
 	int *gid[2];      // original index of slot
@@ -85,6 +97,7 @@ struct smd_ctx {
 	// pair tables
 	double *fC, *uC;
 	bool tables_set, particles_set;
+	bool tables_symmetric;   // fC and uC rows (t1,t2) == (t2,t1): enables the orientation-free fast path of the pair kernel
 
 	// molecules
 	std::vector<smd::ChainBlock> chains;

@@ -224,7 +224,11 @@ __device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, 
 	}
 	for (int d = 0; d < 3; d++) {
 		int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
-		if ((threadIdx.x & 31) == 0 && l != INT_MAX) { atomicMin(bbox + d, l); atomicMax(bbox + 3 + d, h); }
+		// the box of occupied cells hardly moves between steps: only touch the accumulators when they would change
+		if ((threadIdx.x & 31) == 0 && l != INT_MAX) {
+			if (l < ((volatile int *)bbox)[d]) atomicMin(bbox + d, l);
+			if (h > ((volatile int *)bbox)[3 + d]) atomicMax(bbox + 3 + d, h);
+		}
 	}
 }
 
@@ -385,7 +389,8 @@ __global__ void __launch_bounds__(TPB) k_place(int N, const int *cellOfSlot, int
 __global__ void __launch_bounds__(TPB) k_reorder(int N, int cap, const int *order, const int *cellOfSlot, const int *start,
                                                  const Particle *pos_in, Particle *pos_out, const double *vel_in, double *vel_out,
                                                  const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
-                                                 const int *gid_in, int *gid_out, int *slot_of)
+                                                 const int *gid_in, int *gid_out, int *slot_of, float4 *pos32_out,
+                                                 const float *__restrict__ acut)
 {
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= N) return;
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(TPB) k_reorder(int N, int cap, const int *orde
 	int t = b + rank;
 	Particle p = load_particle(pos_in + s);
 	store_particle(pos_out + t, p);
+	pos32_out[t] = make_float4((float)p.x, (float)p.y, (float)p.z, acut[p.type]);   // phase-1 mirror of k_pair_force2
 	vel_out[t] = vel_in[s]; vel_out[cap + t] = vel_in[cap + s]; vel_out[2 * cap + t] = vel_in[2 * cap + s];
 	if (unw_in) { unw_out[t] = unw_in[s]; unw_out[cap + t] = unw_in[cap + s]; unw_out[2 * cap + t] = unw_in[2 * cap + s]; }
 	if (acc_in) { acc_out[t] = acc_in[s]; acc_out[cap + t] = acc_in[cap + s]; acc_out[2 * cap + t] = acc_in[2 * cap + s]; }
@@ -562,6 +568,296 @@ __global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__
 	if (MODE == PAIR_COUNT) {
 		double c = block_sum((double)cnt);
 		if (threadIdx.x == 0) partials[blockIdx.x] = c;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ pair force, two-phase
+// The production force kernel.  Same pairs, same per-pair arithmetic and the same orientation rules as k_pair above
+// (so every pair term stays bit-identical to the reference's), reorganised around what the B200 is short of here:
+// FP64 issue slots.  ncu on k_pair showed 11.4 of 32 lanes active per instruction: the sqrt / divide body ran under
+// a 20 % hit-rate branch.
+//   phase 1  (FP32 / INT / LSU pipes): each lane walks the 9 (y,z) rows of its particle's stencil -- the 3 cells of a
+//            row are contiguous in the sorted order, so a row is one index range -- over a float4 mirror of the
+//            positions and tests r^2 < rc^2 + margin in FP32.  Candidates that pass are appended to a lane-private
+//            list in shared memory (column `lane` of a [CAP][32] array: conflict-free).
+//   phase 2  (FP64 pipe): every lane drains its own list: reload the neighbour's FP64 record, repeat the exact FP64
+//            test (bit-exact membership), evaluate the pair term, accumulate in registers.  Lanes now run the
+//            expensive body together; only the spread of list lengths (63 +- 8) idles lanes.
+// The margin covers the FP32 rounding of absolute coordinates (<= box * 2^-24 each), so phase 1 never drops a pair
+// that the FP64 test accepts; false positives are rejected in phase 2.
+// The Langevin term and the zeroing of a[] are folded into the epilogue when LANGEVIN is set:
+//   a = (-gamma v + sigma (2u-1)) + sum_pairs,   exactly the order MD.cpp:357-413 produces.
+constexpr int PAIR_TPB = 128;
+constexpr int PAIR_CAP = 64;    // list entries per lane: 4 warps x 64 x 32 x 4 B = 32 KiB per block
+constexpr unsigned PAIR_WRAPPED = 0x80000000u;   // list entry flag: candidate seen through a periodic image shift
+
+struct LangevinArgs { double gamma, sigma; uint64_t seed, step; const double *vel; const int *gid; const double *ext_noise; };
+
+// the general pair term: any orientation, periodic images, ordered (possibly asymmetric) constant tables.
+// Same arithmetic as k_pair<PAIR_FORCE>.  Off the fast path, so kept out of line.
+struct D3 { double x, y, z; };
+
+__device__ __noinline__ D3 pair_force_term(int i, Particle pi, int j, Particle pj, const Geom &g, int nT, const double *s_tab, int ntab)
+{
+	D3 f = {0.0, 0.0, 0.0};
+	int cx, cy, cz, jx, jy, jz;
+	unpack_cell(pi.cell, cx, cy, cz);
+	unpack_cell(pj.cell, jx, jy, jz);
+	int ox = jx - cx, oy = jy - cy, oz = jz - cz;
+	double Sx = 0, Sy = 0, Sz = 0;
+	// neighbour cell reached across the periodic boundary: cellOpt.h:811-821
+	if (ox > 1) { ox -= g.nc[0]; Sx = -g.box[0]; } else if (ox < -1) { ox += g.nc[0]; Sx = g.box[0]; }
+	if (oy > 1) { oy -= g.nc[1]; Sy = -g.box[1]; } else if (oy < -1) { oy += g.nc[1]; Sy = g.box[1]; }
+	if (oz > 1) { oz -= g.nc[2]; Sz = -g.box[2]; } else if (oz < -1) { oz += g.nc[2]; Sz = g.box[2]; }
+	bool self = (ox == 0 && oy == 0 && oz == 0);
+	bool fwd = (oz == 1) || (oz == 0 && (ox == 1 || (ox == 0 && oy == 1)));
+	bool shifted = (Sx != 0) || (Sy != 0) || (Sz != 0);
+	double dx, dy, dz;
+	if (!shifted || self) {
+		dx = pi.x - pj.x; dy = pi.y - pj.y; dz = pi.z - pj.z;
+	} else if (fwd) {
+		dx = pi.x - (pj.x + Sx); dy = pi.y - (pj.y + Sy); dz = pi.z - (pj.z + Sz);
+	} else {
+		double bx = pi.x - Sx, by = pi.y - Sy, bz = pi.z - Sz;
+		dx = -(pj.x - bx); dy = -(pj.y - by); dz = -(pj.z - bz);
+	}
+	double dr2 = dx * dx + dy * dy + dz * dz;
+	if (dr2 < g.rc2) {
+		bool home = self ? (i > j) : fwd;
+		int t1 = home ? pi.type : pj.type, t2 = home ? pj.type : pi.type;
+		double m = pair_force_mag(dr2, t1, t2, nT, s_tab, ntab);
+		f.x = dx * m; f.y = dy * m; f.z = dz * m;
+	}
+	return f;
+}
+
+// 1/sqrt(x) to ~2^-43 from the MUFU.RSQ64H seed and one Newton step; x normal and positive
+__device__ __forceinline__ double rsqrt43(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	double e = __fma_rn(-(x * y), y, 1.0);
+	return __fma_rn(0.5 * y, e, y);
+}
+
+// SYMM: both constant tables are symmetric in the two types (checked on the host when they are set; true for every
+// generator of the reference).  Then the orientation of a pair only matters through the image shift,
+// and an unshifted pair needs nothing but d = p_i - p_j, which is exactly antisymmetric.
+//
+// Phase-1 cutoff per candidate: min(a[type_i], a[type_j]) with a[] a per-type FP32 radius^2 (+ margin) carried in
+// pos32[].w.  a[t] = rc^2 + margin when type t has a partner type with a non-zero tail branch; rm^2 + margin when
+// every pair (t,u) has zero tail constants (purely repulsive types, e.g. HEAD: Umin = 0 -- beyond rm their force is
+// exactly +-0 in the reference's arithmetic, so the candidates can be dropped unseen); negative when t interacts
+// with nothing.  min(a_i, a_j) is never below the exact per-pair cutoff, so nothing that matters is dropped.
+//
+// ptab (staged to shared): per ordered type pair 10 doubles {T1, T2 | c0, c1, c2, - | c3, c4, c5, -} = the
+// reference's row (MD.h:795-848) plus the two exact thresholds on r^2 that decide its branch:
+// r < rm <=> r^2 < T1 and r < 2 rm <=> r^2 < T2 (smallest doubles whose correctly rounded square root reaches rm,
+// 2 rm; computed on the host), so the branch never waits for the square root.
+constexpr int PTAB_STRIDE = 10;
+
+template <bool LANGEVIN, bool SYMM>
+__global__ void __launch_bounds__(PAIR_TPB, 5) k_pair_force2(int N, int cap, const Particle *__restrict__ pos,
+                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
+                                                             const int *__restrict__ win, Geom g, int nT,
+                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
+                                                             PairGeo pg, double *__restrict__ acc, LangevinArgs lg)
+{
+	extern __shared__ __align__(16) unsigned char s_raw[];
+	double *s_ptab = reinterpret_cast<double *>(s_raw);
+	const int nptab = PTAB_STRIDE * nT * nT;
+	unsigned *s_list = reinterpret_cast<unsigned *>(s_ptab + nptab) + (threadIdx.x >> 5) * (PAIR_CAP * 32) + (threadIdx.x & 31);
+	for (int k = threadIdx.x; k < nptab; k += blockDim.x) s_ptab[k] = ptab[k];
+	__syncthreads();
+
+	// Which particle does this thread take?  Work per particle differs several-fold between the type classes (a
+	// purely repulsive HEAD only looks at r < rm), and lanes of a warp wait for the slowest one, so the block's
+	// particles are dealt out class by class: long-range types fill the first warps, short-range ones the last.
+	__shared__ int s_perm[PAIR_TPB];
+	__shared__ int s_wcnt[PAIR_TPB / 32];
+	{
+		const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+		const bool heavy = (i0 < N) && pos32[i0].w >= pg.thr32;
+		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
+		const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+		if (lane == 0) s_wcnt[w] = __popc(bal);
+		__syncthreads();
+		int before = 0, total = 0;
+#pragma unroll
+		for (int k = 0; k < PAIR_TPB / 32; k++) { int c = s_wcnt[k]; total += c; if (k < w) before += c; }
+		const int below = __popc(bal & ((1u << lane) - 1u));
+		const int rank = heavy ? before + below : total + (threadIdx.x - before - below);
+		s_perm[rank] = i0;
+		__syncthreads();
+	}
+	const int i = s_perm[threadIdx.x];
+	const bool live = i < N;
+	Particle pi;
+	pi.x = pi.y = pi.z = 0; pi.type = 0; pi.cell = 0;
+	float4 p32 = make_float4(0.f, 0.f, 0.f, -1.f);
+	int cx = 0, cy = 0, cz = 0;
+	if (live) {
+		pi = load_particle(pos + i);
+		p32 = pos32[i];
+		unpack_cell(pi.cell, cx, cy, cz);
+	}
+	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
+	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
+	const char *rowi = reinterpret_cast<const char *>(s_ptab + PTAB_STRIDE * pi.type * nT);
+	const double rc2 = g.rc2;
+	const float thr32 = pg.thr32;
+	const float ai = p32.w;
+	const unsigned ibyte = (unsigned)i * 32u;
+	double ax = 0, ay = 0, az = 0;
+	const unsigned lbase = (unsigned)__cvta_generic_to_shared(s_list);   // the lane's list: entries 128 B apart
+	unsigned wp = lbase;                         // shared-window address of its next free entry
+	const bool anywrap = __any_sync(0xffffffffu, live && (cx == 0 || cx == g.nc[0] - 1));
+
+	// conservative FP32 distances from the particle to the faces of its own cell (minus / plus side per axis): a
+	// neighbour cell at offset o_a = -1 / +1 holds no point closer than that along axis a
+	float fm[3], fp[3];
+	{
+		float c[3] = {p32.x, p32.y, p32.z};
+		int ci[3] = {cx, cy, cz};
+#pragma unroll
+		for (int a = 0; a < 3; a++) {
+			fm[a] = fmaxf(c[a] - (float)ci[a] * pg.cs32[a] - pg.slack32, 0.f);
+			fp[a] = fmaxf((float)(ci[a] + 1) * pg.cs32[a] - c[a] - pg.slack32, 0.f);
+		}
+	}
+
+	// fast path of phase 2: unshifted pair, symmetric tables, r < 2 rm.  Branch-free so that two pairs interleave.
+	// sqrt and the division share one reciprocal square root; both are finished with an exact-residual correction
+	// step (correctly rounded except for vanishingly rare near-ties, then off by one ulp).
+	// e = byte offset of the neighbour's record | PAIR_WRAPPED.  Returns true when the general routine must redo it.
+	auto fast = [&](unsigned e, const Particle &pj) -> bool {
+		double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+		double dr2 = dx * dx + dy * dy + dz * dz;
+		const char *c = rowi + (PTAB_STRIDE * 8) * pj.type;
+		double2 T = *reinterpret_cast<const double2 *>(c);
+		bool in = dr2 < rc2 && e != ibyte;         // the particle itself passes phase 1 (r2 = 0)
+		bool ok = SYMM && in && dr2 < T.y && !(e & PAIR_WRAPPED);
+		c += (dr2 < T.x) ? 16 : 48;                  // pair_branch(): core or tail constants
+		double2 c01 = *reinterpret_cast<const double2 *>(c);
+		double c2 = *reinterpret_cast<const double *>(c + 16);
+		double x = ok ? dr2 : 1.0;
+		double y = rsqrt43(x);
+		double dr = x * y;
+		dr = __fma_rn(__fma_rn(-dr, dr, x), 0.5 * y, dr);     // sqrt(x)
+		double m = c01.x - dr;
+		double num = (c01.y - c2 * m) * m;
+		double q = num * y;
+		q = __fma_rn(__fma_rn(-dr, q, num), y, q);            // num / dr
+		q = ok ? q : 0.0;
+		ax += dx * q; ay += dy * q; az += dz * q;
+		return !ok && ((e & PAIR_WRAPPED) || in);
+	};
+	auto general = [&](unsigned e, const Particle &pj) {
+		D3 f = pair_force_term(i, pi, (int)((e & ~PAIR_WRAPPED) >> 5), pj, g, nT, tab, 6 * nT * nT);
+		ax += f.x; ay += f.y; az += f.z;
+	};
+	const char *posb = reinterpret_cast<const char *>(pos);
+
+#pragma unroll 1
+	for (int s = 0; s <= 27; s++) {
+		const bool last = (s == 27);
+		int jb = 0, je = 0;
+		float sx = 0.f, sy = 0.f, sz = 0.f;
+		if (!last) {
+			int r = s / 3, sub = s - 3 * r;
+			if (sub != 0 && !anywrap) continue;
+			int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
+			int nz = cz + oz, ny = cy + oy;
+			if (nz < 0) { nz += g.nc[2]; sz = -(float)g.box[2]; }
+			if (nz >= g.nc[2]) { nz -= g.nc[2]; sz = (float)g.box[2]; }
+			if (ny < 0) { ny += g.nc[1]; sy = -(float)g.box[1]; }
+			if (ny >= g.nc[1]) { ny -= g.nc[1]; sy = (float)g.box[1]; }
+			int lz = nz - w2, ly = ny - w1;
+			// geometric pruning: the whole row, then its two end cells
+			float gy = oy == 0 ? 0.f : (oy > 0 ? fp[1] : fm[1]), gz = oz == 0 ? 0.f : (oz > 0 ? fp[2] : fm[2]);
+			float gyz = gy * gy + gz * gz;
+			float amax = fminf(ai, thr32);
+			bool row_ok = live && lz >= 0 && lz < d2 && ly >= 0 && ly < d1 && gyz < amax;
+			bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
+			int rowbase = d0 * (ly + d1 * lz);
+			int xlo, xhi;
+			if (sub == 0) {          // cells cx-1 .. cx+1 that need no wrap, clamped to the window (outside it: empty)
+				xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
+			} else if (sub == 1) {   // left face: the image of the last cell of the row
+				xlo = xhi = g.nc[0] - 1 - w0; sx = -(float)g.box[0];
+				row_ok = row_ok && keep_lo && cx == 0 && xlo >= 0 && xlo < d0;
+			} else {                 // right face: the image of the first cell
+				xlo = xhi = 0 - w0; sx = (float)g.box[0];
+				row_ok = row_ok && keep_hi && cx == g.nc[0] - 1 && xlo >= 0 && xlo < d0;
+			}
+			if (row_ok && xlo <= xhi) { jb = start[rowbase + xlo]; je = start[rowbase + xhi + 1]; }
+		}
+		const unsigned flag = (sx != 0.f || sy != 0.f || sz != 0.f) ? PAIR_WRAPPED : 0u;
+		const float qx = p32.x - sx, qy = p32.y - sy, qz = p32.z - sz;
+		int j = jb;
+		while (true) {
+			// ---- phase 1: FP32 prefilter of as many candidates as the list has room for
+			int room = PAIR_CAP - (int)((wp - lbase) >> 7);
+			int left = je - j;
+			int e = j + min(left, room);
+			// groups of four, all four loads in flight, the overhang masked (pos32 is padded by 4 records)
+			for (; j < e; j += 4) {
+				float4 c[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) c[k] = pos32[j + k];
+				const int rem = e - j;
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					float dx = qx - c[k].x, dy = qy - c[k].y, dz = qz - c[k].z;
+					float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+					if (r2 < fminf(ai, c[k].w) && k < rem) {
+						asm volatile("st.shared.u32 [%0], %1;" ::"r"(wp), "r"(((unsigned)(j + k) << 5) | flag) : "memory");
+						wp += 128u;
+					}
+				}
+			}
+			j = e;
+			if (!__any_sync(0xffffffffu, last || left > room)) break;
+			// ---- phase 2: drain the lane's list, two pairs in flight
+			unsigned rp = lbase;
+			auto entry = [](unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
+			for (; rp + 128u < wp; rp += 256u) {
+				unsigned e0 = entry(rp), e1 = entry(rp + 128u);
+				Particle p0 = load_particle(reinterpret_cast<const Particle *>(posb + (e0 & ~PAIR_WRAPPED)));
+				Particle p1 = load_particle(reinterpret_cast<const Particle *>(posb + (e1 & ~PAIR_WRAPPED)));
+				bool s0 = fast(e0, p0);
+				bool s1 = fast(e1, p1);
+				if (s0 || s1) {
+					if (s0) general(e0, p0);
+					if (s1) general(e1, p1);
+				}
+			}
+			if (rp < wp) {
+				unsigned e0 = entry(rp);
+				Particle p0 = load_particle(reinterpret_cast<const Particle *>(posb + (e0 & ~PAIR_WRAPPED)));
+				if (fast(e0, p0)) general(e0, p0);
+			}
+			wp = lbase;
+			if (last) break;
+		}
+	}
+
+	if (live) {
+		if (LANGEVIN) {
+			int id = lg.gid[i];
+			double u[3];
+			if (lg.ext_noise) {
+				u[0] = lg.ext_noise[3 * id]; u[1] = lg.ext_noise[3 * id + 1]; u[2] = lg.ext_noise[3 * id + 2];
+			} else {
+				philox_uniform3(lg.seed, lg.step, (uint32_t)id, u);
+			}
+			double lx = -lg.gamma * lg.vel[i] + lg.sigma * (2.0 * u[0] - 1.0);
+			double ly = -lg.gamma * lg.vel[cap + i] + lg.sigma * (2.0 * u[1] - 1.0);
+			double lz = -lg.gamma * lg.vel[2 * cap + i] + lg.sigma * (2.0 * u[2] - 1.0);
+			acc[i] = lx + ax; acc[cap + i] = ly + ay; acc[2 * cap + i] = lz + az;
+		} else {
+			acc[i] += ax; acc[cap + i] += ay; acc[2 * cap + i] += az;
+		}
 	}
 }
 
