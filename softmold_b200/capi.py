@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsoftmold_b200.so")
+LIB_PATH = os.environ.get("SOFTMOLD_B200_LIB") or os.path.join(HERE, "libsoftmold_b200.so")   # override: A/B builds
 
 SMD_OK, SMD_ERR_ARG, SMD_ERR_CUDA, SMD_ERR_CELL, SMD_ERR_IO, SMD_ERR_UNSUPPORTED = range(6)
 MOL_BOND, MOL_BEND, MOL_CHAIN, MOL_BEAD, MOL_BALL = 6, 7, 8, 9, 19

@@ -214,8 +214,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 		ctx->unw[b] = nullptr;
 		if (desc->track_unwrapped) CKC(cudaMalloc(&ctx->unw[b], 3 * cap * sizeof(double)));
 	}
-	CKC(cudaMalloc(&ctx->pos32, (cap + 4) * sizeof(float4)));   // + overhang of the 4-wide candidate loads
-	CKC(cudaMemset(ctx->pos32, 0, (cap + 4) * sizeof(float4)));
+	CKC(cudaMalloc(&ctx->pos32, (cap + 8) * sizeof(float4)));   // + overhang of the 4-wide candidate loads and their prefetch
+	CKC(cudaMemset(ctx->pos32, 0, (cap + 8) * sizeof(float4)));
 	CKC(cudaMalloc(&ctx->acut, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->win, WIN_WORDS * sizeof(int)));
@@ -250,7 +250,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMallocHost(&ctx->h_pinned, 64 * sizeof(double)));
 #undef CKC
 	{
-		int smem = PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) + (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned);
+		int smem = (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
+		           (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
 		cudaError_t e1 = cudaFuncSetAttribute(k_pair_force2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -653,7 +654,8 @@ static int ready(smd_ctx *ctx)
 
 static int pair_force_smem(smd_ctx *ctx)
 {
-	return PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) + (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned);
+	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
+	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
 }
 
 static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first)

@@ -588,8 +588,14 @@ __global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__
 // The Langevin term and the zeroing of a[] are folded into the epilogue when LANGEVIN is set:
 //   a = (-gamma v + sigma (2u-1)) + sum_pairs,   exactly the order MD.cpp:357-413 produces.
 constexpr int PAIR_TPB = 128;
-constexpr int PAIR_CAP = 64;    // list entries per lane: 4 warps x 64 x 32 x 4 B = 32 KiB per block
-constexpr unsigned PAIR_WRAPPED = 0x80000000u;   // list entry flag: candidate seen through a periodic image shift
+#ifndef SMD_PAIR_CAP
+#define SMD_PAIR_CAP 128
+#endif
+#ifndef SMD_PAIR_BLOCKS
+#define SMD_PAIR_BLOCKS 4
+#endif
+constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 128 x 32 x 2 B = 32 KiB per block
+constexpr int PAIR_SEGBITS = 12;   // entry = (range index << 12) | offset inside the range
 
 struct LangevinArgs { double gamma, sigma; uint64_t seed, step; const double *vel; const int *gid; const double *ext_noise; };
 
@@ -656,41 +662,63 @@ __device__ __forceinline__ double rsqrt43(double x)
 // 2 rm; computed on the host), so the branch never waits for the square root.
 constexpr int PTAB_STRIDE = 10;
 
+// Work distribution inside a block (128 threads, 128 consecutive slots):
+//   * phase 1 is per particle, but lanes of a warp wait for the slowest one and the work differs several-fold between
+//     type classes, so particles are dealt to threads class by class (long-range types fill the first warps);
+//     every lane then walks ITS OWN flat stream of candidate ranges (a small per-thread table in shared memory),
+//     so lanes only meet again at the end of the phase, not after every row.  A list entry is 16 bits:
+//     (range index, offset inside the range);
+//   * phase 2 is per list.  After a block barrier the lists are handed out again sorted by length (counting sort
+//     in shared memory), so the lanes of a warp drain lists of nearly equal length; the thread that drains a list
+//     loads that particle's record and writes its acceleration -- no reduction anywhere.
+// A list that fills up before phase 1 ends is drained on the spot by its own thread (never seen in practice: 128
+// entries); that partial sum travels with the list.  Pairs seen through a periodic image (particles in the outermost
+// cell layers only) go straight to the general routine from a separate, plain loop.
+constexpr int PAIR_NSEG = 9;
+
+struct PairSmem {
+	int perm[PAIR_TPB];                 // particle (slot) taken by each thread in phase 1
+	int cnt[PAIR_TPB];                  // list length per phase-1 thread
+	int order[PAIR_TPB];                // phase-2 thread -> phase-1 thread whose list it drains
+	double part[3][PAIR_TPB];           // sums that do not go through the list (early drains, periodic images)
+	int seg_b[PAIR_NSEG][PAIR_TPB];     // candidate ranges of each thread: first index ...
+	unsigned short seg_n[PAIR_NSEG][PAIR_TPB];   // ... and length (< 4096)
+	int hist[PAIR_CAP + 2];
+	int wcnt[PAIR_TPB / 32];
+};
+
 template <bool LANGEVIN, bool SYMM>
-__global__ void __launch_bounds__(PAIR_TPB, 5) k_pair_force2(int N, int cap, const Particle *__restrict__ pos,
-                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
-                                                             const int *__restrict__ win, Geom g, int nT,
-                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
-                                                             PairGeo pg, double *__restrict__ acc, LangevinArgs lg)
+__global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N, int cap, const Particle *__restrict__ pos,
+                                                            const float4 *__restrict__ pos32, const int *__restrict__ start,
+                                                            const int *__restrict__ win, Geom g, int nT,
+                                                            const double *__restrict__ tab, const double *__restrict__ ptab,
+                                                            PairGeo pg, double *__restrict__ acc, LangevinArgs lg)
 {
 	extern __shared__ __align__(16) unsigned char s_raw[];
-	double *s_ptab = reinterpret_cast<double *>(s_raw);
+	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
+	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
 	const int nptab = PTAB_STRIDE * nT * nT;
-	unsigned *s_list = reinterpret_cast<unsigned *>(s_ptab + nptab) + (threadIdx.x >> 5) * (PAIR_CAP * 32) + (threadIdx.x & 31);
-	for (int k = threadIdx.x; k < nptab; k += blockDim.x) s_ptab[k] = ptab[k];
-	__syncthreads();
+	unsigned short *s_lists = reinterpret_cast<unsigned short *>(s_ptab + nptab);
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	for (int k = tid; k < nptab; k += PAIR_TPB) s_ptab[k] = ptab[k];
+	for (int k = tid; k < PAIR_CAP + 2; k += PAIR_TPB) sm.hist[k] = 0;
 
-	// Which particle does this thread take?  Work per particle differs several-fold between the type classes (a
-	// purely repulsive HEAD only looks at r < rm), and lanes of a warp wait for the slowest one, so the block's
-	// particles are dealt out class by class: long-range types fill the first warps, short-range ones the last.
-	__shared__ int s_perm[PAIR_TPB];
-	__shared__ int s_wcnt[PAIR_TPB / 32];
+	// ---- deal the block's particles to threads by class
 	{
-		const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+		const int i0 = blockIdx.x * PAIR_TPB + tid;
 		const bool heavy = (i0 < N) && pos32[i0].w >= pg.thr32;
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
-		const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-		if (lane == 0) s_wcnt[w] = __popc(bal);
+		if (lane == 0) sm.wcnt[wid] = __popc(bal);
 		__syncthreads();
 		int before = 0, total = 0;
 #pragma unroll
-		for (int k = 0; k < PAIR_TPB / 32; k++) { int c = s_wcnt[k]; total += c; if (k < w) before += c; }
+		for (int k = 0; k < PAIR_TPB / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < wid) before += c; }
 		const int below = __popc(bal & ((1u << lane) - 1u));
-		const int rank = heavy ? before + below : total + (threadIdx.x - before - below);
-		s_perm[rank] = i0;
+		const int rank = heavy ? before + below : total + (tid - before - below);
+		sm.perm[rank] = i0;
 		__syncthreads();
 	}
-	const int i = s_perm[threadIdx.x];
+	const int i = sm.perm[tid];
 	const bool live = i < N;
 	Particle pi;
 	pi.x = pi.y = pi.z = 0; pi.type = 0; pi.cell = 0;
@@ -703,18 +731,95 @@ __global__ void __launch_bounds__(PAIR_TPB, 5) k_pair_force2(int N, int cap, con
 	}
 	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
 	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
-	const char *rowi = reinterpret_cast<const char *>(s_ptab + PTAB_STRIDE * pi.type * nT);
 	const double rc2 = g.rc2;
-	const float thr32 = pg.thr32;
 	const float ai = p32.w;
-	const unsigned ibyte = (unsigned)i * 32u;
-	double ax = 0, ay = 0, az = 0;
-	const unsigned lbase = (unsigned)__cvta_generic_to_shared(s_list);   // the lane's list: entries 128 B apart
-	unsigned wp = lbase;                         // shared-window address of its next free entry
-	const bool anywrap = __any_sync(0xffffffffu, live && (cx == 0 || cx == g.nc[0] - 1));
+	// entries of thread t's list sit 64 B apart (one 16-bit column per lane)
+	auto list_base = [&](int t) { return (unsigned)__cvta_generic_to_shared(s_lists + (t >> 5) * (PAIR_CAP * 32) + (t & 31)); };
+	const unsigned segb_base = (unsigned)__cvta_generic_to_shared(&sm.seg_b[0][0]);
 
-	// conservative FP32 distances from the particle to the faces of its own cell (minus / plus side per axis): a
-	// neighbour cell at offset o_a = -1 / +1 holds no point closer than that along axis a
+	// phase 2 for one list: the particle (slot io, record po) whose ranges belong to phase-1 thread t, against the
+	// entries [rp, wend).  Branch-free except for the hand-over to the general routine (asymmetric tables, r >= 2 rm),
+	// so that two pairs interleave; the records of the next two pairs are already in flight.  sqrt and the division
+	// share one reciprocal square root, each finished with an exact-residual correction step (correctly rounded except
+	// for vanishingly rare near-ties, then off by one ulp).
+	auto drain = [&](int io, const Particle &po, int t, unsigned rp, unsigned wend, double &ax, double &ay, double &az) {
+		const char *rowi = reinterpret_cast<const char *>(s_ptab + PTAB_STRIDE * po.type * nT);
+		const unsigned tb = segb_base + 4u * (unsigned)t;
+		auto fetch = [&](unsigned a, int &j) {       // entry -> neighbour slot and record
+			unsigned short e;
+			asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(a) : "memory");
+			int b;
+			asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(tb + (unsigned)(e >> PAIR_SEGBITS) * (4u * PAIR_TPB)) : "memory");
+			j = b + (int)(e & ((1u << PAIR_SEGBITS) - 1u));
+			return load_particle(pos + j);
+		};
+		auto fast = [&](int j, const Particle &pj) -> bool {
+			double dx = po.x - pj.x, dy = po.y - pj.y, dz = po.z - pj.z;
+			double dr2 = dx * dx + dy * dy + dz * dz;
+			const char *c = rowi + (PTAB_STRIDE * 8) * pj.type;
+			double2 T = *reinterpret_cast<const double2 *>(c);
+			bool in = dr2 < rc2 && j != io;            // the particle itself passes phase 1 (r2 = 0)
+			bool ok = SYMM && in && dr2 < T.y;
+			c += (dr2 < T.x) ? 16 : 48;                  // pair_branch(): core or tail constants
+			double2 c01 = *reinterpret_cast<const double2 *>(c);
+			double c2 = *reinterpret_cast<const double *>(c + 16);
+			double x = ok ? dr2 : 1.0;
+			double y = rsqrt43(x);
+			double dr = x * y;
+			dr = __fma_rn(__fma_rn(-dr, dr, x), 0.5 * y, dr);     // sqrt(x)
+			double m = c01.x - dr;
+			double num = (c01.y - c2 * m) * m;
+			double q = num * y;
+			q = __fma_rn(__fma_rn(-dr, q, num), y, q);            // num / dr
+			q = ok ? q : 0.0;
+			ax += dx * q; ay += dy * q; az += dz * q;
+			return in && !ok;
+		};
+		auto general = [&](int j, const Particle &pj) {
+			D3 f = pair_force_term(io, po, j, pj, g, nT, tab, 6 * nT * nT);
+			ax += f.x; ay += f.y; az += f.z;
+		};
+		if (rp + 64u < wend) {
+			int j0, j1;
+			Particle p0 = fetch(rp, j0), p1 = fetch(rp + 64u, j1);
+			rp += 128u;
+			while (true) {
+				int n0 = j0, n1 = j1;
+				Particle q0 = p0, q1 = p1;
+				const bool more = rp + 64u < wend;
+				if (more) { q0 = fetch(rp, n0); q1 = fetch(rp + 64u, n1); }   // next two pairs: in flight during the math below
+				bool s0 = fast(j0, p0);
+				bool s1 = fast(j1, p1);
+				if (s0 || s1) {
+					if (s0) general(j0, p0);
+					if (s1) general(j1, p1);
+				}
+				if (!more) break;
+				rp += 128u;
+				j0 = n0; j1 = n1; p0 = q0; p1 = q1;
+			}
+		}
+		if (rp < wend) {
+			int j0;
+			Particle p0 = fetch(rp, j0);
+			if (fast(j0, p0)) general(j0, p0);
+		}
+	};
+
+	const unsigned lbase = list_base(tid);
+	unsigned wp = lbase;                         // shared-window address of the next free entry of this thread's list
+	double ex = 0, ey = 0, ez = 0;               // sums that bypass the list
+	auto push = [&](unsigned v) {
+		asm volatile("st.shared.u16 [%0], %1;" ::"r"(wp), "h"((unsigned short)v) : "memory");
+		wp += 64u;
+	};
+	auto drain_if_full = [&]() {
+		if (wp > lbase + 64u * (PAIR_CAP - 4)) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }
+	};
+
+	// ---- the particle's candidate ranges: one per (y,z) row of the stencil, pruned by geometry
+	// conservative FP32 distances to the faces of the own cell: a neighbour cell at offset -1 / +1 along an axis holds
+	// no point closer than that along the axis
 	float fm[3], fp[3];
 	{
 		float c[3] = {p32.x, p32.y, p32.z};
@@ -725,64 +830,92 @@ __global__ void __launch_bounds__(PAIR_TPB, 5) k_pair_force2(int N, int cap, con
 			fp[a] = fmaxf((float)(ci[a] + 1) * pg.cs32[a] - c[a] - pg.slack32, 0.f);
 		}
 	}
-
-	// fast path of phase 2: unshifted pair, symmetric tables, r < 2 rm.  Branch-free so that two pairs interleave.
-	// sqrt and the division share one reciprocal square root; both are finished with an exact-residual correction
-	// step (correctly rounded except for vanishingly rare near-ties, then off by one ulp).
-	// e = byte offset of the neighbour's record | PAIR_WRAPPED.  Returns true when the general routine must redo it.
-	auto fast = [&](unsigned e, const Particle &pj) -> bool {
-		double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-		double dr2 = dx * dx + dy * dy + dz * dz;
-		const char *c = rowi + (PTAB_STRIDE * 8) * pj.type;
-		double2 T = *reinterpret_cast<const double2 *>(c);
-		bool in = dr2 < rc2 && e != ibyte;         // the particle itself passes phase 1 (r2 = 0)
-		bool ok = SYMM && in && dr2 < T.y && !(e & PAIR_WRAPPED);
-		c += (dr2 < T.x) ? 16 : 48;                  // pair_branch(): core or tail constants
-		double2 c01 = *reinterpret_cast<const double2 *>(c);
-		double c2 = *reinterpret_cast<const double *>(c + 16);
-		double x = ok ? dr2 : 1.0;
-		double y = rsqrt43(x);
-		double dr = x * y;
-		dr = __fma_rn(__fma_rn(-dr, dr, x), 0.5 * y, dr);     // sqrt(x)
-		double m = c01.x - dr;
-		double num = (c01.y - c2 * m) * m;
-		double q = num * y;
-		q = __fma_rn(__fma_rn(-dr, q, num), y, q);            // num / dr
-		q = ok ? q : 0.0;
-		ax += dx * q; ay += dy * q; az += dz * q;
-		return !ok && ((e & PAIR_WRAPPED) || in);
-	};
-	auto general = [&](unsigned e, const Particle &pj) {
-		D3 f = pair_force_term(i, pi, (int)((e & ~PAIR_WRAPPED) >> 5), pj, g, nT, tab, 6 * nT * nT);
-		ax += f.x; ay += f.y; az += f.z;
-	};
-	const char *posb = reinterpret_cast<const char *>(pos);
-
+	const float amax = fminf(ai, pg.thr32);
+	int nseg = 0;
+	bool shifted_rows = false;
 #pragma unroll 1
-	for (int s = 0; s <= 27; s++) {
-		const bool last = (s == 27);
+	for (int r = 0; r < 9; r++) {
+		int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
+		int nz = cz + oz, ny = cy + oy;
+		bool wrapyz = nz < 0 || nz >= g.nc[2] || ny < 0 || ny >= g.nc[1];
+		int lz = nz - w2, ly = ny - w1;
+		float gy = oy == 0 ? 0.f : (oy > 0 ? fp[1] : fm[1]), gz = oz == 0 ? 0.f : (oz > 0 ? fp[2] : fm[2]);
+		float gyz = gy * gy + gz * gz;
+		bool row_ok = live && gyz < amax;
+		if (row_ok && (wrapyz || cx == 0 || cx == g.nc[0] - 1)) shifted_rows = true;
+		row_ok = row_ok && !wrapyz && lz >= 0 && lz < d2 && ly >= 0 && ly < d1;
+		bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
+		// cells cx-1 .. cx+1 that need no wrap, clamped to the window (cells outside it are empty)
+		int xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0), xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
 		int jb = 0, je = 0;
-		float sx = 0.f, sy = 0.f, sz = 0.f;
-		if (!last) {
+		if (row_ok && xlo <= xhi) {
+			int rowbase = d0 * (ly + d1 * lz);
+			jb = start[rowbase + xlo]; je = start[rowbase + xhi + 1];
+		}
+		sm.seg_b[r][tid] = jb;
+		const int lim = (1 << PAIR_SEGBITS) - 4;
+		sm.seg_n[r][tid] = (unsigned short)min(je - jb, lim);
+		// a range longer than the 12-bit offset field (> 1300 particles per cell): take the excess one by one
+		for (int j = jb + lim; j < je; j++) {
+			float4 c = pos32[j];
+			float dx = p32.x - c.x, dy = p32.y - c.y, dz = p32.z - c.z;
+			if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w) && j != i) {
+				D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
+				ex += f.x; ey += f.y; ez += f.z;
+			}
+		}
+		nseg = (je > jb) ? r + 1 : nseg;
+	}
+
+	// ---- phase 1: FP32 prefilter along the thread's own stream of ranges; four candidates per step, the next four
+	// already in flight
+	for (int sg = 0; sg < nseg; sg++) {
+		const int jb = sm.seg_b[sg][tid];
+		const int n = sm.seg_n[sg][tid];
+		const unsigned tag = (unsigned)sg << PAIR_SEGBITS;
+		float4 nx[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) nx[k] = pos32[jb + k];   // pos32 is padded: the overhang is masked below
+		for (int q = 0; q < n; q += 4) {
+			float4 c[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) c[k] = nx[k];
+			if (q + 4 < n) {
+#pragma unroll
+				for (int k = 0; k < 4; k++) nx[k] = pos32[jb + q + 4 + k];
+			}
+			const int rem = n - q;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				float dx = p32.x - c[k].x, dy = p32.y - c[k].y, dz = p32.z - c[k].z;
+				float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+				if (r2 < fminf(ai, c[k].w) && k < rem) push(tag | (unsigned)(q + k));
+			}
+			drain_if_full();
+		}
+	}
+
+	// ---- rows and end cells seen through a periodic image (particles in the outermost cell layers only)
+	if (shifted_rows) {
+#pragma unroll 1
+		for (int s = 0; s < 27; s++) {
 			int r = s / 3, sub = s - 3 * r;
-			if (sub != 0 && !anywrap) continue;
 			int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
 			int nz = cz + oz, ny = cy + oy;
+			float sx = 0.f, sy = 0.f, sz = 0.f;
 			if (nz < 0) { nz += g.nc[2]; sz = -(float)g.box[2]; }
 			if (nz >= g.nc[2]) { nz -= g.nc[2]; sz = (float)g.box[2]; }
 			if (ny < 0) { ny += g.nc[1]; sy = -(float)g.box[1]; }
 			if (ny >= g.nc[1]) { ny -= g.nc[1]; sy = (float)g.box[1]; }
 			int lz = nz - w2, ly = ny - w1;
-			// geometric pruning: the whole row, then its two end cells
 			float gy = oy == 0 ? 0.f : (oy > 0 ? fp[1] : fm[1]), gz = oz == 0 ? 0.f : (oz > 0 ? fp[2] : fm[2]);
 			float gyz = gy * gy + gz * gz;
-			float amax = fminf(ai, thr32);
-			bool row_ok = live && lz >= 0 && lz < d2 && ly >= 0 && ly < d1 && gyz < amax;
+			bool row_ok = gyz < amax && lz >= 0 && lz < d2 && ly >= 0 && ly < d1;
 			bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
-			int rowbase = d0 * (ly + d1 * lz);
 			int xlo, xhi;
-			if (sub == 0) {          // cells cx-1 .. cx+1 that need no wrap, clamped to the window (outside it: empty)
+			if (sub == 0) {          // the unwrapped x range of a row shifted in y or z (unshifted rows were done above)
 				xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
+				row_ok = row_ok && (sy != 0.f || sz != 0.f);
 			} else if (sub == 1) {   // left face: the image of the last cell of the row
 				xlo = xhi = g.nc[0] - 1 - w0; sx = -(float)g.box[0];
 				row_ok = row_ok && keep_lo && cx == 0 && xlo >= 0 && xlo < d0;
@@ -790,74 +923,67 @@ __global__ void __launch_bounds__(PAIR_TPB, 5) k_pair_force2(int N, int cap, con
 				xlo = xhi = 0 - w0; sx = (float)g.box[0];
 				row_ok = row_ok && keep_hi && cx == g.nc[0] - 1 && xlo >= 0 && xlo < d0;
 			}
-			if (row_ok && xlo <= xhi) { jb = start[rowbase + xlo]; je = start[rowbase + xhi + 1]; }
-		}
-		const unsigned flag = (sx != 0.f || sy != 0.f || sz != 0.f) ? PAIR_WRAPPED : 0u;
-		const float qx = p32.x - sx, qy = p32.y - sy, qz = p32.z - sz;
-		int j = jb;
-		while (true) {
-			// ---- phase 1: FP32 prefilter of as many candidates as the list has room for
-			int room = PAIR_CAP - (int)((wp - lbase) >> 7);
-			int left = je - j;
-			int e = j + min(left, room);
-			// groups of four, all four loads in flight, the overhang masked (pos32 is padded by 4 records)
-			for (; j < e; j += 4) {
-				float4 c[4];
-#pragma unroll
-				for (int k = 0; k < 4; k++) c[k] = pos32[j + k];
-				const int rem = e - j;
-#pragma unroll
-				for (int k = 0; k < 4; k++) {
-					float dx = qx - c[k].x, dy = qy - c[k].y, dz = qz - c[k].z;
-					float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-					if (r2 < fminf(ai, c[k].w) && k < rem) {
-						asm volatile("st.shared.u32 [%0], %1;" ::"r"(wp), "r"(((unsigned)(j + k) << 5) | flag) : "memory");
-						wp += 128u;
-					}
+			if (!row_ok || xlo > xhi) continue;
+			int rowbase = d0 * (ly + d1 * lz);
+			int jb = start[rowbase + xlo], je = start[rowbase + xhi + 1];
+			const float qx = p32.x - sx, qy = p32.y - sy, qz = p32.z - sz;
+			for (int j = jb; j < je; j++) {
+				float4 c = pos32[j];
+				float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+				if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w)) {
+					D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
+					ex += f.x; ey += f.y; ez += f.z;
 				}
 			}
-			j = e;
-			if (!__any_sync(0xffffffffu, last || left > room)) break;
-			// ---- phase 2: drain the lane's list, two pairs in flight
-			unsigned rp = lbase;
-			auto entry = [](unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; };
-			for (; rp + 128u < wp; rp += 256u) {
-				unsigned e0 = entry(rp), e1 = entry(rp + 128u);
-				Particle p0 = load_particle(reinterpret_cast<const Particle *>(posb + (e0 & ~PAIR_WRAPPED)));
-				Particle p1 = load_particle(reinterpret_cast<const Particle *>(posb + (e1 & ~PAIR_WRAPPED)));
-				bool s0 = fast(e0, p0);
-				bool s1 = fast(e1, p1);
-				if (s0 || s1) {
-					if (s0) general(e0, p0);
-					if (s1) general(e1, p1);
-				}
-			}
-			if (rp < wp) {
-				unsigned e0 = entry(rp);
-				Particle p0 = load_particle(reinterpret_cast<const Particle *>(posb + (e0 & ~PAIR_WRAPPED)));
-				if (fast(e0, p0)) general(e0, p0);
-			}
-			wp = lbase;
-			if (last) break;
 		}
 	}
 
-	if (live) {
-		if (LANGEVIN) {
-			int id = lg.gid[i];
-			double u[3];
-			if (lg.ext_noise) {
-				u[0] = lg.ext_noise[3 * id]; u[1] = lg.ext_noise[3 * id + 1]; u[2] = lg.ext_noise[3 * id + 2];
-			} else {
-				philox_uniform3(lg.seed, lg.step, (uint32_t)id, u);
-			}
-			double lx = -lg.gamma * lg.vel[i] + lg.sigma * (2.0 * u[0] - 1.0);
-			double ly = -lg.gamma * lg.vel[cap + i] + lg.sigma * (2.0 * u[1] - 1.0);
-			double lz = -lg.gamma * lg.vel[2 * cap + i] + lg.sigma * (2.0 * u[2] - 1.0);
-			acc[i] = lx + ax; acc[cap + i] = ly + ay; acc[2 * cap + i] = lz + az;
+	// ---- hand the lists out again, longest first
+	const int cnt = (int)((wp - lbase) >> 6);
+	sm.cnt[tid] = cnt;
+	sm.part[0][tid] = ex; sm.part[1][tid] = ey; sm.part[2][tid] = ez;
+	atomicAdd(&sm.hist[cnt], 1);
+	__syncthreads();
+	if (tid < 32) {   // exclusive prefix over descending length (PAIR_CAP + 1 bins)
+		constexpr int PER = (PAIR_CAP + 1 + 31) / 32;
+		int h[PER], sum = 0;
+#pragma unroll
+		for (int k = 0; k < PER; k++) { int c = PAIR_CAP - (tid * PER + k); h[k] = c >= 0 ? sm.hist[c] : 0; sum += h[k]; }
+		int inc = sum;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, d); if (tid >= d) inc += v; }
+		int run = inc - sum;
+#pragma unroll
+		for (int k = 0; k < PER; k++) { int c = PAIR_CAP - (tid * PER + k); if (c >= 0) sm.hist[c] = run; run += h[k]; }
+	}
+	__syncthreads();
+	sm.order[atomicAdd(&sm.hist[cnt], 1)] = tid;
+	__syncthreads();
+
+	// ---- phase 2: drain one list, FP64
+	const int o = sm.order[tid];
+	const int io = sm.perm[o];
+	if (io >= N) return;
+	const Particle po = load_particle(pos + io);
+	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
+	{
+		const unsigned ob = list_base(o);
+		drain(io, po, o, ob, ob + 64u * (unsigned)sm.cnt[o], ax, ay, az);
+	}
+	if (LANGEVIN) {
+		int id = lg.gid[io];
+		double u[3];
+		if (lg.ext_noise) {
+			u[0] = lg.ext_noise[3 * id]; u[1] = lg.ext_noise[3 * id + 1]; u[2] = lg.ext_noise[3 * id + 2];
 		} else {
-			acc[i] += ax; acc[cap + i] += ay; acc[2 * cap + i] += az;
+			philox_uniform3(lg.seed, lg.step, (uint32_t)id, u);
 		}
+		double lx = -lg.gamma * lg.vel[io] + lg.sigma * (2.0 * u[0] - 1.0);
+		double ly = -lg.gamma * lg.vel[cap + io] + lg.sigma * (2.0 * u[1] - 1.0);
+		double lz = -lg.gamma * lg.vel[2 * cap + io] + lg.sigma * (2.0 * u[2] - 1.0);
+		acc[io] = lx + ax; acc[cap + io] = ly + ay; acc[2 * cap + io] = lz + az;
+	} else {
+		acc[io] += ax; acc[cap + io] += ay; acc[2 * cap + io] += az;
 	}
 }
 
