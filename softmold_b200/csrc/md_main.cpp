@@ -1,0 +1,383 @@
+// MD_b200 -- drop-in replacement of the reference `MD <name>` executable (reference: MD.cpp, 755 lines).
+//
+// Reads <name>.mpd, integrates it on one B200 through the C ABI of libsoftmold_b200.so (include/softmold_b200.h --
+// nothing else: no CUDA, no torch here), and writes what the reference writes, in its formats:
+//   <name>.mpd                  rewritten every storeInterval with initialTime = now   (MD.cpp:373-377)
+//   frames_<name>.xyz           appended every storeInterval (+ the t = 0 frame)       (MD.cpp:267-273, :379-381)
+//   potential_ size_ lBond_ bend_ [beadPotential_] temp_ kinetic_ flicker_ [meanSquareDisplacement_]<name>.dat
+//                               appended every measureInterval                         (dataExtraction.h:827-1693)
+//   kEnergyDensity_<name>.dat   at exit                                                (dataExtraction.h:551-567)
+//   resizeHist_<name>.dat       at exit when deltaLXY != 0                             (MD.cpp:731-746)
+// and on stderr "time<TAB>seconds" per measure interval and the final "Resize acceptance ratio".
+// The schedule (what happens at which step index, restart half kick, Metropolis box move every 8 steps with the
+// MT19937 stream MTRand(seed)) follows MD.cpp:186-333 and the loop :335-729.
+//
+// Differences, all deliberate: the Langevin noise is the counter-based Philox stream of the library (the reference's
+// depends on the OpenMP thread count); gammaType (per-type friction) and the molecule kinds outside the
+// hot path are refused loudly instead of silently ignored; environment variable SMD_DEVICE picks the GPU.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/softmold_b200.h"
+
+namespace {
+
+// MT19937 (Matsumoto & Nishimura 1998) with the 53-bit real of the reference's MTRand::rand53
+// (include/algorithms/MersenneTwister.h:337-341): the barostat stream must be the reference's to the bit.
+struct MT19937 {
+	uint32_t s[624];
+	int pos;
+	explicit MT19937(uint32_t seed)
+	{
+		s[0] = seed;
+		for (int i = 1; i < 624; i++) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+		pos = 624;
+	}
+	uint32_t u32()
+	{
+		if (pos >= 624) {
+			for (int k = 0; k < 624; k++) {
+				uint32_t y = (s[k] & 0x80000000u) | (s[(k + 1) % 624] & 0x7fffffffu);
+				s[k] = s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+			}
+			pos = 0;
+		}
+		uint32_t y = s[pos++];
+		y ^= y >> 11;
+		y ^= (y << 7) & 0x9d2c5680u;
+		y ^= (y << 15) & 0xefc60000u;
+		y ^= y >> 18;
+		return y;
+	}
+	double rand53()
+	{
+		uint32_t a = u32() >> 5, b = u32() >> 6;
+		return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+	}
+};
+
+struct Mol { int type, n, width; int32_t *rec; int nconst; double *c; };
+
+struct Driver {
+	std::string name;
+	smd_mpd *mpd = nullptr;
+	smd_ctx *ctx = nullptr;
+	int n = 0;
+	double *xyz = nullptr, *vel = nullptr;   // borrowed from the mpd object: refreshed before every use
+	int32_t *type = nullptr;
+	std::vector<Mol> mols;
+	std::vector<double> unw, unw_start;      // aP / aPStart of the reference (MD.cpp:96-105, dataExtraction.h:790-803)
+	bool diffusion_started = false;
+	std::vector<long> ke_hist;
+	double temperature = 0, time_now = 0;
+
+	void die(const char *what, int rc)
+	{
+		std::cerr << what << ": " << (ctx ? smd_last_error(ctx) : smd_last_error(nullptr)) << " (code " << rc << ")\n";
+		std::exit(1);
+	}
+	void ck(int rc, const char *what) { if (rc) die(what, rc); }
+
+	void download()
+	{
+		ck(smd_get_particles(ctx, xyz, nullptr, vel), "smd_get_particles");
+	}
+
+	// Script::write + xyzFormat::store at a store step (MD.cpp:373-381)
+	void store(bool write_mpd)
+	{
+		download();
+		if (write_mpd) {
+			double box[3];
+			smd_get_box(ctx, box);
+			smd_mpd_set_size(mpd, box);
+			smd_mpd_set_scalar(mpd, "initialTime", time_now);
+			smd_mpd_set_scalar(mpd, "initialTemp", temperature);
+			char err[512];
+			if (smd_mpd_write(mpd, name.c_str(), err, sizeof err)) { std::cerr << err << "\n"; std::exit(1); }
+		}
+		std::ofstream f("frames_" + name + ".xyz", std::ios::out | std::ios::app);
+		f << n << '\n' << "test\n";
+		for (int i = 0; i < n; i++) f << type[i] << '\t' << xyz[3 * i] << '\t' << xyz[3 * i + 1] << '\t' << xyz[3 * i + 2] << '\n';
+	}
+
+	template <class... A>
+	void line(const char *prefix, A... values)
+	{
+		std::ofstream f(prefix + name + ".dat", std::ios::app | std::ios::out);
+		f << time_now;
+		((f << '\t' << values), ...);
+		f << std::endl;
+	}
+
+	// dataExtraction::compute (dataExtraction.h:827-1693, default build: no ANCHOR_DATA / FLAT_MEMBRANE / NANOPARTICLE)
+	void measure()
+	{
+		double terms[SMD_NTERMS];
+		ck(smd_potential(ctx, terms), "smd_potential");
+		double potential = 0;
+		for (int t = 0; t < SMD_NTERMS; t++) potential += terms[t];
+		double kinetic = 0;
+		ck(smd_kinetic(ctx, &kinetic), "smd_kinetic");
+		download();
+		double s[3];
+		smd_get_box(ctx, s);
+
+		double lBond = 0, costhetaBend = 0, lBend[2] = {0, 0};
+		int nBond = 0, nBend = 0, nBeads = 0;
+		auto image = [&](double d[3]) {
+			for (int a = 0; a < 3; a++) {
+				if (d[a] >= s[a] / 2.0) d[a] -= s[a];
+				if (d[a] <= -s[a] / 2.0) d[a] += s[a];
+			}
+		};
+		for (const Mol &m : mols) {
+			if (m.type == SMD_MOL_BOND) {
+				for (int l = 0; l < m.n; l++) {
+					int a = m.rec[2 * l], b = m.rec[2 * l + 1];
+					double d[3] = {xyz[3 * a] - xyz[3 * b], xyz[3 * a + 1] - xyz[3 * b + 1], xyz[3 * a + 2] - xyz[3 * b + 2]};
+					image(d);
+					lBond += std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+				}
+				nBond += m.n;
+			} else if (m.type == SMD_MOL_BEND) {
+				for (int l = 0; l < m.n; l++) {
+					int a = m.rec[3 * l], b = m.rec[3 * l + 1], c = m.rec[3 * l + 2];
+					double da[3] = {xyz[3 * a] - xyz[3 * b], xyz[3 * a + 1] - xyz[3 * b + 1], xyz[3 * a + 2] - xyz[3 * b + 2]};
+					double db[3] = {xyz[3 * b] - xyz[3 * c], xyz[3 * b + 1] - xyz[3 * c + 1], xyz[3 * b + 2] - xyz[3 * c + 2]};
+					image(da);
+					image(db);
+					double ra = std::sqrt(da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
+					double rb = std::sqrt(db[0] * db[0] + db[1] * db[1] + db[2] * db[2]);
+					lBend[0] += ra;
+					lBend[1] += rb;
+					costhetaBend += (da[0] * db[0] + da[1] * db[1] + da[2] * db[2]) / (ra * rb);
+				}
+				nBend += m.n;
+			} else if (m.type == SMD_MOL_BEAD) {
+				nBeads++;
+			}
+		}
+		line("potential_", potential);
+		line("size_", s[0], s[1], s[2]);
+		line("lBond_", lBond / (double)nBond);
+		if (nBend > 1) { costhetaBend /= nBend; lBend[0] /= nBend; lBend[1] /= nBend; }
+		line("bend_", costhetaBend, lBend[0], lBend[1]);
+		if (nBeads > 0) line("beadPotential_", terms[SMD_TERM_BEAD]);
+		line("temp_", temperature);
+		line("kinetic_", kinetic);
+
+		double lo[3] = {s[0], s[1], s[2]}, hi[3] = {0, 0, 0};
+		for (int i = 0; i < n; i++)
+			for (int a = 0; a < 3; a++) {
+				if (xyz[3 * i + a] < lo[a]) lo[a] = xyz[3 * i + a];
+				if (xyz[3 * i + a] > hi[a]) hi[a] = xyz[3 * i + a];
+			}
+		line("flicker_", hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+
+		const double part = 0.0001;   // kEnergyDensityPartition, dataExtraction.h:390
+		for (int i = 0; i < n; i++) {
+			size_t b = (size_t)(0.5 * (vel[3 * i] * vel[3 * i] + vel[3 * i + 1] * vel[3 * i + 1] + vel[3 * i + 2] * vel[3 * i + 2]) / part);
+			if (b >= ke_hist.size()) ke_hist.resize(b + 1, 0);
+			ke_hist[b]++;
+		}
+
+		if (diffusion_started) {   // dataExtraction.h:1525-1663
+			ck(smd_get_unwrapped(ctx, unw.data()), "smd_get_unwrapped");
+			std::ofstream f("meanSquareDisplacement_" + name + ".dat", std::ios::app | std::ios::out);
+			f << time_now;
+			auto sq = [&](int j) {
+				double d0 = unw[3 * j] - unw_start[3 * j], d1 = unw[3 * j + 1] - unw_start[3 * j + 1], d2 = unw[3 * j + 2] - unw_start[3 * j + 2];
+				return d0 * d0 + d1 * d1 + d2 * d2;
+			};
+			for (const Mol &m : mols) {
+				double msd = 0;
+				int np = 0;
+				if (m.type == SMD_MOL_BOND || m.type == SMD_MOL_BEND || m.type == SMD_MOL_BEAD) {
+					for (int l = 0; l < m.n; l++)
+						for (int k = 0; k < m.width; k++) msd += sq(m.rec[m.width * l + k]);
+					np = m.n * m.width;
+				} else if (m.type == SMD_MOL_CHAIN) {
+					for (int l = 0; l < m.n; l++) {
+						int st = m.rec[3 * l], nch = m.rec[3 * l + 1], len = m.rec[3 * l + 2];
+						for (int j = st; j < st + len * nch; j++) msd += sq(j);
+						np += len * nch;
+					}
+				}
+				if (np != 0) f << '\t' << (msd / (double)np);
+			}
+			f << '\n';
+		}
+	}
+
+	void start_diffusion()
+	{
+		if (diffusion_started) return;
+		unw_start.resize(3 * (size_t)n);
+		ck(smd_get_unwrapped(ctx, unw_start.data()), "smd_get_unwrapped");
+		diffusion_started = true;
+	}
+
+	void finish()
+	{
+		std::ofstream f("kEnergyDensity_" + name + ".dat", std::ios::out);
+		long sum = 0;
+		for (long c : ke_hist) sum += c;
+		for (size_t i = 0; i < ke_hist.size(); i++)
+			f << static_cast<float>(i) * 0.0001 << '\t' << static_cast<float>(ke_hist[i]) / static_cast<float>(sum) << std::endl;
+	}
+};
+
+double scalar(smd_mpd *m, const char *cmd, bool *present = nullptr)
+{
+	double v = 0;
+	int32_t p = 0;
+	smd_mpd_get_scalar(m, cmd, &v, &p);
+	if (present) *present = p != 0;
+	return v;
+}
+
+}   // namespace
+
+int main(int argc, char *argv[])
+{
+	if (argc != 2) {
+		std::cerr << "usage: " << argv[0] << " name\n";   // MD.cpp:74-79
+		return 0;
+	}
+	Driver D;
+	D.name = argv[1];
+	char err[1024];
+	if (smd_mpd_read(argv[1], &D.mpd, err, sizeof err)) {
+		std::cerr << err << "\n";
+		return 1;
+	}
+	smd_mpd *M = D.mpd;
+	const double gamma = scalar(M, "gamma"), dt = scalar(M, "deltaT");
+	bool has_gamma_type = false;
+	scalar(M, "gammaType", &has_gamma_type);
+	if (!(gamma > 0)) {
+		if (has_gamma_type) std::cout << "Error(main): per-type friction (gammaType) is outside the hot path of this build\n";
+		else std::cout << "Error(main): No gamma available!\n";   // MD.cpp:139-143
+		return 0;
+	}
+	const uint32_t seed = (uint32_t)scalar(M, "seed");
+	const double deltaLXY = scalar(M, "deltaLXY"), tension = scalar(M, "tension");
+	const double finalTime = scalar(M, "finalTime"), initialTime = scalar(M, "initialTime");
+	const double finalTemp = scalar(M, "finalTemp"), tempStepInterval = scalar(M, "tempStepInterval");
+	D.temperature = scalar(M, "initialTemp");
+
+	smd_mpd_particles(M, &D.n, &D.xyz, &D.type, &D.vel);
+	for (int k = 0; k < smd_mpd_n_molecules(M); k++) {
+		Mol m;
+		smd_mpd_molecule(M, k, &m.type, &m.n, &m.width, &m.rec, &m.nconst, &m.c);
+		D.mols.push_back(m);
+	}
+	const char *dev = std::getenv("SMD_DEVICE");
+	int rc = smd_create_from_mpd(M, dev ? std::atoi(dev) : 0, SMD_NOISE_PHILOX, 1, &D.ctx);
+	if (rc) {
+		std::cerr << "MD_b200: " << smd_last_error(D.ctx) << " (code " << rc << ")\n";
+		return 1;
+	}
+	smd_ctx *ctx = D.ctx;
+	D.unw.resize(3 * (size_t)D.n);
+
+	// MD.cpp:311-323: integer step indices; the 1e-7 is the reference's
+	const int endInt = int(finalTime / dt + 0.0000001), startInt = int(initialTime / dt + 0.0000001);
+	const int storeint = int(scalar(M, "storeInterval") / dt + 0.0000001), measureint = int(scalar(M, "measureInterval") / dt + 0.0000001);
+	int tempStepInt = 0;
+	double tempStep = 0;
+	if (tempStepInterval > 0) {
+		tempStep = tempStepInterval * (finalTemp - D.temperature) / (finalTime - initialTime);
+		int div = int((finalTime - initialTime) / tempStepInterval);
+		tempStepInt = div ? (endInt - startInt) / div : 0;
+	}
+	const int resizeRate = 8;   // MD.cpp:67
+
+	double resizeHistInterval = 0.00001;
+	std::vector<double> resizeHist, rejectHist;
+	if (deltaLXY != 0) {
+		resizeHistInterval = deltaLXY / 101.0;
+		int nIntervals = static_cast<int>(2.0 * deltaLXY / resizeHistInterval) + 1;
+		resizeHist.assign(nIntervals, 0.0);
+		rejectHist.assign(nIntervals, 0.0);
+	}
+	MT19937 randNum(seed);
+	double trial = 0, accepted = 0;
+
+	// MD.cpp:186-262: forces of the loaded configuration (pair, thermostat, molecules)
+	D.time_now = initialTime;
+	D.ck(smd_compute_forces(ctx, SMD_MASK_ALL, startInt), "smd_compute_forces");
+	if (initialTime == 0) {
+		D.measure();
+		D.store(false);
+	} else {
+		D.ck(smd_resume(ctx), "smd_resume");   // MD.cpp:274-308
+	}
+
+	auto store_at = [&](int i) { return storeint > 0 && i % storeint == 0 && i != startInt; };
+	auto measure_at = [&](int i) { return measureint > 0 && i % measureint == 0 && i != startInt; };
+	auto mc_at = [&](int i) { return i % resizeRate == 0 && i != 0 && deltaLXY != 0; };
+	auto ramp_at = [&](int i) { return tempStepInterval > 0 && tempStepInt != 0 && i % tempStepInt == 0 && i < endInt; };
+	auto plain = [&](int i) { return !store_at(i) && !measure_at(i) && !mc_at(i) && !ramp_at(i); };
+
+	std::cerr << "starting main loop: \n";
+	time_t current = time(NULL);
+	for (int i = startInt; i <= endInt;) {
+		// steps without any host-side event run back to back on the device
+		int nplain = 0;
+		while (i + nplain <= endInt && plain(i + nplain) && nplain < 4096) nplain++;
+		if (nplain > 0) {
+			D.ck(smd_step(ctx, i, nplain), "smd_step");
+			i += nplain;
+			continue;
+		}
+		D.time_now = (double)i * dt;
+		D.ck(smd_step_begin(ctx, i), "smd_step_begin");
+		if (ramp_at(i)) {
+			D.temperature += tempStep;
+			smd_set_temperature(ctx, D.temperature);
+		}
+		if (store_at(i)) D.store(true);
+		D.ck(smd_step_end(ctx, i), "smd_step_end");
+		if (measure_at(i)) {
+			time_t last = current;
+			current = time(NULL);
+			std::cerr << D.time_now << '\t' << current - last << std::endl;
+			if (D.time_now > 100.0) D.start_diffusion();   // DIFFUSION_START, MD.cpp:41,538-539
+			D.measure();
+			current = time(NULL);
+		}
+		if (mc_at(i)) {   // MD.cpp:589-721
+			double u_fluct = randNum.rand53(), u_accept = randNum.rand53();
+			double fluct = deltaLXY * (2.0 * u_fluct - 1.0);
+			int32_t acc = 0;
+			double dU = 0, box[3];
+			D.ck(smd_mc_box_move(ctx, deltaLXY, tension, u_fluct, u_accept, &acc, &dU, box), "smd_mc_box_move");
+			size_t bin = (size_t)((fluct + deltaLXY) / resizeHistInterval);
+			if (bin < resizeHist.size()) (acc ? resizeHist : rejectHist)[bin] += 1.0;   // 0.5 for x + 0.5 for y
+			if (acc) accepted++;
+			trial++;
+		}
+		i++;
+	}
+	D.ck(smd_synchronize(ctx), "smd_synchronize");
+
+	if (deltaLXY != 0) {
+		std::ofstream f("resizeHist_" + D.name + ".dat", std::ios::out);
+		for (size_t k = 0; k < resizeHist.size(); k++)
+			f << (static_cast<double>(k) * resizeHistInterval) - deltaLXY << '\t' << resizeHist[k] << '\t' << rejectHist[k] << std::endl;
+	}
+	std::cerr << "Resize acceptance ratio: " << accepted / trial << std::endl;
+	D.finish();
+	smd_destroy(ctx);
+	smd_mpd_free(M);
+	return 0;
+}

@@ -382,6 +382,7 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 // the steady state does this inside k_verlet_first)
 static int retag_cells(smd_ctx *ctx)
 {
+	LAUNCH(k_arm_bbox, 1, 32, 0, ctx->bbox);
 	LAUNCH(k_tag_cells, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], ctx->geom, ctx->bbox, ctx->errflag);
 	ctx->cells_valid = false;
 	return SMD_OK;
@@ -564,7 +565,8 @@ static int build_cells(smd_ctx *ctx)
 	// particles were tagged with their cell (and bbox[] accumulated) by whoever moved them last
 	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, N, ctx->pos[cur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot);
 	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
-	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, ctx->win, ctx->geom, ctx->cellcap, ctx->errflag);
+	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, ctx->win, ctx->geom, ctx->cellcap, ctx->errflag,
+	       (ctx->rebuilds & 255) == 255 ? 1 : 0);
 	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N);
 	LAUNCH(k_place, nblk(N, TPB), TPB, 0, N, ctx->cellOfSlot, ctx->cursor, ctx->order);
 	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[cur], ctx->pos[nxt],

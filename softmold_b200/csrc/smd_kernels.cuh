@@ -316,7 +316,15 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int 
 }
 
 // single block: exclusive scan of the block sums; thread 0 publishes the window and re-arms the bbox accumulators
-__global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox, int *win, Geom g, long long cellcap, int *errflag)
+__global__ void k_arm_bbox(int *bbox)
+{
+	if (threadIdx.x < 3) { bbox[threadIdx.x] = INT_MAX; bbox[3 + threadIdx.x] = INT_MIN; }
+}
+
+// rearm = 0: the accumulators keep their extremes, so the window never shrinks and the next tagging pass only issues
+// an atomic when a particle leaves the box of cells seen so far (same-address atomics of thousands of warps cost
+// ~25 us per step otherwise).  The host re-arms every few hundred builds to follow a drifting object.
+__global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox, int *win, Geom g, long long cellcap, int *errflag, int rearm)
 {
 	__shared__ int sh[SCAN_BLOCKS];
 	int v = blockSums[threadIdx.x];
@@ -334,7 +342,8 @@ __global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox
 		for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = w.org[d]; win[WIN_DIM + d] = w.dim[d]; }
 		win[WIN_NCELLS] = w.ncells;
 		if (w.ncells == 0) atomicOr(errflag, ERR_WINDOW_CAP);
-		for (int d = 0; d < 3; d++) { bbox[d] = INT_MAX; bbox[3 + d] = INT_MIN; }
+		if (rearm)
+			for (int d = 0; d < 3; d++) { bbox[d] = INT_MAX; bbox[3 + d] = INT_MIN; }
 	}
 }
 

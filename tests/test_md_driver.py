@@ -1,0 +1,116 @@
+"""MD_b200 (softmold_b200/csrc/md_main.cpp), the drop-in replacement of the reference's `MD <name>` executable, run
+side by side with the UNMODIFIED reference binary (oracle/_ref/MD, prebuilt in the build container) on the same
+`.mpd`: same files, same schedule, identical t = 0 observables, identical deterministic columns, statistically
+consistent thermodynamics (the Langevin noise streams differ by design)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from softmold_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+MD_B200 = os.path.join(ROOT, "softmold_b200", "MD_b200")
+MD_REF = os.path.join(ROOT, "oracle", "_ref", "MD")
+
+
+def table(path):
+    rows = []
+    for ln in open(path).read().splitlines():
+        rows.append([float(x) if x not in ("-nan", "nan") else float("nan") for x in ln.split("\t")])
+    return rows
+
+
+def run_pair(tmp_path, orc, m, name):
+    out = {}
+    for tag, exe in (("ours", MD_B200), ("ref", MD_REF)):
+        if not os.path.exists(exe):
+            continue
+        d = tmp_path / tag
+        d.mkdir()
+        orc.write_mpd(str(d / (name + ".mpd")), m)
+        r = subprocess.run([exe, name], cwd=d, capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, OMP_NUM_THREADS="4"))
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[tag] = (d, r)
+    return out
+
+
+def test_usage_and_missing_file(tmp_path):
+    r = subprocess.run([MD_B200], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage:" in r.stderr             # MD.cpp:74-79
+    r = subprocess.run([MD_B200, "nope"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "nope.mpd" in (r.stderr + r.stdout)
+
+
+def test_liposome_run_matches_reference_outputs(tmp_path, orc):
+    m = workloads.liposome(400, 3.45, 11)
+    m.update(finalTime=4.0, storeInterval=2.0, measureInterval=0.4)      # 200 steps, 2 stores, 10 measures
+    res = run_pair(tmp_path, orc, m, "lip")
+    d, r = res["ours"]
+    names = ["potential_", "size_", "lBond_", "bend_", "temp_", "kinetic_", "flicker_", "kEnergyDensity_"]
+    for nm in names:
+        assert (d / f"{nm}lip.dat").exists(), nm
+    assert not (d / "resizeHist_lip.dat").exists()                     # deltaLXY absent
+    pot = table(d / "potential_lip.dat")
+    assert [round(x[0], 6) for x in pot] == [round(0.4 * k, 6) for k in range(11)]
+    frames = open(d / "frames_lip.xyz").read().split("\n")
+    assert frames[0] == "1200" and frames[1] == "test" and len(frames) == 3 * 1202 + 1
+    chk = orc.read_mpd(str(d / "lip.mpd"))
+    assert chk["initialTime"] == 4.0 and chk["nParticles"] == 1200 and chk["molecules"][0]["bonds"].tolist() == [[0, 400, 3]]
+    assert "Resize acceptance ratio" in r.stderr and "starting main loop" in r.stderr
+    if "ref" not in res:
+        pytest.skip("oracle/_ref/MD not built: reference side of the comparison unavailable")
+    dr, rr = res["ref"]
+    assert sorted(os.listdir(d)) == sorted(os.listdir(dr))             # same set of files
+    for nm in names[:-1]:
+        a, b = table(d / f"{nm}lip.dat"), table(dr / f"{nm}lip.dat")
+        assert len(a) == len(b), nm
+        assert [x[0] for x in a] == [x[0] for x in b], nm              # same time stamps
+        assert np.allclose(a[0], b[0], rtol=1e-5, equal_nan=True), nm  # t = 0: same configuration, 6 printed digits
+    for nm in ("size_", "temp_", "lBond_", "bend_"):                   # deterministic columns agree throughout
+        assert np.allclose(table(d / f"{nm}lip.dat"), table(dr / f"{nm}lip.dat"), rtol=1e-5, equal_nan=True), nm
+    # thermodynamics: different noise streams, same ensemble
+    ka, kb = np.array(table(d / "kinetic_lip.dat"))[3:, 1], np.array(table(dr / "kinetic_lip.dat"))[3:, 1]
+    pa, pb = np.array(pot)[3:, 1], np.array(table(dr / "potential_lip.dat"))[3:, 1]
+    assert abs(ka.mean() - kb.mean()) < 0.08 * kb.mean()
+    assert abs(pa.mean() - pb.mean()) < 0.08 * abs(pb.mean())
+    cr = orc.read_mpd(str(dr / "lip.mpd"))
+    for k in ("initialTime", "finalTime", "nParticles", "seed", "storeInterval", "measureInterval", "size"):
+        assert chk[k] == cr[k], k
+    assert open(dr / "frames_lip.xyz").read().count("test\n") == 3
+
+
+def test_bilayer_with_tension_box_moves_and_restart(tmp_path, orc):
+    m = workloads.bilayer(600, 3.11, 5, tension=0.5)
+    m.update(finalTime=1.6, storeInterval=0.8, measureInterval=0.4)      # 80 steps: MC trials at 8, 16, ..., 80
+    res = run_pair(tmp_path, orc, m, "bl")
+    d, r = res["ours"]
+    hist = table(d / "resizeHist_bl.dat")
+    assert abs(sum(h[1] + h[2] for h in hist) - 10.0) < 1e-9               # 10 trials, each lands in one bin
+    ratio = float(r.stderr.split("Resize acceptance ratio:")[1].split()[0])
+    assert 0.0 <= ratio <= 1.0
+    size = table(d / "size_bl.dat")
+    v0, v1 = size[0][1] * size[0][2] * size[0][3], size[-1][1] * size[-1][2] * size[-1][3]
+    assert abs(v1 - v0) < 1e-4 * v0                                         # constant-volume moves (6 printed digits)
+    assert any(row[1] != size[0][1] for row in size)                        # and the box did move
+    if "ref" in res:
+        dr, rr = res["ref"]
+        assert len(table(dr / "resizeHist_bl.dat")) == len(hist)
+        assert sorted(os.listdir(d)) == sorted(os.listdir(dr))
+    # restart from the checkpoint the run left behind (MD.cpp:274-308): continues to a later finalTime
+    chk = orc.read_mpd(str(d / "bl.mpd"))
+    assert chk["initialTime"] == 1.6
+    chk["finalTime"] = 2.0
+    d2 = tmp_path / "restart"
+    d2.mkdir()
+    orc.write_mpd(str(d2 / "bl.mpd"), chk)
+    r2 = subprocess.run([MD_B200, "bl"], cwd=d2, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    pot = table(d2 / "potential_bl.dat")
+    assert [round(x[0], 6) for x in pot] == [2.0]                          # no t0 sample on restart, one measure at 2.0
+    assert not (d2 / "frames_bl.xyz").exists() or open(d2 / "frames_bl.xyz").read().count("test\n") == 0
