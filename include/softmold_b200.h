@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SMD_ABI_VERSION 1
+#define SMD_ABI_VERSION 2
 
 enum {
 	SMD_OK = 0,
@@ -199,6 +199,7 @@ enum { SMD_PHASE_INTEGRATE1 = 0,  /* bead mass, Verlet::first (+ cell tagging), 
        SMD_PHASE_LANGEVIN = 4,    /* Langevin::compute                                  MD.cpp:410     */
        SMD_PHASE_INTEGRATE2 = 5,  /* Verlet::second                                     MD.cpp:511     */
        SMD_PHASE_STEP = 6,        /* one whole smd_step_begin + smd_step_end                           */
+       SMD_PHASE_EXCHANGE = 7,    /* slab mode: migration + halo pack / unpack                         */
        SMD_NPHASES = 8 };
 int smd_profile(smd_ctx *ctx, uint32_t phase_mask);
 int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPHASES]);
@@ -207,6 +208,56 @@ int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPH
  * multiply-add, and with separate multiply + add (what this library issues: it is compiled without contraction to
  * stay bit-exact with the reference's x86-64 build).  Roofline denominator for the pair kernel. */
 int smd_fp64_peak(smd_ctx *ctx, double *fma_tflops, double *muladd_tflops);
+
+/* ------------------------------------------------------------------ slab decomposition over several GPUs
+ * The reference is one shared-memory process (its MPI attempt, MPImem.h / runMPI.cpp, does not compile any more);
+ * large flat-bilayer systems are decomposed here into slabs of cell columns along x, one context (= one GPU, one
+ * process) per slab, SURVEY.md 8(e).  A context created with desc.nranks > 1 is a slab rank:
+ *   - desc.n_particles is the GLOBAL particle count, desc.box the global box; desc.reserved[0] = local capacity in
+ *     particles (0: 1.25 * n/nranks + halo allowance), desc.reserved[1] = entries per halo message (0: default);
+ *   - smd_set_particles takes the GLOBAL arrays (every rank passes the same data) and keeps what this rank owns plus
+ *     its ghost columns; molecule records use global particle indices; only CHAIN molecules are supported;
+ *   - every step the ranks exchange migrating particles and the ghost-column halo (SMD_SLAB_HALO cell columns) by
+ *     writing straight into the neighbour's receive buffer through peer memory (NVLink), inside smd_step_begin
+ *     (send) and smd_step_end (receive): wire the buffers once with smd_slab_ipc_handle / smd_slab_connect_ipc
+ *     (neighbour in another process) or smd_slab_recv_buffer / smd_slab_connect_ptr (same process);
+ *   - smd_potential / smd_dpotential / smd_kinetic / smd_count_pairs return this rank's PARTIAL sums: every pair and
+ *     bonded term is counted by exactly one rank, the caller all-reduces (smd_count_pairs: sum of the owned
+ *     particles' neighbour counts, NOT halved);  smd_mc_box_move is replaced by smd_mc_propose -> smd_dpotential ->
+ *     all-reduce -> smd_mc_accept -> smd_rescale, evaluated identically on every rank;
+ *   - read-back is per rank: smd_slab_get_local. */
+#define SMD_SLAB_HALO 2
+
+/* owned cell columns [col_lo, col_hi) of `rank` when n_cols columns are dealt to nranks slabs (pure host function) */
+int smd_slab_columns(int32_t n_cols, int32_t nranks, int32_t rank, int32_t *col_lo, int32_t *col_hi);
+/* which of the n particles a slab rank keeps: flags[i] = 0 none, 1 owned, 2 ghost (pure host function; the cell
+ * column is int(x / (Lx / int(Lx / cutoff))) with the upper-edge clamp, exactly CellOpt::build's, cellOpt.h:530-539) */
+int smd_slab_select(const double box[3], double cutoff, int32_t nranks, int32_t rank, int32_t n, const double *xyz,
+                    int32_t *flags);
+
+/* own receive buffer of `side` (0: filled by the left neighbour, 1: by the right one) */
+int smd_slab_recv_buffer(smd_ctx *ctx, int32_t side, void **ptr, size_t *bytes);
+/* 64-byte CUDA IPC handle of that buffer, to be shipped to the neighbour process */
+int smd_slab_ipc_handle(smd_ctx *ctx, int32_t side, void *handle64);
+/* dir 0: the buffer is the LEFT neighbour's side-1 receive buffer; dir 1: the RIGHT neighbour's side-0 one */
+int smd_slab_connect_ipc(smd_ctx *ctx, int32_t dir, const void *handle64);
+int smd_slab_connect_ptr(smd_ctx *ctx, int32_t dir, void *peer_buffer);
+/* the two halves of the exchange, for callers that move particles themselves (smd_step_begin / _end call them) */
+int smd_slab_exchange_send(smd_ctx *ctx);
+int smd_slab_exchange_recv(smd_ctx *ctx);
+/* live counts of this rank (synchronises) */
+int smd_slab_counts(smd_ctx *ctx, int32_t *n_local, int32_t *n_owned);
+/* owned particles of this rank, arbitrary order: global index, position, type, velocity, acceleration.  The arrays
+ * must hold the local capacity (smd_slab_capacity); any pointer may be NULL.  *n = number returned. */
+int smd_slab_capacity(smd_ctx *ctx, int32_t *capacity);
+int smd_slab_get_local(smd_ctx *ctx, int32_t *n, int32_t *gid, double *xyz, int32_t *type, double *vel, double *acc);
+
+/* The host arithmetic of one Metropolis box-move trial, MD.cpp:591-613 and :677-695, shared by smd_mc_box_move and by
+ * multi-rank drivers: propose new box + component-wise scale from u_fluct; decide from the all-reduced sum of the
+ * dPotential terms.  Returns 1 = accepted, 0 = rejected in *accepted. */
+int smd_mc_propose(const double box[3], double deltaLXY, double u_fluct, double new_box[3], double scale[3]);
+int smd_mc_accept(double dU_terms_sum, double tension, const double box[3], const double new_box[3], double temperature,
+                  double u_accept, int32_t *accepted, double *dU_total);
 
 /* ------------------------------------------------------------------ host-side file boundary (no GPU needed)
  * `.mpd` reader / writer with the semantics of Script<T,Blob>::read/write + Blob::input/output

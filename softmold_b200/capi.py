@@ -18,7 +18,8 @@ MASK_LANGEVIN = 1 << 16
 MASK_ALL_MOLECULES = sum(1 << t for t in (TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL))
 MASK_ALL = (1 << TERM_PAIR) | MASK_ALL_MOLECULES | MASK_LANGEVIN
 NOISE_PHILOX, NOISE_EXTERNAL = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
+SLAB_HALO = 2
 
 # every symbol include/softmold_b200.h declares
 SYMBOLS = [
@@ -30,6 +31,9 @@ SYMBOLS = [
     "smd_count_pairs", "smd_synchronize", "smd_device_ptr", "smd_stream", "smd_stats", "smd_profile", "smd_profile_read", "smd_fp64_peak", "smd_mpd_read", "smd_mpd_write",
     "smd_mpd_free", "smd_mpd_get_scalar", "smd_mpd_set_scalar", "smd_mpd_get_size", "smd_mpd_set_size",
     "smd_mpd_particles", "smd_mpd_pair_tables", "smd_mpd_n_molecules", "smd_mpd_molecule", "smd_create_from_mpd",
+    "smd_slab_columns", "smd_slab_select", "smd_slab_recv_buffer", "smd_slab_ipc_handle", "smd_slab_connect_ipc",
+    "smd_slab_connect_ptr", "smd_slab_exchange_send", "smd_slab_exchange_recv", "smd_slab_counts", "smd_slab_capacity",
+    "smd_slab_get_local", "smd_mc_propose", "smd_mc_accept",
 ]
 
 
@@ -111,6 +115,19 @@ def lib():
         L.smd_mpd_n_molecules.argtypes = [vp]
         L.smd_mpd_molecule.argtypes = [vp, i32, ip, ip, ip, C.POINTER(ip), ip, C.POINTER(dp)]
         L.smd_create_from_mpd.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+        L.smd_slab_columns.argtypes = [i32, i32, i32, ip, ip]
+        L.smd_slab_select.argtypes = [vp, dbl, i32, i32, i32, vp, vp]
+        L.smd_slab_recv_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.smd_slab_ipc_handle.argtypes = [vp, i32, vp]
+        L.smd_slab_connect_ipc.argtypes = [vp, i32, vp]
+        L.smd_slab_connect_ptr.argtypes = [vp, i32, vp]
+        L.smd_slab_exchange_send.argtypes = [vp]
+        L.smd_slab_exchange_recv.argtypes = [vp]
+        L.smd_slab_counts.argtypes = [vp, ip, ip]
+        L.smd_slab_capacity.argtypes = [vp, ip]
+        L.smd_slab_get_local.argtypes = [vp, ip, vp, vp, vp, vp, vp]
+        L.smd_mc_propose.argtypes = [vp, dbl, dbl, vp, vp]
+        L.smd_mc_accept.argtypes = [dbl, dbl, vp, vp, dbl, dbl, ip, dp]
         _lib = L
     return _lib
 
@@ -132,7 +149,7 @@ class Context:
     the reference's CellOpt / Verlet / Langevin / Blob::do* seams (see include/softmold_b200.h)."""
 
     def __init__(self, n_particles, n_types, box, cutoff, dt, gamma, temperature, seed, device=0,
-                 noise=NOISE_PHILOX, track_unwrapped=False, _handle=None):
+                 noise=NOISE_PHILOX, track_unwrapped=False, _handle=None, rank=0, nranks=1, capacity=0, msg_capacity=0):
         self.L = lib()
         self.n = int(n_particles)
         self.n_types = int(n_types)
@@ -145,7 +162,10 @@ class Context:
         d.box = (C.c_double * 3)(*[float(x) for x in box])
         d.cutoff, d.dt, d.gamma, d.temperature = float(cutoff), float(dt), float(gamma), float(temperature)
         d.seed, d.noise, d.track_unwrapped = int(seed), int(noise), int(bool(track_unwrapped))
-        d.rank, d.nranks = 0, 1
+        d.rank, d.nranks = int(rank), int(nranks)   # nranks > 1: slab rank (n_particles, box are the global ones)
+        d.reserved[0], d.reserved[1] = int(capacity), int(msg_capacity)
+        self.rank, self.nranks = int(rank), int(nranks)
+        self.temperature = float(temperature)
         h = C.c_void_p()
         rc = self.L.smd_create(C.byref(d), C.byref(h))
         if rc:
@@ -169,10 +189,11 @@ class Context:
             raise SoftMoldError(rc, self.L.smd_last_error(self.h).decode())
 
     @classmethod
-    def from_dict(cls, m, device=0, noise=NOISE_PHILOX, track_unwrapped=False):
-        """m: dict with the .mpd fields (as oracle.orc.read_mpd / load_golden produce them)"""
+    def from_dict(cls, m, device=0, noise=NOISE_PHILOX, track_unwrapped=False, **slab):
+        """m: dict with the .mpd fields (as oracle.orc.read_mpd / load_golden produce them); slab: rank, nranks,
+        capacity, msg_capacity for a slab rank of a multi-GPU run (m is always the GLOBAL system)"""
         ctx = cls(m["nParticles"], m["nTypes"], m["size"], m["cutoff"], m["deltaT"], m["gamma"], m["initialTemp"],
-                  m["seed"], device=device, noise=noise, track_unwrapped=track_unwrapped)
+                  m["seed"], device=device, noise=noise, track_unwrapped=track_unwrapped, **slab)
         ctx.set_pair_tables(m["twoBodyFconst"], m["twoBodyUconst"])
         ctx.set_particles(m["xyz"], m["type"], m["vel"])
         for mol in m["molecules"]:
@@ -191,6 +212,43 @@ class Context:
         vel = None if vel is None else _f64(vel)
         self._ck(self.L.smd_set_particles(self.h, _ptr(xyz), _ptr(typ), _ptr(vel)))
 
+    # -- slab decomposition (include/softmold_b200.h, "slab decomposition over several GPUs")
+    def slab_recv_buffer(self, side):
+        p, b = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.smd_slab_recv_buffer(self.h, side, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def slab_ipc_handle(self, side):
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.smd_slab_ipc_handle(self.h, side, buf))
+        return buf.raw
+
+    def slab_connect_ipc(self, direction, handle):
+        self._ck(self.L.smd_slab_connect_ipc(self.h, direction, C.create_string_buffer(handle, 64)))
+
+    def slab_connect_ptr(self, direction, ptr):
+        self._ck(self.L.smd_slab_connect_ptr(self.h, direction, C.c_void_p(ptr)))
+
+    def slab_counts(self, owned=True):
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self.L.smd_slab_counts(self.h, C.byref(a), C.byref(b) if owned else None))
+        return a.value, b.value
+
+    def slab_capacity(self):
+        a = C.c_int32()
+        self._ck(self.L.smd_slab_capacity(self.h, C.byref(a)))
+        return a.value
+
+    def slab_get_local(self):
+        """owned particles of this rank: (gid, xyz, type, vel, acc), arbitrary order"""
+        cap = self.slab_capacity()
+        n = C.c_int32()
+        gid, typ = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        xyz, vel, acc = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3))
+        self._ck(self.L.smd_slab_get_local(self.h, C.byref(n), _ptr(gid), _ptr(xyz), _ptr(typ), _ptr(vel), _ptr(acc)))
+        k = n.value
+        return gid[:k], xyz[:k], typ[:k], vel[:k], acc[:k]
+
     def add_molecule(self, mtype, records, constants):
         r, c = _i32(records), _f64(constants)
         n = len(r)
@@ -201,6 +259,7 @@ class Context:
         self._ck(f(self.h, n, _ptr(r), _ptr(c)))
 
     def set_temperature(self, T):
+        self.temperature = float(T)
         self._ck(self.L.smd_set_temperature(self.h, float(T)))
 
     def set_noise(self, u):
@@ -319,7 +378,7 @@ class Context:
         return a.value, b.value
 
 
-PHASES = ["integrate1", "build", "pair", "molecules", "langevin", "integrate2", "step"]
+PHASES = ["integrate1", "build", "pair", "molecules", "langevin", "integrate2", "step", "exchange"]
 
 
 class Mpd:
@@ -411,3 +470,33 @@ class Mpd:
         n, _ = self.scalar("nParticles")
         nT, _ = self.scalar("nTypes")
         return Context(int(n), int(nT), None, None, None, None, None, None, _handle=h)
+
+
+def slab_columns(n_cols, nranks, rank):
+    lo, hi = C.c_int32(), C.c_int32()
+    if lib().smd_slab_columns(n_cols, nranks, rank, C.byref(lo), C.byref(hi)):
+        raise ValueError("bad slab arguments")
+    return lo.value, hi.value
+
+
+def slab_select(box, cutoff, nranks, rank, xyz):
+    """flags per particle: 0 not on this rank, 1 owned, 2 ghost"""
+    xyz, box = _f64(xyz), _f64(box)
+    flags = np.zeros(len(xyz), np.int32)
+    if lib().smd_slab_select(_ptr(box), float(cutoff), nranks, rank, len(xyz), _ptr(xyz), _ptr(flags)):
+        raise ValueError("bad slab arguments")
+    return flags
+
+
+def mc_propose(box, deltaLXY, u_fluct):
+    box, new_box, scale = _f64(box), np.zeros(3), np.zeros(3)
+    lib().smd_mc_propose(_ptr(box), float(deltaLXY), float(u_fluct), _ptr(new_box), _ptr(scale))
+    return new_box, scale
+
+
+def mc_accept(dU_terms_sum, tension, box, new_box, temperature, u_accept):
+    acc, dU = C.c_int32(), C.c_double()
+    box, new_box = _f64(box), _f64(new_box)
+    lib().smd_mc_accept(float(dU_terms_sum), float(tension), _ptr(box), _ptr(new_box), float(temperature), float(u_accept),
+                        C.byref(acc), C.byref(dU))
+    return bool(acc.value), dU.value

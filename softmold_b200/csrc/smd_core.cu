@@ -37,6 +37,11 @@ static inline int nblk(long long n, int tpb) { return (int)std::max<long long>(1
 
 static const int MAX_PARTIALS = 1 << 20;
 
+// particle count of a launch: by value on a single GPU, from the device word in slab mode (ctx->N is then only the
+// launch bound).  cnt_ext: the count after an unpack (received particles appended, dead ghosts still in place).
+static inline Cnt cnt_of(const smd_ctx *ctx) { Cnt c; c.n = ctx->N; c.dn = ctx->slab ? ctx->dN : nullptr; return c; }
+static inline Cnt cnt_ext(const smd_ctx *ctx) { Cnt c; c.n = ctx->N; c.dn = ctx->slab ? ctx->dN + 1 : nullptr; return c; }
+
 // ------------------------------------------------------------------------------------------------ phase timing
 static cudaEvent_t prof_event(smd_ctx *ctx)
 {
@@ -118,6 +123,14 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 		g.cs[d] = box[d] / g.nc[d];                   // cellOpt.h:207-209 / :1560-1562
 	}
 	g.rc2 = ctx->desc.cutoff * ctx->desc.cutoff;
+	g.slab = 0; g.col_lo = 0; g.col_hi = g.nc[0]; g.halo = 0;
+	if (ctx->slab) {
+		g.slab = 1;
+		g.halo = SMD_SLAB_HALO;
+		int32_t lo = 0, hi = g.nc[0];
+		smd_slab_columns(g.nc[0], ctx->desc.nranks, ctx->desc.rank, &lo, &hi);
+		g.col_lo = lo; g.col_hi = hi;
+	}
 	// FP32 prefilter threshold of k_pair_force2: absolute coordinates (and image shifts) up to maxL carry a rounding
 	// error of maxL * 2^-24 each; a difference of two of them plus its own rounding stays below 4 of those, so
 	// |r2_32 - r2_64| < 2 * sqrt(3) * rc * 4 * maxL * 2^-24 + (FP32 rounding of the squares).  32 * rc * that ulp
@@ -152,8 +165,12 @@ static int check_geom(smd_ctx *ctx)
 			return SMD_ERR_UNSUPPORTED;
 		}
 	}
-	if (g.nc[0] > 2048 || g.nc[1] > 2048 || g.nc[2] > 1024) {
-		ctx->err = "cell grid exceeds 2048 x 2048 x 1024 cells";
+	if (g.nc[0] > 2047 || g.nc[1] > 2047 || g.nc[2] > 1023) {
+		ctx->err = "cell grid exceeds 2047 x 2047 x 1023 cells";
+		return SMD_ERR_UNSUPPORTED;
+	}
+	if (ctx->slab && g.col_hi - g.col_lo < 2 * g.halo + 1) {
+		ctx->err = "slab narrower than 2 * halo + 1 cell columns: use fewer ranks for this box";
 		return SMD_ERR_UNSUPPORTED;
 	}
 	return SMD_OK;
@@ -180,8 +197,21 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	smd_ctx *ctx = new smd_ctx();
 	ctx->desc = *desc;
 	ctx->N = desc->n_particles;
+	ctx->n_global = desc->n_particles;
 	ctx->nT = desc->n_types;
 	ctx->cap = ((std::max(ctx->N, 1) + 255) / 256) * 256;
+	ctx->slab = desc->nranks > 1;
+	memset(&ctx->comm, 0, sizeof ctx->comm);
+	if (ctx->slab) {
+		if (desc->rank < 0 || desc->rank >= desc->nranks) { g_create_error = "rank outside [0, nranks)"; delete ctx; return SMD_ERR_ARG; }
+		if (desc->n_particles >= GID_GHOST) { g_create_error = "slab mode supports fewer than 2^30 particles"; delete ctx; return SMD_ERR_UNSUPPORTED; }
+		if (desc->noise == SMD_NOISE_EXTERNAL) { g_create_error = "slab mode uses the Philox noise only"; delete ctx; return SMD_ERR_UNSUPPORTED; }
+		long long want = desc->reserved[0] > 0 ? desc->reserved[0]
+		                                       : (long long)(1.25 * desc->n_particles / desc->nranks) + 65536;
+		ctx->cap = (int)(((std::min<long long>(want, (long long)desc->n_particles + 65536) + 255) / 256) * 256);
+		ctx->N = ctx->cap;   // launch bound; the live count is the device word dN[0]
+		ctx->comm.capmsg = desc->reserved[1] > 0 ? desc->reserved[1] : std::max(16384, ctx->cap / 8);
+	}
 	ctx->temperature = desc->temperature;
 	ctx->device = desc->device;
 	ctx->cur = 0;
@@ -223,7 +253,24 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
 	CKC(cudaMemset(ctx->acc, 0, 3 * cap * sizeof(double)));
 	CKC(cudaMalloc(&ctx->acc2, 3 * cap * sizeof(double)));
-	CKC(cudaMalloc(&ctx->slot_of, cap * sizeof(int)));
+	CKC(cudaMalloc(&ctx->slot_of, (size_t)std::max<size_t>(cap, (size_t)ctx->n_global) * sizeof(int)));
+	CKC(cudaMemset(ctx->slot_of, 0xff, (size_t)std::max<size_t>(cap, (size_t)ctx->n_global) * sizeof(int)));
+	CKC(cudaMalloc(&ctx->dN, 2 * sizeof(int)));
+	CKC(cudaMemset(ctx->dN, 0, 2 * sizeof(int)));
+	CKC(cudaMalloc(&ctx->d_export_counter, sizeof(int)));
+	for (int b = 0; b < 2; b++) CKC(cudaMemset(ctx->gid[b], 0, cap * sizeof(int)));
+	if (ctx->slab) {
+		// receive buffers: [side][parity] = header + capmsg entries; the neighbours write them through peer memory
+		ctx->comm.parity_stride = (sizeof(SlabMsgHeader) + (size_t)ctx->comm.capmsg * sizeof(SlabMsgEntry) + 255) / 256 * 256;
+		ctx->recv_bytes = 2 * ctx->comm.parity_stride;
+		for (int sd = 0; sd < 2; sd++) {
+			CKC(cudaMalloc(&ctx->recv_base[sd], ctx->recv_bytes));
+			CKC(cudaMemset(ctx->recv_base[sd], 0, ctx->recv_bytes));
+			ctx->comm.recv[sd] = ctx->recv_base[sd];
+		}
+		CKC(cudaMalloc(&ctx->comm.counters, 4 * sizeof(int)));
+		CKC(cudaMemset(ctx->comm.counters, 0, 4 * sizeof(int)));
+	}
 	// dense offset table over the occupied window of the reference grid; capacity = whole grid up to 64 Mi cells
 	long long total = (long long)ctx->geom.nc[0] * ctx->geom.nc[1] * ctx->geom.nc[2];
 	ctx->cellcap = std::min<long long>(std::max<long long>(2 * total, 1 << 16), 64ll << 20);
@@ -285,6 +332,12 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
 	cudaFree(ctx->icount); cudaFree(ctx->stage); cudaFree(ctx->istage);
 	cudaFreeHost(ctx->h_pinned);
+	cudaFree(ctx->dN); cudaFree(ctx->d_export_counter);
+	for (int sd = 0; sd < 2; sd++) {
+		if (ctx->ipc_opened[sd]) cudaIpcCloseMemHandle(ctx->ipc_opened[sd]);
+		cudaFree(ctx->recv_base[sd]);
+	}
+	cudaFree(ctx->comm.counters);
 	for (auto &b : ctx->bonds) cudaFree(b.d_ij);
 	for (auto &b : ctx->bends) cudaFree(b.d_ijk);
 	for (auto &b : ctx->balls) cudaFree(b.d_cj);
@@ -306,6 +359,11 @@ static int check_device_errors(smd_ctx *ctx)
 		ctx->err = "device-side cell error:";
 		if (flag & ERR_OUT_OF_BOX) ctx->err += " particle outside the box or NaN position (reference: 'cell placement is on boundary', cellOpt.h:541-552)";
 		if (flag & ERR_WINDOW_CAP) ctx->err += " occupied cell window exceeds the offset-table capacity";
+		if (flag & ERR_SLAB_MIGRATION) ctx->err += " slab: a particle left its slab by more than the halo width in one step";
+		if (flag & ERR_SLAB_MSG_CAP) ctx->err += " slab: halo message capacity exceeded (desc.reserved[1])";
+		if (flag & ERR_SLAB_CAPACITY) ctx->err += " slab: local particle capacity exceeded (desc.reserved[0])";
+		if (flag & ERR_SLAB_TIMEOUT) ctx->err += " slab: timed out waiting for a neighbour's halo message";
+		if (flag & ERR_SLAB_MISSING) ctx->err += " slab: a chain member is neither owned nor inside the halo";
 		return SMD_ERR_CELL;
 	}
 	return SMD_OK;
@@ -383,7 +441,7 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 static int retag_cells(smd_ctx *ctx)
 {
 	LAUNCH(k_arm_bbox, 1, 32, 0, ctx->bbox);
-	LAUNCH(k_tag_cells, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], ctx->geom, ctx->bbox, ctx->errflag);
+	LAUNCH(k_tag_cells, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->cur], ctx->geom, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur]);
 	ctx->cells_valid = false;
 	return SMD_OK;
 }
@@ -393,7 +451,7 @@ extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t 
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(xyz && type, "null positions / types");
 	CK(cudaSetDevice(ctx->device));
-	int N = ctx->N;
+	int N = ctx->n_global;
 	// the reference refuses out-of-box particles at load (system.h:452-469)
 	for (int i = 0; i < N; i++)
 		for (int d = 0; d < 3; d++) {
@@ -408,12 +466,37 @@ extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t 
 	for (int i = 0; i < N; i++)
 		if (type[i] < 0 || type[i] >= ctx->nT) { ctx->err = "particle type out of range"; return SMD_ERR_ARG; }
 	double *sx = ctx->stage, *sv = ctx->stage + 3 * (size_t)ctx->cap;
+	const int *gid_in = nullptr;
+	std::vector<double> lx, lv;
+	std::vector<int> lt, lg;
+	if (ctx->slab) {
+		// keep what this rank owns plus its ghost columns; every rank was handed the same global arrays
+		std::vector<int32_t> flags((size_t)N);
+		smd_slab_select(ctx->geom.box, ctx->desc.cutoff, ctx->desc.nranks, ctx->desc.rank, N, xyz, flags.data());
+		for (int i = 0; i < N; i++) {
+			if (!flags[i]) continue;
+			for (int d = 0; d < 3; d++) { lx.push_back(xyz[3 * i + d]); lv.push_back(vel ? vel[3 * i + d] : 0.0); }
+			lt.push_back(type[i]);
+			lg.push_back(flags[i] == 2 ? (i | GID_GHOST) : i);
+		}
+		N = (int)lt.size();
+		if (N > ctx->cap) { ctx->err = "slab: local particle capacity exceeded at load (desc.reserved[0])"; return SMD_ERR_ARG; }
+		xyz = lx.data(); type = lt.data(); vel = lv.data();
+		int *dg = ctx->istage + ctx->cap;
+		CK(cudaMemcpyAsync(dg, lg.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+		gid_in = dg;
+		CK(cudaMemsetAsync(ctx->slot_of, 0xff, (size_t)ctx->n_global * sizeof(int), ctx->stream));
+		int nn[2] = {N, N};
+		CK(cudaMemcpyAsync(ctx->dN, nn, sizeof nn, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->exch_pending = false;
+	}
 	CK(cudaMemcpyAsync(sx, xyz, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->istage, type, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 	if (vel) CK(cudaMemcpyAsync(sv, vel, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	ctx->cur = 0;
-	LAUNCH(k_import_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, sx, ctx->istage, vel ? sv : nullptr, ctx->pos[0], ctx->vel[0],
-	       ctx->unw[0], ctx->gid[0], ctx->slot_of);
+	if (N > 0)
+		LAUNCH(k_import_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, sx, ctx->istage, vel ? sv : nullptr, ctx->pos[0], ctx->vel[0],
+		       ctx->unw[0], ctx->gid[0], ctx->slot_of, gid_in);
 	CK(cudaMemsetAsync(ctx->acc, 0, 3 * (size_t)ctx->cap * sizeof(double), ctx->stream));
 	ctx->acc_live = false;
 	retag_cells(ctx);
@@ -426,7 +509,7 @@ extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t 
 static int check_index(smd_ctx *ctx, const int32_t *v, size_t n, const char *what)
 {
 	for (size_t i = 0; i < n; i++)
-		if (v[i] < 0 || v[i] >= ctx->N) {
+		if (v[i] < 0 || v[i] >= ctx->n_global) {
 			ctx->err = std::string(what) + " index out of bounds";   // Blob::errorChecking, system.h:483-545
 			return SMD_ERR_ARG;
 		}
@@ -441,7 +524,7 @@ extern "C" int smd_add_chain(smd_ctx *ctx, int32_t n_blocks, const int32_t *bloc
 		ChainBlock cb;
 		cb.start = blocks[3 * j]; cb.nChains = blocks[3 * j + 1]; cb.len = blocks[3 * j + 2];
 		long long end = (long long)cb.start + (long long)cb.nChains * cb.len;
-		REQUIRE(cb.start >= 0 && cb.nChains >= 0 && end <= ctx->N, "CHAIN Molecule is out of bounds!");
+		REQUIRE(cb.start >= 0 && cb.nChains >= 0 && end <= ctx->n_global, "CHAIN Molecule is out of bounds!");
 		REQUIRE(cb.len >= 3, "CHAIN length below 3 is undefined in the reference (system.h:1834-1836)");
 		for (int k = 0; k < 4; k++) cb.c[k] = c[k];
 		ctx->chains.push_back(cb);
@@ -465,6 +548,7 @@ extern "C" int smd_add_bonds(smd_ctx *ctx, int32_t n, const int32_t *ij, const d
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (ij || n == 0) && c, "bad BOND arguments");
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, ij, 2 * (size_t)n, "BOND Molecule");
 	if (rc) return rc;
 	BondList b;
@@ -480,6 +564,7 @@ extern "C" int smd_add_bends(smd_ctx *ctx, int32_t n, const int32_t *ijk, const 
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (ijk || n == 0) && c, "bad BEND arguments");
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, ijk, 3 * (size_t)n, "BEND Molecule");
 	if (rc) return rc;
 	BendList b;
@@ -522,6 +607,7 @@ extern "C" int smd_add_beads(smd_ctx *ctx, int32_t n, const int32_t *idx, const 
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (idx || n == 0) && C, "bad BEAD arguments");
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, idx, (size_t)n, "BEAD Molecule");
 	if (rc) return rc;
 	CK(cudaSetDevice(ctx->device));
@@ -563,13 +649,16 @@ static int build_cells(smd_ctx *ctx)
 {
 	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1;
 	// particles were tagged with their cell (and bbox[] accumulated) by whoever moved them last
-	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, N, ctx->pos[cur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot);
+	if (ctx->slab && !ctx->ext_valid)   // no unpack since the last build: the extended count is the current one
+		CK(cudaMemcpyAsync(ctx->dN + 1, ctx->dN, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+	ctx->ext_valid = false;
+	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[cur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag);
 	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
 	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, ctx->win, ctx->geom, ctx->cellcap, ctx->errflag,
 	       (ctx->rebuilds & 255) == 255 ? 1 : 0);
-	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N);
-	LAUNCH(k_place, nblk(N, TPB), TPB, 0, N, ctx->cellOfSlot, ctx->cursor, ctx->order);
-	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[cur], ctx->pos[nxt],
+	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N, ctx->slab ? ctx->dN : nullptr);
+	LAUNCH(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order);
+	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[cur], ctx->pos[nxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
 	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut);
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
@@ -600,9 +689,14 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 {
 	const Particle *pos = ctx->pos[ctx->cur];
 	if (mask & SMD_MASK(SMD_TERM_CHAIN))
-		for (auto &cb : ctx->chains)
-			if (cb.nChains > 0)
+		for (auto &cb : ctx->chains) {
+			if (cb.nChains <= 0) continue;
+			if (ctx->slab)
+				LAUNCH(k_chain_slab<0>, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cb,
+				       ctx->acc, nullptr, 1.0, 1.0, 1.0, ctx->errflag);
+			else
 				LAUNCH(k_chain<0>, nblk(cb.nChains, TPB), TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, cb, ctx->acc, nullptr, 1.0, 1.0, 1.0);
+		}
 	if (mask & SMD_MASK(SMD_TERM_BOND))
 		for (auto &b : ctx->bonds)
 			if (b.n > 0)
@@ -641,7 +735,7 @@ static int add_langevin(smd_ctx *ctx, int64_t step)
 		ext = ctx->noise;
 		ctx->noise_ready = false;
 	}
-	LAUNCH(k_langevin, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->cap, ctx->vel[ctx->cur], ctx->acc, ctx->gid[ctx->cur], ctx->desc.gamma, sigma,
+	LAUNCH(k_langevin, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->vel[ctx->cur], ctx->acc, ctx->gid[ctx->cur], ctx->desc.gamma, sigma,
 	       ctx->desc.seed, (uint64_t)step, ext);
 	return SMD_OK;
 }
@@ -665,6 +759,10 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 	int N = ctx->N;
 	// CellOpt::build: always rebuilt (the reference rebuilds every step, MD.cpp:412)
 	ctx->acc_live = false;   // about to be overwritten: no need to carry it through the build
+	if (ctx->slab && ctx->exch_pending) {
+		int rcx = smd_slab_exchange_recv(ctx);
+		if (rcx) return rcx;
+	}
 	if (!ctx->cells_valid) { ProfScope ps(ctx, SMD_PHASE_BUILD); build_cells(ctx); }
 	int rc;
 	LangevinArgs lg = {};
@@ -682,14 +780,14 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
 		ProfScope ps(ctx, SMD_PHASE_PAIR);
 		if (ctx->tables_symmetric)
-			LAUNCH((k_pair_force2<true, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+			LAUNCH((k_pair_force2<true, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
 		else
-			LAUNCH((k_pair_force2<true, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+			LAUNCH((k_pair_force2<true, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
 		ctx->acc_live = true;
 	} else {
-		LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc);
+		LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->acc);
 		ctx->acc_live = true;
 		if (langevin_first && lang) {
 			ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
@@ -698,11 +796,11 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		if (pair) {
 			ProfScope ps(ctx, SMD_PHASE_PAIR);
 			if (ctx->tables_symmetric)
-				LAUNCH((k_pair_force2<false, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+				LAUNCH((k_pair_force2<false, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
 			else
-				LAUNCH((k_pair_force2<false, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg);
+				LAUNCH((k_pair_force2<false, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
+				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
 		}
 		if (!langevin_first && lang) {
 			ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
@@ -729,7 +827,7 @@ extern "C" int smd_resume(smd_ctx *ctx)
 	int rc = ready(ctx);
 	if (rc) return rc;
 	bead_mass_divide(ctx);
-	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);
+	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);
 	return SMD_OK;
 }
 
@@ -742,11 +840,12 @@ extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
 	int N = ctx->N;
 	ProfScope ps(ctx, SMD_PHASE_INTEGRATE1);
 	bead_mass_divide(ctx);                                                         // MD.cpp:340-355
-	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
-	       ctx->desc.dt, ctx->bbox, ctx->errflag);                                 // MD.cpp:356
+	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
+	       ctx->desc.dt, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur]);             // MD.cpp:356
 	// a = 0 (MD.cpp:357-366) is folded into the force evaluation that follows: it overwrites a[]
 	ctx->acc_live = false;
 	ctx->cells_valid = false;
+	if (ctx->slab) return smd_slab_exchange_send(ctx);   // migrants + halo on their way while the host enqueues the rest
 	return SMD_OK;
 }
 
@@ -760,7 +859,7 @@ extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
 	if (rc) return rc;
 	{ ProfScope ps(ctx, SMD_PHASE_MOLECULES); bead_mass_divide(ctx); }             // MD.cpp:480-494
 	ProfScope ps(ctx, SMD_PHASE_INTEGRATE2);
-	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);   // :511
+	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);   // :511
 	return SMD_OK;
 }
 
@@ -792,6 +891,7 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	int rc = ready(ctx);
 	if (rc) return rc;
 	int N = ctx->N;
+	if (ctx->slab && ctx->exch_pending) { ctx->err = "slab: energy call between smd_step_begin and smd_step_end"; return SMD_ERR_ARG; }
 	if (!ctx->cells_valid) build_cells(ctx);   // dataExtraction::compute rebuilds its own CellOpt (dataExtraction.h:839-841)
 	double sx = scale ? scale[0] : 1.0, sy = scale ? scale[1] : 1.0, sz = scale ? scale[2] : 1.0;
 	const Particle *pos = ctx->pos[ctx->cur];
@@ -801,14 +901,18 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + 2 * ctx->beads.size() <= 64, "too many molecule records for one energy call");
 	{
 		int nb = nblk(N, TPB);
-		LAUNCH(k_pair<(MODE == 1 ? PAIR_POTENTIAL : PAIR_DPOTENTIAL)>, nb, TPB, pair_smem(ctx), N, ctx->cap, pos, ctx->gid[ctx->cur], ctx->start,
+		LAUNCH(k_pair<(MODE == 1 ? PAIR_POTENTIAL : PAIR_DPOTENTIAL)>, nb, TPB, pair_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->gid[ctx->cur], ctx->start,
 		       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, nullptr, ctx->partials, nullptr, sx, sy, sz);
 		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
 	}
 	for (auto &cb : ctx->chains) {
 		if (cb.nChains <= 0) continue;
-		int nb = nblk(cb.nChains, TPB);
-		LAUNCH(k_chain<MODE>, nb, TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, cb, nullptr, ctx->partials, sx, sy, sz);
+		int nb = ctx->slab ? nblk(N, TPB) : nblk(cb.nChains, TPB);
+		if (ctx->slab)
+			LAUNCH(k_chain_slab<MODE>, nb, TPB, 0, cnt_of(ctx), ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cb, nullptr, ctx->partials,
+			       sx, sy, sz, ctx->errflag);
+		else
+			LAUNCH(k_chain<MODE>, nb, TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, cb, nullptr, ctx->partials, sx, sy, sz);
 		finish_sum(ctx, nb, push(SMD_TERM_CHAIN), 1.0);
 	}
 	for (auto &b : ctx->bonds) {
@@ -861,7 +965,7 @@ extern "C" int smd_kinetic(smd_ctx *ctx, double *out)
 	REQUIRE(out && ctx->particles_set, "bad call");
 	CK(cudaSetDevice(ctx->device));
 	int nb = std::min(nblk(ctx->N, 256), 1024);
-	LAUNCH(k_kinetic, nb, 256, 0, ctx->N, ctx->cap, ctx->vel[ctx->cur], ctx->partials);
+	LAUNCH(k_kinetic, nb, 256, 0, cnt_of(ctx), ctx->cap, ctx->vel[ctx->cur], ctx->gid[ctx->cur], ctx->partials);
 	finish_sum(ctx, nb, 0, 1.0);
 	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	int rc = check_device_errors(ctx);
@@ -878,7 +982,9 @@ extern "C" int smd_count_pairs(smd_ctx *ctx, int64_t *total, int32_t *per_partic
 	int N = ctx->N;
 	if (!ctx->cells_valid) build_cells(ctx);
 	int nb = nblk(N, TPB);
-	LAUNCH(k_pair<PAIR_COUNT>, nb, TPB, pair_smem(ctx), N, ctx->cap, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom,
+	if (ctx->slab && per_particle) { ctx->err = "slab: per-particle counts are not exported (use smd_slab_get_local)"; return SMD_ERR_UNSUPPORTED; }
+	if (ctx->slab) CK(cudaMemsetAsync(ctx->icount, 0, (size_t)ctx->cap * sizeof(int), ctx->stream));
+	LAUNCH(k_pair<PAIR_COUNT>, nb, TPB, pair_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom,
 	       ctx->nT, ctx->fC, nullptr, ctx->partials, ctx->icount, 1.0, 1.0, 1.0);
 	finish_sum(ctx, nb, 0, 1.0);
 	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -888,7 +994,7 @@ extern "C" int smd_count_pairs(smd_ctx *ctx, int64_t *total, int32_t *per_partic
 	}
 	rc = check_device_errors(ctx);
 	if (rc) return rc;
-	if (total) *total = (int64_t)llround(ctx->h_pinned[0]) / 2;
+	if (total) *total = ctx->slab ? (int64_t)llround(ctx->h_pinned[0]) : (int64_t)llround(ctx->h_pinned[0]) / 2;
 	return SMD_OK;
 }
 
@@ -905,8 +1011,34 @@ extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new
 	if (!rc && total > ctx->cellcap) { ctx->err = "box grew beyond the cell-table capacity"; rc = SMD_ERR_UNSUPPORTED; }
 	if (rc) { set_geom(ctx, old.box); return rc; }
 	if ((rc = upload_acut(ctx))) return rc;
-	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, ctx->N, ctx->pos[ctx->cur], scale[0], scale[1], scale[2]);
+	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->cur], scale[0], scale[1], scale[2]);
 	retag_cells(ctx);
+	return SMD_OK;
+}
+
+extern "C" int smd_mc_propose(const double box[3], double deltaLXY, double u_fluct, double new_box[3], double scale[3])
+{
+	if (!box || !new_box || !scale) return SMD_ERR_ARG;
+	// MD.cpp:591-613
+	double size[3] = {box[0], box[1], box[2]};
+	double fl[3];
+	fl[0] = deltaLXY * (2.0 * u_fluct - 1.0);
+	fl[1] = fl[0];
+	fl[2] = (size[0] * size[1]) / ((size[0] + fl[0]) * (size[1] + fl[1]));
+	size[0] += fl[0]; size[1] += fl[1]; size[2] *= fl[2];
+	for (int d = 0; d < 3; d++) { new_box[d] = size[d]; scale[d] = size[d] / box[d]; }
+	return SMD_OK;
+}
+
+extern "C" int smd_mc_accept(double dU_terms_sum, double tension, const double box[3], const double new_box[3], double temperature,
+                             double u_accept, int32_t *accepted, double *dU_total)
+{
+	if (!box || !new_box || !accepted) return SMD_ERR_ARG;
+	double dPotential = dU_terms_sum;
+	if (tension != 0) dPotential += tension * ((new_box[0] * new_box[1]) - (box[0] * box[1]));   // MD.cpp:677-678
+	double D = exp(dPotential / temperature);                                                       // :683-687
+	*accepted = (D >= u_accept || -dPotential <= 0) ? 1 : 0;                                        // :695
+	if (dU_total) *dU_total = dPotential;
 	return SMD_OK;
 }
 
@@ -914,24 +1046,18 @@ extern "C" int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, do
                                double *dU_total, double box_out[3])
 {
 	if (!ctx) return SMD_ERR_ARG;
-	// MD.cpp:591-613
-	double size[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
-	double oldSize[3] = {size[0], size[1], size[2]};
-	double fl[3];
-	fl[0] = deltaLXY * (2.0 * u_fluct - 1.0);
-	fl[1] = fl[0];
-	fl[2] = (size[0] * size[1]) / ((size[0] + fl[0]) * (size[1] + fl[1]));
-	size[0] += fl[0]; size[1] += fl[1]; size[2] *= fl[2];
-	double aSize[3] = {size[0] / oldSize[0], size[1] / oldSize[1], size[2] / oldSize[2]};
+	REQUIRE(!ctx->slab, "slab: use smd_mc_propose / smd_dpotential / all-reduce / smd_mc_accept / smd_rescale");
+	double oldSize[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
+	double size[3], aSize[3];
+	smd_mc_propose(oldSize, deltaLXY, u_fluct, size, aSize);
 	double terms[SMD_NTERMS];
 	int rc = smd_dpotential(ctx, aSize, terms);
 	if (rc) return rc;
 	// MD.cpp:615-675: pair first, then the molecules in file order (we sum by kind; FP64 sum order differs only)
 	double dPotential = 0;
 	for (int t = 0; t < SMD_NTERMS; t++) dPotential += terms[t];
-	if (tension != 0) dPotential += tension * ((size[0] * size[1]) - (oldSize[0] * oldSize[1]));   // :677-678
-	double D = exp(dPotential / ctx->temperature);                                                    // :683-687
-	int acc = (D >= u_accept || -dPotential <= 0) ? 1 : 0;                                            // :695
+	int32_t acc = 0;
+	smd_mc_accept(dPotential, tension, oldSize, size, ctx->temperature, u_accept, &acc, &dPotential);
 	if (acc) {
 		rc = smd_rescale(ctx, aSize, size);
 		if (rc) return rc;
@@ -947,6 +1073,7 @@ extern "C" int smd_get_particles(smd_ctx *ctx, double *xyz, int32_t *type, doubl
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(ctx->particles_set, "smd_set_particles first");
+	REQUIRE(!ctx->slab, "slab: use smd_slab_get_local");
 	CK(cudaSetDevice(ctx->device));
 	int N = ctx->N;
 	double *sx = ctx->stage, *sv = ctx->stage + 3 * (size_t)ctx->cap;
@@ -962,6 +1089,7 @@ extern "C" int smd_get_forces(smd_ctx *ctx, double *acc)
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(acc && ctx->particles_set, "bad call");
+	REQUIRE(!ctx->slab, "slab: use smd_slab_get_local");
 	CK(cudaSetDevice(ctx->device));
 	int N = ctx->N;
 	LAUNCH(k_export_soa3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc, ctx->gid[ctx->cur], ctx->stage);
@@ -973,6 +1101,7 @@ extern "C" int smd_get_unwrapped(smd_ctx *ctx, double *xyz)
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(xyz && ctx->particles_set && ctx->unw[0], "unwrapped positions are not tracked");
+	REQUIRE(!ctx->slab, "slab: unwrapped read-back is not exported");
 	CK(cudaSetDevice(ctx->device));
 	int N = ctx->N;
 	LAUNCH(k_export_soa3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->stage);
@@ -991,6 +1120,7 @@ extern "C" int smd_get_cell_ids(smd_ctx *ctx, int32_t n_cells_xyz[3], int32_t *c
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(cell_key && cell_rank, "null output");
+	REQUIRE(!ctx->slab, "slab: cell ids are not exported");
 	int rc = ready(ctx);
 	if (rc) return rc;
 	if (!ctx->cells_valid) build_cells(ctx);
@@ -1065,4 +1195,162 @@ extern "C" int smd_stats(smd_ctx *ctx, int64_t *kernel_launches, int64_t *rebuil
 	if (kernel_launches) *kernel_launches = ctx->launches;
 	if (rebuilds) *rebuilds = ctx->rebuilds;
 	return SMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ slab decomposition
+extern "C" int smd_slab_columns(int32_t n_cols, int32_t nranks, int32_t rank, int32_t *col_lo, int32_t *col_hi)
+{
+	if (nranks <= 0 || rank < 0 || rank >= nranks || n_cols <= 0 || !col_lo || !col_hi) return SMD_ERR_ARG;
+	*col_lo = (int32_t)(((long long)rank * n_cols) / nranks);
+	*col_hi = (int32_t)(((long long)(rank + 1) * n_cols) / nranks);
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_select(const double box[3], double cutoff, int32_t nranks, int32_t rank, int32_t n, const double *xyz,
+                               int32_t *flags)
+{
+	if (!box || !xyz || !flags || cutoff <= 0) return SMD_ERR_ARG;
+	int nc = (int)(box[0] / cutoff);              // cellOpt.h:194
+	double cs = box[0] / nc;                      // cellOpt.h:207
+	int32_t lo, hi;
+	int rc = smd_slab_columns(nc, nranks, rank, &lo, &hi);
+	if (rc) return rc;
+	const int W = hi - lo, H = SMD_SLAB_HALO;
+	for (int i = 0; i < n; i++) {
+		int cx = (int)(xyz[3 * (size_t)i] / cs);  // cellOpt.h:532
+		if (cx >= nc) cx -= 1;                    // cellOpt.h:537
+		int rel = cx - lo;
+		if (rel < 0) rel += nc;
+		flags[i] = rel < W ? 1 : ((nranks > 1 && (rel < W + H || rel >= nc - H)) ? 2 : 0);
+	}
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_recv_buffer(smd_ctx *ctx, int32_t side, void **ptr, size_t *bytes)
+{
+	if (!ctx || !ptr) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab && (side == 0 || side == 1), "not a slab context / bad side");
+	*ptr = ctx->recv_base[side];
+	if (bytes) *bytes = ctx->recv_bytes;
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_ipc_handle(smd_ctx *ctx, int32_t side, void *handle64)
+{
+	if (!ctx || !handle64) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab && (side == 0 || side == 1), "not a slab context / bad side");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+	CK(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	CK(cudaIpcGetMemHandle(&h, ctx->recv_base[side]));
+	memcpy(handle64, &h, sizeof h);
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_connect_ptr(smd_ctx *ctx, int32_t dir, void *peer_buffer)
+{
+	if (!ctx || !peer_buffer) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab && (dir == 0 || dir == 1), "not a slab context / bad direction");
+	ctx->comm.send[dir] = (char *)peer_buffer;
+	ctx->peer_set[dir] = true;
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_connect_ipc(smd_ctx *ctx, int32_t dir, const void *handle64)
+{
+	if (!ctx || !handle64) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab && (dir == 0 || dir == 1), "not a slab context / bad direction");
+	CK(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof h);
+	void *p = nullptr;
+	CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	ctx->ipc_opened[dir] = p;
+	return smd_slab_connect_ptr(ctx, dir, p);
+}
+
+extern "C" int smd_slab_exchange_send(smd_ctx *ctx)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab, "not a slab context");
+	REQUIRE(ctx->peer_set[0] && ctx->peer_set[1], "slab: connect both neighbours first (smd_slab_connect_*)");
+	REQUIRE(!ctx->exch_pending, "slab: previous exchange not received yet");
+	CK(cudaSetDevice(ctx->device));
+	ProfScope ps(ctx, SMD_PHASE_EXCHANGE);
+	ctx->xseq++;
+	LAUNCH(k_slab_pack, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
+	       ctx->gid[ctx->cur], ctx->geom, ctx->comm, ctx->xseq, ctx->errflag);
+	ctx->exch_pending = true;
+	ctx->cells_valid = false;
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_exchange_recv(smd_ctx *ctx)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab && ctx->exch_pending, "slab: no exchange in flight");
+	CK(cudaSetDevice(ctx->device));
+	ProfScope ps(ctx, SMD_PHASE_EXCHANGE);
+	int blocks = std::min(nblk(2ll * ctx->comm.capmsg, 256), 296);
+	long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a neighbour that never sends is reported, not waited for
+	LAUNCH(k_slab_unpack, blocks, 256, 0, cnt_of(ctx), ctx->dN + 1, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
+	       ctx->gid[ctx->cur], ctx->comm, ctx->xseq, ctx->errflag, spin_limit);
+	ctx->exch_pending = false;
+	ctx->ext_valid = true;
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_capacity(smd_ctx *ctx, int32_t *capacity)
+{
+	if (!ctx || !capacity) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab, "not a slab context");
+	*capacity = ctx->cap;
+	return SMD_OK;
+}
+
+extern "C" int smd_slab_get_local(smd_ctx *ctx, int32_t *n, int32_t *gid, double *xyz, int32_t *type, double *vel, double *acc)
+{
+	if (!ctx || !n) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab && ctx->particles_set, "not a loaded slab context");
+	REQUIRE(!ctx->exch_pending, "slab: read-back between smd_step_begin and smd_step_end");
+	CK(cudaSetDevice(ctx->device));
+	size_t cap = ctx->cap;
+	int *d_i = nullptr;
+	double *d_d = nullptr;
+	CK(cudaMalloc(&d_i, 2 * cap * sizeof(int)));
+	CK(cudaMalloc(&d_d, 9 * cap * sizeof(double)));
+	CK(cudaMemsetAsync(ctx->d_export_counter, 0, sizeof(int), ctx->stream));
+	LAUNCH(k_slab_export, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->gid[ctx->cur],
+	       ctx->d_export_counter, d_i, d_d, d_d + 3 * cap, d_d + 6 * cap, d_i + cap);
+	int cnt = 0;
+	cudaError_t e = cudaMemcpyAsync(&cnt, ctx->d_export_counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess && gid) e = cudaMemcpy(gid, d_i, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && type) e = cudaMemcpy(type, d_i + cap, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && xyz) e = cudaMemcpy(xyz, d_d, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && vel) e = cudaMemcpy(vel, d_d + 3 * cap, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && acc) e = cudaMemcpy(acc, d_d + 6 * cap, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost);
+	cudaFree(d_i);
+	cudaFree(d_d);
+	if (e != cudaSuccess) { ctx->err = std::string("smd_slab_get_local: ") + cudaGetErrorString(e); return SMD_ERR_CUDA; }
+	*n = cnt;
+	return check_device_errors(ctx);
+}
+
+extern "C" int smd_slab_counts(smd_ctx *ctx, int32_t *n_local, int32_t *n_owned)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab && ctx->particles_set, "not a loaded slab context");
+	CK(cudaSetDevice(ctx->device));
+	int nn[2] = {0, 0};
+	CK(cudaMemcpyAsync(nn, ctx->dN, sizeof nn, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (n_local) *n_local = nn[0];
+	if (n_owned) {
+		int32_t k = 0;
+		int rc = smd_slab_get_local(ctx, &k, nullptr, nullptr, nullptr, nullptr, nullptr);
+		if (rc) return rc;
+		*n_owned = k;
+	}
+	return check_device_errors(ctx);
 }

@@ -30,13 +30,48 @@ struct Geom {
 	double cs[3];   // cell size  = box / nc          (cellOpt.h:207-209)
 	int nc[3];      // cells per axis = int(box / rc) (cellOpt.h:194-196)
 	double rc2;     // cutoff^2
+	// slab decomposition along x (multi-GPU): this context owns the cell columns [col_lo, col_hi) of the global grid
+	// and keeps `halo` ghost columns on each side (periodic: column indices wrap modulo nc[0]).  slab == 0: whole box.
+	int slab, col_lo, col_hi, halo;
 };
+
+// particle count of a launch: a host value (single GPU: N never changes) or a device word (slab mode: the number of
+// local particles changes every step through migration and the halo, and the host never waits for it)
+struct Cnt {
+	int n;
+	const int *dn;
+	__device__ __forceinline__ int get() const { return dn ? *dn : n; }
+};
+
+// slab mode: gid[] carries the ghost flag of a slot in bit 30 (ghost = copy of a particle another rank owns);
+// a record whose cell word is CELL_DEAD is dropped by the next build
+constexpr int GID_GHOST = 1 << 30;
+constexpr int GID_MASK = GID_GHOST - 1;
+constexpr unsigned CELL_DEAD = 0xffffffffu;
 
 // device-resident active window of the cell grid: the bounding box of occupied cells plus one cell each side.
 // win[0..2] origin, win[3..5] extent, win[6] number of cells in the window.
 enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_WORDS = 8 };
 
-enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW_CAP = 4 };
+enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW_CAP = 4, ERR_SLAB_MIGRATION = 8, ERR_SLAB_MSG_CAP = 16, ERR_SLAB_CAPACITY = 32,
+       ERR_SLAB_TIMEOUT = 64, ERR_SLAB_MISSING = 128 };
+
+// slab halo / migration messages.  One receive buffer per side (0: from the left neighbour, 1: from the right one)
+// and parity of the exchange sequence number; the SENDER writes it directly through peer memory (NVLink P2P, or the
+// same device in the single-process test harness) and publishes {count, seq} in the header last.
+struct __align__(32) SlabMsgHeader { int n, seq; int pad[6]; };
+struct __align__(32) SlabMsgEntry {    // 96 B
+	double x, y, z; int type; unsigned cell;     // the Particle record
+	double vx, vy, vz; int gid; int pad0;        // gid carries GID_GHOST for halo copies; velocities only for migrants
+	double ux, uy, uz; double pad1;              // unwrapped position (migrants, when tracked)
+};
+struct SlabComm {
+	char *send[2];          // receive buffer AT the left / right neighbour that this rank fills (parity 0; parity 1 follows)
+	char *recv[2];          // own receive buffers: [0] filled by the left neighbour, [1] by the right one
+	int *counters;          // [0..1] entries claimed per direction, [2] blocks done
+	size_t parity_stride;   // bytes between the two parity copies of a buffer
+	int capmsg;             // entries per message
+};
 
 struct PairGeo {            // phase-1 constants of k_pair_force2
 	float thr32;            // rc^2 + FP32 rounding margin
@@ -120,6 +155,20 @@ struct smd_ctx {
 	double *h_pinned;  // pinned host scratch (scalars)
 
 	long long launches, rebuilds;
+
+	// slab decomposition (desc.nranks > 1): N is then only the launch bound (= cap); the live counts sit on the device
+	bool slab = false;
+	int n_global = 0;      // particles of the whole system (size of slot_of[])
+	int *dN = nullptr;     // [0] local particles (owned + ghost) of the current sorted order, [1] count after an unpack
+	smd::SlabComm comm;    // message buffers (own receive side + the neighbours' as peer pointers)
+	char *recv_base[2] = {nullptr, nullptr};
+	size_t recv_bytes = 0;
+	void *ipc_opened[2] = {nullptr, nullptr};
+	bool peer_set[2] = {false, false};
+	int xseq = 0;          // exchange sequence number (identical on every rank)
+	bool exch_pending = false;   // a pack was issued, the matching unpack not yet
+	bool ext_valid = false;      // dN[1] holds the count after an unpack (consumed by the next build)
+	int *d_export_counter = nullptr;
 
 	// per-phase event timing (smd_profile)
 	struct ProfSpan { int phase; cudaEvent_t e0, e1; };

@@ -94,11 +94,12 @@ __device__ __forceinline__ void philox_uniform3(uint64_t seed, uint64_t step, ui
 // counting sort that follows (tag_cell below).
 __device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, int *errflag, bool live);
 
-__global__ void __launch_bounds__(TPB) k_verlet_first(int N, int cap, Particle *pos, double *vel, const double *acc, double *unw,
-                                                      Geom g, double dt, int *bbox, int *errflag)
+__global__ void __launch_bounds__(TPB) k_verlet_first(Cnt cnt, int cap, Particle *pos, double *vel, const double *acc, double *unw,
+                                                      Geom g, double dt, int *bbox, int *errflag, const int *gid)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	bool live = s < N;
+	bool live = s < cnt.get();
+	if (g.slab && live) live = !(gid[s] & GID_GHOST);   // ghosts are replaced by the exchange that follows
 	Particle p;
 	if (live) {
 		p = load_particle(pos + s);
@@ -124,10 +125,10 @@ __global__ void __launch_bounds__(TPB) k_verlet_first(int N, int cap, Particle *
 }
 
 // Verlet::second, algorithms/verlet.h:463-477
-__global__ void __launch_bounds__(TPB) k_verlet_second(int N, int cap, const Particle *pos, double *vel, const double *acc, double dt)
+__global__ void __launch_bounds__(TPB) k_verlet_second(Cnt cnt, int cap, const Particle *pos, double *vel, const double *acc, double dt)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= N) return;
+	if (s >= cnt.get()) return;
 	if (pos[s].type == 0) return;
 	double h = 0.5 * dt;
 	vel[s] += (acc[s] * h);
@@ -135,20 +136,21 @@ __global__ void __launch_bounds__(TPB) k_verlet_second(int N, int cap, const Par
 	vel[2 * cap + s] += (acc[2 * cap + s] * h);
 }
 
-__global__ void __launch_bounds__(TPB) k_zero3(int N, int cap, double *a)
+__global__ void __launch_bounds__(TPB) k_zero3(Cnt cnt, int cap, double *a)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= N) return;
+	if (s >= cnt.get()) return;
 	a[s] = 0; a[cap + s] = 0; a[2 * cap + s] = 0;
 }
 
 // Langevin::compute scalar-gamma branch, algorithms/langevin.h:284-331: a += -g v + sigma (2u-1)
-__global__ void __launch_bounds__(TPB) k_langevin(int N, int cap, const double *vel, double *acc, const int *gid, double gamma,
+__global__ void __launch_bounds__(TPB) k_langevin(Cnt cnt, int cap, const double *vel, double *acc, const int *gid, double gamma,
                                                   double sigma, uint64_t seed, uint64_t step, const double *ext_noise)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= N) return;
+	if (s >= cnt.get()) return;
 	int id = gid[s];
+	if (id & GID_GHOST) return;
 	double u[3];
 	if (ext_noise) {
 		u[0] = ext_noise[3 * id]; u[1] = ext_noise[3 * id + 1]; u[2] = ext_noise[3 * id + 2];
@@ -163,10 +165,12 @@ __global__ void __launch_bounds__(TPB) k_langevin(int N, int cap, const double *
 }
 
 // Kinetic::compute, algorithms/dataCollection.h:666-674: sum (vx^2+vy^2+vz^2)/2
-__global__ void __launch_bounds__(256) k_kinetic(int N, int cap, const double *vel, double *partials)
+__global__ void __launch_bounds__(256) k_kinetic(Cnt cnt, int cap, const double *vel, const int *gid, double *partials)
 {
 	double e = 0;
+	const int N = cnt.get();
 	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < N; s += gridDim.x * blockDim.x) {
+		if (gid[s] & GID_GHOST) continue;
 		double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
 		e += ((vx * vx + vy * vy + vz * vz) / 2.0);
 	}
@@ -184,10 +188,10 @@ __global__ void __launch_bounds__(256) k_final_sum(int n, const double *partials
 }
 
 // accepted box move: p *= aSize (MD.cpp:697-707)
-__global__ void __launch_bounds__(TPB) k_rescale(int N, Particle *pos, double sx, double sy, double sz)
+__global__ void __launch_bounds__(TPB) k_rescale(Cnt cnt, Particle *pos, double sx, double sy, double sz)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= N) return;
+	if (s >= cnt.get()) return;
 	Particle p = load_particle(pos + s);
 	p.x *= sx; p.y *= sy; p.z *= sz;
 	store_particle(pos + s, p);
@@ -222,6 +226,7 @@ __device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, 
 		for (int d = 0; d < 3; d++) lo[d] = hi[d] = c[d];
 		p.cell = pack_cell(c[0], c[1], c[2]);
 	}
+	if (g.slab) return;   // the window of a slab is fixed by its column range
 	for (int d = 0; d < 3; d++) {
 		int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
 		// the box of occupied cells hardly moves between steps: only touch the accumulators when they would change
@@ -233,10 +238,11 @@ __device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, 
 }
 
 // stand-alone tagging pass (after set_particles / a box move; the steady state does it inside k_verlet_first)
-__global__ void __launch_bounds__(TPB) k_tag_cells(int N, Particle *pos, Geom g, int *bbox, int *errflag)
+__global__ void __launch_bounds__(TPB) k_tag_cells(Cnt cnt, Particle *pos, Geom g, int *bbox, int *errflag, const int *gid)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	bool live = s < N;
+	bool live = s < cnt.get();   // slab mode: ghosts are re-tagged too (an accepted box move scales them like their owners)
+	(void)gid;
 	Particle p;
 	if (live) p = load_particle(pos + s);
 	tag_cell(p, g, bbox, errflag, live);
@@ -249,10 +255,29 @@ __global__ void __launch_bounds__(TPB) k_tag_cells(int N, Particle *pos, Geom g,
 // kernels that run after the build and re-arms bbox[].
 struct Window { int org[3], dim[3]; int ncells; };
 
+// window-local x index of cell column cx.  A slab's window starts `halo` columns left of its first owned column and
+// may run across the periodic boundary, so the index wraps modulo nc[0]; for a single-GPU window (a sub-box of the
+// grid) a column outside the window maps outside [0, dim).
+__device__ __forceinline__ int win_x(int cx, int w0, int nc0)
+{
+	int l = cx - w0;
+	if (l < 0) l += nc0;
+	else if (l >= nc0) l -= nc0;
+	return l;
+}
+
 __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long long cellcap)
 {
 	Window w;
 	long long n = 1;
+	if (g.slab) {   // owned columns + halo on both sides, whole grid in y and z
+		w.org[0] = g.col_lo - g.halo; w.dim[0] = (g.col_hi - g.col_lo) + 2 * g.halo;
+		w.org[1] = 0; w.dim[1] = g.nc[1];
+		w.org[2] = 0; w.dim[2] = g.nc[2];
+		n = (long long)w.dim[0] * w.dim[1] * w.dim[2];
+		w.ncells = (n > cellcap) ? 0 : (int)n;
+		return w;
+	}
 	for (int d = 0; d < 3; d++) {
 		int lo = bbox[d], hi = bbox[3 + d];
 		if (lo == INT_MAX) { lo = 0; hi = 0; }
@@ -268,16 +293,21 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 
 // pass 1 of the counting sort: histogram over the window.  Warp-aggregated: lanes sharing a cell elect a leader
 // that issues one atomicAdd for the group.
-__global__ void __launch_bounds__(TPB) k_bin(int N, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
-                                             int *cellOfSlot)
+__global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
+                                             int *cellOfSlot, int *errflag)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	Window w = window_of(bbox, g, cellcap);
 	int local = -1;
-	if (s < N && w.ncells > 0) {
-		int cx, cy, cz;
-		unpack_cell(pos[s].cell, cx, cy, cz);
-		local = (cx - w.org[0]) + w.dim[0] * ((cy - w.org[1]) + w.dim[1] * (cz - w.org[2]));
+	if (s < cnt.get() && w.ncells > 0) {
+		unsigned c = pos[s].cell;
+		if (c != CELL_DEAD) {   // slab mode: ghosts of the previous step
+			int cx, cy, cz;
+			unpack_cell(c, cx, cy, cz);
+			int lx = win_x(cx, w.org[0], g.nc[0]);
+			if (lx >= w.dim[0]) atomicOr(errflag, ERR_SLAB_MIGRATION);   // cannot happen on a single GPU (window = bbox)
+			else local = lx + w.dim[0] * ((cy - w.org[1]) + w.dim[1] * (cz - w.org[2]));
+		}
 		cellOfSlot[s] = local;
 	}
 	unsigned active = __ballot_sync(0xffffffffu, local >= 0);
@@ -347,7 +377,8 @@ __global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox
 	}
 }
 
-__global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *win, const int *blockSums, int *start, int *cursor, int N)
+// nlive: slab mode only -- the number of live local particles after this build (the last block knows the total)
+__global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *win, const int *blockSums, int *start, int *cursor, int N, int *nlive)
 {
 	int ncells = win[WIN_NCELLS];
 	int b0, b1;
@@ -381,34 +412,43 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *win, 
 		if (threadIdx.x == 0) carry_sh = carry + total;
 		__syncthreads();
 	}
-	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) start[ncells] = N;
+	__syncthreads();
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+		// the last block's carry after its chunk = number of binned particles (every block up to the end of the table
+		// has an empty or final chunk)
+		int total = nlive ? carry_sh : N;
+		start[ncells] = total;
+		if (nlive) *nlive = total;
+	}
 }
 
 // pass 2: claim a position inside the cell's range (arbitrary order, fixed by k_reorder)
-__global__ void __launch_bounds__(TPB) k_place(int N, const int *cellOfSlot, int *cursor, int *order)
+__global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int *order)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= N) return;
-	int q = atomicAdd(cursor + cellOfSlot[s], 1);
+	if (s >= cnt.get()) return;
+	int c = cellOfSlot[s];
+	if (c < 0) return;
+	int q = atomicAdd(cursor + c, 1);
 	order[q] = s;
 }
 
 // pass 3: final slot = cell start + rank by DESCENDING original index, which is exactly the order of the
 // reference's head-inserted linked list (cellOpt.h:572-585) and makes the sort deterministic; move the records.
-__global__ void __launch_bounds__(TPB) k_reorder(int N, int cap, const int *order, const int *cellOfSlot, const int *start,
+__global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int *order, const int *cellOfSlot, const int *start,
                                                  const Particle *pos_in, Particle *pos_out, const double *vel_in, double *vel_out,
                                                  const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
                                                  const int *gid_in, int *gid_out, int *slot_of, float4 *pos32_out,
                                                  const float *__restrict__ acut)
 {
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= N) return;
+	if (q >= cnt.get()) return;
 	int s = order[q];
 	int c = cellOfSlot[s];
 	int b = start[c], e = start[c + 1];
 	int g = gid_in[s];
 	int rank = 0;
-	for (int k = b; k < e; k++) rank += (gid_in[order[k]] > g);
+	for (int k = b; k < e; k++) rank += ((gid_in[order[k]] & GID_MASK) > (g & GID_MASK));
 	int t = b + rank;
 	Particle p = load_particle(pos_in + s);
 	store_particle(pos_out + t, p);
@@ -417,7 +457,7 @@ __global__ void __launch_bounds__(TPB) k_reorder(int N, int cap, const int *orde
 	if (unw_in) { unw_out[t] = unw_in[s]; unw_out[cap + t] = unw_in[cap + s]; unw_out[2 * cap + t] = unw_in[2 * cap + s]; }
 	if (acc_in) { acc_out[t] = acc_in[s]; acc_out[cap + t] = acc_in[cap + s]; acc_out[2 * cap + t] = acc_in[2 * cap + s]; }
 	gid_out[t] = g;
-	slot_of[g] = t;
+	slot_of[g & GID_MASK] = t;
 }
 
 // ------------------------------------------------------------------------------------------------ pair engine
@@ -472,7 +512,7 @@ enum PairMode { PAIR_FORCE = 0, PAIR_POTENTIAL = 1, PAIR_DPOTENTIAL = 2, PAIR_CO
 // PAIR_POTENTIAL / PAIR_DPOTENTIAL visit every pair once (forward cells + lower index first in the own cell) and
 // reduce per block.  tab = fC for force, uC otherwise (staged in shared memory).
 template <int MODE>
-__global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
+__global__ void __launch_bounds__(TPB) k_pair(Cnt cnt, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
                                               const int *__restrict__ start, const int *__restrict__ win, Geom g, int nT,
                                               const double *__restrict__ tab, double *__restrict__ acc, double *__restrict__ partials,
                                               int *__restrict__ icount, double sx, double sy, double sz)
@@ -484,8 +524,10 @@ __global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__
 
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	double ax = 0, ay = 0, az = 0, usum = 0;
-	int cnt = 0;
-	if (i < N) {
+	int cnt_in = 0;
+	// slab mode: only owned particles gather / count; a pair of an owned and a ghost particle is counted by the rank
+	// that owns the reference's home particle of the pair, so every pair is still visited exactly once globally
+	if (i < cnt.get() && !(g.slab && (gid[i] & GID_GHOST))) {
 		Particle pi = load_particle(pos + i);
 		int cx, cy, cz;
 		unpack_cell(pi.cell, cx, cy, cz);
@@ -510,8 +552,8 @@ __global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__
 					double Sx = 0;
 					if (nx < 0) { nx += g.nc[0]; Sx = -g.box[0]; }
 					if (nx >= g.nc[0]) { nx -= g.nc[0]; Sx = g.box[0]; }
-					int lx = nx - w0;
-					if (lx < 0 || lx >= d0) continue;
+					int lx = win_x(nx, w0, g.nc[0]);
+					if (lx >= d0) continue;
 					bool self = (ox == 0 && oy == 0 && oz == 0);
 					// forward offsets of cellOpt.h:715
 					bool fwd = (oz == 1) || (oz == 0 && (ox == 1 || (ox == 0 && oy == 1)));
@@ -535,7 +577,7 @@ __global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__
 						}
 						double dr2 = dx * dx + dy * dy + dz * dz;
 						if (MODE == PAIR_COUNT) {
-							cnt += (dr2 < g.rc2);
+							cnt_in += (dr2 < g.rc2);
 							continue;
 						}
 						// am I the reference's p1 (home cell; in the own cell the later-loaded = lower original index,
@@ -568,14 +610,14 @@ __global__ void __launch_bounds__(TPB) k_pair(int N, int cap, const Particle *__
 		if (MODE == PAIR_FORCE) {
 			acc[i] += ax; acc[cap + i] += ay; acc[2 * cap + i] += az;
 		}
-		if (MODE == PAIR_COUNT) icount[i] = cnt;
+		if (MODE == PAIR_COUNT) icount[i] = cnt_in;
 	}
 	if (MODE == PAIR_POTENTIAL || MODE == PAIR_DPOTENTIAL) {
 		usum = block_sum(usum);
 		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
 	}
 	if (MODE == PAIR_COUNT) {
-		double c = block_sum((double)cnt);
+		double c = block_sum((double)cnt_in);
 		if (threadIdx.x == 0) partials[blockIdx.x] = c;
 	}
 }
@@ -697,12 +739,15 @@ struct PairSmem {
 };
 
 template <bool LANGEVIN, bool SYMM>
-__global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N, int cap, const Particle *__restrict__ pos,
+__global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
                                                             const int *__restrict__ win, Geom g, int nT,
                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
-                                                            PairGeo pg, double *__restrict__ acc, LangevinArgs lg)
+                                                            PairGeo pg, double *__restrict__ acc, LangevinArgs lg,
+                                                            const int *__restrict__ gid)
 {
+	const int N = cnt.get();
+	if ((int)(blockIdx.x * PAIR_TPB) >= N) return;
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
@@ -728,7 +773,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N
 		__syncthreads();
 	}
 	const int i = sm.perm[tid];
-	const bool live = i < N;
+	// slab mode: ghosts are only neighbours, nobody gathers for them
+	const bool live = i < N && !(g.slab && (gid[i] & GID_GHOST));
 	Particle pi;
 	pi.x = pi.y = pi.z = 0; pi.type = 0; pi.cell = 0;
 	float4 p32 = make_float4(0.f, 0.f, 0.f, -1.f);
@@ -855,7 +901,12 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N
 		row_ok = row_ok && !wrapyz && lz >= 0 && lz < d2 && ly >= 0 && ly < d1;
 		bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
 		// cells cx-1 .. cx+1 that need no wrap, clamped to the window (cells outside it are empty)
-		int xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0), xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
+		int xlo, xhi;
+		if (g.slab) {   // the window holds every neighbour column of an owned particle, possibly across the periodic seam
+			xlo = win_x(max(cx - (keep_lo ? 1 : 0), 0), w0, g.nc[0]); xhi = win_x(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1), w0, g.nc[0]);
+		} else {
+			xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
+		}
 		int jb = 0, je = 0;
 		if (row_ok && xlo <= xhi) {
 			int rowbase = d0 * (ly + d1 * lz);
@@ -923,14 +974,18 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N
 			bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
 			int xlo, xhi;
 			if (sub == 0) {          // the unwrapped x range of a row shifted in y or z (unshifted rows were done above)
-				xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
+				if (g.slab) {
+					xlo = win_x(max(cx - (keep_lo ? 1 : 0), 0), w0, g.nc[0]); xhi = win_x(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1), w0, g.nc[0]);
+				} else {
+					xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
+				}
 				row_ok = row_ok && (sy != 0.f || sz != 0.f);
 			} else if (sub == 1) {   // left face: the image of the last cell of the row
-				xlo = xhi = g.nc[0] - 1 - w0; sx = -(float)g.box[0];
-				row_ok = row_ok && keep_lo && cx == 0 && xlo >= 0 && xlo < d0;
+				xlo = xhi = win_x(g.nc[0] - 1, w0, g.nc[0]); sx = -(float)g.box[0];
+				row_ok = row_ok && keep_lo && cx == 0 && xlo < d0;
 			} else {                 // right face: the image of the first cell
-				xlo = xhi = 0 - w0; sx = (float)g.box[0];
-				row_ok = row_ok && keep_hi && cx == g.nc[0] - 1 && xlo >= 0 && xlo < d0;
+				xlo = xhi = win_x(0, w0, g.nc[0]); sx = (float)g.box[0];
+				row_ok = row_ok && keep_hi && cx == g.nc[0] - 1 && xlo < d0;
 			}
 			if (!row_ok || xlo > xhi) continue;
 			int rowbase = d0 * (ly + d1 * lz);
@@ -948,10 +1003,10 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N
 	}
 
 	// ---- hand the lists out again, longest first
-	const int cnt = (int)((wp - lbase) >> 6);
-	sm.cnt[tid] = cnt;
+	const int lcnt = (int)((wp - lbase) >> 6);
+	sm.cnt[tid] = lcnt;
 	sm.part[0][tid] = ex; sm.part[1][tid] = ey; sm.part[2][tid] = ez;
-	atomicAdd(&sm.hist[cnt], 1);
+	atomicAdd(&sm.hist[lcnt], 1);
 	__syncthreads();
 	if (tid < 32) {   // exclusive prefix over descending length (PAIR_CAP + 1 bins)
 		constexpr int PER = (PAIR_CAP + 1 + 31) / 32;
@@ -966,13 +1021,14 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N
 		for (int k = 0; k < PER; k++) { int c = PAIR_CAP - (tid * PER + k); if (c >= 0) sm.hist[c] = run; run += h[k]; }
 	}
 	__syncthreads();
-	sm.order[atomicAdd(&sm.hist[cnt], 1)] = tid;
+	sm.order[atomicAdd(&sm.hist[lcnt], 1)] = tid;
 	__syncthreads();
 
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];
 	const int io = sm.perm[o];
 	if (io >= N) return;
+	if (g.slab && (gid[io] & GID_GHOST)) return;
 	const Particle po = load_particle(pos + io);
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
 	{
@@ -980,7 +1036,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(int N
 		drain(io, po, o, ob, ob + 64u * (unsigned)sm.cnt[o], ax, ay, az);
 	}
 	if (LANGEVIN) {
-		int id = lg.gid[io];
+		int id = lg.gid[io] & GID_MASK;
 		double u[3];
 		if (lg.ext_noise) {
 			u[0] = lg.ext_noise[3 * id]; u[1] = lg.ext_noise[3 * id + 1]; u[2] = lg.ext_noise[3 * id + 2];
@@ -1130,6 +1186,272 @@ __global__ void __launch_bounds__(TPB) k_chain(int cap, const Particle *__restri
 		usum = block_sum(usum);
 		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
 	}
+}
+
+// ---- slab mode (multi-GPU) variant of k_chain.  A chain can straddle the slab seam, and which of its members are
+// local (owned, or ghost copies inside the halo) changes every step, so the work is found from the particles: one
+// thread per local slot; the thread of the lowest-numbered OWNED member of a chain ("leader") walks the chain in the
+// reference's triplet order.  A triplet is evaluated when one of its three members is owned here (all three must
+// then be local: the halo is two cell columns wide, a triplet spans at most two bonds) and only owned members are
+// written, so every owned particle receives exactly the terms, in exactly the order, of the single-GPU kernel.
+// Energies (MODE 1, 2): a triplet's terms are counted by the rank that owns its FIRST member -- once globally.
+__device__ __forceinline__ int slab_find(const int *__restrict__ slot_of, const int *__restrict__ gid, int N, int id, bool &owned)
+{
+	int t = slot_of[id];
+	owned = false;
+	if (t < 0 || t >= N) return -1;
+	int gg = gid[t];
+	if ((gg & GID_MASK) != id) return -1;   // stale entry of a particle that left this rank
+	owned = !(gg & GID_GHOST);
+	return t;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_chain_slab(Cnt cnt, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
+                                                    const int *__restrict__ slot_of, Geom g, ChainBlock cb, double *acc, double *partials,
+                                                    double sx, double sy, double sz, int *errflag)
+{
+	const int N = cnt.get();
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0;
+	bool work = false;
+	int base = 0, lead = 0;
+	if (s < N) {
+		int gi = gid[s];
+		int rel = gi - cb.start;   // a ghost's flag bit makes rel huge: excluded below
+		if (!(gi & GID_GHOST) && rel >= 0 && rel < cb.nChains * cb.len) {
+			int k = rel / cb.len;
+			lead = rel - k * cb.len;
+			base = cb.start + k * cb.len;
+			work = true;
+			for (int m = 0; m < lead; m++) {
+				bool ow;
+				if (slab_find(slot_of, gid, N, base + m, ow) >= 0 && ow) { work = false; break; }
+			}
+		}
+	}
+	if (work) {
+		// triplets that can contain an owned member start at max(lead - 2, 0)
+		int l0 = max(lead - 2, 0);
+		bool o1, o2, o3;
+		int s1 = slab_find(slot_of, gid, N, base + l0, o1), s2 = slab_find(slot_of, gid, N, base + l0 + 1, o2);
+		Particle p1, p2, p3;
+		if (s1 >= 0) p1 = load_particle(pos + s1);
+		if (s2 >= 0) p2 = load_particle(pos + s2);
+		V3 a1 = {0, 0, 0}, a2 = {0, 0, 0};
+		for (int l = l0; l <= cb.len - 3; l++) {
+			bool tail = (l == cb.len - 3);
+			int s3 = slab_find(slot_of, gid, N, base + l + 2, o3);
+			if (s3 >= 0) p3 = load_particle(pos + s3);
+			V3 a3 = {0, 0, 0};
+			bool need = (MODE == 0) ? (o1 || o2 || o3) : o1;
+			if (need && (s1 < 0 || s2 < 0 || s3 < 0)) { atomicOr(errflag, ERR_SLAB_MISSING); need = false; }
+			if (need) {
+				V3 da = diff_mi(p1, p2, g), db = diff_mi(p2, p3, g);
+				if (MODE == 0) {
+					V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
+					a1.x += f.x; a1.y += f.y; a1.z += f.z;
+					a2.x -= f.x; a2.y -= f.y; a2.z -= f.z;
+					if (tail) {
+						V3 f2 = harmonic_f(db, cb.c[0], cb.c[1]);
+						a2.x += f2.x; a2.y += f2.y; a2.z += f2.z;
+						a3.x -= f2.x; a3.y -= f2.y; a3.z -= f2.z;
+					}
+					V3 fa, fb;
+					bend_f(da, db, cb.c[2], cb.c[3], fa, fb);
+					a1.x += fa.x; a1.y += fa.y; a1.z += fa.z;
+					a2.x += (fb.x - fa.x); a2.y += (fb.y - fa.y); a2.z += (fb.z - fa.z);
+					a3.x -= fb.x; a3.y -= fb.y; a3.z -= fb.z;
+				} else if (MODE == 1) {
+					usum += harmonic_p(da, cb.c[0], cb.c[1]);
+					if (tail) usum += harmonic_p(db, cb.c[0], cb.c[1]);
+					usum += bend_p(da, db, cb.c[2], cb.c[3]);
+				} else {
+					double uo = harmonic_p(da, cb.c[0], cb.c[1]);
+					if (tail) uo += harmonic_p(db, cb.c[0], cb.c[1]);
+					uo += bend_p(da, db, cb.c[2], cb.c[3]);
+					V3 ea = scaled(da, sx, sy, sz), eb = scaled(db, sx, sy, sz);
+					double un = harmonic_p(ea, cb.c[0], cb.c[1]);
+					if (tail) un += harmonic_p(eb, cb.c[0], cb.c[1]);
+					un += bend_p(ea, eb, cb.c[2], cb.c[3]);
+					usum += (uo - un);
+				}
+			}
+			if (MODE == 0) {
+				if (o1) { acc[s1] += a1.x; acc[cap + s1] += a1.y; acc[2 * cap + s1] += a1.z; }
+				if (tail) {
+					if (o2) { acc[s2] += a2.x; acc[cap + s2] += a2.y; acc[2 * cap + s2] += a2.z; }
+					if (o3) { acc[s3] += a3.x; acc[cap + s3] += a3.y; acc[2 * cap + s3] += a3.z; }
+				}
+			}
+			s1 = s2; s2 = s3; p1 = p2; p2 = p3; o1 = o2; o2 = o3; a1 = a2; a2 = a3;
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ slab exchange
+// After the particles of a slab moved (Verlet::first, or an accepted box move) and were re-tagged with their cells:
+//   k_slab_pack    every rank, one pass over its slots: old ghosts are marked dead; owned particles whose new column
+//                  lies outside [col_lo, col_hi) MIGRATE to the neighbour on that side (record + velocity [+ unwrapped
+//                  position]) and stay behind as ghosts (their column is inside this rank's halo); owned particles in
+//                  the outermost `halo` columns are copied to the neighbour as ghosts.  Entries are written straight
+//                  into the neighbour's receive buffer through peer memory; the last block to finish publishes
+//                  {count, seq} in the header (release at system scope).
+//   k_slab_unpack  waits for both headers of this exchange (acquire), appends the received particles behind the
+//                  local ones and publishes the extended count; the build that follows sorts them into place and
+//                  drops the dead records.
+// One message per neighbour and step: the migrants a rank sends are exactly the ghosts it would otherwise have to
+// ask back, and what arrives from the neighbour completes the halo.
+__device__ __forceinline__ void st_entry(SlabMsgEntry *e, const Particle &p, double vx, double vy, double vz, int gid)
+{
+	double2 *q = reinterpret_cast<double2 *>(e);
+	long long w = ((long long)(unsigned long long)p.cell << 32) | (unsigned)p.type;
+	q[0] = make_double2(p.x, p.y);
+	q[1] = make_double2(p.z, __longlong_as_double(w));
+	q[2] = make_double2(vx, vy);
+	q[3] = make_double2(vz, __longlong_as_double((long long)(unsigned)gid));
+}
+
+__global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *pos, const double *vel, const double *unw, int *gid, Geom g,
+                                                   SlabComm c, int seq, int *errflag)
+{
+	const int N = cnt.get();
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	int dir = -1;          // 0: entry for the left neighbour, 1: for the right one
+	bool migrant = false;
+	Particle p;
+	int gi = 0;
+	if (s < N) {
+		gi = gid[s];
+		if (gi & GID_GHOST) {
+			pos[s].cell = CELL_DEAD;
+		} else {
+			p = load_particle(pos + s);
+			int cx, cy, cz;
+			unpack_cell(p.cell, cx, cy, cz);
+			int W = g.col_hi - g.col_lo;
+			int rel = cx - g.col_lo;
+			if (rel < 0) rel += g.nc[0];
+			else if (rel >= g.nc[0]) rel -= g.nc[0];
+			if (rel < W) {
+				if (rel < g.halo) dir = 0;
+				else if (rel >= W - g.halo) dir = 1;
+			} else if (rel < W + g.halo) {
+				dir = 1; migrant = true;
+			} else if (rel >= g.nc[0] - g.halo) {
+				dir = 0; migrant = true;
+			} else {
+				atomicOr(errflag, ERR_SLAB_MIGRATION);   // moved further than the halo in one step
+			}
+			if (migrant) gid[s] = gi | GID_GHOST;
+		}
+	}
+#pragma unroll
+	for (int d = 0; d < 2; d++) {
+		unsigned m = __ballot_sync(0xffffffffu, dir == d);
+		if (m == 0) continue;
+		int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+		int basei = 0;
+		if (lane == leader) basei = atomicAdd(c.counters + d, __popc(m));
+		basei = __shfl_sync(0xffffffffu, basei, leader);
+		if (dir == d) {
+			int idx = basei + __popc(m & ((1u << lane) - 1u));
+			if (idx >= c.capmsg) {
+				atomicOr(errflag, ERR_SLAB_MSG_CAP);
+			} else {
+				char *buf = c.send[d] + (size_t)(seq & 1) * c.parity_stride;
+				SlabMsgEntry *e = reinterpret_cast<SlabMsgEntry *>(buf + sizeof(SlabMsgHeader)) + idx;
+				double vx = 0, vy = 0, vz = 0;
+				if (migrant) { vx = vel[s]; vy = vel[cap + s]; vz = vel[2 * cap + s]; }
+				st_entry(e, p, vx, vy, vz, migrant ? gi : (gi | GID_GHOST));
+				if (migrant && unw) {
+					double2 *q = reinterpret_cast<double2 *>(e);
+					q[4] = make_double2(unw[s], unw[cap + s]);
+					q[5] = make_double2(unw[2 * cap + s], 0.0);
+				}
+			}
+		}
+	}
+	// publish: every block fences its entries, the last one writes the two headers
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int t = atomicAdd(c.counters + 2, 1);
+		if (t == (int)gridDim.x - 1) {
+			__threadfence_system();
+			int n0 = min(atomicExch(c.counters + 0, 0), c.capmsg), n1 = min(atomicExch(c.counters + 1, 0), c.capmsg);
+			c.counters[2] = 0;
+			__threadfence_system();
+			volatile int2 *h0 = reinterpret_cast<volatile int2 *>(c.send[0] + (size_t)(seq & 1) * c.parity_stride);
+			volatile int2 *h1 = reinterpret_cast<volatile int2 *>(c.send[1] + (size_t)(seq & 1) * c.parity_stride);
+			int2 v0 = make_int2(n0, seq), v1 = make_int2(n1, seq);
+			asm volatile("st.release.sys.global.v2.s32 [%0], {%1, %2};" ::"l"(h0), "r"(v0.x), "r"(v0.y) : "memory");
+			asm volatile("st.release.sys.global.v2.s32 [%0], {%1, %2};" ::"l"(h1), "r"(v1.x), "r"(v1.y) : "memory");
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int cap, Particle *pos, double *vel, double *unw, int *gid,
+                                                     SlabComm c, int seq, int *errflag, long long spin_limit)
+{
+	__shared__ int n_s[2];
+	if (threadIdx.x < 2) {
+		const char *buf = c.recv[threadIdx.x] + (size_t)(seq & 1) * c.parity_stride;
+		int n = 0, sq = seq - 1;
+		long long t0 = clock64();
+		while (true) {
+			asm volatile("ld.acquire.sys.global.v2.s32 {%0, %1}, [%2];" : "=r"(n), "=r"(sq) : "l"(buf) : "memory");
+			if (sq == seq) break;
+			if (clock64() - t0 > spin_limit) { atomicOr(errflag, ERR_SLAB_TIMEOUT); n = 0; break; }
+			__nanosleep(200);
+		}
+		n_s[threadIdx.x] = n;
+	}
+	__syncthreads();
+	const int N0 = cnt.get(), nL = n_s[0], nR = n_s[1], total = nL + nR;
+	for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+		int side = e >= nL, k = e - (side ? nL : 0);
+		const char *buf = c.recv[side] + (size_t)(seq & 1) * c.parity_stride;
+		const double2 *q = reinterpret_cast<const double2 *>(reinterpret_cast<const SlabMsgEntry *>(buf + sizeof(SlabMsgHeader)) + k);
+		int slot = N0 + e;
+		if (slot >= cap) { atomicOr(errflag, ERR_SLAB_CAPACITY); continue; }
+		double2 a = __ldcg(q), b = __ldcg(q + 1), v0 = __ldcg(q + 2), v1 = __ldcg(q + 3);
+		double2 *o = reinterpret_cast<double2 *>(pos + slot);
+		o[0] = a; o[1] = b;
+		vel[slot] = v0.x; vel[cap + slot] = v0.y; vel[2 * cap + slot] = v1.x;
+		gid[slot] = (int)(unsigned)(__double_as_longlong(v1.y) & 0xffffffffll);
+		if (unw) {
+			double2 u0 = __ldcg(q + 4), u1 = __ldcg(q + 5);
+			unw[slot] = u0.x; unw[cap + slot] = u0.y; unw[2 * cap + slot] = u1.x;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) *dNext = min(N0 + total, cap);
+}
+
+// owned particles of a slab, compacted (order arbitrary): global index, record, velocity
+__global__ void __launch_bounds__(TPB) k_slab_export(Cnt cnt, int cap, const Particle *pos, const double *vel, const double *acc,
+                                                     const int *gid, int *counter, int *out_gid, double *out_xyz, double *out_vel,
+                                                     double *out_acc, int *out_type)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	bool own = s < cnt.get() && !(gid[s] & GID_GHOST) && pos[s].cell != CELL_DEAD;
+	unsigned m = __ballot_sync(0xffffffffu, own);
+	if (m == 0) return;
+	int lane = threadIdx.x & 31, leader = __ffs(m) - 1, b = 0;
+	if (lane == leader) b = atomicAdd(counter, __popc(m));
+	b = __shfl_sync(0xffffffffu, b, leader);
+	if (!own) return;
+	int k = b + __popc(m & ((1u << lane) - 1u));
+	Particle p = load_particle(pos + s);
+	out_gid[k] = gid[s];
+	out_xyz[3 * k] = p.x; out_xyz[3 * k + 1] = p.y; out_xyz[3 * k + 2] = p.z;
+	out_type[k] = p.type;
+	out_vel[3 * k] = vel[s]; out_vel[3 * k + 1] = vel[cap + s]; out_vel[3 * k + 2] = vel[2 * cap + s];
+	out_acc[3 * k] = acc[s]; out_acc[3 * k + 1] = acc[cap + s]; out_acc[3 * k + 2] = acc[2 * cap + s];
 }
 
 // explicit BOND list (system.h:1880-1934, :2717-2747, :3398-3435); one thread per bond, FP64 atomics for the force
@@ -1428,8 +1750,10 @@ __global__ void __launch_bounds__(TPB) k_export_int(int N, const int *v, const i
 	out[gid[s]] = v[s];
 }
 
+// gid_in: slab mode -- global index (+ ghost flag) of each uploaded particle; single GPU: slot s holds particle s
 __global__ void __launch_bounds__(TPB) k_import_particles(int N, int cap, const double *xyz, const int *type, const double *v,
-                                                          Particle *pos, double *vel, double *unw, int *gid, int *slot_of)
+                                                          Particle *pos, double *vel, double *unw, int *gid, int *slot_of,
+                                                          const int *gid_in)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= N) return;
@@ -1440,8 +1764,9 @@ __global__ void __launch_bounds__(TPB) k_import_particles(int N, int cap, const 
 	store_particle(pos + s, p);
 	vel[s] = v ? v[3 * s] : 0.0; vel[cap + s] = v ? v[3 * s + 1] : 0.0; vel[2 * cap + s] = v ? v[3 * s + 2] : 0.0;
 	if (unw) { unw[s] = p.x; unw[cap + s] = p.y; unw[2 * cap + s] = p.z; }
-	gid[s] = s;
-	slot_of[s] = s;
+	int gi = gid_in ? gid_in[s] : s;
+	gid[s] = gi;
+	slot_of[gi & GID_MASK] = s;
 }
 
 // reference cell key and rank inside the cell's list, per original index

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(sm.SYMBOLS), declared ^ set(sm.SYMBOLS)
     for s in declared:
         assert hasattr(L, s)
-    assert L.smd_abi_version() == 1
+    assert L.smd_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -1,0 +1,165 @@
+"""Slab decomposition on the GPU: nranks slab contexts against ONE single-GPU context of the same
+system (which tests/test_gpu_parity.py pins against the reference), through the C ABI.
+
+LocalSlabGroup runs all ranks inside this process on one device: same kernels, same message protocol and per-rank
+state as a multi-GPU run, plain device pointers instead of CUDA IPC / NVLink as transport (the multi-process
+transport is exercised by tests/test_gpu_slab_dist.py when more than one GPU is visible).
+
+Because every particle gathers its own force over its neighbour list in cell order and the Philox noise is keyed on
+the global particle index, a slab run reproduces the single-GPU trajectory to rounding: the bounds below are the
+north star's (1e-5 forces, 1e-7 energies) with a much tighter design check next to them."""
+import numpy as np
+import pytest
+
+import softmold_b200 as sm
+from softmold_b200 import workloads
+from softmold_b200.slab import LocalSlabGroup
+from conftest import golden_path
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, ref):
+    s = np.abs(ref).max()
+    return np.abs(a - ref).max() / (s if s > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def bilayer():
+    m = workloads.bilayer(5000, 3.11, seed=11)     # 15 000 particles, 40.1 x 40.1 x 40 box: 20 cell columns
+    # thermalise a little on one GPU so that the cells are not lattice-aligned
+    ctx = sm.Context.from_dict(m)
+    ctx.compute_forces()
+    ctx.step(0, 60)
+    m = dict(m)
+    m["xyz"], m["type"], m["vel"] = ctx.get_particles()
+    ctx.close()
+    return m
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_slab_forces_and_energies_match_single_gpu(bilayer, nranks):
+    m = bilayer
+    n = m["nParticles"]
+    one = sm.Context.from_dict(m)
+    one.compute_forces(mask=sm.MASK_ALL, step=77)
+    a1 = one.get_forces()
+    U1, K1 = one.potential(), one.kinetic()
+    scale = [1.0005, 1.0005, 1.0 / (1.0005 * 1.0005)]
+    dU1 = one.dpotential(scale)
+    pairs1, _ = one.count_pairs(per_particle=False)
+    one.close()
+
+    grp = LocalSlabGroup(m, nranks)
+    grp.compute_forces(mask=sm.MASK_ALL, step=77)
+    xyz, typ, vel, acc, owner = grp.gather(n)
+    assert np.array_equal(xyz, m["xyz"]) and np.array_equal(typ, m["type"]) and np.array_equal(vel, m["vel"])
+    # ownership = the cell column ranges of the C ABI's own partition function
+    for r in range(nranks):
+        flags = sm.capi.slab_select(m["size"], m["cutoff"], nranks, r, m["xyz"])
+        assert np.array_equal(flags == 1, owner == r)
+    assert len(set(owner)) == nranks
+    err = rel_err(acc, a1)
+    assert err <= 1e-5
+    assert err <= 1e-12, err
+    U, K, dU = grp.potential(), grp.kinetic(), grp.dpotential(scale)
+    assert grp.count_pairs() == pairs1                             # neighbour membership: every pair exactly once
+    for t in (sm.TERM_PAIR, sm.TERM_CHAIN):
+        assert abs(U[t] - U1[t]) <= 1e-7 * abs(U1[t])
+        assert abs(U[t] - U1[t]) <= 1e-12 * abs(U1[t])
+        assert abs(dU[t] - dU1[t]) <= 1e-12 * abs(U1[t]) + 1e-9 * abs(dU1[t])
+    assert abs(K - K1) <= 1e-13 * K1
+    grp.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_slab_trajectory_with_box_moves_matches_single_gpu(bilayer, orc, nranks):
+    """60 steps of the MD.cpp loop incl. a Metropolis box move with tension every 8 steps: particles migrate between
+    slabs, the halo is renewed every step, the box (and with it every column boundary) changes"""
+    m = bilayer
+    n, K = m["nParticles"], 60
+    mc = orc.mt_rand53(m["seed"], 2 * (K // 8 + 2))
+    tension = 0.5
+
+    def run(sim, box_move):
+        sim.compute_forces(mask=sm.MASK_ALL, step=0)
+        trials = acc = 0
+        for i in range(K):
+            sim.step(i, 1)
+            if i % 8 == 0 and i != 0:
+                ok = box_move(m["deltaLXY"], tension, mc[2 * trials], mc[2 * trials + 1])[0]
+                trials += 1
+                acc += bool(ok)
+        return trials, acc
+
+    one = sm.Context.from_dict(m)
+    t1, acc1 = run(one, one.mc_box_move)
+    x1, _, v1 = one.get_particles()
+    box1 = one.get_box()
+    one.close()
+
+    grp = LocalSlabGroup(m, nranks)
+    t2, acc2 = run(grp, grp.mc_box_move)
+    x2, _, v2, _, owner = grp.gather(n)
+    box2 = grp.get_box()
+    moved = sum(int(np.sum((sm.capi.slab_select(m["size"], m["cutoff"], nranks, r, m["xyz"]) == 1) & (owner != r))) for r in range(nranks))
+    grp.close()
+    assert (t1, acc1) == (t2, acc2) and acc1 > 0
+    np.testing.assert_allclose(box2, box1, rtol=1e-14)
+    assert moved > 0                                    # the run did exercise migration
+    assert np.abs(x2 - x1).max() <= 1e-9
+    assert np.abs(v2 - v1).max() <= 1e-8
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_slab_vesicle_across_the_seam_and_empty_ranks(orc, nranks):
+    """a small vesicle in the middle of a 400^3 box: the seam of a 2-rank split cuts it in half; with 4 ranks two of
+    them own nothing but still take part in every exchange"""
+    m, ref = orc.load_golden(golden_path("lipo_eq"))
+    m["initialTime"] = 0.0
+    n = m["nParticles"]
+    one = sm.Context.from_dict(m)
+    one.compute_forces(step=3)
+    one.step(3, 25)
+    x1, _, v1 = one.get_particles()
+    one.close()
+    grp = LocalSlabGroup(m, nranks, capacity=4096, msg_capacity=4096)
+    grp.compute_forces(step=3)
+    grp.step(3, 25)
+    x2, _, v2, _, owner = grp.gather(n)
+    counts = [c.slab_counts() for c in grp.ctx]
+    grp.close()
+    assert np.abs(x2 - x1).max() <= 1e-10 and np.abs(v2 - v1).max() <= 1e-9
+    assert sum(o for _, o in counts) == n
+    if nranks == 2:
+        assert min(o for _, o in counts) > 100              # really split
+        assert all(l > o for l, o in counts)                # ghosts present on both sides
+
+
+def test_slab_errors_are_loud(bilayer):
+    m = bilayer
+    # too many ranks for the box: a slab must be at least 2 * halo + 1 columns wide
+    with pytest.raises(sm.SoftMoldError, match="narrower"):
+        sm.Context.from_dict(m, rank=0, nranks=5)
+    # a particle that jumps over the halo in one step
+    grp = LocalSlabGroup(m, 2)
+    grp.compute_forces()
+    g, x, t, v, a = grp.ctx[0].slab_get_local()
+    bad = dict(m)
+    bad["vel"] = m["vel"].copy()
+    bad["vel"][g[np.argmax(x[:, 0])]] = [600.0, 0.0, 0.0]          # 12 sigma = 6 columns per step, from the slab's last column
+    grp.close()
+    grp = LocalSlabGroup(bad, 2)
+    grp.compute_forces()
+    grp.step(0, 1)
+    with pytest.raises(sm.SoftMoldError, match="halo"):
+        grp.synchronize()
+    for c in grp.ctx:
+        c.close()
+    # slab contexts refuse what they do not support instead of computing something else
+    ctx = sm.Context.from_dict(m, rank=0, nranks=2)
+    with pytest.raises(sm.SoftMoldError, match="CHAIN molecules only"):
+        ctx.add_molecule(sm.MOL_BOND, np.array([[0, 1]], np.int32), [1.0, 1.0])
+    with pytest.raises(sm.SoftMoldError, match="connect both neighbours"):
+        ctx.step(0, 1)
+    ctx.close()
