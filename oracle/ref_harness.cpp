@@ -173,7 +173,8 @@ static int cmd_mt(int argc, char **argv)
 	return 0;
 }
 
-// phases: time the reference's own Verlet / Langevin / CellOpt / do*Force in MD.cpp:335-511 order, no file I/O.
+// phases: time the reference's own Verlet / Langevin / CellOpt / do*Force in MD.cpp:335-511 order plus the Metropolis
+// box move of MD.cpp:589-721 every 8th step when the file has deltaLXY, no file I/O.
 //   ref_harness phases name nsteps [warmup_reps timed_reps]
 // Each rep is <nsteps> MD iterations.  Prints one line per timed rep: N nsteps seconds threads.
 static void molecule_forces(Blob<double> &S)
@@ -204,6 +205,38 @@ static void bead_mass(Blob<double> &S)
 	}
 }
 
+// one Metropolis box-move trial with the reference's own objects, MD.cpp:589-721 (molecule kinds of the hot path)
+static bool box_move(Blob<double> &S, PairEngine &pair, Verlet<double> &integrate, MTRand &randNum)
+{
+	threeVector<double> size = S.readSize(), oldSize = S.readSize(), fluctuation;
+	fluctuation.x = S.readDeltaLXY() * (2.0 * randNum.rand53() - 1.0);
+	fluctuation.y = fluctuation.x;
+	fluctuation.z = (size.x * size.y) / ((size.x + fluctuation.x) * (size.y + fluctuation.y));
+	size.x += fluctuation.x; size.y += fluctuation.y; size.z *= fluctuation.z;
+	threeVector<double> aSize = size;
+	aSize.x /= oldSize.x; aSize.y /= oldSize.y; aSize.z /= oldSize.z;
+	double dPotential = pair.computeDPotential(aSize);
+	for (int k = 0; k < S.readNMolecules(); k++) {
+		int t = S.getMolecule()[k].readType();
+		if (t == BOND) dPotential += S.doBondDPotential(k, aSize);
+		else if (t == BEND) dPotential += S.doBendDPotential(k, aSize);
+		else if (t == CHAIN) dPotential += S.doChainDPotential(k, aSize);
+		else if (t == BEAD) dPotential += S.doBeadDPotential(k, aSize);
+	}
+	if (S.readTension() != 0) dPotential += S.readTension() * ((size.x * size.y) - (oldSize.x * oldSize.y));
+	double D = exp(dPotential / S.readInitialTemp());
+	double randNumber = randNum.rand53();
+	if (D >= randNumber || -dPotential <= 0) {
+		position<double> *p = S.getPositions();
+		for (int k = 0; k < S.readNParticles(); k++) { p[k].x *= aSize.x; p[k].y *= aSize.y; p[k].z *= aSize.z; }
+		pair.resize(size);
+		integrate.resize(size);
+		S.setSize(size);
+		return true;
+	}
+	return false;
+}
+
 static int cmd_phases(int argc, char **argv)
 {
 	if (argc < 4) { fprintf(stderr, "usage: ref_harness phases name nsteps [warmup_reps timed_reps]\n"); return 2; }
@@ -228,9 +261,13 @@ static int cmd_phases(int argc, char **argv)
 	pair.computeForce();
 	thermostat.compute(S.readInitialTemp());
 	molecule_forces(S);
+	// the barostat stream and cadence of MD.cpp:67,149,589 -- active when the file carries deltaLXY
+	MTRand randNum(S.readSeed());
+	const int resizeRate = 8;
+	long step = 0, trials = 0, accepted = 0;
 	for (int rep = 0; rep < warm + reps; rep++) {
 		double t0 = omp_get_wtime();
-		for (int i = 0; i < nsteps; i++) {
+		for (int i = 0; i < nsteps; i++, step++) {
 			bead_mass(S);
 			integrate.first();
 			for (int k = 0; k < n; k++) { acc[k].x = 0; acc[k].y = 0; acc[k].z = 0; }
@@ -240,10 +277,15 @@ static int cmd_phases(int argc, char **argv)
 			molecule_forces(S);
 			bead_mass(S);
 			integrate.second();
+			if (step % resizeRate == 0 && step != 0 && S.readDeltaLXY() != 0) {
+				trials++;
+				if (box_move(S, pair, integrate, randNum)) accepted++;
+			}
 		}
 		double t1 = omp_get_wtime();
 		if (rep >= warm) { printf("%d %d %.6f %d\n", n, nsteps, t1 - t0, omp_get_max_threads()); fflush(stdout); }
 	}
+	fprintf(stderr, "box moves: %ld trials, %ld accepted\n", trials, accepted);
 	return 0;
 }
 
