@@ -200,7 +200,9 @@ enum { SMD_PHASE_INTEGRATE1 = 0,  /* bead mass, Verlet::first (+ cell tagging), 
        SMD_PHASE_INTEGRATE2 = 5,  /* Verlet::second                                     MD.cpp:511     */
        SMD_PHASE_STEP = 6,        /* one whole smd_step_begin + smd_step_end                           */
        SMD_PHASE_EXCHANGE = 7,    /* slab mode: migration + halo pack / unpack                         */
-       SMD_NPHASES = 8 };
+       SMD_PHASE_FUSED = 8,       /* CHAIN-only systems: chain forces + Verlet::second + next Verlet::first in one
+                                     kernel (then phases 0, 3, 5 only count the first / last step of a batch) */
+       SMD_NPHASES = 16 };
 int smd_profile(smd_ctx *ctx, uint32_t phase_mask);
 int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPHASES]);
 

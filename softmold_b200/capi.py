@@ -363,7 +363,7 @@ class Context:
         self._ck(self.L.smd_profile(self.h, mask))
 
     def profile_read(self):
-        ms, cnt = np.zeros(8), np.zeros(8, np.int64)
+        ms, cnt = np.zeros(16), np.zeros(16, np.int64)
         self._ck(self.L.smd_profile_read(self.h, _ptr(ms), _ptr(cnt)))
         return {p: (float(ms[i]), int(cnt[i])) for i, p in enumerate(PHASES)}
 
@@ -378,7 +378,7 @@ class Context:
         return a.value, b.value
 
 
-PHASES = ["integrate1", "build", "pair", "molecules", "langevin", "integrate2", "step", "exchange"]
+PHASES = ["integrate1", "build", "pair", "molecules", "langevin", "integrate2", "step", "exchange", "fused"]
 
 
 class Mpd:

@@ -5,6 +5,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 #include "smd_kernels.cuh"
@@ -147,11 +148,12 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 static int upload_acut(smd_ctx *ctx)
 {
 	if (ctx->acut_raw.empty()) return SMD_OK;
-	std::vector<float> a(ctx->nT);
+	std::vector<float> &a = ctx->acut_host;   // lives in the context: the copy below is not waited for
+	a.resize(ctx->nT);
 	for (int t = 0; t < ctx->nT; t++)
 		a[t] = ctx->acut_raw[t] < 0 ? -1.0f : std::min(ctx->acut_raw[t] + ctx->pgeo.margin32, ctx->pgeo.thr32);
+	// a few bytes from pageable memory: staged by the runtime before the call returns, ordered on the stream
 	cudaError_t e = cudaMemcpyAsync(ctx->acut, a.data(), a.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	if (e != cudaSuccess) { ctx->err = std::string("upload_acut: ") + cudaGetErrorString(e); return SMD_ERR_CUDA; }
 	return SMD_OK;
 }
@@ -215,12 +217,16 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->temperature = desc->temperature;
 	ctx->device = desc->device;
 	ctx->cur = 0;
+	ctx->pcur = 0;
 	ctx->cells_valid = false;
 	ctx->tables_set = ctx->particles_set = false;
 	ctx->noise_ready = false;
 	ctx->acc_live = false;
 	ctx->n_molecules = 0;
 	ctx->launches = ctx->rebuilds = 0;
+	{ const char *e = getenv("SMD_ENERGY_ONEPHASE"); ctx->force_onephase_energy = e && *e == '1'; }
+	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
+	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
 	int rc = check_geom(ctx);
 	if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
@@ -248,6 +254,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMemset(ctx->pos32, 0, (cap + 8) * sizeof(float4)));
 	CKC(cudaMalloc(&ctx->acut, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
+	CKC(cudaMalloc(&ctx->utab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->win, WIN_WORDS * sizeof(int)));
 	CKC(cudaMemset(ctx->win, 0, WIN_WORDS * sizeof(int)));
 	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
@@ -299,10 +306,12 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{
 		int smem = (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
 		           (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
-		cudaError_t e1 = cudaFuncSetAttribute(k_pair_force2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaError_t e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e1 != cudaSuccess) {
 			g_create_error = std::string("cudaFuncSetAttribute(k_pair_force2): ") + cudaGetErrorString(e1);
 			smd_destroy(ctx);
@@ -326,7 +335,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (int b = 0; b < 2; b++) {
 		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]);
 	}
-	cudaFree(ctx->pos32); cudaFree(ctx->acut); cudaFree(ctx->ptab);
+	cudaFree(ctx->pos32); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
 	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
 	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
 	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
@@ -419,6 +428,15 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 			o[6] = r[3]; o[7] = r[4]; o[8] = r[5];
 		}
 		CK(cudaMemcpyAsync(ctx->ptab, pt.data(), pt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		// the potential's constants in the same padded layout (energy modes of the two-phase kernel)
+		std::vector<double> ut((size_t)PTAB_STRIDE * nT * nT, 0.0);
+		for (int k = 0; k < nT * nT; k++) {
+			const double *r = uC + 6 * k;
+			double *o = ut.data() + (size_t)PTAB_STRIDE * k;
+			o[2] = r[0]; o[3] = r[1]; o[4] = r[2];
+			o[6] = r[3]; o[7] = r[4]; o[8] = r[5];
+		}
+		CK(cudaMemcpyAsync(ctx->utab, ut.data(), ut.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 		CK(cudaStreamSynchronize(ctx->stream));
 		int rc = upload_acut(ctx);
 		if (rc) return rc;
@@ -438,10 +456,12 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 
 // tag every particle with its cell and accumulate the occupied bounding box (after set_particles / a box move;
 // the steady state does this inside k_verlet_first)
-static int retag_cells(smd_ctx *ctx)
+static int retag_cells(smd_ctx *ctx, bool rearm = true)
 {
-	LAUNCH(k_arm_bbox, 1, 32, 0, ctx->bbox);
-	LAUNCH(k_tag_cells, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->cur], ctx->geom, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur]);
+	// rearm = false: the cell grid is the same and the particles barely moved (accepted box move): keep the extremes,
+	// so that the tagging pass issues almost no atomics (thousands of warps hitting one address cost ~40 us)
+	if (rearm) LAUNCH(k_arm_bbox, 1, 32, 0, ctx->bbox);
+	LAUNCH(k_tag_cells, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->pcur], ctx->geom, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur]);
 	ctx->cells_valid = false;
 	return SMD_OK;
 }
@@ -494,6 +514,7 @@ extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t 
 	CK(cudaMemcpyAsync(ctx->istage, type, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 	if (vel) CK(cudaMemcpyAsync(sv, vel, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	ctx->cur = 0;
+	ctx->pcur = 0;
 	if (N > 0)
 		LAUNCH(k_import_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, sx, ctx->istage, vel ? sv : nullptr, ctx->pos[0], ctx->vel[0],
 		       ctx->unw[0], ctx->gid[0], ctx->slot_of, gid_in);
@@ -647,22 +668,23 @@ extern "C" int smd_set_noise(smd_ctx *ctx, const double *u)
 // ------------------------------------------------------------------------------------------------ cell build
 static int build_cells(smd_ctx *ctx)
 {
-	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1;
+	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1, pcur = ctx->pcur, pnxt = pcur ^ 1;
 	// particles were tagged with their cell (and bbox[] accumulated) by whoever moved them last
 	if (ctx->slab && !ctx->ext_valid)   // no unpack since the last build: the extended count is the current one
 		CK(cudaMemcpyAsync(ctx->dN + 1, ctx->dN, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
 	ctx->ext_valid = false;
-	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[cur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag);
+	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag);
 	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
 	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, ctx->win, ctx->geom, ctx->cellcap, ctx->errflag,
 	       (ctx->rebuilds & 255) == 255 ? 1 : 0);
 	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N, ctx->slab ? ctx->dN : nullptr);
 	LAUNCH(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order);
-	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[cur], ctx->pos[nxt],
+	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
 	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut);
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
+	ctx->pcur = pnxt;
 	ctx->cells_valid = true;
 	ctx->rebuilds++;
 	return SMD_OK;
@@ -687,7 +709,7 @@ static int pair_smem(smd_ctx *ctx) { return 6 * ctx->nT * ctx->nT * (int)sizeof(
 // build in the reference's loop order), so forces are always evaluated as: [build] -> zero -> terms.
 static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 {
-	const Particle *pos = ctx->pos[ctx->cur];
+	const Particle *pos = ctx->pos[ctx->pcur];
 	if (mask & SMD_MASK(SMD_TERM_CHAIN))
 		for (auto &cb : ctx->chains) {
 			if (cb.nChains <= 0) continue;
@@ -780,11 +802,11 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
 		ProfScope ps(ctx, SMD_PHASE_PAIR);
 		if (ctx->tables_symmetric)
-			LAUNCH((k_pair_force2<true, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
+			LAUNCH((k_pair_force2<0, true, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
 		else
-			LAUNCH((k_pair_force2<true, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
+			LAUNCH((k_pair_force2<0, true, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
 		ctx->acc_live = true;
 	} else {
 		LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->acc);
@@ -796,11 +818,11 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		if (pair) {
 			ProfScope ps(ctx, SMD_PHASE_PAIR);
 			if (ctx->tables_symmetric)
-				LAUNCH((k_pair_force2<false, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
+				LAUNCH((k_pair_force2<0, false, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
 			else
-				LAUNCH((k_pair_force2<false, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->pos32,
-				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur]);
+				LAUNCH((k_pair_force2<0, false, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
 		}
 		if (!langevin_first && lang) {
 			ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
@@ -827,7 +849,7 @@ extern "C" int smd_resume(smd_ctx *ctx)
 	int rc = ready(ctx);
 	if (rc) return rc;
 	bead_mass_divide(ctx);
-	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);
+	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);
 	return SMD_OK;
 }
 
@@ -840,7 +862,7 @@ extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
 	int N = ctx->N;
 	ProfScope ps(ctx, SMD_PHASE_INTEGRATE1);
 	bead_mass_divide(ctx);                                                         // MD.cpp:340-355
-	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
+	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
 	       ctx->desc.dt, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur]);             // MD.cpp:356
 	// a = 0 (MD.cpp:357-366) is folded into the force evaluation that follows: it overwrites a[]
 	ctx->acc_live = false;
@@ -859,20 +881,65 @@ extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
 	if (rc) return rc;
 	{ ProfScope ps(ctx, SMD_PHASE_MOLECULES); bead_mass_divide(ctx); }             // MD.cpp:480-494
 	ProfScope ps(ctx, SMD_PHASE_INTEGRATE2);
-	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);   // :511
+	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);   // :511
 	return SMD_OK;
+}
+
+// CHAIN-only systems: the seam between two consecutive steps (chain forces, Verlet::second, next Verlet::first) is
+// one kernel, see k_chain_kick
+static bool can_fuse(const smd_ctx *ctx)
+{
+	return !ctx->no_fuse && ctx->bonds.empty() && ctx->bends.empty() && ctx->beads.empty() && ctx->balls.empty() &&
+	       (int)ctx->chains.size() <= MAX_FUSED_CHAINS && ctx->desc.noise != SMD_NOISE_EXTERNAL;
+}
+
+static ChainSet chain_set(const smd_ctx *ctx)
+{
+	ChainSet cs;
+	cs.n = 0;
+	for (auto &cb : ctx->chains)
+		if (cb.nChains > 0) cs.b[cs.n++] = cb;
+	return cs;
 }
 
 extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(ctx->desc.noise != SMD_NOISE_EXTERNAL || nsteps <= 1, "external noise: one step per smd_set_noise");
+	if (nsteps <= 0) return SMD_OK;
+	if (!can_fuse(ctx)) {
+		for (int k = 0; k < nsteps; k++) {
+			ProfScope ps(ctx, SMD_PHASE_STEP);
+			int rc = smd_step_begin(ctx, first_step + k);
+			if (rc) return rc;
+			rc = smd_step_end(ctx, first_step + k);
+			if (rc) return rc;
+		}
+		return SMD_OK;
+	}
+	int rc = smd_step_begin(ctx, first_step);
+	if (rc) return rc;
+	const ChainSet cs = chain_set(ctx);
+	const int N = ctx->N;
 	for (int k = 0; k < nsteps; k++) {
 		ProfScope ps(ctx, SMD_PHASE_STEP);
-		int rc = smd_step_begin(ctx, first_step + k);
+		// MD.cpp:410-413: thermostat, build, pair force (one kernel) -- no molecule terms here
+		rc = forces(ctx, SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_LANGEVIN, first_step + k, true);
 		if (rc) return rc;
-		rc = smd_step_end(ctx, first_step + k);
-		if (rc) return rc;
+		const bool last = (k == nsteps - 1);
+		ProfScope pf(ctx, SMD_PHASE_FUSED);
+		if (last) {
+			LAUNCH(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag);
+		} else {
+			LAUNCH(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
+			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
+			       ctx->errflag);
+			ctx->pcur ^= 1;
+			ctx->acc_live = false;
+			ctx->cells_valid = false;
+			if (ctx->slab && (rc = smd_slab_exchange_send(ctx))) return rc;
+		}
 	}
 	return SMD_OK;
 }
@@ -894,12 +961,23 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	if (ctx->slab && ctx->exch_pending) { ctx->err = "slab: energy call between smd_step_begin and smd_step_end"; return SMD_ERR_ARG; }
 	if (!ctx->cells_valid) build_cells(ctx);   // dataExtraction::compute rebuilds its own CellOpt (dataExtraction.h:839-841)
 	double sx = scale ? scale[0] : 1.0, sy = scale ? scale[1] : 1.0, sz = scale ? scale[2] : 1.0;
-	const Particle *pos = ctx->pos[ctx->cur];
+	const Particle *pos = ctx->pos[ctx->pcur];
 	std::vector<int> term_of_slot;
 	int slot = 0;
 	auto push = [&](int term) { term_of_slot.push_back(term); return slot++; };
 	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + 2 * ctx->beads.size() <= 64, "too many molecule records for one energy call");
-	{
+	if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
+		// two-phase kernel, every unordered pair once (see k_pair_force2)
+		int nb = nblk(N, PAIR_TPB);
+		EnergyArgs en;
+		en.sx = sx; en.sy = sy; en.sz = sz; en.partials = ctx->partials;
+		double grow = 0;   // the most a component-wise scaling moves r^2 across a cutoff, relative
+		for (double sc : {sx, sy, sz}) grow = std::max(grow, std::max(fabs(sc * sc - 1.0), fabs(1.0 / (sc * sc) - 1.0)));
+		en.extra32 = MODE == 1 ? 0.0f : nextafterf((float)(1.01 * grow * ctx->geom.rc2 + 1e-7), INFINITY);
+		LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
+		       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en);
+		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
+	} else {
 		int nb = nblk(N, TPB);
 		LAUNCH(k_pair<(MODE == 1 ? PAIR_POTENTIAL : PAIR_DPOTENTIAL)>, nb, TPB, pair_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->gid[ctx->cur], ctx->start,
 		       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, nullptr, ctx->partials, nullptr, sx, sy, sz);
@@ -984,7 +1062,7 @@ extern "C" int smd_count_pairs(smd_ctx *ctx, int64_t *total, int32_t *per_partic
 	int nb = nblk(N, TPB);
 	if (ctx->slab && per_particle) { ctx->err = "slab: per-particle counts are not exported (use smd_slab_get_local)"; return SMD_ERR_UNSUPPORTED; }
 	if (ctx->slab) CK(cudaMemsetAsync(ctx->icount, 0, (size_t)ctx->cap * sizeof(int), ctx->stream));
-	LAUNCH(k_pair<PAIR_COUNT>, nb, TPB, pair_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom,
+	LAUNCH(k_pair<PAIR_COUNT>, nb, TPB, pair_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom,
 	       ctx->nT, ctx->fC, nullptr, ctx->partials, ctx->icount, 1.0, 1.0, 1.0);
 	finish_sum(ctx, nb, 0, 1.0);
 	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1011,8 +1089,9 @@ extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new
 	if (!rc && total > ctx->cellcap) { ctx->err = "box grew beyond the cell-table capacity"; rc = SMD_ERR_UNSUPPORTED; }
 	if (rc) { set_geom(ctx, old.box); return rc; }
 	if ((rc = upload_acut(ctx))) return rc;
-	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->cur], scale[0], scale[1], scale[2]);
-	retag_cells(ctx);
+	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->pcur], scale[0], scale[1], scale[2]);
+	bool same_grid = old.nc[0] == ctx->geom.nc[0] && old.nc[1] == ctx->geom.nc[1] && old.nc[2] == ctx->geom.nc[2];
+	retag_cells(ctx, !same_grid);
 	return SMD_OK;
 }
 
@@ -1077,7 +1156,7 @@ extern "C" int smd_get_particles(smd_ctx *ctx, double *xyz, int32_t *type, doubl
 	CK(cudaSetDevice(ctx->device));
 	int N = ctx->N;
 	double *sx = ctx->stage, *sv = ctx->stage + 3 * (size_t)ctx->cap;
-	LAUNCH(k_export_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->gid[ctx->cur], xyz ? sx : nullptr,
+	LAUNCH(k_export_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->gid[ctx->cur], xyz ? sx : nullptr,
 	       type ? ctx->istage : nullptr, vel ? sv : nullptr);
 	if (xyz) CK(cudaMemcpyAsync(xyz, sx, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	if (type) CK(cudaMemcpyAsync(type, ctx->istage, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1126,7 +1205,7 @@ extern "C" int smd_get_cell_ids(smd_ctx *ctx, int32_t n_cells_xyz[3], int32_t *c
 	if (!ctx->cells_valid) build_cells(ctx);
 	int N = ctx->N;
 	int *key = ctx->istage, *rank = ctx->istage + ctx->cap;
-	LAUNCH(k_export_cells, nblk(N, TPB), TPB, 0, N, ctx->pos[ctx->cur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom, key, rank);
+	LAUNCH(k_export_cells, nblk(N, TPB), TPB, 0, N, ctx->pos[ctx->pcur], ctx->gid[ctx->cur], ctx->start, cur_win(ctx), ctx->geom, key, rank);
 	CK(cudaMemcpyAsync(cell_key, key, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaMemcpyAsync(cell_rank, rank, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	if (n_cells_xyz) for (int d = 0; d < 3; d++) n_cells_xyz[d] = ctx->geom.nc[d];
@@ -1138,7 +1217,7 @@ extern "C" int smd_device_ptr(smd_ctx *ctx, int32_t which, void **ptr, size_t *b
 	if (!ctx || !ptr) return SMD_ERR_ARG;
 	size_t b = 0;
 	switch (which) {
-	case 0: *ptr = ctx->pos[ctx->cur]; b = (size_t)ctx->N * sizeof(Particle); break;
+	case 0: *ptr = ctx->pos[ctx->pcur]; b = (size_t)ctx->N * sizeof(Particle); break;
 	case 1: *ptr = ctx->vel[ctx->cur]; b = 3 * (size_t)ctx->cap * sizeof(double); break;
 	case 2: *ptr = ctx->acc; b = 3 * (size_t)ctx->cap * sizeof(double); break;
 	case 3: *ptr = ctx->gid[ctx->cur]; b = (size_t)ctx->N * sizeof(int); break;
@@ -1278,7 +1357,7 @@ extern "C" int smd_slab_exchange_send(smd_ctx *ctx)
 	CK(cudaSetDevice(ctx->device));
 	ProfScope ps(ctx, SMD_PHASE_EXCHANGE);
 	ctx->xseq++;
-	LAUNCH(k_slab_pack, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
+	LAUNCH(k_slab_pack, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
 	       ctx->gid[ctx->cur], ctx->geom, ctx->comm, ctx->xseq, ctx->errflag);
 	ctx->exch_pending = true;
 	ctx->cells_valid = false;
@@ -1293,7 +1372,7 @@ extern "C" int smd_slab_exchange_recv(smd_ctx *ctx)
 	ProfScope ps(ctx, SMD_PHASE_EXCHANGE);
 	int blocks = std::min(nblk(2ll * ctx->comm.capmsg, 256), 296);
 	long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a neighbour that never sends is reported, not waited for
-	LAUNCH(k_slab_unpack, blocks, 256, 0, cnt_of(ctx), ctx->dN + 1, ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
+	LAUNCH(k_slab_unpack, blocks, 256, 0, cnt_of(ctx), ctx->dN + 1, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
 	       ctx->gid[ctx->cur], ctx->comm, ctx->xseq, ctx->errflag, spin_limit);
 	ctx->exch_pending = false;
 	ctx->ext_valid = true;
@@ -1320,7 +1399,7 @@ extern "C" int smd_slab_get_local(smd_ctx *ctx, int32_t *n, int32_t *gid, double
 	CK(cudaMalloc(&d_i, 2 * cap * sizeof(int)));
 	CK(cudaMalloc(&d_d, 9 * cap * sizeof(double)));
 	CK(cudaMemsetAsync(ctx->d_export_counter, 0, sizeof(int), ctx->stream));
-	LAUNCH(k_slab_export, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->cur], ctx->vel[ctx->cur], ctx->acc, ctx->gid[ctx->cur],
+	LAUNCH(k_slab_export, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->gid[ctx->cur],
 	       ctx->d_export_counter, d_i, d_d, d_d + 3 * cap, d_d + 6 * cap, d_i + cap);
 	int cnt = 0;
 	cudaError_t e = cudaMemcpyAsync(&cnt, ctx->d_export_counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);

@@ -109,12 +109,17 @@ struct smd_ctx {
 	float4 *pos32;    // FP32 mirror {x,y,z,type} of pos[cur], written by the reorder (phase 1 of the pair force kernel)
 	float *acut;      // [nT] FP32 phase-1 class cutoff per type, margin included (see k_pair_force2)
 	double *ptab;     // [nT*nT][PTAB_STRIDE] padded force table + exact branch thresholds
+	double *utab;     // same layout, potential constants (energy modes of the two-phase kernel)
+	bool force_onephase_energy = false;   // SMD_ENERGY_ONEPHASE=1: use the one-phase half-stencil energy kernels (A/B checks)
 	std::vector<float> acut_raw;   // host: rm^2 / +inf / -1 per type, before the margin
+	std::vector<float> acut_host;  // host copy of acut[] (source of an un-waited upload)
 	smd::PairGeo pgeo; // rc^2 + FP32 rounding margin etc. for that phase
 	double *vel[2];   // SoA [3][cap]
 	double *unw[2];   // SoA [3][cap] unwrapped positions (optional)
 	int *gid[2];      // original index of slot
-	int cur;
+	int cur;          // current buffer of vel / unw / gid
+	int pcur;         // current buffer of pos (flips on its own when the fused step kernel writes the drifted positions)
+	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)
 	double *acc;      // SoA [3][cap]
 	double *acc2;     // alternate buffer for builds that must carry live accelerations along
 	bool acc_live;    // acc holds forces a later kick still needs

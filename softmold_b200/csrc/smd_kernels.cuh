@@ -229,10 +229,13 @@ __device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, 
 	if (g.slab) return;   // the window of a slab is fixed by its column range
 	for (int d = 0; d < 3; d++) {
 		int l = __reduce_min_sync(0xffffffffu, lo[d]), h = __reduce_max_sync(0xffffffffu, hi[d]);
-		// the box of occupied cells hardly moves between steps: only touch the accumulators when they would change
+		// the box of occupied cells hardly moves between steps: only touch the accumulators when they would change.
+		// Plain (L1-cached) loads on purpose: the extremes only ever grow during a pass, so a stale copy can at worst
+		// cause a redundant atomic, while volatile loads of one address by every warp of the grid serialise in a
+		// single L2 slice (that was 15 us of the 20 us of the integrator kernel).
 		if ((threadIdx.x & 31) == 0 && l != INT_MAX) {
-			if (l < ((volatile int *)bbox)[d]) atomicMin(bbox + d, l);
-			if (h > ((volatile int *)bbox)[3 + d]) atomicMax(bbox + 3 + d, h);
+			if (l < bbox[d]) atomicMin(bbox + d, l);
+			if (h > bbox[3 + d]) atomicMax(bbox + 3 + d, h);
 		}
 	}
 }
@@ -688,6 +691,37 @@ __device__ __noinline__ D3 pair_force_term(int i, Particle pi, int j, Particle p
 	return f;
 }
 
+// energy twin of pair_force_term for the two-phase kernel's slow path (pairs seen through a periodic image): the term
+// of the pair (i, j) if i is the reference's home particle of it, else 0 -- both ends call it, one of them counts.
+// EMODE 1: U (cellOpt.h:928-1041), 2: U(d) - U(d o scale) (cellOpt.h:1043-1180).  Same arithmetic as k_pair.
+template <int EMODE>
+__device__ __noinline__ double pair_energy_term(int i, Particle pi, int j, Particle pj, const Geom &g, int nT, const double *uC,
+                                                double sx, double sy, double sz, bool always)
+{
+	int cx, cy, cz, jx, jy, jz;
+	unpack_cell(pi.cell, cx, cy, cz);
+	unpack_cell(pj.cell, jx, jy, jz);
+	int ox = jx - cx, oy = jy - cy, oz = jz - cz;
+	double Sx = 0, Sy = 0, Sz = 0;
+	if (ox > 1) { ox -= g.nc[0]; Sx = -g.box[0]; } else if (ox < -1) { ox += g.nc[0]; Sx = g.box[0]; }
+	if (oy > 1) { oy -= g.nc[1]; Sy = -g.box[1]; } else if (oy < -1) { oy += g.nc[1]; Sy = g.box[1]; }
+	if (oz > 1) { oz -= g.nc[2]; Sz = -g.box[2]; } else if (oz < -1) { oz += g.nc[2]; Sz = g.box[2]; }
+	bool self = (ox == 0 && oy == 0 && oz == 0);
+	bool fwd = (oz == 1) || (oz == 0 && (ox == 1 || (ox == 0 && oy == 1)));
+	bool home = self ? (i > j) : fwd;
+	if (!home && !always) return 0.0;   // always: an unshifted pair the caller visits once (symmetric tables)
+	double qx = pj.x, qy = pj.y, qz = pj.z;
+	if (!self && !always) { qx += Sx; qy += Sy; qz += Sz; }   // adding a zero shift is exact
+	double dx = pi.x - qx, dy = pi.y - qy, dz = pi.z - qz;
+	double dr2 = dx * dx + dy * dy + dz * dz;
+	double uo = (dr2 < g.rc2) ? pair_potential_val(dr2, pi.type, pj.type, nT, uC) : 0.0;
+	if (EMODE == 1) return uo;
+	double ex = pi.x * sx - qx * sx, ey = pi.y * sy - qy * sy, ez = pi.z * sz - qz * sz;
+	double er2 = ex * ex + ey * ey + ez * ez;
+	double un = (er2 < g.rc2) ? pair_potential_val(er2, pi.type, pj.type, nT, uC) : 0.0;
+	return uo - un;
+}
+
 // 1/sqrt(x) to ~2^-43 from the MUFU.RSQ64H seed and one Newton step; x normal and positive
 __device__ __forceinline__ double rsqrt43(double x)
 {
@@ -738,16 +772,28 @@ struct PairSmem {
 	int wcnt[PAIR_TPB / 32];
 };
 
-template <bool LANGEVIN, bool SYMM>
+//
+// EMODE 0: forces.  EMODE 1 / 2: the same two-phase machinery evaluates the pair potential / the dPotential of a box
+// move (SYMM tables only; tab = uC, ptab = the potential's padded table): every unordered pair is visited ONCE --
+// phase 1 walks only the forward rows of the stencil (oz = 1, or oz = 0 and oy = 1) and, in the particle's own row,
+// the slots behind its own (the rest of its cell and the cell at +x) -- and a block reduction replaces the write of
+// a[].  Phase 1 widens its cutoffs by `extra32`, the most a component-wise scaling of the box can move r^2 across a
+// cutoff (a pair outside rc before the move and inside after it still has a term).
+struct EnergyArgs { double sx, sy, sz; float extra32; double *partials; };
+
+template <int EMODE, bool LANGEVIN, bool SYMM>
 __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
                                                             const int *__restrict__ win, Geom g, int nT,
                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
                                                             PairGeo pg, double *__restrict__ acc, LangevinArgs lg,
-                                                            const int *__restrict__ gid)
+                                                            const int *__restrict__ gid, EnergyArgs en)
 {
 	const int N = cnt.get();
-	if ((int)(blockIdx.x * PAIR_TPB) >= N) return;
+	if ((int)(blockIdx.x * PAIR_TPB) >= N) {
+		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
+		return;
+	}
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
@@ -834,6 +880,54 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			D3 f = pair_force_term(io, po, j, pj, g, nT, tab, 6 * nT * nT);
 			ax += f.x; ay += f.y; az += f.z;
 		};
+		// Potential<T>, MD.h:895-930, on r^2 (x normal and positive): correctly rounded sqrt as above, both branches
+		// evaluated and selected
+		auto upot = [&](double x, const char *c) {
+			double y = rsqrt43(x);
+			double dr = x * y;
+			dr = __fma_rn(__fma_rn(-dr, dr, x), 0.5 * y, dr);
+			double2 c01 = *reinterpret_cast<const double2 *>(c + 16);
+			double c2 = *reinterpret_cast<const double *>(c + 32);
+			double2 c34 = *reinterpret_cast<const double2 *>(c + 48);
+			double c5 = *reinterpret_cast<const double *>(c + 64);
+			double tc = c01.x - dr, tt = c34.x - dr;
+			double ucore = c01.y * tc * tc + c2;
+			double utail = tt * tt * (c34.y - tt * c5);
+			return (dr <= c01.x) ? ucore : utail;
+		};
+		auto efast = [&](int j, const Particle &pj) {
+			double dx = po.x - pj.x, dy = po.y - pj.y, dz = po.z - pj.z;
+			double dr2 = dx * dx + dy * dy + dz * dz;
+			const char *c = rowi + (PTAB_STRIDE * 8) * pj.type;
+			bool in = dr2 < rc2 && j != io;
+			double u = upot(in ? dr2 : 1.0, c);
+			u = in ? u : 0.0;
+			if (EMODE == 2) {
+				double ex = po.x * en.sx - pj.x * en.sx, ey = po.y * en.sy - pj.y * en.sy, ez = po.z * en.sz - pj.z * en.sz;
+				double er2 = ex * ex + ey * ey + ez * ez;
+				bool in2 = er2 < rc2 && j != io;
+				double un = upot(in2 ? er2 : 1.0, c);
+				u = u - (in2 ? un : 0.0);
+			}
+			ax += u;
+		};
+		if (EMODE != 0) {
+			while (rp < wend) {
+				int j0;
+				Particle p0 = fetch(rp, j0);
+				rp += 64u;
+				if (rp < wend) {
+					int j1;
+					Particle p1 = fetch(rp, j1);
+					rp += 64u;
+					efast(j0, p0);
+					efast(j1, p1);
+				} else {
+					efast(j0, p0);
+				}
+			}
+			return;
+		}
 		if (rp + 64u < wend) {
 			int j0, j1;
 			Particle p0 = fetch(rp, j0), p1 = fetch(rp + 64u, j1);
@@ -885,7 +979,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			fp[a] = fmaxf((float)(ci[a] + 1) * pg.cs32[a] - c[a] - pg.slack32, 0.f);
 		}
 	}
-	const float amax = fminf(ai, pg.thr32);
+	const float ext = EMODE != 0 ? en.extra32 : 0.f;
+	const float amax = fminf(ai, pg.thr32) + ext;
 	int nseg = 0;
 	bool shifted_rows = false;
 #pragma unroll 1
@@ -898,6 +993,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		float gyz = gy * gy + gz * gz;
 		bool row_ok = live && gyz < amax;
 		if (row_ok && (wrapyz || cx == 0 || cx == g.nc[0] - 1)) shifted_rows = true;
+		if (EMODE != 0 && (oz < 0 || (oz == 0 && oy < 0))) row_ok = false;   // backward rows: the other particle counts the pair
 		row_ok = row_ok && !wrapyz && lz >= 0 && lz < d2 && ly >= 0 && ly < d1;
 		bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
 		// cells cx-1 .. cx+1 that need no wrap, clamped to the window (cells outside it are empty)
@@ -911,6 +1007,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (row_ok && xlo <= xhi) {
 			int rowbase = d0 * (ly + d1 * lz);
 			jb = start[rowbase + xlo]; je = start[rowbase + xhi + 1];
+			if (EMODE != 0 && oz == 0 && oy == 0) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
 		}
 		sm.seg_b[r][tid] = jb;
 		const int lim = (1 << PAIR_SEGBITS) - 4;
@@ -919,9 +1016,13 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		for (int j = jb + lim; j < je; j++) {
 			float4 c = pos32[j];
 			float dx = p32.x - c.x, dy = p32.y - c.y, dz = p32.z - c.z;
-			if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w) && j != i) {
-				D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
-				ex += f.x; ey += f.y; ez += f.z;
+			if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w) + ext && j != i) {
+				if (EMODE == 0) {
+					D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
+					ex += f.x; ey += f.y; ez += f.z;
+				} else {
+					ex += pair_energy_term<(EMODE ? EMODE : 1)>(i, pi, j, load_particle(pos + j), g, nT, tab, en.sx, en.sy, en.sz, true);
+				}
 			}
 		}
 		nseg = (je > jb) ? r + 1 : nseg;
@@ -949,7 +1050,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			for (int k = 0; k < 4; k++) {
 				float dx = p32.x - c[k].x, dy = p32.y - c[k].y, dz = p32.z - c[k].z;
 				float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-				if (r2 < fminf(ai, c[k].w) && k < rem) push(tag | (unsigned)(q + k));
+				const float thr = EMODE != 0 ? fminf(ai, c[k].w) + ext : fminf(ai, c[k].w);
+				if (r2 < thr && k < rem) push(tag | (unsigned)(q + k));
 			}
 			drain_if_full();
 		}
@@ -994,9 +1096,13 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			for (int j = jb; j < je; j++) {
 				float4 c = pos32[j];
 				float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-				if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w)) {
-					D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
-					ex += f.x; ey += f.y; ez += f.z;
+				if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w) + ext) {
+					if (EMODE == 0) {
+						D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
+						ex += f.x; ey += f.y; ez += f.z;
+					} else {
+						ex += pair_energy_term<(EMODE ? EMODE : 1)>(i, pi, j, load_particle(pos + j), g, nT, tab, en.sx, en.sy, en.sz, false);
+					}
 				}
 			}
 		}
@@ -1027,13 +1133,18 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];
 	const int io = sm.perm[o];
-	if (io >= N) return;
-	if (g.slab && (gid[io] & GID_GHOST)) return;
-	const Particle po = load_particle(pos + io);
+	const bool act = io < N && !(g.slab && (gid[io] & GID_GHOST));
+	if (EMODE == 0 && !act) return;
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
-	{
+	if (act) {
+		const Particle po = load_particle(pos + io);
 		const unsigned ob = list_base(o);
 		drain(io, po, o, ob, ob + 64u * (unsigned)sm.cnt[o], ax, ay, az);
+	}
+	if (EMODE != 0) {   // one partial sum per block, reduced deterministically by k_final_sum
+		double tot = block_sum(act ? ax : 0.0);
+		if (tid == 0) en.partials[blockIdx.x] = tot;
+		return;
 	}
 	if (LANGEVIN) {
 		int id = lg.gid[io] & GID_MASK;
@@ -1452,6 +1563,123 @@ __global__ void __launch_bounds__(TPB) k_slab_export(Cnt cnt, int cap, const Par
 	out_type[k] = p.type;
 	out_vel[3 * k] = vel[s]; out_vel[3 * k + 1] = vel[cap + s]; out_vel[3 * k + 2] = vel[2 * cap + s];
 	out_acc[3 * k] = acc[s]; out_acc[3 * k + 1] = acc[cap + s]; out_acc[3 * k + 2] = acc[2 * cap + s];
+}
+
+// ------------------------------------------------------------------------------------------------ fused step seam
+// Between the pair force of step i and the cell build of step i+1 the reference runs, per particle, Blob::doChainForce
+// (system.h:1782-1866), Verlet::second (verlet.h:463-477) and -- next iteration -- Verlet::first (verlet.h:288-356).
+// For systems whose only molecules are CHAIN blocks (C1, C2, C5) k_chain_kick does all of it in ONE pass with one
+// thread per particle: the particle gathers its own chain terms (the one to three triplets it belongs to, evaluated
+// and accumulated in the reference's order, so the sum a_chain is bit-identical to the per-chain kernel's), adds them
+// to the pair + Langevin acceleration, applies the two half kicks one after the other (two roundings, as two kernels
+// would), drifts, wraps and tags the new cell.  New positions go to the other position buffer: neighbours still read
+// the old ones for their chain terms.  Three latency-bound passes (43 us on C2) become one.
+// LAST = true ends a batch of steps instead: chain terms + Verlet::second only, a[] is stored for whoever comes next.
+constexpr int MAX_FUSED_CHAINS = 4;
+struct ChainSet { int n; ChainBlock b[MAX_FUSED_CHAINS]; };
+
+// the chain terms of the particle with global index gi (role by role, system.h:1798-1863)
+__device__ __forceinline__ bool chain_gather(int gi, const Particle &me, int N, const Particle *__restrict__ pos, const int *__restrict__ gid,
+                                             const int *__restrict__ slot_of, const Geom &g, const ChainSet &cs, V3 &A)
+{
+	A.x = A.y = A.z = 0;
+	for (int b = 0; b < cs.n; b++) {
+		const ChainBlock &cb = cs.b[b];
+		int rel = gi - cb.start;
+		if (rel < 0 || rel >= cb.nChains * cb.len) continue;
+		int k = rel / cb.len, l = rel - k * cb.len, base = cb.start + k * cb.len;
+		// members l-2 .. l+2 that exist
+		Particle q[5];
+		bool have[5];
+#pragma unroll
+		for (int d = 0; d < 5; d++) {
+			int m = l + d - 2;
+			have[d] = false;
+			if (d == 2) { q[d] = me; have[d] = true; continue; }
+			if (m < 0 || m >= cb.len) continue;
+			// which triplets need member m: only those that contain l
+			int t;
+			if (g.slab) {
+				bool ow;
+				t = slab_find(slot_of, gid, N, base + m, ow);
+			} else {
+				t = slot_of[base + m];
+			}
+			if (t >= 0) { q[d] = load_particle(pos + t); have[d] = true; }
+		}
+		bool ok = true;
+#pragma unroll
+		for (int r = 2; r >= 0; r--) {          // role 2 (triplet l-2), then role 1 (l-1), then role 0 (l): the reference's order
+			int t = l - r;
+			if (t < 0 || t > cb.len - 3) continue;
+			bool tail = (t == cb.len - 3);
+			const int o = 2 - r;                // q index of the triplet's first member
+			if (!(have[o] && have[o + 1] && have[o + 2])) { ok = false; continue; }
+			V3 da = diff_mi(q[o], q[o + 1], g), db = diff_mi(q[o + 1], q[o + 2], g);
+			V3 fa, fb;
+			bend_f(da, db, cb.c[2], cb.c[3], fa, fb);
+			if (r == 2) {
+				if (tail) { V3 f2 = harmonic_f(db, cb.c[0], cb.c[1]); A.x -= f2.x; A.y -= f2.y; A.z -= f2.z; }
+				A.x -= fb.x; A.y -= fb.y; A.z -= fb.z;
+			} else if (r == 1) {
+				V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
+				A.x -= f.x; A.y -= f.y; A.z -= f.z;
+				if (tail) { V3 f2 = harmonic_f(db, cb.c[0], cb.c[1]); A.x += f2.x; A.y += f2.y; A.z += f2.z; }
+				A.x += (fb.x - fa.x); A.y += (fb.y - fa.y); A.z += (fb.z - fa.z);
+			} else {
+				V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
+				A.x += f.x; A.y += f.y; A.z += f.z;
+				A.x += fa.x; A.y += fa.y; A.z += fa.z;
+			}
+		}
+		return ok;
+	}
+	return true;
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(TPB) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
+                                                    double *vel, double *acc, double *unw, const int *__restrict__ gid,
+                                                    const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag)
+{
+	const int N = cnt.get();
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	bool valid = s < N;
+	Particle p;
+	int gi = 0;
+	if (valid) { p = load_particle(pos_in + s); gi = gid[s]; }
+	bool live = valid && !(g.slab && (gi & GID_GHOST));
+	if (live) {
+		V3 A;
+		if (!chain_gather(gi & GID_MASK, p, N, pos_in, gid, slot_of, g, cs, A)) atomicOr(errflag, ERR_SLAB_MISSING);
+		double ax = acc[s] + A.x, ay = acc[cap + s] + A.y, az = acc[2 * cap + s] + A.z;   // Blob::doChainForce: a += chain terms
+		if (LAST) { acc[s] = ax; acc[cap + s] = ay; acc[2 * cap + s] = az; }
+		if (p.type != 0) {
+			double h = 0.5 * dt;
+			double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
+			vx += (ax * h); vy += (ay * h); vz += (az * h);                                 // Verlet::second of this step
+			if (!LAST) {
+				vx += (ax * h); vy += (ay * h); vz += (az * h);                             // Verlet::first of the next one
+				p.x += vx * dt; p.y += vy * dt; p.z += vz * dt;
+				if (unw) { unw[s] += vx * dt; unw[cap + s] += vy * dt; unw[2 * cap + s] += vz * dt; }
+			}
+			vel[s] = vx; vel[cap + s] = vy; vel[2 * cap + s] = vz;
+		}
+		if (!LAST) {
+			if (p.x > g.box[0]) p.x -= g.box[0];
+			if (p.x < 0) p.x += g.box[0];
+			if (p.y > g.box[1]) p.y -= g.box[1];
+			if (p.y < 0) p.y += g.box[1];
+			if (p.z > g.box[2]) p.z -= g.box[2];
+			if (p.z < 0) p.z += g.box[2];
+		}
+	}
+	if (LAST) return;
+	tag_cell(p, g, bbox, errflag, live);
+	if (valid) {
+		if (!live) p.cell = CELL_DEAD;   // slab ghost: replaced by the exchange that follows
+		store_particle(pos_out + s, p);
+	}
 }
 
 // explicit BOND list (system.h:1880-1934, :2717-2747, :3398-3435); one thread per bond, FP64 atomics for the force

@@ -89,7 +89,15 @@ class LocalSlabGroup(_SlabBase):
     def compute_forces(self, mask=capi.MASK_ALL, step=0):
         self._each(lambda c: c.compute_forces(mask, step))
 
-    def step(self, first_step, nsteps=1):
+    def step(self, first_step, nsteps=1, batched=False):
+        """batched=False: one step at a time, all sends before all receives.  batched=True: every context enqueues
+        a whole smd_step batch (the production call, with the fused step kernel) one after the other; the wait
+        kernels of the first contexts then spin until the host has enqueued the later contexts' sends, which is fine
+        for the short batches used here (nothing may fill a launch queue while it waits)"""
+        if batched:
+            for k in range(0, nsteps, 4):
+                self._each(lambda c: c.step(first_step + k, min(4, nsteps - k)))
+            return
         for k in range(nsteps):
             self._each(lambda c: c.step_begin(first_step + k))
             self._each(lambda c: c.step_end(first_step + k))

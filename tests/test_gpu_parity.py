@@ -236,3 +236,59 @@ def test_errors_are_loud(orc):
     with pytest.raises(sm.SoftMoldError, match="outside the box"):
         ctx.synchronize()
     ctx.close()
+
+
+def test_two_phase_energy_kernels_match_one_phase(orc):
+    """potential / dPotential through the two-phase kernel (every unordered pair once, FP32 prefilter widened by the
+    scaling) against the one-phase half-stencil kernels, on a membrane that spans the periodic box, for box moves far
+    larger than the 0.01 steps of MD.cpp"""
+    import os
+    from softmold_b200 import workloads
+    m = workloads.bilayer(4000, 3.11, seed=3)
+    ctx = sm.Context.from_dict(m)
+    ctx.compute_forces()
+    ctx.step(0, 50)
+    m = dict(m)
+    m["xyz"], m["type"], m["vel"] = ctx.get_particles()
+    scales = [[1.0005, 1.0005, 1.0 / 1.0005 ** 2], [0.99, 0.99, 1.0 / 0.99 ** 2], [1.03, 1.03, 1.0 / 1.03 ** 2], [1.0, 1.0, 1.0]]
+    two = [ctx.potential()] + [ctx.dpotential(sc) for sc in scales]
+    ctx.close()
+    os.environ["SMD_ENERGY_ONEPHASE"] = "1"
+    try:
+        ctx = sm.Context.from_dict(m)
+        one = [ctx.potential()] + [ctx.dpotential(sc) for sc in scales]
+        ctx.close()
+    finally:
+        del os.environ["SMD_ENERGY_ONEPHASE"]
+    U = abs(one[0][sm.TERM_PAIR])
+    for a, b in zip(two, one):
+        assert abs(a[sm.TERM_PAIR] - b[sm.TERM_PAIR]) <= 1e-12 * U, (a[sm.TERM_PAIR], b[sm.TERM_PAIR])
+    assert two[-1][sm.TERM_PAIR] == 0.0
+
+
+@pytest.mark.parametrize("case", ["lipo_eq", "bilayer_eq", "lipocyto_chains"])
+def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
+    """smd_step fuses chain forces + Verlet::second + the next Verlet::first into one per-particle kernel for
+    CHAIN-only systems; the trajectory must not change by a single bit against the separate kernels"""
+    import os
+    if case == "lipocyto_chains":      # two CHAIN molecules of different length (3 and 10), explicit BOND list dropped
+        m, _ = orc.load_golden(golden_path("lipocyto_eq"))
+        m = dict(m, molecules=[mol for mol in m["molecules"] if mol["type"] == sm.MOL_CHAIN])
+    else:
+        m, _ = orc.load_golden(golden_path(case))
+    out = []
+    for env in ("0", "1"):
+        os.environ["SMD_NO_FUSE"] = env
+        try:
+            ctx = sm.Context.from_dict(m, track_unwrapped=True)
+        finally:
+            del os.environ["SMD_NO_FUSE"]
+        ctx.compute_forces(step=5)
+        ctx.step(5, 33)
+        ctx.step(38, 1)
+        ctx.step(39, 7)
+        out.append(ctx.get_particles() + (ctx.get_forces(), ctx.get_unwrapped(), ctx.stats()[0]))
+        ctx.close()
+    (x0, _, v0, a0, u0, l0), (x1, _, v1, a1, u1, l1) = out
+    assert np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(a0, a1) and np.array_equal(u0, u1)
+    assert l0 < l1          # fewer launches: the fused path did run

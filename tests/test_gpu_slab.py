@@ -125,7 +125,8 @@ def test_slab_vesicle_across_the_seam_and_empty_ranks(orc, nranks):
     one.close()
     grp = LocalSlabGroup(m, nranks, capacity=4096, msg_capacity=4096)
     grp.compute_forces(step=3)
-    grp.step(3, 25)
+    grp.step(3, 13)
+    grp.step(16, 12, batched=True)      # smd_step batches: the fused step kernel + exchange inside one call
     x2, _, v2, _, owner = grp.gather(n)
     counts = [c.slab_counts() for c in grp.ctx]
     grp.close()
