@@ -1433,3 +1433,14 @@ extern "C" int smd_slab_counts(smd_ctx *ctx, int32_t *n_local, int32_t *n_owned)
 	}
 	return check_device_errors(ctx);
 }
+
+#ifdef SMD_EXP_TIMING
+// experiment builds only (not part of the ABI)
+extern "C" int smd_exp_pair_timing(unsigned long long out[4], int reset)
+{
+	cudaDeviceSynchronize();
+	cudaMemcpyFromSymbol(out, g_pair_timing, 4 * sizeof(unsigned long long));
+	if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_pair_timing, z, sizeof z); }
+	return 0;
+}
+#endif

@@ -761,7 +761,13 @@ constexpr int PTAB_STRIDE = 10;
 // cell layers only) go straight to the general routine from a separate, plain loop.
 constexpr int PAIR_NSEG = 9;
 
+#ifdef SMD_EXP_TIMING
+__device__ unsigned long long g_pair_timing[4];   // experiment builds only: clock sums of setup / phase 1 / phase 2 (per warp), warps
+#endif
 struct PairSmem {
+#ifdef SMD_EXP_TIMING
+	long long t_sync;
+#endif
 	int perm[PAIR_TPB];                 // particle (slot) taken by each thread in phase 1
 	int cnt[PAIR_TPB];                  // list length per phase-1 thread
 	int order[PAIR_TPB];                // phase-2 thread -> phase-1 thread whose list it drains
@@ -794,6 +800,9 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
 		return;
 	}
+#ifdef SMD_EXP_TIMING
+	long long t_exp = clock64();
+#endif
 	extern __shared__ __align__(16) unsigned char s_raw[];
 	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
@@ -962,9 +971,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		asm volatile("st.shared.u16 [%0], %1;" ::"r"(wp), "h"((unsigned short)v) : "memory");
 		wp += 64u;
 	};
-	auto drain_if_full = [&]() {
-		if (wp > lbase + 64u * (PAIR_CAP - 4)) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }
-	};
+	unsigned wlim = lbase + 64u * (PAIR_CAP - 8);    // checked once per two groups of four
+	asm volatile("" : "+r"(wlim));               // opaque: rematerialising the shared-window address cost 8 instructions per group
 
 	// ---- the particle's candidate ranges: one per (y,z) row of the stencil, pruned by geometry
 	// conservative FP32 distances to the faces of the own cell: a neighbour cell at offset -1 / +1 along an axis holds
@@ -996,6 +1004,9 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (EMODE != 0 && (oz < 0 || (oz == 0 && oy < 0))) row_ok = false;   // backward rows: the other particle counts the pair
 		row_ok = row_ok && !wrapyz && lz >= 0 && lz < d2 && ly >= 0 && ly < d1;
 		bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
+#ifdef SMD_EXP_NO_XPRUNE
+		keep_lo = keep_hi = true;
+#endif
 		// cells cx-1 .. cx+1 that need no wrap, clamped to the window (cells outside it are empty)
 		int xlo, xhi;
 		if (g.slab) {   // the window holds every neighbour column of an owned particle, possibly across the periodic seam
@@ -1028,33 +1039,45 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		nseg = (je > jb) ? r + 1 : nseg;
 	}
 
+#ifdef SMD_EXP_TIMING
+	if (EMODE == 0 && tid == 0) { long long t = clock64(); atomicAdd(&g_pair_timing[0], (unsigned long long)(t - t_exp)); t_exp = t; }
+#endif
 	// ---- phase 1: FP32 prefilter along the thread's own stream of ranges; four candidates per step, the next four
 	// already in flight
 	for (int sg = 0; sg < nseg; sg++) {
-		const int jb = sm.seg_b[sg][tid];
 		const int n = sm.seg_n[sg][tid];
+		if (n == 0) continue;
+		const float4 *cp = pos32 + sm.seg_b[sg][tid];
 		const unsigned tag = (unsigned)sg << PAIR_SEGBITS;
-		float4 nx[4];
+		float4 ga[4], gb[4];                         // ping-pong buffers: one group under test, the next in flight
 #pragma unroll
-		for (int k = 0; k < 4; k++) nx[k] = pos32[jb + k];   // pos32 is padded: the overhang is masked below
-		for (int q = 0; q < n; q += 4) {
-			float4 c[4];
-#pragma unroll
-			for (int k = 0; k < 4; k++) c[k] = nx[k];
-			if (q + 4 < n) {
-#pragma unroll
-				for (int k = 0; k < 4; k++) nx[k] = pos32[jb + q + 4 + k];
-			}
+		for (int k = 0; k < 4; k++) ga[k] = cp[k];   // pos32 is padded: the overhang is masked below
+		int q = 0;
+		// tests the group c[] at offset q and meanwhile loads the following one into nx[]; false after the last group
+		auto group = [&](const float4 (&c)[4], float4 (&nx)[4]) {
+			const unsigned e0 = tag | (unsigned)q;
 			const int rem = n - q;
+			q += 4;
+			const bool more = q < n;
+			if (more) {
+#pragma unroll
+				for (int k = 0; k < 4; k++) nx[k] = cp[q + k];
+			}
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
 				float dx = p32.x - c[k].x, dy = p32.y - c[k].y, dz = p32.z - c[k].z;
 				float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
 				const float thr = EMODE != 0 ? fminf(ai, c[k].w) + ext : fminf(ai, c[k].w);
-				if (r2 < thr && k < rem) push(tag | (unsigned)(q + k));
+				if (r2 < thr && k < rem) push(e0 + k);
 			}
-			drain_if_full();
+			return more;
+		};
+		while (true) {
+			if (!group(ga, gb)) break;
+			if (!group(gb, ga)) break;
+			if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }   // list nearly full: never seen in practice
 		}
+		if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }
 	}
 
 	// ---- rows and end cells seen through a periodic image (particles in the outermost cell layers only)
@@ -1128,8 +1151,14 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	}
 	__syncthreads();
 	sm.order[atomicAdd(&sm.hist[lcnt], 1)] = tid;
+#ifdef SMD_EXP_TIMING
+	if (tid == 0) sm.t_sync = clock64();
+#endif
 	__syncthreads();
 
+#ifdef SMD_EXP_TIMING
+	if (EMODE == 0 && tid == 0) { long long t = clock64(); atomicAdd(&g_pair_timing[1], (unsigned long long)(t - t_exp)); t_exp = t; }
+#endif
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];
 	const int io = sm.perm[o];
@@ -1161,6 +1190,13 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	} else {
 		acc[io] += ax; acc[cap + io] += ay; acc[2 * cap + io] += az;
 	}
+#ifdef SMD_EXP_TIMING
+	if (EMODE == 0 && lane == 0) {   // per warp: phase 2 as seen by each warp; [3] counts warps
+		long long t = clock64();
+		atomicAdd(&g_pair_timing[2], (unsigned long long)(t - sm.t_sync));
+		atomicAdd(&g_pair_timing[3], 1ull);
+	}
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ bonded terms
@@ -1607,27 +1643,40 @@ __device__ __forceinline__ bool chain_gather(int gi, const Particle &me, int N, 
 			}
 			if (t >= 0) { q[d] = load_particle(pos + t); have[d] = true; }
 		}
+		// The particle's triplets in ascending order = role 2 (triplet l-2), then role 1, then role 0: the reference's
+		// order.  The loop runs over "my j-th triplet", not over roles, so that the lanes of a warp -- particles at
+		// different positions of their chains -- evaluate their square roots and divisions together; only the few
+		// additions that differ between the roles diverge.
 		bool ok = true;
+		const int tmin = max(l - 2, 0), tmax = min(l, cb.len - 3);
 #pragma unroll
-		for (int r = 2; r >= 0; r--) {          // role 2 (triplet l-2), then role 1 (l-1), then role 0 (l): the reference's order
-			int t = l - r;
-			if (t < 0 || t > cb.len - 3) continue;
-			bool tail = (t == cb.len - 3);
-			const int o = 2 - r;                // q index of the triplet's first member
-			if (!(have[o] && have[o + 1] && have[o + 2])) { ok = false; continue; }
-			V3 da = diff_mi(q[o], q[o + 1], g), db = diff_mi(q[o + 1], q[o + 2], g);
+		for (int j = 0; j < 3; j++) {
+			const int t = tmin + j;
+			if (t > tmax) break;
+			const int r = l - t;                // my position inside the triplet
+			const bool tail = (t == cb.len - 3);
+			const bool r2 = (r == 2), r1 = (r == 1);
+			const bool h0 = r2 ? have[0] : (r1 ? have[1] : have[2]);
+			const bool h1 = r2 ? have[1] : (r1 ? have[2] : have[3]);
+			const bool h2 = r2 ? have[2] : (r1 ? have[3] : have[4]);
+			if (!(h0 && h1 && h2)) { ok = false; continue; }
+			const Particle &P0 = r2 ? q[0] : (r1 ? q[1] : q[2]);
+			const Particle &P1 = r2 ? q[1] : (r1 ? q[2] : q[3]);
+			const Particle &P2 = r2 ? q[2] : (r1 ? q[3] : q[4]);
+			V3 da = diff_mi(P0, P1, g), db = diff_mi(P1, P2, g);
 			V3 fa, fb;
 			bend_f(da, db, cb.c[2], cb.c[3], fa, fb);
-			if (r == 2) {
-				if (tail) { V3 f2 = harmonic_f(db, cb.c[0], cb.c[1]); A.x -= f2.x; A.y -= f2.y; A.z -= f2.z; }
+			V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
+			V3 f2 = {0, 0, 0};
+			if (tail) f2 = harmonic_f(db, cb.c[0], cb.c[1]);
+			if (r2) {
+				if (tail) { A.x -= f2.x; A.y -= f2.y; A.z -= f2.z; }
 				A.x -= fb.x; A.y -= fb.y; A.z -= fb.z;
-			} else if (r == 1) {
-				V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
+			} else if (r1) {
 				A.x -= f.x; A.y -= f.y; A.z -= f.z;
-				if (tail) { V3 f2 = harmonic_f(db, cb.c[0], cb.c[1]); A.x += f2.x; A.y += f2.y; A.z += f2.z; }
+				if (tail) { A.x += f2.x; A.y += f2.y; A.z += f2.z; }
 				A.x += (fb.x - fa.x); A.y += (fb.y - fa.y); A.z += (fb.z - fa.z);
 			} else {
-				V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
 				A.x += f.x; A.y += f.y; A.z += f.z;
 				A.x += fa.x; A.y += fa.y; A.z += fa.z;
 			}

@@ -1,11 +1,11 @@
 #!/bin/bash
 # usage (GPU box, via gpurun): tools/profile_round.sh <tag>
 # 1. launch list of a short bench run (every launch with its device time), 2. one full capture of the top kernel,
-# 3. full captures of the next kernels of the step (one launch each).
+# 3. full captures of the other kernels of the step (one launch each).
 tag=${1:-r01}
 mkdir -p gpurun_out
 ARGS="--steps 2 --warmup 3 --md-steps 8 --equil 32 --no-cpu-baseline --no-e2e"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 500 --csv --log-file gpurun_out/launches_$tag.csv python bench.py $ARGS > gpurun_out/ncu_launches_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_pair_force2ILi0 -s 40 -c 1 -o gpurun_out/pair_$tag python bench.py $ARGS > gpurun_out/ncu_full_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:k_verlet_first|k_chain|k_reorder|k_pair_force2ILi2|k_verlet_second|k_place|k_bin" -s 120 -c 12 -o gpurun_out/others_$tag python bench.py $ARGS > gpurun_out/ncu_others_$tag.log 2>&1
-tail -1 gpurun_out/ncu_full_$tag.log
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_pair_force2<0" -s 40 -c 1 -o gpurun_out/pair_$tag python bench.py $ARGS > gpurun_out/ncu_full_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_chain_kick|k_reorder|k_pair_force2<2|k_place|k_bin|k_scan|k_final_sum" -s 150 -c 10 -o gpurun_out/others_$tag python bench.py $ARGS > gpurun_out/ncu_others_$tag.log 2>&1
+tail -2 gpurun_out/ncu_full_$tag.log gpurun_out/ncu_others_$tag.log
