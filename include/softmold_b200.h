@@ -247,6 +247,11 @@ int smd_slab_connect_ptr(smd_ctx *ctx, int32_t dir, void *peer_buffer);
 /* the two halves of the exchange, for callers that move particles themselves (smd_step_begin / _end call them) */
 int smd_slab_exchange_send(smd_ctx *ctx);
 int smd_slab_exchange_recv(smd_ctx *ctx);
+/* Load THIS rank's own particles only (restart from per-rank data): n particles with their global indices; nothing
+ * else is kept.  Collective in effect: every rank calls it, then smd_compute_forces -- the ghost columns arrive from
+ * the neighbours through the ordinary exchange (sent here, received by the force evaluation), and a particle that
+ * sits up to SMD_SLAB_HALO columns outside this rank's range migrates to its owner on the way. */
+int smd_slab_set_local(smd_ctx *ctx, int32_t n, const int32_t *gid, const double *xyz, const int32_t *type, const double *vel);
 /* live counts of this rank (synchronises) */
 int smd_slab_counts(smd_ctx *ctx, int32_t *n_local, int32_t *n_owned);
 /* owned particles of this rank, arbitrary order: global index, position, type, velocity, acceleration.  The arrays

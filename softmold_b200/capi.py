@@ -33,7 +33,7 @@ SYMBOLS = [
     "smd_mpd_particles", "smd_mpd_pair_tables", "smd_mpd_n_molecules", "smd_mpd_molecule", "smd_create_from_mpd",
     "smd_slab_columns", "smd_slab_select", "smd_slab_recv_buffer", "smd_slab_ipc_handle", "smd_slab_connect_ipc",
     "smd_slab_connect_ptr", "smd_slab_exchange_send", "smd_slab_exchange_recv", "smd_slab_counts", "smd_slab_capacity",
-    "smd_slab_get_local", "smd_mc_propose", "smd_mc_accept",
+    "smd_slab_get_local", "smd_slab_set_local", "smd_mc_propose", "smd_mc_accept",
 ]
 
 
@@ -126,6 +126,7 @@ def lib():
         L.smd_slab_counts.argtypes = [vp, ip, ip]
         L.smd_slab_capacity.argtypes = [vp, ip]
         L.smd_slab_get_local.argtypes = [vp, ip, vp, vp, vp, vp, vp]
+        L.smd_slab_set_local.argtypes = [vp, i32, vp, vp, vp, vp]
         L.smd_mc_propose.argtypes = [vp, dbl, dbl, vp, vp]
         L.smd_mc_accept.argtypes = [dbl, dbl, vp, vp, dbl, dbl, ip, dp]
         _lib = L
@@ -238,6 +239,12 @@ class Context:
         a = C.c_int32()
         self._ck(self.L.smd_slab_capacity(self.h, C.byref(a)))
         return a.value
+
+    def slab_set_local(self, gid, xyz, typ, vel=None):
+        """load this rank's own particles only; every rank calls it, then compute_forces (ghosts arrive by exchange)"""
+        gid, xyz, typ = _i32(gid), _f64(xyz), _i32(typ)
+        vel = None if vel is None else _f64(vel)
+        self._ck(self.L.smd_slab_set_local(self.h, len(gid), _ptr(gid), _ptr(xyz), _ptr(typ), _ptr(vel)))
 
     def slab_get_local(self):
         """owned particles of this rank: (gid, xyz, type, vel, acc), arbitrary order"""

@@ -1379,6 +1379,48 @@ extern "C" int smd_slab_exchange_recv(smd_ctx *ctx)
 	return SMD_OK;
 }
 
+extern "C" int smd_slab_set_local(smd_ctx *ctx, int32_t n, const int32_t *gid, const double *xyz, const int32_t *type, const double *vel)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->slab, "not a slab context");
+	REQUIRE(n >= 0 && (n == 0 || (gid && xyz && type)), "null arrays");
+	REQUIRE(n <= ctx->cap, "slab: local particle capacity exceeded at load (desc.reserved[0])");
+	REQUIRE(ctx->peer_set[0] && ctx->peer_set[1], "slab: connect both neighbours first (smd_slab_connect_*)");
+	REQUIRE(!ctx->exch_pending, "slab: previous exchange not received yet");
+	CK(cudaSetDevice(ctx->device));
+	for (int i = 0; i < n; i++) {
+		if (gid[i] < 0 || gid[i] >= ctx->n_global) { ctx->err = "global particle index out of range"; return SMD_ERR_ARG; }
+		if (type[i] < 0 || type[i] >= ctx->nT) { ctx->err = "particle type out of range"; return SMD_ERR_ARG; }
+		for (int d = 0; d < 3; d++) {
+			double x = xyz[3 * (size_t)i + d];
+			if (!(x >= 0 && x <= ctx->geom.box[d])) { ctx->err = "position of a particle is out of bounds."; return SMD_ERR_CELL; }   // system.h:452-469
+		}
+	}
+	double *sx = ctx->stage, *sv = ctx->stage + 3 * (size_t)ctx->cap;
+	int *dg = ctx->istage + ctx->cap;
+	CK(cudaMemcpyAsync(sx, xyz, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->istage, type, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(dg, gid, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+	if (vel) CK(cudaMemcpyAsync(sv, vel, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemsetAsync(ctx->slot_of, 0xff, (size_t)ctx->n_global * sizeof(int), ctx->stream));
+	int nn[2] = {n, n};
+	CK(cudaMemcpyAsync(ctx->dN, nn, sizeof nn, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->cur = 0;
+	ctx->pcur = 0;
+	ctx->ext_valid = false;
+	if (n > 0)
+		LAUNCH(k_import_particles, nblk(n, TPB), TPB, 0, n, ctx->cap, sx, ctx->istage, vel ? sv : nullptr, ctx->pos[0], ctx->vel[0], ctx->unw[0],
+		       ctx->gid[0], ctx->slot_of, dg);
+	CK(cudaMemsetAsync(ctx->acc, 0, 3 * (size_t)ctx->cap * sizeof(double), ctx->stream));
+	ctx->acc_live = false;
+	retag_cells(ctx);
+	CK(cudaStreamSynchronize(ctx->stream));   // host buffers may be reused by the caller
+	ctx->particles_set = true;
+	// ghosts come from the neighbours (and strays go to them) through the ordinary exchange; received by the next
+	// force evaluation
+	return smd_slab_exchange_send(ctx);
+}
+
 extern "C" int smd_slab_capacity(smd_ctx *ctx, int32_t *capacity)
 {
 	if (!ctx || !capacity) return SMD_ERR_ARG;
