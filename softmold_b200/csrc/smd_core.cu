@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "smd_kernels.cuh"
+#include "smd_pair_split.cuh"
 
 using namespace smd;
 
@@ -226,6 +227,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->launches = ctx->rebuilds = 0;
 	{ const char *e = getenv("SMD_ENERGY_ONEPHASE"); ctx->force_onephase_energy = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
+	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
 	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
 	int rc = check_geom(ctx);
@@ -255,6 +257,12 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->acut, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->utab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
+	if (ctx->pair_split) {   // global candidate lists of the two-kernel pair engine (smd_pair_split.cuh)
+		CKC(cudaMalloc(&ctx->nl_ent, ((size_t)cap * NL_CAP + 64) * sizeof(unsigned short)));
+		CKC(cudaMalloc(&ctx->nl_rng, (size_t)PAIR_NSEG * cap * sizeof(int)));
+		CKC(cudaMalloc(&ctx->nl_cnt, cap * sizeof(int)));
+		CKC(cudaMalloc(&ctx->nl_part, 3 * cap * sizeof(double)));
+	}
 	CKC(cudaMalloc(&ctx->win, WIN_WORDS * sizeof(int)));
 	CKC(cudaMemset(ctx->win, 0, WIN_WORDS * sizeof(int)));
 	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
@@ -336,6 +344,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]);
 	}
 	cudaFree(ctx->pos32); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
+	cudaFree(ctx->nl_ent); cudaFree(ctx->nl_rng); cudaFree(ctx->nl_cnt); cudaFree(ctx->nl_part);
 	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
 	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
 	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
@@ -776,6 +785,39 @@ static int pair_force_smem(smd_ctx *ctx)
 	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
 }
 
+static NeighLists neigh_lists(smd_ctx *ctx)
+{
+	NeighLists nl;
+	nl.ent = ctx->nl_ent; nl.rng = ctx->nl_rng; nl.cnt = ctx->nl_cnt; nl.part = ctx->nl_part;
+	return nl;
+}
+
+// the pair force of all particles into acc[] (LANGEVIN: a = thermostat term + pair sum, else a += pair sum)
+template <bool LANGEVIN>
+static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
+{
+	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
+	if (ctx->pair_split) {
+		const int dsm = PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double);
+		LAUNCH(k_pair_lists<0>, nb, PAIR_TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
+		       ctx->fC, ctx->pgeo, ctx->gid[ctx->cur], EnergyArgs{}, neigh_lists(ctx));
+		if (ctx->tables_symmetric)
+			LAUNCH((k_pair_drain<0, LANGEVIN, true>), nb, PAIR_TPB, dsm, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->geom, ctx->nT, ctx->fC,
+			       ctx->ptab, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, neigh_lists(ctx));
+		else
+			LAUNCH((k_pair_drain<0, LANGEVIN, false>), nb, PAIR_TPB, dsm, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->geom, ctx->nT, ctx->fC,
+			       ctx->ptab, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, neigh_lists(ctx));
+		return SMD_OK;
+	}
+	if (ctx->tables_symmetric)
+		LAUNCH((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+	else
+		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+	return SMD_OK;
+}
+
 static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first)
 {
 	int N = ctx->N;
@@ -801,12 +843,7 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		lg.seed = ctx->desc.seed; lg.step = (uint64_t)step;
 		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
 		ProfScope ps(ctx, SMD_PHASE_PAIR);
-		if (ctx->tables_symmetric)
-			LAUNCH((k_pair_force2<0, true, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
-		else
-			LAUNCH((k_pair_force2<0, true, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+		if ((rc = launch_pair_force<true>(ctx, lg))) return rc;
 		ctx->acc_live = true;
 	} else {
 		LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->acc);
@@ -817,12 +854,7 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		}
 		if (pair) {
 			ProfScope ps(ctx, SMD_PHASE_PAIR);
-			if (ctx->tables_symmetric)
-				LAUNCH((k_pair_force2<0, false, true>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
-			else
-				LAUNCH((k_pair_force2<0, false, false>), nblk(N, PAIR_TPB), PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-				       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+			if ((rc = launch_pair_force<false>(ctx, lg))) return rc;
 		}
 		if (!langevin_first && lang) {
 			ProfScope ps(ctx, SMD_PHASE_LANGEVIN);
@@ -974,8 +1006,15 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 		double grow = 0;   // the most a component-wise scaling moves r^2 across a cutoff, relative
 		for (double sc : {sx, sy, sz}) grow = std::max(grow, std::max(fabs(sc * sc - 1.0), fabs(1.0 / (sc * sc) - 1.0)));
 		en.extra32 = MODE == 1 ? 0.0f : nextafterf((float)(1.01 * grow * ctx->geom.rc2 + 1e-7), INFINITY);
-		LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
-		       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en);
+		if (ctx->pair_split) {
+			LAUNCH(k_pair_lists<MODE>, nb, PAIR_TPB, 0, cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->uC,
+			       ctx->pgeo, ctx->gid[ctx->cur], en, neigh_lists(ctx));
+			LAUNCH((k_pair_drain<MODE, false, true>), nb, PAIR_TPB, PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double), cnt_of(ctx), ctx->cap, pos,
+			       ctx->geom, ctx->nT, ctx->uC, ctx->utab, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, neigh_lists(ctx));
+		} else {
+			LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
+			       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en);
+		}
 		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
 	} else {
 		int nb = nblk(N, TPB);

@@ -119,6 +119,10 @@ struct smd_ctx {
 	int *gid[2];      // original index of slot
 	int cur;          // current buffer of vel / unw / gid
 	int pcur;         // current buffer of pos (flips on its own when the fused step kernel writes the drifted positions)
+	bool pair_split = false; // SMD_PAIR_SPLIT=1: lists + drain kernels (smd_pair_split.cuh) instead of the one-kernel pair engine
+	unsigned short *nl_ent = nullptr;   // two-kernel pair engine: global candidate lists (smd_pair_split.cuh)
+	int *nl_rng = nullptr, *nl_cnt = nullptr;
+	double *nl_part = nullptr;
 	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)
 	double *acc;      // SoA [3][cap]
 	double *acc2;     // alternate buffer for builds that must carry live accelerations along

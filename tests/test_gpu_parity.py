@@ -292,3 +292,28 @@ def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
     (x0, _, v0, a0, u0, l0), (x1, _, v1, a1, u1, l1) = out
     assert np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(a0, a1) and np.array_equal(u0, u1)
     assert l0 < l1          # fewer launches: the fused path did run
+
+
+def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
+    """SMD_PAIR_SPLIT=1 (k_pair_lists + k_pair_drain, global candidate lists) against k_pair_force2: forces, energies and
+    a short trajectory, bit for bit"""
+    import os
+    from softmold_b200 import workloads
+    m = workloads.bilayer(4000, 3.11, seed=5)
+    out = []
+    for env in ("0", "1"):
+        os.environ["SMD_PAIR_SPLIT"] = env
+        try:
+            ctx = sm.Context.from_dict(m)
+        finally:
+            del os.environ["SMD_PAIR_SPLIT"]
+        ctx.compute_forces(step=2)
+        ctx.step(2, 40)
+        a = ctx.get_forces()
+        U = ctx.potential()
+        dU = ctx.dpotential([1.001, 1.001, 1.0 / 1.001 ** 2])
+        ctx.compute_forces(mask=1 << sm.TERM_PAIR)
+        out.append((ctx.get_particles()[0], a, ctx.get_forces(), U[sm.TERM_PAIR], dU[sm.TERM_PAIR]))
+        ctx.close()
+    for u, w in zip(*out):
+        assert np.array_equal(u, w)
