@@ -1397,7 +1397,7 @@ extern "C" int smd_slab_exchange_send(smd_ctx *ctx)
 	ProfScope ps(ctx, SMD_PHASE_EXCHANGE);
 	ctx->xseq++;
 	LAUNCH(k_slab_pack, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
-	       ctx->gid[ctx->cur], ctx->geom, ctx->comm, ctx->xseq, ctx->errflag);
+	       ctx->gid[ctx->cur], ctx->geom, ctx->comm, ctx->xseq, ctx->errflag, ctx->slot_of);
 	ctx->exch_pending = true;
 	ctx->cells_valid = false;
 	return SMD_OK;

@@ -1464,7 +1464,7 @@ __device__ __forceinline__ void st_entry(SlabMsgEntry *e, const Particle &p, dou
 }
 
 __global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *pos, const double *vel, const double *unw, int *gid, Geom g,
-                                                   SlabComm c, int seq, int *errflag)
+                                                   SlabComm c, int seq, int *errflag, int *slot_of)
 {
 	const int N = cnt.get();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1476,6 +1476,7 @@ __global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *p
 		gi = gid[s];
 		if (gi & GID_GHOST) {
 			pos[s].cell = CELL_DEAD;
+			slot_of[gi & GID_MASK] = -1;   // keeps the index table exact: whoever is still here is re-entered by the build
 		} else {
 			p = load_particle(pos + s);
 			int cx, cy, cz;
@@ -1634,13 +1635,9 @@ __device__ __forceinline__ bool chain_gather(int gi, const Particle &me, int N, 
 			if (d == 2) { q[d] = me; have[d] = true; continue; }
 			if (m < 0 || m >= cb.len) continue;
 			// which triplets need member m: only those that contain l
-			int t;
-			if (g.slab) {
-				bool ow;
-				t = slab_find(slot_of, gid, N, base + m, ow);
-			} else {
-				t = slot_of[base + m];
-			}
+			// slab mode: slot_of[] is exact after every build (the exchange clears the entries of dropped ghosts), so
+			// a non-negative entry is a local particle, owned or ghost
+			const int t = slot_of[base + m];
 			if (t >= 0) { q[d] = load_particle(pos + t); have[d] = true; }
 		}
 		// The particle's triplets in ascending order = role 2 (triplet l-2), then role 1, then role 0: the reference's
