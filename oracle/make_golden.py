@@ -171,5 +171,39 @@ def main():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def stats():
+    """long-run observables of the reference `MD` executable itself: a tensionless flat bilayer with box moves, 20 000
+    steps, two independent runs (seeds 99 / 100, 8 OpenMP threads).  tests/golden/stat_bilayer.npz holds the input
+    configuration and the reference's own kinetic_ / potential_ / size_ time series; the GPU test runs MD_b200 on the
+    same input and compares ensemble means (temperature, potential energy per particle, area per lipid)."""
+    tmp = tempfile.mkdtemp(prefix="golden_stat_")
+    env8 = dict(os.environ, OMP_NUM_THREADS="8")
+    try:
+        subprocess.run([os.path.join(REF, "bilayer"), "sb", "99", "600", "3.11", "0", "0", "0", "0"], cwd=tmp, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        m = orc.read_mpd(os.path.join(tmp, "sb.mpd"))
+        m.update(finalTime=400.0, storeInterval=400.0, measureInterval=1.0)
+        out = {}
+        for tag, seed in (("a", 99), ("b", 100)):
+            d = os.path.join(tmp, tag)
+            os.makedirs(d)
+            mm = dict(m, seed=seed)
+            orc.write_mpd(os.path.join(d, "sb.mpd"), mm)
+            subprocess.run([os.path.join(REF, "MD"), "sb"], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env8)
+            for nm in ("kinetic", "potential", "size"):
+                out[f"{nm}_{tag}"] = np.loadtxt(os.path.join(d, f"{nm}_sb.dat"))
+        mm = dict(m, seed=99)
+        orc.write_mpd(os.path.join(tmp, "in.mpd"), mm)
+        out["mpd_text"] = np.frombuffer(open(os.path.join(tmp, "in.mpd"), "rb").read(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(OUT, "stat_bilayer.npz"), **out)
+        n = m["nParticles"]
+        for tag in "ab":
+            k, u, sz = out[f"kinetic_{tag}"], out[f"potential_{tag}"], out[f"size_{tag}"]
+            h = len(k) // 2
+            print(tag, "T", (2 * k[h:, 1] / (3 * n)).mean(), "U/N", (u[h:, 1] / n).mean(), "A", (sz[h:, 1] * sz[h:, 2]).mean())
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
-    main()
+    stats() if len(sys.argv) > 1 and sys.argv[1] == "stats" else main()

@@ -114,3 +114,37 @@ def test_bilayer_with_tension_box_moves_and_restart(tmp_path, orc):
     pot = table(d2 / "potential_bl.dat")
     assert [round(x[0], 6) for x in pot] == [2.0]                          # no t0 sample on restart, one measure at 2.0
     assert not (d2 / "frames_bl.xyz").exists() or open(d2 / "frames_bl.xyz").read().count("test\n") == 0
+
+
+def test_long_run_observables_agree_with_the_reference_statistically(tmp_path):
+    """north star: "long-run observables (area per lipid, membrane tension, temperature) agree statistically".
+    tests/golden/stat_bilayer.npz (oracle/make_golden.py stats) holds the reference `MD` executable's own kinetic_ /
+    potential_ / size_ series of two independent 20 000-step runs of a tensionless bilayer with box moves; MD_b200
+    runs the same input (its own Philox noise).  Means over the second half must agree within the scatter the two
+    reference runs show between themselves (plus the standard error of a 200-sample mean)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "stat_bilayer.npz"))
+    d = tmp_path / "stat"
+    d.mkdir()
+    (d / "sb.mpd").write_bytes(g["mpd_text"].tobytes())
+    r = subprocess.run([MD_B200, "sb"], cwd=d, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n = 1734
+
+    def means(k, u, sz):
+        h = len(k) // 2
+        T, U, A = 2 * k[h:, 1] / (3 * n), u[h:, 1] / n, sz[h:, 1] * sz[h:, 2]
+        blocks = lambda x: x[: len(x) // 10 * 10].reshape(10, -1).mean(axis=1)     # 10 block averages -> standard error
+        return [(x.mean(), blocks(x).std(ddof=1) / np.sqrt(10)) for x in (T, U, A)]
+
+    ours = means(np.loadtxt(d / "kinetic_sb.dat"), np.loadtxt(d / "potential_sb.dat"), np.loadtxt(d / "size_sb.dat"))
+    ra = means(g["kinetic_a"], g["potential_a"], g["size_a"])
+    rb = means(g["kinetic_b"], g["potential_b"], g["size_b"])
+    assert len(np.loadtxt(d / "kinetic_sb.dat")) == len(g["kinetic_a"]) == 401
+    for name, (mo, so), (ma, sa), (mb, sb) in zip(("temperature", "potential per particle", "box area"), ours, ra, rb):
+        ref = 0.5 * (ma + mb)
+        tol = 3.0 * abs(ma - mb) + 5.0 * max(so, sa, sb) + 2e-3 * abs(ref)
+        assert abs(mo - ref) <= tol, (name, mo, ma, mb, tol)
+    # the thermostat holds the set temperature in both codes (T = 3; dt = 0.02 gives the same small offset)
+    assert abs(ours[0][0] - 3.0) < 0.06 and abs(ra[0][0] - 3.0) < 0.06
+    ratio = float(r.stderr.split("Resize acceptance ratio:")[1].split()[0])
+    assert 0.2 < ratio < 0.95
