@@ -684,13 +684,12 @@ static int build_cells(smd_ctx *ctx)
 	ctx->ext_valid = false;
 	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag);
 	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
-	LAUNCH(k_scan2, 1, SCAN_BLOCKS, 0, ctx->blockSums, ctx->bbox, ctx->win, ctx->geom, ctx->cellcap, ctx->errflag,
-	       (ctx->rebuilds & 255) == 255 ? 1 : 0);
-	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N, ctx->slab ? ctx->dN : nullptr);
+	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N,
+	       ctx->slab ? ctx->dN : nullptr, ctx->errflag);
 	LAUNCH(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order);
 	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
-	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut);
+	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0);
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
 	ctx->pcur = pnxt;

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(TPB) k_tag_cells(Cnt cnt, Particle *pos, Geom 
 
 // The offset table covers only the occupied window of the reference grid: the exact bounding box of the cells
 // tagged above, plus one empty cell on each side so that stencil look-ups of boundary cells stay inside the table.
-// Every kernel of the build derives it from bbox[] with this one function; k_scan2 publishes it in win[] for the
+// Every kernel of the build derives it from bbox[] with this one function; k_scan3 publishes it in win[] for the
 // kernels that run after the build and re-arms bbox[].
 struct Window { int org[3], dim[3]; int ncells; };
 
@@ -290,7 +290,7 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 		w.dim[d] = hi - lo + 1;
 		n *= w.dim[d];
 	}
-	w.ncells = (n > cellcap) ? 0 : (int)n;   // over capacity: flagged by k_scan2, nothing is binned
+	w.ncells = (n > cellcap) ? 0 : (int)n;   // over capacity: flagged by k_scan3, nothing is binned
 	return w;
 }
 
@@ -348,48 +348,42 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int 
 	}
 }
 
-// single block: exclusive scan of the block sums; thread 0 publishes the window and re-arms the bbox accumulators
+// start the occupied-cell extremes from scratch (after set_particles / a box move that changed the grid)
 __global__ void k_arm_bbox(int *bbox)
 {
 	if (threadIdx.x < 3) { bbox[threadIdx.x] = INT_MAX; bbox[3 + threadIdx.x] = INT_MIN; }
 }
 
-// rearm = 0: the accumulators keep their extremes, so the window never shrinks and the next tagging pass only issues
-// an atomic when a particle leaves the box of cells seen so far (same-address atomics of thousands of warps cost
-// ~25 us per step otherwise).  The host re-arms every few hundred builds to follow a drifting object.
-__global__ void __launch_bounds__(SCAN_BLOCKS) k_scan2(int *blockSums, int *bbox, int *win, Geom g, long long cellcap, int *errflag, int rearm)
-{
-	__shared__ int sh[SCAN_BLOCKS];
-	int v = blockSums[threadIdx.x];
-	sh[threadIdx.x] = v;
-	__syncthreads();
-	for (int o = 1; o < SCAN_BLOCKS; o <<= 1) {
-		int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
-		__syncthreads();
-		sh[threadIdx.x] += t;
-		__syncthreads();
-	}
-	blockSums[threadIdx.x] = sh[threadIdx.x] - v;
-	if (threadIdx.x == 0) {
-		Window w = window_of(bbox, g, cellcap);
-		for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = w.org[d]; win[WIN_DIM + d] = w.dim[d]; }
-		win[WIN_NCELLS] = w.ncells;
-		if (w.ncells == 0) atomicOr(errflag, ERR_WINDOW_CAP);
-		if (rearm)
-			for (int d = 0; d < 3; d++) { bbox[d] = INT_MAX; bbox[3 + d] = INT_MIN; }
-	}
-}
-
+// Second and last phase of the scan.  Every block sums the partial sums of the blocks before it itself (256 values:
+// cheaper than a kernel of its own), block 0 publishes the window for the kernels that follow.
 // nlive: slab mode only -- the number of live local particles after this build (the last block knows the total)
-__global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *win, const int *blockSums, int *start, int *cursor, int N, int *nlive)
+__global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox, Geom g, long long cellcap, int *win, const int *blockSums,
+                                                    int *start, int *cursor, int N, int *nlive, int *errflag)
 {
-	int ncells = win[WIN_NCELLS];
+	const Window wd = window_of(bbox, g, cellcap);
+	const int ncells = wd.ncells;
 	int b0, b1;
 	scan_chunk(ncells, b0, b1);
 	__shared__ int sh[SCAN_TPB / 32];
 	__shared__ int carry_sh;
-	if (threadIdx.x == 0) carry_sh = blockSums[blockIdx.x];
-	__syncthreads();
+	{
+		static_assert(SCAN_BLOCKS <= SCAN_TPB, "one thread per block sum");
+		int v = ((int)threadIdx.x < (int)blockIdx.x && threadIdx.x < SCAN_BLOCKS) ? blockSums[threadIdx.x] : 0;
+		v = __reduce_add_sync(0xffffffffu, v);
+		if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			int t = 0;
+			for (int w = 0; w < SCAN_TPB / 32; w++) t += sh[w];
+			carry_sh = t;
+			if (blockIdx.x == 0) {
+				for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = wd.org[d]; win[WIN_DIM + d] = wd.dim[d]; }
+				win[WIN_NCELLS] = wd.ncells;
+				if (wd.ncells == 0) atomicOr(errflag, ERR_WINDOW_CAP);
+			}
+		}
+		__syncthreads();
+	}
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	for (int base = b0; base < b1; base += SCAN_TPB) {
 		int i = base + threadIdx.x;
@@ -442,9 +436,12 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int *or
                                                  const Particle *pos_in, Particle *pos_out, const double *vel_in, double *vel_out,
                                                  const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
                                                  const int *gid_in, int *gid_out, int *slot_of, float4 *pos32_out,
-                                                 const float *__restrict__ acut)
+                                                 const float *__restrict__ acut, int *bbox, int rearm)
 {
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
+	// rearm: every few hundred builds the occupied-cell extremes start from scratch, to follow a drifting object (nobody
+	// reads them between the scan and the next tagging pass)
+	if (rearm && q < 3) { bbox[q] = INT_MAX; bbox[3 + q] = INT_MIN; }
 	if (q >= cnt.get()) return;
 	int s = order[q];
 	int c = cellOfSlot[s];
@@ -1171,7 +1168,12 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		drain(io, po, o, ob, ob + 64u * (unsigned)sm.cnt[o], ax, ay, az);
 	}
 	if (EMODE != 0) {   // one partial sum per block, reduced deterministically by k_final_sum
-		double tot = block_sum(act ? ax : 0.0);
+		// summed in particle order, not in the (arrival-dependent) order the lists were handed out in: the energy is
+		// reproducible to the last bit
+		__syncthreads();
+		sm.part[0][o] = act ? ax : 0.0;
+		__syncthreads();
+		double tot = block_sum(sm.part[0][tid]);
 		if (tid == 0) en.partials[blockIdx.x] = tot;
 		return;
 	}
@@ -1683,8 +1685,11 @@ __device__ __forceinline__ bool chain_gather(int gi, const Particle &me, int N, 
 	return true;
 }
 
+#ifndef SMD_KICK_BLOCKS
+#define SMD_KICK_BLOCKS 5   // 96 registers with a few spilled words beat 122 registers at 4 blocks (22.9 vs 25.1 us on C2)
+#endif
 template <bool LAST>
-__global__ void __launch_bounds__(TPB) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
+__global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
                                                     double *vel, double *acc, double *unw, const int *__restrict__ gid,
                                                     const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag)
 {

@@ -258,6 +258,7 @@ struct DrainSmem {
 	int order[PAIR_TPB];                // thread -> particle (offset in the block) whose list it drains
 	int seg_b[PAIR_NSEG][PAIR_TPB];     // candidate range starts of each particle
 	int hist[NL_CAP + 2];
+	double usum[PAIR_TPB];              // energy modes: per-particle sums, reduced in particle order
 };
 
 template <int EMODE, bool LANGEVIN, bool SYMM>
@@ -429,7 +430,12 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_DRAIN_BLOCKS) k_pair_drain(Cnt c
 		}
 	}
 	if (EMODE != 0) {   // one partial sum per block, reduced deterministically by k_final_sum
-		double tot = block_sum(act ? ax : 0.0);
+		// summed in particle order, not in the (arrival-dependent) order the lists were handed out in: the energy is
+		// reproducible to the last bit
+		__syncthreads();
+		sm.usum[o] = act ? ax : 0.0;
+		__syncthreads();
+		double tot = block_sum(sm.usum[tid]);
 		if (tid == 0) en.partials[blockIdx.x] = tot;
 		return;
 	}
