@@ -146,6 +146,8 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 }
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
+static int pair_force_smem(smd_ctx *ctx);
+
 static int upload_acut(smd_ctx *ctx)
 {
 	if (ctx->acut_raw.empty()) return SMD_OK;
@@ -230,6 +232,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
 	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
+	ctx->pgeo.rmin32 = (float)desc->cutoff;
 	int rc = check_geom(ctx);
 	if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
 
@@ -255,6 +258,9 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->pos32, (cap + 8) * sizeof(float4)));   // + overhang of the 4-wide candidate loads and their prefetch
 	CKC(cudaMemset(ctx->pos32, 0, (cap + 8) * sizeof(float4)));
 	CKC(cudaMalloc(&ctx->acut, (size_t)ctx->nT * sizeof(float)));
+	CKC(cudaMalloc(&ctx->pos16, (cap + 16) * sizeof(uint2)));   // + overhang, as for pos32
+	CKC(cudaMemset(ctx->pos16, 0, (cap + 16) * sizeof(uint2)));
+	CKC(cudaMalloc(&ctx->arad, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->utab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	if (ctx->pair_split) {   // global candidate lists of the two-kernel pair engine (smd_pair_split.cuh)
@@ -312,8 +318,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMallocHost(&ctx->h_pinned, 64 * sizeof(double)));
 #undef CKC
 	{
-		int smem = (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
-		           (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
+		int smem = pair_force_smem(ctx);
 		cudaError_t e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -343,7 +348,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (int b = 0; b < 2; b++) {
 		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]);
 	}
-	cudaFree(ctx->pos32); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
+	cudaFree(ctx->pos32); cudaFree(ctx->pos16); cudaFree(ctx->arad); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
 	cudaFree(ctx->nl_ent); cudaFree(ctx->nl_rng); cudaFree(ctx->nl_cnt); cudaFree(ctx->nl_part);
 	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
 	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
@@ -420,6 +425,18 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 				}
 				ctx->acut_raw[a] = std::max(ctx->acut_raw[a], c);
 			}
+		{   // class radius per type for the 16-bit phase-1 records: rm for purely repulsive types, rc else, -1: none
+			std::vector<float> rad(nT);
+			float rmin = (float)ctx->desc.cutoff;
+			for (int t = 0; t < nT; t++) {
+				float raw = ctx->acut_raw[t];
+				rad[t] = raw < 0 ? -1.0f : (std::isinf(raw) ? (float)ctx->desc.cutoff : std::min(nextafterf(sqrtf(raw), INFINITY), (float)ctx->desc.cutoff));
+				if (rad[t] > 0) rmin = std::min(rmin, rad[t]);
+			}
+			ctx->pgeo.rmin32 = rmin;
+			CK(cudaMemcpyAsync(ctx->arad, rad.data(), rad.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+			CK(cudaStreamSynchronize(ctx->stream));
+		}
 		// smallest double whose correctly rounded square root is >= v
 		auto sq_threshold = [](double v) {
 			double x = v * v;
@@ -689,7 +706,8 @@ static int build_cells(smd_ctx *ctx)
 	LAUNCH(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order);
 	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
-	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0);
+	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0, ctx->pos16, ctx->arad, ctx->win,
+	       ctx->geom);
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
 	ctx->pcur = pnxt;
@@ -781,7 +799,7 @@ static int ready(smd_ctx *ctx)
 static int pair_force_smem(smd_ctx *ctx)
 {
 	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
-	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
+	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short) + (STAGE_CAP + 8) * (int)sizeof(uint2);
 }
 
 static NeighLists neigh_lists(smd_ctx *ctx)
@@ -810,10 +828,10 @@ static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
 	}
 	if (ctx->tables_symmetric)
 		LAUNCH((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
 	else
 		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
 	return SMD_OK;
 }
 
@@ -1012,7 +1030,7 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 			       ctx->geom, ctx->nT, ctx->uC, ctx->utab, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, neigh_lists(ctx));
 		} else {
 			LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
-			       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en);
+			       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, ctx->pos16);
 		}
 		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
 	} else {
@@ -1516,11 +1534,11 @@ extern "C" int smd_slab_counts(smd_ctx *ctx, int32_t *n_local, int32_t *n_owned)
 
 #ifdef SMD_EXP_TIMING
 // experiment builds only (not part of the ABI)
-extern "C" int smd_exp_pair_timing(unsigned long long out[4], int reset)
+extern "C" int smd_exp_pair_timing(unsigned long long out[8], int reset)
 {
 	cudaDeviceSynchronize();
-	cudaMemcpyFromSymbol(out, g_pair_timing, 4 * sizeof(unsigned long long));
-	if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_pair_timing, z, sizeof z); }
+	cudaMemcpyFromSymbol(out, g_pair_timing, 8 * sizeof(unsigned long long));
+	if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_pair_timing, z, sizeof z); }
 	return 0;
 }
 #endif

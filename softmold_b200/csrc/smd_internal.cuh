@@ -50,8 +50,9 @@ constexpr int GID_MASK = GID_GHOST - 1;
 constexpr unsigned CELL_DEAD = 0xffffffffu;
 
 // device-resident active window of the cell grid: the bounding box of occupied cells plus one cell each side.
-// win[0..2] origin, win[3..5] extent, win[6] number of cells in the window.
-enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_WORDS = 8 };
+// win[0..2] origin, win[3..5] extent, win[6] number of cells in the window, win[8..9] the resolution of the 16-bit
+// window-relative coordinates of pos16[] and its inverse (float bit patterns; see quant_res).
+enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_RES = 8, WIN_INVRES = 9, WIN_WORDS = 12 };
 
 enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW_CAP = 4, ERR_SLAB_MIGRATION = 8, ERR_SLAB_MSG_CAP = 16, ERR_SLAB_CAPACITY = 32,
        ERR_SLAB_TIMEOUT = 64, ERR_SLAB_MISSING = 128 };
@@ -78,6 +79,7 @@ struct PairGeo {            // phase-1 constants of k_pair_force2
 	float margin32;         // that margin
 	float slack32;          // FP32 rounding of a coordinate difference against a cell face
 	float cs32[3];          // cell size
+	float rmin32;           // smallest positive per-type phase-1 radius (pos16 path: widening of the energy modes' cutoffs)
 };
 
 struct ChainBlock { int start, nChains, len; double c[4]; };
@@ -108,6 +110,8 @@ struct smd_ctx {
 	smd::Particle *pos[2];
 	float4 *pos32;    // FP32 mirror {x,y,z,type} of pos[cur], written by the reorder (phase 1 of the pair force kernel)
 	float *acut;      // [nT] FP32 phase-1 class cutoff per type, margin included (see k_pair_force2)
+	uint2 *pos16;     // 8-byte phase-1 candidates {x,y,z: 16-bit window-relative fixed point; cutoff^2 as a bf16} of pos[cur]
+	float *arad;      // [nT] phase-1 class radius per type (rc, rm, or -1: interacts with nothing), no margin
 	double *ptab;     // [nT*nT][PTAB_STRIDE] padded force table + exact branch thresholds
 	double *utab;     // same layout, potential constants (energy modes of the two-phase kernel)
 	bool force_onephase_energy = false;   // SMD_ENERGY_ONEPHASE=1: use the one-phase half-stencil energy kernels (A/B checks)

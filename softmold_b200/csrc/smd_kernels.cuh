@@ -294,6 +294,40 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 	return w;
 }
 
+// pos16[]: the 8-byte phase-1 candidate record of k_pair_force2.  Coordinates are 16-bit fixed point relative to the
+// window's origin with ONE resolution for the three axes (so r^2 needs no per-axis scaling): the longest window edge
+// maps to just under 65535 steps.  A coordinate inside the window is off by at most 0.505 steps (round to nearest +
+// the FP32 rounding of 1/res), a difference of two by 1.01, a difference vector by 1.75 steps (sqrt(3) * 1.01).
+// The fourth half-word is the particle's class cutoff^2 in steps^2, ((R + 1.75 res) / res)^2 rounded UP to a bf16:
+// a pair the exact FP64 test accepts always passes the 16-bit test, the rest are dropped again in phase 2.
+__device__ __forceinline__ float quant_res(const Window &w, const Geom &g)
+{
+	double ext = 0;
+	for (int d = 0; d < 3; d++) ext = fmax(ext, (double)w.dim[d] * g.cs[d]);
+	return __double2float_ru(ext * (1.0 + 1e-6) / 65535.0);
+}
+
+__device__ __forceinline__ uint2 quantize16(const Particle &p, const Geom &g, const int *win, float res, float inv_res, float radius)
+{
+	unsigned q[3];
+	const double c[3] = {p.x, p.y, p.z};
+#pragma unroll
+	for (int d = 0; d < 3; d++) {
+		double rel = (c[d] - (double)win[WIN_ORG + d] * g.cs[d]) * (double)inv_res;
+		// outside the window only for the ghost columns a slab keeps across the periodic seam; those are never looked
+		// at through this record (their pairs go through the periodic-image path, absolute FP32 coordinates)
+		q[d] = (unsigned)min(max(__double2int_rn(rel), 0), 65535);
+	}
+	unsigned thr = 0xFF80u;   // -inf: interacts with nothing
+	if (radius >= 0.f) {
+		float t = __fmaf_rn(radius, inv_res, 1.75f);
+		t = (t * t) * 1.000001f;
+		thr = (__float_as_uint(t) + 0xFFFFu) >> 16;
+	}
+	(void)res;
+	return make_uint2(q[0] | (q[1] << 16), q[2] | (thr << 16));
+}
+
 // pass 1 of the counting sort: histogram over the window.  Warp-aggregated: lanes sharing a cell elect a leader
 // that issues one atomicAdd for the group.
 __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
@@ -379,6 +413,9 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox,
 			if (blockIdx.x == 0) {
 				for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = wd.org[d]; win[WIN_DIM + d] = wd.dim[d]; }
 				win[WIN_NCELLS] = wd.ncells;
+				const float res = quant_res(wd, g);
+				win[WIN_RES] = __float_as_int(res);
+				win[WIN_INVRES] = __float_as_int(1.0f / res);
 				if (wd.ncells == 0) atomicOr(errflag, ERR_WINDOW_CAP);
 			}
 		}
@@ -436,7 +473,8 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int *or
                                                  const Particle *pos_in, Particle *pos_out, const double *vel_in, double *vel_out,
                                                  const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
                                                  const int *gid_in, int *gid_out, int *slot_of, float4 *pos32_out,
-                                                 const float *__restrict__ acut, int *bbox, int rearm)
+                                                 const float *__restrict__ acut, int *bbox, int rearm, uint2 *pos16_out,
+                                                 const float *__restrict__ arad, const int *__restrict__ win, Geom geo)
 {
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	// rearm: every few hundred builds the occupied-cell extremes start from scratch, to follow a drifting object (nobody
@@ -452,7 +490,8 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int *or
 	int t = b + rank;
 	Particle p = load_particle(pos_in + s);
 	store_particle(pos_out + t, p);
-	pos32_out[t] = make_float4((float)p.x, (float)p.y, (float)p.z, acut[p.type]);   // phase-1 mirror of k_pair_force2
+	pos32_out[t] = make_float4((float)p.x, (float)p.y, (float)p.z, acut[p.type]);   // FP32 mirror: periodic-image path of k_pair_force2
+	pos16_out[t] = quantize16(p, geo, win, __int_as_float(win[WIN_RES]), __int_as_float(win[WIN_INVRES]), arad[p.type]);   // its phase-1 candidates
 	vel_out[t] = vel_in[s]; vel_out[cap + t] = vel_in[cap + s]; vel_out[2 * cap + t] = vel_in[2 * cap + s];
 	if (unw_in) { unw_out[t] = unw_in[s]; unw_out[cap + t] = unw_in[cap + s]; unw_out[2 * cap + t] = unw_in[2 * cap + s]; }
 	if (acc_in) { acc_out[t] = acc_in[s]; acc_out[cap + t] = acc_in[cap + s]; acc_out[2 * cap + t] = acc_in[2 * cap + s]; }
@@ -640,12 +679,17 @@ __global__ void __launch_bounds__(TPB) k_pair(Cnt cnt, int cap, const Particle *
 //   a = (-gamma v + sigma (2u-1)) + sum_pairs,   exactly the order MD.cpp:357-413 produces.
 constexpr int PAIR_TPB = 128;
 #ifndef SMD_PAIR_CAP
-#define SMD_PAIR_CAP 128
+#define SMD_PAIR_CAP 104
+#endif
+#ifndef SMD_STAGE_CAP
+#define SMD_STAGE_CAP 1792
 #endif
 #ifndef SMD_PAIR_BLOCKS
 #define SMD_PAIR_BLOCKS 4
 #endif
-constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 128 x 32 x 2 B = 32 KiB per block
+constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 104 x 32 x 2 B = 26 KiB per block
+constexpr int STAGE_CAP = SMD_STAGE_CAP; // staged phase-1 candidates per block, 8 B each (even; + 8 entries of overhang)
+constexpr int STAGE_NONE = INT_MIN;
 constexpr int PAIR_SEGBITS = 12;   // entry = (range index << 12) | offset inside the range
 
 struct LangevinArgs { double gamma, sigma; uint64_t seed, step; const double *vel; const int *gid; const double *ext_noise; };
@@ -759,7 +803,7 @@ constexpr int PTAB_STRIDE = 10;
 constexpr int PAIR_NSEG = 9;
 
 #ifdef SMD_EXP_TIMING
-__device__ unsigned long long g_pair_timing[4];   // experiment builds only: clock sums of setup / phase 1 / phase 2 (per warp), warps
+__device__ unsigned long long g_pair_timing[8];   // experiment builds only: clock sums of setup / phase 1 / phase 2 (per warp), warps
 #endif
 struct PairSmem {
 #ifdef SMD_EXP_TIMING
@@ -773,6 +817,11 @@ struct PairSmem {
 	unsigned short seg_n[PAIR_NSEG][PAIR_TPB];   // ... and length (< 4096)
 	int hist[PAIR_CAP + 2];
 	int wcnt[PAIR_TPB / 32];
+	// staging of the block's phase-1 candidates (see k_pair_force2)
+	int st_gs[PAIR_NSEG], st_ge[PAIR_NSEG];       // slots of the cells that row r of any of the block's particles can reach
+	int st_delta[PAIR_NSEG];                      // shared index - slot of the staged copy, STAGE_NONE: read from global
+	int st_src[PAIR_NSEG], st_dst[PAIR_NSEG], st_len[PAIR_NSEG];   // bulk copies issued by thread 0
+	unsigned long long mbar;                      // their completion barrier
 };
 
 //
@@ -790,7 +839,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
                                                             const int *__restrict__ win, Geom g, int nT,
                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
                                                             PairGeo pg, double *__restrict__ acc, LangevinArgs lg,
-                                                            const int *__restrict__ gid, EnergyArgs en)
+                                                            const int *__restrict__ gid, EnergyArgs en,
+                                                            const uint2 *__restrict__ pos16)
 {
 	const int N = cnt.get();
 	if ((int)(blockIdx.x * PAIR_TPB) >= N) {
@@ -805,9 +855,38 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
 	const int nptab = PTAB_STRIDE * nT * nT;
 	unsigned short *s_lists = reinterpret_cast<unsigned short *>(s_ptab + nptab);
+	uint2 *s_stage = reinterpret_cast<uint2 *>(s_lists + (PAIR_TPB / 32) * PAIR_CAP * 32);
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int k = tid; k < nptab; k += PAIR_TPB) s_ptab[k] = ptab[k];
 	for (int k = tid; k < PAIR_CAP + 2; k += PAIR_TPB) sm.hist[k] = 0;
+	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
+	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
+
+	// ---- staging, step 1: the block's 128 slots are consecutive in the cell-sorted order, so the cells its particles
+	// live in form ONE interval [cf, cl] of the window's linear cell index, and the cells that stencil row r = (oy, oz)
+	// of any of them can reach form the interval [cf + off_r - 1, cl + off_r + 1]: nine slot ranges [gs, ge) hold every
+	// phase-1 candidate of the block (about 1 300 of them, each wanted by ~20 of the block's particles).
+	const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sm.mbar);
+	if (tid == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (tid < PAIR_NSEG) {
+		const int sf = blockIdx.x * PAIR_TPB, sl = min(sf + PAIR_TPB, N) - 1;
+		auto lin_of = [&](int s_) {
+			int ax, ay, az;
+			unpack_cell(pos[s_].cell, ax, ay, az);
+			const int lx = g.slab ? win_x(ax, w0, g.nc[0]) : ax - w0;
+			return lx + d0 * ((ay - w1) + d1 * (az - w2));
+		};
+		const int ncells = d0 * d1 * d2;
+		const int oz = tid / 3 - 1, oy = tid - 3 * (tid / 3) - 1;
+		const int off = d0 * (oy + d1 * oz);
+		const int a = min(max(lin_of(sf) + off - 1, 0), ncells);
+		const int e = max(min(max(lin_of(sl) + off + 2, 0), ncells), a);
+		sm.st_gs[tid] = start[a];
+		sm.st_ge[tid] = start[e];
+	}
 
 	// ---- deal the block's particles to threads by class
 	{
@@ -816,6 +895,35 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
 		if (lane == 0) sm.wcnt[wid] = __popc(bal);
 		__syncthreads();
+		// ---- staging, step 2 (one thread): lay the nine ranges out in the staging buffer -- ranges that overlap or
+		// touch (a block that spans several cell rows) continue the same run, a range that no longer fits stays in
+		// global memory -- and start one bulk copy (TMA, cp.async.bulk) per piece.  The copies land while the threads
+		// work out their own candidate ranges below; everybody waits on the mbarrier just before phase 1.
+		if (tid == 0) {
+			int cursor = 0, run_end = 0, run_delta = 0, np = 0;
+			for (int r = 0; r < PAIR_NSEG; r++) {
+				const int gs = sm.st_gs[r], ge = sm.st_ge[r];
+				int dl = STAGE_NONE;
+				if (ge > gs) {
+					const int pe = (ge + 1) & ~1;   // pieces start and end on even slots: 16-byte granules
+					int b, len, d;
+					if (cursor > 0 && gs <= run_end) { b = run_end; len = max(pe - run_end, 0); d = run_delta; }
+					else { b = gs & ~1; len = pe - b; d = cursor - b; }
+					if (cursor + len <= STAGE_CAP) {
+						if (len > 0) { sm.st_src[np] = b; sm.st_dst[np] = cursor; sm.st_len[np] = len; np++; }
+						cursor += len; run_end = b + len; run_delta = d; dl = d;
+						if (len == 0) run_end = max(run_end, pe);
+					}
+				}
+				sm.st_delta[r] = dl;
+			}
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)cursor * 8u) : "memory");
+			const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_stage);
+			for (int k = 0; k < np; k++)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + 8u * (unsigned)sm.st_dst[k]),
+				             "l"(pos16 + sm.st_src[k]), "r"(8u * (unsigned)sm.st_len[k]), "r"(mbar)
+				             : "memory");
+		}
 		int before = 0, total = 0;
 #pragma unroll
 		for (int k = 0; k < PAIR_TPB / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < wid) before += c; }
@@ -836,8 +944,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		p32 = pos32[i];
 		unpack_cell(pi.cell, cx, cy, cz);
 	}
-	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
-	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
 	const double rc2 = g.rc2;
 	const float ai = p32.w;
 	// entries of thread t's list sit 64 B apart (one 16-bit column per lane)
@@ -1039,19 +1145,54 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 #ifdef SMD_EXP_TIMING
 	if (EMODE == 0 && tid == 0) { long long t = clock64(); atomicAdd(&g_pair_timing[0], (unsigned long long)(t - t_exp)); t_exp = t; }
 #endif
-	// ---- phase 1: FP32 prefilter along the thread's own stream of ranges; four candidates per step, the next four
-	// already in flight
+	// ---- phase 1: prefilter along the thread's own stream of ranges over the 8-byte candidate records (16-bit
+	// window-relative coordinates, see quantize16) -- from the block's staged copy in shared memory where the range was
+	// staged, else from global memory; four candidates per step, the next four already in flight.  The coordinates are
+	// spliced into the mantissa of 2^23 (one PRMT each), so that a float subtraction gives their exact difference.
+	float qx = 0.f, qy = 0.f, qz = 0.f, aiq = -INFINITY, extq = 0.f;
+	if (live) {
+		const uint2 me = pos16[i];
+		qx = __uint_as_float(__byte_perm(me.x, 0x4B000000u, 0x7610));
+		qy = __uint_as_float(__byte_perm(me.x, 0x4B000000u, 0x7632));
+		qz = __uint_as_float(__byte_perm(me.y, 0x4B000000u, 0x7610));
+		aiq = __uint_as_float(me.y & 0xffff0000u);
+	}
+	if (EMODE != 0) {
+		// the widening of the cutoffs in steps^2: (R^2 + ext) / res^2 plus the cross term of the 1.75-step slack
+		const float ir = __int_as_float(win[WIN_INVRES]);
+		extq = (ext * ir) * ir * (1.000001f + 1.75f / (pg.rmin32 * ir));
+	}
+#ifdef SMD_EXP_TIMING
+	long long t_w0 = clock64();
+#endif
+	{   // the staged candidates have landed?
+		unsigned ok;
+		do {
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+			             : "=r"(ok) : "r"(mbar), "r"(0u) : "memory");
+		} while (!ok);
+	}
+#ifdef SMD_EXP_TIMING
+	if (EMODE == 0 && tid == 0) {
+		atomicAdd(&g_pair_timing[4], (unsigned long long)(clock64() - t_w0));
+		int staged = 0;
+		for (int r = 0; r < PAIR_NSEG; r++) staged += sm.st_delta[r] != STAGE_NONE || sm.st_ge[r] <= sm.st_gs[r];
+		atomicAdd(&g_pair_timing[5], (unsigned long long)staged);
+		atomicAdd(&g_pair_timing[6], 1ull);
+	}
+#endif
 	for (int sg = 0; sg < nseg; sg++) {
 		const int n = sm.seg_n[sg][tid];
 		if (n == 0) continue;
-		const float4 *cp = pos32 + sm.seg_b[sg][tid];
+		const int jb = sm.seg_b[sg][tid], dl = sm.st_delta[sg];
+		const uint2 *cp = dl != STAGE_NONE ? s_stage + (jb + dl) : pos16 + jb;
 		const unsigned tag = (unsigned)sg << PAIR_SEGBITS;
-		float4 ga[4], gb[4];                         // ping-pong buffers: one group under test, the next in flight
+		uint2 ga[4], gb[4];                          // ping-pong buffers: one group under test, the next in flight
 #pragma unroll
-		for (int k = 0; k < 4; k++) ga[k] = cp[k];   // pos32 is padded: the overhang is masked below
+		for (int k = 0; k < 4; k++) ga[k] = cp[k];   // both arrays are padded: the overhang is masked below
 		int q = 0;
 		// tests the group c[] at offset q and meanwhile loads the following one into nx[]; false after the last group
-		auto group = [&](const float4 (&c)[4], float4 (&nx)[4]) {
+		auto group = [&](const uint2 (&c)[4], uint2 (&nx)[4]) {
 			const unsigned e0 = tag | (unsigned)q;
 			const int rem = n - q;
 			q += 4;
@@ -1062,9 +1203,12 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			}
 #pragma unroll
 			for (int k = 0; k < 4; k++) {
-				float dx = p32.x - c[k].x, dy = p32.y - c[k].y, dz = p32.z - c[k].z;
+				float dx = qx - __uint_as_float(__byte_perm(c[k].x, 0x4B000000u, 0x7610));
+				float dy = qy - __uint_as_float(__byte_perm(c[k].x, 0x4B000000u, 0x7632));
+				float dz = qz - __uint_as_float(__byte_perm(c[k].y, 0x4B000000u, 0x7610));
 				float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-				const float thr = EMODE != 0 ? fminf(ai, c[k].w) + ext : fminf(ai, c[k].w);
+				const float cw = __uint_as_float(c[k].y & 0xffff0000u);
+				const float thr = EMODE != 0 ? fminf(aiq, cw) + extq : fminf(aiq, cw);
 				if (r2 < thr && k < rem) push(e0 + k);
 			}
 			return more;
