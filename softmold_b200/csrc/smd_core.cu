@@ -799,7 +799,7 @@ static int ready(smd_ctx *ctx)
 static int pair_force_smem(smd_ctx *ctx)
 {
 	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
-	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short) + (STAGE_CAP + 8) * (int)sizeof(uint2);
+	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short) + (STAGE_CAP > 0 ? (STAGE_CAP + 8) * (int)sizeof(uint2) : 0);
 }
 
 static NeighLists neigh_lists(smd_ctx *ctx)

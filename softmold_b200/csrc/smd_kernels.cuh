@@ -678,17 +678,21 @@ __global__ void __launch_bounds__(TPB) k_pair(Cnt cnt, int cap, const Particle *
 // The Langevin term and the zeroing of a[] are folded into the epilogue when LANGEVIN is set:
 //   a = (-gamma v + sigma (2u-1)) + sum_pairs,   exactly the order MD.cpp:357-413 produces.
 constexpr int PAIR_TPB = 128;
-#ifndef SMD_PAIR_CAP
-#define SMD_PAIR_CAP 104
-#endif
+// SMD_STAGE_CAP > 0: the block's phase-1 candidates are first staged in shared memory by TMA bulk copies (build with
+// -DSMD_STAGE_CAP=1792 -DSMD_PAIR_CAP=104 to keep four blocks per SM).  Measured on C2: 179 us against 172 us for
+// plain L1-cached loads of the same 8-byte records -- the lanes of a cell read the same lines, the loads were never
+// the limit, and the staging buffer costs L1 capacity that phase 2 wants -- so it is off by default.
 #ifndef SMD_STAGE_CAP
-#define SMD_STAGE_CAP 1792
+#define SMD_STAGE_CAP 0
+#endif
+#ifndef SMD_PAIR_CAP
+#define SMD_PAIR_CAP 128
 #endif
 #ifndef SMD_PAIR_BLOCKS
 #define SMD_PAIR_BLOCKS 4
 #endif
-constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 104 x 32 x 2 B = 26 KiB per block
-constexpr int STAGE_CAP = SMD_STAGE_CAP; // staged phase-1 candidates per block, 8 B each (even; + 8 entries of overhang)
+constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 128 x 32 x 2 B = 32 KiB per block
+constexpr int STAGE_CAP = SMD_STAGE_CAP; // staged phase-1 candidates per block, 8 B each (even; + 8 entries of overhang); 0: no staging
 constexpr int STAGE_NONE = INT_MIN;
 constexpr int PAIR_SEGBITS = 12;   // entry = (range index << 12) | offset inside the range
 
@@ -855,13 +859,16 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
 	const int nptab = PTAB_STRIDE * nT * nT;
 	unsigned short *s_lists = reinterpret_cast<unsigned short *>(s_ptab + nptab);
+#if SMD_STAGE_CAP > 0
 	uint2 *s_stage = reinterpret_cast<uint2 *>(s_lists + (PAIR_TPB / 32) * PAIR_CAP * 32);
+#endif
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int k = tid; k < nptab; k += PAIR_TPB) s_ptab[k] = ptab[k];
 	for (int k = tid; k < PAIR_CAP + 2; k += PAIR_TPB) sm.hist[k] = 0;
 	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
 	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
 
+#if SMD_STAGE_CAP > 0
 	// ---- staging, step 1: the block's 128 slots are consecutive in the cell-sorted order, so the cells its particles
 	// live in form ONE interval [cf, cl] of the window's linear cell index, and the cells that stencil row r = (oy, oz)
 	// of any of them can reach form the interval [cf + off_r - 1, cl + off_r + 1]: nine slot ranges [gs, ge) hold every
@@ -887,6 +894,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		sm.st_gs[tid] = start[a];
 		sm.st_ge[tid] = start[e];
 	}
+#endif
 
 	// ---- deal the block's particles to threads by class
 	{
@@ -895,6 +903,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
 		if (lane == 0) sm.wcnt[wid] = __popc(bal);
 		__syncthreads();
+#if SMD_STAGE_CAP > 0
 		// ---- staging, step 2 (one thread): lay the nine ranges out in the staging buffer -- ranges that overlap or
 		// touch (a block that spans several cell rows) continue the same run, a range that no longer fits stays in
 		// global memory -- and start one bulk copy (TMA, cp.async.bulk) per piece.  The copies land while the threads
@@ -924,6 +933,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 				             "l"(pos16 + sm.st_src[k]), "r"(8u * (unsigned)sm.st_len[k]), "r"(mbar)
 				             : "memory");
 		}
+#endif
 		int before = 0, total = 0;
 #pragma unroll
 		for (int k = 0; k < PAIR_TPB / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < wid) before += c; }
@@ -1094,9 +1104,11 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const float amax = fminf(ai, pg.thr32) + ext;
 	int nseg = 0;
 	bool shifted_rows = false;
-#pragma unroll 1
-	for (int r = 0; r < 9; r++) {
-		int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
+	int rjb[PAIR_NSEG], rje[PAIR_NSEG];
+	// all eighteen look-ups of start[] are issued before any of them is used (one trip to L2 instead of nine)
+#pragma unroll
+	for (int r = 0; r < PAIR_NSEG; r++) {
+		const int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
 		int nz = cz + oz, ny = cy + oy;
 		bool wrapyz = nz < 0 || nz >= g.nc[2] || ny < 0 || ny >= g.nc[1];
 		int lz = nz - w2, ly = ny - w1;
@@ -1117,12 +1129,17 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		} else {
 			xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
 		}
-		int jb = 0, je = 0;
+		rjb[r] = 0; rje[r] = 0;
 		if (row_ok && xlo <= xhi) {
 			int rowbase = d0 * (ly + d1 * lz);
-			jb = start[rowbase + xlo]; je = start[rowbase + xhi + 1];
-			if (EMODE != 0 && oz == 0 && oy == 0) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
+			rjb[r] = start[rowbase + xlo]; rje[r] = start[rowbase + xhi + 1];
 		}
+	}
+#pragma unroll
+	for (int r = 0; r < PAIR_NSEG; r++) {
+		int jb = rjb[r];
+		const int je = rje[r];
+		if (EMODE != 0 && r == 4) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
 		sm.seg_b[r][tid] = jb;
 		const int lim = (1 << PAIR_SEGBITS) - 4;
 		sm.seg_n[r][tid] = (unsigned short)min(je - jb, lim);
@@ -1162,6 +1179,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const float ir = __int_as_float(win[WIN_INVRES]);
 		extq = (ext * ir) * ir * (1.000001f + 1.75f / (pg.rmin32 * ir));
 	}
+#if SMD_STAGE_CAP > 0
 #ifdef SMD_EXP_TIMING
 	long long t_w0 = clock64();
 #endif
@@ -1181,11 +1199,17 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		atomicAdd(&g_pair_timing[6], 1ull);
 	}
 #endif
+#endif
+	const int aiqi = __float_as_int(aiq);
 	for (int sg = 0; sg < nseg; sg++) {
 		const int n = sm.seg_n[sg][tid];
 		if (n == 0) continue;
+#if SMD_STAGE_CAP > 0
 		const int jb = sm.seg_b[sg][tid], dl = sm.st_delta[sg];
 		const uint2 *cp = dl != STAGE_NONE ? s_stage + (jb + dl) : pos16 + jb;
+#else
+		const uint2 *cp = pos16 + sm.seg_b[sg][tid];
+#endif
 		const unsigned tag = (unsigned)sg << PAIR_SEGBITS;
 		uint2 ga[4], gb[4];                          // ping-pong buffers: one group under test, the next in flight
 #pragma unroll
@@ -1207,9 +1231,15 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 				float dy = qy - __uint_as_float(__byte_perm(c[k].x, 0x4B000000u, 0x7632));
 				float dz = qz - __uint_as_float(__byte_perm(c[k].y, 0x4B000000u, 0x7610));
 				float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-				const float cw = __uint_as_float(c[k].y & 0xffff0000u);
-				const float thr = EMODE != 0 ? fminf(aiq, cw) + extq : fminf(aiq, cw);
-				if (r2 < thr && k < rem) push(e0 + k);
+				if (EMODE != 0) {
+					const float cw = __uint_as_float(c[k].y & 0xffff0000u);
+					if (r2 < fminf(aiq, cw) + extq && k < rem) push(e0 + k);
+				} else {
+					// r2 >= 0, so its bit pattern orders like an integer; the candidate's cutoff is compared in place, with
+					// the z half-word below it (less than one bf16 step more permissive; phase 2 sorts it out)
+					const int r2i = __float_as_int(r2);
+					if (r2i < (int)c[k].y && r2i < aiqi && k < rem) push(e0 + k);
+				}
 			}
 			return more;
 		};
