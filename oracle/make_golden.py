@@ -171,6 +171,29 @@ def main():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def ball():
+    """BALL molecule (system.h:1936-1971: a half-harmonic wall around a centre particle; no shipped generator emits
+    one, `MD` handles it, MD.cpp:251,467,662): the equilibrated 300-lipid vesicle of lipo_eq with two balls in one
+    record list -- the records of the second centre exercise the reference's quirk of taking the centre of every
+    record from record 0 in the force routine only."""
+    tmp = tempfile.mkdtemp(prefix="golden_ball_")
+    try:
+        m, _ = orc.load_golden(os.path.join(OUT, "lipo_eq.npz"))
+        m = dict(m)
+        n = m["nParticles"]
+        heads = [i for i in range(n) if m["type"][i] == 2]
+        c1, c2 = 1, 451   # two tail particles
+        rec = [[c1, j] for j in heads[0::2]] + [[c2, j] for j in heads[1::2]]
+        m["molecules"] = list(m["molecules"]) + [{"type": orc.BALL, "constants": np.array([5.0, 20.0]),
+                                                  "bonds": np.array(rec, np.int32)}]
+        m["nMolecules"] = len(m["molecules"])
+        orc.write_mpd(os.path.join(tmp, "ball.mpd"), m)
+        t, _ = traj(tmp, m, "ball_run", 16)
+        save("ball", pack(m, harness(tmp, "ball", (0.9993, 0.9993, 1.0 / 0.9993 ** 2)), t))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def stats():
     """long-run observables of the reference `MD` executable itself: a tensionless flat bilayer with box moves, 20 000
     steps, two independent runs (seeds 99 / 100, 8 OpenMP threads).  tests/golden/stat_bilayer.npz holds the input
@@ -206,4 +229,4 @@ def stats():
 
 
 if __name__ == "__main__":
-    stats() if len(sys.argv) > 1 and sys.argv[1] == "stats" else main()
+    {"stats": stats, "ball": ball}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()

@@ -49,7 +49,7 @@ def lib():
         L.orc_chain_potential.restype = C.c_double
         L.orc_chain_dpotential.argtypes = [_dp, d3, C.c_int, C.c_int, C.c_int, d4, d3]
         L.orc_chain_dpotential.restype = C.c_double
-        for nm in ("bond", "bend"):
+        for nm in ("bond", "bend", "ball"):
             getattr(L, f"orc_{nm}_force").argtypes = [_dp, d3, C.c_int, _ip, d2, _dp]
             getattr(L, f"orc_{nm}_potential").argtypes = [_dp, d3, C.c_int, _ip, d2]
             getattr(L, f"orc_{nm}_potential").restype = C.c_double
@@ -180,7 +180,7 @@ class _Sys(C.Structure):
                 ("accepted", C.c_longlong), ("unwrapped", C.c_void_p), ("last_dU", C.c_double)]
 
 
-BOND, BEND, CHAIN, BEAD = 6, 7, 8, 9
+BOND, BEND, CHAIN, BEAD, BALL = 6, 7, 8, 9, 19
 
 
 class System:

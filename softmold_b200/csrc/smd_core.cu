@@ -318,13 +318,21 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMallocHost(&ctx->h_pinned, 64 * sizeof(double)));
 #undef CKC
 	{
+		// the opt-in shared-memory size is a property of the FUNCTION on this device, shared by every context of the
+		// process: only ever raise it (a later context with fewer particle types must not shrink it under an earlier one)
+		static int smem_set[64] = {0};
 		int smem = pair_force_smem(ctx);
-		cudaError_t e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-		if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		int &have = smem_set[ctx->device & 63];
+		cudaError_t e1 = cudaSuccess;
+		if (smem > have) {
+			e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) have = smem;
+		}
 		if (e1 != cudaSuccess) {
 			g_create_error = std::string("cudaFuncSetAttribute(k_pair_force2): ") + cudaGetErrorString(e1);
 			smd_destroy(ctx);
@@ -626,9 +634,17 @@ extern "C" int smd_add_bends(smd_ctx *ctx, int32_t n, const int32_t *ijk, const 
 extern "C" int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const double c[2])
 {
 	if (!ctx) return SMD_ERR_ARG;
-	(void)n; (void)cj; (void)c;
-	ctx->err = "BALL molecules are not implemented yet";
-	return SMD_ERR_UNSUPPORTED;
+	REQUIRE(n >= 0 && (cj || n == 0) && c, "bad BALL arguments");
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
+	int rc = check_index(ctx, cj, 2 * (size_t)n, "BALL Molecule");
+	if (rc) return rc;
+	BallList b;
+	b.n = n; b.c[0] = c[0]; b.c[1] = c[1];
+	rc = upload_list<int>(ctx, cj, 2 * (size_t)n, &b.d_cj);
+	if (rc) return rc;
+	ctx->balls.push_back(b);
+	ctx->n_molecules++;
+	return SMD_OK;
 }
 
 // rebuild the assembled bead lists: molecule i sees its own beads followed by those of every later BEAD molecule
@@ -753,6 +769,10 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 		for (auto &b : ctx->bends)
 			if (b.n > 0)
 				LAUNCH(k_bend<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+	if (mask & SMD_MASK(SMD_TERM_BALL))
+		for (auto &b : ctx->balls)
+			if (b.n > 0)
+				LAUNCH(k_ball<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_cj, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
 	if (mask & SMD_MASK(SMD_TERM_BEAD))
 		for (auto &b : ctx->beads) {
 			if (b.nOwn <= 0) continue;
@@ -1014,7 +1034,7 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	std::vector<int> term_of_slot;
 	int slot = 0;
 	auto push = [&](int term) { term_of_slot.push_back(term); return slot++; };
-	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + 2 * ctx->beads.size() <= 64, "too many molecule records for one energy call");
+	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + ctx->balls.size() + 2 * ctx->beads.size() <= 64, "too many molecule records for one energy call");
 	if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
 		// two-phase kernel, every unordered pair once (see k_pair_force2)
 		int nb = nblk(N, PAIR_TPB);
@@ -1060,6 +1080,12 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 		int nb = nblk(b.n, TPB);
 		LAUNCH(k_bend<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz);
 		finish_sum(ctx, nb, push(SMD_TERM_BEND), 1.0);
+	}
+	for (auto &b : ctx->balls) {
+		if (b.n <= 0) continue;
+		int nb = nblk(b.n, TPB);
+		LAUNCH(k_ball<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_cj, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz);
+		finish_sum(ctx, nb, push(SMD_TERM_BALL), 1.0);
 	}
 	for (auto &b : ctx->beads) {
 		if (b.nOwn <= 0) continue;

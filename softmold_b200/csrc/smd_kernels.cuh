@@ -1935,6 +1935,56 @@ __global__ void __launch_bounds__(TPB) k_bond(int nb, int cap, const Particle *_
 	}
 }
 
+// BALL (system.h:1936-1971, :2751-2781, :3439-3474; harmonicHalfF / harmonicHalfP, MD.h:1164-1222): a harmonic wall
+// around a centre particle that acts only INSIDE r0.  One thread per record {centre, j}; the centre's share is
+// block-reduced and added with one atomic per block.  Quirk reproduced: the force routine takes the centre of
+// EVERY record from record 0 (`first=bond[0].s[0]`, system.h:1943), the two energy routines read each record's own.
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_ball(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                              const int *__restrict__ cj, double r0, double kk, double *acc, double *partials,
+                                              double sx, double sy, double sz)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0, fx = 0, fy = 0, fz = 0;
+	const int s1f = (MODE == 0) ? slot_of[cj[0]] : 0;
+	auto half_p = [&](V3 d) {
+		double dr = d.x * d.x + d.y * d.y + d.z * d.z;
+		double u = 0;
+		if (dr < r0 * r0) {
+			dr = sqrt(dr);
+			u = dr - r0;
+			u = 0.5 * kk * u * u;
+		}
+		return u;
+	};
+	if (b < nb) {
+		int s1 = (MODE == 0) ? s1f : slot_of[cj[2 * b]], s2 = slot_of[cj[2 * b + 1]];
+		V3 d = diff_mi(load_particle(pos + s1), load_particle(pos + s2), g);
+		if (MODE == 0) {
+			double dr = d.x * d.x + d.y * d.y + d.z * d.z;
+			if (dr < r0 * r0) {
+				dr = sqrt(dr);
+				double m = dr - r0;
+				m = -m * kk / dr;
+				fx = d.x * m; fy = d.y * m; fz = d.z * m;
+				atomicAdd(acc + s2, -fx); atomicAdd(acc + cap + s2, -fy); atomicAdd(acc + 2 * cap + s2, -fz);
+			}
+		} else if (MODE == 1) {
+			usum = half_p(d);
+		} else {
+			double uo = half_p(d);
+			usum = uo - half_p(scaled(d, sx, sy, sz));
+		}
+	}
+	if (MODE == 0) {
+		fx = block_sum(fx); fy = block_sum(fy); fz = block_sum(fz);
+		if (threadIdx.x == 0) { atomicAdd(acc + s1f, fx); atomicAdd(acc + cap + s1f, fy); atomicAdd(acc + 2 * cap + s1f, fz); }
+	} else {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
 // explicit BEND list (system.h:1975-2040, :2781-2822, :3476-3527)
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_bend(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,

@@ -94,7 +94,8 @@ def test_pair_force_potential_dpotential(contexts, case):
     assert close_energy(ctx.kinetic(), ref["kinetic"][0]) <= 1e-13
 
 
-TERM_OF = {sm.MOL_CHAIN: sm.TERM_CHAIN, sm.MOL_BOND: sm.TERM_BOND, sm.MOL_BEND: sm.TERM_BEND, sm.MOL_BEAD: sm.TERM_BEAD}
+TERM_OF = {sm.MOL_CHAIN: sm.TERM_CHAIN, sm.MOL_BOND: sm.TERM_BOND, sm.MOL_BEND: sm.TERM_BEND, sm.MOL_BEAD: sm.TERM_BEAD,
+           sm.MOL_BALL: sm.TERM_BALL}
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -154,7 +155,7 @@ def test_philox_uniforms_bit_exact(orc):
     assert abs(u.mean() - 0.5) < 2e-3 and abs(u.var() - 1 / 12) < 1e-3 and u.min() >= 0 and u.max() < 1
 
 
-@pytest.mark.parametrize("case", ["lipo_t0", "lipo_eq", "bilayer_t0", "bilayer_eq", "bead1", "bead2"])
+@pytest.mark.parametrize("case", ["lipo_t0", "lipo_eq", "bilayer_t0", "bilayer_eq", "bead1", "bead2", "ball"])
 def test_trajectory_matches_reference_md(contexts, orc, case):
     """The whole loop of MD.cpp for K steps against the state the reference `MD` executable wrote (one thread):
     Langevin noise = the reference's MT19937 stream fed through smd_set_noise, MC box moves with tension driven by
