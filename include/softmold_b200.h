@@ -166,6 +166,21 @@ int smd_get_forces(smd_ctx *ctx, double *acc);
 int smd_get_unwrapped(smd_ctx *ctx, double *xyz);
 int smd_get_box(smd_ctx *ctx, double box[3]);
 
+/* Asynchronous read-back for the checkpoint / trajectory / observable writers (MD.cpp:373-381 Script::write +
+ * xyzFormat::store, dataExtraction::compute :525-543 -- all synchronous in the reference, where one 240 000-particle
+ * store is cheap next to 1 000 CPU steps; next to 1 000 GPU steps it is not, so the driver moves the text formatting
+ * to a worker thread and the device keeps stepping).
+ *   smd_host_alloc / smd_host_free   page-locked host memory (so that the copy really is asynchronous)
+ *   smd_snapshot        gathers the state into original particle order on the context's stream and starts the
+ *                       device-to-host copies on a separate copy stream; returns a ticket at once.  Any of xyz [n][3],
+ *                       vel [n][3], unwrapped [n][3] may be NULL; the buffers must stay valid until the ticket was
+ *                       waited for.  At most two tickets may be outstanding.
+ *   smd_snapshot_wait   blocks the calling thread -- ANY thread -- until the copies of that ticket have landed */
+int smd_host_alloc(void **ptr, size_t bytes);
+int smd_host_free(void *ptr);
+int smd_snapshot(smd_ctx *ctx, double *xyz, double *vel, double *unwrapped, int64_t *ticket);
+int smd_snapshot_wait(smd_ctx *ctx, int64_t ticket);
+
 /* cell membership as the reference computes it (cellOpt.h:530-556): key of every particle, and the particles of
  * every occupied cell in the reference's list order (descending particle index, cellOpt.h:572-585).
  * n_cells_xyz[3] = nCells.  cell_key / cell_rank are [n]: rank = position of the particle in its cell's list. */

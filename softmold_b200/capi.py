@@ -34,6 +34,7 @@ SYMBOLS = [
     "smd_slab_columns", "smd_slab_select", "smd_slab_recv_buffer", "smd_slab_ipc_handle", "smd_slab_connect_ipc",
     "smd_slab_connect_ptr", "smd_slab_exchange_send", "smd_slab_exchange_recv", "smd_slab_counts", "smd_slab_capacity",
     "smd_slab_get_local", "smd_slab_set_local", "smd_mc_propose", "smd_mc_accept",
+    "smd_host_alloc", "smd_host_free", "smd_snapshot", "smd_snapshot_wait",
 ]
 
 
@@ -67,6 +68,10 @@ def lib():
         L.smd_last_error.argtypes = [C.c_void_p]
         vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.smd_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+        L.smd_host_free.argtypes = [vp]
+        L.smd_snapshot.argtypes = [vp, vp, vp, vp, C.POINTER(i64)]
+        L.smd_snapshot_wait.argtypes = [vp, i64]
         L.smd_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
         L.smd_destroy.argtypes = [vp]
         L.smd_set_pair_tables.argtypes = [vp, vp, vp]
@@ -327,6 +332,26 @@ class Context:
             xyz, typ, vel = out
         self._ck(self.L.smd_get_particles(self.h, _ptr(xyz), _ptr(typ), _ptr(vel)))
         return xyz, typ, vel
+
+    def snapshot(self, unwrapped=False):
+        """asynchronous read-back (smd_snapshot): returns wait() -> (xyz, vel[, unwrapped]) in page-locked buffers"""
+        n = self.n
+        bufs, ptrs = [], []
+        for _ in range(3 if unwrapped else 2):
+            p = C.c_void_p()
+            self._ck(self.L.smd_host_alloc(C.byref(p), 24 * n))
+            ptrs.append(p)
+            bufs.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n, 3)))
+        t = C.c_int64()
+        self._ck(self.L.smd_snapshot(self.h, ptrs[0], ptrs[1], ptrs[2] if unwrapped else None, C.byref(t)))
+
+        def wait():
+            self._ck(self.L.smd_snapshot_wait(self.h, t))
+            out = tuple(b.copy() for b in bufs)
+            for p in ptrs:
+                self.L.smd_host_free(p)
+            return out
+        return wait
 
     def get_forces(self):
         a = np.zeros((self.n, 3))

@@ -12,11 +12,24 @@
 // The schedule (what happens at which step index, restart half kick, Metropolis box move every 8 steps with the
 // MT19937 stream MTRand(seed)) follows MD.cpp:186-333 and the loop :335-729.
 //
+// Checkpoints, frames and observables are written by a WORKER THREAD from page-locked snapshots (smd_snapshot): one
+// 240 000-particle store is 26 MB of text = 0.3 s of formatting, more than the 1 000 MD steps between two stores take
+// on the device, so the device keeps stepping while the previous store is being formatted.  The files are the same,
+// in the same order (one FIFO); SMD_SYNC_IO=1 does the work inline instead (A/B timing).
+//
 // Differences, all deliberate: the Langevin noise is the counter-based Philox stream of the library (the reference's
 // depends on the OpenMP thread count); gammaType (per-type friction) and the molecule kinds outside the
 // hot path are refused loudly instead of silently ignored; environment variable SMD_DEVICE picks the GPU.
+#include <algorithm>
+#include <charconv>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <ctime>
@@ -65,70 +78,184 @@ struct MT19937 {
 
 struct Mol { int type, n, width; int32_t *rec; int nconst; double *c; };
 
+struct Job {
+	int kind;                 // 0: store (Script::write + xyz frame), 1: measure (dataExtraction::compute)
+	bool write_mpd, diffusion;
+	double time_now, temperature, box[3], terms[SMD_NTERMS], kinetic;
+	int slot;
+	int64_t ticket;
+};
+
 struct Driver {
 	std::string name;
 	smd_mpd *mpd = nullptr;
 	smd_ctx *ctx = nullptr;
 	int n = 0;
-	double *xyz = nullptr, *vel = nullptr;   // borrowed from the mpd object: refreshed before every use
+	double *xyz = nullptr, *vel = nullptr;   // borrowed from the mpd object; written by the worker only
 	int32_t *type = nullptr;
 	std::vector<Mol> mols;
-	std::vector<double> unw, unw_start;      // aP / aPStart of the reference (MD.cpp:96-105, dataExtraction.h:790-803)
+	std::vector<double> unw_start;           // aPStart of the reference (MD.cpp:96-105, dataExtraction.h:790-803)
 	bool diffusion_started = false;
 	std::vector<long> ke_hist;
 	double temperature = 0, time_now = 0;
 
+	// snapshots in flight: two page-locked buffer sets, one FIFO of jobs, one worker
+	struct Slot { double *xyz = nullptr, *vel = nullptr, *unw = nullptr; bool busy = false; } slots[2];
+	std::thread worker;
+	std::mutex mu;
+	std::condition_variable cv_job, cv_free;
+	std::deque<Job> jobs;
+	bool quit = false, sync_io = false;
+
 	void die(const char *what, int rc)
 	{
 		std::cerr << what << ": " << (ctx ? smd_last_error(ctx) : smd_last_error(nullptr)) << " (code " << rc << ")\n";
-		std::exit(1);
+		std::_Exit(1);
 	}
 	void ck(int rc, const char *what) { if (rc) die(what, rc); }
 
-	void download()
+	void start_io()
 	{
-		ck(smd_get_particles(ctx, xyz, nullptr, vel), "smd_get_particles");
+		sync_io = std::getenv("SMD_SYNC_IO") != nullptr;
+		for (Slot &s : slots) {
+			ck(smd_host_alloc((void **)&s.xyz, 3 * (size_t)n * sizeof(double)), "smd_host_alloc");
+			ck(smd_host_alloc((void **)&s.vel, 3 * (size_t)n * sizeof(double)), "smd_host_alloc");
+			ck(smd_host_alloc((void **)&s.unw, 3 * (size_t)n * sizeof(double)), "smd_host_alloc");
+		}
+		if (!sync_io) worker = std::thread([this] { work(); });
+	}
+
+	void stop_io()
+	{
+		if (worker.joinable()) {
+			{ std::lock_guard<std::mutex> l(mu); quit = true; }
+			cv_job.notify_all();
+			worker.join();
+		}
+		for (Slot &s : slots) { smd_host_free(s.xyz); smd_host_free(s.vel); smd_host_free(s.unw); }
+	}
+
+	void work()
+	{
+		for (;;) {
+			Job j;
+			{
+				std::unique_lock<std::mutex> l(mu);
+				cv_job.wait(l, [this] { return quit || !jobs.empty(); });
+				if (jobs.empty()) return;
+				j = jobs.front();
+				jobs.pop_front();
+			}
+			run(j);
+			{ std::lock_guard<std::mutex> l(mu); slots[j.slot].busy = false; }
+			cv_free.notify_all();
+		}
+	}
+
+	// snapshot of the current state into a free buffer set + the job that consumes it
+	void submit(Job j, bool want_unw)
+	{
+		{
+			std::unique_lock<std::mutex> l(mu);
+			cv_free.wait(l, [this] { return !slots[0].busy || !slots[1].busy; });
+			j.slot = slots[0].busy ? 1 : 0;
+			slots[j.slot].busy = true;
+		}
+		Slot &s = slots[j.slot];
+		ck(smd_snapshot(ctx, s.xyz, s.vel, want_unw ? s.unw : nullptr, &j.ticket), "smd_snapshot");
+		if (sync_io) {
+			run(j);
+			slots[j.slot].busy = false;
+			return;
+		}
+		{ std::lock_guard<std::mutex> l(mu); jobs.push_back(j); }
+		cv_job.notify_all();
+	}
+
+	void run(const Job &j)
+	{
+		ck(smd_snapshot_wait(ctx, j.ticket), "smd_snapshot_wait");
+		if (j.kind == 0) do_store(j, slots[j.slot]);
+		else do_measure(j, slots[j.slot]);
 	}
 
 	// Script::write + xyzFormat::store at a store step (MD.cpp:373-381)
 	void store(bool write_mpd)
 	{
-		download();
-		if (write_mpd) {
-			double box[3];
-			smd_get_box(ctx, box);
-			smd_mpd_set_size(mpd, box);
-			smd_mpd_set_scalar(mpd, "initialTime", time_now);
-			smd_mpd_set_scalar(mpd, "initialTemp", temperature);
+		Job j = {};
+		j.kind = 0; j.write_mpd = write_mpd; j.time_now = time_now; j.temperature = temperature;
+		smd_get_box(ctx, j.box);
+		submit(j, false);
+	}
+
+	void do_store(const Job &j, const Slot &s)
+	{
+		if (j.write_mpd) {
+			std::memcpy(xyz, s.xyz, 3 * (size_t)n * sizeof(double));
+			std::memcpy(vel, s.vel, 3 * (size_t)n * sizeof(double));
+			smd_mpd_set_size(mpd, j.box);
+			smd_mpd_set_scalar(mpd, "initialTime", j.time_now);
+			smd_mpd_set_scalar(mpd, "initialTemp", j.temperature);
 			char err[512];
-			if (smd_mpd_write(mpd, name.c_str(), err, sizeof err)) { std::cerr << err << "\n"; std::exit(1); }
+			if (smd_mpd_write(mpd, name.c_str(), err, sizeof err)) { std::cerr << err << "\n"; std::_Exit(1); }
+		}
+		// xyzFormat::store (xyzFormat.h:111-143): default stream precision = %g; formatted in parallel chunks
+		const unsigned T = n < 32768 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+		std::vector<std::string> part(T);
+		auto fill = [&](unsigned t) {
+			std::string &o = part[t];
+			o.reserve(((size_t)n / T + 1) * 48);
+			char buf[64];
+			for (size_t i = (size_t)n * t / T; i < (size_t)n * (t + 1) / T; i++) {
+				o += std::to_string(type[i]);
+				for (int a = 0; a < 3; a++) {
+					o += '\t';
+					const double v = s.xyz[3 * i + a];
+					if (std::isfinite(v)) o.append(buf, std::to_chars(buf, buf + sizeof buf, v, std::chars_format::general, 6).ptr);
+					else { snprintf(buf, sizeof buf, "%g", v); o += buf; }
+				}
+				o += '\n';
+			}
+		};
+		if (T == 1) fill(0);
+		else {
+			std::vector<std::thread> th;
+			for (unsigned t = 0; t < T; t++) th.emplace_back(fill, t);
+			for (auto &x : th) x.join();
 		}
 		std::ofstream f("frames_" + name + ".xyz", std::ios::out | std::ios::app);
 		f << n << '\n' << "test\n";
-		for (int i = 0; i < n; i++) f << type[i] << '\t' << xyz[3 * i] << '\t' << xyz[3 * i + 1] << '\t' << xyz[3 * i + 2] << '\n';
+		for (auto &o : part) f << o;
 	}
 
 	template <class... A>
-	void line(const char *prefix, A... values)
+	void line(double t, const char *prefix, A... values)
 	{
 		std::ofstream f(prefix + name + ".dat", std::ios::app | std::ios::out);
-		f << time_now;
+		f << t;
 		((f << '\t' << values), ...);
 		f << std::endl;
 	}
 
-	// dataExtraction::compute (dataExtraction.h:827-1693, default build: no ANCHOR_DATA / FLAT_MEMBRANE / NANOPARTICLE)
+	// dataExtraction::compute (dataExtraction.h:827-1693, default build: no ANCHOR_DATA / FLAT_MEMBRANE / NANOPARTICLE):
+	// the energies are reduced on the device, the geometric observables by the worker from a snapshot
 	void measure()
 	{
-		double terms[SMD_NTERMS];
-		ck(smd_potential(ctx, terms), "smd_potential");
+		Job j = {};
+		j.kind = 1; j.time_now = time_now; j.temperature = temperature; j.diffusion = diffusion_started;
+		ck(smd_potential(ctx, j.terms), "smd_potential");
+		ck(smd_kinetic(ctx, &j.kinetic), "smd_kinetic");
+		smd_get_box(ctx, j.box);
+		submit(j, diffusion_started);
+	}
+
+	void do_measure(const Job &j, const Slot &sl)
+	{
+		const double *xyz = sl.xyz, *vel = sl.vel, *unw = sl.unw;
+		const double *terms = j.terms, *s = j.box;
+		const double kinetic = j.kinetic, temperature = j.temperature, time_now = j.time_now;
 		double potential = 0;
 		for (int t = 0; t < SMD_NTERMS; t++) potential += terms[t];
-		double kinetic = 0;
-		ck(smd_kinetic(ctx, &kinetic), "smd_kinetic");
-		download();
-		double s[3];
-		smd_get_box(ctx, s);
 
 		double lBond = 0, costhetaBend = 0, lBend[2] = {0, 0};
 		int nBond = 0, nBend = 0, nBeads = 0;
@@ -165,14 +292,14 @@ struct Driver {
 				nBeads++;
 			}
 		}
-		line("potential_", potential);
-		line("size_", s[0], s[1], s[2]);
-		line("lBond_", lBond / (double)nBond);
+		line(time_now, "potential_", potential);
+		line(time_now, "size_", s[0], s[1], s[2]);
+		line(time_now, "lBond_", lBond / (double)nBond);
 		if (nBend > 1) { costhetaBend /= nBend; lBend[0] /= nBend; lBend[1] /= nBend; }
-		line("bend_", costhetaBend, lBend[0], lBend[1]);
-		if (nBeads > 0) line("beadPotential_", terms[SMD_TERM_BEAD]);
-		line("temp_", temperature);
-		line("kinetic_", kinetic);
+		line(time_now, "bend_", costhetaBend, lBend[0], lBend[1]);
+		if (nBeads > 0) line(time_now, "beadPotential_", terms[SMD_TERM_BEAD]);
+		line(time_now, "temp_", temperature);
+		line(time_now, "kinetic_", kinetic);
 
 		double lo[3] = {s[0], s[1], s[2]}, hi[3] = {0, 0, 0};
 		for (int i = 0; i < n; i++)
@@ -180,7 +307,7 @@ struct Driver {
 				if (xyz[3 * i + a] < lo[a]) lo[a] = xyz[3 * i + a];
 				if (xyz[3 * i + a] > hi[a]) hi[a] = xyz[3 * i + a];
 			}
-		line("flicker_", hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+		line(time_now, "flicker_", hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
 
 		const double part = 0.0001;   // kEnergyDensityPartition, dataExtraction.h:390
 		for (int i = 0; i < n; i++) {
@@ -189,12 +316,11 @@ struct Driver {
 			ke_hist[b]++;
 		}
 
-		if (diffusion_started) {   // dataExtraction.h:1525-1663
-			ck(smd_get_unwrapped(ctx, unw.data()), "smd_get_unwrapped");
+		if (j.diffusion) {   // dataExtraction.h:1525-1663
 			std::ofstream f("meanSquareDisplacement_" + name + ".dat", std::ios::app | std::ios::out);
 			f << time_now;
-			auto sq = [&](int j) {
-				double d0 = unw[3 * j] - unw_start[3 * j], d1 = unw[3 * j + 1] - unw_start[3 * j + 1], d2 = unw[3 * j + 2] - unw_start[3 * j + 2];
+			auto sq = [&](int k) {
+				double d0 = unw[3 * k] - unw_start[3 * k], d1 = unw[3 * k + 1] - unw_start[3 * k + 1], d2 = unw[3 * k + 2] - unw_start[3 * k + 2];
 				return d0 * d0 + d1 * d1 + d2 * d2;
 			};
 			for (const Mol &m : mols) {
@@ -207,7 +333,7 @@ struct Driver {
 				} else if (m.type == SMD_MOL_CHAIN) {
 					for (int l = 0; l < m.n; l++) {
 						int st = m.rec[3 * l], nch = m.rec[3 * l + 1], len = m.rec[3 * l + 2];
-						for (int j = st; j < st + len * nch; j++) msd += sq(j);
+						for (int k = st; k < st + len * nch; k++) msd += sq(k);
 						np += len * nch;
 					}
 				}
@@ -287,7 +413,7 @@ int main(int argc, char *argv[])
 		return 1;
 	}
 	smd_ctx *ctx = D.ctx;
-	D.unw.resize(3 * (size_t)D.n);
+	D.start_io();
 
 	// MD.cpp:311-323: integer step indices; the 1e-7 is the reference's
 	const int endInt = int(finalTime / dt + 0.0000001), startInt = int(initialTime / dt + 0.0000001);
@@ -330,6 +456,7 @@ int main(int argc, char *argv[])
 
 	std::cerr << "starting main loop: \n";
 	time_t current = time(NULL);
+	const auto loop_t0 = std::chrono::steady_clock::now();
 	for (int i = startInt; i <= endInt;) {
 		// steps without any host-side event run back to back on the device
 		int nplain = 0;
@@ -369,6 +496,13 @@ int main(int argc, char *argv[])
 		i++;
 	}
 	D.ck(smd_synchronize(ctx), "smd_synchronize");
+	const auto loop_t1 = std::chrono::steady_clock::now();
+	D.stop_io();   // every queued store / measurement is on disk
+	if (std::getenv("SMD_TIMING")) {   // not part of the reference's output: loop seconds, then seconds until the writer had drained
+		const auto loop_t2 = std::chrono::steady_clock::now();
+		std::cerr << "SMD_TIMING loop " << std::chrono::duration<double>(loop_t1 - loop_t0).count() << " drained "
+		          << std::chrono::duration<double>(loop_t2 - loop_t0).count() << std::endl;
+	}
 
 	if (deltaLXY != 0) {
 		std::ofstream f("resizeHist_" + D.name + ".dat", std::ios::out);

@@ -8,14 +8,18 @@
 // Written from the format's behaviour, not from the reference's state machine: a straight tokenizer + a writer
 // that reproduces the byte layout of Script::write (every emitted item is followed by one space, absent optional
 // commands leave a lone space, rows end with "\n").
+#include <algorithm>
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <charconv>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/softmold_b200.h"
@@ -262,6 +266,33 @@ std::string num(double v)
 	return buf;
 }
 
+// the two big blocks (positions, velocities: 6 numbers per particle, 26 MB for 240 000 particles) are formatted in
+// parallel chunks with std::to_chars -- by the C++17 rule the same characters as printf("%.15g") in the C locale
+inline void put_num(std::string &o, double v)
+{
+	char buf[64];
+	if (std::isfinite(v)) {
+		auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::general, 15);
+		o.append(buf, r.ptr);
+	} else {
+		o += num(v);
+	}
+	o += ' ';
+}
+
+template <class F>
+void parallel_text(size_t n, std::string &o, F fill)
+{
+	unsigned T = n < 32768 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+	if (T == 1) { fill((size_t)0, n, o); return; }
+	std::vector<std::string> part(T);
+	std::vector<std::thread> th;
+	for (unsigned t = 0; t < T; t++)
+		th.emplace_back([&, t] { part[t].reserve((n / T + 1) * 80); fill(n * t / T, n * (t + 1) / T, part[t]); });
+	for (auto &x : th) x.join();
+	for (auto &x : part) o += x;
+}
+
 std::string serialize(const smd_mpd &m)
 {
 	std::string o;
@@ -290,19 +321,30 @@ std::string serialize(const smd_mpd &m)
 			break;
 		}
 		case POSITIONS:
-			for (size_t i = 0; i < m.type.size(); i++) {
-				put(o, std::string(i == 0 ? "\n " : "") + std::to_string(m.type[i]));
-				put(o, num(m.xyz[3 * i]));
-				put(o, num(m.xyz[3 * i + 1]));
-				put(o, num(m.xyz[3 * i + 2]) + "\n");
-			}
+			parallel_text(m.type.size(), o, [&](size_t i0, size_t i1, std::string &t) {
+				for (size_t i = i0; i < i1; i++) {
+					if (i == 0) t += "\n ";
+					t += std::to_string(m.type[i]);
+					t += ' ';
+					put_num(t, m.xyz[3 * i]);
+					put_num(t, m.xyz[3 * i + 1]);
+					put_num(t, m.xyz[3 * i + 2]);
+					t.back() = '\n';
+					t += ' ';
+				}
+			});
 			break;
 		case VELOCITIES:
-			for (size_t i = 0; i < m.vel.size() / 3; i++) {
-				put(o, std::string(i == 0 ? "\n " : "") + num(m.vel[3 * i]));
-				put(o, num(m.vel[3 * i + 1]));
-				put(o, num(m.vel[3 * i + 2]) + "\n");
-			}
+			parallel_text(m.vel.size() / 3, o, [&](size_t i0, size_t i1, std::string &t) {
+				for (size_t i = i0; i < i1; i++) {
+					if (i == 0) t += "\n ";
+					put_num(t, m.vel[3 * i]);
+					put_num(t, m.vel[3 * i + 1]);
+					put_num(t, m.vel[3 * i + 2]);
+					t.back() = '\n';
+					t += ' ';
+				}
+			});
 			break;
 		case MOLECULE:
 			for (size_t k = 0; k < m.mol.size(); k++) {

@@ -369,6 +369,10 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 		cudaFree(ctx->recv_base[sd]);
 	}
 	cudaFree(ctx->comm.counters);
+	if (ctx->snap_stage) {
+		cudaFree(ctx->snap_stage); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->snap_gathered);
+		cudaEventDestroy(ctx->snap_done[0]); cudaEventDestroy(ctx->snap_done[1]);
+	}
 	for (auto &b : ctx->bonds) cudaFree(b.d_ij);
 	for (auto &b : ctx->bends) cudaFree(b.d_ijk);
 	for (auto &b : ctx->balls) cudaFree(b.d_cj);
@@ -1268,6 +1272,62 @@ extern "C" int smd_get_unwrapped(smd_ctx *ctx, double *xyz)
 	LAUNCH(k_export_soa3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->stage);
 	CK(cudaMemcpyAsync(xyz, ctx->stage, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	return check_device_errors(ctx);
+}
+
+extern "C" int smd_host_alloc(void **ptr, size_t bytes)
+{
+	if (!ptr) return SMD_ERR_ARG;
+	cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+	if (e != cudaSuccess) { *ptr = nullptr; g_create_error = std::string("smd_host_alloc: ") + cudaGetErrorString(e); return SMD_ERR_CUDA; }
+	return SMD_OK;
+}
+
+extern "C" int smd_host_free(void *ptr)
+{
+	if (ptr) cudaFreeHost(ptr);
+	return SMD_OK;
+}
+
+extern "C" int smd_snapshot(smd_ctx *ctx, double *xyz, double *vel, double *unwrapped, int64_t *ticket)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ticket && ctx->particles_set, "bad call");
+	REQUIRE(!ctx->slab, "slab: use smd_slab_get_local");
+	REQUIRE(!unwrapped || ctx->unw[0], "unwrapped positions are not tracked");
+	CK(cudaSetDevice(ctx->device));
+	const int N = ctx->N;
+	const size_t cap3 = 3 * (size_t)ctx->cap;
+	if (!ctx->snap_stage) {
+		CK(cudaMalloc(&ctx->snap_stage, 3 * cap3 * sizeof(double)));
+		CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&ctx->snap_gathered, cudaEventDisableTiming));
+		for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&ctx->snap_done[k], cudaEventDisableTiming | cudaEventBlockingSync));
+	}
+	// the gather buffer is free again once the copies of the previous ticket have read it
+	if (ctx->snap_seq > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->snap_done[(ctx->snap_seq - 1) & 1], 0));
+	double *sx = ctx->snap_stage, *sv = sx + cap3, *su = sv + cap3;
+	if (xyz || vel)
+		LAUNCH(k_export_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->gid[ctx->cur], xyz ? sx : nullptr,
+		       (int *)nullptr, vel ? sv : nullptr);
+	if (unwrapped) LAUNCH(k_export_soa3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->unw[ctx->cur], ctx->gid[ctx->cur], su);
+	CK(cudaEventRecord(ctx->snap_gathered, ctx->stream));
+	CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->snap_gathered, 0));
+	const size_t bytes = 3 * (size_t)N * sizeof(double);
+	if (xyz) CK(cudaMemcpyAsync(xyz, sx, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+	if (vel) CK(cudaMemcpyAsync(vel, sv, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+	if (unwrapped) CK(cudaMemcpyAsync(unwrapped, su, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+	CK(cudaEventRecord(ctx->snap_done[ctx->snap_seq & 1], ctx->copy_stream));
+	*ticket = ctx->snap_seq++;
+	return SMD_OK;
+}
+
+extern "C" int smd_snapshot_wait(smd_ctx *ctx, int64_t ticket)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	// called from the writer thread while the owner keeps enqueueing work: touches nothing but the ticket's event
+	if (ticket < 0 || ticket >= ctx->snap_seq || ticket + 2 < ctx->snap_seq) return SMD_ERR_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return SMD_ERR_CUDA;
+	return cudaEventSynchronize(ctx->snap_done[ticket & 1]) == cudaSuccess ? SMD_OK : SMD_ERR_CUDA;
 }
 
 extern "C" int smd_get_box(smd_ctx *ctx, double box[3])

@@ -183,6 +183,12 @@ struct smd_ctx {
 	bool ext_valid = false;      // dN[1] holds the count after an unpack (consumed by the next build)
 	int *d_export_counter = nullptr;
 
+	// asynchronous snapshots (smd_snapshot): gather buffer, copy stream, one event per ticket parity
+	double *snap_stage = nullptr;          // [9][cap]: xyz, vel, unwrapped in original order
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t snap_gathered = nullptr, snap_done[2] = {nullptr, nullptr};
+	long long snap_seq = 0;
+
 	// per-phase event timing (smd_profile)
 	struct ProfSpan { int phase; cudaEvent_t e0, e1; };
 	uint32_t prof_mask = 0;
