@@ -688,6 +688,18 @@ constexpr int PAIR_TPB = 128;
 #ifndef SMD_PAIR_CAP
 #define SMD_PAIR_CAP 128
 #endif
+// SMD_PAIR_FLAT=1: phase 1 walks one flat stream per thread instead of meeting the other lanes after every stencil
+// row.  More lanes stay busy (24 instead of 18 of 32 per instruction, 10 % fewer warp instructions), but the lanes of
+// a cell, which walk nearly the same ranges, drift apart and stop sharing their loads: a warp-wide load that was a
+// broadcast of a few addresses becomes 32 different ones, and the L1 data pipe is the busiest unit of this kernel.
+// Measured on C2: 192 us against 162 us (also with the staged copy in shared memory, and with the particles dealt to
+// the threads by candidate count: 194 - 201 us).  Off by default.
+#ifndef SMD_PAIR_FLAT
+#define SMD_PAIR_FLAT 0
+#endif
+#if SMD_PAIR_FLAT && SMD_STAGE_CAP > 0
+#error "SMD_PAIR_FLAT reads the candidates through L1: build with SMD_STAGE_CAP=0"
+#endif
 #ifndef SMD_PAIR_BLOCKS
 #define SMD_PAIR_BLOCKS 4
 #endif
@@ -1140,9 +1152,17 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		int jb = rjb[r];
 		const int je = rje[r];
 		if (EMODE != 0 && r == 4) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
-		sm.seg_b[r][tid] = jb;
 		const int lim = (1 << PAIR_SEGBITS) - 4;
+#if SMD_PAIR_FLAT
+		if (je > jb) {   // the table holds the non-empty ranges back to back (list entries carry the table row)
+			sm.seg_b[nseg][tid] = jb;
+			sm.seg_n[nseg][tid] = (unsigned short)min(je - jb, lim);
+			nseg++;
+		}
+#else
+		sm.seg_b[r][tid] = jb;
 		sm.seg_n[r][tid] = (unsigned short)min(je - jb, lim);
+#endif
 		// a range longer than the 12-bit offset field (> 1300 particles per cell): take the excess one by one
 		for (int j = jb + lim; j < je; j++) {
 			float4 c = pos32[j];
@@ -1156,7 +1176,9 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 				}
 			}
 		}
+#if !SMD_PAIR_FLAT
 		nseg = (je > jb) ? r + 1 : nseg;
+#endif
 	}
 
 #ifdef SMD_EXP_TIMING
@@ -1201,6 +1223,62 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 #endif
 #endif
 	const int aiqi = __float_as_int(aiq);
+#if SMD_PAIR_FLAT
+	// ONE flat stream per thread: the particle's ranges back to back, four candidates per step, the next four (of this
+	// range or of the next one, whose table entry is fetched a whole range ahead) already in flight; no branch in the
+	// hand-over from range to range, so the lanes of a warp only meet again at the end of the phase
+	auto test4 = [&](const uint2 (&c)[4], int rem, unsigned e0) {
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			float dx = qx - __uint_as_float(__byte_perm(c[k].x, 0x4B000000u, 0x7610));
+			float dy = qy - __uint_as_float(__byte_perm(c[k].x, 0x4B000000u, 0x7632));
+			float dz = qz - __uint_as_float(__byte_perm(c[k].y, 0x4B000000u, 0x7610));
+			float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+			if (EMODE != 0) {
+				const float cw = __uint_as_float(c[k].y & 0xffff0000u);
+				if (r2 < fminf(aiq, cw) + extq && k < rem) push(e0 + k);
+			} else {
+				const int r2i = __float_as_int(r2);
+				if (r2i < (int)c[k].y && r2i < aiqi && k < rem) push(e0 + k);
+			}
+		}
+	};
+	if (nseg > 0) {
+		const uint2 *cp = pos16 + sm.seg_b[0][tid], *ncp = cp;
+		int rem = sm.seg_n[0][tid], nn = 0, k = 0;
+		if (nseg > 1) { ncp = pos16 + sm.seg_b[1][tid]; nn = sm.seg_n[1][tid]; }
+		unsigned e0 = 0;
+		uint2 ga[4], gb[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) ga[j] = cp[j];   // pos16[] is padded: the overhang is masked in test4
+		bool more = true;
+		auto step = [&](const uint2 (&c)[4], uint2 (&nx)[4]) {
+			const unsigned ecur = e0;
+			const int rcur = rem;
+			const bool adv = rem <= 4;
+			cp = adv ? ncp : cp + 4;
+			rem = adv ? nn : rem - 4;
+			e0 = adv ? (unsigned)(k + 1) << PAIR_SEGBITS : e0 + 4u;
+			if (adv) {
+				k++;
+				more = k < nseg;
+				if (k + 1 < nseg) { ncp = pos16 + sm.seg_b[k + 1][tid]; nn = sm.seg_n[k + 1][tid]; }
+			}
+			if (more) {
+#pragma unroll
+				for (int j = 0; j < 4; j++) nx[j] = cp[j];
+			}
+			test4(c, rcur, ecur);
+			return more;
+		};
+		while (true) {
+			if (!step(ga, gb)) break;
+			if (!step(gb, ga)) break;
+			if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }   // list nearly full: never seen in practice
+		}
+		if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }
+	}
+#else
 	for (int sg = 0; sg < nseg; sg++) {
 		const int n = sm.seg_n[sg][tid];
 		if (n == 0) continue;
@@ -1250,6 +1328,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		}
 		if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }
 	}
+
+#endif
 
 	// ---- rows and end cells seen through a periodic image (particles in the outermost cell layers only)
 	if (shifted_rows) {

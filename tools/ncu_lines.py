@@ -29,7 +29,10 @@ for r in rows:
     if len(r) > 10 and r[0] == "Line No": hdr = r; continue
     if hdr is None or len(r) < 10 or r[0] == "": continue
     iS, iI, iT = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
-    agg.append((int(r[iI]), int(r[iS]), int(r[iT]), cur, r[0], r[1][:100]))
+    try:
+        agg.append((int(r[iI]), int(r[iS]), int(r[iT]), cur, r[0], r[1][:100]))
+    except ValueError:
+        continue
 tot = sum(a[0] for a in agg) or 1; tots = sum(a[1] for a in agg) or 1
 print("total warp-inst", tot, "samples", tots)
 for a in sorted(agg, reverse=True)[:top]:
