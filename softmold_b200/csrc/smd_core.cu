@@ -301,7 +301,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->cursor, (ctx->cellcap + 1) * sizeof(int)));
 	CKC(cudaMalloc(&ctx->blockSums, SCAN_BLOCKS * sizeof(int)));
 	CKC(cudaMalloc(&ctx->cellOfSlot, cap * sizeof(int)));
-	CKC(cudaMalloc(&ctx->order, cap * sizeof(int)));
+	CKC(cudaMalloc(&ctx->order, cap * sizeof(int2)));
 	CKC(cudaMalloc(&ctx->bbox, 6 * sizeof(int)));
 	int bb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
 	CKC(cudaMemcpy(ctx->bbox, bb, sizeof bb, cudaMemcpyHostToDevice));
@@ -723,7 +723,7 @@ static int build_cells(smd_ctx *ctx)
 	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
 	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N,
 	       ctx->slab ? ctx->dN : nullptr, ctx->errflag);
-	LAUNCH(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order);
+	LAUNCH(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order, ctx->gid[cur]);
 	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
 	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0, ctx->pos16, ctx->arad, ctx->win,

@@ -136,7 +136,8 @@ struct smd_ctx {
 	// cell grid
 	long long cellcap;
 	int *count, *start, *cursor, *blockSums;
-	int *cellOfSlot, *order;
+	int *cellOfSlot;
+	int2 *order;      // {previous slot, original index} of every position claimed by k_place
 	int *win;         // window descriptor of the current sorted order (device)
 	int *bbox;        // [6] min xyz, max xyz accumulators
 	int *errflag;

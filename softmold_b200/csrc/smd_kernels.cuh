@@ -457,19 +457,19 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox,
 }
 
 // pass 2: claim a position inside the cell's range (arbitrary order, fixed by k_reorder)
-__global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int *order)
+__global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int2 *order, const int *__restrict__ gid)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= cnt.get()) return;
 	int c = cellOfSlot[s];
 	if (c < 0) return;
 	int q = atomicAdd(cursor + c, 1);
-	order[q] = s;
+	order[q] = make_int2(s, gid[s] & GID_MASK);   // the original index travels along: k_reorder ranks a cell without a second gather
 }
 
 // pass 3: final slot = cell start + rank by DESCENDING original index, which is exactly the order of the
 // reference's head-inserted linked list (cellOpt.h:572-585) and makes the sort deterministic; move the records.
-__global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int *order, const int *cellOfSlot, const int *start,
+__global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *__restrict__ order, const int *cellOfSlot, const int *start,
                                                  const Particle *pos_in, Particle *pos_out, const double *vel_in, double *vel_out,
                                                  const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
                                                  const int *gid_in, int *gid_out, int *slot_of, float4 *pos32_out,
@@ -481,12 +481,13 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int *or
 	// reads them between the scan and the next tagging pass)
 	if (rearm && q < 3) { bbox[q] = INT_MAX; bbox[3 + q] = INT_MIN; }
 	if (q >= cnt.get()) return;
-	int s = order[q];
+	const int2 me = order[q];
+	int s = me.x;
 	int c = cellOfSlot[s];
 	int b = start[c], e = start[c + 1];
 	int g = gid_in[s];
 	int rank = 0;
-	for (int k = b; k < e; k++) rank += ((gid_in[order[k]] & GID_MASK) > (g & GID_MASK));
+	for (int k = b; k < e; k++) rank += (order[k].y > me.y);
 	int t = b + rank;
 	Particle p = load_particle(pos_in + s);
 	store_particle(pos_out + t, p);
@@ -1476,12 +1477,40 @@ __device__ __forceinline__ V3 diff_mi(const Particle &a, const Particle &b, cons
 	return d;
 }
 
+// Square root and reciprocal for the bonded force terms.  The reference divides by r = sqrt(d.d) fourteen times per
+// CHAIN triplet (MD.h:384-403, :683-723); IEEE sqrt / division sequences made the fused step kernel FP64-latency bound.
+// Here one MUFU.RSQ64H seed per distinct length gives r = sqrt(x) (correctly rounded, as in the pair kernel) and
+// 1 / r to full precision, and every quotient n / r is one multiply plus an exact-residual correction
+// (q = n * inv; q += fma(-r, q, n) * inv): correctly rounded except for vanishingly rare near-ties (then one ulp off).
+struct SqrtRcp { double r, inv; };
+
+__device__ __forceinline__ SqrtRcp sqrt_rcp(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	double e = __fma_rn(-(x * y), y, 1.0);
+	y = __fma_rn(0.5 * y, e, y);                              // 1/sqrt(x) to ~2^-43
+	double r = x * y;
+	r = __fma_rn(__fma_rn(-r, r, x), 0.5 * y, r);             // sqrt(x)
+	y = __fma_rn(__fma_rn(-r, y, 1.0), y, y);                 // 1/r, refined against the rounded r
+	y = __fma_rn(__fma_rn(-r, y, 1.0), y, y);
+	SqrtRcp o = {r, y};
+	if (!(x > 0.0) || x == INFINITY) { o.r = sqrt(x); o.inv = 1.0 / o.r; }   // coincident particles / NaN: IEEE root and reciprocal (the run is lost either way)
+	return o;
+}
+
+__device__ __forceinline__ double div_cr(double n, const SqrtRcp &d)
+{
+	double q = n * d.inv;
+	return __fma_rn(__fma_rn(-d.r, q, n), d.inv, q);
+}
+
 // MD.h:384-403 harmonicF: returns f with a1 += f, a2 -= f
 __device__ __forceinline__ V3 harmonic_f(V3 d, double r0, double k)
 {
-	double dr = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
-	double m = dr - r0;
-	m = -m * k / dr;
+	SqrtRcp dr = sqrt_rcp(d.x * d.x + d.y * d.y + d.z * d.z);
+	double m = dr.r - r0;
+	m = div_cr(-m * k, dr);
 	V3 f = {d.x * m, d.y * m, d.z * m};
 	return f;
 }
@@ -1497,16 +1526,16 @@ __device__ __forceinline__ double harmonic_p(V3 d, double r0, double k)
 // MD.h:683-723 bendF: a1 += fa ; a2 += (fb - fa) ; a3 -= fb
 __device__ __forceinline__ void bend_f(V3 da, V3 db, double c0, double k, V3 &fa, V3 &fb)
 {
-	double dra = sqrt(da.x * da.x + da.y * da.y + da.z * da.z);
-	double drb = sqrt(db.x * db.x + db.y * db.y + db.z * db.z);
-	da.x /= dra; da.y /= dra; da.z /= dra;
-	db.x /= drb; db.y /= drb; db.z /= drb;
+	const SqrtRcp dra = sqrt_rcp(da.x * da.x + da.y * da.y + da.z * da.z);
+	const SqrtRcp drb = sqrt_rcp(db.x * db.x + db.y * db.y + db.z * db.z);
+	da.x = div_cr(da.x, dra); da.y = div_cr(da.y, dra); da.z = div_cr(da.z, dra);
+	db.x = div_cr(db.x, drb); db.y = div_cr(db.y, drb); db.z = div_cr(db.z, drb);
 	double ct = (da.x * db.x) + (da.y * db.y) + (da.z * db.z);
 	double m = c0 - ct;
 	m *= k;
-	fa.x = m * (db.x - (da.x * ct)) / dra; fb.x = m * (da.x - (db.x * ct)) / drb;
-	fa.y = m * (db.y - (da.y * ct)) / dra; fb.y = m * (da.y - (db.y * ct)) / drb;
-	fa.z = m * (db.z - (da.z * ct)) / dra; fb.z = m * (da.z - (db.z * ct)) / drb;
+	fa.x = div_cr(m * (db.x - (da.x * ct)), dra); fb.x = div_cr(m * (da.x - (db.x * ct)), drb);
+	fa.y = div_cr(m * (db.y - (da.y * ct)), dra); fb.y = div_cr(m * (da.y - (db.y * ct)), drb);
+	fa.z = div_cr(m * (db.z - (da.z * ct)), dra); fb.z = div_cr(m * (da.z - (db.z * ct)), drb);
 }
 
 // MD.h:769-789 bendP
