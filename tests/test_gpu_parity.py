@@ -318,3 +318,24 @@ def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
         ctx.close()
     for u, w in zip(*out):
         assert np.array_equal(u, w)
+
+
+def test_async_snapshot_equals_blocking_readback(orc):
+    """smd_snapshot / smd_snapshot_wait (the writer thread's read-back) against smd_get_particles / smd_get_unwrapped,
+    with the device stepping on between the snapshot and the wait"""
+    m, _ = orc.load_golden(golden_path("bilayer_eq"))
+    ctx = sm.Context.from_dict(m, track_unwrapped=True)
+    ctx.compute_forces(mask=sm.MASK_ALL, step=0)
+    ctx.step(0, 5)
+    xyz, _, vel = ctx.get_particles()
+    unw = ctx.get_unwrapped()
+    w1 = ctx.snapshot(unwrapped=True)
+    ctx.step(5, 7)                       # overwrites the state the snapshot was taken from
+    w2 = ctx.snapshot()
+    a = w1()
+    assert np.array_equal(a[0], xyz) and np.array_equal(a[1], vel) and np.array_equal(a[2], unw)
+    xyz2, _, vel2 = ctx.get_particles()
+    b = w2()
+    assert np.array_equal(b[0], xyz2) and np.array_equal(b[1], vel2)
+    assert not np.array_equal(xyz, xyz2)
+    ctx.close()
