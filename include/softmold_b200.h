@@ -40,15 +40,20 @@ enum {
 };
 
 /* molecule type ids, identical to the reference enum (include/algorithms/molecules.h:6-40) */
-enum { SMD_MOL_BOND = 6, SMD_MOL_BEND = 7, SMD_MOL_CHAIN = 8, SMD_MOL_BEAD = 9, SMD_MOL_BALL = 19 };
+enum { SMD_MOL_BOND = 6, SMD_MOL_BEND = 7, SMD_MOL_CHAIN = 8, SMD_MOL_BEAD = 9, SMD_MOL_SOLID = 10, SMD_MOL_BOUNDARY = 11,
+       SMD_MOL_RIGIDBEND = 12, SMD_MOL_PULLBEAD = 13, SMD_MOL_OFFSET_BOUNDARY = 14, SMD_MOL_FLOATING_BASE = 15,
+       SMD_MOL_ZTORQUE = 16, SMD_MOL_ZPOWERPOTENTIAL = 17, SMD_MOL_NANOCORE = 18, SMD_MOL_BALL = 19 };
 
 /* energy / force terms.  Bit masks select terms in smd_compute_forces; indices address out_terms[] arrays. */
 enum { SMD_TERM_PAIR = 0, SMD_TERM_CHAIN = 1, SMD_TERM_BOND = 2, SMD_TERM_BEND = 3, SMD_TERM_BEAD = 4,
-       SMD_TERM_BALL = 5, SMD_NTERMS = 8 };
+       SMD_TERM_BALL = 5,
+       SMD_TERM_FIELD = 6,      /* BOUNDARY + FLOATING_BASE + ZTORQUE + ZPOWERPOTENTIAL: one-body / orientation fields */
+       SMD_TERM_NANOCORE = 7, SMD_NTERMS = 8 };
 #define SMD_MASK(term) (1u << (term))
 #define SMD_MASK_LANGEVIN (1u << 16)
 #define SMD_MASK_ALL_MOLECULES (SMD_MASK(SMD_TERM_CHAIN) | SMD_MASK(SMD_TERM_BOND) | SMD_MASK(SMD_TERM_BEND) | \
-                                SMD_MASK(SMD_TERM_BEAD) | SMD_MASK(SMD_TERM_BALL))
+                                SMD_MASK(SMD_TERM_BEAD) | SMD_MASK(SMD_TERM_BALL) | SMD_MASK(SMD_TERM_FIELD) | \
+                                SMD_MASK(SMD_TERM_NANOCORE))
 #define SMD_MASK_ALL (SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_ALL_MOLECULES | SMD_MASK_LANGEVIN)
 
 /* Langevin noise source */
@@ -103,12 +108,31 @@ int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t *type, cons
  *   BOND   c[2] = {r0, k},           ij[n][2]                                                 (system.h:1880-1934)
  *   BEND   c[2] = {cosTheta0, k},    ijk[n][3]                                                (system.h:1975-2040)
  *   BEAD   C[22*nTypes^2],           idx[n]                                                   (system.h:2043-2212)
- *   BALL   c[2] = {r0, k},           cj[n][2] = {centre, j}                                   (system.h:1936-1971) */
+ *   BALL   c[2] = {r0, k},           cj[n][2] = {centre, j}                                   (system.h:1936-1971)
+ * and the remaining kinds of MD.cpp's switch (MD.cpp:414-478), none of which takes part in the box move (MD.cpp:642-669):
+ *   BOUNDARY         c[4] = {dim, centre, unused, k},   idx[n]                                (system.h:2334-2348, MD.h:543-626)
+ *   FLOATING_BASE    C[6*nTypes] (row = particle type), idx[n]                                (system.h:2402-2446, MD.h:457-494)
+ *   ZTORQUE          c[4] = {a, b, c, d},               blocks[n][3] = {start, nChains, length}  (system.h:2582-2663, MD.h:1116-1140)
+ *   ZPOWERPOTENTIAL  c[2] = {k, n},                     blocks[n][2] = {start, count}         (system.h:2665-2715, MD.h:1142-1153)
+ *   NANOCORE         C[22*n] (one bead row per bead),   idx[n]                                (system.h:2215-2332, :3028-3075, :3708-3760)
+ * SOLID, OFFSET_BOUNDARY, RIGIDBEND and PULLBEAD are parsed by the reference but do nothing in `MD` (default case of the
+ * switch): smd_create_from_mpd accepts and skips them. */
 int smd_add_chain(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[4]);
 int smd_add_bonds(smd_ctx *ctx, int32_t n, const int32_t *ij, const double c[2]);
 int smd_add_bends(smd_ctx *ctx, int32_t n, const int32_t *ijk, const double c[2]);
 int smd_add_beads(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C);
 int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const double c[2]);
+int smd_add_boundary(smd_ctx *ctx, int32_t n, const int32_t *idx, const double c[4]);
+int smd_add_floating_base(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C);
+int smd_add_ztorque(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[4]);
+int smd_add_zpower(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[2]);
+int smd_add_nanocore(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C);
+
+/* Per-type friction, the `gammaType` command (MD.cpp:134-138, Langevin::compute algorithms/langevin.h:236-281).  What the
+ * reference does with it, reproduced: the type lookup is commented out (`int type=0;//p[i].type;`), so EVERY particle
+ * gets gamma_type[0]; and the noise amplitudes sT[] are computed once, at the temperature of the first evaluation, so a
+ * later temperature ramp does not change them.  Replaces desc.gamma. */
+int smd_set_gamma_type(smd_ctx *ctx, int32_t n_types, const double *gamma_type);
 
 /* temperature may be ramped by the driver (MD.cpp:369-371) */
 int smd_set_temperature(smd_ctx *ctx, double temperature);
@@ -156,7 +180,9 @@ int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3]);
 
 /* One Metropolis box-move trial exactly as MD.cpp:589-721 given the two rand53 draws the reference takes from
  * MTRand randNum(seed): u_fluct (:595) and u_accept (:688).  Returns accepted (0/1), the total dPotential incl.
- * tension*dA, and the box after the trial. */
+ * tension*dA, and the box after the trial.  As in MD.cpp:657-666 the BALL and NANOCORE terms of smd_dpotential are
+ * evaluated but NOT part of the Metropolis sum (the reference drops the return value), and the one-body fields have
+ * no dPotential at all. */
 int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, double u_fluct, double u_accept,
                     int32_t *accepted, double *dU_total, double box_out[3]);
 

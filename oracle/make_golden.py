@@ -194,6 +194,71 @@ def ball():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def spangler_row(rc, rm, rad, density, Umax, Umin):
+    """one 22-constant bead row (potentials/laradjiSpangler.h:186-223, laradjiSpanglerFCrow)"""
+    D = density * np.pi * rad
+    A = Umax - Umin
+    out = [rc + rad, -7.0 / 4.0 * rm, 2.0 * rm * rm, Umin * np.pi * rad * density / (rm * rm * rm), rad, rm,
+           -D * A / (2.0 * rm * rm), 2.0 * D * A / (3.0 * rm), -D * Umin, 2.0 * D * Umin * rm, D * 1.3 * Umin * rm * rm]
+    D = (2.0 * np.pi * density * rad) ** 2.0 / (rm * rm * rm)
+    out += [2.0 * rad + rm, 2.0 * rad + rc, Umin * D * 2.0 / 30.0, -Umin * D * 7.0 * rm / 20.0, Umin * D * rm * rm / 2.0,
+            -D * A * rm / 20.0, D * A * rm * rm / 12.0, -D * Umin * rm ** 3.0 / 6.0, D * Umin * rm ** 4.0 / 2.0,
+            D * 1.3 * Umin * rm ** 5.0 / 2.0, D * 13.0 * Umin * rm ** 6.0 / 60.0]
+    return out
+
+
+def fields():
+    """The remaining molecule kinds of MD.cpp's switch (MD.cpp:414-478): BOUNDARY, FLOATING_BASE, ZTORQUE, ZPOWERPOTENTIAL,
+    NANOCORE (+ a BALL, + the kinds MD parses and ignores: SOLID, OFFSET_BOUNDARY), on the equilibrated periodic flat
+    bilayer of bilayer_eq WITH Metropolis box moves, so that the 24-step trajectory of the reference `MD` also pins which
+    terms take part in the box move (none of these: MD.cpp:642-669 drops the NANOCORE and BALL results)."""
+    tmp = tempfile.mkdtemp(prefix="golden_fields_")
+    try:
+        m, _ = orc.load_golden(os.path.join(OUT, "bilayer_eq.npz"))
+        m = dict(m)
+        n, nT = m["nParticles"], m["nTypes"]
+        xyz, typ = m["xyz"], m["type"]
+        z = xyz[:, 2]
+        zmid = float(np.median(z))
+        ch = m["molecules"][0]
+        # two nanocore particles (type 1) above and below the bilayer, within range of the head groups
+        top, bot = float(z.max()), float(z.min())
+        cx, cy = m["size"][0] / 2, m["size"][1] / 2
+        extra = np.array([[cx, cy, top + 3.45], [cx * 0.4, cy * 1.3, bot - 4.4]])   # gap R + 1.4: the attractive tail
+        m["xyz"] = np.vstack([xyz, extra])
+        m["vel"] = np.vstack([m["vel"], [[0.05, -0.1, 0.02], [-0.03, 0.04, 0.01]]])
+        m["type"] = np.append(typ, [1, 1]).astype(np.int32)
+        m["nParticles"] = n + 2
+        z = m["xyz"][:, 2]
+        heads = np.where(m["type"][:n] == 2)[0]
+        low = heads[np.argsort(z[heads])[:120]]          # lowest head groups
+        wall = float(z[low].min()) - 1.05                 # |d| from 1.05 upwards: some inside sqrt(2), none near 0
+        fb = np.zeros((nT, 6))
+        for t in range(nT):
+            fb[t] = [zmid - 0.4 + 0.1 * t, zmid + 1.6 + 0.05 * t, 0.0002 * (t + 1), 1e-6 * (t + 1), 0.3, 0.0015 * (t + 1)]
+        mols = list(m["molecules"])
+        mols.append({"type": orc.BOUNDARY, "constants": np.array([2.0, wall, 0.0, 0.35]), "bonds": low.reshape(-1, 1).astype(np.int32)})
+        mols.append({"type": orc.FLOATING_BASE, "constants": fb.ravel(), "bonds": np.arange(1, n, 3, dtype=np.int32).reshape(-1, 1)})
+        mols.append({"type": orc.ZTORQUE, "constants": np.array([0.8, 0.5, 0.7, zmid + 0.3]), "bonds": ch["bonds"].astype(np.int32)})
+        mols.append({"type": orc.ZPOWER, "constants": np.array([-3.0 * 0.000085 / 4.0, 2.1]), "bonds": np.array([[0, 150], [300, 77]], np.int32)})
+        mols.append({"type": orc.NANOCORE, "constants": np.array(spangler_row(2.0, 1.0, 2.0, 5.88, 100.0, -0.5) +
+                                                                  spangler_row(2.0, 1.0, 3.0, 5.88, 100.0, -0.3)),
+                     "bonds": np.array([[n], [n + 1]], np.int32)})
+        mols.append({"type": orc.BALL, "constants": np.array([4.0, 15.0]), "bonds": np.array([[n, int(j)] for j in heads[::7]], np.int32)})
+        mols.append({"type": orc.SOLID, "constants": np.array([1.0]), "bonds": np.array([[3], [4]], np.int32)})
+        mols.append({"type": orc.OFFSET_BOUNDARY, "constants": np.array([2.0, wall, 1.0, 0.35]), "bonds": low[:10].reshape(-1, 1).astype(np.int32)})
+        m["molecules"] = mols
+        m["nMolecules"] = len(mols)
+        orc.write_mpd(os.path.join(tmp, "fields.mpd"), m)
+        t, _ = traj(tmp, m, "fields_run", 24)   # restart path (initialTime != 0) + MC trials
+        g = harness(tmp, "fields", (1.0004, 1.0004, 1.0 / 1.0004 ** 2))
+        for k, mol in enumerate(mols):
+            print(k, mol["type"], "U", g["U_mol"][k], "dU", g["dU_mol"][k], "max|a|", np.abs(g[f"a_mol{k}"]).max())
+        save("fields", pack(m, g, t))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def stats():
     """long-run observables of the reference `MD` executable itself: a tensionless flat bilayer with box moves, 20 000
     steps, two independent runs (seeds 99 / 100, 8 OpenMP threads).  tests/golden/stat_bilayer.npz holds the input
@@ -229,4 +294,4 @@ def stats():
 
 
 if __name__ == "__main__":
-    {"stats": stats, "ball": ball}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()
+    {"stats": stats, "ball": ball, "fields": fields}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()

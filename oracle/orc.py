@@ -55,6 +55,23 @@ def lib():
             getattr(L, f"orc_{nm}_potential").restype = C.c_double
             getattr(L, f"orc_{nm}_dpotential").argtypes = [_dp, d3, C.c_int, _ip, d2, d3]
             getattr(L, f"orc_{nm}_dpotential").restype = C.c_double
+        L.orc_boundary_force.argtypes = [_dp, d3, C.c_int, _ip, d4, _dp]
+        L.orc_boundary_potential.argtypes = [_dp, d3, C.c_int, _ip, d4]
+        L.orc_boundary_potential.restype = C.c_double
+        L.orc_floating_base_force.argtypes = [_dp, _ip, C.c_int, _ip, _dp, _dp]
+        L.orc_floating_base_potential.argtypes = [_dp, _ip, C.c_int, _ip, _dp]
+        L.orc_floating_base_potential.restype = C.c_double
+        L.orc_ztorque_force.argtypes = [_dp, d3, C.c_int, _ip, d4, _dp]
+        L.orc_ztorque_potential.argtypes = [_dp, d3, C.c_int, _ip, d4]
+        L.orc_ztorque_potential.restype = C.c_double
+        L.orc_zpower_force.argtypes = [_dp, C.c_int, _ip, d2, _dp]
+        L.orc_zpower_potential.argtypes = [_dp, C.c_int, _ip, d2]
+        L.orc_zpower_potential.restype = C.c_double
+        L.orc_nanocore_force.argtypes = [C.c_int, _dp, d3, C.c_int, _ip, _dp, _dp]
+        L.orc_nanocore_potential.argtypes = [C.c_int, _dp, d3, C.c_int, _ip, _dp]
+        L.orc_nanocore_potential.restype = C.c_double
+        L.orc_nanocore_dpotential.argtypes = [C.c_int, _dp, d3, C.c_int, _ip, _dp, d3]
+        L.orc_nanocore_dpotential.restype = C.c_double
         L.orc_bead_force.argtypes = [C.c_int, _dp, _ip, C.c_int, d3, C.c_int, C.c_int, _ip, _dp, _dp]
         L.orc_bead_potential.argtypes = [C.c_int, _dp, _ip, C.c_int, d3, C.c_int, C.c_int, _ip, _dp]
         L.orc_bead_potential.restype = C.c_double
@@ -181,6 +198,7 @@ class _Sys(C.Structure):
 
 
 BOND, BEND, CHAIN, BEAD, BALL = 6, 7, 8, 9, 19
+SOLID, BOUNDARY, RIGIDBEND, PULLBEAD, OFFSET_BOUNDARY, FLOATING_BASE, ZTORQUE, ZPOWER, NANOCORE = 10, 11, 12, 13, 14, 15, 16, 17, 18
 
 
 class System:
@@ -280,7 +298,19 @@ def read_dump(path):
     return out
 
 
-_MOL_SHAPE = {BOND: (2, 2), BEND: (2, 3), CHAIN: (4, 3), 19: (2, 2)}  # type -> (nConstants, ints per bond record)
+# type -> (nConstants, ints per bond record), system.h:1036-1120; BEAD / FLOATING_BASE / NANOCORE depend on nTypes / nBonds
+_MOL_SHAPE = {BOND: (2, 2), BEND: (2, 3), CHAIN: (4, 3), BALL: (2, 2), SOLID: (1, 1), BOUNDARY: (4, 1), OFFSET_BOUNDARY: (4, 1),
+              RIGIDBEND: (5, 2), PULLBEAD: (4, 1), ZTORQUE: (4, 3), ZPOWER: (2, 2)}
+
+
+def mol_shape(t, nTypes, nBonds):
+    if t == BEAD:
+        return 22 * nTypes ** 2, 1
+    if t == FLOATING_BASE:
+        return 6 * nTypes, 1
+    if t == NANOCORE:
+        return 22 * nBonds, 1
+    return _MOL_SHAPE[t]
 
 
 def read_mpd(path):
@@ -319,12 +349,15 @@ def read_mpd(path):
             for _ in range(m["nMolecules"]):
                 t, nb = int(tok[i]), int(tok[i + 1])
                 i += 2
-                ncst, width = (22 * m["nTypes"] ** 2, 1) if t == BEAD else _MOL_SHAPE[t]
+                ncst, width = mol_shape(t, m["nTypes"], nb)
                 c = np.array(tok[i:i + ncst], np.float64)
                 i += ncst
                 b = np.array(tok[i:i + nb * width], np.int32).reshape(nb, width)
                 i += nb * width
                 m["molecules"].append({"type": t, "constants": c, "bonds": b})
+        elif w == "gammaType":
+            m[w] = [float(t) for t in tok[i:i + m["nTypes"]]]
+            i += m["nTypes"]
         elif w == "banana":
             pass
         else:
@@ -361,6 +394,8 @@ def write_mpd(path, m):
         for k in ("deltaLXY", "removeSolvent", "tempStepInterval", "tension"):
             if k in m:
                 f.write(f"{k} {r(m[k])}\n")
+        if "gammaType" in m:
+            f.write("gammaType " + " ".join(r(x) for x in m["gammaType"]) + "\n")
 
 
 def load_golden(path):

@@ -137,6 +137,11 @@ static int cmd_dump(int argc, char **argv)
 		case CHAIN: S.doChainForce(k); U[k] = S.doChainPotential(k); dU[k] = S.doChainDPotential(k, scale); break;
 		case BEAD:  S.doBeadForce(k);  U[k] = S.doBeadPotential(k);  dU[k] = S.doBeadDPotential(k, scale);  break;
 		case BALL:  S.doBallForce(k);  U[k] = S.doBallPotential(k);  dU[k] = S.doBallDPotential(k, scale);  break;
+		case BOUNDARY:        S.doBoundaryForce(k);     U[k] = S.doBoundaryPotential(k);     break;
+		case FLOATING_BASE:   S.doFloatingBaseForce(k); U[k] = S.doFloatingBasePotential(k); break;
+		case ZTORQUE:         S.doZTorqueForce(k);      U[k] = S.doZTorquePotential(k);      break;
+		case ZPOWERPOTENTIAL: S.doZPowerForce(k);       U[k] = S.doZPowerPotential(k);       break;
+		case NANOCORE: S.doNanoCoreForce(k); U[k] = S.doNanoCorePotential(k); dU[k] = S.doNanoCoreDPotential(k, scale); break;
 		default: break;
 		}
 		snprintf(nm, sizeof nm, "a_mol%d", k);

@@ -5,5 +5,6 @@ boundary) and the `MD_b200` host driver.  This package only binds the C ABI for 
 There is no CPU fallback: `capi.lib()` raises when the library has not been built, and every compute call raises
 when no B200-class GPU is usable."""
 from .capi import (Context, Mpd, SoftMoldError, lib, LIB_PATH, SYMBOLS, MASK_ALL, MASK_ALL_MOLECULES, MASK_LANGEVIN,  # noqa: F401
-                   TERM_PAIR, TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL, NTERMS, NOISE_PHILOX,
-                   NOISE_EXTERNAL, MOL_BOND, MOL_BEND, MOL_CHAIN, MOL_BEAD, MOL_BALL, PHASES)
+                   TERM_PAIR, TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL, TERM_FIELD, TERM_NANOCORE, NTERMS, NOISE_PHILOX,
+                   NOISE_EXTERNAL, MOL_BOND, MOL_BEND, MOL_CHAIN, MOL_BEAD, MOL_BALL, MOL_BOUNDARY, MOL_FLOATING_BASE, MOL_ZTORQUE,
+                   MOL_ZPOWERPOTENTIAL, MOL_NANOCORE, MOL_IGNORED, PHASES)

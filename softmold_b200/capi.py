@@ -13,9 +13,12 @@ LIB_PATH = os.environ.get("SOFTMOLD_B200_LIB") or os.path.join(HERE, "libsoftmol
 
 SMD_OK, SMD_ERR_ARG, SMD_ERR_CUDA, SMD_ERR_CELL, SMD_ERR_IO, SMD_ERR_UNSUPPORTED = range(6)
 MOL_BOND, MOL_BEND, MOL_CHAIN, MOL_BEAD, MOL_BALL = 6, 7, 8, 9, 19
-TERM_PAIR, TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL, NTERMS = 0, 1, 2, 3, 4, 5, 8
+MOL_SOLID, MOL_BOUNDARY, MOL_RIGIDBEND, MOL_PULLBEAD, MOL_OFFSET_BOUNDARY = 10, 11, 12, 13, 14
+MOL_FLOATING_BASE, MOL_ZTORQUE, MOL_ZPOWERPOTENTIAL, MOL_NANOCORE = 15, 16, 17, 18
+MOL_IGNORED = (MOL_SOLID, MOL_RIGIDBEND, MOL_PULLBEAD, MOL_OFFSET_BOUNDARY)   # `MD` parses them and does nothing (MD.cpp:414-478)
+TERM_PAIR, TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL, TERM_FIELD, TERM_NANOCORE, NTERMS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 MASK_LANGEVIN = 1 << 16
-MASK_ALL_MOLECULES = sum(1 << t for t in (TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL))
+MASK_ALL_MOLECULES = sum(1 << t for t in (TERM_CHAIN, TERM_BOND, TERM_BEND, TERM_BEAD, TERM_BALL, TERM_FIELD, TERM_NANOCORE))
 MASK_ALL = (1 << TERM_PAIR) | MASK_ALL_MOLECULES | MASK_LANGEVIN
 NOISE_PHILOX, NOISE_EXTERNAL = 0, 1
 ABI_VERSION = 2
@@ -25,6 +28,7 @@ SLAB_HALO = 2
 SYMBOLS = [
     "smd_abi_version", "smd_last_error", "smd_device_count", "smd_create", "smd_destroy", "smd_set_pair_tables",
     "smd_set_particles", "smd_add_chain", "smd_add_bonds", "smd_add_bends", "smd_add_beads", "smd_add_ball",
+    "smd_add_boundary", "smd_add_floating_base", "smd_add_ztorque", "smd_add_zpower", "smd_add_nanocore", "smd_set_gamma_type",
     "smd_set_temperature", "smd_set_noise", "smd_build_cells", "smd_compute_forces", "smd_resume", "smd_step",
     "smd_step_begin", "smd_step_end", "smd_potential", "smd_kinetic", "smd_dpotential", "smd_rescale",
     "smd_mc_box_move", "smd_get_particles", "smd_get_forces", "smd_get_unwrapped", "smd_get_box", "smd_get_cell_ids",
@@ -81,6 +85,9 @@ def lib():
         L.smd_add_bends.argtypes = [vp, i32, vp, vp]
         L.smd_add_beads.argtypes = [vp, i32, vp, vp]
         L.smd_add_ball.argtypes = [vp, i32, vp, vp]
+        for nm in ("boundary", "floating_base", "ztorque", "zpower", "nanocore"):
+            getattr(L, "smd_add_" + nm).argtypes = [vp, i32, vp, vp]
+        L.smd_set_gamma_type.argtypes = [vp, i32, vp]
         L.smd_set_temperature.argtypes = [vp, dbl]
         L.smd_set_noise.argtypes = [vp, vp]
         L.smd_build_cells.argtypes = [vp]
@@ -265,10 +272,18 @@ class Context:
         r, c = _i32(records), _f64(constants)
         n = len(r)
         f = {MOL_CHAIN: self.L.smd_add_chain, MOL_BOND: self.L.smd_add_bonds, MOL_BEND: self.L.smd_add_bends,
-             MOL_BEAD: self.L.smd_add_beads, MOL_BALL: self.L.smd_add_ball}.get(int(mtype))
+             MOL_BEAD: self.L.smd_add_beads, MOL_BALL: self.L.smd_add_ball, MOL_BOUNDARY: self.L.smd_add_boundary,
+             MOL_FLOATING_BASE: self.L.smd_add_floating_base, MOL_ZTORQUE: self.L.smd_add_ztorque,
+             MOL_ZPOWERPOTENTIAL: self.L.smd_add_zpower, MOL_NANOCORE: self.L.smd_add_nanocore}.get(int(mtype))
+        if int(mtype) in MOL_IGNORED:
+            return
         if f is None:
             raise SoftMoldError(SMD_ERR_UNSUPPORTED, f"molecule type {mtype} is outside the hot path")
         self._ck(f(self.h, n, _ptr(r), _ptr(c)))
+
+    def set_gamma_type(self, gamma_type):
+        g = _f64(gamma_type)
+        self._ck(self.L.smd_set_gamma_type(self.h, len(g), _ptr(g)))
 
     def set_temperature(self, T):
         self.temperature = float(T)

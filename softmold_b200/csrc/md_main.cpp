@@ -18,8 +18,8 @@
 // in the same order (one FIFO); SMD_SYNC_IO=1 does the work inline instead (A/B timing).
 //
 // Differences, all deliberate: the Langevin noise is the counter-based Philox stream of the library (the reference's
-// depends on the OpenMP thread count); gammaType (per-type friction) and the molecule kinds outside the
-// hot path are refused loudly instead of silently ignored; environment variable SMD_DEVICE picks the GPU.
+// depends on the OpenMP thread count); the old-style molecule kinds MD itself cannot parse (TORSION,
+// DIHEDRAL, ...) are refused loudly; environment variable SMD_DEVICE picks the GPU.
 #include <algorithm>
 #include <charconv>
 #include <chrono>
@@ -288,7 +288,7 @@ struct Driver {
 					costhetaBend += (da[0] * db[0] + da[1] * db[1] + da[2] * db[2]) / (ra * rb);
 				}
 				nBend += m.n;
-			} else if (m.type == SMD_MOL_BEAD) {
+			} else if (m.type == SMD_MOL_BEAD || m.type == SMD_MOL_NANOCORE) {   // dataExtraction.h:936-942, :971-978
 				nBeads++;
 			}
 		}
@@ -297,7 +297,7 @@ struct Driver {
 		line(time_now, "lBond_", lBond / (double)nBond);
 		if (nBend > 1) { costhetaBend /= nBend; lBend[0] /= nBend; lBend[1] /= nBend; }
 		line(time_now, "bend_", costhetaBend, lBend[0], lBend[1]);
-		if (nBeads > 0) line(time_now, "beadPotential_", terms[SMD_TERM_BEAD]);
+		if (nBeads > 0) line(time_now, "beadPotential_", terms[SMD_TERM_BEAD] + terms[SMD_TERM_NANOCORE]);
 		line(time_now, "temp_", temperature);
 		line(time_now, "kinetic_", kinetic);
 
@@ -389,9 +389,8 @@ int main(int argc, char *argv[])
 	const double gamma = scalar(M, "gamma"), dt = scalar(M, "deltaT");
 	bool has_gamma_type = false;
 	scalar(M, "gammaType", &has_gamma_type);
-	if (!(gamma > 0)) {
-		if (has_gamma_type) std::cout << "Error(main): per-type friction (gammaType) is outside the hot path of this build\n";
-		else std::cout << "Error(main): No gamma available!\n";   // MD.cpp:139-143
+	if (!(gamma > 0) && !has_gamma_type) {   // MD.cpp:129-143: gamma, else gammaType (smd_set_gamma_type), else give up
+		std::cout << "Error(main): No gamma available!\n";
 		return 0;
 	}
 	const uint32_t seed = (uint32_t)scalar(M, "seed");

@@ -537,7 +537,8 @@ extern "C" int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, in
 	for (int k = 0; k < 3; k++) d.box[k] = m->size[k];
 	d.cutoff = m->scalar[CUTOFF];
 	d.dt = m->scalar[DELTAT];
-	d.gamma = m->scalar[GAMMA];
+	const bool per_type = !(m->scalar[GAMMA] > 0) && !m->gammaType.empty();   // MD.cpp:129-138: gamma first, gammaType second
+	d.gamma = per_type ? m->gammaType[0] : m->scalar[GAMMA];
 	d.temperature = m->scalar[INITIALTEMP];
 	d.seed = (uint64_t)(long long)m->scalar[SEED];
 	d.noise = noise;
@@ -549,6 +550,7 @@ extern "C" int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, in
 	*out = ctx;   // handed out even on later failure so the caller can read smd_last_error and destroy
 	if (m->fC.empty() || m->uC.empty()) return SMD_ERR_ARG;
 	if ((rc = smd_set_pair_tables(ctx, m->fC.data(), m->uC.data()))) return rc;
+	if (per_type && (rc = smd_set_gamma_type(ctx, (int32_t)m->gammaType.size(), m->gammaType.data()))) return rc;
 	if ((rc = smd_set_particles(ctx, m->xyz.data(), m->type.data(), m->vel.data()))) return rc;
 	for (auto &mol : m->mol) {
 		switch (mol.type) {
@@ -557,6 +559,13 @@ extern "C" int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, in
 		case SMD_MOL_BEND: rc = smd_add_bends(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
 		case SMD_MOL_BEAD: rc = smd_add_beads(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
 		case SMD_MOL_BALL: rc = smd_add_ball(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
+		case SMD_MOL_BOUNDARY: rc = smd_add_boundary(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
+		case SMD_MOL_FLOATING_BASE: rc = smd_add_floating_base(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
+		case SMD_MOL_ZTORQUE: rc = smd_add_ztorque(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
+		case SMD_MOL_ZPOWERPOTENTIAL: rc = smd_add_zpower(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
+		case SMD_MOL_NANOCORE: rc = smd_add_nanocore(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
+		// parsed and written back by the reference, but `MD` does nothing with them (default case of MD.cpp:414-478)
+		case SMD_MOL_SOLID: case SMD_MOL_OFFSET_BOUNDARY: case SMD_MOL_RIGIDBEND: case SMD_MOL_PULLBEAD: rc = SMD_OK; break;
 		default: rc = SMD_ERR_UNSUPPORTED;
 		}
 		if (rc) return rc;

@@ -377,6 +377,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto &b : ctx->bends) cudaFree(b.d_ijk);
 	for (auto &b : ctx->balls) cudaFree(b.d_cj);
 	for (auto &b : ctx->beads) { cudaFree(b.d_beads); cudaFree(b.d_C); }
+	for (auto &f : ctx->fields) { cudaFree(f.d_idx); cudaFree(f.d_C); }
 	prof_drain(ctx);
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
@@ -651,6 +652,115 @@ extern "C" int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const do
 	return SMD_OK;
 }
 
+// ---- the remaining molecule kinds of MD.cpp's switch (MD.cpp:414-478): one-body fields and NANOCORE
+static int add_field(smd_ctx *ctx, int kind, int32_t n, const int32_t *idx, const double *c, int nc_host, const double *C, size_t nC,
+                     const int32_t *blocks, int width, const char *what)
+{
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
+	CK(cudaSetDevice(ctx->device));
+	FieldMol f;
+	f.kind = kind; f.n = n; f.d_idx = nullptr; f.d_C = nullptr;
+	for (int k = 0; k < 4; k++) f.c[k] = (c && k < nc_host) ? c[k] : 0.0;
+	if (idx) {
+		int rc = check_index(ctx, idx, (size_t)n, what);
+		if (rc) return rc;
+		rc = upload_list<int>(ctx, idx, (size_t)n, &f.d_idx);
+		if (rc) return rc;
+	}
+	if (blocks) f.blocks.assign(blocks, blocks + (size_t)n * width);
+	if (C && nC) {
+		CK(cudaMalloc(&f.d_C, nC * sizeof(double)));
+		CK(cudaMemcpy(f.d_C, C, nC * sizeof(double), cudaMemcpyHostToDevice));
+	}
+	ctx->fields.push_back(f);
+	ctx->n_molecules++;
+	return SMD_OK;
+}
+
+extern "C" int smd_add_boundary(smd_ctx *ctx, int32_t n, const int32_t *idx, const double c[4])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (idx || n == 0) && c, "bad BOUNDARY arguments");
+	int dim = (int)c[0];   // static_cast<int>(constants[0]), MD.h:569
+	REQUIRE(dim >= 0 && dim <= 2, "BOUNDARY: constants[0] must name an axis (0, 1 or 2)");
+	return add_field(ctx, SMD_MOL_BOUNDARY, n, idx, c, 4, nullptr, 0, nullptr, 0, "BOUNDARY Molecule");
+}
+
+extern "C" int smd_add_floating_base(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (idx || n == 0) && C, "bad FLOATING_BASE arguments");
+	return add_field(ctx, SMD_MOL_FLOATING_BASE, n, idx, nullptr, 0, C, 6 * (size_t)ctx->nT, nullptr, 0, "FLOATING_BASE Molecule");
+}
+
+extern "C" int smd_add_ztorque(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[4])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n_blocks >= 0 && (blocks || n_blocks == 0) && c, "bad ZTORQUE arguments");
+	for (int j = 0; j < n_blocks; j++) {
+		long long start = blocks[3 * j], nCh = blocks[3 * j + 1], len = blocks[3 * j + 2];
+		REQUIRE(start >= 0 && nCh >= 0 && len >= 0 && start + nCh * len <= ctx->n_global, "ZTORQUE Molecule is out of bounds!");
+	}
+	return add_field(ctx, SMD_MOL_ZTORQUE, n_blocks, nullptr, c, 4, nullptr, 0, blocks, 3, "ZTORQUE Molecule");
+}
+
+extern "C" int smd_add_zpower(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[2])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n_blocks >= 0 && (blocks || n_blocks == 0) && c, "bad ZPOWERPOTENTIAL arguments");
+	for (int j = 0; j < n_blocks; j++) {
+		long long start = blocks[2 * j], cnt = blocks[2 * j + 1];
+		REQUIRE(start >= 0 && cnt >= 0 && start + cnt <= ctx->n_global, "ZPOWERPOTENTIAL Molecule is out of bounds!");
+	}
+	return add_field(ctx, SMD_MOL_ZPOWERPOTENTIAL, n_blocks, nullptr, c, 2, nullptr, 0, blocks, 2, "ZPOWERPOTENTIAL Molecule");
+}
+
+extern "C" int smd_add_nanocore(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (idx || n == 0) && (C || n == 0), "bad NANOCORE arguments");
+	return add_field(ctx, SMD_MOL_NANOCORE, n, idx, nullptr, 0, C, 22 * (size_t)n, nullptr, 0, "NANOCORE Molecule");
+}
+
+// force (MODE 0) or potential (MODE 1; partial sums finished by `done(blocks, term)`) of one field molecule
+template <int MODE, class Done>
+static int launch_field(smd_ctx *ctx, const FieldMol &f, const Particle *pos, Done done)
+{
+	double *acc = MODE == 0 ? ctx->acc : nullptr, *part = MODE == 0 ? nullptr : ctx->partials;
+	switch (f.kind) {
+	case SMD_MOL_BOUNDARY:
+		if (f.n <= 0) break;
+		LAUNCH(k_boundary<MODE>, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, ctx->geom, f.d_idx, (int)f.c[0], f.c[1], f.c[3], acc, part);
+		done(nblk(f.n, TPB), SMD_TERM_FIELD);
+		break;
+	case SMD_MOL_FLOATING_BASE:
+		if (f.n <= 0) break;
+		LAUNCH(k_floating_base<MODE>, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, f.d_idx, f.d_C, acc, part);
+		done(nblk(f.n, TPB), SMD_TERM_FIELD);
+		break;
+	case SMD_MOL_ZTORQUE:
+		for (int j = 0; j < f.n; j++) {
+			int start = f.blocks[3 * j], nCh = f.blocks[3 * j + 1], len = f.blocks[3 * j + 2];
+			long long nt = (long long)nCh * (len - 2);
+			if (len < 3 || nt <= 0) continue;
+			LAUNCH(k_ztorque<MODE>, nblk((int)nt, TPB), TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, start, nCh, len, f.c[0], f.c[1], f.c[2], f.c[3],
+			       acc, part);
+			done(nblk((int)nt, TPB), SMD_TERM_FIELD);
+		}
+		break;
+	case SMD_MOL_ZPOWERPOTENTIAL:
+		for (int j = 0; j < f.n; j++) {
+			int start = f.blocks[2 * j], cnt = f.blocks[2 * j + 1];
+			if (cnt <= 0) continue;
+			LAUNCH(k_zpower<MODE>, nblk(cnt, TPB), TPB, 0, cnt, ctx->cap, pos, ctx->slot_of, start, f.c[0], f.c[1], acc, part);
+			done(nblk(cnt, TPB), SMD_TERM_FIELD);
+		}
+		break;
+	default: break;
+	}
+	return SMD_OK;
+}
+
 // rebuild the assembled bead lists: molecule i sees its own beads followed by those of every later BEAD molecule
 static int rebuild_bead_lists(smd_ctx *ctx)
 {
@@ -783,9 +893,26 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 			LAUNCH(k_beadbead<0>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius,
 			       ctx->acc, nullptr, 1.0, 1.0, 1.0);
 			LAUNCH(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
-			       b.d_beads, b.d_C, b.nOwn <= 20 ? 1 : 0, ctx->acc, nullptr, 1.0, 1.0, 1.0);
+			       b.d_beads, b.d_C, b.nOwn <= 20 ? 1 : 0, 0, ctx->acc, nullptr, 1.0, 1.0, 1.0);
 		}
+	if (mask & SMD_MASK(SMD_TERM_FIELD))
+		for (auto &f : ctx->fields) {
+			int rc = launch_field<0>(ctx, f, pos, [](int, int) {});
+			if (rc) return rc;
+		}
+	if (mask & SMD_MASK(SMD_TERM_NANOCORE))
+		for (auto &f : ctx->fields)
+			if (f.kind == SMD_MOL_NANOCORE && f.n > 0)
+				LAUNCH(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
+				       f.d_idx, f.d_C, 0, 1, ctx->acc, nullptr, 1.0, 1.0, 1.0);
 	return SMD_OK;
+}
+
+static size_t field_sum_slots(const smd_ctx *ctx)
+{
+	size_t k = 0;
+	for (auto &f : ctx->fields) k += (f.kind == SMD_MOL_ZTORQUE || f.kind == SMD_MOL_ZPOWERPOTENTIAL) ? (size_t)f.n : 1;
+	return k;
 }
 
 static int bead_mass_divide(smd_ctx *ctx)
@@ -798,9 +925,42 @@ static int bead_mass_divide(smd_ctx *ctx)
 	return SMD_OK;
 }
 
+// NANOCORE beads are divided by their mass on restart (MD.cpp:290-303) and before the second half kick (:495-508), but
+// not at the top of the step (:340-355 handles BEAD only)
+static int nanocore_mass_divide(smd_ctx *ctx)
+{
+	for (auto &f : ctx->fields)
+		if (f.kind == SMD_MOL_NANOCORE && f.n > 0)
+			LAUNCH(k_nanocore_mass, nblk(f.n, 64), 64, 0, f.n, ctx->cap, f.d_idx, ctx->slot_of, f.d_C, ctx->acc);
+	return SMD_OK;
+}
+
+// langevin.h:235; with per-type friction the reference computes sT[] ONCE, at the temperature of its first call
+// (langevin.h:236-241: `if(gT!=NULL && sT==NULL)`), so a temperature ramp never reaches the noise amplitude
+static double langevin_sigma(smd_ctx *ctx)
+{
+	if (ctx->sigma_frozen) {
+		if (!(ctx->sigma_temperature >= 0)) ctx->sigma_temperature = ctx->temperature;   // first evaluation
+		return sqrt((6.0 * ctx->sigma_temperature * ctx->desc.gamma) / ctx->desc.dt);
+	}
+	return sqrt((6.0 * ctx->temperature * ctx->desc.gamma) / ctx->desc.dt);
+}
+
+extern "C" int smd_set_gamma_type(smd_ctx *ctx, int32_t n_types, const double *gamma_type)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(gamma_type && n_types == ctx->nT, "gammaType needs one value per particle type");
+	REQUIRE(gamma_type[0] > 0, "gammaType[0] must be positive");
+	// Langevin::compute with gT != NULL (langevin.h:248-281): `int type=0;//p[i].type;` -- every particle gets gT[0], sT[0]
+	ctx->desc.gamma = gamma_type[0];
+	ctx->sigma_frozen = true;
+	ctx->sigma_temperature = -1.0;
+	return SMD_OK;
+}
+
 static int add_langevin(smd_ctx *ctx, int64_t step)
 {
-	double sigma = sqrt((6.0 * ctx->temperature * ctx->desc.gamma) / ctx->desc.dt);   // langevin.h:235
+	double sigma = langevin_sigma(ctx);
 	const double *ext = nullptr;
 	if (ctx->desc.noise == SMD_NOISE_EXTERNAL) {
 		REQUIRE(ctx->noise_ready, "SMD_NOISE_EXTERNAL: call smd_set_noise before every Langevin evaluation");
@@ -880,7 +1040,7 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 			ctx->noise_ready = false;
 		}
 		lg.gamma = ctx->desc.gamma;
-		lg.sigma = sqrt((6.0 * ctx->temperature * ctx->desc.gamma) / ctx->desc.dt);   // langevin.h:235
+		lg.sigma = langevin_sigma(ctx);
 		lg.seed = ctx->desc.seed; lg.step = (uint64_t)step;
 		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
 		ProfScope ps(ctx, SMD_PHASE_PAIR);
@@ -922,6 +1082,7 @@ extern "C" int smd_resume(smd_ctx *ctx)
 	int rc = ready(ctx);
 	if (rc) return rc;
 	bead_mass_divide(ctx);
+	nanocore_mass_divide(ctx);
 	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);
 	return SMD_OK;
 }
@@ -952,7 +1113,7 @@ extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
 	// MD.cpp:410-478: thermostat, build, pair, molecules
 	rc = forces(ctx, SMD_MASK_ALL, step, true);
 	if (rc) return rc;
-	{ ProfScope ps(ctx, SMD_PHASE_MOLECULES); bead_mass_divide(ctx); }             // MD.cpp:480-494
+	{ ProfScope ps(ctx, SMD_PHASE_MOLECULES); bead_mass_divide(ctx); nanocore_mass_divide(ctx); }   // MD.cpp:480-508
 	ProfScope ps(ctx, SMD_PHASE_INTEGRATE2);
 	LAUNCH(k_verlet_second, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->desc.dt);   // :511
 	return SMD_OK;
@@ -962,7 +1123,7 @@ extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
 // one kernel, see k_chain_kick
 static bool can_fuse(const smd_ctx *ctx)
 {
-	return !ctx->no_fuse && ctx->bonds.empty() && ctx->bends.empty() && ctx->beads.empty() && ctx->balls.empty() &&
+	return !ctx->no_fuse && ctx->bonds.empty() && ctx->bends.empty() && ctx->beads.empty() && ctx->balls.empty() && ctx->fields.empty() &&
 	       (int)ctx->chains.size() <= MAX_FUSED_CHAINS && ctx->desc.noise != SMD_NOISE_EXTERNAL;
 }
 
@@ -1038,7 +1199,8 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	std::vector<int> term_of_slot;
 	int slot = 0;
 	auto push = [&](int term) { term_of_slot.push_back(term); return slot++; };
-	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + ctx->balls.size() + 2 * ctx->beads.size() <= 64, "too many molecule records for one energy call");
+	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + ctx->balls.size() + 2 * ctx->beads.size() + field_sum_slots(ctx) <= 64,
+	        "too many molecule records for one energy call");
 	if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
 		// two-phase kernel, every unordered pair once (see k_pair_force2)
 		int nb = nblk(N, PAIR_TPB);
@@ -1097,9 +1259,21 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 		       ctx->partials, sx, sy, sz);
 		finish_sum(ctx, 1, push(SMD_TERM_BEAD), 1.0);
 		int nb = nblk(N, TPB);
-		LAUNCH(k_bead<MODE>, nb, TPB, 0, N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, 0,
+		LAUNCH(k_bead<MODE>, nb, TPB, 0, N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, 0, 0,
 		       nullptr, ctx->partials, sx, sy, sz);
 		finish_sum(ctx, nb, push(SMD_TERM_BEAD), 1.0);
+	}
+	for (auto &f : ctx->fields) {
+		if (f.kind == SMD_MOL_NANOCORE) {
+			if (f.n <= 0) continue;
+			int nb = nblk(N, TPB);
+			LAUNCH(k_bead<MODE>, nb, TPB, 0, N, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT, f.d_idx, f.d_C, 0, 1,
+			       nullptr, ctx->partials, sx, sy, sz);
+			finish_sum(ctx, nb, push(SMD_TERM_NANOCORE), 1.0);
+		} else if (MODE == 1) {   // the one-body fields have no dPotential (MD.cpp:642-669)
+			int frc = launch_field<1>(ctx, f, pos, [&](int nb, int term) { finish_sum(ctx, nb, push(term), 1.0); });
+			if (frc) return frc;
+		}
 	}
 	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, slot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	rc = check_device_errors(ctx);
@@ -1219,8 +1393,10 @@ extern "C" int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, do
 	int rc = smd_dpotential(ctx, aSize, terms);
 	if (rc) return rc;
 	// MD.cpp:615-675: pair first, then the molecules in file order (we sum by kind; FP64 sum order differs only)
+	// MD.cpp:657-666 evaluates doNanoCoreDPotential / doBallDPotential and DROPS the result (no `dPotential+=`)
 	double dPotential = 0;
-	for (int t = 0; t < SMD_NTERMS; t++) dPotential += terms[t];
+	for (int t = 0; t < SMD_NTERMS; t++)
+		if (t != SMD_TERM_BALL && t != SMD_TERM_NANOCORE) dPotential += terms[t];
 	int32_t acc = 0;
 	smd_mc_accept(dPotential, tension, oldSize, size, ctx->temperature, u_accept, &acc, &dPotential);
 	if (acc) {

@@ -86,6 +86,14 @@ struct ChainBlock { int start, nChains, len; double c[4]; };
 struct BondList { int n; int *d_ij; double c[2]; };
 struct BendList { int n; int *d_ijk; double c[2]; };
 struct BallList { int n; int *d_cj; double c[2]; };
+// BOUNDARY / FLOATING_BASE / ZTORQUE / ZPOWERPOTENTIAL / NANOCORE (kind = the reference's molecule type id)
+struct FieldMol {
+	int kind, n;               // n records (particles or blocks)
+	int *d_idx;                // [n] original particle indices (BOUNDARY, FLOATING_BASE, NANOCORE)
+	double *d_C;               // device constants (FLOATING_BASE 6*nT, NANOCORE 22*n)
+	double c[4];               // host constants (BOUNDARY, ZTORQUE, ZPOWERPOTENTIAL)
+	std::vector<int> blocks;   // host block records (ZTORQUE [n][3], ZPOWERPOTENTIAL [n][2])
+};
 struct BeadMol {
 	int nOwn, nAll;        // beads of this molecule / of the list assembled from molecules j >= i (system.h:2053-2070)
 	int *d_beads;          // [nAll] original particle indices, own beads first
@@ -154,9 +162,12 @@ struct smd_ctx {
 	std::vector<smd::BendList> bends;
 	std::vector<smd::BallList> balls;
 	std::vector<smd::BeadMol> beads;
+	std::vector<smd::FieldMol> fields;
 	int n_molecules;
 
 	// noise
+	bool sigma_frozen = false;          // per-type friction path: noise amplitude fixed at its first temperature
+	double sigma_temperature = -1.0;
 	double *noise;     // [N][3] original order, external uniforms
 	bool noise_ready;
 

@@ -2243,10 +2243,13 @@ __global__ void __launch_bounds__(TPB) k_beadbead(int nOwn, int nAll, int cap, c
 // bead - particle terms: one thread per particle, loop over the molecule's own beads (system.h:2165-2210 brute-force
 // branch; the hash-cell branch :2105-2164 visits the same pairs).  excl_all: the force excludes every own bead when
 // nOwn <= 20 and only the bead itself otherwise; potential / dPotential always exclude only the bead itself (Q7).
+// nano: NANOCORE molecules (doNanoCoreForce system.h:2215-2332, doNanoCorePotential :3028-3075, doNanoCoreDPotential
+// :3708-3760) are the same term with ONE constants row per bead (C + 22 j, cutoff from that row) whatever the particle's
+// type, only the bead itself excluded, and no bead-bead term.
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_bead(int N, int nOwn, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
                                               const int *__restrict__ slot_of, Geom g, int nT, const int *__restrict__ beads,
-                                              const double *__restrict__ C, int excl_all, double *acc, double *partials,
+                                              const double *__restrict__ C, int excl_all, int nano, double *acc, double *partials,
                                               double sx, double sy, double sz)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2268,7 +2271,8 @@ __global__ void __launch_bounds__(TPB) k_bead(int N, int nOwn, int cap, const Pa
 		if (live && bs != s && !own) {
 			V3 d = diff_mi(pb, p, g);
 			double dr2 = d.x * d.x + d.y * d.y + d.z * d.z;
-			const double *Cr = C + 22 * (pb.type * nT + p.type);
+			const double *Cr = nano ? C + 22 * j : C + 22 * (pb.type * nT + p.type);
+			if (nano) cut2 = Cr[0] * Cr[0];
 			if (MODE == 0) {
 				double m = bead_mag(dr2, Cr, cut2);
 				if (m != 0) {
@@ -2302,11 +2306,157 @@ __global__ void __launch_bounds__(TPB) k_bead(int N, int nOwn, int cap, const Pa
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ external fields
+// The remaining molecule kinds of MD.cpp's switch (MD.cpp:414-478).  One thread per record (or per bond of
+// a block), FP64 atomics for the force because nothing stops a list from naming a particle twice.  None of them has a
+// dPotential: MD.cpp:642-669 leaves them out of the Metropolis box move.  MODE 0 force, 1 potential.
+
+// BOUNDARY (doBoundaryForce system.h:2334-2348, doBoundaryPotential :3137-3151; boundaryF MD.h:543-580, boundaryP
+// :586-626): U = k (1/d^4 - 1/d^2) for d^2 <= 2 along one axis around a plane; c = {dim, centre, unused, k}
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_boundary(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                                  const int *__restrict__ idx, int dim, double centre, double kk, double *acc, double *partials)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0;
+	if (b < nb) {
+		int s = slot_of[idx[b]];
+		Particle p = load_particle(pos + s);
+		double L = g.box[dim];
+		double d = (dim == 0 ? p.x : dim == 1 ? p.y : p.z) - centre;
+		d -= (d > L / 2.0) ? L : 0;
+		d += (d < -L / 2.0) ? L : 0;
+		double dir = (d < 0) ? -1.0 : 1.0;   // MD.h:81 #define sign(v)
+		d = fabs(d);
+		double d2 = d * d;
+		if (MODE == 0) {
+			double magnitude = 0;
+			if (d2 <= 2.0) magnitude = kk * (4.0 / (d2 * d2 * d) - 2.0 / (d2 * d));
+			atomicAdd(acc + dim * cap + s, magnitude * dir);
+		} else {
+			if (d2 <= 2.0) usum = kk * (1.0 / (d2 * d2) - 1.0 / d2);
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// FLOATING_BASE (doFloatingBaseForce system.h:2402-2422, doFloatingBasePotential :2424-2446; floatingBaseForce MD.h:457-472,
+// floatingBasePotential :475-494): a polynomial wall in z, constants row 6 * type.  Quirk reproduced: the force takes z
+// itself, the potential z - C[0] of ROW 0.
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_floating_base(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of,
+                                                       const int *__restrict__ idx, const double *__restrict__ C, double *acc, double *partials)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0;
+	if (b < nb) {
+		int s = slot_of[idx[b]];
+		Particle p = load_particle(pos + s);
+		const double *k = C + 6 * p.type;
+		double k0 = k[0], k1 = k[1];
+		if (MODE == 0) {
+			double z = p.z;
+			if (z <= k0) {
+				atomicAdd(acc + 2 * cap + s, k[3] * z * z * z - 2 * k[3] * k0 * z * z + (2 * k[2] + k[3] * k0 * k0) * z);
+			} else if (z < k1) {
+				double rcz = z - k1;
+				atomicAdd(acc + 2 * cap + s, k[5] * (rcz * rcz) * (2 * z * z - (4 * k1 - 7 * k0) * z + 2 * k1 * k1 + k0 * (-7 * k1 + 6 * k0)));
+			}
+		} else {
+			double z = p.z - C[0];
+			if (z <= k0) {
+				double rmz = k0 - z;
+				usum = k[2] * (k0 * k0 - z * z) + k[3] * rmz * rmz * rmz * ((k0 / 3.0) - (1.0 / 4.0) * rmz) + k[4];
+			} else if (z < k1) {
+				double rcz = k1 - z;
+				usum = k[5] * rcz * rcz * rcz * (rcz * ((2.0 / 5.0) * rcz - (7.0 / 4.0) * k0) + (2.0) * k0 * k0);
+			}
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// ZTORQUE (doZTorqueForce system.h:2625-2663, doZTorquePotential :2582-2623; zTorqueForce MD.h:1126-1140, zTorquePotential
+// :1116-1124): aligns the bonds (l, l+1), l = k .. k+len-3, of a block of chains with z, strength eps(z) = a - b tanh(c (z - d))
+// at the bond's mid height; the force switches eps off above z = d, the potential does not.  One thread per bond.
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_ztorque(int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                                 int start, int nChains, int len, double c0, double c1, double c2, double c3,
+                                                 double *acc, double *partials)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	int per = len - 2;
+	double usum = 0;
+	if (per > 0 && t < nChains * per) {
+		int l = start + (t / per) * len + (t % per);
+		int s1 = slot_of[l], s2 = slot_of[l + 1];
+		Particle p1 = load_particle(pos + s1);
+		V3 d = diff_mi(p1, load_particle(pos + s2), g);
+		double z = p1.z + d.z / 2.0;
+		while (z >= g.box[2]) z -= g.box[2];
+		while (z < 0) z += g.box[2];
+		double mag = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+		double eps = c0 - c1 * tanh(c2 * (z - c3));
+		if (MODE == 0) {
+			if (z > c3) eps = 0;
+			double m = -eps * (d.z / (mag * mag * mag * mag));
+			double fx = d.z * m * d.x, fy = d.z * m * d.y, fz = m * (d.x * d.x + d.y * d.y);
+			atomicAdd(acc + s1, fx); atomicAdd(acc + cap + s1, fy); atomicAdd(acc + 2 * cap + s1, -fz);
+			atomicAdd(acc + s2, -fx); atomicAdd(acc + cap + s2, -fy); atomicAdd(acc + 2 * cap + s2, fz);
+		} else {
+			double cosTheta = fabs(d.z) / mag;
+			usum = eps * (1.0 - cosTheta * cosTheta) / 2.0;
+		}
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
+// ZPOWERPOTENTIAL (doZPowerForce system.h:2692-2715, doZPowerPotential :2665-2690; zPowerForce MD.h:1148-1153,
+// zPowerPotential :1142-1146): a.z += k z^n, U = -k z^(n+1) / (n+1) for the particles start .. start+count-1
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_zpower(int count, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, int start,
+                                                double kk, double n, double *acc, double *partials)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	double usum = 0;
+	if (t < count) {
+		int s = slot_of[start + t];
+		double z = load_particle(pos + s).z;
+		if (MODE == 0) atomicAdd(acc + 2 * cap + s, kk * pow(z, n));
+		else usum = -kk * pow(z, n + 1) / (n + 1);
+	}
+	if (MODE != 0) {
+		usum = block_sum(usum);
+		if (threadIdx.x == 0) partials[blockIdx.x] = usum;
+	}
+}
+
 // a[bead] /= 4 pi R^2 (MD.cpp:340-355, :480-494)
 __global__ void k_bead_mass(int n, int cap, const int *__restrict__ beads, const int *__restrict__ slot_of, double mass, double *acc)
 {
 	int j = blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
+	int s = slot_of[beads[j]];
+	acc[s] /= mass; acc[cap + s] /= mass; acc[2 * cap + s] /= mass;
+}
+
+// NANOCORE: a[bead j] /= 4 pi R_j^2, R_j = C[22 j + 4] (MD.cpp:290-303, :495-508)
+__global__ void k_nanocore_mass(int n, int cap, const int *__restrict__ beads, const int *__restrict__ slot_of, const double *__restrict__ C,
+                                double *acc)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	double R = C[22 * j + 4];
+	double mass = (4.0) * M_PI * R * R;
 	int s = slot_of[beads[j]];
 	acc[s] /= mass; acc[cap + s] /= mass; acc[2 * cap + s] /= mass;
 }

@@ -8,7 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["lipo_t0", "lipo_eq", "bondbend", "bilayer_t0", "bilayer_eq", "lipocyto_eq", "bead1", "bead2", "ball"]
+CASES = ["lipo_t0", "lipo_eq", "bondbend", "bilayer_t0", "bilayer_eq", "lipocyto_eq", "bead1", "bead2", "ball", "fields"]
 
 
 def pytest_configure(config):

@@ -95,7 +95,8 @@ def test_pair_force_potential_dpotential(contexts, case):
 
 
 TERM_OF = {sm.MOL_CHAIN: sm.TERM_CHAIN, sm.MOL_BOND: sm.TERM_BOND, sm.MOL_BEND: sm.TERM_BEND, sm.MOL_BEAD: sm.TERM_BEAD,
-           sm.MOL_BALL: sm.TERM_BALL}
+           sm.MOL_BALL: sm.TERM_BALL, sm.MOL_BOUNDARY: sm.TERM_FIELD, sm.MOL_FLOATING_BASE: sm.TERM_FIELD,
+           sm.MOL_ZTORQUE: sm.TERM_FIELD, sm.MOL_ZPOWERPOTENTIAL: sm.TERM_FIELD, sm.MOL_NANOCORE: sm.TERM_NANOCORE}
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -104,6 +105,9 @@ def test_molecule_terms(contexts, case):
     U, dU = ctx.potential(), ctx.dpotential(ref["scale"])
     by_term_a, by_term_U, by_term_dU = {}, {}, {}
     for k, mol in enumerate(m["molecules"]):
+        if mol["type"] in sm.MOL_IGNORED:      # SOLID, OFFSET_BOUNDARY, ...: `MD` does nothing with them, nor does the reference harness
+            assert not ref[f"a_mol{k}"].any() and ref["U_mol"][k] == 0
+            continue
         t = TERM_OF[mol["type"]]
         by_term_a[t] = by_term_a.get(t, 0) + ref[f"a_mol{k}"].reshape(-1, 3)
         by_term_U[t] = by_term_U.get(t, 0) + ref["U_mol"][k]
@@ -155,7 +159,7 @@ def test_philox_uniforms_bit_exact(orc):
     assert abs(u.mean() - 0.5) < 2e-3 and abs(u.var() - 1 / 12) < 1e-3 and u.min() >= 0 and u.max() < 1
 
 
-@pytest.mark.parametrize("case", ["lipo_t0", "lipo_eq", "bilayer_t0", "bilayer_eq", "bead1", "bead2", "ball"])
+@pytest.mark.parametrize("case", ["lipo_t0", "lipo_eq", "bilayer_t0", "bilayer_eq", "bead1", "bead2", "ball", "fields"])
 def test_trajectory_matches_reference_md(contexts, orc, case):
     """The whole loop of MD.cpp for K steps against the state the reference `MD` executable wrote (one thread):
     Langevin noise = the reference's MT19937 stream fed through smd_set_noise, MC box moves with tension driven by

@@ -116,6 +116,56 @@ def test_bilayer_with_tension_box_moves_and_restart(tmp_path, orc):
     assert not (d2 / "frames_bl.xyz").exists() or open(d2 / "frames_bl.xyz").read().count("test\n") == 0
 
 
+def test_every_molecule_kind_of_the_md_switch(tmp_path, orc):
+    """tests/golden/fields: BOUNDARY, FLOATING_BASE, ZTORQUE, ZPOWERPOTENTIAL, NANOCORE, BALL (+ SOLID and OFFSET_BOUNDARY,
+    which `MD` parses and ignores) on a periodic bilayer with box moves.  Same files as the reference binary, same t = 0
+    observables incl. beadPotential_ (NANOCORE counts as a bead, dataExtraction.h:971-978), checkpoint carries every
+    molecule back."""
+    from conftest import golden_path
+    m, _ = orc.load_golden(golden_path("fields"))
+    m = dict(m, initialTime=0.0, finalTime=0.8, storeInterval=0.4, measureInterval=0.2)
+    res = run_pair(tmp_path, orc, m, "fld")
+    d, r = res["ours"]
+    assert (d / "beadPotential_fld.dat").exists()
+    chk = orc.read_mpd(str(d / "fld.mpd"))
+    assert [mol["type"] for mol in chk["molecules"]] == [mol["type"] for mol in m["molecules"]]
+    for a, b in zip(chk["molecules"], m["molecules"]):
+        assert np.array_equal(a["bonds"], b["bonds"]) and np.allclose(a["constants"], b["constants"], rtol=1e-14)
+    assert chk["initialTime"] == 0.8
+    if "ref" not in res:
+        pytest.skip("oracle/_ref/MD not built: reference side of the comparison unavailable")
+    dr, rr = res["ref"]
+    assert sorted(os.listdir(d)) == sorted(os.listdir(dr))
+    for nm in ("potential_", "beadPotential_", "kinetic_", "size_", "lBond_", "bend_", "flicker_"):
+        a, b = table(d / f"{nm}fld.dat"), table(dr / f"{nm}fld.dat")
+        assert [x[0] for x in a] == [x[0] for x in b], nm
+        assert np.allclose(a[0], b[0], rtol=1e-5, equal_nan=True), (nm, a[0], b[0])
+
+
+def test_per_type_friction_command(tmp_path, orc):
+    """`gammaType` with gamma 0 (MD.cpp:129-138).  The reference's own .mpd parser writes the values into a vector it never
+    sized (system.h:1269) and the binary dies on such a file, so there is no reference run to compare with; the semantics
+    are those of Langevin::compute (langevin.h:236-281): every particle gets entry 0, the noise amplitude is fixed at the
+    first temperature.  With gammaType[0] = gamma the run must therefore reproduce the plain-gamma run bit for bit."""
+    m = workloads.liposome(300, 3.45, 3)
+    m.update(finalTime=0.8, storeInterval=0.8, measureInterval=0.2)
+    outs = {}
+    for tag, extra in (("plain", {}), ("typed", {"gamma": 0.0, "gammaType": [m["gamma"]] + [0.125] * (m["nTypes"] - 1)})):
+        d = tmp_path / tag
+        d.mkdir()
+        orc.write_mpd(str(d / "g.mpd"), dict(m, **extra))
+        r = subprocess.run([MD_B200, "g"], cwd=d, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = orc.read_mpd(str(d / "g.mpd"))
+    assert np.array_equal(outs["plain"]["xyz"], outs["typed"]["xyz"]) and np.array_equal(outs["plain"]["vel"], outs["typed"]["vel"])
+    assert outs["typed"]["gammaType"][1] == 0.125 and outs["typed"]["gamma"] == 0.0     # echoed back as given
+    d = tmp_path / "none"
+    d.mkdir()
+    orc.write_mpd(str(d / "g.mpd"), dict(m, gamma=0.0))
+    r = subprocess.run([MD_B200, "g"], cwd=d, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "No gamma available" in r.stdout                        # MD.cpp:139-143
+
+
 def test_long_run_observables_agree_with_the_reference_statistically(tmp_path):
     """north star: "long-run observables (area per lipid, membrane tension, temperature) agree statistically".
     tests/golden/stat_bilayer.npz (oracle/make_golden.py stats) holds the reference `MD` executable's own kinetic_ /
