@@ -116,6 +116,24 @@ extern "C" int smd_device_count(void)
 	return n;
 }
 
+// x slices per reference cell in the sort key (Geom::xs).  The sliced order no longer lists a cell's particles by
+// descending original index, which is what the ORDERED look-up of an asymmetric constant table keys on (the reference's
+// "later-loaded particle first", cellOpt.h:572-585): asymmetric tables, the slab decomposition (column bookkeeping), the
+// two-kernel engine and the TMA-staged variant keep xs = 1.
+static void choose_xs(smd_ctx *ctx)
+{
+	Geom &g = ctx->geom;
+	int xs = ctx->xs_wanted;
+	if (ctx->slab || ctx->pair_split || STAGE_CAP > 0 || (ctx->tables_set && !ctx->tables_symmetric)) xs = 1;
+	const long long cap = ctx->cellcap > 0 ? ctx->cellcap : ctx->cellcap_limit;   // before / after the tables were allocated
+	while (xs > 1 && ((long long)g.nc[0] * g.nc[1] * g.nc[2] * xs > cap)) xs >>= 1;
+	if (xs < 1) xs = 1;
+	if (g.xs != xs) ctx->cells_valid = false;
+	g.xs = xs;
+	g.finv = (double)xs / g.cs[0];
+	ctx->pgeo.finv32 = (float)g.finv;
+}
+
 static void set_geom(smd_ctx *ctx, const double box[3])
 {
 	Geom &g = ctx->geom;
@@ -143,6 +161,7 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 	ctx->pgeo.margin32 = nextafterf((float)margin, INFINITY);
 	ctx->pgeo.slack32 = (float)(8.0 * maxL * (1.0 / 16777216.0) + 1e-6 * ctx->desc.cutoff);
 	for (int d = 0; d < 3; d++) ctx->pgeo.cs32[d] = (float)g.cs[d];
+	choose_xs(ctx);
 }
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
@@ -229,6 +248,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->launches = ctx->rebuilds = 0;
 	{ const char *e = getenv("SMD_ENERGY_ONEPHASE"); ctx->force_onephase_energy = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
+	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
 	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
@@ -294,7 +314,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	}
 	// dense offset table over the occupied window of the reference grid; capacity = whole grid up to 64 Mi cells
 	long long total = (long long)ctx->geom.nc[0] * ctx->geom.nc[1] * ctx->geom.nc[2];
-	ctx->cellcap = std::min<long long>(std::max<long long>(2 * total, 1 << 16), 64ll << 20);
+	ctx->cellcap = std::min<long long>(std::max<long long>(std::max<long long>(2, ctx->geom.xs) * total, 1 << 16), 64ll << 20);
 	CKC(cudaMalloc(&ctx->count, (ctx->cellcap + 1) * sizeof(int)));
 	CKC(cudaMemset(ctx->count, 0, (ctx->cellcap + 1) * sizeof(int)));
 	CKC(cudaMalloc(&ctx->start, (ctx->cellcap + 1) * sizeof(int)));
@@ -490,6 +510,7 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 			for (int k = 0; k < 6; k++)
 				if (fC[6 * (a * ctx->nT + b) + k] != fC[6 * (b * ctx->nT + a) + k] || uC[6 * (a * ctx->nT + b) + k] != uC[6 * (b * ctx->nT + a) + k])
 					ctx->tables_symmetric = false;
+	choose_xs(ctx);
 	return SMD_OK;
 }
 
@@ -1688,7 +1709,10 @@ extern "C" int smd_slab_exchange_recv(smd_ctx *ctx)
 	REQUIRE(ctx->slab && ctx->exch_pending, "slab: no exchange in flight");
 	CK(cudaSetDevice(ctx->device));
 	ProfScope ps(ctx, SMD_PHASE_EXCHANGE);
-	int blocks = std::min(nblk(2ll * ctx->comm.capmsg, 256), 296);
+	// A few blocks only (grid-stride over <= 2 * capmsg entries): the kernel SPINS on the neighbours' headers, and when
+	// several ranks share one device (the single-process test harness) their waiting kernels must never fill the machine
+	// and starve the pack kernel they wait for (four ranks x 296 blocks x 256 threads did exactly that, intermittently).
+	int blocks = std::min(nblk(2ll * ctx->comm.capmsg, 256), 24);
 	long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a neighbour that never sends is reported, not waited for
 	LAUNCH(k_slab_unpack, blocks, 256, 0, cnt_of(ctx), ctx->dN + 1, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
 	       ctx->gid[ctx->cur], ctx->comm, ctx->xseq, ctx->errflag, spin_limit);

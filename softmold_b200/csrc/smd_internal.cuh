@@ -33,6 +33,12 @@ struct Geom {
 	// slab decomposition along x (multi-GPU): this context owns the cell columns [col_lo, col_hi) of the global grid
 	// and keeps `halo` ghost columns on each side (periodic: column indices wrap modulo nc[0]).  slab == 0: whole box.
 	int slab, col_lo, col_hi, halo;
+	// x sub-cells: the SORT KEY (and the offset table start[]) splits every reference cell into xs slices along x, so a
+	// stencil row -- the three cells of a (y,z) row are contiguous in the sorted order -- is sorted by x to a resolution
+	// of cs[0] / xs and k_pair_force2 reads only the slices within the particle's reach (4 sigma of the row's 6).
+	// Particle::cell still holds the reference's own cell coordinates.  xs = 1: slab mode, asymmetric tables.
+	int xs;
+	double finv;    // xs / cs[0]
 };
 
 // particle count of a launch: a host value (single GPU: N never changes) or a device word (slab mode: the number of
@@ -52,7 +58,7 @@ constexpr unsigned CELL_DEAD = 0xffffffffu;
 // device-resident active window of the cell grid: the bounding box of occupied cells plus one cell each side.
 // win[0..2] origin, win[3..5] extent, win[6] number of cells in the window, win[8..9] the resolution of the 16-bit
 // window-relative coordinates of pos16[] and its inverse (float bit patterns; see quant_res).
-enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_RES = 8, WIN_INVRES = 9, WIN_WORDS = 12 };
+enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_FD0 = 7, WIN_RES = 8, WIN_INVRES = 9, WIN_WORDS = 12 };
 
 enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW_CAP = 4, ERR_SLAB_MIGRATION = 8, ERR_SLAB_MSG_CAP = 16, ERR_SLAB_CAPACITY = 32,
        ERR_SLAB_TIMEOUT = 64, ERR_SLAB_MISSING = 128 };
@@ -80,6 +86,7 @@ struct PairGeo {            // phase-1 constants of k_pair_force2
 	float slack32;          // FP32 rounding of a coordinate difference against a cell face
 	float cs32[3];          // cell size
 	float rmin32;           // smallest positive per-type phase-1 radius (pos16 path: widening of the energy modes' cutoffs)
+	float finv32;           // x slices per unit length (Geom::finv)
 };
 
 struct ChainBlock { int start, nChains, len; double c[4]; };
@@ -142,7 +149,9 @@ struct smd_ctx {
 	int *slot_of;     // [N] slot of original index
 
 	// cell grid
-	long long cellcap;
+	long long cellcap = 0;
+	long long cellcap_limit = 64ll << 20;   // the offset tables never grow beyond this many entries
+	int xs_wanted;     // x slices per cell when the fast path applies (SMD_XSUB, default 4)
 	int *count, *start, *cursor, *blockSums;
 	int *cellOfSlot;
 	int2 *order;      // {previous slot, original index} of every position claimed by k_place

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(TPB) k_tag_cells(Cnt cnt, Particle *pos, Geom 
 // tagged above, plus one empty cell on each side so that stencil look-ups of boundary cells stay inside the table.
 // Every kernel of the build derives it from bbox[] with this one function; k_scan3 publishes it in win[] for the
 // kernels that run after the build and re-arms bbox[].
-struct Window { int org[3], dim[3]; int ncells; };
+struct Window { int org[3], dim[3]; int ncells; int fd0; };   // fd0 = dim[0] * xs: x extent of the offset table in slices
 
 // window-local x index of cell column cx.  A slab's window starts `halo` columns left of its first owned column and
 // may run across the periodic boundary, so the index wraps modulo nc[0]; for a single-GPU window (a sub-box of the
@@ -278,6 +278,7 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 		w.org[1] = 0; w.dim[1] = g.nc[1];
 		w.org[2] = 0; w.dim[2] = g.nc[2];
 		n = (long long)w.dim[0] * w.dim[1] * w.dim[2];
+		w.fd0 = w.dim[0];   // slab mode: xs = 1
 		w.ncells = (n > cellcap) ? 0 : (int)n;
 		return w;
 	}
@@ -290,6 +291,8 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 		w.dim[d] = hi - lo + 1;
 		n *= w.dim[d];
 	}
+	w.fd0 = w.dim[0] * g.xs;
+	n *= g.xs;
 	w.ncells = (n > cellcap) ? 0 : (int)n;   // over capacity: flagged by k_scan3, nothing is binned
 	return w;
 }
@@ -337,13 +340,17 @@ __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom 
 	Window w = window_of(bbox, g, cellcap);
 	int local = -1;
 	if (s < cnt.get() && w.ncells > 0) {
-		unsigned c = pos[s].cell;
+		const Particle p = load_particle(pos + s);
+		unsigned c = p.cell;
 		if (c != CELL_DEAD) {   // slab mode: ghosts of the previous step
 			int cx, cy, cz;
 			unpack_cell(c, cx, cy, cz);
 			int lx = win_x(cx, w.org[0], g.nc[0]);
+			// x slice inside the reference cell (sort key only; clamped, so that slice / xs is always the reference's cell)
+			int sub = 0;
+			if (g.xs > 1) sub = min(max((int)((p.x - (double)cx * g.cs[0]) * g.finv), 0), g.xs - 1);
 			if (lx >= w.dim[0]) atomicOr(errflag, ERR_SLAB_MIGRATION);   // cannot happen on a single GPU (window = bbox)
-			else local = lx + w.dim[0] * ((cy - w.org[1]) + w.dim[1] * (cz - w.org[2]));
+			else local = (lx * g.xs + sub) + w.fd0 * ((cy - w.org[1]) + w.dim[1] * (cz - w.org[2]));
 		}
 		cellOfSlot[s] = local;
 	}
@@ -413,6 +420,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox,
 			if (blockIdx.x == 0) {
 				for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = wd.org[d]; win[WIN_DIM + d] = wd.dim[d]; }
 				win[WIN_NCELLS] = wd.ncells;
+				win[WIN_FD0] = wd.fd0;
 				const float res = quant_res(wd, g);
 				win[WIN_RES] = __float_as_int(res);
 				win[WIN_INVRES] = __float_as_int(1.0f / res);
@@ -599,8 +607,8 @@ __global__ void __launch_bounds__(TPB) k_pair(Cnt cnt, int cap, const Particle *
 					bool fwd = (oz == 1) || (oz == 0 && (ox == 1 || (ox == 0 && oy == 1)));
 					if (MODE == PAIR_POTENTIAL || MODE == PAIR_DPOTENTIAL)
 						if (!self && !fwd) continue;
-					int c = lx + d0 * (ly + d1 * lz);
-					int jb = start[c], je = start[c + 1];
+					int c = lx * g.xs + win[WIN_FD0] * (ly + d1 * lz);   // the cell's x slices are consecutive table entries
+					int jb = start[c], je = start[c + g.xs];
 					bool shifted = (Sx != 0) || (Sy != 0) || (Sz != 0);
 					// backward: the neighbour's cell is home and shifts US by the opposite image vector
 					double bx = pi.x - Sx, by = pi.y - Sy, bz = pi.z - Sz;
@@ -660,6 +668,203 @@ __global__ void __launch_bounds__(TPB) k_pair(Cnt cnt, int cap, const Particle *
 		double c = block_sum((double)cnt_in);
 		if (threadIdx.x == 0) partials[blockIdx.x] = c;
 	}
+}
+
+// ------------------------------------------------------------------------------------------------ bonded terms
+// minimum image per component with strict compares, system.h:1809-1817
+__device__ __forceinline__ void min_image(double &dx, double &dy, double &dz, const Geom &g)
+{
+	if (dx > g.box[0] / 2.0) dx -= g.box[0];
+	if (dx < -g.box[0] / 2.0) dx += g.box[0];
+	if (dy > g.box[1] / 2.0) dy -= g.box[1];
+	if (dy < -g.box[1] / 2.0) dy += g.box[1];
+	if (dz > g.box[2] / 2.0) dz -= g.box[2];
+	if (dz < -g.box[2] / 2.0) dz += g.box[2];
+}
+
+struct V3 { double x, y, z; };
+
+__device__ __forceinline__ V3 diff_mi(const Particle &a, const Particle &b, const Geom &g)
+{
+	V3 d = {a.x - b.x, a.y - b.y, a.z - b.z};
+	min_image(d.x, d.y, d.z, g);
+	return d;
+}
+
+// Square root and reciprocal for the bonded force terms.  The reference divides by r = sqrt(d.d) fourteen times per
+// CHAIN triplet (MD.h:384-403, :683-723); IEEE sqrt / division sequences made the fused step kernel FP64-latency bound.
+// Here one MUFU.RSQ64H seed per distinct length gives r = sqrt(x) (correctly rounded, as in the pair kernel) and
+// 1 / r to full precision, and every quotient n / r is one multiply plus an exact-residual correction
+// (q = n * inv; q += fma(-r, q, n) * inv): correctly rounded except for vanishingly rare near-ties (then one ulp off).
+struct SqrtRcp { double r, inv; };
+
+__device__ __forceinline__ SqrtRcp sqrt_rcp(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	double e = __fma_rn(-(x * y), y, 1.0);
+	y = __fma_rn(0.5 * y, e, y);                              // 1/sqrt(x) to ~2^-43
+	double r = x * y;
+	r = __fma_rn(__fma_rn(-r, r, x), 0.5 * y, r);             // sqrt(x)
+	y = __fma_rn(__fma_rn(-r, y, 1.0), y, y);                 // 1/r, refined against the rounded r
+	y = __fma_rn(__fma_rn(-r, y, 1.0), y, y);
+	SqrtRcp o = {r, y};
+	if (!(x > 0.0) || x == INFINITY) { o.r = sqrt(x); o.inv = 1.0 / o.r; }   // coincident particles / NaN: IEEE root and reciprocal (the run is lost either way)
+	return o;
+}
+
+__device__ __forceinline__ double div_cr(double n, const SqrtRcp &d)
+{
+	double q = n * d.inv;
+	return __fma_rn(__fma_rn(-d.r, q, n), d.inv, q);
+}
+
+// MD.h:384-403 harmonicF: returns f with a1 += f, a2 -= f
+__device__ __forceinline__ V3 harmonic_f(V3 d, double r0, double k)
+{
+	SqrtRcp dr = sqrt_rcp(d.x * d.x + d.y * d.y + d.z * d.z);
+	double m = dr.r - r0;
+	m = div_cr(-m * k, dr);
+	V3 f = {d.x * m, d.y * m, d.z * m};
+	return f;
+}
+
+// MD.h:422-431 harmonicP
+__device__ __forceinline__ double harmonic_p(V3 d, double r0, double k)
+{
+	double dr = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+	double u = dr - r0;
+	return 0.5 * k * u * u;
+}
+
+// MD.h:683-723 bendF: a1 += fa ; a2 += (fb - fa) ; a3 -= fb
+__device__ __forceinline__ void bend_f(V3 da, V3 db, double c0, double k, V3 &fa, V3 &fb)
+{
+	const SqrtRcp dra = sqrt_rcp(da.x * da.x + da.y * da.y + da.z * da.z);
+	const SqrtRcp drb = sqrt_rcp(db.x * db.x + db.y * db.y + db.z * db.z);
+	da.x = div_cr(da.x, dra); da.y = div_cr(da.y, dra); da.z = div_cr(da.z, dra);
+	db.x = div_cr(db.x, drb); db.y = div_cr(db.y, drb); db.z = div_cr(db.z, drb);
+	double ct = (da.x * db.x) + (da.y * db.y) + (da.z * db.z);
+	double m = c0 - ct;
+	m *= k;
+	fa.x = div_cr(m * (db.x - (da.x * ct)), dra); fb.x = div_cr(m * (da.x - (db.x * ct)), drb);
+	fa.y = div_cr(m * (db.y - (da.y * ct)), dra); fb.y = div_cr(m * (da.y - (db.y * ct)), drb);
+	fa.z = div_cr(m * (db.z - (da.z * ct)), dra); fb.z = div_cr(m * (da.z - (db.z * ct)), drb);
+}
+
+// MD.h:769-789 bendP
+__device__ __forceinline__ double bend_p(V3 da, V3 db, double c0, double k)
+{
+	double dra = sqrt(da.x * da.x + da.y * da.y + da.z * da.z);
+	double drb = sqrt(db.x * db.x + db.y * db.y + db.z * db.z);
+	da.x /= dra; da.y /= dra; da.z /= dra;
+	db.x /= drb; db.y /= drb; db.z /= drb;
+	double ct = (da.x * db.x) + (da.y * db.y) + (da.z * db.z);
+	double u = c0 - ct;
+	return k * u * u * 0.5;
+}
+
+__device__ __forceinline__ V3 scaled(V3 d, double sx, double sy, double sz)
+{
+	V3 r = {d.x * sx, d.y * sy, d.z * sz};
+	return r;
+}
+
+// CHAIN blocks, one thread per chain, same triplet order as Blob::doChainForce (system.h:1782-1866) /
+// doChainPotential (:2487-2568) / doChainDPotential (:3280-3384).  Chains are disjoint, so the force variant
+// updates acc[] without atomics; each particle's chain terms are summed in the reference's order.
+// MODE 0 force, 1 potential, 2 dPotential.
+// slot of the particle with global index id on this rank, or -1 (slab mode: owned or ghost copy; see k_chain_slab)
+__device__ __forceinline__ int slab_find(const int *__restrict__ slot_of, const int *__restrict__ gid, int N, int id, bool &owned)
+{
+	int t = slot_of[id];
+	owned = false;
+	if (t < 0 || t >= N) return -1;
+	int gg = gid[t];
+	if ((gg & GID_MASK) != id) return -1;   // stale entry of a particle that left this rank
+	owned = !(gg & GID_GHOST);
+	return t;
+}
+
+// ------------------------------------------------------------------------------------------------ fused step seam
+// Between the pair force of step i and the cell build of step i+1 the reference runs, per particle, Blob::doChainForce
+// (system.h:1782-1866), Verlet::second (verlet.h:463-477) and -- next iteration -- Verlet::first (verlet.h:288-356).
+// For systems whose only molecules are CHAIN blocks (C1, C2, C5) k_chain_kick does all of it in ONE pass with one
+// thread per particle: the particle gathers its own chain terms (the one to three triplets it belongs to, evaluated
+// and accumulated in the reference's order, so the sum a_chain is bit-identical to the per-chain kernel's), adds them
+// to the pair + Langevin acceleration, applies the two half kicks one after the other (two roundings, as two kernels
+// would), drifts, wraps and tags the new cell.  New positions go to the other position buffer: neighbours still read
+// the old ones for their chain terms.  Three latency-bound passes (43 us on C2) become one.
+// LAST = true ends a batch of steps instead: chain terms + Verlet::second only, a[] is stored for whoever comes next.
+constexpr int MAX_FUSED_CHAINS = 4;
+struct ChainSet { int n; ChainBlock b[MAX_FUSED_CHAINS]; };
+
+// the chain terms of the particle with global index gi (role by role, system.h:1798-1863)
+__device__ __forceinline__ bool chain_gather(int gi, const Particle &me, int N, const Particle *__restrict__ pos, const int *__restrict__ gid,
+                                             const int *__restrict__ slot_of, const Geom &g, const ChainSet &cs, V3 &A)
+{
+	A.x = A.y = A.z = 0;
+	for (int b = 0; b < cs.n; b++) {
+		const ChainBlock &cb = cs.b[b];
+		int rel = gi - cb.start;
+		if (rel < 0 || rel >= cb.nChains * cb.len) continue;
+		int k = rel / cb.len, l = rel - k * cb.len, base = cb.start + k * cb.len;
+		// members l-2 .. l+2 that exist
+		Particle q[5];
+		bool have[5];
+#pragma unroll
+		for (int d = 0; d < 5; d++) {
+			int m = l + d - 2;
+			have[d] = false;
+			if (d == 2) { q[d] = me; have[d] = true; continue; }
+			if (m < 0 || m >= cb.len) continue;
+			// which triplets need member m: only those that contain l
+			// slab mode: slot_of[] is exact after every build (the exchange clears the entries of dropped ghosts), so
+			// a non-negative entry is a local particle, owned or ghost
+			const int t = slot_of[base + m];
+			if (t >= 0) { q[d] = load_particle(pos + t); have[d] = true; }
+		}
+		// The particle's triplets in ascending order = role 2 (triplet l-2), then role 1, then role 0: the reference's
+		// order.  The loop runs over "my j-th triplet", not over roles, so that the lanes of a warp -- particles at
+		// different positions of their chains -- evaluate their square roots and divisions together; only the few
+		// additions that differ between the roles diverge.
+		bool ok = true;
+		const int tmin = max(l - 2, 0), tmax = min(l, cb.len - 3);
+#pragma unroll
+		for (int j = 0; j < 3; j++) {
+			const int t = tmin + j;
+			if (t > tmax) break;
+			const int r = l - t;                // my position inside the triplet
+			const bool tail = (t == cb.len - 3);
+			const bool r2 = (r == 2), r1 = (r == 1);
+			const bool h0 = r2 ? have[0] : (r1 ? have[1] : have[2]);
+			const bool h1 = r2 ? have[1] : (r1 ? have[2] : have[3]);
+			const bool h2 = r2 ? have[2] : (r1 ? have[3] : have[4]);
+			if (!(h0 && h1 && h2)) { ok = false; continue; }
+			const Particle &P0 = r2 ? q[0] : (r1 ? q[1] : q[2]);
+			const Particle &P1 = r2 ? q[1] : (r1 ? q[2] : q[3]);
+			const Particle &P2 = r2 ? q[2] : (r1 ? q[3] : q[4]);
+			V3 da = diff_mi(P0, P1, g), db = diff_mi(P1, P2, g);
+			V3 fa, fb;
+			bend_f(da, db, cb.c[2], cb.c[3], fa, fb);
+			V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
+			V3 f2 = {0, 0, 0};
+			if (tail) f2 = harmonic_f(db, cb.c[0], cb.c[1]);
+			if (r2) {
+				if (tail) { A.x -= f2.x; A.y -= f2.y; A.z -= f2.z; }
+				A.x -= fb.x; A.y -= fb.y; A.z -= fb.z;
+			} else if (r1) {
+				A.x -= f.x; A.y -= f.y; A.z -= f.z;
+				if (tail) { A.x += f2.x; A.y += f2.y; A.z += f2.z; }
+				A.x += (fb.x - fa.x); A.y += (fb.y - fa.y); A.z += (fb.z - fa.z);
+			} else {
+				A.x += f.x; A.y += f.y; A.z += f.z;
+				A.x += fa.x; A.y += fa.y; A.z += fa.z;
+			}
+		}
+		return ok;
+	}
+	return true;
 }
 
 // ------------------------------------------------------------------------------------------------ pair force, two-phase
@@ -880,6 +1085,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	for (int k = tid; k < PAIR_CAP + 2; k += PAIR_TPB) sm.hist[k] = 0;
 	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
 	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
+	const int fd0 = win[WIN_FD0], xs = g.xs;
 
 #if SMD_STAGE_CAP > 0
 	// ---- staging, step 1: the block's 128 slots are consecutive in the cell-sorted order, so the cells its particles
@@ -1143,9 +1349,18 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
 		}
 		rjb[r] = 0; rje[r] = 0;
-		if (row_ok && xlo <= xhi) {
-			int rowbase = d0 * (ly + d1 * lz);
-			rjb[r] = start[rowbase + xlo]; rje[r] = start[rowbase + xhi + 1];
+		// x slices: the row is sorted by x to cs / xs, read only the slices within reach of this particle in this row
+		// (conservative: the FP32 errors of the slice coordinate are ~1e-4 of a slice, the slack is 0.02)
+		int flo = xlo * xs, fhi = xhi * xs + (xs - 1);
+		if (xs > 1) {
+			const float reach = sqrtf(fmaxf(amax - gyz, 0.f)) + pg.slack32;
+			const float rel = p32.x - (float)w0 * pg.cs32[0];
+			flo = max(flo, (int)floorf((rel - reach) * pg.finv32 - 0.02f));
+			fhi = min(fhi, (int)floorf((rel + reach) * pg.finv32 + 0.02f));
+		}
+		if (row_ok && flo <= fhi) {
+			int rowbase = fd0 * (ly + d1 * lz);
+			rjb[r] = start[rowbase + flo]; rje[r] = start[rowbase + fhi + 1];
 		}
 	}
 #pragma unroll
@@ -1365,8 +1580,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 				row_ok = row_ok && keep_hi && cx == g.nc[0] - 1 && xlo < d0;
 			}
 			if (!row_ok || xlo > xhi) continue;
-			int rowbase = d0 * (ly + d1 * lz);
-			int jb = start[rowbase + xlo], je = start[rowbase + xhi + 1];
+			int rowbase = fd0 * (ly + d1 * lz);
+			int jb = start[rowbase + xlo * xs], je = start[rowbase + (xhi + 1) * xs];
 			const float qx = p32.x - sx, qy = p32.y - sy, qz = p32.z - sz;
 			for (int j = jb; j < je; j++) {
 				float4 c = pos32[j];
@@ -1456,110 +1671,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 #endif
 }
 
-// ------------------------------------------------------------------------------------------------ bonded terms
-// minimum image per component with strict compares, system.h:1809-1817
-__device__ __forceinline__ void min_image(double &dx, double &dy, double &dz, const Geom &g)
-{
-	if (dx > g.box[0] / 2.0) dx -= g.box[0];
-	if (dx < -g.box[0] / 2.0) dx += g.box[0];
-	if (dy > g.box[1] / 2.0) dy -= g.box[1];
-	if (dy < -g.box[1] / 2.0) dy += g.box[1];
-	if (dz > g.box[2] / 2.0) dz -= g.box[2];
-	if (dz < -g.box[2] / 2.0) dz += g.box[2];
-}
-
-struct V3 { double x, y, z; };
-
-__device__ __forceinline__ V3 diff_mi(const Particle &a, const Particle &b, const Geom &g)
-{
-	V3 d = {a.x - b.x, a.y - b.y, a.z - b.z};
-	min_image(d.x, d.y, d.z, g);
-	return d;
-}
-
-// Square root and reciprocal for the bonded force terms.  The reference divides by r = sqrt(d.d) fourteen times per
-// CHAIN triplet (MD.h:384-403, :683-723); IEEE sqrt / division sequences made the fused step kernel FP64-latency bound.
-// Here one MUFU.RSQ64H seed per distinct length gives r = sqrt(x) (correctly rounded, as in the pair kernel) and
-// 1 / r to full precision, and every quotient n / r is one multiply plus an exact-residual correction
-// (q = n * inv; q += fma(-r, q, n) * inv): correctly rounded except for vanishingly rare near-ties (then one ulp off).
-struct SqrtRcp { double r, inv; };
-
-__device__ __forceinline__ SqrtRcp sqrt_rcp(double x)
-{
-	double y;
-	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-	double e = __fma_rn(-(x * y), y, 1.0);
-	y = __fma_rn(0.5 * y, e, y);                              // 1/sqrt(x) to ~2^-43
-	double r = x * y;
-	r = __fma_rn(__fma_rn(-r, r, x), 0.5 * y, r);             // sqrt(x)
-	y = __fma_rn(__fma_rn(-r, y, 1.0), y, y);                 // 1/r, refined against the rounded r
-	y = __fma_rn(__fma_rn(-r, y, 1.0), y, y);
-	SqrtRcp o = {r, y};
-	if (!(x > 0.0) || x == INFINITY) { o.r = sqrt(x); o.inv = 1.0 / o.r; }   // coincident particles / NaN: IEEE root and reciprocal (the run is lost either way)
-	return o;
-}
-
-__device__ __forceinline__ double div_cr(double n, const SqrtRcp &d)
-{
-	double q = n * d.inv;
-	return __fma_rn(__fma_rn(-d.r, q, n), d.inv, q);
-}
-
-// MD.h:384-403 harmonicF: returns f with a1 += f, a2 -= f
-__device__ __forceinline__ V3 harmonic_f(V3 d, double r0, double k)
-{
-	SqrtRcp dr = sqrt_rcp(d.x * d.x + d.y * d.y + d.z * d.z);
-	double m = dr.r - r0;
-	m = div_cr(-m * k, dr);
-	V3 f = {d.x * m, d.y * m, d.z * m};
-	return f;
-}
-
-// MD.h:422-431 harmonicP
-__device__ __forceinline__ double harmonic_p(V3 d, double r0, double k)
-{
-	double dr = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
-	double u = dr - r0;
-	return 0.5 * k * u * u;
-}
-
-// MD.h:683-723 bendF: a1 += fa ; a2 += (fb - fa) ; a3 -= fb
-__device__ __forceinline__ void bend_f(V3 da, V3 db, double c0, double k, V3 &fa, V3 &fb)
-{
-	const SqrtRcp dra = sqrt_rcp(da.x * da.x + da.y * da.y + da.z * da.z);
-	const SqrtRcp drb = sqrt_rcp(db.x * db.x + db.y * db.y + db.z * db.z);
-	da.x = div_cr(da.x, dra); da.y = div_cr(da.y, dra); da.z = div_cr(da.z, dra);
-	db.x = div_cr(db.x, drb); db.y = div_cr(db.y, drb); db.z = div_cr(db.z, drb);
-	double ct = (da.x * db.x) + (da.y * db.y) + (da.z * db.z);
-	double m = c0 - ct;
-	m *= k;
-	fa.x = div_cr(m * (db.x - (da.x * ct)), dra); fb.x = div_cr(m * (da.x - (db.x * ct)), drb);
-	fa.y = div_cr(m * (db.y - (da.y * ct)), dra); fb.y = div_cr(m * (da.y - (db.y * ct)), drb);
-	fa.z = div_cr(m * (db.z - (da.z * ct)), dra); fb.z = div_cr(m * (da.z - (db.z * ct)), drb);
-}
-
-// MD.h:769-789 bendP
-__device__ __forceinline__ double bend_p(V3 da, V3 db, double c0, double k)
-{
-	double dra = sqrt(da.x * da.x + da.y * da.y + da.z * da.z);
-	double drb = sqrt(db.x * db.x + db.y * db.y + db.z * db.z);
-	da.x /= dra; da.y /= dra; da.z /= dra;
-	db.x /= drb; db.y /= drb; db.z /= drb;
-	double ct = (da.x * db.x) + (da.y * db.y) + (da.z * db.z);
-	double u = c0 - ct;
-	return k * u * u * 0.5;
-}
-
-__device__ __forceinline__ V3 scaled(V3 d, double sx, double sy, double sz)
-{
-	V3 r = {d.x * sx, d.y * sy, d.z * sz};
-	return r;
-}
-
-// CHAIN blocks, one thread per chain, same triplet order as Blob::doChainForce (system.h:1782-1866) /
-// doChainPotential (:2487-2568) / doChainDPotential (:3280-3384).  Chains are disjoint, so the force variant
-// updates acc[] without atomics; each particle's chain terms are summed in the reference's order.
-// MODE 0 force, 1 potential, 2 dPotential.
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_chain(int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
                                                ChainBlock cb, double *acc, double *partials, double sx, double sy, double sz)
@@ -1627,17 +1738,6 @@ __global__ void __launch_bounds__(TPB) k_chain(int cap, const Particle *__restri
 // then be local: the halo is two cell columns wide, a triplet spans at most two bonds) and only owned members are
 // written, so every owned particle receives exactly the terms, in exactly the order, of the single-GPU kernel.
 // Energies (MODE 1, 2): a triplet's terms are counted by the rank that owns its FIRST member -- once globally.
-__device__ __forceinline__ int slab_find(const int *__restrict__ slot_of, const int *__restrict__ gid, int N, int id, bool &owned)
-{
-	int t = slot_of[id];
-	owned = false;
-	if (t < 0 || t >= N) return -1;
-	int gg = gid[t];
-	if ((gg & GID_MASK) != id) return -1;   // stale entry of a particle that left this rank
-	owned = !(gg & GID_GHOST);
-	return t;
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_chain_slab(Cnt cnt, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
                                                     const int *__restrict__ slot_of, Geom g, ChainBlock cb, double *acc, double *partials,
@@ -1887,87 +1987,7 @@ __global__ void __launch_bounds__(TPB) k_slab_export(Cnt cnt, int cap, const Par
 	out_acc[3 * k] = acc[s]; out_acc[3 * k + 1] = acc[cap + s]; out_acc[3 * k + 2] = acc[2 * cap + s];
 }
 
-// ------------------------------------------------------------------------------------------------ fused step seam
-// Between the pair force of step i and the cell build of step i+1 the reference runs, per particle, Blob::doChainForce
-// (system.h:1782-1866), Verlet::second (verlet.h:463-477) and -- next iteration -- Verlet::first (verlet.h:288-356).
-// For systems whose only molecules are CHAIN blocks (C1, C2, C5) k_chain_kick does all of it in ONE pass with one
-// thread per particle: the particle gathers its own chain terms (the one to three triplets it belongs to, evaluated
-// and accumulated in the reference's order, so the sum a_chain is bit-identical to the per-chain kernel's), adds them
-// to the pair + Langevin acceleration, applies the two half kicks one after the other (two roundings, as two kernels
-// would), drifts, wraps and tags the new cell.  New positions go to the other position buffer: neighbours still read
-// the old ones for their chain terms.  Three latency-bound passes (43 us on C2) become one.
-// LAST = true ends a batch of steps instead: chain terms + Verlet::second only, a[] is stored for whoever comes next.
-constexpr int MAX_FUSED_CHAINS = 4;
-struct ChainSet { int n; ChainBlock b[MAX_FUSED_CHAINS]; };
-
-// the chain terms of the particle with global index gi (role by role, system.h:1798-1863)
-__device__ __forceinline__ bool chain_gather(int gi, const Particle &me, int N, const Particle *__restrict__ pos, const int *__restrict__ gid,
-                                             const int *__restrict__ slot_of, const Geom &g, const ChainSet &cs, V3 &A)
-{
-	A.x = A.y = A.z = 0;
-	for (int b = 0; b < cs.n; b++) {
-		const ChainBlock &cb = cs.b[b];
-		int rel = gi - cb.start;
-		if (rel < 0 || rel >= cb.nChains * cb.len) continue;
-		int k = rel / cb.len, l = rel - k * cb.len, base = cb.start + k * cb.len;
-		// members l-2 .. l+2 that exist
-		Particle q[5];
-		bool have[5];
-#pragma unroll
-		for (int d = 0; d < 5; d++) {
-			int m = l + d - 2;
-			have[d] = false;
-			if (d == 2) { q[d] = me; have[d] = true; continue; }
-			if (m < 0 || m >= cb.len) continue;
-			// which triplets need member m: only those that contain l
-			// slab mode: slot_of[] is exact after every build (the exchange clears the entries of dropped ghosts), so
-			// a non-negative entry is a local particle, owned or ghost
-			const int t = slot_of[base + m];
-			if (t >= 0) { q[d] = load_particle(pos + t); have[d] = true; }
-		}
-		// The particle's triplets in ascending order = role 2 (triplet l-2), then role 1, then role 0: the reference's
-		// order.  The loop runs over "my j-th triplet", not over roles, so that the lanes of a warp -- particles at
-		// different positions of their chains -- evaluate their square roots and divisions together; only the few
-		// additions that differ between the roles diverge.
-		bool ok = true;
-		const int tmin = max(l - 2, 0), tmax = min(l, cb.len - 3);
-#pragma unroll
-		for (int j = 0; j < 3; j++) {
-			const int t = tmin + j;
-			if (t > tmax) break;
-			const int r = l - t;                // my position inside the triplet
-			const bool tail = (t == cb.len - 3);
-			const bool r2 = (r == 2), r1 = (r == 1);
-			const bool h0 = r2 ? have[0] : (r1 ? have[1] : have[2]);
-			const bool h1 = r2 ? have[1] : (r1 ? have[2] : have[3]);
-			const bool h2 = r2 ? have[2] : (r1 ? have[3] : have[4]);
-			if (!(h0 && h1 && h2)) { ok = false; continue; }
-			const Particle &P0 = r2 ? q[0] : (r1 ? q[1] : q[2]);
-			const Particle &P1 = r2 ? q[1] : (r1 ? q[2] : q[3]);
-			const Particle &P2 = r2 ? q[2] : (r1 ? q[3] : q[4]);
-			V3 da = diff_mi(P0, P1, g), db = diff_mi(P1, P2, g);
-			V3 fa, fb;
-			bend_f(da, db, cb.c[2], cb.c[3], fa, fb);
-			V3 f = harmonic_f(da, cb.c[0], cb.c[1]);
-			V3 f2 = {0, 0, 0};
-			if (tail) f2 = harmonic_f(db, cb.c[0], cb.c[1]);
-			if (r2) {
-				if (tail) { A.x -= f2.x; A.y -= f2.y; A.z -= f2.z; }
-				A.x -= fb.x; A.y -= fb.y; A.z -= fb.z;
-			} else if (r1) {
-				A.x -= f.x; A.y -= f.y; A.z -= f.z;
-				if (tail) { A.x += f2.x; A.y += f2.y; A.z += f2.z; }
-				A.x += (fb.x - fa.x); A.y += (fb.y - fa.y); A.z += (fb.z - fa.z);
-			} else {
-				A.x += f.x; A.y += f.y; A.z += f.z;
-				A.x += fa.x; A.y += fa.y; A.z += fa.z;
-			}
-		}
-		return ok;
-	}
-	return true;
-}
-
+// ------------------------------------------------------------------------------------------------ fused step seam (kernel; chain_gather is defined ahead of the pair kernel)
 #ifndef SMD_KICK_BLOCKS
 #define SMD_KICK_BLOCKS 5   // 96 registers with a few spilled words beat 122 registers at 4 blocks (22.9 vs 25.1 us on C2)
 #endif
@@ -2541,8 +2561,12 @@ __global__ void __launch_bounds__(TPB) k_export_cells(int N, const Particle *pos
 	unpack_cell(pos[s].cell, cx, cy, cz);
 	int id = gid[s];
 	key[id] = cx + cy * g.nc[0] + cz * g.nc[0] * g.nc[1];
-	int c = (cx - win[WIN_ORG]) + win[WIN_DIM] * ((cy - win[WIN_ORG + 1]) + win[WIN_DIM + 1] * (cz - win[WIN_ORG + 2]));
-	rank[id] = s - start[c];
+	// position in the reference's head-inserted linked list of the cell (cellOpt.h:572-585): descending original index.
+	// (The sorted order itself is by x slice first, see Geom::xs.)
+	int c = (cx - win[WIN_ORG]) * g.xs + win[WIN_FD0] * ((cy - win[WIN_ORG + 1]) + win[WIN_DIM + 1] * (cz - win[WIN_ORG + 2]));
+	int r = 0;
+	for (int k = start[c]; k < start[c + g.xs]; k++) r += ((gid[k] & GID_MASK) > (id & GID_MASK));
+	rank[id] = r;
 }
 
 } // namespace smd

@@ -100,6 +100,7 @@ class LocalSlabGroup(_SlabBase):
             return
         for k in range(nsteps):
             self._each(lambda c: c.step_begin(first_step + k))
+            self._each(lambda c: c.synchronize())      # every message is out before any rank starts waiting for one
             self._each(lambda c: c.step_end(first_step + k))
 
     def synchronize(self):

@@ -308,10 +308,11 @@ def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
     out = []
     for env in ("0", "1"):
         os.environ["SMD_PAIR_SPLIT"] = env
+        os.environ["SMD_XSUB"] = "1"      # the split engine sorts by cell only: same order, same sums
         try:
             ctx = sm.Context.from_dict(m)
         finally:
-            del os.environ["SMD_PAIR_SPLIT"]
+            del os.environ["SMD_PAIR_SPLIT"], os.environ["SMD_XSUB"]
         ctx.compute_forces(step=2)
         ctx.step(2, 40)
         a = ctx.get_forces()
@@ -322,6 +323,37 @@ def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
         ctx.close()
     for u, w in zip(*out):
         assert np.array_equal(u, w)
+
+
+def test_x_sliced_sort_changes_nothing_but_the_summation_order(orc):
+    """Geom::xs: the sort key splits every reference cell into x slices so that phase 1 of the pair kernel reads only the
+    slices within reach.  Against SMD_XSUB=1 (cell-sorted only): identical cell ids and linked-list ranks, identical
+    in-range pair counts per particle, forces / energies / a trajectory equal to rounding."""
+    import os
+    from softmold_b200 import workloads
+    out = []
+    for m in (workloads.bilayer(4000, 3.11, seed=5), workloads.liposome(3000, 3.45, 2)):
+        res = []
+        for xs in ("1", "2", "4", "8"):
+            os.environ["SMD_XSUB"] = xs
+            try:
+                ctx = sm.Context.from_dict(m)
+            finally:
+                del os.environ["SMD_XSUB"]
+            ctx.compute_forces(step=2)
+            ctx.step(2, 30)
+            a = ctx.get_forces()
+            nc, key, rank = ctx.get_cell_ids()
+            tot, per = ctx.count_pairs(per_particle=True)
+            U = ctx.potential()
+            dU = ctx.dpotential([1.001, 1.001, 1.0 / 1.001 ** 2])
+            res.append((ctx.get_particles()[0], a, key, rank, per, U[sm.TERM_PAIR], dU[sm.TERM_PAIR]))
+            ctx.close()
+        x0, a0, k0, r0, p0, U0, dU0 = res[0]
+        for x, a, k, r, p, U, dU in res[1:]:
+            assert np.array_equal(k, k0) and np.array_equal(r, r0) and np.array_equal(p, p0)
+            assert np.abs(x - x0).max() <= 1e-9 and rel_force_err(a, a0) <= 1e-9
+            assert abs(U - U0) <= 1e-11 * abs(U0) and abs(dU - dU0) <= 1e-11 * abs(U0)
 
 
 def test_async_snapshot_equals_blocking_readback(orc):

@@ -152,8 +152,8 @@ def test_slab_errors_are_loud(bilayer):
     grp.close()
     grp = LocalSlabGroup(bad, 2)
     grp.compute_forces()
-    grp.step(0, 1)
-    with pytest.raises(sm.SoftMoldError, match="halo"):
+    with pytest.raises(sm.SoftMoldError, match="halo"):    # reported at the first synchronisation point
+        grp.step(0, 1)
         grp.synchronize()
     for c in grp.ctx:
         c.close()
