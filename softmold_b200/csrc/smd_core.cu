@@ -247,7 +247,13 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->n_molecules = 0;
 	ctx->launches = ctx->rebuilds = 0;
 	{ const char *e = getenv("SMD_ENERGY_ONEPHASE"); ctx->force_onephase_energy = e && *e == '1'; }
+	// SMD_NO_FUSE=1: every phase of the step in its own kernel (A/B and bit-identity tests).
+	// SMD_PAIR_SEAM=1: run the step seam in the epilogue of the pair kernel instead of a kernel of its own (k_chain_kick).
+	// Bit-identical; measured on C2: the pair kernel grows from 156.5 to 173.3 us while the 20.4 us seam kernel disappears
+	// (-3.7 us per step, nothing once the unfused step before every box move is counted): the seam's chain of dependent
+	// gathers keeps a 128-register block resident ~10 k cycles longer instead of hiding behind the other blocks.  Off.
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
+	{ const char *e = getenv("SMD_PAIR_SEAM"); ctx->no_pair_fuse = !(e && *e == '1'); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
 	ctx->pcur = 0;
@@ -346,6 +352,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 		cudaError_t e1 = cudaSuccess;
 		if (smem > have) {
 			e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1016,9 +1023,15 @@ static NeighLists neigh_lists(smd_ctx *ctx)
 
 // the pair force of all particles into acc[] (LANGEVIN: a = thermostat term + pair sum, else a += pair sum)
 template <bool LANGEVIN>
-static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
+static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg, const SeamArgs *seam = nullptr)
 {
 	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
+	if (seam) {   // forces + Langevin + the step seam in one kernel (see SeamArgs); the caller checked pair_fusable()
+		LAUNCH((k_pair_force2<0, true, true, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16,
+		       *seam);
+		return SMD_OK;
+	}
 	if (ctx->pair_split) {
 		const int dsm = PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double);
 		LAUNCH(k_pair_lists<0>, nb, PAIR_TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
@@ -1033,14 +1046,14 @@ static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
 	}
 	if (ctx->tables_symmetric)
 		LAUNCH((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
 	else
 		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
 	return SMD_OK;
 }
 
-static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first)
+static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first, const SeamArgs *seam = nullptr)
 {
 	int N = ctx->N;
 	// CellOpt::build: always rebuilt (the reference rebuilds every step, MD.cpp:412)
@@ -1065,8 +1078,14 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		lg.seed = ctx->desc.seed; lg.step = (uint64_t)step;
 		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
 		ProfScope ps(ctx, SMD_PHASE_PAIR);
-		if ((rc = launch_pair_force<true>(ctx, lg))) return rc;
-		ctx->acc_live = true;
+		SeamArgs sa;
+		if (seam) {
+			sa = *seam;
+			sa.pos_out = ctx->pos[ctx->pcur ^ 1]; sa.vel = ctx->vel[ctx->cur]; sa.unw = ctx->unw[ctx->cur];
+			seam = &sa;
+		}
+		if ((rc = launch_pair_force<true>(ctx, lg, seam))) return rc;
+		ctx->acc_live = !seam;   // the fused kernel consumes the acceleration in registers
 	} else {
 		LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->acc);
 		ctx->acc_live = true;
@@ -1142,12 +1161,23 @@ extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
 
 // CHAIN-only systems: the seam between two consecutive steps (chain forces, Verlet::second, next Verlet::first) is
 // one kernel, see k_chain_kick
+// The fused step seam (k_chain_kick) gathers the CHAIN terms per particle and applies both half kicks; list molecules and
+// one-body fields (BOND, BEND, BALL, BOUNDARY, ...) scatter into a[] with atomics BEFORE it.  BEAD / NANOCORE systems keep
+// the separate kernels: their particles are divided by the bead mass between the two half kicks (MD.cpp:340-355, :480-508).
+static bool has_nanocore(const smd_ctx *ctx)
+{
+	for (auto &f : ctx->fields) if (f.kind == SMD_MOL_NANOCORE) return true;
+	return false;
+}
 static bool can_fuse(const smd_ctx *ctx)
 {
-	return !ctx->no_fuse && ctx->bonds.empty() && ctx->bends.empty() && ctx->beads.empty() && ctx->balls.empty() && ctx->fields.empty() &&
-	       (int)ctx->chains.size() <= MAX_FUSED_CHAINS && ctx->desc.noise != SMD_NOISE_EXTERNAL;
+	return !ctx->no_fuse && ctx->beads.empty() && !has_nanocore(ctx) && (int)ctx->chains.size() <= MAX_FUSED_CHAINS &&
+	       ctx->desc.noise != SMD_NOISE_EXTERNAL;
 }
-
+static bool only_chains(const smd_ctx *ctx)
+{
+	return ctx->bonds.empty() && ctx->bends.empty() && ctx->balls.empty() && ctx->fields.empty() && ctx->beads.empty();
+}
 static ChainSet chain_set(const smd_ctx *ctx)
 {
 	ChainSet cs;
@@ -1176,12 +1206,28 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	if (rc) return rc;
 	const ChainSet cs = chain_set(ctx);
 	const int N = ctx->N;
+	const bool pair_fusable = !ctx->no_pair_fuse && ctx->tables_symmetric && !ctx->pair_split && only_chains(ctx);
+	// molecule kinds that add to a[] before the seam (none for CHAIN-only systems)
+	const uint32_t scatter = only_chains(ctx) ? 0u : (SMD_MASK(SMD_TERM_BOND) | SMD_MASK(SMD_TERM_BEND) | SMD_MASK(SMD_TERM_BALL) | SMD_MASK(SMD_TERM_FIELD));
 	for (int k = 0; k < nsteps; k++) {
 		ProfScope ps(ctx, SMD_PHASE_STEP);
-		// MD.cpp:410-413: thermostat, build, pair force (one kernel) -- no molecule terms here
-		rc = forces(ctx, SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_LANGEVIN, first_step + k, true);
-		if (rc) return rc;
 		const bool last = (k == nsteps - 1);
+		if (!last && pair_fusable) {
+			// thermostat, build, pair force, chain terms, Verlet::second, next Verlet::first: the build + ONE kernel
+			SeamArgs sa;
+			sa.pos_out = nullptr; sa.vel = nullptr; sa.unw = nullptr;   // filled in by forces() once the build has flipped the buffers
+			sa.slot_of = ctx->slot_of; sa.cs = cs; sa.dt = ctx->desc.dt; sa.bbox = ctx->bbox; sa.errflag = ctx->errflag;
+			rc = forces(ctx, SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_LANGEVIN, first_step + k, true, &sa);
+			if (rc) return rc;
+			ctx->pcur ^= 1;
+			ctx->acc_live = false;
+			ctx->cells_valid = false;
+			if (ctx->slab && (rc = smd_slab_exchange_send(ctx))) return rc;
+			continue;
+		}
+		// MD.cpp:410-413: thermostat, build, pair force (one kernel); then the scattering molecule kinds, if any
+		rc = forces(ctx, SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_LANGEVIN | scatter, first_step + k, true);
+		if (rc) return rc;
 		ProfScope pf(ctx, SMD_PHASE_FUSED);
 		if (last) {
 			LAUNCH(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
@@ -1237,7 +1283,7 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 			       ctx->geom, ctx->nT, ctx->uC, ctx->utab, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, neigh_lists(ctx));
 		} else {
 			LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
-			       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, ctx->pos16);
+			       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, ctx->pos16, SeamArgs{});
 		}
 		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
 	} else {

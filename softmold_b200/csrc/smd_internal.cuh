@@ -143,6 +143,7 @@ struct smd_ctx {
 	int *nl_rng = nullptr, *nl_cnt = nullptr;
 	double *nl_part = nullptr;
 	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)
+	bool no_pair_fuse = true;    // unless SMD_PAIR_SEAM=1: the step seam is a kernel of its own, not the pair kernel's epilogue
 	double *acc;      // SoA [3][cap]
 	double *acc2;     // alternate buffer for builds that must carry live accelerations along
 	bool acc_live;    // acc holds forces a later kick still needs

@@ -1055,15 +1055,24 @@ struct PairSmem {
 // cutoff (a pair outside rc before the move and inside after it still has a term).
 struct EnergyArgs { double sx, sy, sz; float extra32; double *partials; };
 
-template <int EMODE, bool LANGEVIN, bool SYMM>
+// FUSE (forces with the Langevin term only): the thread that has just finished a particle's pair sum also runs the
+// step seam for it -- the particle's chain terms, Verlet::second of this step and Verlet::first of the next one, wrap,
+// cell tag (what k_chain_kick<false> does in a kernel of its own, same arithmetic in the same order: bit-identical) --
+// and writes the new position into the OTHER position buffer, which nobody reads during this kernel.  a[] is never
+// stored.  The seam's chain of dependent gathers (gid -> slot_of -> neighbour record) hides behind the other blocks'
+// pair work instead of being a latency-bound 20 us kernel.
+struct SeamArgs { Particle *pos_out; double *vel; double *unw; const int *slot_of; ChainSet cs; double dt; int *bbox; int *errflag; };
+
+template <int EMODE, bool LANGEVIN, bool SYMM, bool FUSE = false>
 __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
                                                             const int *__restrict__ win, Geom g, int nT,
                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
                                                             PairGeo pg, double *__restrict__ acc, LangevinArgs lg,
                                                             const int *__restrict__ gid, EnergyArgs en,
-                                                            const uint2 *__restrict__ pos16)
+                                                            const uint2 *__restrict__ pos16, SeamArgs sa)
 {
+	static_assert(!FUSE || (EMODE == 0 && LANGEVIN), "the step seam follows the force + Langevin evaluation");
 	const int N = cnt.get();
 	if ((int)(blockIdx.x * PAIR_TPB) >= N) {
 		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
@@ -1630,7 +1639,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const int o = sm.order[tid];
 	const int io = sm.perm[o];
 	const bool act = io < N && !(g.slab && (gid[io] & GID_GHOST));
-	if (EMODE == 0 && !act) return;
+	if (EMODE == 0 && !FUSE && !act) return;
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
 	if (act) {
 		const Particle po = load_particle(pos + io);
@@ -1645,6 +1654,50 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		__syncthreads();
 		double tot = block_sum(sm.part[0][tid]);
 		if (tid == 0) en.partials[blockIdx.x] = tot;
+		return;
+	}
+	if (FUSE) {
+		const bool valid = io < N;
+		Particle p;
+		p.x = p.y = p.z = 0; p.type = 0; p.cell = 0;
+		int gi = 0;
+		if (valid) { p = load_particle(pos + io); gi = gid[io]; }
+		if (act) {
+			const int id = gi & GID_MASK;
+			double u[3];
+			if (lg.ext_noise) {
+				u[0] = lg.ext_noise[3 * id]; u[1] = lg.ext_noise[3 * id + 1]; u[2] = lg.ext_noise[3 * id + 2];
+			} else {
+				philox_uniform3(lg.seed, lg.step, (uint32_t)id, u);
+			}
+			double vx = sa.vel[io], vy = sa.vel[cap + io], vz = sa.vel[2 * cap + io];
+			// a = (Langevin + pair sum) + chain terms: the two sums k_pair_force2 and k_chain_kick would have formed
+			double fx = (-lg.gamma * vx + lg.sigma * (2.0 * u[0] - 1.0)) + ax;
+			double fy = (-lg.gamma * vy + lg.sigma * (2.0 * u[1] - 1.0)) + ay;
+			double fz = (-lg.gamma * vz + lg.sigma * (2.0 * u[2] - 1.0)) + az;
+			V3 A;
+			if (!chain_gather(id, p, N, pos, gid, sa.slot_of, g, sa.cs, A)) atomicOr(sa.errflag, ERR_SLAB_MISSING);
+			fx = fx + A.x; fy = fy + A.y; fz = fz + A.z;
+			if (p.type != 0) {
+				const double h = 0.5 * sa.dt;
+				vx += (fx * h); vy += (fy * h); vz += (fz * h);                                 // Verlet::second of this step
+				vx += (fx * h); vy += (fy * h); vz += (fz * h);                                 // Verlet::first of the next one
+				p.x += vx * sa.dt; p.y += vy * sa.dt; p.z += vz * sa.dt;
+				if (sa.unw) { sa.unw[io] += vx * sa.dt; sa.unw[cap + io] += vy * sa.dt; sa.unw[2 * cap + io] += vz * sa.dt; }
+				sa.vel[io] = vx; sa.vel[cap + io] = vy; sa.vel[2 * cap + io] = vz;
+			}
+			if (p.x > g.box[0]) p.x -= g.box[0];
+			if (p.x < 0) p.x += g.box[0];
+			if (p.y > g.box[1]) p.y -= g.box[1];
+			if (p.y < 0) p.y += g.box[1];
+			if (p.z > g.box[2]) p.z -= g.box[2];
+			if (p.z < 0) p.z += g.box[2];
+		}
+		tag_cell(p, g, sa.bbox, sa.errflag, act);
+		if (valid) {
+			if (!act) p.cell = CELL_DEAD;   // slab ghost: replaced by the exchange that follows
+			store_particle(sa.pos_out + io, p);
+		}
 		return;
 	}
 	if (LANGEVIN) {

@@ -273,8 +273,9 @@ def test_two_phase_energy_kernels_match_one_phase(orc):
 
 @pytest.mark.parametrize("case", ["lipo_eq", "bilayer_eq", "lipocyto_chains"])
 def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
-    """smd_step fuses chain forces + Verlet::second + the next Verlet::first into one per-particle kernel for
-    CHAIN-only systems; the trajectory must not change by a single bit against the separate kernels"""
+    """smd_step fuses chain forces + Verlet::second + the next Verlet::first into one per-particle kernel for CHAIN-only
+    systems (SMD_PAIR_SEAM=1: into the epilogue of the pair kernel; SMD_NO_FUSE=1: separate kernels); the trajectory must
+    not change by a single bit"""
     import os
     if case == "lipocyto_chains":      # two CHAIN molecules of different length (3 and 10), explicit BOND list dropped
         m, _ = orc.load_golden(golden_path("lipocyto_eq"))
@@ -282,21 +283,52 @@ def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
     else:
         m, _ = orc.load_golden(golden_path(case))
     out = []
-    for env in ("0", "1"):
-        os.environ["SMD_NO_FUSE"] = env
+    for env in ({"SMD_PAIR_SEAM": "1"}, {}, {"SMD_NO_FUSE": "1"}):
+        os.environ.update(env)
         try:
             ctx = sm.Context.from_dict(m, track_unwrapped=True)
         finally:
-            del os.environ["SMD_NO_FUSE"]
+            for k in env:
+                del os.environ[k]
         ctx.compute_forces(step=5)
         ctx.step(5, 33)
         ctx.step(38, 1)
         ctx.step(39, 7)
         out.append(ctx.get_particles() + (ctx.get_forces(), ctx.get_unwrapped(), ctx.stats()[0]))
         ctx.close()
-    (x0, _, v0, a0, u0, l0), (x1, _, v1, a1, u1, l1) = out
+    (x0, _, v0, a0, u0, l0), (x2, _, v2, a2, u2, l2), (x1, _, v1, a1, u1, l1) = out
     assert np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(a0, a1) and np.array_equal(u0, u1)
-    assert l0 < l1          # fewer launches: the fused path did run
+    assert np.array_equal(x2, x1) and np.array_equal(v2, v1) and np.array_equal(a2, a1) and np.array_equal(u2, u1)
+    assert l0 < l2 < l1     # fewer launches: the fused paths did run
+
+
+@pytest.mark.parametrize("case", ["bondbend", "lipocyto_eq", "ball", "fields_no_nanocore"])
+def test_fused_step_kernel_with_list_molecules_and_fields(orc, case):
+    """systems with BOND / BEND / BALL lists or one-body fields next to (or without) CHAIN blocks also take the fused step
+    seam: their kernels scatter into a[] before it.  Only the order in which a particle's terms are added differs from the
+    separate kernels, so the trajectories agree to rounding (not to the bit); BEAD / NANOCORE systems stay unfused."""
+    import os
+    m, _ = orc.load_golden(golden_path("fields" if case == "fields_no_nanocore" else case))
+    if case == "fields_no_nanocore":
+        m = dict(m, molecules=[mol for mol in m["molecules"] if mol["type"] != sm.MOL_NANOCORE])
+    m = dict(m, initialTime=0.0)
+    out = []
+    for env in ("0", "1"):
+        os.environ["SMD_NO_FUSE"] = env
+        try:
+            ctx = sm.Context.from_dict(m, track_unwrapped=True)
+        finally:
+            del os.environ["SMD_NO_FUSE"]
+        ctx.compute_forces(step=0)
+        ctx.step(0, 24)
+        ctx.step(24, 1)
+        ctx.step(25, 6)
+        out.append(ctx.get_particles() + (ctx.get_forces(), ctx.get_unwrapped(), ctx.stats()[0]))
+        ctx.close()
+    (x0, _, v0, a0, u0, l0), (x1, _, v1, a1, u1, l1) = out
+    assert l0 < l1                       # the fused path did run
+    assert np.abs(x0 - x1).max() <= 1e-9 and np.abs(v0 - v1).max() <= 1e-8 and np.abs(u0 - u1).max() <= 1e-9
+    assert rel_force_err(a0, a1) <= 1e-9
 
 
 def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
