@@ -696,6 +696,8 @@ static int add_field(smd_ctx *ctx, int kind, int32_t n, const int32_t *idx, cons
 		if (rc) return rc;
 	}
 	if (blocks) f.blocks.assign(blocks, blocks + (size_t)n * width);
+	if (kind == SMD_MOL_NANOCORE)
+		for (int j = 0; j < n; j++) { f.host_idx.push_back(idx[j]); f.host_radius.push_back(C[22 * j + 4]); }   // BEADRADIUS, MD.h:53
 	if (C && nC) {
 		CK(cudaMalloc(&f.d_C, nC * sizeof(double)));
 		CK(cudaMemcpy(f.d_C, C, nC * sizeof(double), cudaMemcpyHostToDevice));
@@ -1161,18 +1163,30 @@ extern "C" int smd_step_end(smd_ctx *ctx, int64_t step)
 
 // CHAIN-only systems: the seam between two consecutive steps (chain forces, Verlet::second, next Verlet::first) is
 // one kernel, see k_chain_kick
-// The fused step seam (k_chain_kick) gathers the CHAIN terms per particle and applies both half kicks; list molecules and
-// one-body fields (BOND, BEND, BALL, BOUNDARY, ...) scatter into a[] with atomics BEFORE it.  BEAD / NANOCORE systems keep
-// the separate kernels: their particles are divided by the bead mass between the two half kicks (MD.cpp:340-355, :480-508).
-static bool has_nanocore(const smd_ctx *ctx)
+// The fused step seam (k_chain_kick) gathers the CHAIN terms per particle and applies both half kicks; every other
+// molecule kind (BOND, BEND, BALL, BEAD, NANOCORE, the one-body fields) scatters into a[] with atomics BEFORE it.  The
+// continuum-sphere particles of BEAD / NANOCORE molecules are divided by their mass inside the seam (BeadSet).
+static bool bead_set(const smd_ctx *ctx, BeadSet &bs)
 {
-	for (auto &f : ctx->fields) if (f.kind == SMD_MOL_NANOCORE) return true;
-	return false;
+	bs.n = 0;
+	auto add = [&](int id, double R, int twice) {
+		for (int k = 0; k < bs.n; k++) if (bs.id[k] == id) return false;   // listed twice: divided twice, leave it to the plain path
+		if (bs.n >= MAX_FUSED_BEADS) return false;
+		bs.id[bs.n] = id; bs.twice[bs.n] = twice; bs.mass[bs.n] = (4.0) * M_PI * R * R;   // MD.cpp:346
+		bs.n++;
+		return true;
+	};
+	for (auto &b : ctx->beads)
+		for (int id : b.own) if (!add(id, b.radius, 1)) return false;
+	for (auto &f : ctx->fields)
+		if (f.kind == SMD_MOL_NANOCORE)
+			for (int j = 0; j < f.n; j++) if (!add(f.host_idx[j], f.host_radius[j], 0)) return false;
+	return true;
 }
 static bool can_fuse(const smd_ctx *ctx)
 {
-	return !ctx->no_fuse && ctx->beads.empty() && !has_nanocore(ctx) && (int)ctx->chains.size() <= MAX_FUSED_CHAINS &&
-	       ctx->desc.noise != SMD_NOISE_EXTERNAL;
+	BeadSet bs;
+	return !ctx->no_fuse && bead_set(ctx, bs) && (int)ctx->chains.size() <= MAX_FUSED_CHAINS && ctx->desc.noise != SMD_NOISE_EXTERNAL;
 }
 static bool only_chains(const smd_ctx *ctx)
 {
@@ -1205,10 +1219,12 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	int rc = smd_step_begin(ctx, first_step);
 	if (rc) return rc;
 	const ChainSet cs = chain_set(ctx);
+	BeadSet bs;
+	bead_set(ctx, bs);
 	const int N = ctx->N;
 	const bool pair_fusable = !ctx->no_pair_fuse && ctx->tables_symmetric && !ctx->pair_split && only_chains(ctx);
 	// molecule kinds that add to a[] before the seam (none for CHAIN-only systems)
-	const uint32_t scatter = only_chains(ctx) ? 0u : (SMD_MASK(SMD_TERM_BOND) | SMD_MASK(SMD_TERM_BEND) | SMD_MASK(SMD_TERM_BALL) | SMD_MASK(SMD_TERM_FIELD));
+	const uint32_t scatter = only_chains(ctx) ? 0u : (SMD_MASK_ALL_MOLECULES & ~SMD_MASK(SMD_TERM_CHAIN));
 	for (int k = 0; k < nsteps; k++) {
 		ProfScope ps(ctx, SMD_PHASE_STEP);
 		const bool last = (k == nsteps - 1);
@@ -1231,11 +1247,11 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 		ProfScope pf(ctx, SMD_PHASE_FUSED);
 		if (last) {
 			LAUNCH(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag);
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs);
 		} else {
 			LAUNCH(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
 			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
-			       ctx->errflag);
+			       ctx->errflag, bs);
 			ctx->pcur ^= 1;
 			ctx->acc_live = false;
 			ctx->cells_valid = false;

@@ -100,6 +100,8 @@ struct FieldMol {
 	double *d_C;               // device constants (FLOATING_BASE 6*nT, NANOCORE 22*n)
 	double c[4];               // host constants (BOUNDARY, ZTORQUE, ZPOWERPOTENTIAL)
 	std::vector<int> blocks;   // host block records (ZTORQUE [n][3], ZPOWERPOTENTIAL [n][2])
+	std::vector<int> host_idx;          // NANOCORE: host copy of the bead indices and radii (mass division in the fused seam)
+	std::vector<double> host_radius;
 };
 struct BeadMol {
 	int nOwn, nAll;        // beads of this molecule / of the list assembled from molecules j >= i (system.h:2053-2070)

@@ -2044,10 +2044,17 @@ __global__ void __launch_bounds__(TPB) k_slab_export(Cnt cnt, int cap, const Par
 #ifndef SMD_KICK_BLOCKS
 #define SMD_KICK_BLOCKS 5   // 96 registers with a few spilled words beat 122 registers at 4 blocks (22.9 vs 25.1 us on C2)
 #endif
+// Continuum-sphere particles (BEAD and NANOCORE molecules) are divided by their "mass" 4 pi R^2 between the force
+// evaluation and the kicks: BEAD beads before Verlet::second (MD.cpp:480-494) AND again before the next Verlet::first
+// (:340-355, quirk Q3), NANOCORE beads only before Verlet::second (:495-508).  A handful of particles: a by-value list.
+constexpr int MAX_FUSED_BEADS = 8;
+struct BeadSet { int n; int id[MAX_FUSED_BEADS]; int twice[MAX_FUSED_BEADS]; double mass[MAX_FUSED_BEADS]; };
+
 template <bool LAST>
 __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
                                                     double *vel, double *acc, double *unw, const int *__restrict__ gid,
-                                                    const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag)
+                                                    const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag,
+                                                    BeadSet bs)
 {
 	const int N = cnt.get();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2060,13 +2067,20 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 		V3 A;
 		if (!chain_gather(gi & GID_MASK, p, N, pos_in, gid, slot_of, g, cs, A)) atomicOr(errflag, ERR_SLAB_MISSING);
 		double ax = acc[s] + A.x, ay = acc[cap + s] + A.y, az = acc[2 * cap + s] + A.z;   // Blob::doChainForce: a += chain terms
+		double bx = ax, by = ay, bz = az;   // the acceleration the NEXT Verlet::first sees
+		for (int b = 0; b < bs.n; b++)
+			if ((gi & GID_MASK) == bs.id[b]) {
+				ax /= bs.mass[b]; ay /= bs.mass[b]; az /= bs.mass[b];                       // MD.cpp:480-508
+				bx = ax; by = ay; bz = az;
+				if (bs.twice[b]) { bx /= bs.mass[b]; by /= bs.mass[b]; bz /= bs.mass[b]; }  // MD.cpp:340-355
+			}
 		if (LAST) { acc[s] = ax; acc[cap + s] = ay; acc[2 * cap + s] = az; }
 		if (p.type != 0) {
 			double h = 0.5 * dt;
 			double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
 			vx += (ax * h); vy += (ay * h); vz += (az * h);                                 // Verlet::second of this step
 			if (!LAST) {
-				vx += (ax * h); vy += (ay * h); vz += (az * h);                             // Verlet::first of the next one
+				vx += (bx * h); vy += (by * h); vz += (bz * h);                             // Verlet::first of the next one
 				p.x += vx * dt; p.y += vy * dt; p.z += vz * dt;
 				if (unw) { unw[s] += vx * dt; unw[cap + s] += vy * dt; unw[2 * cap + s] += vz * dt; }
 			}
