@@ -38,6 +38,9 @@ static inline int nblk(long long n, int tpb) { return (int)std::max<long long>(1
 	} while (0)
 
 static const int MAX_PARTIALS = 1 << 20;
+#ifndef SMD_DEFAULT_CHUNKS
+#define SMD_DEFAULT_CHUNKS 1
+#endif
 
 // particle count of a launch: by value on a single GPU, from the device word in slab mode (ctx->N is then only the
 // launch bound).  cnt_ext: the count after an unpack (received particles appended, dead ghosts still in place).
@@ -254,11 +257,13 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	// gathers keeps a 128-register block resident ~10 k cycles longer instead of hiding behind the other blocks.  Off.
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_PAIR_SEAM"); ctx->no_pair_fuse = !(e && *e == '1'); }
+	{ const char *e = getenv("SMD_CHUNKS"); int v = e ? atoi(e) : SMD_DEFAULT_CHUNKS; ctx->chunks = std::min(std::max(v, 1), 8); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
 	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
 	ctx->pgeo.rmin32 = (float)desc->cutoff;
+	ctx->pgeo.block0 = 0;
 	int rc = check_geom(ctx);
 	if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
 
@@ -407,6 +412,8 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto &f : ctx->fields) { cudaFree(f.d_idx); cudaFree(f.d_C); }
 	prof_drain(ctx);
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
+	for (int c = 0; c < 8; c++) { if (ctx->cstream[c]) cudaStreamDestroy(ctx->cstream[c]); if (ctx->ev_chunk[c]) cudaEventDestroy(ctx->ev_chunk[c]); }
+	if (ctx->ev_build) cudaEventDestroy(ctx->ev_build);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 	return SMD_OK;
@@ -1201,6 +1208,75 @@ static ChainSet chain_set(const smd_ctx *ctx)
 	return cs;
 }
 
+// One MD step of the fused path as a pipeline over `chunks` runs of blocks (see smd_ctx::chunks): build on the main stream,
+// then per chunk, on its own stream (earlier chunks at higher priority): pair force + Langevin of the chunk's particles,
+// the chunk's step seam.  A seam only needs the accelerations of its own particles and writes the OTHER position buffer,
+// so the seam of chunk c runs beside the pair kernel of chunk c + 1.  Same kernels, same arithmetic: bit-identical.
+static int step_chunked(smd_ctx *ctx, int64_t step, bool last, const ChainSet &cs, const BeadSet &bs)
+{
+	const int N = ctx->N, C = ctx->chunks;
+	if (!ctx->ev_build) {
+		int least = 0, greatest = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));   // numerically lower = higher priority
+		CK(cudaEventCreateWithFlags(&ctx->ev_build, cudaEventDisableTiming));
+		for (int c = 0; c < C; c++) {
+			CK(cudaStreamCreateWithPriority(&ctx->cstream[c], cudaStreamNonBlocking, std::min(greatest + c, least)));
+			CK(cudaEventCreateWithFlags(&ctx->ev_chunk[c], cudaEventDisableTiming));
+		}
+	}
+	ctx->acc_live = false;
+	if (!ctx->cells_valid) { ProfScope ps(ctx, SMD_PHASE_BUILD); build_cells(ctx); }
+	LangevinArgs lg = {};
+	lg.gamma = ctx->desc.gamma;
+	lg.sigma = langevin_sigma(ctx);
+	lg.seed = ctx->desc.seed; lg.step = (uint64_t)step;
+	lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
+	cudaStream_t main_stream = ctx->stream;
+	CK(cudaEventRecord(ctx->ev_build, main_stream));
+	const int nb = nblk(N, PAIR_TPB);
+	const bool prof_pair = (ctx->prof_mask >> SMD_PHASE_PAIR) & 1u;
+	cudaEvent_t e0 = nullptr;
+	const PairGeo pg_keep = ctx->pgeo;
+	for (int c = 0; c < C; c++) {
+		const int b0 = (int)((long long)nb * c / C), b1 = (int)((long long)nb * (c + 1) / C);
+		if (b1 <= b0) continue;
+		cudaStream_t st = ctx->cstream[c];
+		CK(cudaStreamWaitEvent(st, ctx->ev_build, 0));
+		if (prof_pair && !e0) { e0 = prof_event(ctx); cudaEventRecord(e0, st); }
+		ctx->stream = st;   // LAUNCH goes to ctx->stream
+		PairGeo pg = pg_keep;
+		pg.block0 = b0;
+		if (ctx->tables_symmetric)
+			LAUNCH((k_pair_force2<0, true, true>), b1 - b0, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
+		else
+			LAUNCH((k_pair_force2<0, true, false>), b1 - b0, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
+		if (prof_pair && c == C - 1) {   // the span of the chunks' pair kernels (seams of earlier chunks run inside it)
+			cudaEvent_t e1 = prof_event(ctx);
+			cudaEventRecord(e1, st);
+			ctx->prof_pending.push_back({SMD_PHASE_PAIR, e0, e1});
+		}
+		if (last)
+			LAUNCH(k_chain_kick<true>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur], ctx->acc,
+			       ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB);
+		else
+			LAUNCH(k_chain_kick<false>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1], ctx->vel[ctx->cur],
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB);
+		ctx->stream = main_stream;
+		CK(cudaEventRecord(ctx->ev_chunk[c], st));
+		CK(cudaStreamWaitEvent(main_stream, ctx->ev_chunk[c], 0));
+	}
+	if (last) {
+		ctx->acc_live = true;
+	} else {
+		ctx->pcur ^= 1;
+		ctx->acc_live = false;
+		ctx->cells_valid = false;
+	}
+	return SMD_OK;
+}
+
 extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 {
 	if (!ctx) return SMD_ERR_ARG;
@@ -1225,9 +1301,15 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	const bool pair_fusable = !ctx->no_pair_fuse && ctx->tables_symmetric && !ctx->pair_split && only_chains(ctx);
 	// molecule kinds that add to a[] before the seam (none for CHAIN-only systems)
 	const uint32_t scatter = only_chains(ctx) ? 0u : (SMD_MASK_ALL_MOLECULES & ~SMD_MASK(SMD_TERM_CHAIN));
+	static_assert(TPB == PAIR_TPB, "the step pipeline cuts the pair grid and the seam grid at the same slots");
+	const bool chunked = ctx->chunks > 1 && !ctx->slab && !ctx->pair_split && only_chains(ctx) && !pair_fusable && N >= 2 * PAIR_TPB * ctx->chunks;
 	for (int k = 0; k < nsteps; k++) {
 		ProfScope ps(ctx, SMD_PHASE_STEP);
 		const bool last = (k == nsteps - 1);
+		if (chunked) {
+			if ((rc = step_chunked(ctx, first_step + k, last, cs, bs))) return rc;
+			continue;
+		}
 		if (!last && pair_fusable) {
 			// thermostat, build, pair force, chain terms, Verlet::second, next Verlet::first: the build + ONE kernel
 			SeamArgs sa;
@@ -1247,11 +1329,11 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 		ProfScope pf(ctx, SMD_PHASE_FUSED);
 		if (last) {
 			LAUNCH(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs);
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0);
 		} else {
 			LAUNCH(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
 			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
-			       ctx->errflag, bs);
+			       ctx->errflag, bs, 0);
 			ctx->pcur ^= 1;
 			ctx->acc_live = false;
 			ctx->cells_valid = false;

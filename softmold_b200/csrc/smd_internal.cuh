@@ -87,6 +87,7 @@ struct PairGeo {            // phase-1 constants of k_pair_force2
 	float cs32[3];          // cell size
 	float rmin32;           // smallest positive per-type phase-1 radius (pos16 path: widening of the energy modes' cutoffs)
 	float finv32;           // x slices per unit length (Geom::finv)
+	int block0;             // first block of this launch when the grid is launched in chunks (else 0)
 };
 
 struct ChainBlock { int start, nChains, len; double c[4]; };
@@ -144,6 +145,14 @@ struct smd_ctx {
 	unsigned short *nl_ent = nullptr;   // two-kernel pair engine: global candidate lists (smd_pair_split.cuh)
 	int *nl_rng = nullptr, *nl_cnt = nullptr;
 	double *nl_part = nullptr;
+	// step pipeline (smd_step, single GPU, CHAIN-only systems; SMD_CHUNKS, default 1 = off): the particles are cut into
+	// `chunks` runs of blocks, each with its own stream: pair force of the chunk, then its step seam, so that the seam of one
+	// chunk could overlap the pair kernel of the next.  Bit-identical.  Measured on C2 (us per MD step): 1 chunk 229.0,
+	// 2: 236.8, 3: 224.8, 4: 233.1, 6: 229.8 -- no consistent gain: the pair kernel's four resident blocks hold the whole
+	// register file of an SM, so a seam block only ever starts in a pair chunk's tail, and every chunk adds a tail.
+	int chunks = 1;
+	cudaStream_t cstream[8] = {};
+	cudaEvent_t ev_build = nullptr, ev_chunk[8] = {};
 	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)
 	bool no_pair_fuse = true;    // unless SMD_PAIR_SEAM=1: the step seam is a kernel of its own, not the pair kernel's epilogue
 	double *acc;      // SoA [3][cap]

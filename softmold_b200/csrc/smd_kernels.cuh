@@ -1074,7 +1074,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 {
 	static_assert(!FUSE || (EMODE == 0 && LANGEVIN), "the step seam follows the force + Langevin evaluation");
 	const int N = cnt.get();
-	if ((int)(blockIdx.x * PAIR_TPB) >= N) {
+	const int bid = (int)blockIdx.x + pg.block0;   // block0 != 0: one chunk of a grid launched in pieces (forces only)
+	if (bid * PAIR_TPB >= N) {
 		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
 		return;
 	}
@@ -1107,7 +1108,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (tid < PAIR_NSEG) {
-		const int sf = blockIdx.x * PAIR_TPB, sl = min(sf + PAIR_TPB, N) - 1;
+		const int sf = bid * PAIR_TPB, sl = min(sf + PAIR_TPB, N) - 1;
 		auto lin_of = [&](int s_) {
 			int ax, ay, az;
 			unpack_cell(pos[s_].cell, ax, ay, az);
@@ -1126,7 +1127,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 
 	// ---- deal the block's particles to threads by class
 	{
-		const int i0 = blockIdx.x * PAIR_TPB + tid;
+		const int i0 = bid * PAIR_TPB + tid;
 		const bool heavy = (i0 < N) && pos32[i0].w >= pg.thr32;
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
 		if (lane == 0) sm.wcnt[wid] = __popc(bal);
@@ -2054,10 +2055,10 @@ template <bool LAST>
 __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
                                                     double *vel, double *acc, double *unw, const int *__restrict__ gid,
                                                     const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag,
-                                                    BeadSet bs)
+                                                    BeadSet bs, int slot0)
 {
 	const int N = cnt.get();
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	int s = slot0 + blockIdx.x * blockDim.x + threadIdx.x;   // slot0 != 0: one chunk of the step pipeline (smd_step)
 	bool valid = s < N;
 	Particle p;
 	int gi = 0;

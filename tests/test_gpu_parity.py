@@ -283,7 +283,9 @@ def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
     else:
         m, _ = orc.load_golden(golden_path(case))
     out = []
-    for env in ({"SMD_PAIR_SEAM": "1"}, {}, {"SMD_NO_FUSE": "1"}):
+    envs = ({"SMD_PAIR_SEAM": "1", "SMD_CHUNKS": "1"}, {"SMD_CHUNKS": "3"}, {"SMD_CHUNKS": "2"}, {"SMD_CHUNKS": "1"},
+            {"SMD_NO_FUSE": "1"})
+    for env in envs:
         os.environ.update(env)
         try:
             ctx = sm.Context.from_dict(m, track_unwrapped=True)
@@ -296,10 +298,11 @@ def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
         ctx.step(39, 7)
         out.append(ctx.get_particles() + (ctx.get_forces(), ctx.get_unwrapped(), ctx.stats()[0]))
         ctx.close()
-    (x0, _, v0, a0, u0, l0), (x2, _, v2, a2, u2, l2), (x1, _, v1, a1, u1, l1) = out
-    assert np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(a0, a1) and np.array_equal(u0, u1)
-    assert np.array_equal(x2, x1) and np.array_equal(v2, v1) and np.array_equal(a2, a1) and np.array_equal(u2, u1)
-    assert l0 < l2 < l1     # fewer launches: the fused paths did run
+    x1, _, v1, a1, u1, l1 = out[-1]                 # separate kernels
+    for x, _, v, a, u, l in out[:-1]:
+        assert np.array_equal(x, x1) and np.array_equal(v, v1) and np.array_equal(a, a1) and np.array_equal(u, u1)
+    assert out[0][5] < out[3][5] < l1               # launches: pair-epilogue seam < seam kernel < separate kernels
+    assert out[1][5] > out[2][5] > out[3][5]        # the step pipeline did cut the grids into 3 / 2 chunks
 
 
 @pytest.mark.parametrize("case", ["bondbend", "lipocyto_eq", "ball", "fields", "bead1", "bead2"])
