@@ -424,7 +424,10 @@ int main(int argc, char *argv[])
 		int div = int((finalTime - initialTime) / tempStepInterval);
 		tempStepInt = div ? (endInt - startInt) / div : 0;
 	}
-	const int resizeRate = 8;   // MD.cpp:67
+	// MD.cpp:67 `#define resizeRate 8`; the driver variant MDanneal.cpp:67 is the same loop with `resizeRate 4` (its temperature
+	// ramp is the tempStepInterval command, handled below for every run): SMD_RESIZE_RATE=4 makes this executable that variant
+	int resizeRate = 8;
+	if (const char *e = std::getenv("SMD_RESIZE_RATE")) { int v = std::atoi(e); if (v >= 1) resizeRate = v; }
 
 	double resizeHistInterval = 0.00001;
 	std::vector<double> resizeHist, rejectHist;

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom 
 __device__ __forceinline__ void scan_chunk(int ncells, int &b0, int &b1)
 {
 	int chunk = (ncells + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
-	chunk = (chunk + SCAN_TPB - 1) / SCAN_TPB * SCAN_TPB;
+	chunk = (chunk + 4 * SCAN_TPB - 1) / (4 * SCAN_TPB) * (4 * SCAN_TPB);   // k_scan3 takes four cells per thread and pass
 	long long a = (long long)blockIdx.x * chunk;
 	b0 = (int)min(a, (long long)ncells);
 	b1 = (int)min(a + chunk, (long long)ncells);
@@ -430,10 +430,20 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox,
 		__syncthreads();
 	}
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	for (int base = b0; base < b1; base += SCAN_TPB) {
-		int i = base + threadIdx.x;
-		int v = (i < b1) ? count[i] : 0;
-		int inc = v;
+	// four consecutive cells per thread and pass (16-byte loads and stores: the table has 4 x the cells since the sort
+	// key carries x slices); chunk starts are multiples of 4 and the arrays come from cudaMalloc
+	for (int base = b0; base < b1; base += 4 * SCAN_TPB) {
+		const int i = base + 4 * (int)threadIdx.x;
+		const bool full = i + 3 < b1;
+		int4 v = make_int4(0, 0, 0, 0);
+		if (full) v = *reinterpret_cast<const int4 *>(count + i);
+		else {
+			if (i < b1) v.x = count[i];
+			if (i + 1 < b1) v.y = count[i + 1];
+			if (i + 2 < b1) v.z = count[i + 2];
+		}
+		const int sum4 = (v.x + v.y) + (v.z + v.w);
+		int inc = sum4;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
 			int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -448,8 +458,17 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox,
 			total += t;
 		}
 		int carry = carry_sh;
-		int ex = carry + woff + inc - v;
-		if (i < b1) { start[i] = ex; cursor[i] = ex; count[i] = 0; }
+		const int ex = carry + woff + inc - sum4;
+		const int4 e = make_int4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+		if (full) {
+			*reinterpret_cast<int4 *>(start + i) = e;
+			*reinterpret_cast<int4 *>(cursor + i) = e;
+			*reinterpret_cast<int4 *>(count + i) = make_int4(0, 0, 0, 0);
+		} else {
+			if (i < b1) { start[i] = e.x; cursor[i] = e.x; count[i] = 0; }
+			if (i + 1 < b1) { start[i + 1] = e.y; cursor[i + 1] = e.y; count[i + 1] = 0; }
+			if (i + 2 < b1) { start[i + 2] = e.z; cursor[i + 2] = e.z; count[i + 2] = 0; }
+		}
 		__syncthreads();
 		if (threadIdx.x == 0) carry_sh = carry + total;
 		__syncthreads();

@@ -116,6 +116,24 @@ def test_bilayer_with_tension_box_moves_and_restart(tmp_path, orc):
     assert not (d2 / "frames_bl.xyz").exists() or open(d2 / "frames_bl.xyz").read().count("test\n") == 0
 
 
+def test_resize_rate_of_the_anneal_variant(tmp_path, orc):
+    """MDanneal.cpp is MD.cpp with `resizeRate 4` (and the temperature ramp every driver has): SMD_RESIZE_RATE=4 doubles the
+    number of Metropolis trials of the same run; a temperature ramp (tempStepInterval) reaches the thermostat"""
+    m = workloads.bilayer(600, 3.11, 5, tension=0.5)
+    m.update(finalTime=1.6, storeInterval=1.6, measureInterval=0.4, finalTemp=1.0, tempStepInterval=0.4)
+    trials = {}
+    for rate in ("8", "4"):
+        d = tmp_path / rate
+        d.mkdir()
+        orc.write_mpd(str(d / "bl.mpd"), m)
+        r = subprocess.run([MD_B200, "bl"], cwd=d, capture_output=True, text=True, timeout=600, env=dict(os.environ, SMD_RESIZE_RATE=rate))
+        assert r.returncode == 0, r.stderr[-2000:]
+        trials[rate] = sum(h[1] + h[2] for h in table(d / "resizeHist_bl.dat"))
+        temp = [row[1] for row in table(d / "temp_bl.dat")]
+        assert temp[0] == 3.0 and temp[-1] < temp[0]              # ramped down towards finalTemp
+    assert abs(trials["8"] - 10.0) < 1e-9 and abs(trials["4"] - 20.0) < 1e-9
+
+
 def test_every_molecule_kind_of_the_md_switch(tmp_path, orc):
     """tests/golden/fields: BOUNDARY, FLOATING_BASE, ZTORQUE, ZPOWERPOTENTIAL, NANOCORE, BALL (+ SOLID and OFFSET_BOUNDARY,
     which `MD` parses and ignores) on a periodic bilayer with box moves.  Same files as the reference binary, same t = 0
