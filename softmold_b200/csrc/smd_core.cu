@@ -121,13 +121,13 @@ extern "C" int smd_device_count(void)
 
 // x slices per reference cell in the sort key (Geom::xs).  The sliced order no longer lists a cell's particles by
 // descending original index, which is what the ORDERED look-up of an asymmetric constant table keys on (the reference's
-// "later-loaded particle first", cellOpt.h:572-585): asymmetric tables, the slab decomposition (column bookkeeping), the
-// two-kernel engine and the TMA-staged variant keep xs = 1.
+// "later-loaded particle first", cellOpt.h:572-585): asymmetric tables, the two-kernel engine and the TMA-staged variant
+// keep xs = 1.
 static void choose_xs(smd_ctx *ctx)
 {
 	Geom &g = ctx->geom;
 	int xs = ctx->xs_wanted;
-	if (ctx->slab || ctx->pair_split || STAGE_CAP > 0 || (ctx->tables_set && !ctx->tables_symmetric)) xs = 1;
+	if (ctx->pair_split || STAGE_CAP > 0 || (ctx->tables_set && !ctx->tables_symmetric)) xs = 1;
 	const long long cap = ctx->cellcap > 0 ? ctx->cellcap : ctx->cellcap_limit;   // before / after the tables were allocated
 	while (xs > 1 && ((long long)g.nc[0] * g.nc[1] * g.nc[2] * xs > cap)) xs >>= 1;
 	if (xs < 1) xs = 1;

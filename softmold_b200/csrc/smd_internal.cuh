@@ -36,7 +36,7 @@ struct Geom {
 	// x sub-cells: the SORT KEY (and the offset table start[]) splits every reference cell into xs slices along x, so a
 	// stencil row -- the three cells of a (y,z) row are contiguous in the sorted order -- is sorted by x to a resolution
 	// of cs[0] / xs and k_pair_force2 reads only the slices within the particle's reach (4 sigma of the row's 6).
-	// Particle::cell still holds the reference's own cell coordinates.  xs = 1: slab mode, asymmetric tables.
+	// Particle::cell still holds the reference's own cell coordinates.  xs = 1: asymmetric tables.
 	int xs;
 	double finv;    // xs / cs[0]
 };

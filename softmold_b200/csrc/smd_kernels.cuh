@@ -277,8 +277,8 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 		w.org[0] = g.col_lo - g.halo; w.dim[0] = (g.col_hi - g.col_lo) + 2 * g.halo;
 		w.org[1] = 0; w.dim[1] = g.nc[1];
 		w.org[2] = 0; w.dim[2] = g.nc[2];
-		n = (long long)w.dim[0] * w.dim[1] * w.dim[2];
-		w.fd0 = w.dim[0];   // slab mode: xs = 1
+		w.fd0 = w.dim[0] * g.xs;
+		n = (long long)w.fd0 * w.dim[1] * w.dim[2];
 		w.ncells = (n > cellcap) ? 0 : (int)n;
 		return w;
 	}
@@ -1383,7 +1383,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		int flo = xlo * xs, fhi = xhi * xs + (xs - 1);
 		if (xs > 1) {
 			const float reach = sqrtf(fmaxf(amax - gyz, 0.f)) + pg.slack32;
-			const float rel = p32.x - (float)w0 * pg.cs32[0];
+			// x relative to the window origin: own window column (wraps across the periodic seam in slab mode) + offset in the cell
+			const float rel = (float)win_x(cx, w0, g.nc[0]) * pg.cs32[0] + (p32.x - (float)cx * pg.cs32[0]);
 			flo = max(flo, (int)floorf((rel - reach) * pg.finv32 - 0.02f));
 			fhi = min(fhi, (int)floorf((rel + reach) * pg.finv32 + 0.02f));
 		}
