@@ -186,6 +186,14 @@ int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3]);
 int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, double u_fluct, double u_accept,
                     int32_t *accepted, double *dU_total, double box_out[3]);
 
+/* smd_step(first_step, nsteps) followed by smd_mc_box_move(...) on the configuration it leaves -- the reference's cadence
+ * (MD.cpp:335-729: resizeRate steps, then one trial), with the same results -- in one call, so that the pair kernel of the
+ * LAST step can sum the pair dPotential of the proposed move in the same pass over the pairs as its forces (the trial sees
+ * the positions of that force evaluation; Verlet::second only moves velocities).  Falls back to the two calls where that
+ * does not apply (asymmetric tables, external noise, ...). */
+int smd_step_mc(smd_ctx *ctx, int64_t first_step, int32_t nsteps, double deltaLXY, double tension, double u_fluct,
+                double u_accept, int32_t *accepted, double *dU_total, double box_out[3]);
+
 /* read back (original particle order).  Any pointer may be NULL. */
 int smd_get_particles(smd_ctx *ctx, double *xyz, int32_t *type, double *vel);
 int smd_get_forces(smd_ctx *ctx, double *acc);
@@ -243,6 +251,7 @@ enum { SMD_PHASE_INTEGRATE1 = 0,  /* bead mass, Verlet::first (+ cell tagging), 
        SMD_PHASE_EXCHANGE = 7,    /* slab mode: migration + halo pack / unpack                         */
        SMD_PHASE_FUSED = 8,       /* CHAIN-only systems: chain forces + Verlet::second + next Verlet::first in one
                                      kernel (then phases 0, 3, 5 only count the first / last step of a batch) */
+       SMD_PHASE_PAIR_DU = 9,     /* the pair kernel of a step that also sums the dPotential of the box move (smd_step_mc) */
        SMD_NPHASES = 16 };
 int smd_profile(smd_ctx *ctx, uint32_t phase_mask);
 int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPHASES]);

@@ -456,6 +456,20 @@ int main(int argc, char *argv[])
 	auto ramp_at = [&](int i) { return tempStepInterval > 0 && tempStepInt != 0 && i % tempStepInt == 0 && i < endInt; };
 	auto plain = [&](int i) { return !store_at(i) && !measure_at(i) && !mc_at(i) && !ramp_at(i); };
 
+	// one Metropolis box-move trial, MD.cpp:589-721: the two draws of MTRand randNum(seed), the trial itself (`run`), the
+	// histograms of resizeHist_<name>.dat
+	auto mc_trial_bookkeeping = [&](auto run) {
+		double u_fluct = randNum.rand53(), u_accept = randNum.rand53();
+		double fluct = deltaLXY * (2.0 * u_fluct - 1.0);
+		int32_t acc = 0;
+		double dU = 0, box[3];
+		run(u_fluct, u_accept, &acc, &dU, box);
+		size_t bin = (size_t)((fluct + deltaLXY) / resizeHistInterval);
+		if (bin < resizeHist.size()) (acc ? resizeHist : rejectHist)[bin] += 1.0;   // 0.5 for x + 0.5 for y
+		if (acc) accepted++;
+		trial++;
+	};
+
 	std::cerr << "starting main loop: \n";
 	time_t current = time(NULL);
 	const auto loop_t0 = std::chrono::steady_clock::now();
@@ -463,6 +477,16 @@ int main(int argc, char *argv[])
 		// steps without any host-side event run back to back on the device
 		int nplain = 0;
 		while (i + nplain <= endInt && plain(i + nplain) && nplain < 4096) nplain++;
+		// ... and when all the next eventful step does is a box-move trial, it joins them: smd_step_mc lets the pair kernel
+		// of that step sum the dPotential of the proposed move along with its forces
+		const int j = i + nplain;
+		if (j <= endInt && mc_at(j) && !store_at(j) && !measure_at(j) && !ramp_at(j)) {
+			mc_trial_bookkeeping([&](double u_fluct, double u_accept, int32_t *acc, double *dU, double *box) {
+				D.ck(smd_step_mc(ctx, i, nplain + 1, deltaLXY, tension, u_fluct, u_accept, acc, dU, box), "smd_step_mc");
+			});
+			i = j + 1;
+			continue;
+		}
 		if (nplain > 0) {
 			D.ck(smd_step(ctx, i, nplain), "smd_step");
 			i += nplain;
@@ -484,17 +508,10 @@ int main(int argc, char *argv[])
 			D.measure();
 			current = time(NULL);
 		}
-		if (mc_at(i)) {   // MD.cpp:589-721
-			double u_fluct = randNum.rand53(), u_accept = randNum.rand53();
-			double fluct = deltaLXY * (2.0 * u_fluct - 1.0);
-			int32_t acc = 0;
-			double dU = 0, box[3];
-			D.ck(smd_mc_box_move(ctx, deltaLXY, tension, u_fluct, u_accept, &acc, &dU, box), "smd_mc_box_move");
-			size_t bin = (size_t)((fluct + deltaLXY) / resizeHistInterval);
-			if (bin < resizeHist.size()) (acc ? resizeHist : rejectHist)[bin] += 1.0;   // 0.5 for x + 0.5 for y
-			if (acc) accepted++;
-			trial++;
-		}
+		if (mc_at(i))
+			mc_trial_bookkeeping([&](double u_fluct, double u_accept, int32_t *acc, double *dU, double *box) {
+				D.ck(smd_mc_box_move(ctx, deltaLXY, tension, u_fluct, u_accept, acc, dU, box), "smd_mc_box_move");
+			});
 		i++;
 	}
 	D.ck(smd_synchronize(ctx), "smd_synchronize");

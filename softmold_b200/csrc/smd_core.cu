@@ -168,7 +168,7 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 }
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
-static int pair_force_smem(smd_ctx *ctx);
+static int pair_force_smem(smd_ctx *ctx, bool du = false);
 
 static int upload_acut(smd_ctx *ctx)
 {
@@ -257,6 +257,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	// gathers keeps a 128-register block resident ~10 k cycles longer instead of hiding behind the other blocks.  Off.
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_PAIR_SEAM"); ctx->no_pair_fuse = !(e && *e == '1'); }
+	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }   // smd_step_mc: dPotential in a pass of its own (A/B)
 	{ const char *e = getenv("SMD_CHUNKS"); int v = e ? atoi(e) : SMD_DEFAULT_CHUNKS; ctx->chunks = std::min(std::max(v, 1), 8); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
@@ -363,6 +364,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_force_smem(ctx, true));
 			if (e1 == cudaSuccess) have = smem;
 		}
 		if (e1 != cudaSuccess) {
@@ -1017,9 +1019,10 @@ static int ready(smd_ctx *ctx)
 	return SMD_OK;
 }
 
-static int pair_force_smem(smd_ctx *ctx)
+static int pair_force_smem(smd_ctx *ctx, bool du)   // du: the force + dPotential instance (EMODE 3) stages a second table
 {
 	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
+	       (du ? (PTAB_STRIDE * ctx->nT * ctx->nT + PAIR_TPB) * (int)sizeof(double) : 0) +
 	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short) + (STAGE_CAP > 0 ? (STAGE_CAP + 8) * (int)sizeof(uint2) : 0);
 }
 
@@ -1035,6 +1038,14 @@ template <bool LANGEVIN>
 static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg, const SeamArgs *seam = nullptr)
 {
 	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
+	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric && !ctx->pair_split && !seam) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
+		ctx->du_armed = false;
+		LAUNCH((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16,
+		       SeamArgs{});
+		ctx->du_ready = true;
+		return SMD_OK;
+	}
 	if (seam) {   // forces + Langevin + the step seam in one kernel (see SeamArgs); the caller checked pair_fusable()
 		LAUNCH((k_pair_force2<0, true, true, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16,
@@ -1086,7 +1097,11 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		lg.sigma = langevin_sigma(ctx);
 		lg.seed = ctx->desc.seed; lg.step = (uint64_t)step;
 		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
-		ProfScope ps(ctx, SMD_PHASE_PAIR);
+		// (a launch that also sums a dPotential is timed apart: bench.py's roofline describes the plain force launch; when
+		// only the plain phase is being profiled, the other one inherits the request)
+		const bool du_launch = ctx->du_armed && ctx->tables_symmetric && !ctx->pair_split;
+		if (du_launch && ((ctx->prof_mask >> SMD_PHASE_PAIR) & 1u)) ctx->prof_mask |= 1u << SMD_PHASE_PAIR_DU;
+		ProfScope ps(ctx, du_launch ? SMD_PHASE_PAIR_DU : SMD_PHASE_PAIR);
 		SeamArgs sa;
 		if (seam) {
 			sa = *seam;
@@ -1310,6 +1325,7 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 			if ((rc = step_chunked(ctx, first_step + k, last, cs, bs))) return rc;
 			continue;
 		}
+		ctx->du_armed = last && ctx->du_for_last;
 		if (!last && pair_fusable) {
 			// thermostat, build, pair force, chain terms, Verlet::second, next Verlet::first: the build + ONE kernel
 			SeamArgs sa;
@@ -1366,7 +1382,11 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	auto push = [&](int term) { term_of_slot.push_back(term); return slot++; };
 	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + ctx->balls.size() + 2 * ctx->beads.size() + field_sum_slots(ctx) <= 64,
 	        "too many molecule records for one energy call");
-	if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
+	if (MODE == 2 && ctx->du_ready) {
+		// the block sums of this very dPotential were left in partials[] by the force kernel of the step (smd_step_mc)
+		ctx->du_ready = false;
+		finish_sum(ctx, nblk(N, PAIR_TPB), push(SMD_TERM_PAIR), 1.0);
+	} else if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
 		// two-phase kernel, every unordered pair once (see k_pair_force2)
 		int nb = nblk(N, PAIR_TPB);
 		EnergyArgs en;
@@ -1546,14 +1566,10 @@ extern "C" int smd_mc_accept(double dU_terms_sum, double tension, const double b
 	return SMD_OK;
 }
 
-extern "C" int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, double u_fluct, double u_accept, int32_t *accepted,
-                               double *dU_total, double box_out[3])
+// the trial of MD.cpp:589-721 on the current configuration; `proposed`: box and scale already drawn (smd_step_mc)
+static int mc_trial(smd_ctx *ctx, const double oldSize[3], const double size[3], const double aSize[3], double tension, double u_accept,
+                    int32_t *accepted, double *dU_total, double box_out[3])
 {
-	if (!ctx) return SMD_ERR_ARG;
-	REQUIRE(!ctx->slab, "slab: use smd_mc_propose / smd_dpotential / all-reduce / smd_mc_accept / smd_rescale");
-	double oldSize[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
-	double size[3], aSize[3];
-	smd_mc_propose(oldSize, deltaLXY, u_fluct, size, aSize);
 	double terms[SMD_NTERMS];
 	int rc = smd_dpotential(ctx, aSize, terms);
 	if (rc) return rc;
@@ -1572,6 +1588,50 @@ extern "C" int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, do
 	if (dU_total) *dU_total = dPotential;
 	if (box_out) for (int d = 0; d < 3; d++) box_out[d] = ctx->geom.box[d];
 	return SMD_OK;
+}
+
+extern "C" int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, double u_fluct, double u_accept, int32_t *accepted,
+                               double *dU_total, double box_out[3])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(!ctx->slab, "slab: use smd_mc_propose / smd_dpotential / all-reduce / smd_mc_accept / smd_rescale");
+	double oldSize[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
+	double size[3], aSize[3];
+	smd_mc_propose(oldSize, deltaLXY, u_fluct, size, aSize);
+	ctx->du_ready = false;
+	return mc_trial(ctx, oldSize, size, aSize, tension, u_accept, accepted, dU_total, box_out);
+}
+
+extern "C" int smd_step_mc(smd_ctx *ctx, int64_t first_step, int32_t nsteps, double deltaLXY, double tension, double u_fluct, double u_accept,
+                           int32_t *accepted, double *dU_total, double box_out[3])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(!ctx->slab, "slab: use smd_step and smd_mc_propose / smd_dpotential / all-reduce / smd_mc_accept / smd_rescale");
+	double oldSize[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
+	double size[3], aSize[3];
+	smd_mc_propose(oldSize, deltaLXY, u_fluct, size, aSize);
+	// The trial sees the positions of the last step's force evaluation (Verlet::second only moves velocities), so that
+	// step's pair kernel can also sum the pair dPotential: one pass over the pairs instead of two.
+	const bool fuse = nsteps > 0 && can_fuse(ctx) && ctx->tables_symmetric && !ctx->pair_split && !ctx->force_onephase_energy &&
+	                  ctx->chunks == 1 && !ctx->no_du_fuse && ctx->desc.noise != SMD_NOISE_EXTERNAL;
+	ctx->du_ready = false;
+	if (fuse) {
+		EnergyArgs en;
+		en.sx = aSize[0]; en.sy = aSize[1]; en.sz = aSize[2];
+		en.partials = ctx->partials; en.uC = ctx->uC; en.utab = ctx->utab;
+		double grow = 0;   // as in energy_terms<2>: the most the scaling moves r^2 across a cutoff, relative
+		for (double sc : {aSize[0], aSize[1], aSize[2]}) grow = std::max(grow, std::max(fabs(sc * sc - 1.0), fabs(1.0 / (sc * sc) - 1.0)));
+		en.extra32 = nextafterf((float)(1.01 * grow * ctx->geom.rc2 + 1e-7), INFINITY);
+		ctx->du_en = en;
+		ctx->du_for_last = true;
+	}
+	int rc = smd_step(ctx, first_step, nsteps);
+	ctx->du_for_last = false;
+	ctx->du_armed = false;
+	if (rc) { ctx->du_ready = false; return rc; }
+	rc = mc_trial(ctx, oldSize, size, aSize, tension, u_accept, accepted, dU_total, box_out);
+	ctx->du_ready = false;
+	return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ read back

@@ -90,6 +90,10 @@ struct PairGeo {            // phase-1 constants of k_pair_force2
 	int block0;             // first block of this launch when the grid is launched in chunks (else 0)
 };
 
+// energy modes of k_pair_force2: the proposed scaling, the widening of the phase-1 cutoffs, where the block sums go;
+// uC / utab (the potential's tables) only for EMODE 3, which runs on the force tables
+struct EnergyArgs { double sx, sy, sz; float extra32; double *partials; const double *uC, *utab; };
+
 struct ChainBlock { int start, nChains, len; double c[4]; };
 struct BondList { int n; int *d_ij; double c[2]; };
 struct BendList { int n; int *d_ijk; double c[2]; };
@@ -153,6 +157,9 @@ struct smd_ctx {
 	int chunks = 1;
 	cudaStream_t cstream[8] = {};
 	cudaEvent_t ev_build = nullptr, ev_chunk[8] = {};
+	// smd_step_mc: the last step's pair kernel also sums the dPotential of the box move that follows (k_pair_force2 EMODE 3)
+	bool du_for_last = false, du_armed = false, du_ready = false, no_du_fuse = false;
+	smd::EnergyArgs du_en;
 	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)
 	bool no_pair_fuse = true;    // unless SMD_PAIR_SEAM=1: the step seam is a kernel of its own, not the pair kernel's epilogue
 	double *acc;      // SoA [3][cap]

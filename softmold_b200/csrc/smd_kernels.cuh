@@ -1072,7 +1072,11 @@ struct PairSmem {
 // the slots behind its own (the rest of its cell and the cell at +x) -- and a block reduction replaces the write of
 // a[].  Phase 1 widens its cutoffs by `extra32`, the most a component-wise scaling of the box can move r^2 across a
 // cutoff (a pair outside rc before the move and inside after it still has a term).
-struct EnergyArgs { double sx, sy, sz; float extra32; double *partials; };
+// EMODE 3: forces AND the dPotential of a box move proposed for the same configuration (the Metropolis trial that follows
+// an MD step sees the positions of that step's force evaluation, MD.cpp:511-615): the force pass with the widened
+// phase-1 cutoffs of EMODE 2; every in-range (before or after the move) entry also contributes half of its U - U', the
+// other half comes from the other end of the pair.  Forces stay bit-identical to EMODE 0 (same pairs, same order).
+// (EnergyArgs: smd_internal.cuh)
 
 // FUSE (forces with the Langevin term only): the thread that has just finished a particle's pair sum also runs the
 // step seam for it -- the particle's chain terms, Verlet::second of this step and Verlet::first of the next one, wrap,
@@ -1092,6 +1096,9 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
                                                             const uint2 *__restrict__ pos16, SeamArgs sa)
 {
 	static_assert(!FUSE || (EMODE == 0 && LANGEVIN), "the step seam follows the force + Langevin evaluation");
+	static_assert(EMODE != 3 || SYMM, "forces + dPotential in one pass: symmetric tables only");
+	constexpr bool ENERGY_ONLY = (EMODE == 1 || EMODE == 2);   // no forces; every unordered pair once
+	constexpr bool DU = (EMODE == 3);                          // forces + dPotential
 	const int N = cnt.get();
 	const int bid = (int)blockIdx.x + pg.block0;   // block0 != 0: one chunk of a grid launched in pieces (forces only)
 	if (bid * PAIR_TPB >= N) {
@@ -1105,12 +1112,17 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
 	const int nptab = PTAB_STRIDE * nT * nT;
-	unsigned short *s_lists = reinterpret_cast<unsigned short *>(s_ptab + nptab);
+	// EMODE 3 only (its launches reserve the room; every byte of shared memory is L1 the other instances want): the
+	// potential's padded table next to the force's, and the dPotential terms that bypass the lists
+	double *s_utab = s_ptab + nptab;
+	double *s_dup = s_utab + nptab;
+	unsigned short *s_lists = reinterpret_cast<unsigned short *>(DU ? s_dup + PAIR_TPB : s_ptab + nptab);
 #if SMD_STAGE_CAP > 0
 	uint2 *s_stage = reinterpret_cast<uint2 *>(s_lists + (PAIR_TPB / 32) * PAIR_CAP * 32);
 #endif
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int k = tid; k < nptab; k += PAIR_TPB) s_ptab[k] = ptab[k];
+	if (DU) for (int k = tid; k < nptab; k += PAIR_TPB) s_utab[k] = en.utab[k];
 	for (int k = tid; k < PAIR_CAP + 2; k += PAIR_TPB) sm.hist[k] = 0;
 	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
 	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
@@ -1208,6 +1220,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	auto list_base = [&](int t) { return (unsigned)__cvta_generic_to_shared(s_lists + (t >> 5) * (PAIR_CAP * 32) + (t & 31)); };
 	const unsigned segb_base = (unsigned)__cvta_generic_to_shared(&sm.seg_b[0][0]);
 
+	double du = 0.0;   // EMODE 3: this thread's share of the dPotential
 	// phase 2 for one list: the particle (slot io, record po) whose ranges belong to phase-1 thread t, against the
 	// entries [rp, wend).  Branch-free except for the hand-over to the general routine (asymmetric tables, r >= 2 rm),
 	// so that two pairs interleave; the records of the next two pairs are already in flight.  sqrt and the division
@@ -1224,6 +1237,22 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			j = b + (int)(e & ((1u << PAIR_SEGBITS) - 1u));
 			return load_particle(pos + j);
 		};
+		// Potential<T>, MD.h:895-930, on r^2 (x normal and positive): correctly rounded sqrt as above, both branches
+		// evaluated and selected
+		auto upot = [&](double x, const char *c) {
+			double y = rsqrt43(x);
+			double dr = x * y;
+			dr = __fma_rn(__fma_rn(-dr, dr, x), 0.5 * y, dr);
+			double2 c01 = *reinterpret_cast<const double2 *>(c + 16);
+			double c2 = *reinterpret_cast<const double *>(c + 32);
+			double2 c34 = *reinterpret_cast<const double2 *>(c + 48);
+			double c5 = *reinterpret_cast<const double *>(c + 64);
+			double tc = c01.x - dr, tt = c34.x - dr;
+			double ucore = c01.y * tc * tc + c2;
+			double utail = tt * tt * (c34.y - tt * c5);
+			return (dr <= c01.x) ? ucore : utail;
+		};
+		const char *rowu = reinterpret_cast<const char *>(s_utab + PTAB_STRIDE * po.type * nT);   // EMODE 3
 		auto fast = [&](int j, const Particle &pj) -> bool {
 			double dx = po.x - pj.x, dy = po.y - pj.y, dz = po.z - pj.z;
 			double dr2 = dx * dx + dy * dy + dz * dz;
@@ -1244,26 +1273,22 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			q = __fma_rn(__fma_rn(-dr, q, num), y, q);            // num / dr
 			q = ok ? q : 0.0;
 			ax += dx * q; ay += dy * q; az += dz * q;
+			if (DU && !(in && !ok)) {   // (pairs handed to the general routine take their energy term there)
+				const char *cu = rowu + (PTAB_STRIDE * 8) * pj.type;
+				double uo = upot(in ? dr2 : 1.0, cu);
+				uo = in ? uo : 0.0;
+				double ex = po.x * en.sx - pj.x * en.sx, ey = po.y * en.sy - pj.y * en.sy, ez = po.z * en.sz - pj.z * en.sz;
+				double er2 = ex * ex + ey * ey + ez * ez;
+				bool in2 = er2 < rc2 && j != io;
+				double un = upot(in2 ? er2 : 1.0, cu);
+				du += 0.5 * (uo - (in2 ? un : 0.0));   // the other half: the same entry in the neighbour's list
+			}
 			return in && !ok;
 		};
 		auto general = [&](int j, const Particle &pj) {
 			D3 f = pair_force_term(io, po, j, pj, g, nT, tab, 6 * nT * nT);
 			ax += f.x; ay += f.y; az += f.z;
-		};
-		// Potential<T>, MD.h:895-930, on r^2 (x normal and positive): correctly rounded sqrt as above, both branches
-		// evaluated and selected
-		auto upot = [&](double x, const char *c) {
-			double y = rsqrt43(x);
-			double dr = x * y;
-			dr = __fma_rn(__fma_rn(-dr, dr, x), 0.5 * y, dr);
-			double2 c01 = *reinterpret_cast<const double2 *>(c + 16);
-			double c2 = *reinterpret_cast<const double *>(c + 32);
-			double2 c34 = *reinterpret_cast<const double2 *>(c + 48);
-			double c5 = *reinterpret_cast<const double *>(c + 64);
-			double tc = c01.x - dr, tt = c34.x - dr;
-			double ucore = c01.y * tc * tc + c2;
-			double utail = tt * tt * (c34.y - tt * c5);
-			return (dr <= c01.x) ? ucore : utail;
+			if (DU) du += pair_energy_term<2>(io, po, j, pj, g, nT, en.uC, en.sx, en.sy, en.sz, false);   // counted by the pair's home particle
 		};
 		auto efast = [&](int j, const Particle &pj) {
 			double dx = po.x - pj.x, dy = po.y - pj.y, dz = po.z - pj.z;
@@ -1281,7 +1306,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			}
 			ax += u;
 		};
-		if (EMODE != 0) {
+		if (ENERGY_ONLY) {
 			while (rp < wend) {
 				int j0;
 				Particle p0 = fetch(rp, j0);
@@ -1364,7 +1389,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		float gyz = gy * gy + gz * gz;
 		bool row_ok = live && gyz < amax;
 		if (row_ok && (wrapyz || cx == 0 || cx == g.nc[0] - 1)) shifted_rows = true;
-		if (EMODE != 0 && (oz < 0 || (oz == 0 && oy < 0))) row_ok = false;   // backward rows: the other particle counts the pair
+		if (ENERGY_ONLY && (oz < 0 || (oz == 0 && oy < 0))) row_ok = false;   // backward rows: the other particle counts the pair
 		row_ok = row_ok && !wrapyz && lz >= 0 && lz < d2 && ly >= 0 && ly < d1;
 		bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
 #ifdef SMD_EXP_NO_XPRUNE
@@ -1397,7 +1422,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	for (int r = 0; r < PAIR_NSEG; r++) {
 		int jb = rjb[r];
 		const int je = rje[r];
-		if (EMODE != 0 && r == 4) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
+		if (ENERGY_ONLY && r == 4) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
 		const int lim = (1 << PAIR_SEGBITS) - 4;
 #if SMD_PAIR_FLAT
 		if (je > jb) {   // the table holds the non-empty ranges back to back (list entries carry the table row)
@@ -1414,11 +1439,13 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			float4 c = pos32[j];
 			float dx = p32.x - c.x, dy = p32.y - c.y, dz = p32.z - c.z;
 			if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w) + ext && j != i) {
-				if (EMODE == 0) {
-					D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
+				if (!ENERGY_ONLY) {
+					const Particle pj = load_particle(pos + j);
+					D3 f = pair_force_term(i, pi, j, pj, g, nT, tab, 6 * nT * nT);
 					ex += f.x; ey += f.y; ez += f.z;
+					if (DU) du += pair_energy_term<2>(i, pi, j, pj, g, nT, en.uC, en.sx, en.sy, en.sz, false);
 				} else {
-					ex += pair_energy_term<(EMODE ? EMODE : 1)>(i, pi, j, load_particle(pos + j), g, nT, tab, en.sx, en.sy, en.sz, true);
+					ex += pair_energy_term<(ENERGY_ONLY ? EMODE : 1)>(i, pi, j, load_particle(pos + j), g, nT, tab, en.sx, en.sy, en.sz, true);
 				}
 			}
 		}
@@ -1617,11 +1644,13 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 				float4 c = pos32[j];
 				float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
 				if (__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) < fminf(ai, c.w) + ext) {
-					if (EMODE == 0) {
-						D3 f = pair_force_term(i, pi, j, load_particle(pos + j), g, nT, tab, 6 * nT * nT);
+					if (!ENERGY_ONLY) {
+						const Particle pj = load_particle(pos + j);
+						D3 f = pair_force_term(i, pi, j, pj, g, nT, tab, 6 * nT * nT);
 						ex += f.x; ey += f.y; ez += f.z;
+						if (DU) du += pair_energy_term<2>(i, pi, j, pj, g, nT, en.uC, en.sx, en.sy, en.sz, false);
 					} else {
-						ex += pair_energy_term<(EMODE ? EMODE : 1)>(i, pi, j, load_particle(pos + j), g, nT, tab, en.sx, en.sy, en.sz, false);
+						ex += pair_energy_term<(ENERGY_ONLY ? EMODE : 1)>(i, pi, j, load_particle(pos + j), g, nT, tab, en.sx, en.sy, en.sz, false);
 					}
 				}
 			}
@@ -1632,6 +1661,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const int lcnt = (int)((wp - lbase) >> 6);
 	sm.cnt[tid] = lcnt;
 	sm.part[0][tid] = ex; sm.part[1][tid] = ey; sm.part[2][tid] = ez;
+	if (DU) s_dup[tid] = du;   // energy terms that bypassed the list (periodic images, early drains): they travel with it
 	atomicAdd(&sm.hist[lcnt], 1);
 	__syncthreads();
 	if (tid < 32) {   // exclusive prefix over descending length (PAIR_CAP + 1 bins)
@@ -1662,12 +1692,21 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const bool act = io < N && !(g.slab && (gid[io] & GID_GHOST));
 	if (EMODE == 0 && !FUSE && !act) return;
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
+	if (DU) du = s_dup[o];
 	if (act) {
 		const Particle po = load_particle(pos + io);
 		const unsigned ob = list_base(o);
 		drain(io, po, o, ob, ob + 64u * (unsigned)sm.cnt[o], ax, ay, az);
 	}
-	if (EMODE != 0) {   // one partial sum per block, reduced deterministically by k_final_sum
+	if (DU) {   // the block's share of the dPotential, summed in particle order (see below); then the force epilogue
+		__syncthreads();
+		sm.part[0][o] = act ? du : 0.0;
+		__syncthreads();
+		double tot = block_sum(sm.part[0][tid]);
+		if (tid == 0) en.partials[blockIdx.x] = tot;
+		if (!act) return;
+	}
+	if (ENERGY_ONLY) {   // one partial sum per block, reduced deterministically by k_final_sum
 		// summed in particle order, not in the (arrival-dependent) order the lists were handed out in: the energy is
 		// reproducible to the last bit
 		__syncthreads();

@@ -335,6 +335,51 @@ def test_fused_step_kernel_with_every_molecule_kind(orc, case):
     assert rel_force_err(a0, a1) <= 1e-9
 
 
+@pytest.mark.parametrize("case", ["bilayer_eq", "lipo_eq", "lipocyto_eq", "fields"])
+def test_step_mc_equals_step_then_box_move(orc, case):
+    """smd_step_mc: the pair kernel of the last step also sums the dPotential of the proposed box move (k_pair_force2 EMODE
+    3) instead of a second pass over the pairs.  Against smd_step + smd_mc_box_move and against SMD_NO_DU_FUSE=1: the same
+    decisions, dU equal to rounding, forces of the fused pass bit-identical -- so the trajectories stay identical bit for
+    bit as long as the decisions agree."""
+    import os
+    m, _ = orc.load_golden(golden_path(case))
+    m = dict(m, initialTime=0.0)
+    dl, tension = 0.01, 0.4
+    mc = orc.mt_rand53(7, 64)
+    runs = []
+    for mode in ("two_calls", "fused", "unfused_env"):
+        if mode == "unfused_env":
+            os.environ["SMD_NO_DU_FUSE"] = "1"
+        try:
+            ctx = sm.Context.from_dict(m)
+        finally:
+            os.environ.pop("SMD_NO_DU_FUSE", None)
+        ctx.compute_forces(step=0)
+        log = []
+        for t in range(6):
+            if mode == "two_calls":
+                ctx.step(8 * t, 8)
+                acc, dU, box = ctx.mc_box_move(dl, tension, mc[2 * t], mc[2 * t + 1])
+            else:
+                acc, dU, box = ctx.step_mc(8 * t, 8, dl, tension, mc[2 * t], mc[2 * t + 1])
+            log.append((acc, dU, tuple(box)))
+        runs.append((log, ctx.get_particles(), ctx.get_forces(), ctx.stats()[0], abs(ctx.potential()[sm.TERM_PAIR])))
+        ctx.close()
+    (l0, p0, a0, n0, U0), (l1, p1, a1, n1, _), (l2, p2, a2, n2, _) = runs
+    assert [x[0] for x in l0] == [x[0] for x in l1] == [x[0] for x in l2] and any(x[0] for x in l0)
+    exact = case in ("bilayer_eq", "lipo_eq")     # list molecules add their forces with FP64 atomics: not reproducible to the bit
+    for (_, d0, b0), (_, d1, b1), (_, d2, b2) in zip(l0, l1, l2):
+        assert abs(d0 - d1) <= 1e-12 * U0 and abs(d0 - d2) <= 1e-12 * U0 and np.allclose(b0, b1, rtol=1e-15) and np.allclose(b0, b2, rtol=1e-15)
+        assert not exact or (d0 == d2 and b0 == b1 == b2)
+    if exact:
+        assert np.array_equal(p0[0], p1[0]) and np.array_equal(p0[2], p1[2]) and np.array_equal(a0, a1)
+        assert np.array_equal(p0[0], p2[0]) and np.array_equal(a0, a2)
+    else:
+        assert np.abs(p0[0] - p1[0]).max() <= 1e-9 and np.abs(p0[0] - p2[0]).max() <= 1e-9 and rel_force_err(a1, a0) <= 1e-9
+    if case != "fields":                 # (BEAD / NANOCORE-free systems take the fused step path, which smd_step_mc needs)
+        assert n1 < n0                   # fewer launches: the dPotential kernel is gone
+
+
 def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
     """SMD_PAIR_SPLIT=1 (k_pair_lists + k_pair_drain, global candidate lists) against k_pair_force2: forces, energies and
     a short trajectory, bit for bit"""
