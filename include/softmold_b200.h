@@ -186,11 +186,18 @@ int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3]);
 int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, double u_fluct, double u_accept,
                     int32_t *accepted, double *dU_total, double box_out[3]);
 
+/* Arms the NEXT smd_step call: the pair kernel of its last step also sums the pair dPotential of the box scaling `scale`
+ * in the same pass over the pairs as its forces (a Metropolis trial sees the positions of the last force evaluation:
+ * Verlet::second only moves velocities, MD.cpp:511-615).  The first smd_dpotential call for that same scale afterwards,
+ * with the particles untouched in between, takes its pair term from there.  A no-op where the fast path does not apply
+ * (asymmetric tables, external noise): smd_dpotential then works as always.  Slab mode: every rank arms the same scale. */
+int smd_arm_dpotential(smd_ctx *ctx, const double scale[3]);
+
 /* smd_step(first_step, nsteps) followed by smd_mc_box_move(...) on the configuration it leaves -- the reference's cadence
  * (MD.cpp:335-729: resizeRate steps, then one trial), with the same results -- in one call, so that the pair kernel of the
  * LAST step can sum the pair dPotential of the proposed move in the same pass over the pairs as its forces (the trial sees
  * the positions of that force evaluation; Verlet::second only moves velocities).  Falls back to the two calls where that
- * does not apply (asymmetric tables, external noise, ...). */
+ * does not apply (asymmetric tables, external noise, ...).  = smd_mc_propose + smd_arm_dpotential + smd_step + the trial. */
 int smd_step_mc(smd_ctx *ctx, int64_t first_step, int32_t nsteps, double deltaLXY, double tension, double u_fluct,
                 double u_accept, int32_t *accepted, double *dU_total, double box_out[3]);
 

@@ -31,7 +31,7 @@ SYMBOLS = [
     "smd_add_boundary", "smd_add_floating_base", "smd_add_ztorque", "smd_add_zpower", "smd_add_nanocore", "smd_set_gamma_type",
     "smd_set_temperature", "smd_set_noise", "smd_build_cells", "smd_compute_forces", "smd_resume", "smd_step",
     "smd_step_begin", "smd_step_end", "smd_potential", "smd_kinetic", "smd_dpotential", "smd_rescale",
-    "smd_mc_box_move", "smd_step_mc", "smd_get_particles", "smd_get_forces", "smd_get_unwrapped", "smd_get_box", "smd_get_cell_ids",
+    "smd_mc_box_move", "smd_step_mc", "smd_arm_dpotential", "smd_get_particles", "smd_get_forces", "smd_get_unwrapped", "smd_get_box", "smd_get_cell_ids",
     "smd_count_pairs", "smd_synchronize", "smd_device_ptr", "smd_stream", "smd_stats", "smd_profile", "smd_profile_read", "smd_fp64_peak", "smd_mpd_read", "smd_mpd_write",
     "smd_mpd_free", "smd_mpd_get_scalar", "smd_mpd_set_scalar", "smd_mpd_get_size", "smd_mpd_set_size",
     "smd_mpd_particles", "smd_mpd_pair_tables", "smd_mpd_n_molecules", "smd_mpd_molecule", "smd_create_from_mpd",
@@ -102,6 +102,7 @@ def lib():
         L.smd_rescale.argtypes = [vp, vp, vp]
         L.smd_mc_box_move.argtypes = [vp, dbl, dbl, dbl, dbl, ip, dp, vp]
         L.smd_step_mc.argtypes = [vp, i64, i32, dbl, dbl, dbl, dbl, ip, dp, vp]
+        L.smd_arm_dpotential.argtypes = [vp, vp]
         L.smd_get_particles.argtypes = [vp, vp, vp, vp]
         L.smd_get_forces.argtypes = [vp, vp]
         L.smd_get_unwrapped.argtypes = [vp, vp]
@@ -337,6 +338,11 @@ class Context:
         acc, dU, box = C.c_int32(), C.c_double(), np.zeros(3)
         self._ck(self.L.smd_mc_box_move(self.h, deltaLXY, tension, u_fluct, u_accept, C.byref(acc), C.byref(dU), _ptr(box)))
         return bool(acc.value), dU.value, box
+
+    def arm_dpotential(self, scale):
+        """the next step() call also sums the pair dPotential of `scale` in its last force pass; dpotential(scale) then reuses it"""
+        sc = _f64(scale)
+        self._ck(self.L.smd_arm_dpotential(self.h, _ptr(sc)))
 
     def step_mc(self, first_step, nsteps, deltaLXY, tension, u_fluct, u_accept):
         """step(first_step, nsteps) then mc_box_move(...) in one call: the last step's pair kernel also sums the dPotential"""

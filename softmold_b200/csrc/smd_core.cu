@@ -416,6 +416,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
 	for (int c = 0; c < 8; c++) { if (ctx->cstream[c]) cudaStreamDestroy(ctx->cstream[c]); if (ctx->ev_chunk[c]) cudaEventDestroy(ctx->ev_chunk[c]); }
 	if (ctx->ev_build) cudaEventDestroy(ctx->ev_build);
+	if (ctx->du_partials) cudaFree(ctx->du_partials);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 	return SMD_OK;
@@ -545,6 +546,7 @@ static int retag_cells(smd_ctx *ctx, bool rearm = true)
 extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t *type, const double *vel)
 {
 	if (!ctx) return SMD_ERR_ARG;
+	ctx->du_ready = false;   // the particles change: block sums armed by smd_arm_dpotential no longer describe them
 	REQUIRE(xyz && type, "null positions / types");
 	CK(cudaSetDevice(ctx->device));
 	int N = ctx->n_global;
@@ -1154,6 +1156,7 @@ extern "C" int smd_resume(smd_ctx *ctx)
 extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
 {
 	if (!ctx) return SMD_ERR_ARG;
+	ctx->du_ready = false;   // the particles change: block sums armed by smd_arm_dpotential no longer describe them
 	(void)step;
 	int rc = ready(ctx);
 	if (rc) return rc;
@@ -1297,6 +1300,8 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(ctx->desc.noise != SMD_NOISE_EXTERNAL || nsteps <= 1, "external noise: one step per smd_set_noise");
 	if (nsteps <= 0) return SMD_OK;
+	struct Disarm { smd_ctx *c; ~Disarm() { c->du_for_last = false; c->du_armed = false; } } disarm{ctx};   // one call only
+	ctx->du_ready = false;   // the particles are about to move
 	if (!can_fuse(ctx)) {
 		for (int k = 0; k < nsteps; k++) {
 			ProfScope ps(ctx, SMD_PHASE_STEP);
@@ -1382,10 +1387,10 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	auto push = [&](int term) { term_of_slot.push_back(term); return slot++; };
 	REQUIRE(1 + ctx->chains.size() + ctx->bonds.size() + ctx->bends.size() + ctx->balls.size() + 2 * ctx->beads.size() + field_sum_slots(ctx) <= 64,
 	        "too many molecule records for one energy call");
-	if (MODE == 2 && ctx->du_ready) {
-		// the block sums of this very dPotential were left in partials[] by the force kernel of the step (smd_step_mc)
+	if (MODE == 2 && ctx->du_ready && sx == ctx->du_en.sx && sy == ctx->du_en.sy && sz == ctx->du_en.sz) {
+		// the block sums of this very dPotential were left behind by the force kernel of the last step (smd_arm_dpotential)
 		ctx->du_ready = false;
-		finish_sum(ctx, nblk(N, PAIR_TPB), push(SMD_TERM_PAIR), 1.0);
+		LAUNCH(k_final_sum, 1, 256, 0, nblk(N, PAIR_TPB), ctx->du_partials, ctx->scalars, push(SMD_TERM_PAIR), 1.0);
 	} else if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
 		// two-phase kernel, every unordered pair once (see k_pair_force2)
 		int nb = nblk(N, PAIR_TPB);
@@ -1525,6 +1530,7 @@ extern "C" int smd_count_pairs(smd_ctx *ctx, int64_t *total, int32_t *per_partic
 extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3])
 {
 	if (!ctx) return SMD_ERR_ARG;
+	ctx->du_ready = false;   // the particles change: block sums armed by smd_arm_dpotential no longer describe them
 	REQUIRE(scale && new_box && ctx->particles_set, "bad call");
 	CK(cudaSetDevice(ctx->device));
 	Geom old = ctx->geom;
@@ -1598,40 +1604,57 @@ extern "C" int smd_mc_box_move(smd_ctx *ctx, double deltaLXY, double tension, do
 	double oldSize[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
 	double size[3], aSize[3];
 	smd_mc_propose(oldSize, deltaLXY, u_fluct, size, aSize);
-	ctx->du_ready = false;
 	return mc_trial(ctx, oldSize, size, aSize, tension, u_accept, accepted, dU_total, box_out);
+}
+
+// The NEXT smd_step call lets the pair kernel of its last step also sum the pair dPotential of the box scaling `scale`
+// (k_pair_force2 EMODE 3); the first smd_dpotential call for that same scale afterwards, with the particles untouched in
+// between, takes the pair term from there instead of running a pass of its own.  Returns SMD_OK whether or not the fast
+// path applies (asymmetric tables, external noise, ...: nothing is armed and smd_dpotential works as always).
+extern "C" int smd_arm_dpotential(smd_ctx *ctx, const double scale[3])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(scale, "null scale");
+	ctx->du_ready = false;
+	ctx->du_for_last = false;
+	const bool fuse = can_fuse(ctx) && ctx->tables_symmetric && !ctx->pair_split && !ctx->force_onephase_energy && ctx->chunks == 1 &&
+	                  !ctx->no_du_fuse && ctx->desc.noise != SMD_NOISE_EXTERNAL;
+	if (!fuse) return SMD_OK;
+	CK(cudaSetDevice(ctx->device));
+	const size_t need = (size_t)nblk(ctx->N, PAIR_TPB);
+	if (ctx->du_partials_n < need) {   // block sums of its own: nothing else may overwrite them before they are used
+		if (ctx->du_partials) cudaFree(ctx->du_partials);
+		ctx->du_partials = nullptr; ctx->du_partials_n = 0;
+		CK(cudaMalloc(&ctx->du_partials, need * sizeof(double)));
+		ctx->du_partials_n = need;
+	}
+	EnergyArgs en;
+	en.sx = scale[0]; en.sy = scale[1]; en.sz = scale[2];
+	en.partials = ctx->du_partials; en.uC = ctx->uC; en.utab = ctx->utab;
+	double grow = 0;   // as in energy_terms<2>: the most the scaling moves r^2 across a cutoff, relative
+	for (double sc : {scale[0], scale[1], scale[2]}) grow = std::max(grow, std::max(fabs(sc * sc - 1.0), fabs(1.0 / (sc * sc) - 1.0)));
+	en.extra32 = nextafterf((float)(1.01 * grow * ctx->geom.rc2 + 1e-7), INFINITY);
+	ctx->du_en = en;
+	ctx->du_for_last = true;
+	return SMD_OK;
 }
 
 extern "C" int smd_step_mc(smd_ctx *ctx, int64_t first_step, int32_t nsteps, double deltaLXY, double tension, double u_fluct, double u_accept,
                            int32_t *accepted, double *dU_total, double box_out[3])
 {
 	if (!ctx) return SMD_ERR_ARG;
-	REQUIRE(!ctx->slab, "slab: use smd_step and smd_mc_propose / smd_dpotential / all-reduce / smd_mc_accept / smd_rescale");
+	REQUIRE(!ctx->slab, "slab: use smd_arm_dpotential / smd_step and smd_mc_propose / smd_dpotential / all-reduce / smd_mc_accept / smd_rescale");
 	double oldSize[3] = {ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]};
 	double size[3], aSize[3];
 	smd_mc_propose(oldSize, deltaLXY, u_fluct, size, aSize);
 	// The trial sees the positions of the last step's force evaluation (Verlet::second only moves velocities), so that
 	// step's pair kernel can also sum the pair dPotential: one pass over the pairs instead of two.
-	const bool fuse = nsteps > 0 && can_fuse(ctx) && ctx->tables_symmetric && !ctx->pair_split && !ctx->force_onephase_energy &&
-	                  ctx->chunks == 1 && !ctx->no_du_fuse && ctx->desc.noise != SMD_NOISE_EXTERNAL;
-	ctx->du_ready = false;
-	if (fuse) {
-		EnergyArgs en;
-		en.sx = aSize[0]; en.sy = aSize[1]; en.sz = aSize[2];
-		en.partials = ctx->partials; en.uC = ctx->uC; en.utab = ctx->utab;
-		double grow = 0;   // as in energy_terms<2>: the most the scaling moves r^2 across a cutoff, relative
-		for (double sc : {aSize[0], aSize[1], aSize[2]}) grow = std::max(grow, std::max(fabs(sc * sc - 1.0), fabs(1.0 / (sc * sc) - 1.0)));
-		en.extra32 = nextafterf((float)(1.01 * grow * ctx->geom.rc2 + 1e-7), INFINITY);
-		ctx->du_en = en;
-		ctx->du_for_last = true;
+	int rc = SMD_OK;
+	if (nsteps > 0) {
+		if ((rc = smd_arm_dpotential(ctx, aSize))) return rc;
+		if ((rc = smd_step(ctx, first_step, nsteps))) return rc;
 	}
-	int rc = smd_step(ctx, first_step, nsteps);
-	ctx->du_for_last = false;
-	ctx->du_armed = false;
-	if (rc) { ctx->du_ready = false; return rc; }
-	rc = mc_trial(ctx, oldSize, size, aSize, tension, u_accept, accepted, dU_total, box_out);
-	ctx->du_ready = false;
-	return rc;
+	return mc_trial(ctx, oldSize, size, aSize, tension, u_accept, accepted, dU_total, box_out);
 }
 
 // ------------------------------------------------------------------------------------------------ read back
@@ -1928,6 +1951,7 @@ extern "C" int smd_slab_exchange_recv(smd_ctx *ctx)
 extern "C" int smd_slab_set_local(smd_ctx *ctx, int32_t n, const int32_t *gid, const double *xyz, const int32_t *type, const double *vel)
 {
 	if (!ctx) return SMD_ERR_ARG;
+	ctx->du_ready = false;   // the particles change: block sums armed by smd_arm_dpotential no longer describe them
 	REQUIRE(ctx->slab, "not a slab context");
 	REQUIRE(n >= 0 && (n == 0 || (gid && xyz && type)), "null arrays");
 	REQUIRE(n <= ctx->cap, "slab: local particle capacity exceeded at load (desc.reserved[0])");

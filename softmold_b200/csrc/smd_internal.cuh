@@ -160,6 +160,8 @@ struct smd_ctx {
 	// smd_step_mc: the last step's pair kernel also sums the dPotential of the box move that follows (k_pair_force2 EMODE 3)
 	bool du_for_last = false, du_armed = false, du_ready = false, no_du_fuse = false;
 	smd::EnergyArgs du_en;
+	double *du_partials = nullptr;   // block sums of the armed dPotential (their own buffer: nothing else writes it)
+	size_t du_partials_n = 0;
 	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)
 	bool no_pair_fuse = true;    // unless SMD_PAIR_SEAM=1: the step seam is a kernel of its own, not the pair kernel's epilogue
 	double *acc;      // SoA [3][cap]

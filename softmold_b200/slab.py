@@ -53,6 +53,19 @@ class _SlabBase:
         return accepted, dU, (new_box if accepted else box)
 
 
+    def step_mc(self, first_step, nsteps, deltaLXY, tension, u_fluct, u_accept):
+        """step(first_step, nsteps) then mc_box_move(...): every rank arms the proposed scaling first, so that the pair kernel
+        of its last step also sums its share of the pair dPotential (smd_arm_dpotential) and the trial needs no second pass"""
+        box = self.get_box()
+        new_box, scale = capi.mc_propose(box, deltaLXY, u_fluct)
+        self.step(first_step, nsteps, arm_scale=scale)
+        terms = self.dpotential(scale)
+        accepted, dU = capi.mc_accept(float(terms.sum()), tension, box, new_box, self.temperature, u_accept)
+        if accepted:
+            self._each(lambda c: c.rescale(scale, new_box))
+        return accepted, dU, (new_box if accepted else box)
+
+
 class LocalSlabGroup(_SlabBase):
     """nranks slab contexts in ONE process on one device, wired to each other with plain device pointers.  The
     kernels, the message protocol and the per-rank state are exactly those of a multi-GPU run; only the transport
@@ -89,13 +102,20 @@ class LocalSlabGroup(_SlabBase):
     def compute_forces(self, mask=capi.MASK_ALL, step=0):
         self._each(lambda c: c.compute_forces(mask, step))
 
-    def step(self, first_step, nsteps=1, batched=False):
-        """batched=False: one step at a time, all sends before all receives.  batched=True: every context enqueues
+    batched_default = False
+
+    def step(self, first_step, nsteps=1, batched=None, arm_scale=None):
+        """arm_scale: smd_arm_dpotential before the smd_step call that holds the last step (batched mode only).
+        batched=False: one step at a time, all sends before all receives.  batched=True: every context enqueues
         a whole smd_step batch (the production call, with the fused step kernel) one after the other; the wait
         kernels of the first contexts then spin until the host has enqueued the later contexts' sends, which is fine
         for the short batches used here (nothing may fill a launch queue while it waits)"""
+        if batched is None:
+            batched = self.batched_default
         if batched:
             for k in range(0, nsteps, 4):
+                if arm_scale is not None and k + 4 >= nsteps:
+                    self._each(lambda c: c.arm_dpotential(arm_scale))
                 self._each(lambda c: c.step(first_step + k, min(4, nsteps - k)))
             return
         for k in range(nsteps):
@@ -162,7 +182,9 @@ class DistSlab(_SlabBase):
     def compute_forces(self, mask=capi.MASK_ALL, step=0):
         self.c.compute_forces(mask, step)
 
-    def step(self, first_step, nsteps=1):
+    def step(self, first_step, nsteps=1, arm_scale=None):
+        if arm_scale is not None:
+            self.c.arm_dpotential(arm_scale)
         self.c.step(first_step, nsteps)
 
     def synchronize(self):

@@ -111,6 +111,39 @@ def test_slab_trajectory_with_box_moves_matches_single_gpu(bilayer, orc, nranks)
     assert np.abs(v2 - v1).max() <= 1e-8
 
 
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_step_mc_sums_the_dpotential_in_the_force_pass(bilayer, orc, nranks):
+    """step_mc in slab mode: every rank arms the proposed scaling (smd_arm_dpotential), the pair kernel of its last step sums
+    its share of the pair dPotential, the all-reduced total and the decisions equal those of step + mc_box_move, and the
+    dPotential kernel is not launched"""
+    m = bilayer
+    mc = orc.mt_rand53(3, 32)
+    out = []
+    for fused in (False, True):
+        grp = LocalSlabGroup(m, nranks)
+        grp.batched_default = True
+        grp.compute_forces(mask=sm.MASK_ALL, step=0)
+        log = []
+        for t in range(4):
+            if fused:
+                acc, dU, box = grp.step_mc(8 * t, 8, m["deltaLXY"], 0.5, mc[2 * t], mc[2 * t + 1])
+            else:
+                grp.step(8 * t, 8)
+                acc, dU, box = grp.mc_box_move(m["deltaLXY"], 0.5, mc[2 * t], mc[2 * t + 1])
+            log.append((acc, dU, tuple(box)))
+        x, _, v, _, _ = grp.gather(m["nParticles"])
+        launches = sum(c.stats()[0] for c in grp.ctx)
+        U = abs(grp.potential()[sm.TERM_PAIR])
+        grp.close()
+        out.append((log, x, v, launches, U))
+    (l0, x0, v0, n0, U), (l1, x1, v1, n1, _) = out
+    assert [a for a, _, _ in l0] == [a for a, _, _ in l1] and any(a for a, _, _ in l0)
+    for (_, d0, b0), (_, d1, b1) in zip(l0, l1):
+        assert abs(d0 - d1) <= 1e-12 * U and b0 == b1
+    assert np.array_equal(x0, x1) and np.array_equal(v0, v1)      # forces of the fused pass are bit-identical
+    assert n1 < n0                                                # four dPotential pair kernels per rank fewer
+
+
 @pytest.mark.parametrize("nranks", [2, 4])
 def test_slab_vesicle_across_the_seam_and_empty_ranks(orc, nranks):
     """a small vesicle in the middle of a 400^3 box: the seam of a 2-rank split cuts it in half; with 4 ranks two of
