@@ -257,7 +257,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	// gathers keeps a 128-register block resident ~10 k cycles longer instead of hiding behind the other blocks.  Off.
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_PAIR_SEAM"); ctx->no_pair_fuse = !(e && *e == '1'); }
-	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }   // smd_step_mc: dPotential in a pass of its own (A/B)
+	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
+	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }   // slab mode: exchange packed by a kernel of its own (A/B)   // smd_step_mc: dPotential in a pass of its own (A/B)
 	{ const char *e = getenv("SMD_CHUNKS"); int v = e ? atoi(e) : SMD_DEFAULT_CHUNKS; ctx->chunks = std::min(std::max(v, 1), 8); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
@@ -870,7 +871,8 @@ static int build_cells(smd_ctx *ctx)
 	if (ctx->slab && !ctx->ext_valid)   // no unpack since the last build: the extended count is the current one
 		CK(cudaMemcpyAsync(ctx->dN + 1, ctx->dN, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
 	ctx->ext_valid = false;
-	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag);
+	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag,
+	       ctx->gid[cur], ctx->slab ? ctx->slot_of : nullptr);
 	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
 	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N,
 	       ctx->slab ? ctx->dN : nullptr, ctx->errflag);
@@ -1277,10 +1279,10 @@ static int step_chunked(smd_ctx *ctx, int64_t step, bool last, const ChainSet &c
 		}
 		if (last)
 			LAUNCH(k_chain_kick<true>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur], ctx->acc,
-			       ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB);
+			       ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr);
 		else
 			LAUNCH(k_chain_kick<false>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1], ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB);
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr);
 		ctx->stream = main_stream;
 		CK(cudaEventRecord(ctx->ev_chunk[c], st));
 		CK(cudaStreamWaitEvent(main_stream, ctx->ev_chunk[c], 0));
@@ -1350,15 +1352,24 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 		ProfScope pf(ctx, SMD_PHASE_FUSED);
 		if (last) {
 			LAUNCH(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0);
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr);
 		} else {
+			// slab mode: the seam kernel is also the send side of the exchange (migrants + halo packed as the particles get
+			// their new positions, written straight into the neighbours' buffers); SMD_NO_SEAM_PACK=1: separate pack kernel
+			const bool seam_pack = ctx->slab && !ctx->no_seam_pack;
+			if (seam_pack) {
+				REQUIRE(ctx->peer_set[0] && ctx->peer_set[1], "slab: connect both neighbours first (smd_slab_connect_*)");
+				REQUIRE(!ctx->exch_pending, "slab: previous exchange not received yet");
+				ctx->xseq++;
+			}
 			LAUNCH(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
 			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
-			       ctx->errflag, bs, 0);
+			       ctx->errflag, bs, 0, seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr);
 			ctx->pcur ^= 1;
 			ctx->acc_live = false;
 			ctx->cells_valid = false;
-			if (ctx->slab && (rc = smd_slab_exchange_send(ctx))) return rc;
+			if (seam_pack) ctx->exch_pending = true;
+			else if (ctx->slab && (rc = smd_slab_exchange_send(ctx))) return rc;
 		}
 	}
 	return SMD_OK;

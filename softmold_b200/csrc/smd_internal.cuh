@@ -159,6 +159,7 @@ struct smd_ctx {
 	cudaEvent_t ev_build = nullptr, ev_chunk[8] = {};
 	// smd_step_mc: the last step's pair kernel also sums the dPotential of the box move that follows (k_pair_force2 EMODE 3)
 	bool du_for_last = false, du_armed = false, du_ready = false, no_du_fuse = false;
+	bool no_seam_pack = false;
 	smd::EnergyArgs du_en;
 	double *du_partials = nullptr;   // block sums of the armed dPotential (their own buffer: nothing else writes it)
 	size_t du_partials_n = 0;

@@ -334,7 +334,7 @@ __device__ __forceinline__ uint2 quantize16(const Particle &p, const Geom &g, co
 // pass 1 of the counting sort: histogram over the window.  Warp-aggregated: lanes sharing a cell elect a leader
 // that issues one atomicAdd for the group.
 __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
-                                             int *cellOfSlot, int *errflag)
+                                             int *cellOfSlot, int *errflag, const int *__restrict__ gid, int *slot_of)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	Window w = window_of(bbox, g, cellcap);
@@ -342,7 +342,11 @@ __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom 
 	if (s < cnt.get() && w.ncells > 0) {
 		const Particle p = load_particle(pos + s);
 		unsigned c = p.cell;
-		if (c != CELL_DEAD) {   // slab mode: ghosts of the previous step
+		// slab mode: a ghost of the previous step.  Its entry of the index table is given back here -- the exchange that
+		// dropped it may have run inside the step seam, where other threads were still looking partners up through the
+		// table; if the particle has just been received again, k_reorder (later in this build) re-enters it.
+		if (c == CELL_DEAD && slot_of) slot_of[gid[s] & GID_MASK] = -1;
+		if (c != CELL_DEAD) {
 			int cx, cy, cz;
 			unpack_cell(c, cx, cy, cz);
 			int lx = win_x(cx, w.org[0], g.nc[0]);
@@ -1961,40 +1965,31 @@ __device__ __forceinline__ void st_entry(SlabMsgEntry *e, const Particle &p, dou
 	q[3] = make_double2(vz, __longlong_as_double((long long)(unsigned)gid));
 }
 
-__global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *pos, const double *vel, const double *unw, int *gid, Geom g,
-                                                   SlabComm c, int seq, int *errflag, int *slot_of)
+// One owned particle (or none: own == false) of the exchange, called by all 32 lanes of a warp: p carries the new position
+// and cell tag; (vx, vy, vz) and (ux, uy, uz) travel only with migrants.  Marks a migrant as a ghost in gid[s].
+__device__ __forceinline__ bool slab_pack_one(bool own, int s, const Particle &p, int gi, double vx, double vy, double vz, bool has_unw,
+                                              double ux, double uy, double uz, int *gid, const Geom &g, const SlabComm &c, int seq, int *errflag)
 {
-	const int N = cnt.get();
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	int dir = -1;          // 0: entry for the left neighbour, 1: for the right one
-	bool migrant = false;
-	Particle p;
-	int gi = 0;
-	if (s < N) {
-		gi = gid[s];
-		if (gi & GID_GHOST) {
-			pos[s].cell = CELL_DEAD;
-			slot_of[gi & GID_MASK] = -1;   // keeps the index table exact: whoever is still here is re-entered by the build
+	bool migrant = false, wrote = false;
+	if (own) {
+		int cx, cy, cz;
+		unpack_cell(p.cell, cx, cy, cz);
+		int W = g.col_hi - g.col_lo;
+		int rel = cx - g.col_lo;
+		if (rel < 0) rel += g.nc[0];
+		else if (rel >= g.nc[0]) rel -= g.nc[0];
+		if (rel < W) {
+			if (rel < g.halo) dir = 0;
+			else if (rel >= W - g.halo) dir = 1;
+		} else if (rel < W + g.halo) {
+			dir = 1; migrant = true;
+		} else if (rel >= g.nc[0] - g.halo) {
+			dir = 0; migrant = true;
 		} else {
-			p = load_particle(pos + s);
-			int cx, cy, cz;
-			unpack_cell(p.cell, cx, cy, cz);
-			int W = g.col_hi - g.col_lo;
-			int rel = cx - g.col_lo;
-			if (rel < 0) rel += g.nc[0];
-			else if (rel >= g.nc[0]) rel -= g.nc[0];
-			if (rel < W) {
-				if (rel < g.halo) dir = 0;
-				else if (rel >= W - g.halo) dir = 1;
-			} else if (rel < W + g.halo) {
-				dir = 1; migrant = true;
-			} else if (rel >= g.nc[0] - g.halo) {
-				dir = 0; migrant = true;
-			} else {
-				atomicOr(errflag, ERR_SLAB_MIGRATION);   // moved further than the halo in one step
-			}
-			if (migrant) gid[s] = gi | GID_GHOST;
+			atomicOr(errflag, ERR_SLAB_MIGRATION);   // moved further than the halo in one step
 		}
+		if (migrant) gid[s] = gi | GID_GHOST;
 	}
 #pragma unroll
 	for (int d = 0; d < 2; d++) {
@@ -2011,19 +2006,26 @@ __global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *p
 			} else {
 				char *buf = c.send[d] + (size_t)(seq & 1) * c.parity_stride;
 				SlabMsgEntry *e = reinterpret_cast<SlabMsgEntry *>(buf + sizeof(SlabMsgHeader)) + idx;
-				double vx = 0, vy = 0, vz = 0;
-				if (migrant) { vx = vel[s]; vy = vel[cap + s]; vz = vel[2 * cap + s]; }
-				st_entry(e, p, vx, vy, vz, migrant ? gi : (gi | GID_GHOST));
-				if (migrant && unw) {
+				st_entry(e, p, migrant ? vx : 0.0, migrant ? vy : 0.0, migrant ? vz : 0.0, migrant ? gi : (gi | GID_GHOST));
+				if (migrant && has_unw) {
 					double2 *q = reinterpret_cast<double2 *>(e);
-					q[4] = make_double2(unw[s], unw[cap + s]);
-					q[5] = make_double2(unw[2 * cap + s], 0.0);
+					q[4] = make_double2(ux, uy);
+					q[5] = make_double2(uz, 0.0);
 				}
+				wrote = true;
 			}
 		}
 	}
-	// publish: every block fences its entries, the last one writes the two headers
-	__threadfence_system();
+	return wrote;
+}
+
+// publish (all threads of every block of the grid that packed): the threads that wrote an entry fence it at system scope
+// (only they: a system fence waits for everything the thread has in flight, and in the step seam that is every thread's
+// position / velocity stores -- fencing all 10^6 threads cost more than the pack pass it replaced), the last block to
+// arrive writes the two headers
+__device__ __forceinline__ void slab_publish(const SlabComm &c, int seq, bool wrote)
+{
+	if (wrote) __threadfence_system();
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		int t = atomicAdd(c.counters + 2, 1);
@@ -2039,6 +2041,32 @@ __global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *p
 			asm volatile("st.release.sys.global.v2.s32 [%0], {%1, %2};" ::"l"(h1), "r"(v1.x), "r"(v1.y) : "memory");
 		}
 	}
+}
+
+__global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *pos, const double *vel, const double *unw, int *gid, Geom g,
+                                                   SlabComm c, int seq, int *errflag, int *slot_of)
+{
+	const int N = cnt.get();
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	bool own = false;
+	Particle p;
+	p.x = p.y = p.z = 0; p.type = 0; p.cell = 0;
+	int gi = 0;
+	double vx = 0, vy = 0, vz = 0, ux = 0, uy = 0, uz = 0;
+	if (s < N) {
+		gi = gid[s];
+		if (gi & GID_GHOST) {
+			pos[s].cell = CELL_DEAD;
+			slot_of[gi & GID_MASK] = -1;   // keeps the index table exact: whoever is still here is re-entered by the build
+		} else {
+			own = true;
+			p = load_particle(pos + s);
+			vx = vel[s]; vy = vel[cap + s]; vz = vel[2 * cap + s];
+			if (unw) { ux = unw[s]; uy = unw[cap + s]; uz = unw[2 * cap + s]; }
+		}
+	}
+	const bool wrote = slab_pack_one(own, s, p, gi, vx, vy, vz, unw != nullptr, ux, uy, uz, gid, g, c, seq, errflag);
+	slab_publish(c, seq, wrote);
 }
 
 __global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int cap, Particle *pos, double *vel, double *unw, int *gid,
@@ -2114,8 +2142,11 @@ template <bool LAST>
 __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
                                                     double *vel, double *acc, double *unw, const int *__restrict__ gid,
                                                     const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag,
-                                                    BeadSet bs, int slot0)
+                                                    BeadSet bs, int slot0, SlabComm comm, int seq, int *gid_w)
 {
+	// seq > 0 (slab mode, not LAST): this kernel is also the SEND side of the step's halo / migration exchange -- every
+	// owned particle is packed as soon as it has its new position (slab_pack_one), straight into the neighbour's receive
+	// buffer through peer memory, and the last block publishes the headers: no separate pass over the slots
 	const int N = cnt.get();
 	int s = slot0 + blockIdx.x * blockDim.x + threadIdx.x;   // slot0 != 0: one chunk of the step pipeline (smd_step)
 	bool valid = s < N;
@@ -2123,6 +2154,7 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 	int gi = 0;
 	if (valid) { p = load_particle(pos_in + s); gi = gid[s]; }
 	bool live = valid && !(g.slab && (gi & GID_GHOST));
+	double mvx = 0, mvy = 0, mvz = 0, mux = 0, muy = 0, muz = 0;   // what a migrant takes along (slab mode)
 	if (live) {
 		V3 A;
 		if (!chain_gather(gi & GID_MASK, p, N, pos_in, gid, slot_of, g, cs, A)) atomicOr(errflag, ERR_SLAB_MISSING);
@@ -2142,9 +2174,16 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 			if (!LAST) {
 				vx += (bx * h); vy += (by * h); vz += (bz * h);                             // Verlet::first of the next one
 				p.x += vx * dt; p.y += vy * dt; p.z += vz * dt;
-				if (unw) { unw[s] += vx * dt; unw[cap + s] += vy * dt; unw[2 * cap + s] += vz * dt; }
+				if (unw) {
+					mux = unw[s] + vx * dt; muy = unw[cap + s] + vy * dt; muz = unw[2 * cap + s] + vz * dt;
+					unw[s] = mux; unw[cap + s] = muy; unw[2 * cap + s] = muz;
+				}
 			}
 			vel[s] = vx; vel[cap + s] = vy; vel[2 * cap + s] = vz;
+			mvx = vx; mvy = vy; mvz = vz;
+		} else if (!LAST && seq > 0) {   // type 0 never moves, but it is exchanged like everybody else
+			mvx = vel[s]; mvy = vel[cap + s]; mvz = vel[2 * cap + s];
+			if (unw) { mux = unw[s]; muy = unw[cap + s]; muz = unw[2 * cap + s]; }
 		}
 		if (!LAST) {
 			if (p.x > g.box[0]) p.x -= g.box[0];
@@ -2158,8 +2197,12 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 	if (LAST) return;
 	tag_cell(p, g, bbox, errflag, live);
 	if (valid) {
-		if (!live) p.cell = CELL_DEAD;   // slab ghost: replaced by the exchange that follows
+		if (!live) p.cell = CELL_DEAD;   // slab ghost: replaced by the exchange (its index-table entry is given back by k_bin)
 		store_particle(pos_out + s, p);
+	}
+	if (seq > 0) {
+		const bool wrote = slab_pack_one(live, s, p, gi, mvx, mvy, mvz, unw != nullptr, mux, muy, muz, gid_w, g, comm, seq, errflag);
+		slab_publish(comm, seq, wrote);
 	}
 }
 

@@ -144,6 +144,31 @@ def test_slab_step_mc_sums_the_dpotential_in_the_force_pass(bilayer, orc, nranks
     assert n1 < n0                                                # four dPotential pair kernels per rank fewer
 
 
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_exchange_packed_by_the_step_seam_is_bit_identical(bilayer, nranks):
+    """smd_step in slab mode: the fused seam kernel is also the send side of the exchange (every owned particle is packed
+    into the neighbour's buffer as it gets its new position).  Against SMD_NO_SEAM_PACK=1 (a pack kernel of its own after
+    the seam): same particles on the same ranks, bit for bit, after 40 steps with migration; one launch per step fewer."""
+    import os
+    m = bilayer
+    out = []
+    for env in ("1", "0"):
+        os.environ["SMD_NO_SEAM_PACK"] = env
+        try:
+            grp = LocalSlabGroup(m, nranks)
+        finally:
+            del os.environ["SMD_NO_SEAM_PACK"]
+        grp.compute_forces(mask=sm.MASK_ALL, step=0)
+        grp.step(0, 40, batched=True)
+        x, t, v, a, owner = grp.gather(m["nParticles"])
+        launches = sum(c.stats()[0] for c in grp.ctx)
+        grp.close()
+        out.append((x, v, owner, launches))
+    (x0, v0, o0, l0), (x1, v1, o1, l1) = out
+    assert np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(o0, o1)
+    assert l1 < l0
+
+
 @pytest.mark.parametrize("nranks", [2, 4])
 def test_slab_vesicle_across_the_seam_and_empty_ranks(orc, nranks):
     """a small vesicle in the middle of a 400^3 box: the seam of a 2-rank split cuts it in half; with 4 ranks two of
