@@ -258,7 +258,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_PAIR_SEAM"); ctx->no_pair_fuse = !(e && *e == '1'); }
 	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
-	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }   // slab mode: exchange packed by a kernel of its own (A/B)   // smd_step_mc: dPotential in a pass of its own (A/B)
+	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }
+	{ const char *e = getenv("SMD_PDL"); ctx->pdl = !(e && *e == '0'); }   // slab mode: exchange packed by a kernel of its own (A/B)   // smd_step_mc: dPotential in a pass of its own (A/B)
 	{ const char *e = getenv("SMD_CHUNKS"); int v = e ? atoi(e) : SMD_DEFAULT_CHUNKS; ctx->chunks = std::min(std::max(v, 1), 8); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
@@ -266,6 +267,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	set_geom(ctx, desc->box);
 	ctx->pgeo.rmin32 = (float)desc->cutoff;
 	ctx->pgeo.block0 = 0;
+	ctx->pgeo.done = nullptr; ctx->pgeo.epoch = 0;
 	int rc = check_geom(ctx);
 	if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
 
@@ -417,6 +419,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
 	for (int c = 0; c < 8; c++) { if (ctx->cstream[c]) cudaStreamDestroy(ctx->cstream[c]); if (ctx->ev_chunk[c]) cudaEventDestroy(ctx->ev_chunk[c]); }
 	if (ctx->ev_build) cudaEventDestroy(ctx->ev_build);
+	if (ctx->pair_done) cudaFree(ctx->pair_done);
 	if (ctx->du_partials) cudaFree(ctx->du_partials);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -1219,6 +1222,20 @@ static bool only_chains(const smd_ctx *ctx)
 {
 	return ctx->bonds.empty() && ctx->bends.empty() && ctx->balls.empty() && ctx->fields.empty() && ctx->beads.empty();
 }
+// launch with the programmatic-stream-serialization attribute: the kernel may become resident before its predecessor in the
+// stream has completed, and orders itself against it on the device (k_chain_kick: per-block completion words)
+template <class... KArgs, class... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static ChainSet chain_set(const smd_ctx *ctx)
 {
 	ChainSet cs;
@@ -1279,10 +1296,10 @@ static int step_chunked(smd_ctx *ctx, int64_t step, bool last, const ChainSet &c
 		}
 		if (last)
 			LAUNCH(k_chain_kick<true>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur], ctx->acc,
-			       ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr);
+			       ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0);
 		else
 			LAUNCH(k_chain_kick<false>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1], ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr);
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0);
 		ctx->stream = main_stream;
 		CK(cudaEventRecord(ctx->ev_chunk[c], st));
 		CK(cudaStreamWaitEvent(main_stream, ctx->ev_chunk[c], 0));
@@ -1346,13 +1363,34 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 			if (ctx->slab && (rc = smd_slab_exchange_send(ctx))) return rc;
 			continue;
 		}
+		// The seam as a programmatic dependent of the pair kernel (CHAIN-only systems, nothing recorded in between): its
+		// blocks move in where the tail of the pair grid has left SMs empty and start on their 128 slots as soon as the
+		// pair block of those slots has signalled (PairGeo::done) -- the seam hides in the pair kernel's last, sparse round.
+		const bool pdl = ctx->pdl && scatter == 0 && ctx->prof_mask == 0 && !ctx->pair_split && ctx->tables_symmetric;
+		if (pdl) {
+			if (!ctx->pair_done) {
+				CK(cudaMalloc(&ctx->pair_done, (size_t)nblk(ctx->cap, PAIR_TPB) * sizeof(int)));
+				CK(cudaMemsetAsync(ctx->pair_done, 0, (size_t)nblk(ctx->cap, PAIR_TPB) * sizeof(int), ctx->stream));
+			}
+			ctx->pgeo.done = ctx->pair_done;
+			ctx->pgeo.epoch = ++ctx->pair_epoch;
+		}
 		// MD.cpp:410-413: thermostat, build, pair force (one kernel); then the scattering molecule kinds, if any
 		rc = forces(ctx, SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_LANGEVIN | scatter, first_step + k, true);
+		ctx->pgeo.done = nullptr;
 		if (rc) return rc;
+		const int *done = pdl ? ctx->pair_done : nullptr;
+		const int epoch = ctx->pair_epoch;
 		ProfScope pf(ctx, SMD_PHASE_FUSED);
-		if (last) {
+		if (last && pdl) {
+			CK(launch_dependent(k_chain_kick<true>, nblk(N, TPB), TPB, ctx->stream, cnt_of(ctx), ctx->cap, (const Particle *)ctx->pos[ctx->pcur],
+			                    (Particle *)nullptr, ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], (const int *)ctx->gid[ctx->cur],
+			                    (const int *)ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr,
+			                    done, epoch));
+			ctx->launches++;
+		} else if (last) {
 			LAUNCH(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr);
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0);
 		} else {
 			// slab mode: the seam kernel is also the send side of the exchange (migrants + halo packed as the particles get
 			// their new positions, written straight into the neighbours' buffers); SMD_NO_SEAM_PACK=1: separate pack kernel
@@ -1362,9 +1400,18 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 				REQUIRE(!ctx->exch_pending, "slab: previous exchange not received yet");
 				ctx->xseq++;
 			}
+			if (pdl) {
+				CK(launch_dependent(k_chain_kick<false>, nblk(N, TPB), TPB, ctx->stream, cnt_of(ctx), ctx->cap, (const Particle *)ctx->pos[ctx->pcur],
+				                    ctx->pos[ctx->pcur ^ 1], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], (const int *)ctx->gid[ctx->cur],
+				                    (const int *)ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0,
+				                    seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr,
+				                    done, epoch));
+				ctx->launches++;
+			} else
 			LAUNCH(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
 			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
-			       ctx->errflag, bs, 0, seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr);
+			       ctx->errflag, bs, 0, seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr,
+			       (const int *)nullptr, 0);
 			ctx->pcur ^= 1;
 			ctx->acc_live = false;
 			ctx->cells_valid = false;

@@ -88,6 +88,8 @@ struct PairGeo {            // phase-1 constants of k_pair_force2
 	float rmin32;           // smallest positive per-type phase-1 radius (pos16 path: widening of the energy modes' cutoffs)
 	float finv32;           // x slices per unit length (Geom::finv)
 	int block0;             // first block of this launch when the grid is launched in chunks (else 0)
+	int *done;              // per-block completion words for a programmatic dependent launch of the step seam (else null)
+	int epoch;              // value a block stores there
 };
 
 // energy modes of k_pair_force2: the proposed scaling, the widening of the phase-1 cutoffs, where the block sums go;
@@ -160,6 +162,9 @@ struct smd_ctx {
 	// smd_step_mc: the last step's pair kernel also sums the dPotential of the box move that follows (k_pair_force2 EMODE 3)
 	bool du_for_last = false, du_armed = false, du_ready = false, no_du_fuse = false;
 	bool no_seam_pack = false;
+	bool pdl = true;            // step seam as a programmatic dependent of the pair kernel (SMD_PDL=0: plain stream order)
+	int *pair_done = nullptr;   // [blocks] completion words, see PairGeo::done
+	int pair_epoch = 0;
 	smd::EnergyArgs du_en;
 	double *du_partials = nullptr;   // block sums of the armed dPotential (their own buffer: nothing else writes it)
 	size_t du_partials_n = 0;

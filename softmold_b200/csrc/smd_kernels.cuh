@@ -1109,6 +1109,10 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
 		return;
 	}
+	// pg.done: the step seam is launched as a programmatic dependent of this kernel.  All its blocks may become resident as
+	// soon as every block of this grid has started (they only fit where pair blocks have left: the tail of the grid); seam
+	// block b then waits for done[b] == epoch, which block b of this grid sets when its accelerations are written.
+	if (pg.done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef SMD_EXP_TIMING
 	long long t_exp = clock64();
 #endif
@@ -1694,7 +1698,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const int o = sm.order[tid];
 	const int io = sm.perm[o];
 	const bool act = io < N && !(g.slab && (gid[io] & GID_GHOST));
-	if (EMODE == 0 && !FUSE && !act) return;
+	if (EMODE == 0 && !FUSE && !act && !pg.done) return;
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
 	if (DU) du = s_dup[o];
 	if (act) {
@@ -1708,7 +1712,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		__syncthreads();
 		double tot = block_sum(sm.part[0][tid]);
 		if (tid == 0) en.partials[blockIdx.x] = tot;
-		if (!act) return;
+		if (!act && !pg.done) return;
 	}
 	if (ENERGY_ONLY) {   // one partial sum per block, reduced deterministically by k_final_sum
 		// summed in particle order, not in the (arrival-dependent) order the lists were handed out in: the energy is
@@ -1764,7 +1768,9 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		}
 		return;
 	}
-	if (LANGEVIN) {
+	if (!act) {
+		// (only reached with pg.done: every thread of the block takes part in the hand-over below)
+	} else if (LANGEVIN) {
 		int id = lg.gid[io] & GID_MASK;
 		double u[3];
 		if (lg.ext_noise) {
@@ -1778,6 +1784,11 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		acc[io] = lx + ax; acc[cap + io] = ly + ay; acc[2 * cap + io] = lz + az;
 	} else {
 		acc[io] += ax; acc[cap + io] += ay; acc[2 * cap + io] += az;
+	}
+	if (pg.done) {   // this block's accelerations are complete: release its seam block
+		__threadfence();
+		__syncthreads();
+		if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(pg.done + bid), "r"(pg.epoch) : "memory");
 	}
 #ifdef SMD_EXP_TIMING
 	if (EMODE == 0 && lane == 0) {   // per warp: phase 2 as seen by each warp; [3] counts warps
@@ -2142,8 +2153,23 @@ template <bool LAST>
 __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
                                                     double *vel, double *acc, double *unw, const int *__restrict__ gid,
                                                     const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag,
-                                                    BeadSet bs, int slot0, SlabComm comm, int seq, int *gid_w)
+                                                    BeadSet bs, int slot0, SlabComm comm, int seq, int *gid_w, const int *done, int epoch)
 {
+	// done != nullptr: launched as a programmatic dependent of the pair kernel -- this block may be resident while the
+	// tail of that grid is still running and only needs the accelerations of its own 128 slots, which pair block `blk`
+	// signals with done[blk] = epoch (everything else it reads was final before the pair kernel started)
+	if (done) {
+		const int blk = slot0 / TPB + (int)blockIdx.x;
+		if (blk * TPB < cnt.get()) {
+			if (threadIdx.x == 0) {
+				int v;
+				do {
+					asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + blk) : "memory");
+				} while (v != epoch);
+			}
+			__syncthreads();
+		}
+	}
 	// seq > 0 (slab mode, not LAST): this kernel is also the SEND side of the step's halo / migration exchange -- every
 	// owned particle is packed as soon as it has its new position (slab_pack_one), straight into the neighbour's receive
 	// buffer through peer memory, and the last block publishes the headers: no separate pass over the slots
