@@ -37,7 +37,30 @@ static inline int nblk(long long n, int tpb) { return (int)std::max<long long>(1
 		ctx->launches++;                                                                                  \
 	} while (0)
 
+// LAUNCHP: like LAUNCH, but with the programmatic-stream-serialization attribute when the context allows it (SMD_PDL, no
+// profiling events in the stream): the kernel may become resident before its predecessor has completed and MUST order
+// itself on the device (pdl_prologue(), or k_chain_kick's completion words).
+template <class... KArgs, class... Args>
+static cudaError_t launch_ex(bool pdl, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define LAUNCHP(kernel, grid, block, smem, ...)                                                           \
+	do {                                                                                                  \
+		CK(launch_ex(ctx->pdl_chain && ctx->prof_mask == 0, kernel, (grid), (block), (smem), ctx->stream, __VA_ARGS__)); \
+		ctx->launches++;                                                                                  \
+	} while (0)
+
 static const int MAX_PARTIALS = 1 << 20;
+#ifndef SMD_DEFAULT_PDL_CHAIN
+#define SMD_DEFAULT_PDL_CHAIN true
+#endif
 #ifndef SMD_DEFAULT_CHUNKS
 #define SMD_DEFAULT_CHUNKS 1
 #endif
@@ -259,7 +282,10 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_PAIR_SEAM"); ctx->no_pair_fuse = !(e && *e == '1'); }
 	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }
-	{ const char *e = getenv("SMD_PDL"); ctx->pdl = !(e && *e == '0'); }   // slab mode: exchange packed by a kernel of its own (A/B)   // smd_step_mc: dPotential in a pass of its own (A/B)
+	// SMD_PDL=0: plain stream order everywhere; 1: only the step seam is a programmatic dependent (of the pair kernel);
+	// 2 (default): so are the kernels of the build, the pair kernel itself and the slab unpack (LAUNCHP).  Measured per MD
+	// step: C2 218.3 / 213.9 / 203.4 us, a 15 000-particle vesicle 72.7 / 77.4 / 66.3 us.
+	{ const char *e = getenv("SMD_PDL"); ctx->pdl = !(e && *e == '0'); ctx->pdl_chain = e ? (*e == '2') : SMD_DEFAULT_PDL_CHAIN; }   // slab mode: exchange packed by a kernel of its own (A/B)   // smd_step_mc: dPotential in a pass of its own (A/B)
 	{ const char *e = getenv("SMD_CHUNKS"); int v = e ? atoi(e) : SMD_DEFAULT_CHUNKS; ctx->chunks = std::min(std::max(v, 1), 8); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
@@ -874,13 +900,13 @@ static int build_cells(smd_ctx *ctx)
 	if (ctx->slab && !ctx->ext_valid)   // no unpack since the last build: the extended count is the current one
 		CK(cudaMemcpyAsync(ctx->dN + 1, ctx->dN, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
 	ctx->ext_valid = false;
-	LAUNCH(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag,
+	LAUNCHP(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag,
 	       ctx->gid[cur], ctx->slab ? ctx->slot_of : nullptr);
-	LAUNCH(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
-	LAUNCH(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N,
+	LAUNCHP(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
+	LAUNCHP(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N,
 	       ctx->slab ? ctx->dN : nullptr, ctx->errflag);
-	LAUNCH(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order, ctx->gid[cur]);
-	LAUNCH(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
+	LAUNCHP(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order, ctx->gid[cur]);
+	LAUNCHP(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
 	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0, ctx->pos16, ctx->arad, ctx->win,
 	       ctx->geom);
@@ -1047,7 +1073,7 @@ static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg, const SeamArg
 	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
 	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric && !ctx->pair_split && !seam) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
 		ctx->du_armed = false;
-		LAUNCH((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		LAUNCHP((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16,
 		       SeamArgs{});
 		ctx->du_ready = true;
@@ -1072,7 +1098,7 @@ static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg, const SeamArg
 		return SMD_OK;
 	}
 	if (ctx->tables_symmetric)
-		LAUNCH((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		LAUNCHP((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
 	else
 		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
@@ -1999,7 +2025,7 @@ extern "C" int smd_slab_exchange_recv(smd_ctx *ctx)
 	// and starve the pack kernel they wait for (four ranks x 296 blocks x 256 threads did exactly that, intermittently).
 	int blocks = std::min(nblk(2ll * ctx->comm.capmsg, 256), 24);
 	long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a neighbour that never sends is reported, not waited for
-	LAUNCH(k_slab_unpack, blocks, 256, 0, cnt_of(ctx), ctx->dN + 1, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
+	LAUNCHP(k_slab_unpack, blocks, 256, 0, cnt_of(ctx), ctx->dN + 1, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
 	       ctx->gid[ctx->cur], ctx->comm, ctx->xseq, ctx->errflag, spin_limit);
 	ctx->exch_pending = false;
 	ctx->ext_valid = true;

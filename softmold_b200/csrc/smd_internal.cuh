@@ -163,6 +163,7 @@ struct smd_ctx {
 	bool du_for_last = false, du_armed = false, du_ready = false, no_du_fuse = false;
 	bool no_seam_pack = false;
 	bool pdl = true;            // step seam as a programmatic dependent of the pair kernel (SMD_PDL=0: plain stream order)
+	bool pdl_chain = false;     // SMD_PDL=2: the build kernels and the pair kernel are programmatic dependents too
 	int *pair_done = nullptr;   // [blocks] completion words, see PairGeo::done
 	int pair_epoch = 0;
 	smd::EnergyArgs du_en;

@@ -33,6 +33,17 @@ __device__ __forceinline__ double block_sum(double v)
 	return v;
 }
 
+// Programmatic dependent launch (the kernels of the step loop are launched with the stream-serialization attribute when
+// nothing is recorded between them): wait for the grid before this one to complete and flush -- a no-op under a plain
+// launch --, then let the grid after this one become resident on whatever this one leaves free.  Every kernel launched
+// with the attribute calls this first thing (k_chain_kick orders itself by completion words instead), so completion is
+// transitive along the chain.
+__device__ __forceinline__ void pdl_prologue()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ Particle load_particle(const Particle *p)
 {
 	// two 16-byte loads of one aligned 32-byte record (one sector)
@@ -336,6 +347,7 @@ __device__ __forceinline__ uint2 quantize16(const Particle &p, const Geom &g, co
 __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
                                              int *cellOfSlot, int *errflag, const int *__restrict__ gid, int *slot_of)
 {
+	pdl_prologue();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	Window w = window_of(bbox, g, cellcap);
 	int local = -1;
@@ -378,6 +390,7 @@ __device__ __forceinline__ void scan_chunk(int ncells, int &b0, int &b1)
 
 __global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int *bbox, Geom g, long long cellcap, int *blockSums)
 {
+	pdl_prologue();
 	int b0, b1;
 	scan_chunk(window_of(bbox, g, cellcap).ncells, b0, b1);
 	int sum = 0;
@@ -405,6 +418,7 @@ __global__ void k_arm_bbox(int *bbox)
 __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox, Geom g, long long cellcap, int *win, const int *blockSums,
                                                     int *start, int *cursor, int N, int *nlive, int *errflag)
 {
+	pdl_prologue();
 	const Window wd = window_of(bbox, g, cellcap);
 	const int ncells = wd.ncells;
 	int b0, b1;
@@ -490,6 +504,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox,
 // pass 2: claim a position inside the cell's range (arbitrary order, fixed by k_reorder)
 __global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int2 *order, const int *__restrict__ gid)
 {
+	pdl_prologue();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= cnt.get()) return;
 	int c = cellOfSlot[s];
@@ -507,6 +522,7 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *_
                                                  const float *__restrict__ acut, int *bbox, int rearm, uint2 *pos16_out,
                                                  const float *__restrict__ arad, const int *__restrict__ win, Geom geo)
 {
+	pdl_prologue();
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	// rearm: every few hundred builds the occupied-cell extremes start from scratch, to follow a drifting object (nobody
 	// reads them between the scan and the next tagging pass)
@@ -1099,6 +1115,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
                                                             const int *__restrict__ gid, EnergyArgs en,
                                                             const uint2 *__restrict__ pos16, SeamArgs sa)
 {
+	asm volatile("griddepcontrol.wait;" ::: "memory");   // (its dependents are released further down, see pg.done)
 	static_assert(!FUSE || (EMODE == 0 && LANGEVIN), "the step seam follows the force + Langevin evaluation");
 	static_assert(EMODE != 3 || SYMM, "forces + dPotential in one pass: symmetric tables only");
 	constexpr bool ENERGY_ONLY = (EMODE == 1 || EMODE == 2);   // no forces; every unordered pair once
@@ -2083,6 +2100,7 @@ __global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *p
 __global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int cap, Particle *pos, double *vel, double *unw, int *gid,
                                                      SlabComm c, int seq, int *errflag, long long spin_limit)
 {
+	pdl_prologue();
 	__shared__ int n_s[2];
 	if (threadIdx.x < 2) {
 		const char *buf = c.recv[threadIdx.x] + (size_t)(seq & 1) * c.parity_stride;
@@ -2158,6 +2176,7 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 	// done != nullptr: launched as a programmatic dependent of the pair kernel -- this block may be resident while the
 	// tail of that grid is still running and only needs the accelerations of its own 128 slots, which pair block `blk`
 	// signals with done[blk] = epoch (everything else it reads was final before the pair kernel started)
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the build that follows waits for this grid (pdl_prologue)
 	if (done) {
 		const int blk = slot0 / TPB + (int)blockIdx.x;
 		if (blk * TPB < cnt.get()) {

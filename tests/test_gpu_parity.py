@@ -283,8 +283,9 @@ def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
     else:
         m, _ = orc.load_golden(golden_path(case))
     out = []
+    # (SMD_PDL=0: plain stream order; 2: programmatic dependent launches along every kernel of the step, not only the seam)
     envs = ({"SMD_PAIR_SEAM": "1", "SMD_CHUNKS": "1"}, {"SMD_CHUNKS": "3"}, {"SMD_CHUNKS": "2"}, {"SMD_CHUNKS": "1"},
-            {"SMD_NO_FUSE": "1"})
+            {"SMD_PDL": "0"}, {"SMD_PDL": "2"}, {"SMD_NO_FUSE": "1"})
     for env in envs:
         os.environ.update(env)
         try:

@@ -57,6 +57,54 @@ def test_mc_helpers_follow_md_cpp():
     assert not capi.mc_accept(-50.0, 0.0, box, new_box, 3.0, 0.5)[0]
 
 
+def test_step_mc_host_sequence_arms_the_call_that_holds_the_last_step():
+    """softmold_b200/slab.py step_mc without a GPU: recording stand-ins for the contexts.  The scaling is proposed from the
+    box BEFORE the steps, every rank is armed with it right before the smd_step call that contains the last step (the
+    batched driver cuts a run into calls of four steps), dpotential is asked for that same scaling, the all-reduced sum
+    decides, and an accepted move rescales every rank."""
+    from softmold_b200.slab import LocalSlabGroup
+
+    class FakeCtx:
+        def __init__(self, share):
+            self.calls, self.share, self.box = [], share, np.array([30.0, 20.0, 40.0])
+
+        def get_box(self):
+            return self.box.copy()
+
+        def arm_dpotential(self, scale):
+            self.calls.append(("arm", tuple(scale)))
+
+        def step(self, first, n):
+            self.calls.append(("step", first, n))
+
+        def dpotential(self, scale):
+            self.calls.append(("dU", tuple(scale)))
+            t = np.zeros(capi.NTERMS)
+            t[capi.TERM_PAIR] = self.share
+            return t
+
+        def rescale(self, scale, new_box):
+            self.calls.append(("rescale", tuple(scale)))
+            self.box = np.array(new_box)
+
+    grp = LocalSlabGroup.__new__(LocalSlabGroup)
+    grp.nranks, grp.temperature, grp.batched_default = 3, 3.0, True
+    grp.ctx = [FakeCtx(0.5), FakeCtx(0.25), FakeCtx(0.25)]        # partial sums: +1.0 in total -> always accepted
+    box0 = grp.get_box()
+    new_box, scale = capi.mc_propose(box0, 0.01, 0.9)
+    acc, dU, box = grp.step_mc(16, 10, 0.01, 0.5, 0.9, 0.3)
+    assert acc and np.array_equal(box, new_box)
+    assert dU == 1.0 + 0.5 * (new_box[0] * new_box[1] - box0[0] * box0[1])
+    for c in grp.ctx:
+        assert c.calls == [("step", 16, 4), ("step", 20, 4), ("arm", tuple(scale)), ("step", 24, 2), ("dU", tuple(scale)),
+                           ("rescale", tuple(scale))]
+    # a rejected move rescales nobody
+    grp.ctx = [FakeCtx(-40.0), FakeCtx(-40.0)]
+    grp.nranks = 2
+    acc, _, box = grp.step_mc(0, 4, 0.01, 0.0, 0.9, 0.999)
+    assert not acc and all(c.calls[-1][0] == "dU" and c.calls[0][0] == "arm" for c in grp.ctx)
+
+
 def test_two_rank_gloo_partition_and_replicated_decisions():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
