@@ -801,12 +801,12 @@ static int launch_field(smd_ctx *ctx, const FieldMol &f, const Particle *pos, Do
 	switch (f.kind) {
 	case SMD_MOL_BOUNDARY:
 		if (f.n <= 0) break;
-		LAUNCH(k_boundary<MODE>, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, ctx->geom, f.d_idx, (int)f.c[0], f.c[1], f.c[3], acc, part);
+		LAUNCHP(k_boundary<MODE>, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, ctx->geom, f.d_idx, (int)f.c[0], f.c[1], f.c[3], acc, part);
 		done(nblk(f.n, TPB), SMD_TERM_FIELD);
 		break;
 	case SMD_MOL_FLOATING_BASE:
 		if (f.n <= 0) break;
-		LAUNCH(k_floating_base<MODE>, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, f.d_idx, f.d_C, acc, part);
+		LAUNCHP(k_floating_base<MODE>, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, f.d_idx, f.d_C, acc, part);
 		done(nblk(f.n, TPB), SMD_TERM_FIELD);
 		break;
 	case SMD_MOL_ZTORQUE:
@@ -814,7 +814,7 @@ static int launch_field(smd_ctx *ctx, const FieldMol &f, const Particle *pos, Do
 			int start = f.blocks[3 * j], nCh = f.blocks[3 * j + 1], len = f.blocks[3 * j + 2];
 			long long nt = (long long)nCh * (len - 2);
 			if (len < 3 || nt <= 0) continue;
-			LAUNCH(k_ztorque<MODE>, nblk((int)nt, TPB), TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, start, nCh, len, f.c[0], f.c[1], f.c[2], f.c[3],
+			LAUNCHP(k_ztorque<MODE>, nblk((int)nt, TPB), TPB, 0, ctx->cap, pos, ctx->slot_of, ctx->geom, start, nCh, len, f.c[0], f.c[1], f.c[2], f.c[3],
 			       acc, part);
 			done(nblk((int)nt, TPB), SMD_TERM_FIELD);
 		}
@@ -823,7 +823,7 @@ static int launch_field(smd_ctx *ctx, const FieldMol &f, const Particle *pos, Do
 		for (int j = 0; j < f.n; j++) {
 			int start = f.blocks[2 * j], cnt = f.blocks[2 * j + 1];
 			if (cnt <= 0) continue;
-			LAUNCH(k_zpower<MODE>, nblk(cnt, TPB), TPB, 0, cnt, ctx->cap, pos, ctx->slot_of, start, f.c[0], f.c[1], acc, part);
+			LAUNCHP(k_zpower<MODE>, nblk(cnt, TPB), TPB, 0, cnt, ctx->cap, pos, ctx->slot_of, start, f.c[0], f.c[1], acc, part);
 			done(nblk(cnt, TPB), SMD_TERM_FIELD);
 		}
 		break;
@@ -950,21 +950,21 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 	if (mask & SMD_MASK(SMD_TERM_BOND))
 		for (auto &b : ctx->bonds)
 			if (b.n > 0)
-				LAUNCH(k_bond<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+				LAUNCHP(k_bond<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
 	if (mask & SMD_MASK(SMD_TERM_BEND))
 		for (auto &b : ctx->bends)
 			if (b.n > 0)
-				LAUNCH(k_bend<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+				LAUNCHP(k_bend<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
 	if (mask & SMD_MASK(SMD_TERM_BALL))
 		for (auto &b : ctx->balls)
 			if (b.n > 0)
-				LAUNCH(k_ball<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_cj, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+				LAUNCHP(k_ball<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_cj, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
 	if (mask & SMD_MASK(SMD_TERM_BEAD))
 		for (auto &b : ctx->beads) {
 			if (b.nOwn <= 0) continue;
-			LAUNCH(k_beadbead<0>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius,
+			LAUNCHP(k_beadbead<0>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius,
 			       ctx->acc, nullptr, 1.0, 1.0, 1.0);
-			LAUNCH(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
+			LAUNCHP(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
 			       b.d_beads, b.d_C, b.nOwn <= 20 ? 1 : 0, 0, ctx->acc, nullptr, 1.0, 1.0, 1.0);
 		}
 	if (mask & SMD_MASK(SMD_TERM_FIELD))
@@ -975,7 +975,7 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 	if (mask & SMD_MASK(SMD_TERM_NANOCORE))
 		for (auto &f : ctx->fields)
 			if (f.kind == SMD_MOL_NANOCORE && f.n > 0)
-				LAUNCH(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
+				LAUNCHP(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
 				       f.d_idx, f.d_C, 0, 1, ctx->acc, nullptr, 1.0, 1.0, 1.0);
 	return SMD_OK;
 }
@@ -1415,7 +1415,7 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 			                    done, epoch));
 			ctx->launches++;
 		} else if (last) {
-			LAUNCH(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
+			LAUNCHP(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
 			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0);
 		} else {
 			// slab mode: the seam kernel is also the send side of the exchange (migrants + halo packed as the particles get
@@ -1434,7 +1434,7 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 				                    done, epoch));
 				ctx->launches++;
 			} else
-			LAUNCH(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
+			LAUNCHP(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
 			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
 			       ctx->errflag, bs, 0, seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr,
 			       (const int *)nullptr, 0);

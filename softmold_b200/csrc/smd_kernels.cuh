@@ -2176,6 +2176,8 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 	// done != nullptr: launched as a programmatic dependent of the pair kernel -- this block may be resident while the
 	// tail of that grid is still running and only needs the accelerations of its own 128 slots, which pair block `blk`
 	// signals with done[blk] = epoch (everything else it reads was final before the pair kernel started)
+	// without completion words (systems with list molecules or fields: their kernels ran in between) the plain dependency
+	if (!done) asm volatile("griddepcontrol.wait;" ::: "memory");
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the build that follows waits for this grid (pdl_prologue)
 	if (done) {
 		const int blk = slot0 / TPB + (int)blockIdx.x;
@@ -2257,6 +2259,7 @@ __global__ void __launch_bounds__(TPB) k_bond(int nb, int cap, const Particle *_
                                               const int *__restrict__ ij, double r0, double kk, double *acc, double *partials,
                                               double sx, double sy, double sz)
 {
+	pdl_prologue();
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0;
 	if (b < nb) {
@@ -2288,6 +2291,7 @@ __global__ void __launch_bounds__(TPB) k_ball(int nb, int cap, const Particle *_
                                               const int *__restrict__ cj, double r0, double kk, double *acc, double *partials,
                                               double sx, double sy, double sz)
 {
+	pdl_prologue();
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0, fx = 0, fy = 0, fz = 0;
 	const int s1f = (MODE == 0) ? slot_of[cj[0]] : 0;
@@ -2335,6 +2339,7 @@ __global__ void __launch_bounds__(TPB) k_bend(int nb, int cap, const Particle *_
                                               const int *__restrict__ ijk, double c0, double kk, double *acc, double *partials,
                                               double sx, double sy, double sz)
 {
+	pdl_prologue();
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0;
 	if (b < nb) {
@@ -2445,6 +2450,7 @@ __global__ void __launch_bounds__(TPB) k_beadbead(int nOwn, int nAll, int cap, c
                                                   const double *__restrict__ C, double R, double *acc, double *partials,
                                                   double sx, double sy, double sz)
 {
+	pdl_prologue();
 	double usum = 0;
 	for (int t = threadIdx.x; t < nOwn * nAll; t += blockDim.x) {
 		int j = t / nAll, k = t % nAll;
@@ -2487,6 +2493,7 @@ __global__ void __launch_bounds__(TPB) k_bead(int N, int nOwn, int cap, const Pa
                                               const double *__restrict__ C, int excl_all, int nano, double *acc, double *partials,
                                               double sx, double sy, double sz)
 {
+	pdl_prologue();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	bool live = s < N;
 	Particle p;
@@ -2552,6 +2559,7 @@ template <int MODE>
 __global__ void __launch_bounds__(TPB) k_boundary(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
                                                   const int *__restrict__ idx, int dim, double centre, double kk, double *acc, double *partials)
 {
+	pdl_prologue();
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0;
 	if (b < nb) {
@@ -2585,6 +2593,7 @@ template <int MODE>
 __global__ void __launch_bounds__(TPB) k_floating_base(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of,
                                                        const int *__restrict__ idx, const double *__restrict__ C, double *acc, double *partials)
 {
+	pdl_prologue();
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0;
 	if (b < nb) {
@@ -2625,6 +2634,7 @@ __global__ void __launch_bounds__(TPB) k_ztorque(int cap, const Particle *__rest
                                                  int start, int nChains, int len, double c0, double c1, double c2, double c3,
                                                  double *acc, double *partials)
 {
+	pdl_prologue();
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	int per = len - 2;
 	double usum = 0;
@@ -2661,6 +2671,7 @@ template <int MODE>
 __global__ void __launch_bounds__(TPB) k_zpower(int count, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, int start,
                                                 double kk, double n, double *acc, double *partials)
 {
+	pdl_prologue();
 	int t = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0;
 	if (t < count) {
