@@ -79,3 +79,17 @@ def test_mpd_errors_like_the_reference(tmp_path):
         sm.Mpd(str(tmp_path / "bad"))
     with pytest.raises(sm.SoftMoldError, match="Could not open"):
         sm.Mpd(str(tmp_path / "missing"))
+
+
+def test_documented_switches_exist_in_the_sources():
+    """README.md's table of run-time switches against the sources: a documented variable that nothing reads is a lie"""
+    import re
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    table = readme[readme.index("Run-time switches"):]
+    names = set(re.findall(r"`(SMD_[A-Z_]+)", table))
+    assert len(names) >= 12
+    src = ""
+    for f in ("smd_core.cu", "md_main.cpp", "smd_kernels.cuh"):
+        src += open(os.path.join(ROOT, "softmold_b200", "csrc", f)).read()
+    missing = [n for n in sorted(names) if f'"{n}"' not in src]
+    assert not missing, missing
