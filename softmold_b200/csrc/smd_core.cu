@@ -10,6 +10,7 @@
 
 #include "smd_kernels.cuh"
 #include "smd_pair_split.cuh"
+#include "smd_pair_tile.cuh"
 
 using namespace smd;
 
@@ -150,7 +151,7 @@ static void choose_xs(smd_ctx *ctx)
 {
 	Geom &g = ctx->geom;
 	int xs = ctx->xs_wanted;
-	if (ctx->pair_split || STAGE_CAP > 0 || (ctx->tables_set && !ctx->tables_symmetric)) xs = 1;
+	if (ctx->pair_split || (STAGE_CAP > 0 && !SMD_STAGE64) || (ctx->tables_set && !ctx->tables_symmetric)) xs = 1;
 	const long long cap = ctx->cellcap > 0 ? ctx->cellcap : ctx->cellcap_limit;   // before / after the tables were allocated
 	while (xs > 1 && ((long long)g.nc[0] * g.nc[1] * g.nc[2] * xs > cap)) xs >>= 1;
 	if (xs < 1) xs = 1;
@@ -192,6 +193,7 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
 static int pair_force_smem(smd_ctx *ctx, bool du = false);
+static int pair_tile_smem(smd_ctx *ctx, bool du);
 
 static int upload_acut(smd_ctx *ctx)
 {
@@ -288,6 +290,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_PDL"); ctx->pdl = !(e && *e == '0'); ctx->pdl_chain = e ? (*e == '2') : SMD_DEFAULT_PDL_CHAIN; }   // slab mode: exchange packed by a kernel of its own (A/B)   // smd_step_mc: dPotential in a pass of its own (A/B)
 	{ const char *e = getenv("SMD_CHUNKS"); int v = e ? atoi(e) : SMD_DEFAULT_CHUNKS; ctx->chunks = std::min(std::max(v, 1), 8); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
+	{ const char *e = getenv("SMD_PAIR_ENGINE"); ctx->pair_tile = e && *e == '1'; }   // 1: the warp-cooperative experiment k_pair_tile (smd_pair_tile.cuh; measured slower)
 	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
 	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
@@ -321,6 +324,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->acut, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->pos16, (cap + 16) * sizeof(uint2)));   // + overhang, as for pos32
 	CKC(cudaMemset(ctx->pos16, 0, (cap + 16) * sizeof(uint2)));
+	CKC(cudaMalloc(&ctx->pos8, (cap + 32) * sizeof(unsigned)));
+	CKC(cudaMemset(ctx->pos8, 0, (cap + 32) * sizeof(unsigned)));
 	CKC(cudaMalloc(&ctx->arad, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->utab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
@@ -394,6 +399,13 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_force_smem(ctx, true));
+			const int tsm = pair_tile_smem(ctx, false), tsmd = pair_tile_smem(ctx, true);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
+			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsmd);
 			if (e1 == cudaSuccess) have = smem;
 		}
 		if (e1 != cudaSuccess) {
@@ -419,7 +431,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (int b = 0; b < 2; b++) {
 		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]);
 	}
-	cudaFree(ctx->pos32); cudaFree(ctx->pos16); cudaFree(ctx->arad); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
+	cudaFree(ctx->pos32); cudaFree(ctx->pos16); cudaFree(ctx->pos8); cudaFree(ctx->arad); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
 	cudaFree(ctx->nl_ent); cudaFree(ctx->nl_rng); cudaFree(ctx->nl_cnt); cudaFree(ctx->nl_part);
 	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
 	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
@@ -514,6 +526,9 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 				if (rad[t] > 0) rmin = std::min(rmin, rad[t]);
 			}
 			ctx->pgeo.rmin32 = rmin;
+			ctx->rad_short = -1.0f;   // k_pair_tile: one radius for every short-range class = the largest of them
+			for (int t = 0; t < nT; t++)
+				if (rad[t] > 0 && rad[t] < (float)ctx->desc.cutoff) ctx->rad_short = std::max(ctx->rad_short, rad[t]);
 			CK(cudaMemcpyAsync(ctx->arad, rad.data(), rad.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 			CK(cudaStreamSynchronize(ctx->stream));
 		}
@@ -893,6 +908,34 @@ extern "C" int smd_set_noise(smd_ctx *ctx, const double *u)
 }
 
 // ------------------------------------------------------------------------------------------------ cell build
+// quantisation of the 4-byte candidate records of k_pair_tile: TILE_M steps per cell edge, per axis
+static Tile8 tile8(const smd_ctx *ctx)
+{
+	Tile8 t;
+	for (int d = 0; d < 3; d++) t.tq[d] = (double)TILE_M / ctx->geom.cs[d];
+	t.rcf = (float)ctx->desc.cutoff;
+	return t;
+}
+
+// phase-1 cutoffs of k_pair_tile in steps^2 of the finest axis (see smd_pair_tile.cuh): ((R / s_min) + 1.75)^2, R^2 widened
+// by `extra` for the launches that also sum a dPotential, and the class weights that ride in the fourth byte
+static TileGeo tile_geo(const smd_ctx *ctx, double extra)
+{
+	const Geom &g = ctx->geom;
+	const double smin = std::min(g.cs[0], std::min(g.cs[1], g.cs[2])) / TILE_M;
+	auto cutq = [&](double R2) {
+		const double v = sqrt(R2 + extra) / smin + 1.75;
+		return (int)floor(v * v * (1.0 + 1e-9)) + 1;
+	};
+	TileGeo t;
+	t.cut_long = cutq(g.rc2);
+	t.cut_short = ctx->rad_short > 0 ? std::min(cutq((double)ctx->rad_short * ctx->rad_short), t.cut_long) : t.cut_long;
+	const int half = (t.cut_long - t.cut_short) / 2;
+	if (half <= 255) { t.wA = half > 0 ? 1 : 0; t.wB = half; }
+	else { t.wB = 255; t.wA = half / 255; }
+	return t;
+}
+
 static int build_cells(smd_ctx *ctx)
 {
 	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1, pcur = ctx->pcur, pnxt = pcur ^ 1;
@@ -909,7 +952,7 @@ static int build_cells(smd_ctx *ctx)
 	LAUNCHP(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
 	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0, ctx->pos16, ctx->arad, ctx->win,
-	       ctx->geom);
+	       ctx->geom, ctx->pos8, tile8(ctx));
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
 	ctx->pcur = pnxt;
@@ -1056,7 +1099,13 @@ static int pair_force_smem(smd_ctx *ctx, bool du)   // du: the force + dPotentia
 {
 	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
 	       (du ? (PTAB_STRIDE * ctx->nT * ctx->nT + PAIR_TPB) * (int)sizeof(double) : 0) +
-	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short) + (STAGE_CAP > 0 ? (STAGE_CAP + 8) * (int)sizeof(uint2) : 0);
+	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short) + (STAGE_CAP > 0 ? (SMD_STAGE64 ? 32 + STAGE_CAP * (int)sizeof(Particle) : (STAGE_CAP + 8) * (int)sizeof(uint2)) : 0);
+}
+
+static int pair_tile_smem(smd_ctx *ctx, bool du)
+{
+	const int tabs = PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double);
+	return (int)((sizeof(TileSmem) + 15) & ~size_t(15)) + tabs + (du ? tabs + PAIR_TPB * (int)sizeof(double) : 0);
 }
 
 static NeighLists neigh_lists(smd_ctx *ctx)
@@ -1071,6 +1120,28 @@ template <bool LANGEVIN>
 static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg, const SeamArgs *seam = nullptr)
 {
 	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
+	if (ctx->pair_tile && !seam && !ctx->pair_split) {   // the round-2 engine (smd_pair_tile.cuh)
+		if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
+			ctx->du_armed = false;
+			LAUNCHP((k_pair_tile<3, true, true>), nb, PAIR_TPB, pair_tile_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, ctx->du_en.extra32), ctx->acc, lg,
+			       ctx->gid[ctx->cur], ctx->du_en);
+			ctx->du_ready = true;
+			return SMD_OK;
+		}
+		if (getenv("SMD_TILE_P1ONLY")) {
+			LAUNCHP((k_pair_tile<0, LANGEVIN, true, true>), nb, PAIR_TPB, pair_tile_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, 0.0), ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+			return SMD_OK;
+		}
+		if (ctx->tables_symmetric)
+			LAUNCHP((k_pair_tile<0, LANGEVIN, true>), nb, PAIR_TPB, pair_tile_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, 0.0), ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+		else
+			LAUNCH((k_pair_tile<0, LANGEVIN, false>), nb, PAIR_TPB, pair_tile_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, 0.0), ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
+		return SMD_OK;
+	}
 	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric && !ctx->pair_split && !seam) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
 		ctx->du_armed = false;
 		LAUNCHP((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,

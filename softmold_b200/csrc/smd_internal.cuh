@@ -136,6 +136,9 @@ struct smd_ctx {
 	float *acut;      // [nT] FP32 phase-1 class cutoff per type, margin included (see k_pair_force2)
 	uint2 *pos16;     // 8-byte phase-1 candidates {x,y,z: 16-bit window-relative fixed point; cutoff^2 as a bf16} of pos[cur]
 	float *arad;      // [nT] phase-1 class radius per type (rc, rm, or -1: interacts with nothing), no margin
+	unsigned *pos8;   // 4-byte phase-1 candidates of k_pair_tile {x,y,z: 8-bit coordinates inside the own cell; class, cx & 3} of pos[cur]
+	float rad_short = -1.0f;   // largest class radius below the cutoff (purely repulsive types), -1: none
+	bool pair_tile = false;    // SMD_PAIR_ENGINE=1: the warp-cooperative experiment k_pair_tile
 	double *ptab;     // [nT*nT][PTAB_STRIDE] padded force table + exact branch thresholds
 	double *utab;     // same layout, potential constants (energy modes of the two-phase kernel)
 	bool force_onephase_energy = false;   // SMD_ENERGY_ONEPHASE=1: use the one-phase half-stencil energy kernels (A/B checks)

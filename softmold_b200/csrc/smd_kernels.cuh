@@ -342,6 +342,22 @@ __device__ __forceinline__ uint2 quantize16(const Particle &p, const Geom &g, co
 	return make_uint2(q[0] | (q[1] << 16), q[2] | (thr << 16));
 }
 
+// pos8[]: the 4-byte phase-1 candidate record of k_pair_tile (smd_pair_tile.cuh).
+constexpr int TILE_M = 80;           // steps per cell edge: three cells = 240 <= 255
+// 4-byte candidate record of a particle: coordinates inside its own reference cell in TILE_M steps per edge (clamped:
+// the cell index carries the reference's upper-edge clamp), class, cx & 3
+struct Tile8 { double tq[3]; float rcf; };   // TILE_M / cell size per axis; the cutoff as a float (class of a type: arad[] against it)
+__device__ __forceinline__ unsigned quantize8(const Particle &p, const Geom &g, const double tq[3], float rad, float rcf)
+{
+	int cx, cy, cz;
+	unpack_cell(p.cell, cx, cy, cz);
+	const int lx = min(max((int)((p.x - (double)cx * g.cs[0]) * tq[0]), 0), TILE_M - 1);
+	const int ly = min(max((int)((p.y - (double)cy * g.cs[1]) * tq[1]), 0), TILE_M - 1);
+	const int lz = min(max((int)((p.z - (double)cz * g.cs[2]) * tq[2]), 0), TILE_M - 1);
+	const unsigned cls = rad < 0.f ? 2u : (rad < rcf ? 1u : 0u);
+	return (unsigned)lx | ((unsigned)ly << 8) | ((unsigned)lz << 16) | ((cls | ((unsigned)(cx & 3) << 2)) << 24);
+}
+
 // pass 1 of the counting sort: histogram over the window.  Warp-aggregated: lanes sharing a cell elect a leader
 // that issues one atomicAdd for the group.
 __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
@@ -520,7 +536,8 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *_
                                                  const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
                                                  const int *gid_in, int *gid_out, int *slot_of, float4 *pos32_out,
                                                  const float *__restrict__ acut, int *bbox, int rearm, uint2 *pos16_out,
-                                                 const float *__restrict__ arad, const int *__restrict__ win, Geom geo)
+                                                 const float *__restrict__ arad, const int *__restrict__ win, Geom geo, unsigned *pos8_out,
+                                                 Tile8 t8)
 {
 	pdl_prologue();
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,6 +557,7 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *_
 	store_particle(pos_out + t, p);
 	pos32_out[t] = make_float4((float)p.x, (float)p.y, (float)p.z, acut[p.type]);   // FP32 mirror: periodic-image path of k_pair_force2
 	pos16_out[t] = quantize16(p, geo, win, __int_as_float(win[WIN_RES]), __int_as_float(win[WIN_INVRES]), arad[p.type]);   // its phase-1 candidates
+	pos8_out[t] = quantize8(p, geo, t8.tq, arad[p.type], t8.rcf);   // phase-1 candidates of k_pair_tile
 	vel_out[t] = vel_in[s]; vel_out[cap + t] = vel_in[cap + s]; vel_out[2 * cap + t] = vel_in[2 * cap + s];
 	if (unw_in) { unw_out[t] = unw_in[s]; unw_out[cap + t] = unw_in[cap + s]; unw_out[2 * cap + t] = unw_in[2 * cap + s]; }
 	if (acc_in) { acc_out[t] = acc_in[s]; acc_out[cap + t] = acc_in[cap + s]; acc_out[2 * cap + t] = acc_in[2 * cap + s]; }
@@ -933,6 +951,13 @@ constexpr int PAIR_TPB = 128;
 #ifndef SMD_PAIR_CAP
 #define SMD_PAIR_CAP 128
 #endif
+// SMD_STAGE64=1 (with SMD_STAGE_CAP = records per block): what is staged is not phase 1's 8-byte candidates but the 32-byte
+// FP64 records of the same nine slot ranges, for PHASE 2: its gathers (two 16-byte loads per list entry, the long-scoreboard
+// stall that bounds the evaluation when it runs alone: 8.7 stalled warps per issue in k_pair_drain) become shared-memory
+// loads; the bulk copies land during phase 1.
+#ifndef SMD_STAGE64
+#define SMD_STAGE64 0
+#endif
 // SMD_PAIR_FLAT=1: phase 1 walks one flat stream per thread instead of meeting the other lanes after every stencil
 // row.  More lanes stay busy (24 instead of 18 of 32 per instruction, 10 % fewer warp instructions), but the lanes of
 // a cell, which walk nearly the same ranges, drift apart and stop sharing their loads: a warp-wide load that was a
@@ -1133,7 +1158,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 #ifdef SMD_EXP_TIMING
 	long long t_exp = clock64();
 #endif
-	extern __shared__ __align__(16) unsigned char s_raw[];
+	extern __shared__ __align__(128) unsigned char s_raw[];
 	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
 	const int nptab = PTAB_STRIDE * nT * nT;
@@ -1142,7 +1167,10 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	double *s_utab = s_ptab + nptab;
 	double *s_dup = s_utab + nptab;
 	unsigned short *s_lists = reinterpret_cast<unsigned short *>(DU ? s_dup + PAIR_TPB : s_ptab + nptab);
-#if SMD_STAGE_CAP > 0
+#if SMD_STAGE_CAP > 0 && SMD_STAGE64
+	const Particle *s_stage = reinterpret_cast<const Particle *>(
+	    s_raw + ((reinterpret_cast<unsigned char *>(s_lists + (PAIR_TPB / 32) * PAIR_CAP * 32) - s_raw + 31) & ~size_t(31)));
+#elif SMD_STAGE_CAP > 0
 	uint2 *s_stage = reinterpret_cast<uint2 *>(s_lists + (PAIR_TPB / 32) * PAIR_CAP * 32);
 #endif
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1176,8 +1204,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const int off = d0 * (oy + d1 * oz);
 		const int a = min(max(lin_of(sf) + off - 1, 0), ncells);
 		const int e = max(min(max(lin_of(sl) + off + 2, 0), ncells), a);
-		sm.st_gs[tid] = start[a];
-		sm.st_ge[tid] = start[e];
+		sm.st_gs[tid] = start[a * xs];   // (the offset table has xs entries per cell)
+		sm.st_ge[tid] = start[e * xs];
 	}
 #endif
 
@@ -1194,28 +1222,40 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		// global memory -- and start one bulk copy (TMA, cp.async.bulk) per piece.  The copies land while the threads
 		// work out their own candidate ranges below; everybody waits on the mbarrier just before phase 1.
 		if (tid == 0) {
-			int cursor = 0, run_end = 0, run_delta = 0, np = 0;
-			for (int r = 0; r < PAIR_NSEG; r++) {
+			int cursor = 0, run_start = 0, run_end = 0, run_delta = 0, np = 0;
+			for (int rr = 0; rr < PAIR_NSEG; rr++) {
+#if SMD_STAGE64
+				// most wanted first: the own row, the four rows that share a face with it, the four corner rows (14 % of the hits)
+				const int r = (0x862075314ull >> (4 * rr)) & 15;
+#else
+				const int r = rr;
+#endif
 				const int gs = sm.st_gs[r], ge = sm.st_ge[r];
 				int dl = STAGE_NONE;
 				if (ge > gs) {
+#if SMD_STAGE64
+					const int pe = ge;              // 32-byte records: any slot is a 16-byte granule
+#else
 					const int pe = (ge + 1) & ~1;   // pieces start and end on even slots: 16-byte granules
+#endif
 					int b, len, d;
-					if (cursor > 0 && gs <= run_end) { b = run_end; len = max(pe - run_end, 0); d = run_delta; }
-					else { b = gs & ~1; len = pe - b; d = cursor - b; }
+					if (cursor > 0 && gs >= run_start && gs <= run_end) { b = run_end; len = max(pe - run_end, 0); d = run_delta; }
+					else { b = SMD_STAGE64 ? gs : (gs & ~1); len = pe - b; d = cursor - b; }
 					if (cursor + len <= STAGE_CAP) {
 						if (len > 0) { sm.st_src[np] = b; sm.st_dst[np] = cursor; sm.st_len[np] = len; np++; }
+						if (d != run_delta || cursor == 0) run_start = b;
 						cursor += len; run_end = b + len; run_delta = d; dl = d;
 						if (len == 0) run_end = max(run_end, pe);
 					}
 				}
 				sm.st_delta[r] = dl;
 			}
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)cursor * 8u) : "memory");
+			constexpr unsigned RECB = SMD_STAGE64 ? 32u : 8u;
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)cursor * RECB) : "memory");
 			const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_stage);
 			for (int k = 0; k < np; k++)
-				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + 8u * (unsigned)sm.st_dst[k]),
-				             "l"(pos16 + sm.st_src[k]), "r"(8u * (unsigned)sm.st_len[k]), "r"(mbar)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + RECB * (unsigned)sm.st_dst[k]),
+				             "l"(SMD_STAGE64 ? (const void *)(pos + sm.st_src[k]) : (const void *)(pos16 + sm.st_src[k])), "r"(RECB * (unsigned)sm.st_len[k]), "r"(mbar)
 				             : "memory");
 		}
 #endif
@@ -1260,6 +1300,18 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			int b;
 			asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(tb + (unsigned)(e >> PAIR_SEGBITS) * (4u * PAIR_TPB)) : "memory");
 			j = b + (int)(e & ((1u << PAIR_SEGBITS) - 1u));
+#if SMD_STAGE_CAP > 0 && SMD_STAGE64
+			const int dl = sm.st_delta[e >> PAIR_SEGBITS];
+			if (dl != STAGE_NONE) {
+				const double2 *q = reinterpret_cast<const double2 *>(s_stage + (j + dl));
+				const double2 a0 = q[0], b0 = q[1];
+				Particle r_;
+				r_.x = a0.x; r_.y = a0.y; r_.z = b0.x;
+				r_.type = (int)(__double_as_longlong(b0.y) & 0xffffffffll);
+				r_.cell = (unsigned)((unsigned long long)__double_as_longlong(b0.y) >> 32);
+				return r_;
+			}
+#endif
 			return load_particle(pos + j);
 		};
 		// Potential<T>, MD.h:895-930, on r^2 (x normal and positive): correctly rounded sqrt as above, both branches
@@ -1499,7 +1551,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const float ir = __int_as_float(win[WIN_INVRES]);
 		extq = (ext * ir) * ir * (1.000001f + 1.75f / (pg.rmin32 * ir));
 	}
-#if SMD_STAGE_CAP > 0
+#if SMD_STAGE_CAP > 0 && !SMD_STAGE64
 #ifdef SMD_EXP_TIMING
 	long long t_w0 = clock64();
 #endif
@@ -1580,7 +1632,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	for (int sg = 0; sg < nseg; sg++) {
 		const int n = sm.seg_n[sg][tid];
 		if (n == 0) continue;
-#if SMD_STAGE_CAP > 0
+#if SMD_STAGE_CAP > 0 && !SMD_STAGE64
 		const int jb = sm.seg_b[sg][tid], dl = sm.st_delta[sg];
 		const uint2 *cp = dl != STAGE_NONE ? s_stage + (jb + dl) : pos16 + jb;
 #else
@@ -1710,6 +1762,15 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 
 #ifdef SMD_EXP_TIMING
 	if (EMODE == 0 && tid == 0) { long long t = clock64(); atomicAdd(&g_pair_timing[1], (unsigned long long)(t - t_exp)); t_exp = t; }
+#endif
+#if SMD_STAGE_CAP > 0 && SMD_STAGE64
+	{   // the staged records have landed? (the copies were issued before phase 1)
+		unsigned ok;
+		do {
+			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+			             : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(&sm.mbar)), "r"(0u) : "memory");
+		} while (!ok);
+	}
 #endif
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];

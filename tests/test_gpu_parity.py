@@ -407,6 +407,45 @@ def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
         assert np.array_equal(u, w)
 
 
+@pytest.mark.parametrize("workload", ["bilayer", "liposome", "gas", "gas_asym"])
+def test_tile_pair_engine_is_bit_identical_to_the_round1_engine(orc, workload):
+    """k_pair_tile (warp-cooperative 8-bit dp4a prefilter, bit-mask lists; smd_pair_tile.cuh) against k_pair_force2
+    (SMD_PAIR_ENGINE=0): the same pairs summed in the same order -- forces, the force + dPotential pass of smd_step_mc and
+    a trajectory with box moves, bit for bit.  The gases make every cell a boundary cell (periodic-image path) and, with
+    asymmetric tables, send every pair through the general routine."""
+    import os
+    from softmold_b200 import workloads
+    from test_gpu_edge import gas
+    if workload == "bilayer":
+        m = workloads.bilayer(4000, 3.11, seed=5)
+    elif workload == "liposome":
+        m = workloads.liposome(3000, 3.45, 2)
+    else:
+        m = gas(11, 6000, (17.0, 9.3, 13.1), n_types=4, symmetric=(workload == "gas"), chains=((300, 3),))
+    out = []
+    for env in ("0", "1"):
+        os.environ["SMD_PAIR_ENGINE"] = env
+        try:
+            ctx = sm.Context.from_dict(m)
+        finally:
+            del os.environ["SMD_PAIR_ENGINE"]
+        ctx.compute_forces(mask=1 << sm.TERM_PAIR)
+        a0 = ctx.get_forces()
+        ctx.compute_forces(step=2)
+        ctx.step(2, 20)
+        a = ctx.get_forces()
+        boxes = []
+        if workload != "gas_asym":
+            rng = np.random.default_rng(3)
+            for k in range(3):
+                boxes.append(ctx.step_mc(22 + 8 * k, 8, 0.01, 0.1, rng.random(), rng.random())[2])
+        x, _, v = ctx.get_particles()
+        out.append((a0, a, x, v, np.array(boxes)))
+        ctx.close()
+    for u, w in zip(*out):
+        assert np.array_equal(u, w)
+
+
 def test_x_sliced_sort_changes_nothing_but_the_summation_order(orc):
     """Geom::xs: the sort key splits every reference cell into x slices so that phase 1 of the pair kernel reads only the
     slices within reach.  Against SMD_XSUB=1 (cell-sorted only): identical cell ids and linked-list ranks, identical
