@@ -9,8 +9,6 @@
 #include <algorithm>
 
 #include "smd_kernels.cuh"
-#include "smd_pair_split.cuh"
-#include "smd_pair_tile.cuh"
 
 using namespace smd;
 
@@ -61,9 +59,6 @@ static cudaError_t launch_ex(bool pdl, void (*kernel)(KArgs...), int grid, int b
 static const int MAX_PARTIALS = 1 << 20;
 #ifndef SMD_DEFAULT_PDL_CHAIN
 #define SMD_DEFAULT_PDL_CHAIN true
-#endif
-#ifndef SMD_DEFAULT_CHUNKS
-#define SMD_DEFAULT_CHUNKS 1
 #endif
 
 // particle count of a launch: by value on a single GPU, from the device word in slab mode (ctx->N is then only the
@@ -151,7 +146,7 @@ static void choose_xs(smd_ctx *ctx)
 {
 	Geom &g = ctx->geom;
 	int xs = ctx->xs_wanted;
-	if (ctx->pair_split || (STAGE_CAP > 0 && !SMD_STAGE64) || (ctx->tables_set && !ctx->tables_symmetric)) xs = 1;
+	if (ctx->tables_set && !ctx->tables_symmetric) xs = 1;
 	const long long cap = ctx->cellcap > 0 ? ctx->cellcap : ctx->cellcap_limit;   // before / after the tables were allocated
 	while (xs > 1 && ((long long)g.nc[0] * g.nc[1] * g.nc[2] * xs > cap)) xs >>= 1;
 	if (xs < 1) xs = 1;
@@ -193,7 +188,6 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
 static int pair_force_smem(smd_ctx *ctx, bool du = false);
-static int pair_tile_smem(smd_ctx *ctx, bool du);
 
 static int upload_acut(smd_ctx *ctx)
 {
@@ -276,26 +270,17 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->launches = ctx->rebuilds = 0;
 	{ const char *e = getenv("SMD_ENERGY_ONEPHASE"); ctx->force_onephase_energy = e && *e == '1'; }
 	// SMD_NO_FUSE=1: every phase of the step in its own kernel (A/B and bit-identity tests).
-	// SMD_PAIR_SEAM=1: run the step seam in the epilogue of the pair kernel instead of a kernel of its own (k_chain_kick).
-	// Bit-identical; measured on C2: the pair kernel grows from 156.5 to 173.3 us while the 20.4 us seam kernel disappears
-	// (-3.7 us per step, nothing once the unfused step before every box move is counted): the seam's chain of dependent
-	// gathers keeps a 128-register block resident ~10 k cycles longer instead of hiding behind the other blocks.  Off.
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
-	{ const char *e = getenv("SMD_PAIR_SEAM"); ctx->no_pair_fuse = !(e && *e == '1'); }
 	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }
 	// SMD_PDL=0: plain stream order everywhere; 1: only the step seam is a programmatic dependent (of the pair kernel);
 	// 2 (default): so are the kernels of the build, the pair kernel itself and the slab unpack (LAUNCHP).  Measured per MD
 	// step: C2 218.3 / 213.9 / 203.4 us, a 15 000-particle vesicle 72.7 / 77.4 / 66.3 us.
 	{ const char *e = getenv("SMD_PDL"); ctx->pdl = !(e && *e == '0'); ctx->pdl_chain = e ? (*e == '2') : SMD_DEFAULT_PDL_CHAIN; }   // slab mode: exchange packed by a kernel of its own (A/B)   // smd_step_mc: dPotential in a pass of its own (A/B)
-	{ const char *e = getenv("SMD_CHUNKS"); int v = e ? atoi(e) : SMD_DEFAULT_CHUNKS; ctx->chunks = std::min(std::max(v, 1), 8); }
 	{ const char *e = getenv("SMD_XSUB"); int v = e ? atoi(e) : 4; ctx->xs_wanted = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }
-	{ const char *e = getenv("SMD_PAIR_ENGINE"); ctx->pair_tile = e && *e == '1'; }   // 1: the warp-cooperative experiment k_pair_tile (smd_pair_tile.cuh; measured slower)
-	{ const char *e = getenv("SMD_PAIR_SPLIT"); ctx->pair_split = e && *e == '1'; }   // measured slower (237 vs 177 us on C2): off by default
 	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
 	ctx->pgeo.rmin32 = (float)desc->cutoff;
-	ctx->pgeo.block0 = 0;
 	ctx->pgeo.done = nullptr; ctx->pgeo.epoch = 0;
 	int rc = check_geom(ctx);
 	if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
@@ -324,17 +309,9 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->acut, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->pos16, (cap + 16) * sizeof(uint2)));   // + overhang, as for pos32
 	CKC(cudaMemset(ctx->pos16, 0, (cap + 16) * sizeof(uint2)));
-	CKC(cudaMalloc(&ctx->pos8, (cap + 32) * sizeof(unsigned)));
-	CKC(cudaMemset(ctx->pos8, 0, (cap + 32) * sizeof(unsigned)));
 	CKC(cudaMalloc(&ctx->arad, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->utab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
-	if (ctx->pair_split) {   // global candidate lists of the two-kernel pair engine (smd_pair_split.cuh)
-		CKC(cudaMalloc(&ctx->nl_ent, ((size_t)cap * NL_CAP + 64) * sizeof(unsigned short)));
-		CKC(cudaMalloc(&ctx->nl_rng, (size_t)PAIR_NSEG * cap * sizeof(int)));
-		CKC(cudaMalloc(&ctx->nl_cnt, cap * sizeof(int)));
-		CKC(cudaMalloc(&ctx->nl_part, 3 * cap * sizeof(double)));
-	}
 	CKC(cudaMalloc(&ctx->win, WIN_WORDS * sizeof(int)));
 	CKC(cudaMemset(ctx->win, 0, WIN_WORDS * sizeof(int)));
 	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
@@ -392,20 +369,12 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 		cudaError_t e1 = cudaSuccess;
 		if (smem > have) {
 			e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_force2<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_force_smem(ctx, true));
-			const int tsm = pair_tile_smem(ctx, false), tsmd = pair_tile_smem(ctx, true);
-			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
-			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
-			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
-			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
-			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm);
-			if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_pair_tile<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsmd);
 			if (e1 == cudaSuccess) have = smem;
 		}
 		if (e1 != cudaSuccess) {
@@ -431,8 +400,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (int b = 0; b < 2; b++) {
 		cudaFree(ctx->pos[b]); cudaFree(ctx->vel[b]); cudaFree(ctx->gid[b]); cudaFree(ctx->unw[b]);
 	}
-	cudaFree(ctx->pos32); cudaFree(ctx->pos16); cudaFree(ctx->pos8); cudaFree(ctx->arad); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
-	cudaFree(ctx->nl_ent); cudaFree(ctx->nl_rng); cudaFree(ctx->nl_cnt); cudaFree(ctx->nl_part);
+	cudaFree(ctx->pos32); cudaFree(ctx->pos16); cudaFree(ctx->arad); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
 	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
 	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
 	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
@@ -455,8 +423,6 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto &f : ctx->fields) { cudaFree(f.d_idx); cudaFree(f.d_C); }
 	prof_drain(ctx);
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
-	for (int c = 0; c < 8; c++) { if (ctx->cstream[c]) cudaStreamDestroy(ctx->cstream[c]); if (ctx->ev_chunk[c]) cudaEventDestroy(ctx->ev_chunk[c]); }
-	if (ctx->ev_build) cudaEventDestroy(ctx->ev_build);
 	if (ctx->pair_done) cudaFree(ctx->pair_done);
 	if (ctx->du_partials) cudaFree(ctx->du_partials);
 	cudaStreamDestroy(ctx->stream);
@@ -526,9 +492,6 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 				if (rad[t] > 0) rmin = std::min(rmin, rad[t]);
 			}
 			ctx->pgeo.rmin32 = rmin;
-			ctx->rad_short = -1.0f;   // k_pair_tile: one radius for every short-range class = the largest of them
-			for (int t = 0; t < nT; t++)
-				if (rad[t] > 0 && rad[t] < (float)ctx->desc.cutoff) ctx->rad_short = std::max(ctx->rad_short, rad[t]);
 			CK(cudaMemcpyAsync(ctx->arad, rad.data(), rad.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 			CK(cudaStreamSynchronize(ctx->stream));
 		}
@@ -908,34 +871,6 @@ extern "C" int smd_set_noise(smd_ctx *ctx, const double *u)
 }
 
 // ------------------------------------------------------------------------------------------------ cell build
-// quantisation of the 4-byte candidate records of k_pair_tile: TILE_M steps per cell edge, per axis
-static Tile8 tile8(const smd_ctx *ctx)
-{
-	Tile8 t;
-	for (int d = 0; d < 3; d++) t.tq[d] = (double)TILE_M / ctx->geom.cs[d];
-	t.rcf = (float)ctx->desc.cutoff;
-	return t;
-}
-
-// phase-1 cutoffs of k_pair_tile in steps^2 of the finest axis (see smd_pair_tile.cuh): ((R / s_min) + 1.75)^2, R^2 widened
-// by `extra` for the launches that also sum a dPotential, and the class weights that ride in the fourth byte
-static TileGeo tile_geo(const smd_ctx *ctx, double extra)
-{
-	const Geom &g = ctx->geom;
-	const double smin = std::min(g.cs[0], std::min(g.cs[1], g.cs[2])) / TILE_M;
-	auto cutq = [&](double R2) {
-		const double v = sqrt(R2 + extra) / smin + 1.75;
-		return (int)floor(v * v * (1.0 + 1e-9)) + 1;
-	};
-	TileGeo t;
-	t.cut_long = cutq(g.rc2);
-	t.cut_short = ctx->rad_short > 0 ? std::min(cutq((double)ctx->rad_short * ctx->rad_short), t.cut_long) : t.cut_long;
-	const int half = (t.cut_long - t.cut_short) / 2;
-	if (half <= 255) { t.wA = half > 0 ? 1 : 0; t.wB = half; }
-	else { t.wB = 255; t.wA = half / 255; }
-	return t;
-}
-
 static int build_cells(smd_ctx *ctx)
 {
 	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1, pcur = ctx->pcur, pnxt = pcur ^ 1;
@@ -952,7 +887,7 @@ static int build_cells(smd_ctx *ctx)
 	LAUNCHP(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
 	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
 	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0, ctx->pos16, ctx->arad, ctx->win,
-	       ctx->geom, ctx->pos8, tile8(ctx));
+	       ctx->geom);
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
 	ctx->pcur = pnxt;
@@ -1099,85 +1034,31 @@ static int pair_force_smem(smd_ctx *ctx, bool du)   // du: the force + dPotentia
 {
 	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
 	       (du ? (PTAB_STRIDE * ctx->nT * ctx->nT + PAIR_TPB) * (int)sizeof(double) : 0) +
-	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short) + (STAGE_CAP > 0 ? (SMD_STAGE64 ? 32 + STAGE_CAP * (int)sizeof(Particle) : (STAGE_CAP + 8) * (int)sizeof(uint2)) : 0);
-}
-
-static int pair_tile_smem(smd_ctx *ctx, bool du)
-{
-	const int tabs = PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double);
-	return (int)((sizeof(TileSmem) + 15) & ~size_t(15)) + tabs + (du ? tabs + PAIR_TPB * (int)sizeof(double) : 0);
-}
-
-static NeighLists neigh_lists(smd_ctx *ctx)
-{
-	NeighLists nl;
-	nl.ent = ctx->nl_ent; nl.rng = ctx->nl_rng; nl.cnt = ctx->nl_cnt; nl.part = ctx->nl_part;
-	return nl;
+	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
 }
 
 // the pair force of all particles into acc[] (LANGEVIN: a = thermostat term + pair sum, else a += pair sum)
 template <bool LANGEVIN>
-static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg, const SeamArgs *seam = nullptr)
+static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
 {
 	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
-	if (ctx->pair_tile && !seam && !ctx->pair_split) {   // the round-2 engine (smd_pair_tile.cuh)
-		if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
-			ctx->du_armed = false;
-			LAUNCHP((k_pair_tile<3, true, true>), nb, PAIR_TPB, pair_tile_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, ctx->du_en.extra32), ctx->acc, lg,
-			       ctx->gid[ctx->cur], ctx->du_en);
-			ctx->du_ready = true;
-			return SMD_OK;
-		}
-		if (getenv("SMD_TILE_P1ONLY")) {
-			LAUNCHP((k_pair_tile<0, LANGEVIN, true, true>), nb, PAIR_TPB, pair_tile_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, 0.0), ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
-			return SMD_OK;
-		}
-		if (ctx->tables_symmetric)
-			LAUNCHP((k_pair_tile<0, LANGEVIN, true>), nb, PAIR_TPB, pair_tile_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, 0.0), ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
-		else
-			LAUNCH((k_pair_tile<0, LANGEVIN, false>), nb, PAIR_TPB, pair_tile_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->pos8,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, tile_geo(ctx, 0.0), ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{});
-		return SMD_OK;
-	}
-	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric && !ctx->pair_split && !seam) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
+	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
 		ctx->du_armed = false;
 		LAUNCHP((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16,
-		       SeamArgs{});
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16);
 		ctx->du_ready = true;
-		return SMD_OK;
-	}
-	if (seam) {   // forces + Langevin + the step seam in one kernel (see SeamArgs); the caller checked pair_fusable()
-		LAUNCH((k_pair_force2<0, true, true, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16,
-		       *seam);
-		return SMD_OK;
-	}
-	if (ctx->pair_split) {
-		const int dsm = PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double);
-		LAUNCH(k_pair_lists<0>, nb, PAIR_TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
-		       ctx->fC, ctx->pgeo, ctx->gid[ctx->cur], EnergyArgs{}, neigh_lists(ctx));
-		if (ctx->tables_symmetric)
-			LAUNCH((k_pair_drain<0, LANGEVIN, true>), nb, PAIR_TPB, dsm, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->geom, ctx->nT, ctx->fC,
-			       ctx->ptab, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, neigh_lists(ctx));
-		else
-			LAUNCH((k_pair_drain<0, LANGEVIN, false>), nb, PAIR_TPB, dsm, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->geom, ctx->nT, ctx->fC,
-			       ctx->ptab, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, neigh_lists(ctx));
 		return SMD_OK;
 	}
 	if (ctx->tables_symmetric)
 		LAUNCHP((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
 	else
 		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
 	return SMD_OK;
 }
 
-static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first, const SeamArgs *seam = nullptr)
+static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first)
 {
 	int N = ctx->N;
 	// CellOpt::build: always rebuilt (the reference rebuilds every step, MD.cpp:412)
@@ -1203,17 +1084,11 @@ static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first
 		lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
 		// (a launch that also sums a dPotential is timed apart: bench.py's roofline describes the plain force launch; when
 		// only the plain phase is being profiled, the other one inherits the request)
-		const bool du_launch = ctx->du_armed && ctx->tables_symmetric && !ctx->pair_split;
+		const bool du_launch = ctx->du_armed && ctx->tables_symmetric;
 		if (du_launch && ((ctx->prof_mask >> SMD_PHASE_PAIR) & 1u)) ctx->prof_mask |= 1u << SMD_PHASE_PAIR_DU;
 		ProfScope ps(ctx, du_launch ? SMD_PHASE_PAIR_DU : SMD_PHASE_PAIR);
-		SeamArgs sa;
-		if (seam) {
-			sa = *seam;
-			sa.pos_out = ctx->pos[ctx->pcur ^ 1]; sa.vel = ctx->vel[ctx->cur]; sa.unw = ctx->unw[ctx->cur];
-			seam = &sa;
-		}
-		if ((rc = launch_pair_force<true>(ctx, lg, seam))) return rc;
-		ctx->acc_live = !seam;   // the fused kernel consumes the acceleration in registers
+		if ((rc = launch_pair_force<true>(ctx, lg))) return rc;
+		ctx->acc_live = true;
 	} else {
 		LAUNCH(k_zero3, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->acc);
 		ctx->acc_live = true;
@@ -1342,75 +1217,6 @@ static ChainSet chain_set(const smd_ctx *ctx)
 	return cs;
 }
 
-// One MD step of the fused path as a pipeline over `chunks` runs of blocks (see smd_ctx::chunks): build on the main stream,
-// then per chunk, on its own stream (earlier chunks at higher priority): pair force + Langevin of the chunk's particles,
-// the chunk's step seam.  A seam only needs the accelerations of its own particles and writes the OTHER position buffer,
-// so the seam of chunk c runs beside the pair kernel of chunk c + 1.  Same kernels, same arithmetic: bit-identical.
-static int step_chunked(smd_ctx *ctx, int64_t step, bool last, const ChainSet &cs, const BeadSet &bs)
-{
-	const int N = ctx->N, C = ctx->chunks;
-	if (!ctx->ev_build) {
-		int least = 0, greatest = 0;
-		CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));   // numerically lower = higher priority
-		CK(cudaEventCreateWithFlags(&ctx->ev_build, cudaEventDisableTiming));
-		for (int c = 0; c < C; c++) {
-			CK(cudaStreamCreateWithPriority(&ctx->cstream[c], cudaStreamNonBlocking, std::min(greatest + c, least)));
-			CK(cudaEventCreateWithFlags(&ctx->ev_chunk[c], cudaEventDisableTiming));
-		}
-	}
-	ctx->acc_live = false;
-	if (!ctx->cells_valid) { ProfScope ps(ctx, SMD_PHASE_BUILD); build_cells(ctx); }
-	LangevinArgs lg = {};
-	lg.gamma = ctx->desc.gamma;
-	lg.sigma = langevin_sigma(ctx);
-	lg.seed = ctx->desc.seed; lg.step = (uint64_t)step;
-	lg.vel = ctx->vel[ctx->cur]; lg.gid = ctx->gid[ctx->cur];
-	cudaStream_t main_stream = ctx->stream;
-	CK(cudaEventRecord(ctx->ev_build, main_stream));
-	const int nb = nblk(N, PAIR_TPB);
-	const bool prof_pair = (ctx->prof_mask >> SMD_PHASE_PAIR) & 1u;
-	cudaEvent_t e0 = nullptr;
-	const PairGeo pg_keep = ctx->pgeo;
-	for (int c = 0; c < C; c++) {
-		const int b0 = (int)((long long)nb * c / C), b1 = (int)((long long)nb * (c + 1) / C);
-		if (b1 <= b0) continue;
-		cudaStream_t st = ctx->cstream[c];
-		CK(cudaStreamWaitEvent(st, ctx->ev_build, 0));
-		if (prof_pair && !e0) { e0 = prof_event(ctx); cudaEventRecord(e0, st); }
-		ctx->stream = st;   // LAUNCH goes to ctx->stream
-		PairGeo pg = pg_keep;
-		pg.block0 = b0;
-		if (ctx->tables_symmetric)
-			LAUNCH((k_pair_force2<0, true, true>), b1 - b0, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
-		else
-			LAUNCH((k_pair_force2<0, true, false>), b1 - b0, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16, SeamArgs{});
-		if (prof_pair && c == C - 1) {   // the span of the chunks' pair kernels (seams of earlier chunks run inside it)
-			cudaEvent_t e1 = prof_event(ctx);
-			cudaEventRecord(e1, st);
-			ctx->prof_pending.push_back({SMD_PHASE_PAIR, e0, e1});
-		}
-		if (last)
-			LAUNCH(k_chain_kick<true>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur], ctx->acc,
-			       ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0);
-		else
-			LAUNCH(k_chain_kick<false>, b1 - b0, TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1], ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, b0 * PAIR_TPB, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0);
-		ctx->stream = main_stream;
-		CK(cudaEventRecord(ctx->ev_chunk[c], st));
-		CK(cudaStreamWaitEvent(main_stream, ctx->ev_chunk[c], 0));
-	}
-	if (last) {
-		ctx->acc_live = true;
-	} else {
-		ctx->pcur ^= 1;
-		ctx->acc_live = false;
-		ctx->cells_valid = false;
-	}
-	return SMD_OK;
-}
-
 extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 {
 	if (!ctx) return SMD_ERR_ARG;
@@ -1434,36 +1240,17 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	BeadSet bs;
 	bead_set(ctx, bs);
 	const int N = ctx->N;
-	const bool pair_fusable = !ctx->no_pair_fuse && ctx->tables_symmetric && !ctx->pair_split && only_chains(ctx);
 	// molecule kinds that add to a[] before the seam (none for CHAIN-only systems)
 	const uint32_t scatter = only_chains(ctx) ? 0u : (SMD_MASK_ALL_MOLECULES & ~SMD_MASK(SMD_TERM_CHAIN));
-	static_assert(TPB == PAIR_TPB, "the step pipeline cuts the pair grid and the seam grid at the same slots");
-	const bool chunked = ctx->chunks > 1 && !ctx->slab && !ctx->pair_split && only_chains(ctx) && !pair_fusable && N >= 2 * PAIR_TPB * ctx->chunks;
+	static_assert(TPB == PAIR_TPB, "seam block b waits for the completion word of pair block b: same slots");
 	for (int k = 0; k < nsteps; k++) {
 		ProfScope ps(ctx, SMD_PHASE_STEP);
 		const bool last = (k == nsteps - 1);
-		if (chunked) {
-			if ((rc = step_chunked(ctx, first_step + k, last, cs, bs))) return rc;
-			continue;
-		}
 		ctx->du_armed = last && ctx->du_for_last;
-		if (!last && pair_fusable) {
-			// thermostat, build, pair force, chain terms, Verlet::second, next Verlet::first: the build + ONE kernel
-			SeamArgs sa;
-			sa.pos_out = nullptr; sa.vel = nullptr; sa.unw = nullptr;   // filled in by forces() once the build has flipped the buffers
-			sa.slot_of = ctx->slot_of; sa.cs = cs; sa.dt = ctx->desc.dt; sa.bbox = ctx->bbox; sa.errflag = ctx->errflag;
-			rc = forces(ctx, SMD_MASK(SMD_TERM_PAIR) | SMD_MASK_LANGEVIN, first_step + k, true, &sa);
-			if (rc) return rc;
-			ctx->pcur ^= 1;
-			ctx->acc_live = false;
-			ctx->cells_valid = false;
-			if (ctx->slab && (rc = smd_slab_exchange_send(ctx))) return rc;
-			continue;
-		}
 		// The seam as a programmatic dependent of the pair kernel (CHAIN-only systems, nothing recorded in between): its
 		// blocks move in where the tail of the pair grid has left SMs empty and start on their 128 slots as soon as the
 		// pair block of those slots has signalled (PairGeo::done) -- the seam hides in the pair kernel's last, sparse round.
-		const bool pdl = ctx->pdl && scatter == 0 && ctx->prof_mask == 0 && !ctx->pair_split && ctx->tables_symmetric;
+		const bool pdl = ctx->pdl && scatter == 0 && ctx->prof_mask == 0 && ctx->tables_symmetric;
 		if (pdl) {
 			if (!ctx->pair_done) {
 				CK(cudaMalloc(&ctx->pair_done, (size_t)nblk(ctx->cap, PAIR_TPB) * sizeof(int)));
@@ -1554,15 +1341,8 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 		double grow = 0;   // the most a component-wise scaling moves r^2 across a cutoff, relative
 		for (double sc : {sx, sy, sz}) grow = std::max(grow, std::max(fabs(sc * sc - 1.0), fabs(1.0 / (sc * sc) - 1.0)));
 		en.extra32 = MODE == 1 ? 0.0f : nextafterf((float)(1.01 * grow * ctx->geom.rc2 + 1e-7), INFINITY);
-		if (ctx->pair_split) {
-			LAUNCH(k_pair_lists<MODE>, nb, PAIR_TPB, 0, cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->uC,
-			       ctx->pgeo, ctx->gid[ctx->cur], en, neigh_lists(ctx));
-			LAUNCH((k_pair_drain<MODE, false, true>), nb, PAIR_TPB, PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double), cnt_of(ctx), ctx->cap, pos,
-			       ctx->geom, ctx->nT, ctx->uC, ctx->utab, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, neigh_lists(ctx));
-		} else {
-			LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
-			       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, ctx->pos16, SeamArgs{});
-		}
+		LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
+		       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, ctx->pos16);
 		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
 	} else {
 		int nb = nblk(N, TPB);
@@ -1772,7 +1552,7 @@ extern "C" int smd_arm_dpotential(smd_ctx *ctx, const double scale[3])
 	REQUIRE(scale, "null scale");
 	ctx->du_ready = false;
 	ctx->du_for_last = false;
-	const bool fuse = can_fuse(ctx) && ctx->tables_symmetric && !ctx->pair_split && !ctx->force_onephase_energy && ctx->chunks == 1 &&
+	const bool fuse = can_fuse(ctx) && ctx->tables_symmetric && !ctx->force_onephase_energy &&
 	                  !ctx->no_du_fuse && ctx->desc.noise != SMD_NOISE_EXTERNAL;
 	if (!fuse) return SMD_OK;
 	CK(cudaSetDevice(ctx->device));

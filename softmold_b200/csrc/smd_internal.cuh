@@ -87,7 +87,6 @@ struct PairGeo {            // phase-1 constants of k_pair_force2
 	float cs32[3];          // cell size
 	float rmin32;           // smallest positive per-type phase-1 radius (pos16 path: widening of the energy modes' cutoffs)
 	float finv32;           // x slices per unit length (Geom::finv)
-	int block0;             // first block of this launch when the grid is launched in chunks (else 0)
 	int *done;              // per-block completion words for a programmatic dependent launch of the step seam (else null)
 	int epoch;              // value a block stores there
 };
@@ -136,9 +135,6 @@ struct smd_ctx {
 	float *acut;      // [nT] FP32 phase-1 class cutoff per type, margin included (see k_pair_force2)
 	uint2 *pos16;     // 8-byte phase-1 candidates {x,y,z: 16-bit window-relative fixed point; cutoff^2 as a bf16} of pos[cur]
 	float *arad;      // [nT] phase-1 class radius per type (rc, rm, or -1: interacts with nothing), no margin
-	unsigned *pos8;   // 4-byte phase-1 candidates of k_pair_tile {x,y,z: 8-bit coordinates inside the own cell; class, cx & 3} of pos[cur]
-	float rad_short = -1.0f;   // largest class radius below the cutoff (purely repulsive types), -1: none
-	bool pair_tile = false;    // SMD_PAIR_ENGINE=1: the warp-cooperative experiment k_pair_tile
 	double *ptab;     // [nT*nT][PTAB_STRIDE] padded force table + exact branch thresholds
 	double *utab;     // same layout, potential constants (energy modes of the two-phase kernel)
 	bool force_onephase_energy = false;   // SMD_ENERGY_ONEPHASE=1: use the one-phase half-stencil energy kernels (A/B checks)
@@ -150,18 +146,6 @@ struct smd_ctx {
 	int *gid[2];      // original index of slot
 	int cur;          // current buffer of vel / unw / gid
 	int pcur;         // current buffer of pos (flips on its own when the fused step kernel writes the drifted positions)
-	bool pair_split = false; // SMD_PAIR_SPLIT=1: lists + drain kernels (smd_pair_split.cuh) instead of the one-kernel pair engine
-	unsigned short *nl_ent = nullptr;   // two-kernel pair engine: global candidate lists (smd_pair_split.cuh)
-	int *nl_rng = nullptr, *nl_cnt = nullptr;
-	double *nl_part = nullptr;
-	// step pipeline (smd_step, single GPU, CHAIN-only systems; SMD_CHUNKS, default 1 = off): the particles are cut into
-	// `chunks` runs of blocks, each with its own stream: pair force of the chunk, then its step seam, so that the seam of one
-	// chunk could overlap the pair kernel of the next.  Bit-identical.  Measured on C2 (us per MD step): 1 chunk 229.0,
-	// 2: 236.8, 3: 224.8, 4: 233.1, 6: 229.8 -- no consistent gain: the pair kernel's four resident blocks hold the whole
-	// register file of an SM, so a seam block only ever starts in a pair chunk's tail, and every chunk adds a tail.
-	int chunks = 1;
-	cudaStream_t cstream[8] = {};
-	cudaEvent_t ev_build = nullptr, ev_chunk[8] = {};
 	// smd_step_mc: the last step's pair kernel also sums the dPotential of the box move that follows (k_pair_force2 EMODE 3)
 	bool du_for_last = false, du_armed = false, du_ready = false, no_du_fuse = false;
 	bool no_seam_pack = false;
@@ -173,7 +157,6 @@ struct smd_ctx {
 	double *du_partials = nullptr;   // block sums of the armed dPotential (their own buffer: nothing else writes it)
 	size_t du_partials_n = 0;
 	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)
-	bool no_pair_fuse = true;    // unless SMD_PAIR_SEAM=1: the step seam is a kernel of its own, not the pair kernel's epilogue
 	double *acc;      // SoA [3][cap]
 	double *acc2;     // alternate buffer for builds that must carry live accelerations along
 	bool acc_live;    // acc holds forces a later kick still needs

@@ -342,22 +342,6 @@ __device__ __forceinline__ uint2 quantize16(const Particle &p, const Geom &g, co
 	return make_uint2(q[0] | (q[1] << 16), q[2] | (thr << 16));
 }
 
-// pos8[]: the 4-byte phase-1 candidate record of k_pair_tile (smd_pair_tile.cuh).
-constexpr int TILE_M = 80;           // steps per cell edge: three cells = 240 <= 255
-// 4-byte candidate record of a particle: coordinates inside its own reference cell in TILE_M steps per edge (clamped:
-// the cell index carries the reference's upper-edge clamp), class, cx & 3
-struct Tile8 { double tq[3]; float rcf; };   // TILE_M / cell size per axis; the cutoff as a float (class of a type: arad[] against it)
-__device__ __forceinline__ unsigned quantize8(const Particle &p, const Geom &g, const double tq[3], float rad, float rcf)
-{
-	int cx, cy, cz;
-	unpack_cell(p.cell, cx, cy, cz);
-	const int lx = min(max((int)((p.x - (double)cx * g.cs[0]) * tq[0]), 0), TILE_M - 1);
-	const int ly = min(max((int)((p.y - (double)cy * g.cs[1]) * tq[1]), 0), TILE_M - 1);
-	const int lz = min(max((int)((p.z - (double)cz * g.cs[2]) * tq[2]), 0), TILE_M - 1);
-	const unsigned cls = rad < 0.f ? 2u : (rad < rcf ? 1u : 0u);
-	return (unsigned)lx | ((unsigned)ly << 8) | ((unsigned)lz << 16) | ((cls | ((unsigned)(cx & 3) << 2)) << 24);
-}
-
 // pass 1 of the counting sort: histogram over the window.  Warp-aggregated: lanes sharing a cell elect a leader
 // that issues one atomicAdd for the group.
 __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom g, const int *bbox, long long cellcap, int *count,
@@ -536,8 +520,7 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *_
                                                  const double *unw_in, double *unw_out, const double *acc_in, double *acc_out,
                                                  const int *gid_in, int *gid_out, int *slot_of, float4 *pos32_out,
                                                  const float *__restrict__ acut, int *bbox, int rearm, uint2 *pos16_out,
-                                                 const float *__restrict__ arad, const int *__restrict__ win, Geom geo, unsigned *pos8_out,
-                                                 Tile8 t8)
+                                                 const float *__restrict__ arad, const int *__restrict__ win, Geom geo)
 {
 	pdl_prologue();
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -557,7 +540,6 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *_
 	store_particle(pos_out + t, p);
 	pos32_out[t] = make_float4((float)p.x, (float)p.y, (float)p.z, acut[p.type]);   // FP32 mirror: periodic-image path of k_pair_force2
 	pos16_out[t] = quantize16(p, geo, win, __int_as_float(win[WIN_RES]), __int_as_float(win[WIN_INVRES]), arad[p.type]);   // its phase-1 candidates
-	pos8_out[t] = quantize8(p, geo, t8.tq, arad[p.type], t8.rcf);   // phase-1 candidates of k_pair_tile
 	vel_out[t] = vel_in[s]; vel_out[cap + t] = vel_in[cap + s]; vel_out[2 * cap + t] = vel_in[2 * cap + s];
 	if (unw_in) { unw_out[t] = unw_in[s]; unw_out[cap + t] = unw_in[cap + s]; unw_out[2 * cap + t] = unw_in[2 * cap + s]; }
 	if (acc_in) { acc_out[t] = acc_in[s]; acc_out[cap + t] = acc_in[cap + s]; acc_out[2 * cap + t] = acc_in[2 * cap + s]; }
@@ -941,41 +923,13 @@ __device__ __forceinline__ bool chain_gather(int gi, const Particle &me, int N, 
 // The Langevin term and the zeroing of a[] are folded into the epilogue when LANGEVIN is set:
 //   a = (-gamma v + sigma (2u-1)) + sum_pairs,   exactly the order MD.cpp:357-413 produces.
 constexpr int PAIR_TPB = 128;
-// SMD_STAGE_CAP > 0: the block's phase-1 candidates are first staged in shared memory by TMA bulk copies (build with
-// -DSMD_STAGE_CAP=1792 -DSMD_PAIR_CAP=104 to keep four blocks per SM).  Measured on C2: 179 us against 172 us for
-// plain L1-cached loads of the same 8-byte records -- the lanes of a cell read the same lines, the loads were never
-// the limit, and the staging buffer costs L1 capacity that phase 2 wants -- so it is off by default.
-#ifndef SMD_STAGE_CAP
-#define SMD_STAGE_CAP 0
-#endif
 #ifndef SMD_PAIR_CAP
 #define SMD_PAIR_CAP 128
-#endif
-// SMD_STAGE64=1 (with SMD_STAGE_CAP = records per block): what is staged is not phase 1's 8-byte candidates but the 32-byte
-// FP64 records of the same nine slot ranges, for PHASE 2: its gathers (two 16-byte loads per list entry, the long-scoreboard
-// stall that bounds the evaluation when it runs alone: 8.7 stalled warps per issue in k_pair_drain) become shared-memory
-// loads; the bulk copies land during phase 1.
-#ifndef SMD_STAGE64
-#define SMD_STAGE64 0
-#endif
-// SMD_PAIR_FLAT=1: phase 1 walks one flat stream per thread instead of meeting the other lanes after every stencil
-// row.  More lanes stay busy (24 instead of 18 of 32 per instruction, 10 % fewer warp instructions), but the lanes of
-// a cell, which walk nearly the same ranges, drift apart and stop sharing their loads: a warp-wide load that was a
-// broadcast of a few addresses becomes 32 different ones, and the L1 data pipe is the busiest unit of this kernel.
-// Measured on C2: 192 us against 162 us (also with the staged copy in shared memory, and with the particles dealt to
-// the threads by candidate count: 194 - 201 us).  Off by default.
-#ifndef SMD_PAIR_FLAT
-#define SMD_PAIR_FLAT 0
-#endif
-#if SMD_PAIR_FLAT && SMD_STAGE_CAP > 0
-#error "SMD_PAIR_FLAT reads the candidates through L1: build with SMD_STAGE_CAP=0"
 #endif
 #ifndef SMD_PAIR_BLOCKS
 #define SMD_PAIR_BLOCKS 4
 #endif
 constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 128 x 32 x 2 B = 32 KiB per block
-constexpr int STAGE_CAP = SMD_STAGE_CAP; // staged phase-1 candidates per block, 8 B each (even; + 8 entries of overhang); 0: no staging
-constexpr int STAGE_NONE = INT_MIN;
 constexpr int PAIR_SEGBITS = 12;   // entry = (range index << 12) | offset inside the range
 
 struct LangevinArgs { double gamma, sigma; uint64_t seed, step; const double *vel; const int *gid; const double *ext_noise; };
@@ -1088,13 +1042,7 @@ constexpr int PTAB_STRIDE = 10;
 // cell layers only) go straight to the general routine from a separate, plain loop.
 constexpr int PAIR_NSEG = 9;
 
-#ifdef SMD_EXP_TIMING
-__device__ unsigned long long g_pair_timing[8];   // experiment builds only: clock sums of setup / phase 1 / phase 2 (per warp), warps
-#endif
 struct PairSmem {
-#ifdef SMD_EXP_TIMING
-	long long t_sync;
-#endif
 	int perm[PAIR_TPB];                 // particle (slot) taken by each thread in phase 1
 	int cnt[PAIR_TPB];                  // list length per phase-1 thread
 	int order[PAIR_TPB];                // phase-2 thread -> phase-1 thread whose list it drains
@@ -1103,11 +1051,6 @@ struct PairSmem {
 	unsigned short seg_n[PAIR_NSEG][PAIR_TPB];   // ... and length (< 4096)
 	int hist[PAIR_CAP + 2];
 	int wcnt[PAIR_TPB / 32];
-	// staging of the block's phase-1 candidates (see k_pair_force2)
-	int st_gs[PAIR_NSEG], st_ge[PAIR_NSEG];       // slots of the cells that row r of any of the block's particles can reach
-	int st_delta[PAIR_NSEG];                      // shared index - slot of the staged copy, STAGE_NONE: read from global
-	int st_src[PAIR_NSEG], st_dst[PAIR_NSEG], st_len[PAIR_NSEG];   // bulk copies issued by thread 0
-	unsigned long long mbar;                      // their completion barrier
 };
 
 //
@@ -1123,30 +1066,21 @@ struct PairSmem {
 // other half comes from the other end of the pair.  Forces stay bit-identical to EMODE 0 (same pairs, same order).
 // (EnergyArgs: smd_internal.cuh)
 
-// FUSE (forces with the Langevin term only): the thread that has just finished a particle's pair sum also runs the
-// step seam for it -- the particle's chain terms, Verlet::second of this step and Verlet::first of the next one, wrap,
-// cell tag (what k_chain_kick<false> does in a kernel of its own, same arithmetic in the same order: bit-identical) --
-// and writes the new position into the OTHER position buffer, which nobody reads during this kernel.  a[] is never
-// stored.  The seam's chain of dependent gathers (gid -> slot_of -> neighbour record) hides behind the other blocks'
-// pair work instead of being a latency-bound 20 us kernel.
-struct SeamArgs { Particle *pos_out; double *vel; double *unw; const int *slot_of; ChainSet cs; double dt; int *bbox; int *errflag; };
-
-template <int EMODE, bool LANGEVIN, bool SYMM, bool FUSE = false>
+template <int EMODE, bool LANGEVIN, bool SYMM>
 __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
                                                             const int *__restrict__ win, Geom g, int nT,
                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
                                                             PairGeo pg, double *__restrict__ acc, LangevinArgs lg,
                                                             const int *__restrict__ gid, EnergyArgs en,
-                                                            const uint2 *__restrict__ pos16, SeamArgs sa)
+                                                            const uint2 *__restrict__ pos16)
 {
 	asm volatile("griddepcontrol.wait;" ::: "memory");   // (its dependents are released further down, see pg.done)
-	static_assert(!FUSE || (EMODE == 0 && LANGEVIN), "the step seam follows the force + Langevin evaluation");
 	static_assert(EMODE != 3 || SYMM, "forces + dPotential in one pass: symmetric tables only");
 	constexpr bool ENERGY_ONLY = (EMODE == 1 || EMODE == 2);   // no forces; every unordered pair once
 	constexpr bool DU = (EMODE == 3);                          // forces + dPotential
 	const int N = cnt.get();
-	const int bid = (int)blockIdx.x + pg.block0;   // block0 != 0: one chunk of a grid launched in pieces (forces only)
+	const int bid = (int)blockIdx.x;
 	if (bid * PAIR_TPB >= N) {
 		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
 		return;
@@ -1155,9 +1089,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	// soon as every block of this grid has started (they only fit where pair blocks have left: the tail of the grid); seam
 	// block b then waits for done[b] == epoch, which block b of this grid sets when its accelerations are written.
 	if (pg.done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#ifdef SMD_EXP_TIMING
-	long long t_exp = clock64();
-#endif
 	extern __shared__ __align__(128) unsigned char s_raw[];
 	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
 	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
@@ -1167,12 +1098,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	double *s_utab = s_ptab + nptab;
 	double *s_dup = s_utab + nptab;
 	unsigned short *s_lists = reinterpret_cast<unsigned short *>(DU ? s_dup + PAIR_TPB : s_ptab + nptab);
-#if SMD_STAGE_CAP > 0 && SMD_STAGE64
-	const Particle *s_stage = reinterpret_cast<const Particle *>(
-	    s_raw + ((reinterpret_cast<unsigned char *>(s_lists + (PAIR_TPB / 32) * PAIR_CAP * 32) - s_raw + 31) & ~size_t(31)));
-#elif SMD_STAGE_CAP > 0
-	uint2 *s_stage = reinterpret_cast<uint2 *>(s_lists + (PAIR_TPB / 32) * PAIR_CAP * 32);
-#endif
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int k = tid; k < nptab; k += PAIR_TPB) s_ptab[k] = ptab[k];
 	if (DU) for (int k = tid; k < nptab; k += PAIR_TPB) s_utab[k] = en.utab[k];
@@ -1181,33 +1106,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
 	const int fd0 = win[WIN_FD0], xs = g.xs;
 
-#if SMD_STAGE_CAP > 0
-	// ---- staging, step 1: the block's 128 slots are consecutive in the cell-sorted order, so the cells its particles
-	// live in form ONE interval [cf, cl] of the window's linear cell index, and the cells that stencil row r = (oy, oz)
-	// of any of them can reach form the interval [cf + off_r - 1, cl + off_r + 1]: nine slot ranges [gs, ge) hold every
-	// phase-1 candidate of the block (about 1 300 of them, each wanted by ~20 of the block's particles).
-	const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sm.mbar);
-	if (tid == 0) {
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	if (tid < PAIR_NSEG) {
-		const int sf = bid * PAIR_TPB, sl = min(sf + PAIR_TPB, N) - 1;
-		auto lin_of = [&](int s_) {
-			int ax, ay, az;
-			unpack_cell(pos[s_].cell, ax, ay, az);
-			const int lx = g.slab ? win_x(ax, w0, g.nc[0]) : ax - w0;
-			return lx + d0 * ((ay - w1) + d1 * (az - w2));
-		};
-		const int ncells = d0 * d1 * d2;
-		const int oz = tid / 3 - 1, oy = tid - 3 * (tid / 3) - 1;
-		const int off = d0 * (oy + d1 * oz);
-		const int a = min(max(lin_of(sf) + off - 1, 0), ncells);
-		const int e = max(min(max(lin_of(sl) + off + 2, 0), ncells), a);
-		sm.st_gs[tid] = start[a * xs];   // (the offset table has xs entries per cell)
-		sm.st_ge[tid] = start[e * xs];
-	}
-#endif
 
 	// ---- deal the block's particles to threads by class
 	{
@@ -1216,49 +1114,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
 		if (lane == 0) sm.wcnt[wid] = __popc(bal);
 		__syncthreads();
-#if SMD_STAGE_CAP > 0
-		// ---- staging, step 2 (one thread): lay the nine ranges out in the staging buffer -- ranges that overlap or
-		// touch (a block that spans several cell rows) continue the same run, a range that no longer fits stays in
-		// global memory -- and start one bulk copy (TMA, cp.async.bulk) per piece.  The copies land while the threads
-		// work out their own candidate ranges below; everybody waits on the mbarrier just before phase 1.
-		if (tid == 0) {
-			int cursor = 0, run_start = 0, run_end = 0, run_delta = 0, np = 0;
-			for (int rr = 0; rr < PAIR_NSEG; rr++) {
-#if SMD_STAGE64
-				// most wanted first: the own row, the four rows that share a face with it, the four corner rows (14 % of the hits)
-				const int r = (0x862075314ull >> (4 * rr)) & 15;
-#else
-				const int r = rr;
-#endif
-				const int gs = sm.st_gs[r], ge = sm.st_ge[r];
-				int dl = STAGE_NONE;
-				if (ge > gs) {
-#if SMD_STAGE64
-					const int pe = ge;              // 32-byte records: any slot is a 16-byte granule
-#else
-					const int pe = (ge + 1) & ~1;   // pieces start and end on even slots: 16-byte granules
-#endif
-					int b, len, d;
-					if (cursor > 0 && gs >= run_start && gs <= run_end) { b = run_end; len = max(pe - run_end, 0); d = run_delta; }
-					else { b = SMD_STAGE64 ? gs : (gs & ~1); len = pe - b; d = cursor - b; }
-					if (cursor + len <= STAGE_CAP) {
-						if (len > 0) { sm.st_src[np] = b; sm.st_dst[np] = cursor; sm.st_len[np] = len; np++; }
-						if (d != run_delta || cursor == 0) run_start = b;
-						cursor += len; run_end = b + len; run_delta = d; dl = d;
-						if (len == 0) run_end = max(run_end, pe);
-					}
-				}
-				sm.st_delta[r] = dl;
-			}
-			constexpr unsigned RECB = SMD_STAGE64 ? 32u : 8u;
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((unsigned)cursor * RECB) : "memory");
-			const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_stage);
-			for (int k = 0; k < np; k++)
-				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + RECB * (unsigned)sm.st_dst[k]),
-				             "l"(SMD_STAGE64 ? (const void *)(pos + sm.st_src[k]) : (const void *)(pos16 + sm.st_src[k])), "r"(RECB * (unsigned)sm.st_len[k]), "r"(mbar)
-				             : "memory");
-		}
-#endif
 		int before = 0, total = 0;
 #pragma unroll
 		for (int k = 0; k < PAIR_TPB / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < wid) before += c; }
@@ -1300,18 +1155,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 			int b;
 			asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(tb + (unsigned)(e >> PAIR_SEGBITS) * (4u * PAIR_TPB)) : "memory");
 			j = b + (int)(e & ((1u << PAIR_SEGBITS) - 1u));
-#if SMD_STAGE_CAP > 0 && SMD_STAGE64
-			const int dl = sm.st_delta[e >> PAIR_SEGBITS];
-			if (dl != STAGE_NONE) {
-				const double2 *q = reinterpret_cast<const double2 *>(s_stage + (j + dl));
-				const double2 a0 = q[0], b0 = q[1];
-				Particle r_;
-				r_.x = a0.x; r_.y = a0.y; r_.z = b0.x;
-				r_.type = (int)(__double_as_longlong(b0.y) & 0xffffffffll);
-				r_.cell = (unsigned)((unsigned long long)__double_as_longlong(b0.y) >> 32);
-				return r_;
-			}
-#endif
 			return load_particle(pos + j);
 		};
 		// Potential<T>, MD.h:895-930, on r^2 (x normal and positive): correctly rounded sqrt as above, both branches
@@ -1469,9 +1312,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (ENERGY_ONLY && (oz < 0 || (oz == 0 && oy < 0))) row_ok = false;   // backward rows: the other particle counts the pair
 		row_ok = row_ok && !wrapyz && lz >= 0 && lz < d2 && ly >= 0 && ly < d1;
 		bool keep_lo = gyz + fm[0] * fm[0] < amax, keep_hi = gyz + fp[0] * fp[0] < amax;
-#ifdef SMD_EXP_NO_XPRUNE
-		keep_lo = keep_hi = true;
-#endif
 		// cells cx-1 .. cx+1 that need no wrap, clamped to the window (cells outside it are empty)
 		int xlo, xhi;
 		if (g.slab) {   // the window holds every neighbour column of an owned particle, possibly across the periodic seam
@@ -1501,16 +1341,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const int je = rje[r];
 		if (ENERGY_ONLY && r == 4) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
 		const int lim = (1 << PAIR_SEGBITS) - 4;
-#if SMD_PAIR_FLAT
-		if (je > jb) {   // the table holds the non-empty ranges back to back (list entries carry the table row)
-			sm.seg_b[nseg][tid] = jb;
-			sm.seg_n[nseg][tid] = (unsigned short)min(je - jb, lim);
-			nseg++;
-		}
-#else
 		sm.seg_b[r][tid] = jb;
 		sm.seg_n[r][tid] = (unsigned short)min(je - jb, lim);
-#endif
 		// a range longer than the 12-bit offset field (> 1300 particles per cell): take the excess one by one
 		for (int j = jb + lim; j < je; j++) {
 			float4 c = pos32[j];
@@ -1526,14 +1358,9 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 				}
 			}
 		}
-#if !SMD_PAIR_FLAT
 		nseg = (je > jb) ? r + 1 : nseg;
-#endif
 	}
 
-#ifdef SMD_EXP_TIMING
-	if (EMODE == 0 && tid == 0) { long long t = clock64(); atomicAdd(&g_pair_timing[0], (unsigned long long)(t - t_exp)); t_exp = t; }
-#endif
 	// ---- phase 1: prefilter along the thread's own stream of ranges over the 8-byte candidate records (16-bit
 	// window-relative coordinates, see quantize16) -- from the block's staged copy in shared memory where the range was
 	// staged, else from global memory; four candidates per step, the next four already in flight.  The coordinates are
@@ -1551,93 +1378,11 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		const float ir = __int_as_float(win[WIN_INVRES]);
 		extq = (ext * ir) * ir * (1.000001f + 1.75f / (pg.rmin32 * ir));
 	}
-#if SMD_STAGE_CAP > 0 && !SMD_STAGE64
-#ifdef SMD_EXP_TIMING
-	long long t_w0 = clock64();
-#endif
-	{   // the staged candidates have landed?
-		unsigned ok;
-		do {
-			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-			             : "=r"(ok) : "r"(mbar), "r"(0u) : "memory");
-		} while (!ok);
-	}
-#ifdef SMD_EXP_TIMING
-	if (EMODE == 0 && tid == 0) {
-		atomicAdd(&g_pair_timing[4], (unsigned long long)(clock64() - t_w0));
-		int staged = 0;
-		for (int r = 0; r < PAIR_NSEG; r++) staged += sm.st_delta[r] != STAGE_NONE || sm.st_ge[r] <= sm.st_gs[r];
-		atomicAdd(&g_pair_timing[5], (unsigned long long)staged);
-		atomicAdd(&g_pair_timing[6], 1ull);
-	}
-#endif
-#endif
 	const int aiqi = __float_as_int(aiq);
-#if SMD_PAIR_FLAT
-	// ONE flat stream per thread: the particle's ranges back to back, four candidates per step, the next four (of this
-	// range or of the next one, whose table entry is fetched a whole range ahead) already in flight; no branch in the
-	// hand-over from range to range, so the lanes of a warp only meet again at the end of the phase
-	auto test4 = [&](const uint2 (&c)[4], int rem, unsigned e0) {
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			float dx = qx - __uint_as_float(__byte_perm(c[k].x, 0x4B000000u, 0x7610));
-			float dy = qy - __uint_as_float(__byte_perm(c[k].x, 0x4B000000u, 0x7632));
-			float dz = qz - __uint_as_float(__byte_perm(c[k].y, 0x4B000000u, 0x7610));
-			float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-			if (EMODE != 0) {
-				const float cw = __uint_as_float(c[k].y & 0xffff0000u);
-				if (r2 < fminf(aiq, cw) + extq && k < rem) push(e0 + k);
-			} else {
-				const int r2i = __float_as_int(r2);
-				if (r2i < (int)c[k].y && r2i < aiqi && k < rem) push(e0 + k);
-			}
-		}
-	};
-	if (nseg > 0) {
-		const uint2 *cp = pos16 + sm.seg_b[0][tid], *ncp = cp;
-		int rem = sm.seg_n[0][tid], nn = 0, k = 0;
-		if (nseg > 1) { ncp = pos16 + sm.seg_b[1][tid]; nn = sm.seg_n[1][tid]; }
-		unsigned e0 = 0;
-		uint2 ga[4], gb[4];
-#pragma unroll
-		for (int j = 0; j < 4; j++) ga[j] = cp[j];   // pos16[] is padded: the overhang is masked in test4
-		bool more = true;
-		auto step = [&](const uint2 (&c)[4], uint2 (&nx)[4]) {
-			const unsigned ecur = e0;
-			const int rcur = rem;
-			const bool adv = rem <= 4;
-			cp = adv ? ncp : cp + 4;
-			rem = adv ? nn : rem - 4;
-			e0 = adv ? (unsigned)(k + 1) << PAIR_SEGBITS : e0 + 4u;
-			if (adv) {
-				k++;
-				more = k < nseg;
-				if (k + 1 < nseg) { ncp = pos16 + sm.seg_b[k + 1][tid]; nn = sm.seg_n[k + 1][tid]; }
-			}
-			if (more) {
-#pragma unroll
-				for (int j = 0; j < 4; j++) nx[j] = cp[j];
-			}
-			test4(c, rcur, ecur);
-			return more;
-		};
-		while (true) {
-			if (!step(ga, gb)) break;
-			if (!step(gb, ga)) break;
-			if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }   // list nearly full: never seen in practice
-		}
-		if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }
-	}
-#else
 	for (int sg = 0; sg < nseg; sg++) {
 		const int n = sm.seg_n[sg][tid];
 		if (n == 0) continue;
-#if SMD_STAGE_CAP > 0 && !SMD_STAGE64
-		const int jb = sm.seg_b[sg][tid], dl = sm.st_delta[sg];
-		const uint2 *cp = dl != STAGE_NONE ? s_stage + (jb + dl) : pos16 + jb;
-#else
 		const uint2 *cp = pos16 + sm.seg_b[sg][tid];
-#endif
 		const unsigned tag = (unsigned)sg << PAIR_SEGBITS;
 		uint2 ga[4], gb[4];                          // ping-pong buffers: one group under test, the next in flight
 #pragma unroll
@@ -1679,7 +1424,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (wp > wlim) { drain(i, pi, tid, lbase, wp, ex, ey, ez); wp = lbase; }
 	}
 
-#endif
 
 	// ---- rows and end cells seen through a periodic image (particles in the outermost cell layers only)
 	if (shifted_rows) {
@@ -1755,28 +1499,13 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	}
 	__syncthreads();
 	sm.order[atomicAdd(&sm.hist[lcnt], 1)] = tid;
-#ifdef SMD_EXP_TIMING
-	if (tid == 0) sm.t_sync = clock64();
-#endif
 	__syncthreads();
 
-#ifdef SMD_EXP_TIMING
-	if (EMODE == 0 && tid == 0) { long long t = clock64(); atomicAdd(&g_pair_timing[1], (unsigned long long)(t - t_exp)); t_exp = t; }
-#endif
-#if SMD_STAGE_CAP > 0 && SMD_STAGE64
-	{   // the staged records have landed? (the copies were issued before phase 1)
-		unsigned ok;
-		do {
-			asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-			             : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(&sm.mbar)), "r"(0u) : "memory");
-		} while (!ok);
-	}
-#endif
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];
 	const int io = sm.perm[o];
 	const bool act = io < N && !(g.slab && (gid[io] & GID_GHOST));
-	if (EMODE == 0 && !FUSE && !act && !pg.done) return;
+	if (EMODE == 0 && !act && !pg.done) return;
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
 	if (DU) du = s_dup[o];
 	if (act) {
@@ -1802,50 +1531,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (tid == 0) en.partials[blockIdx.x] = tot;
 		return;
 	}
-	if (FUSE) {
-		const bool valid = io < N;
-		Particle p;
-		p.x = p.y = p.z = 0; p.type = 0; p.cell = 0;
-		int gi = 0;
-		if (valid) { p = load_particle(pos + io); gi = gid[io]; }
-		if (act) {
-			const int id = gi & GID_MASK;
-			double u[3];
-			if (lg.ext_noise) {
-				u[0] = lg.ext_noise[3 * id]; u[1] = lg.ext_noise[3 * id + 1]; u[2] = lg.ext_noise[3 * id + 2];
-			} else {
-				philox_uniform3(lg.seed, lg.step, (uint32_t)id, u);
-			}
-			double vx = sa.vel[io], vy = sa.vel[cap + io], vz = sa.vel[2 * cap + io];
-			// a = (Langevin + pair sum) + chain terms: the two sums k_pair_force2 and k_chain_kick would have formed
-			double fx = (-lg.gamma * vx + lg.sigma * (2.0 * u[0] - 1.0)) + ax;
-			double fy = (-lg.gamma * vy + lg.sigma * (2.0 * u[1] - 1.0)) + ay;
-			double fz = (-lg.gamma * vz + lg.sigma * (2.0 * u[2] - 1.0)) + az;
-			V3 A;
-			if (!chain_gather(id, p, N, pos, gid, sa.slot_of, g, sa.cs, A)) atomicOr(sa.errflag, ERR_SLAB_MISSING);
-			fx = fx + A.x; fy = fy + A.y; fz = fz + A.z;
-			if (p.type != 0) {
-				const double h = 0.5 * sa.dt;
-				vx += (fx * h); vy += (fy * h); vz += (fz * h);                                 // Verlet::second of this step
-				vx += (fx * h); vy += (fy * h); vz += (fz * h);                                 // Verlet::first of the next one
-				p.x += vx * sa.dt; p.y += vy * sa.dt; p.z += vz * sa.dt;
-				if (sa.unw) { sa.unw[io] += vx * sa.dt; sa.unw[cap + io] += vy * sa.dt; sa.unw[2 * cap + io] += vz * sa.dt; }
-				sa.vel[io] = vx; sa.vel[cap + io] = vy; sa.vel[2 * cap + io] = vz;
-			}
-			if (p.x > g.box[0]) p.x -= g.box[0];
-			if (p.x < 0) p.x += g.box[0];
-			if (p.y > g.box[1]) p.y -= g.box[1];
-			if (p.y < 0) p.y += g.box[1];
-			if (p.z > g.box[2]) p.z -= g.box[2];
-			if (p.z < 0) p.z += g.box[2];
-		}
-		tag_cell(p, g, sa.bbox, sa.errflag, act);
-		if (valid) {
-			if (!act) p.cell = CELL_DEAD;   // slab ghost: replaced by the exchange that follows
-			store_particle(sa.pos_out + io, p);
-		}
-		return;
-	}
 	if (!act) {
 		// (only reached with pg.done: every thread of the block takes part in the hand-over below)
 	} else if (LANGEVIN) {
@@ -1868,13 +1553,6 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		__syncthreads();
 		if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(pg.done + bid), "r"(pg.epoch) : "memory");
 	}
-#ifdef SMD_EXP_TIMING
-	if (EMODE == 0 && lane == 0) {   // per warp: phase 2 as seen by each warp; [3] counts warps
-		long long t = clock64();
-		atomicAdd(&g_pair_timing[2], (unsigned long long)(t - sm.t_sync));
-		atomicAdd(&g_pair_timing[3], 1ull);
-	}
-#endif
 }
 
 template <int MODE>

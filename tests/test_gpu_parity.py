@@ -274,7 +274,7 @@ def test_two_phase_energy_kernels_match_one_phase(orc):
 @pytest.mark.parametrize("case", ["lipo_eq", "bilayer_eq", "lipocyto_chains"])
 def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
     """smd_step fuses chain forces + Verlet::second + the next Verlet::first into one per-particle kernel for CHAIN-only
-    systems (SMD_PAIR_SEAM=1: into the epilogue of the pair kernel; SMD_NO_FUSE=1: separate kernels); the trajectory must
+    systems (SMD_NO_FUSE=1: separate kernels; SMD_PDL: how the kernels of the step are chained); the trajectory must
     not change by a single bit"""
     import os
     if case == "lipocyto_chains":      # two CHAIN molecules of different length (3 and 10), explicit BOND list dropped
@@ -284,8 +284,7 @@ def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
         m, _ = orc.load_golden(golden_path(case))
     out = []
     # (SMD_PDL=0: plain stream order; 2: programmatic dependent launches along every kernel of the step, not only the seam)
-    envs = ({"SMD_PAIR_SEAM": "1", "SMD_CHUNKS": "1"}, {"SMD_CHUNKS": "3"}, {"SMD_CHUNKS": "2"}, {"SMD_CHUNKS": "1"},
-            {"SMD_PDL": "0"}, {"SMD_PDL": "2"}, {"SMD_NO_FUSE": "1"})
+    envs = ({"SMD_PDL": "1"}, {"SMD_PDL": "0"}, {"SMD_PDL": "2"}, {"SMD_NO_FUSE": "1"})
     for env in envs:
         os.environ.update(env)
         try:
@@ -302,8 +301,7 @@ def test_fused_step_kernel_is_bit_identical_to_separate_kernels(orc, case):
     x1, _, v1, a1, u1, l1 = out[-1]                 # separate kernels
     for x, _, v, a, u, l in out[:-1]:
         assert np.array_equal(x, x1) and np.array_equal(v, v1) and np.array_equal(a, a1) and np.array_equal(u, u1)
-    assert out[0][5] < out[3][5] < l1               # launches: pair-epilogue seam < seam kernel < separate kernels
-    assert out[1][5] > out[2][5] > out[3][5]        # the step pipeline did cut the grids into 3 / 2 chunks
+    assert out[0][5] < l1                           # launches: one seam kernel < separate kernels
 
 
 @pytest.mark.parametrize("case", ["bondbend", "lipocyto_eq", "ball", "fields", "bead1", "bead2"])
@@ -379,71 +377,6 @@ def test_step_mc_equals_step_then_box_move(orc, case):
         assert np.abs(p0[0] - p1[0]).max() <= 1e-9 and np.abs(p0[0] - p2[0]).max() <= 1e-9 and rel_force_err(a1, a0) <= 1e-9
     if case != "fields":                 # (BEAD / NANOCORE-free systems take the fused step path, which smd_step_mc needs)
         assert n1 < n0                   # fewer launches: the dPotential kernel is gone
-
-
-def test_split_pair_kernels_are_bit_identical_to_the_one_kernel_engine(orc):
-    """SMD_PAIR_SPLIT=1 (k_pair_lists + k_pair_drain, global candidate lists) against k_pair_force2: forces, energies and
-    a short trajectory, bit for bit"""
-    import os
-    from softmold_b200 import workloads
-    m = workloads.bilayer(4000, 3.11, seed=5)
-    out = []
-    for env in ("0", "1"):
-        os.environ["SMD_PAIR_SPLIT"] = env
-        os.environ["SMD_XSUB"] = "1"      # the split engine sorts by cell only: same order, same sums
-        try:
-            ctx = sm.Context.from_dict(m)
-        finally:
-            del os.environ["SMD_PAIR_SPLIT"], os.environ["SMD_XSUB"]
-        ctx.compute_forces(step=2)
-        ctx.step(2, 40)
-        a = ctx.get_forces()
-        U = ctx.potential()
-        dU = ctx.dpotential([1.001, 1.001, 1.0 / 1.001 ** 2])
-        ctx.compute_forces(mask=1 << sm.TERM_PAIR)
-        out.append((ctx.get_particles()[0], a, ctx.get_forces(), U[sm.TERM_PAIR], dU[sm.TERM_PAIR]))
-        ctx.close()
-    for u, w in zip(*out):
-        assert np.array_equal(u, w)
-
-
-@pytest.mark.parametrize("workload", ["bilayer", "liposome", "gas", "gas_asym"])
-def test_tile_pair_engine_is_bit_identical_to_the_round1_engine(orc, workload):
-    """k_pair_tile (warp-cooperative 8-bit dp4a prefilter, bit-mask lists; smd_pair_tile.cuh) against k_pair_force2
-    (SMD_PAIR_ENGINE=0): the same pairs summed in the same order -- forces, the force + dPotential pass of smd_step_mc and
-    a trajectory with box moves, bit for bit.  The gases make every cell a boundary cell (periodic-image path) and, with
-    asymmetric tables, send every pair through the general routine."""
-    import os
-    from softmold_b200 import workloads
-    from test_gpu_edge import gas
-    if workload == "bilayer":
-        m = workloads.bilayer(4000, 3.11, seed=5)
-    elif workload == "liposome":
-        m = workloads.liposome(3000, 3.45, 2)
-    else:
-        m = gas(11, 6000, (17.0, 9.3, 13.1), n_types=4, symmetric=(workload == "gas"), chains=((300, 3),))
-    out = []
-    for env in ("0", "1"):
-        os.environ["SMD_PAIR_ENGINE"] = env
-        try:
-            ctx = sm.Context.from_dict(m)
-        finally:
-            del os.environ["SMD_PAIR_ENGINE"]
-        ctx.compute_forces(mask=1 << sm.TERM_PAIR)
-        a0 = ctx.get_forces()
-        ctx.compute_forces(step=2)
-        ctx.step(2, 20)
-        a = ctx.get_forces()
-        boxes = []
-        if workload != "gas_asym":
-            rng = np.random.default_rng(3)
-            for k in range(3):
-                boxes.append(ctx.step_mc(22 + 8 * k, 8, 0.01, 0.1, rng.random(), rng.random())[2])
-        x, _, v = ctx.get_particles()
-        out.append((a0, a, x, v, np.array(boxes)))
-        ctx.close()
-    for u, w in zip(*out):
-        assert np.array_equal(u, w)
 
 
 def test_x_sliced_sort_changes_nothing_but_the_summation_order(orc):
