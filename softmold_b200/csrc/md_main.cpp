@@ -107,9 +107,13 @@ struct Driver {
 	std::deque<Job> jobs;
 	bool quit = false, sync_io = false;
 
+	std::timed_mutex store_mu;   // held while a checkpoint is being written
 	void die(const char *what, int rc)
 	{
 		std::cerr << what << ": " << (ctx ? smd_last_error(ctx) : smd_last_error(nullptr)) << " (code " << rc << ")\n";
+		// a checkpoint the worker is writing right now describes a state from BEFORE this error: let it finish (the write
+		// itself is atomic, smd_mpd_write renames a finished sibling over the old file, so this only saves the newer state)
+		if (store_mu.try_lock_for(std::chrono::seconds(30))) store_mu.unlock();
 		std::_Exit(1);
 	}
 	void ck(int rc, const char *what) { if (rc) die(what, rc); }
@@ -184,6 +188,9 @@ struct Driver {
 	{
 		Job j = {};
 		j.kind = 0; j.write_mpd = write_mpd; j.time_now = time_now; j.temperature = temperature;
+		// device-side errors (a particle outside the box, NaN positions) only surface at a synchronisation: a state that
+		// has already raised one must not replace the last good checkpoint
+		if (write_mpd) ck(smd_synchronize(ctx), "state check before the checkpoint");
 		smd_get_box(ctx, j.box);
 		submit(j, false);
 	}
@@ -197,6 +204,7 @@ struct Driver {
 			smd_mpd_set_scalar(mpd, "initialTime", j.time_now);
 			smd_mpd_set_scalar(mpd, "initialTemp", j.temperature);
 			char err[512];
+			std::lock_guard<std::timed_mutex> hold(store_mu);
 			if (smd_mpd_write(mpd, name.c_str(), err, sizeof err)) { std::cerr << err << "\n"; std::_Exit(1); }
 		}
 		// xyzFormat::store (xyzFormat.h:111-143): default stream precision = %g; formatted in parallel chunks
@@ -442,7 +450,9 @@ int main(int argc, char *argv[])
 
 	// MD.cpp:186-262: forces of the loaded configuration (pair, thermostat, molecules)
 	D.time_now = initialTime;
-	D.ck(smd_compute_forces(ctx, SMD_MASK_ALL, startInt), "smd_compute_forces");
+	// (the noise of this evaluation is keyed startInt - 1: the first iteration of the loop below evaluates forces under the
+	// key startInt, and two evaluations must never share their random kicks -- the reference draws fresh numbers each time)
+	D.ck(smd_compute_forces(ctx, SMD_MASK_ALL, (int64_t)startInt - 1), "smd_compute_forces");
 	if (initialTime == 0) {
 		D.measure();
 		D.store(false);

@@ -21,6 +21,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 
 #include "../../include/softmold_b200.h"
 
@@ -433,13 +434,20 @@ extern "C" int smd_mpd_write(const smd_mpd *m, const char *name, char *err, size
 	if (!m || !name) return SMD_ERR_ARG;
 	std::string path = std::string(name) + ".mpd";
 	std::string text = serialize(*m);
-	FILE *f = fopen(path.c_str(), "wb");
+	// The checkpoint is the only restart file and is rewritten in place every storeInterval (MD.cpp:373-377), here from a
+	// worker thread while the run goes on: write a sibling, flush it to disk, then rename() over the old file, so that a
+	// process that dies mid-write leaves the last good checkpoint behind, never a truncated one.
+	std::string tmp = path + ".tmp";
+	FILE *f = fopen(tmp.c_str(), "wb");
 	if (!f) {
 		set_err(err, errlen, "Could not open " + path + " in Script class!");
 		return SMD_ERR_IO;
 	}
 	size_t w = fwrite(text.data(), 1, text.size(), f);
-	if (fclose(f) != 0 || w != text.size()) {
+	bool ok = w == text.size() && fflush(f) == 0 && fsync(fileno(f)) == 0;
+	ok = (fclose(f) == 0) && ok;
+	if (!ok || rename(tmp.c_str(), path.c_str()) != 0) {
+		remove(tmp.c_str());
 		set_err(err, errlen, "short write to " + path);
 		return SMD_ERR_IO;
 	}

@@ -140,8 +140,7 @@ extern "C" int smd_device_count(void)
 
 // x slices per reference cell in the sort key (Geom::xs).  The sliced order no longer lists a cell's particles by
 // descending original index, which is what the ORDERED look-up of an asymmetric constant table keys on (the reference's
-// "later-loaded particle first", cellOpt.h:572-585): asymmetric tables, the two-kernel engine and the TMA-staged variant
-// keep xs = 1.
+// "later-loaded particle first", cellOpt.h:572-585): asymmetric tables keep xs = 1.
 static void choose_xs(smd_ctx *ctx)
 {
 	Geom &g = ctx->geom;
@@ -1462,6 +1461,27 @@ extern "C" int smd_count_pairs(smd_ctx *ctx, int64_t *total, int32_t *per_partic
 }
 
 // ------------------------------------------------------------------------------------------------ box moves
+static int grow_cell_tables(smd_ctx *ctx, long long need)
+{
+	if (need > ctx->cellcap_limit) { ctx->err = "box grew beyond the cell-table limit of 64 Mi entries"; return SMD_ERR_UNSUPPORTED; }
+	const long long cap = std::min<long long>(need + need / 4, ctx->cellcap_limit);
+	CK(cudaStreamSynchronize(ctx->stream));
+	int *cnt = nullptr, *st = nullptr, *cu = nullptr;
+	if (cudaMalloc(&cnt, (cap + 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&st, (cap + 1) * sizeof(int)) != cudaSuccess ||
+	    cudaMalloc(&cu, (cap + 1) * sizeof(int)) != cudaSuccess) {
+		cudaFree(cnt); cudaFree(st); cudaFree(cu);
+		cudaGetLastError();
+		ctx->err = "out of device memory growing the cell tables";
+		return SMD_ERR_CUDA;
+	}
+	CK(cudaMemsetAsync(cnt, 0, (cap + 1) * sizeof(int), ctx->stream));   // the histogram is left zeroed by every build
+	cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
+	ctx->count = cnt; ctx->start = st; ctx->cursor = cu;
+	ctx->cellcap = cap;
+	ctx->cells_valid = false;
+	return SMD_OK;
+}
+
 extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3])
 {
 	if (!ctx) return SMD_ERR_ARG;
@@ -1469,12 +1489,19 @@ extern "C" int smd_rescale(smd_ctx *ctx, const double scale[3], const double new
 	REQUIRE(scale && new_box && ctx->particles_set, "bad call");
 	CK(cudaSetDevice(ctx->device));
 	Geom old = ctx->geom;
+	const PairGeo old_pg = ctx->pgeo;
 	set_geom(ctx, new_box);
 	int rc = check_geom(ctx);
 	long long total = (long long)ctx->geom.nc[0] * ctx->geom.nc[1] * ctx->geom.nc[2];
-	if (!rc && total > ctx->cellcap) { ctx->err = "box grew beyond the cell-table capacity"; rc = SMD_ERR_UNSUPPORTED; }
-	if (rc) { set_geom(ctx, old.box); return rc; }
-	if ((rc = upload_acut(ctx))) return rc;
+	// the grid outgrew the offset tables: CellOpt::resize reallocates (cellOpt.h:1525-1570), and so do we -- an accepted box
+	// move is rare enough for a synchronisation
+	if (!rc && total * std::max(2, ctx->geom.xs) > ctx->cellcap) rc = grow_cell_tables(ctx, total * std::max(2, ctx->geom.xs));
+	if (!rc) rc = upload_acut(ctx);
+	if (rc) {   // nothing has touched the particles yet: back to the old geometry on every error path
+		ctx->geom = old; ctx->pgeo = old_pg;
+		upload_acut(ctx);
+		return rc;
+	}
 	LAUNCH(k_rescale, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->pcur], scale[0], scale[1], scale[2]);
 	bool same_grid = old.nc[0] == ctx->geom.nc[0] && old.nc[1] == ctx->geom.nc[1] && old.nc[2] == ctx->geom.nc[2];
 	retag_cells(ctx, !same_grid);
@@ -1663,7 +1690,8 @@ extern "C" int smd_snapshot(smd_ctx *ctx, double *xyz, double *vel, double *unwr
 		for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&ctx->snap_done[k], cudaEventDisableTiming | cudaEventBlockingSync));
 	}
 	// the gather buffer is free again once the copies of the previous ticket have read it
-	if (ctx->snap_seq > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->snap_done[(ctx->snap_seq - 1) & 1], 0));
+	const long long seq = ctx->snap_seq.load();
+	if (seq > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->snap_done[(seq - 1) & 1], 0));
 	double *sx = ctx->snap_stage, *sv = sx + cap3, *su = sv + cap3;
 	if (xyz || vel)
 		LAUNCH(k_export_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->gid[ctx->cur], xyz ? sx : nullptr,
@@ -1675,8 +1703,9 @@ extern "C" int smd_snapshot(smd_ctx *ctx, double *xyz, double *vel, double *unwr
 	if (xyz) CK(cudaMemcpyAsync(xyz, sx, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
 	if (vel) CK(cudaMemcpyAsync(vel, sv, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
 	if (unwrapped) CK(cudaMemcpyAsync(unwrapped, su, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-	CK(cudaEventRecord(ctx->snap_done[ctx->snap_seq & 1], ctx->copy_stream));
-	*ticket = ctx->snap_seq++;
+	CK(cudaEventRecord(ctx->snap_done[seq & 1], ctx->copy_stream));
+	*ticket = seq;
+	ctx->snap_seq.store(seq + 1);
 	return SMD_OK;
 }
 
@@ -1684,7 +1713,8 @@ extern "C" int smd_snapshot_wait(smd_ctx *ctx, int64_t ticket)
 {
 	if (!ctx) return SMD_ERR_ARG;
 	// called from the writer thread while the owner keeps enqueueing work: touches nothing but the ticket's event
-	if (ticket < 0 || ticket >= ctx->snap_seq || ticket + 2 < ctx->snap_seq) return SMD_ERR_ARG;
+	const long long seq = ctx->snap_seq.load();
+	if (ticket < 0 || ticket >= seq || ticket + 2 < seq) return SMD_ERR_ARG;
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return SMD_ERR_CUDA;
 	return cudaEventSynchronize(ctx->snap_done[ticket & 1]) == cudaSuccess ? SMD_OK : SMD_ERR_CUDA;
 }

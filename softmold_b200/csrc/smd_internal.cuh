@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -222,7 +223,7 @@ struct smd_ctx {
 	double *snap_stage = nullptr;          // [9][cap]: xyz, vel, unwrapped in original order
 	cudaStream_t copy_stream = nullptr;
 	cudaEvent_t snap_gathered = nullptr, snap_done[2] = {nullptr, nullptr};
-	long long snap_seq = 0;
+	std::atomic<long long> snap_seq{0};   // (smd_snapshot_wait reads it from the writer thread)
 
 	// per-phase event timing (smd_profile)
 	struct ProfSpan { int phase; cudaEvent_t e0, e1; };

@@ -47,11 +47,21 @@ class _SlabBase:
         box = self.get_box()
         new_box, scale = capi.mc_propose(box, deltaLXY, u_fluct)
         terms = self.dpotential(scale)
-        accepted, dU = capi.mc_accept(float(terms.sum()), tension, box, new_box, self.temperature, u_accept)
+        accepted, dU = capi.mc_accept(self._mc_sum(terms), tension, box, new_box, self.temperature, u_accept)
         if accepted:
             self._each(lambda c: c.rescale(scale, new_box))
         return accepted, dU, (new_box if accepted else box)
 
+    @staticmethod
+    def _mc_sum(terms):
+        """the terms MD.cpp:642-669 adds into the Metropolis sum: doBallDPotential / doNanoCoreDPotential are evaluated there
+        but their results are dropped (the single-GPU trial, smd_mc_box_move, leaves them out the same way)"""
+        return float(sum(terms[t] for t in range(NTERMS) if t not in (capi.TERM_BALL, capi.TERM_NANOCORE)))
+
+    def set_temperature(self, T):
+        """temperature ramp (MD.cpp:366-371): the thermostat of every context and the acceptance test follow it"""
+        self.temperature = float(T)
+        self._each(lambda c: c.set_temperature(T))
 
     def step_mc(self, first_step, nsteps, deltaLXY, tension, u_fluct, u_accept):
         """step(first_step, nsteps) then mc_box_move(...): every rank arms the proposed scaling first, so that the pair kernel
@@ -60,7 +70,7 @@ class _SlabBase:
         new_box, scale = capi.mc_propose(box, deltaLXY, u_fluct)
         self.step(first_step, nsteps, arm_scale=scale)
         terms = self.dpotential(scale)
-        accepted, dU = capi.mc_accept(float(terms.sum()), tension, box, new_box, self.temperature, u_accept)
+        accepted, dU = capi.mc_accept(self._mc_sum(terms), tension, box, new_box, self.temperature, u_accept)
         if accepted:
             self._each(lambda c: c.rescale(scale, new_box))
         return accepted, dU, (new_box if accepted else box)
