@@ -293,5 +293,62 @@ def stats():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def bead24():
+    """24 continuum-sphere beads in ONE BEAD molecule around a vesicle: more than 20 beads switch doBeadForce to its
+    hash-cell branch (system.h:2105-2164), whose exclusion rule differs -- only the bead itself is skipped, so the beads
+    also meet each other through the bead-particle term (the <= 20 branch :2167-2185 skips every bead of the molecule)."""
+    tmp = tempfile.mkdtemp(prefix="golden_bead24_")
+    try:
+        run([os.path.join(REF, "continuumSphereAndLiposome"), "cs", "1234", "1200", "3.45", "3", "-6", "40", "5.88",
+             "0", "1", "0", "2.0"], tmp)
+        m = orc.read_mpd(os.path.join(tmp, "cs.mpd"))
+        b = int(m["molecules"][1]["bonds"][0, 0])
+        m["xyz"][b, 2] -= 2.2                                   # onto the outer leaflet, as for bead1
+        lip = np.arange(m["nParticles"]) != b
+        c = m["xyz"][lip].mean(0)
+        rng = np.random.default_rng(24)
+        extra = []
+        while len(extra) < 23:                                  # the same distance from the vesicle's centre, other directions
+            q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            x = c + q @ (m["xyz"][b] - c)
+            others = np.array([m["xyz"][b]] + extra)
+            d = np.linalg.norm(others - x, axis=1).min()
+            if d > 5.0 and (len(extra) % 3 != 2 or d < 7.5):   # never overlapping; every third one within bead-bead range (2R + 2 = 8)
+                extra.append(x)
+        extra = np.array(extra)
+        m2 = dict(m)
+        m2["xyz"] = np.vstack([m["xyz"], extra])
+        m2["vel"] = np.vstack([m["vel"], rng.normal(0, 0.1, (23, 3))])
+        m2["type"] = np.append(m["type"], np.full(23, m["type"][b])).astype(np.int32)
+        m2["nParticles"] = m["nParticles"] + 23
+        idx = np.array([[b]] + [[m["nParticles"] + k] for k in range(23)], np.int32)
+        m2["molecules"] = [m["molecules"][0], {"type": orc.BEAD, "constants": m["molecules"][1]["constants"], "bonds": idx}]
+        assert np.all(m2["xyz"] > 0) and np.all(m2["xyz"] < np.array(m2["size"]))
+        orc.write_mpd(os.path.join(tmp, "bead24.mpd"), m2)
+        g = harness(tmp, "bead24")
+        t, _ = traj(tmp, m2, "bead24_run", 8)
+        save("bead24", pack(m2, g, t))
+        print("bead molecule: |a| max", np.abs(g["a_mol1"]).max(), "U", g["U_mol"][1], "dU", g["dU_mol"][1])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def kat():
+    """SURVEY.md 8(c)'s known-answer system at BASELINE size C1: `liposome kat5000 5000 5000 3.45` (N = 15 000, t = 0), the
+    reference generator's own output and the reference's per-term quantities for the scaling (1.0005, 1.0005, 1.0005^-2)"""
+    tmp = tempfile.mkdtemp(prefix="golden_kat_")
+    try:
+        run([os.path.join(REF, "liposome"), "kat5000", "5000", "5000", "3.45"], tmp)
+        m = orc.read_mpd(os.path.join(tmp, "kat5000.mpd"))
+        g = harness(tmp, "kat5000", (1.0005, 1.0005, 1.0 / 1.0005 ** 2))
+        t, _ = traj(tmp, m, "kat_run", 16)   # + 16 steps of the reference `MD` binary at this size
+        save("kat5000", pack(m, g, t))
+        a = g["a_pair"].reshape(-1, 3)
+        print("U_pair %.15e  dU_pair %.15e  dU_chain %.15e" % (g["U_pair"][0], g["dU_pair"][0], g["dU_mol"][0]))
+        print("a_pair[0]", ["%.15e" % v for v in a[0]], "sum|F|^2 %.15e max|F| %.15e" % ((a * a).sum(), np.sqrt((a * a).sum(1)).max()))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
-    {"stats": stats, "ball": ball, "fields": fields}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()
+    {"stats": stats, "ball": ball, "fields": fields, "kat": kat, "bead24": bead24}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()

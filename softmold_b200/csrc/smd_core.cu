@@ -941,7 +941,7 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 			if (b.nOwn <= 0) continue;
 			LAUNCHP(k_beadbead<0>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius,
 			       ctx->acc, nullptr, 1.0, 1.0, 1.0);
-			LAUNCHP(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
+			LAUNCHP(k_bead<0>, b.nOwn, TPB, 0, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
 			       b.d_beads, b.d_C, b.nOwn <= 20 ? 1 : 0, 0, ctx->acc, nullptr, 1.0, 1.0, 1.0);
 		}
 	if (mask & SMD_MASK(SMD_TERM_FIELD))
@@ -952,7 +952,7 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 	if (mask & SMD_MASK(SMD_TERM_NANOCORE))
 		for (auto &f : ctx->fields)
 			if (f.kind == SMD_MOL_NANOCORE && f.n > 0)
-				LAUNCHP(k_bead<0>, nblk(ctx->N, TPB), TPB, 0, ctx->N, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT,
+				LAUNCHP(k_bead<0>, f.n, TPB, 0, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
 				       f.d_idx, f.d_C, 0, 1, ctx->acc, nullptr, 1.0, 1.0, 1.0);
 	return SMD_OK;
 }
@@ -1382,18 +1382,16 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 		LAUNCH(k_beadbead<MODE>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius, nullptr,
 		       ctx->partials, sx, sy, sz);
 		finish_sum(ctx, 1, push(SMD_TERM_BEAD), 1.0);
-		int nb = nblk(N, TPB);
-		LAUNCH(k_bead<MODE>, nb, TPB, 0, N, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, 0, 0,
+		LAUNCH(k_bead<MODE>, b.nOwn, TPB, 0, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, b.d_beads, b.d_C, 0, 0,
 		       nullptr, ctx->partials, sx, sy, sz);
-		finish_sum(ctx, nb, push(SMD_TERM_BEAD), 1.0);
+		finish_sum(ctx, b.nOwn, push(SMD_TERM_BEAD), 1.0);
 	}
 	for (auto &f : ctx->fields) {
 		if (f.kind == SMD_MOL_NANOCORE) {
 			if (f.n <= 0) continue;
-			int nb = nblk(N, TPB);
-			LAUNCH(k_bead<MODE>, nb, TPB, 0, N, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, ctx->nT, f.d_idx, f.d_C, 0, 1,
+			LAUNCH(k_bead<MODE>, f.n, TPB, 0, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, f.d_idx, f.d_C, 0, 1,
 			       nullptr, ctx->partials, sx, sy, sz);
-			finish_sum(ctx, nb, push(SMD_TERM_NANOCORE), 1.0);
+			finish_sum(ctx, f.n, push(SMD_TERM_NANOCORE), 1.0);
 		} else if (MODE == 1) {   // the one-body fields have no dPotential (MD.cpp:642-669)
 			int frc = launch_field<1>(ctx, f, pos, [&](int nb, int term) { finish_sum(ctx, nb, push(term), 1.0); });
 			if (frc) return frc;

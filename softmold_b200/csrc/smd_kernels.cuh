@@ -2220,67 +2220,117 @@ __global__ void __launch_bounds__(TPB) k_beadbead(int nOwn, int nAll, int cap, c
 	}
 }
 
-// bead - particle terms: one thread per particle, loop over the molecule's own beads (system.h:2165-2210 brute-force
-// branch; the hash-cell branch :2105-2164 visits the same pairs).  excl_all: the force excludes every own bead when
-// nOwn <= 20 and only the bead itself otherwise; potential / dPotential always exclude only the bead itself (Q7).
+// bead - particle terms THROUGH THE CELL GRID: one block per bead; only the particles in the cells within R + rc of the
+// bead are visited (the reference's brute-force branch system.h:2165-2210 tests every particle against the same cutoff, its
+// hash-cell branch :2105-2164 -- more than 20 beads -- walks cells of 2 (R + rc); all three visit the same pairs).  The
+// cube of cells around the bead is cut into (y,z) rows, a row into at most two x segments (periodic wrap), a segment is
+// one contiguous slot range of the cell-sorted order, clipped to the occupied window (cells outside it are empty).
+// excl_all: the force excludes every own bead when nOwn <= 20 and only the bead itself otherwise; potential / dPotential
+// always exclude only the bead itself (Q7).
 // nano: NANOCORE molecules (doNanoCoreForce system.h:2215-2332, doNanoCorePotential :3028-3075, doNanoCoreDPotential
 // :3708-3760) are the same term with ONE constants row per bead (C + 22 j, cutoff from that row) whatever the particle's
 // type, only the bead itself excluded, and no bead-bead term.
+// Force on a particle: one FP64 atomic per component (several beads may touch it); reaction on the bead: summed in
+// registers over the whole cube, one block reduction and one atomic per bead.
+constexpr int BEAD_SEGS = 1024;
 template <int MODE>
-__global__ void __launch_bounds__(TPB) k_bead(int N, int nOwn, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
-                                              const int *__restrict__ slot_of, Geom g, int nT, const int *__restrict__ beads,
-                                              const double *__restrict__ C, int excl_all, int nano, double *acc, double *partials,
-                                              double sx, double sy, double sz)
+__global__ void __launch_bounds__(TPB) k_bead(int nOwn, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
+                                              const int *__restrict__ slot_of, const int *__restrict__ start, const int *__restrict__ win,
+                                              Geom g, int nT, const int *__restrict__ beads, const double *__restrict__ C, int excl_all,
+                                              int nano, double *acc, double *partials, double sx, double sy, double sz)
 {
 	pdl_prologue();
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	bool live = s < N;
-	Particle p;
-	int id = -1;
-	if (live) { p = load_particle(pos + s); id = gid[s]; }
-	double cut2 = C[0] * C[0];   // (R + rc)^2 from row 0, system.h:2100-2101
-	double usum = 0;
-	double ax = 0, ay = 0, az = 0;
-	bool own = false;
-	if (live && excl_all)
-		for (int e = 0; e < nOwn; e++) own |= (beads[e] == id);
-	for (int j = 0; j < nOwn; j++) {
-		int bs = slot_of[beads[j]];
-		Particle pb = load_particle(pos + bs);
-		double fx = 0, fy = 0, fz = 0;
-		bool hit = false;
-		if (live && bs != s && !own) {
-			V3 d = diff_mi(pb, p, g);
-			double dr2 = d.x * d.x + d.y * d.y + d.z * d.z;
-			const double *Cr = nano ? C + 22 * j : C + 22 * (pb.type * nT + p.type);
-			if (nano) cut2 = Cr[0] * Cr[0];
-			if (MODE == 0) {
-				double m = bead_mag(dr2, Cr, cut2);
-				if (m != 0) {
-					fx = d.x * m; fy = d.y * m; fz = d.z * m;
-					ax -= fx; ay -= fy; az -= fz;
-					hit = true;
+	__shared__ int seg_b[BEAD_SEGS], seg_e[BEAD_SEGS];
+	const int j = blockIdx.x;
+	const int bs = slot_of[beads[j]];
+	const Particle pb = load_particle(pos + bs);
+	const double cutR = nano ? C[22 * j] : C[0];   // R + rc (BEAD: row 0, system.h:2100-2101; NANOCORE: the bead's own row)
+	const double cut2 = cutR * cutR;
+	// MODE 2: a pair outside the cutoff may be inside it after the proposed scaling and then still has a term
+	const double reach = MODE == 2 ? cutR * fmax(1.0, 1.0 / fmin(sx, fmin(sy, sz))) * (1.0 + 1e-9) : cutR;
+	const double reach2 = reach * reach;
+	int c[3];
+	{ int cx, cy, cz; unpack_cell(pb.cell, cx, cy, cz); c[0] = cx; c[1] = cy; c[2] = cz; }
+	// cell layers around the bead's cell that can hold a particle within the cutoff, and cells per axis to visit
+	int k[3], cnt[3];
+	for (int d = 0; d < 3; d++) {
+		k[d] = (int)(reach / g.cs[d]) + 1;
+		cnt[d] = min(2 * k[d] + 1, g.nc[d]);   // a cube wider than the box: every cell once
+	}
+	const int w[3] = {win[WIN_ORG], win[WIN_ORG + 1], win[WIN_ORG + 2]};
+	const int dm[3] = {win[WIN_DIM], win[WIN_DIM + 1], win[WIN_DIM + 2]};
+	const int fd0 = win[WIN_FD0], xs = g.xs;
+	auto axis_cell = [&](int d, int i) {   // i-th visited cell along axis d
+		if (cnt[d] == g.nc[d]) return i;
+		int v = c[d] - k[d] + i;
+		if (v < 0) v += g.nc[d];
+		if (v >= g.nc[d]) v -= g.nc[d];
+		return v;
+	};
+	double usum = 0, rx = 0, ry = 0, rz = 0;
+	const int nrows = cnt[1] * cnt[2];
+	for (int r0 = 0; r0 < nrows; r0 += BEAD_SEGS / 2) {
+		// ---- the slot ranges of up to BEAD_SEGS / 2 rows, two x segments each
+		__syncthreads();
+		for (int q = threadIdx.x; q < BEAD_SEGS / 2; q += blockDim.x) {
+			int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
+			const int r = r0 + q;
+			if (r < nrows) {
+				const int ly = axis_cell(1, r % cnt[1]) - w[1], lz = axis_cell(2, r / cnt[1]) - w[2];
+				if (ly >= 0 && ly < dm[1] && lz >= 0 && lz < dm[2]) {
+					const int rowbase = fd0 * (ly + dm[1] * lz);
+					auto range = [&](int xlo, int xhi, int &b, int &e) {   // cells xlo .. xhi (no wrap inside), clipped to the window
+						xlo = max(xlo - w[0], 0); xhi = min(xhi - w[0], dm[0] - 1);
+						if (xlo <= xhi) { b = start[rowbase + xlo * xs]; e = start[rowbase + (xhi + 1) * xs]; }
+					};
+					if (cnt[0] == g.nc[0]) range(0, g.nc[0] - 1, b0, e0);
+					else {
+						const int lo = c[0] - k[0], hi = c[0] + k[0];
+						if (lo < 0) { range(lo + g.nc[0], g.nc[0] - 1, b0, e0); range(0, hi, b1, e1); }
+						else if (hi >= g.nc[0]) { range(lo, g.nc[0] - 1, b0, e0); range(0, hi - g.nc[0], b1, e1); }
+						else range(lo, hi, b0, e0);
+					}
 				}
-			} else if (MODE == 1) {
-				usum += bead_pot(dr2, Cr, cut2);
-			} else {
-				double uo = bead_pot(dr2, Cr, cut2);
-				V3 e = scaled(d, sx, sy, sz);
-				usum += (uo - bead_pot(e.x * e.x + e.y * e.y + e.z * e.z, Cr, cut2));
 			}
+			seg_b[2 * q] = b0; seg_e[2 * q] = e0; seg_b[2 * q + 1] = b1; seg_e[2 * q + 1] = e1;
 		}
-		if (MODE == 0) {
-			// reaction on the bead: reduce over the block only when somebody touched it
-			if (__syncthreads_or(hit)) {
-				double rx = block_sum(fx), ry = block_sum(fy), rz = block_sum(fz);
-				if (threadIdx.x == 0) { atomicAdd(acc + bs, rx); atomicAdd(acc + cap + bs, ry); atomicAdd(acc + 2 * cap + bs, rz); }
+		__syncthreads();
+		// ---- the particles of those ranges
+		for (int sgm = 0; sgm < BEAD_SEGS; sgm++) {
+			const int e = seg_e[sgm];
+			for (int s = seg_b[sgm] + threadIdx.x; s < e; s += blockDim.x) {
+				if (s == bs) continue;
+				const Particle p = load_particle(pos + s);
+				if (excl_all) {
+					const int id = gid[s] & GID_MASK;
+					bool own = false;
+					for (int q = 0; q < nOwn; q++) own |= (beads[q] == id);
+					if (own) continue;
+				}
+				V3 d = diff_mi(pb, p, g);
+				const double dr2 = d.x * d.x + d.y * d.y + d.z * d.z;
+				if (!(dr2 < reach2)) continue;
+				const double *Cr = nano ? C + 22 * j : C + 22 * (pb.type * nT + p.type);
+				if (MODE == 0) {
+					const double m = bead_mag(dr2, Cr, cut2);
+					if (m != 0) {
+						const double fx = d.x * m, fy = d.y * m, fz = d.z * m;
+						atomicAdd(acc + s, -fx); atomicAdd(acc + cap + s, -fy); atomicAdd(acc + 2 * cap + s, -fz);
+						rx += fx; ry += fy; rz += fz;
+					}
+				} else if (MODE == 1) {
+					usum += bead_pot(dr2, Cr, cut2);
+				} else {
+					const double uo = bead_pot(dr2, Cr, cut2);
+					V3 e2 = scaled(d, sx, sy, sz);
+					usum += (uo - bead_pot(e2.x * e2.x + e2.y * e2.y + e2.z * e2.z, Cr, cut2));
+				}
 			}
 		}
 	}
 	if (MODE == 0) {
-		if (live && (ax != 0 || ay != 0 || az != 0)) {
-			atomicAdd(acc + s, ax); atomicAdd(acc + cap + s, ay); atomicAdd(acc + 2 * cap + s, az);
-		}
+		rx = block_sum(rx); ry = block_sum(ry); rz = block_sum(rz);
+		if (threadIdx.x == 0 && (rx != 0 || ry != 0 || rz != 0)) { atomicAdd(acc + bs, rx); atomicAdd(acc + cap + bs, ry); atomicAdd(acc + 2 * cap + bs, rz); }
 	} else {
 		usum = block_sum(usum);
 		if (threadIdx.x == 0) partials[blockIdx.x] = usum;

@@ -175,3 +175,59 @@ def test_full_size_properties():
     xyz, _, _ = ctx.get_particles()
     assert (xyz >= 0).all() and (xyz <= np.array(m["size"])).all()
     ctx.close()
+
+
+def test_hundred_beads_through_the_cell_grid(orc):
+    """A vesicle studded with 100 continuum-sphere beads in one BEAD molecule plus 30 in a second one (bead lists assembled
+    from molecules j >= i, system.h:2053-2070), in a box small enough that bead cubes wrap around it: k_bead visits only the
+    cells within R + rc of each bead.  Forces, energies, dPotential and a short trajectory against the oracle, whose > 20
+    bead rule is pinned to the reference by tests/golden/bead24.npz."""
+    from conftest import golden_path
+    m, _ = orc.load_golden(golden_path("bead1"))
+    b = int(m["molecules"][1]["bonds"][0, 0])
+    lip = np.arange(m["nParticles"]) != b
+    c = m["xyz"][lip].mean(0)
+    rng = np.random.default_rng(100)
+    extra = []
+    for _ in range(100000):     # (bounded: 129 spheres 3.6 apart fit between 0.97 and 1.5 vesicle radii in ~1 300 draws)
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        x = c + (q @ (m["xyz"][b] - c)) * rng.uniform(0.97, 1.5)
+        if np.linalg.norm(np.array([m["xyz"][b]] + extra) - x, axis=1).min() > 3.6 and np.all(x > 1) and np.all(x < np.array(m["size"]) - 1):
+            extra.append(x)
+        if len(extra) == 129:
+            break
+    assert len(extra) == 129
+    n0 = m["nParticles"]
+    m = dict(m, xyz=np.vstack([m["xyz"], extra]), vel=np.vstack([m["vel"], rng.normal(0, 0.1, (129, 3))]),
+             type=np.append(m["type"], np.full(129, m["type"][b])).astype(np.int32), nParticles=n0 + 129)
+    own1 = np.array([[b]] + [[n0 + k] for k in range(99)], np.int32)
+    own2 = np.array([[n0 + k] for k in range(99, 129)], np.int32)
+    C = m["molecules"][1]["constants"]
+    m["molecules"] = [m["molecules"][0], {"type": sm.MOL_BEAD, "constants": C, "bonds": own1},
+                      {"type": sm.MOL_BEAD, "constants": C, "bonds": own2}]
+    m["nMolecules"] = 3
+    # shrink the box around the vesicle so that the cubes of cells around outer beads wrap across the periodic faces
+    lo, hi = m["xyz"].min(0) - 1.5, m["xyz"].max(0) + 1.5
+    m["xyz"] = m["xyz"] - lo
+    m["size"] = [float(v) for v in (hi - lo)]
+    ctx = sm.Context.from_dict(m)
+    S = orc.System(m, noise="philox")
+    S.init(7)
+    ctx.compute_forces(mask=sm.MASK_ALL, step=7)
+    a = ctx.get_forces()
+    assert np.abs(a - S.acc).max() <= 1e-11 * np.abs(S.acc).max()
+    ctx.compute_forces(mask=1 << sm.TERM_BEAD)
+    ab = ctx.get_forces()
+    assert np.abs(ab).max() > 10.0                     # the beads really press on the membrane and on each other
+    U, Uo = ctx.potential(), S.potential()
+    assert abs(U.sum() - Uo) <= 1e-11 * abs(Uo) and U[sm.TERM_BEAD] != 0.0
+    scale = (0.9991, 0.9991, 1.0 / 0.9991 ** 2)
+    dU, dUo = ctx.dpotential(scale), S.dpotential(scale)
+    assert abs(dU.sum() - dUo) <= 1e-11 * abs(Uo)
+    ctx.compute_forces(mask=sm.MASK_ALL, step=7)       # (a[] held the bead term alone)
+    ctx.step(7, 6)
+    for i in range(6):
+        S.step(7 + i)
+    xyz, _, vel = ctx.get_particles()
+    assert np.abs(xyz - S.xyz).max() <= 1e-9 and np.abs(vel - S.vel).max() <= 1e-7
+    ctx.close()

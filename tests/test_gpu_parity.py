@@ -94,6 +94,24 @@ def test_pair_force_potential_dpotential(contexts, case):
     assert close_energy(ctx.kinetic(), ref["kinetic"][0]) <= 1e-13
 
 
+def test_known_answers_of_the_survey_at_baseline_size_c1(orc):
+    """SURVEY.md 8(c)'s KAT table (`liposome kat5000 5000 5000 3.45`, N = 15 000 = BASELINE config C1 at full size), FP64"""
+    from conftest import KAT5000 as K
+    m, _ = orc.load_golden(golden_path("kat5000"))
+    ctx = sm.Context.from_dict(m)
+    ctx.compute_forces(mask=1 << sm.TERM_PAIR)
+    a = ctx.get_forces()
+    assert np.abs(a[0] - np.array(K["a_pair0"])).max() <= 1e-12 * K["maxF"]
+    assert abs((a * a).sum() - K["sumF2"]) <= 1e-12 * K["sumF2"]
+    assert abs(np.sqrt((a * a).sum(1)).max() - K["maxF"]) <= 1e-12 * K["maxF"]
+    U = ctx.potential()
+    assert abs(U[sm.TERM_PAIR] - K["U_pair"]) <= 1e-12 * abs(K["U_pair"])
+    dU = ctx.dpotential(K["scale"])
+    assert abs(dU[sm.TERM_PAIR] - K["dU_pair"]) <= 1e-12 * abs(K["U_pair"])
+    assert abs(dU[sm.TERM_CHAIN] - K["dU_chain"]) <= 1e-9 * abs(K["dU_chain"])
+    ctx.close()
+
+
 TERM_OF = {sm.MOL_CHAIN: sm.TERM_CHAIN, sm.MOL_BOND: sm.TERM_BOND, sm.MOL_BEND: sm.TERM_BEND, sm.MOL_BEAD: sm.TERM_BEAD,
            sm.MOL_BALL: sm.TERM_BALL, sm.MOL_BOUNDARY: sm.TERM_FIELD, sm.MOL_FLOATING_BASE: sm.TERM_FIELD,
            sm.MOL_ZTORQUE: sm.TERM_FIELD, sm.MOL_ZPOWERPOTENTIAL: sm.TERM_FIELD, sm.MOL_NANOCORE: sm.TERM_NANOCORE}
@@ -159,7 +177,7 @@ def test_philox_uniforms_bit_exact(orc):
     assert abs(u.mean() - 0.5) < 2e-3 and abs(u.var() - 1 / 12) < 1e-3 and u.min() >= 0 and u.max() < 1
 
 
-@pytest.mark.parametrize("case", ["lipo_t0", "lipo_eq", "bilayer_t0", "bilayer_eq", "bead1", "bead2", "ball", "fields"])
+@pytest.mark.parametrize("case", ["lipo_t0", "lipo_eq", "bilayer_t0", "bilayer_eq", "bead1", "bead2", "bead24", "ball", "fields", "kat5000"])
 def test_trajectory_matches_reference_md(contexts, orc, case):
     """The whole loop of MD.cpp for K steps against the state the reference `MD` executable wrote (one thread):
     Langevin noise = the reference's MT19937 stream fed through smd_set_noise, MC box moves with tension driven by
