@@ -259,6 +259,10 @@ enum { SMD_PHASE_INTEGRATE1 = 0,  /* bead mass, Verlet::first (+ cell tagging), 
        SMD_PHASE_FUSED = 8,       /* CHAIN-only systems: chain forces + Verlet::second + next Verlet::first in one
                                      kernel (then phases 0, 3, 5 only count the first / last step of a batch) */
        SMD_PHASE_PAIR_DU = 9,     /* the pair kernel of a step that also sums the dPotential of the box move (smd_step_mc) */
+       SMD_PHASE_BUILD_HIST = 10, /* the kernels of the cell build one by one (inside SMD_PHASE_BUILD): histogram,        */
+       SMD_PHASE_BUILD_SCAN = 11, /*   exclusive scan of the offset table,                                                */
+       SMD_PHASE_BUILD_PLACE = 12,/*   claim of a position inside the cell's range,                                       */
+       SMD_PHASE_BUILD_REORDER = 13, /* rank inside the cell (descending index) + move of the records                     */
        SMD_NPHASES = 16 };
 int smd_profile(smd_ctx *ctx, uint32_t phase_mask);
 int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPHASES]);

@@ -438,7 +438,8 @@ class Context:
         return a.value, b.value
 
 
-PHASES = ["integrate1", "build", "pair", "molecules", "langevin", "integrate2", "step", "exchange", "fused", "pair_du"]
+PHASES = ["integrate1", "build", "pair", "molecules", "langevin", "integrate2", "step", "exchange", "fused", "pair_du",
+          "build_hist", "build_scan", "build_place", "build_reorder"]
 
 
 class Mpd:

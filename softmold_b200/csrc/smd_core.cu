@@ -187,6 +187,7 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
 static int pair_force_smem(smd_ctx *ctx, bool du = false);
+static int drop_pending_histogram(smd_ctx *ctx);
 
 static int upload_acut(smd_ctx *ctx)
 {
@@ -270,6 +271,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_ENERGY_ONEPHASE"); ctx->force_onephase_energy = e && *e == '1'; }
 	// SMD_NO_FUSE=1: every phase of the step in its own kernel (A/B and bit-identity tests).
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
+	{ const char *e = getenv("SMD_NO_PREBIN"); ctx->prebin = !(e && *e == '1'); }
 	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }
 	// SMD_PDL=0: plain stream order everywhere; 1: only the step seam is a programmatic dependent (of the pair kernel);
@@ -311,8 +313,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMalloc(&ctx->arad, (size_t)ctx->nT * sizeof(float)));
 	CKC(cudaMalloc(&ctx->ptab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
 	CKC(cudaMalloc(&ctx->utab, (size_t)PTAB_STRIDE * ctx->nT * ctx->nT * sizeof(double)));
-	CKC(cudaMalloc(&ctx->win, WIN_WORDS * sizeof(int)));
-	CKC(cudaMemset(ctx->win, 0, WIN_WORDS * sizeof(int)));
+	CKC(cudaMalloc(&ctx->win, 2 * WIN_WORDS * sizeof(int)));
+	CKC(cudaMemset(ctx->win, 0, 2 * WIN_WORDS * sizeof(int)));
 	CKC(cudaMalloc(&ctx->acc, 3 * cap * sizeof(double)));
 	CKC(cudaMemset(ctx->acc, 0, 3 * cap * sizeof(double)));
 	CKC(cudaMalloc(&ctx->acc2, 3 * cap * sizeof(double)));
@@ -341,7 +343,10 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	CKC(cudaMemset(ctx->count, 0, (ctx->cellcap + 1) * sizeof(int)));
 	CKC(cudaMalloc(&ctx->start, (ctx->cellcap + 1) * sizeof(int)));
 	CKC(cudaMalloc(&ctx->cursor, (ctx->cellcap + 1) * sizeof(int)));
-	CKC(cudaMalloc(&ctx->blockSums, SCAN_BLOCKS * sizeof(int)));
+	CKC(cudaMalloc(&ctx->scan_state, (size_t)(2 * SCAN_BLOCKS) * sizeof(unsigned long long)));
+	CKC(cudaMemset(ctx->scan_state, 0, (size_t)(2 * SCAN_BLOCKS) * sizeof(unsigned long long)));
+	CKC(cudaMalloc(&ctx->scan_barrier, 2 * sizeof(unsigned)));   // [0] grid barrier of the fallback, [1] arrival tickets
+	CKC(cudaMemset(ctx->scan_barrier, 0, 2 * sizeof(unsigned)));
 	CKC(cudaMalloc(&ctx->cellOfSlot, cap * sizeof(int)));
 	CKC(cudaMalloc(&ctx->order, cap * sizeof(int2)));
 	CKC(cudaMalloc(&ctx->bbox, 6 * sizeof(int)));
@@ -401,7 +406,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	}
 	cudaFree(ctx->pos32); cudaFree(ctx->pos16); cudaFree(ctx->arad); cudaFree(ctx->acut); cudaFree(ctx->ptab); cudaFree(ctx->utab);
 	cudaFree(ctx->win); cudaFree(ctx->acc); cudaFree(ctx->acc2); cudaFree(ctx->slot_of); cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
-	cudaFree(ctx->blockSums); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
+	cudaFree(ctx->scan_state); cudaFree(ctx->scan_barrier); cudaFree(ctx->cellOfSlot); cudaFree(ctx->order); cudaFree(ctx->bbox); cudaFree(ctx->errflag);
 	cudaFree(ctx->fC); cudaFree(ctx->uC); cudaFree(ctx->noise); cudaFree(ctx->partials); cudaFree(ctx->scalars);
 	cudaFree(ctx->icount); cudaFree(ctx->stage); cudaFree(ctx->istage);
 	cudaFreeHost(ctx->h_pinned);
@@ -461,6 +466,7 @@ extern "C" int smd_set_pair_tables(smd_ctx *ctx, const double *fC, const double 
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(fC && uC, "null table");
 	CK(cudaSetDevice(ctx->device));
+	{ int rcd = drop_pending_histogram(ctx); if (rcd) return rcd; }   // (the sort key may change with the tables: choose_xs)
 	size_t bytes = 6 * (size_t)ctx->nT * ctx->nT * sizeof(double);
 	CK(cudaMemcpyAsync(ctx->fC, fC, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->uC, uC, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -544,6 +550,8 @@ static int retag_cells(smd_ctx *ctx, bool rearm = true)
 {
 	// rearm = false: the cell grid is the same and the particles barely moved (accepted box move): keep the extremes,
 	// so that the tagging pass issues almost no atomics (thousands of warps hitting one address cost ~40 us)
+	int rcd = drop_pending_histogram(ctx);
+	if (rcd) return rcd;
 	if (rearm) LAUNCH(k_arm_bbox, 1, 32, 0, ctx->bbox);
 	LAUNCH(k_tag_cells, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->pos[ctx->pcur], ctx->geom, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur]);
 	ctx->cells_valid = false;
@@ -870,6 +878,32 @@ extern "C" int smd_set_noise(smd_ctx *ctx, const double *u)
 }
 
 // ------------------------------------------------------------------------------------------------ cell build
+// the window the CURRENT sorted order / start[] refer to, and the one the next tagging pass bins into
+static inline int *cur_win(smd_ctx *ctx) { return ctx->win + ctx->wcur * WIN_WORDS; }
+static inline int *next_win(smd_ctx *ctx) { return ctx->win + (ctx->wcur ^ 1) * WIN_WORDS; }
+
+// what a kernel that moves the particles needs to fill the histogram of the following build itself (bin_particle); not
+// in slab mode (received particles arrive after the pass) and not before a build has published the next window.
+// The caller is about to launch such a pass: the histogram is pending from here on.
+static BinArgs bin_args(smd_ctx *ctx)
+{
+	BinArgs b = {nullptr, nullptr, nullptr};
+	if (ctx->hist_pending) drop_pending_histogram(ctx);   // a second pass without a build in between: that histogram is stale
+	if (!ctx->prebin || ctx->slab || !ctx->next_win_valid || !ctx->cells_valid) return b;
+	b.win = next_win(ctx); b.count = ctx->count; b.cellOfSlot = ctx->cellOfSlot;
+	ctx->hist_pending = true;
+	return b;
+}
+
+// the particles are about to be replaced / rescaled / re-tagged by a pass that does not bin: drop a pending histogram
+static int drop_pending_histogram(smd_ctx *ctx)
+{
+	if (ctx->hist_pending) LAUNCH(k_clear_count, 296, 256, 0, next_win(ctx), ctx->count);
+	ctx->hist_pending = false;
+	ctx->next_win_valid = false;
+	return SMD_OK;
+}
+
 static int build_cells(smd_ctx *ctx)
 {
 	int N = ctx->N, cur = ctx->cur, nxt = cur ^ 1, pcur = ctx->pcur, pnxt = pcur ^ 1;
@@ -877,16 +911,32 @@ static int build_cells(smd_ctx *ctx)
 	if (ctx->slab && !ctx->ext_valid)   // no unpack since the last build: the extended count is the current one
 		CK(cudaMemcpyAsync(ctx->dN + 1, ctx->dN, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
 	ctx->ext_valid = false;
-	LAUNCHP(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag,
-	       ctx->gid[cur], ctx->slab ? ctx->slot_of : nullptr);
-	LAUNCHP(k_scan1, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->blockSums);
-	LAUNCHP(k_scan3, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, ctx->win, ctx->blockSums, ctx->start, ctx->cursor, N,
-	       ctx->slab ? ctx->dN : nullptr, ctx->errflag);
-	LAUNCHP(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order, ctx->gid[cur]);
-	LAUNCHP(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
-	       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
-	       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0, ctx->pos16, ctx->arad, ctx->win,
-	       ctx->geom);
+	const bool prebinned = ctx->hist_pending;   // the kernel that moved the particles has filled the histogram (bin_particle)
+	ctx->hist_pending = false;
+	if (prebinned) ctx->wcur ^= 1;              // ... under the window the last build published for it: this build's window
+	else {
+		ProfScope ps(ctx, SMD_PHASE_BUILD_HIST);
+		LAUNCHP(k_bin, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->pos[pcur], ctx->geom, ctx->bbox, ctx->cellcap, ctx->count, ctx->cellOfSlot, ctx->errflag,
+		       ctx->gid[cur], ctx->slab ? ctx->slot_of : nullptr);
+	}
+	{
+		ProfScope ps(ctx, SMD_PHASE_BUILD_SCAN);
+		LAUNCHP(k_scan, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, cur_win(ctx), ctx->slab ? (int *)nullptr : next_win(ctx),
+		       prebinned ? 1 : 0, ctx->start, ctx->cursor, N, ctx->slab ? ctx->dN : nullptr, ctx->errflag, ctx->scan_state, (unsigned)(ctx->rebuilds + 1),
+		       (const Particle *)ctx->pos[pcur], ctx->cellOfSlot, ctx->scan_barrier);
+		ctx->next_win_valid = !ctx->slab;
+	}
+	{
+		ProfScope ps(ctx, SMD_PHASE_BUILD_PLACE);
+		LAUNCHP(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order, ctx->gid[cur]);
+	}
+	{
+		ProfScope ps(ctx, SMD_PHASE_BUILD_REORDER);
+		LAUNCHP(k_reorder, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->order, ctx->cellOfSlot, ctx->start, ctx->pos[pcur], ctx->pos[pnxt],
+		       ctx->vel[cur], ctx->vel[nxt], ctx->unw[cur], ctx->unw[nxt], ctx->acc_live ? ctx->acc : nullptr, ctx->acc2, ctx->gid[cur],
+		       ctx->gid[nxt], ctx->slot_of, ctx->pos32, ctx->acut, ctx->bbox, (ctx->rebuilds & 255) == 255 ? 1 : 0, ctx->pos16, ctx->arad, cur_win(ctx),
+		       ctx->geom);
+	}
 	if (ctx->acc_live) std::swap(ctx->acc, ctx->acc2);   // a build in between force evaluation and the next kick keeps acc aligned
 	ctx->cur = nxt;
 	ctx->pcur = pnxt;
@@ -895,8 +945,6 @@ static int build_cells(smd_ctx *ctx)
 	return SMD_OK;
 }
 
-// the window the CURRENT sorted order / start[] refer to
-static inline int *cur_win(smd_ctx *ctx) { return ctx->win; }
 
 extern "C" int smd_build_cells(smd_ctx *ctx)
 {
@@ -1140,7 +1188,7 @@ extern "C" int smd_step_begin(smd_ctx *ctx, int64_t step)
 	ProfScope ps(ctx, SMD_PHASE_INTEGRATE1);
 	bead_mass_divide(ctx);                                                         // MD.cpp:340-355
 	LAUNCH(k_verlet_first, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->geom,
-	       ctx->desc.dt, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur]);             // MD.cpp:356
+	       ctx->desc.dt, ctx->bbox, ctx->errflag, ctx->gid[ctx->cur], bin_args(ctx));             // MD.cpp:356
 	// a = 0 (MD.cpp:357-366) is folded into the force evaluation that follows: it overwrites a[]
 	ctx->acc_live = false;
 	ctx->cells_valid = false;
@@ -1269,11 +1317,11 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 			CK(launch_dependent(k_chain_kick<true>, nblk(N, TPB), TPB, ctx->stream, cnt_of(ctx), ctx->cap, (const Particle *)ctx->pos[ctx->pcur],
 			                    (Particle *)nullptr, ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], (const int *)ctx->gid[ctx->cur],
 			                    (const int *)ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr,
-			                    done, epoch));
+			                    done, epoch, BinArgs{}));
 			ctx->launches++;
 		} else if (last) {
 			LAUNCHP(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0);
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0, BinArgs{});
 		} else {
 			// slab mode: the seam kernel is also the send side of the exchange (migrants + halo packed as the particles get
 			// their new positions, written straight into the neighbours' buffers); SMD_NO_SEAM_PACK=1: separate pack kernel
@@ -1283,18 +1331,19 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 				REQUIRE(!ctx->exch_pending, "slab: previous exchange not received yet");
 				ctx->xseq++;
 			}
+			const BinArgs bin = bin_args(ctx);
 			if (pdl) {
 				CK(launch_dependent(k_chain_kick<false>, nblk(N, TPB), TPB, ctx->stream, cnt_of(ctx), ctx->cap, (const Particle *)ctx->pos[ctx->pcur],
 				                    ctx->pos[ctx->pcur ^ 1], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], (const int *)ctx->gid[ctx->cur],
 				                    (const int *)ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0,
 				                    seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr,
-				                    done, epoch));
+				                    done, epoch, bin));
 				ctx->launches++;
 			} else
 			LAUNCHP(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
 			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
 			       ctx->errflag, bs, 0, seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr,
-			       (const int *)nullptr, 0);
+			       (const int *)nullptr, 0, bin);
 			ctx->pcur ^= 1;
 			ctx->acc_live = false;
 			ctx->cells_valid = false;
@@ -1465,18 +1514,22 @@ static int grow_cell_tables(smd_ctx *ctx, long long need)
 	const long long cap = std::min<long long>(need + need / 4, ctx->cellcap_limit);
 	CK(cudaStreamSynchronize(ctx->stream));
 	int *cnt = nullptr, *st = nullptr, *cu = nullptr;
+	unsigned long long *ss = nullptr;
 	if (cudaMalloc(&cnt, (cap + 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&st, (cap + 1) * sizeof(int)) != cudaSuccess ||
-	    cudaMalloc(&cu, (cap + 1) * sizeof(int)) != cudaSuccess) {
-		cudaFree(cnt); cudaFree(st); cudaFree(cu);
+	    cudaMalloc(&cu, (cap + 1) * sizeof(int)) != cudaSuccess || cudaMalloc(&ss, (size_t)(2 * SCAN_BLOCKS) * sizeof(unsigned long long)) != cudaSuccess) {
+		cudaFree(cnt); cudaFree(st); cudaFree(cu); cudaFree(ss);
 		cudaGetLastError();
 		ctx->err = "out of device memory growing the cell tables";
 		return SMD_ERR_CUDA;
 	}
 	CK(cudaMemsetAsync(cnt, 0, (cap + 1) * sizeof(int), ctx->stream));   // the histogram is left zeroed by every build
-	cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor);
-	ctx->count = cnt; ctx->start = st; ctx->cursor = cu;
+	CK(cudaMemsetAsync(ss, 0, (size_t)(2 * SCAN_BLOCKS) * sizeof(unsigned long long), ctx->stream));
+	cudaFree(ctx->count); cudaFree(ctx->start); cudaFree(ctx->cursor); cudaFree(ctx->scan_state);
+	ctx->count = cnt; ctx->start = st; ctx->cursor = cu; ctx->scan_state = ss;
 	ctx->cellcap = cap;
 	ctx->cells_valid = false;
+	ctx->hist_pending = false;     // (went with the old table)
+	ctx->next_win_valid = false;
 	return SMD_OK;
 }
 

@@ -59,10 +59,14 @@ constexpr unsigned CELL_DEAD = 0xffffffffu;
 // device-resident active window of the cell grid: the bounding box of occupied cells plus one cell each side.
 // win[0..2] origin, win[3..5] extent, win[6] number of cells in the window, win[8..9] the resolution of the 16-bit
 // window-relative coordinates of pos16[] and its inverse (float bit patterns; see quant_res).
-enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_FD0 = 7, WIN_RES = 8, WIN_INVRES = 9, WIN_WORDS = 12 };
+enum { WIN_ORG = 0, WIN_DIM = 3, WIN_NCELLS = 6, WIN_FD0 = 7, WIN_RES = 8, WIN_INVRES = 9, WIN_DIRTY = 10, WIN_WORDS = 12 };
 
 enum { ERR_OUT_OF_BOX = 1, ERR_WINDOW_CAP = 4, ERR_SLAB_MIGRATION = 8, ERR_SLAB_MSG_CAP = 16, ERR_SLAB_CAPACITY = 32,
        ERR_SLAB_TIMEOUT = 64, ERR_SLAB_MISSING = 128 };
+
+// The tagging pass (the kernel that moves the particles) may fill the histogram of the NEXT build's counting sort itself
+// (bin_particle): the window it bins into, the histogram, the key of every slot.  count == nullptr: k_bin does it later.
+struct BinArgs { int *win; int *count; int *cellOfSlot; };
 
 // slab halo / migration messages.  One receive buffer per side (0: from the left neighbour, 1: from the right one)
 // and parity of the exchange sequence number; the SENDER writes it directly through peer memory (NVLink P2P, or the
@@ -167,10 +171,17 @@ struct smd_ctx {
 	long long cellcap = 0;
 	long long cellcap_limit = 64ll << 20;   // the offset tables never grow beyond this many entries
 	int xs_wanted;     // x slices per cell when the fast path applies (SMD_XSUB, default 4)
-	int *count, *start, *cursor, *blockSums;
+	int *count, *start, *cursor;
+	unsigned long long *scan_state;   // k_scan: [SCAN_BLOCKS] prefix words, then [SCAN_BLOCKS] chunk totals
+	unsigned *scan_barrier = nullptr; // grid-barrier counter of k_scan's re-binning fallback
 	int *cellOfSlot;
 	int2 *order;      // {previous slot, original index} of every position claimed by k_place
-	int *win;         // window descriptor of the current sorted order (device)
+	int *win;         // [2][WIN_WORDS] window descriptors (device): [wcur] of the current sorted order, [wcur ^ 1] the one the next
+	                  // tagging pass bins into (published by every build: occupied box + 1 cell)
+	int wcur = 0;
+	bool prebin = true;         // SMD_NO_PREBIN=1: the histogram of the build is always a pass of its own (k_bin)
+	bool hist_pending = false;  // count[] holds the histogram of the current positions under win[wcur ^ 1] (a tagging pass filled it)
+	bool next_win_valid = false; // win[wcur ^ 1] was published by the last build and nothing has changed the geometry since
 	int *bbox;        // [6] min xyz, max xyz accumulators
 	int *errflag;
 	bool cells_valid;  // sorted order + start[] describe the current positions

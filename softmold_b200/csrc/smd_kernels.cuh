@@ -7,7 +7,7 @@
 namespace smd {
 
 constexpr int TPB = 128;          // threads per block for per-particle kernels
-constexpr int SCAN_BLOCKS = 256;  // fixed grid of the 3-phase cell-offset scan
+constexpr int SCAN_BLOCKS = 296;  // persistent grid of the single-pass cell-offset scan (two blocks per SM)
 constexpr int SCAN_TPB = 256;
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -104,9 +104,10 @@ __device__ __forceinline__ void philox_uniform3(uint64_t seed, uint64_t step, ui
 // the reference grid are packed into the record and the bounding box of occupied cells is accumulated for the
 // counting sort that follows (tag_cell below).
 __device__ __forceinline__ void tag_cell(Particle &p, const Geom &g, int *bbox, int *errflag, bool live);
+__device__ __forceinline__ int bin_particle(const Particle &p, bool live, const Geom &g, const BinArgs &b, int *errflag);
 
 __global__ void __launch_bounds__(TPB) k_verlet_first(Cnt cnt, int cap, Particle *pos, double *vel, const double *acc, double *unw,
-                                                      Geom g, double dt, int *bbox, int *errflag, const int *gid)
+                                                      Geom g, double dt, int *bbox, int *errflag, const int *gid, BinArgs bin)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	bool live = s < cnt.get();
@@ -133,6 +134,10 @@ __global__ void __launch_bounds__(TPB) k_verlet_first(Cnt cnt, int cap, Particle
 	}
 	tag_cell(p, g, bbox, errflag, live);
 	if (live) store_particle(pos + s, p);
+	if (bin.count) {
+		const int local = bin_particle(p, live, g, bin, errflag);
+		if (s < cnt.get()) bin.cellOfSlot[s] = local;
+	}
 }
 
 // Verlet::second, algorithms/verlet.h:463-477
@@ -296,6 +301,9 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 	for (int d = 0; d < 3; d++) {
 		int lo = bbox[d], hi = bbox[3 + d];
 		if (lo == INT_MAX) { lo = 0; hi = 0; }
+		// one empty cell on each side; a particle in the first (last) cell of an axis moves to the last (first) one when it
+		// wraps around the box, so an occupied box that touches a face takes the whole axis
+		if (lo == 0 || hi == g.nc[d] - 1) { lo = 0; hi = g.nc[d] - 1; }
 		lo = max(lo - 1, 0);
 		hi = min(hi + 1, g.nc[d] - 1);
 		w.org[d] = lo;
@@ -306,6 +314,42 @@ __device__ __forceinline__ Window window_of(const int *bbox, const Geom &g, long
 	n *= g.xs;
 	w.ncells = (n > cellcap) ? 0 : (int)n;   // over capacity: flagged by k_scan3, nothing is binned
 	return w;
+}
+
+// First pass of the counting sort FUSED into the kernel that moved the particle: key of p (k_bin's: window-local cell, x slice)
+// under the window b.win, one warp-aggregated atomic per distinct key.  b.win was published by the previous build as the
+// occupied box of ITS positions plus one cell on every side (k_scan, win_next), so a particle can only fall outside it by
+// moving more than a whole cell beyond everything that was occupied in one step.  That is legal (the reference follows any
+// motion inside the box): the window is then marked dirty and the build that follows redoes the histogram under the
+// window of the new occupied box (k_scan's fallback).  Returns the key (-1: not binned).  Must be called by all 32 lanes.
+__device__ __forceinline__ int bin_particle(const Particle &p, bool live, const Geom &g, const BinArgs &b, int *errflag)
+{
+	int local = -1;
+	if (live) {
+		int cx, cy, cz;
+		unpack_cell(p.cell, cx, cy, cz);
+		const int lx = cx - b.win[WIN_ORG], ly = cy - b.win[WIN_ORG + 1], lz = cz - b.win[WIN_ORG + 2];
+		const int d0 = b.win[WIN_DIM], d1 = b.win[WIN_DIM + 1], d2 = b.win[WIN_DIM + 2];
+		if (b.win[WIN_NCELLS] == 0 || lx < 0 || lx >= d0 || ly < 0 || ly >= d1 || lz < 0 || lz >= d2) b.win[WIN_DIRTY] = 1;
+		else {
+			int sub = 0;
+			if (g.xs > 1) sub = min(max((int)((p.x - (double)cx * g.cs[0]) * g.finv), 0), g.xs - 1);
+			local = (lx * g.xs + sub) + b.win[WIN_FD0] * (ly + d1 * lz);
+		}
+	}
+	const unsigned active = __ballot_sync(0xffffffffu, local >= 0);
+	if (local >= 0) {
+		const unsigned peers = __match_any_sync(active, local);
+		if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(b.count + local, __popc(peers));
+	}
+	return local;
+}
+
+// zero the histogram a tagging pass filled when no build is going to consume it (the particles are replaced or rescaled first)
+__global__ void __launch_bounds__(256) k_clear_count(const int *win, int *count)
+{
+	const int n = win[WIN_NCELLS];
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) count[i] = 0;
 }
 
 // pos16[]: the 8-byte phase-1 candidate record of k_pair_force2.  Coordinates are 16-bit fixed point relative to the
@@ -378,127 +422,217 @@ __global__ void __launch_bounds__(TPB) k_bin(Cnt cnt, const Particle *pos, Geom 
 	}
 }
 
-// 3-phase exclusive scan of count[0..ncells) with a fixed grid (ncells lives on the device)
-__device__ __forceinline__ void scan_chunk(int ncells, int &b0, int &b1)
-{
-	int chunk = (ncells + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
-	chunk = (chunk + 4 * SCAN_TPB - 1) / (4 * SCAN_TPB) * (4 * SCAN_TPB);   // k_scan3 takes four cells per thread and pass
-	long long a = (long long)blockIdx.x * chunk;
-	b0 = (int)min(a, (long long)ncells);
-	b1 = (int)min(a + chunk, (long long)ncells);
-}
-
-__global__ void __launch_bounds__(SCAN_TPB) k_scan1(const int *count, const int *bbox, Geom g, long long cellcap, int *blockSums)
-{
-	pdl_prologue();
-	int b0, b1;
-	scan_chunk(window_of(bbox, g, cellcap).ncells, b0, b1);
-	int sum = 0;
-	for (int i = b0 + threadIdx.x; i < b1; i += SCAN_TPB) sum += count[i];
-	__shared__ int sh[SCAN_TPB / 32];
-	sum = __reduce_add_sync(0xffffffffu, sum);
-	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		int t = 0;
-		for (int w = 0; w < SCAN_TPB / 32; w++) t += sh[w];
-		blockSums[blockIdx.x] = t;
-	}
-}
-
 // start the occupied-cell extremes from scratch (after set_particles / a box move that changed the grid)
 __global__ void k_arm_bbox(int *bbox)
 {
 	if (threadIdx.x < 3) { bbox[threadIdx.x] = INT_MAX; bbox[3 + threadIdx.x] = INT_MIN; }
 }
 
-// Second and last phase of the scan.  Every block sums the partial sums of the blocks before it itself (256 values:
-// cheaper than a kernel of its own), block 0 publishes the window for the kernels that follow.
-// nlive: slab mode only -- the number of live local particles after this build (the last block knows the total)
-__global__ void __launch_bounds__(SCAN_TPB) k_scan3(int *count, const int *bbox, Geom g, long long cellcap, int *win, const int *blockSums,
-                                                    int *start, int *cursor, int N, int *nlive, int *errflag)
+// Exclusive scan of count[0..ncells) in ONE kernel (ncells lives on the device; the grid is fixed and persistent, all
+// blocks resident): chunk totals, a scan of the totals by the block that arrives last, then the chunks themselves (see the
+// body).  Measured first: decoupled look-back over tiles dealt round-robin -- with one wave of tiles every predecessor is
+// still an aggregate, so tile t polls all t states: 16 k polls on a dozen cache lines of one L2 slice, 16 us.  Here a
+// block polls one word.  Prefix word: {epoch : 30 | flag : 2 | value : 32}; the epoch (the build counter) makes the words of
+// earlier builds read as "not yet", so nothing is ever cleared.
+// Block 0 publishes the window of this build in win[] (the kernels that follow read it there) and, in win_next[], the
+// window the NEXT tagging pass may bin into (see bin_particle): the occupied box of the positions of this build + 1 cell.
+// prebinned: the histogram was filled by the tagging pass itself under the window already in win[]; else (after
+// set_particles / a box move / in slab mode) k_bin filled it under window_of(bbox), which is published here.
+// nlive: slab mode only -- the number of live local particles after this build
+constexpr int SCAN_TILE = 8 * SCAN_TPB;
+constexpr unsigned long long SCAN_AGG = 1ull, SCAN_PREFIX = 2ull;
+
+__device__ __forceinline__ void publish_window(int *win, const Window &wd, const Geom &g)
+{
+	for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = wd.org[d]; win[WIN_DIM + d] = wd.dim[d]; }
+	win[WIN_NCELLS] = wd.ncells;
+	win[WIN_FD0] = wd.fd0;
+	const float res = quant_res(wd, g);
+	win[WIN_RES] = __float_as_int(res);
+	win[WIN_INVRES] = __float_as_int(1.0f / res);
+	win[WIN_DIRTY] = 0;
+}
+
+// barrier over a grid whose blocks are all resident (k_scan's rarely taken fallback); *ctr only ever grows
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, int *errflag)
+{
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const unsigned ticket = atomicAdd(ctr, 1u);
+		const unsigned target = (ticket / gridDim.x + 1u) * gridDim.x;
+		const long long t0 = clock64();
+		while ((int)(atomicAdd(ctr, 0u) - target) < 0)
+			if (clock64() - t0 > 20000000000ll) { atomicOr(errflag, ERR_WINDOW_CAP); break; }   // ~10 s: never hang the device
+		__threadfence();
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan(int *count, const int *bbox, Geom g, long long cellcap, int *win, int *win_next, int prebinned,
+                                                   int *start, int *cursor, int N, int *nlive, int *errflag,
+                                                   unsigned long long *state, unsigned epoch, const Particle *pos, int *cellOfSlot,
+                                                   unsigned *barrier)
 {
 	pdl_prologue();
-	const Window wd = window_of(bbox, g, cellcap);
-	const int ncells = wd.ncells;
-	int b0, b1;
-	scan_chunk(ncells, b0, b1);
 	__shared__ int sh[SCAN_TPB / 32];
-	__shared__ int carry_sh;
-	{
-		static_assert(SCAN_BLOCKS <= SCAN_TPB, "one thread per block sum");
-		int v = ((int)threadIdx.x < (int)blockIdx.x && threadIdx.x < SCAN_BLOCKS) ? blockSums[threadIdx.x] : 0;
-		v = __reduce_add_sync(0xffffffffu, v);
-		if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			int t = 0;
-			for (int w = 0; w < SCAN_TPB / 32; w++) t += sh[w];
-			carry_sh = t;
-			if (blockIdx.x == 0) {
-				for (int d = 0; d < 3; d++) { win[WIN_ORG + d] = wd.org[d]; win[WIN_DIM + d] = wd.dim[d]; }
-				win[WIN_NCELLS] = wd.ncells;
-				win[WIN_FD0] = wd.fd0;
-				const float res = quant_res(wd, g);
-				win[WIN_RES] = __float_as_int(res);
-				win[WIN_INVRES] = __float_as_int(1.0f / res);
-				if (wd.ncells == 0) atomicOr(errflag, ERR_WINDOW_CAP);
+	__shared__ int s_excl;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	int ncells;
+	if (prebinned && win[WIN_DIRTY]) {
+		// A particle left the window the tagging pass binned into (bin_particle): redo the histogram under the window of the
+		// new occupied box.  The flag was final before this grid started, so every block takes this path together; the grid is
+		// persistent (all blocks resident), which makes the two barriers safe.
+		const int oldn = win[WIN_NCELLS];
+		const int gtid = blockIdx.x * SCAN_TPB + tid, gsz = gridDim.x * SCAN_TPB;
+		for (int i = gtid; i < oldn; i += gsz) count[i] = 0;
+		grid_barrier(barrier, errflag);
+		const Window wd = window_of(bbox, g, cellcap);
+		if (blockIdx.x == 0 && tid == 0) publish_window(win, wd, g);
+		for (int s0 = (gtid & ~31); s0 < N; s0 += gsz) {   // (whole warps: the aggregation votes)
+			const int s = s0 + lane;
+			int local = -1;
+			if (s < N && wd.ncells > 0) {
+				const Particle p = load_particle(pos + s);
+				int cx, cy, cz;
+				unpack_cell(p.cell, cx, cy, cz);
+				int sub = 0;
+				if (g.xs > 1) sub = min(max((int)((p.x - (double)cx * g.cs[0]) * g.finv), 0), g.xs - 1);
+				local = ((cx - wd.org[0]) * g.xs + sub) + wd.fd0 * ((cy - wd.org[1]) + wd.dim[1] * (cz - wd.org[2]));
+				cellOfSlot[s] = local;
+			}
+			const unsigned active = __ballot_sync(0xffffffffu, local >= 0);
+			if (local >= 0) {
+				const unsigned peers = __match_any_sync(active, local);
+				if (lane == __ffs(peers) - 1) atomicAdd(count + local, __popc(peers));
 			}
 		}
-		__syncthreads();
+		grid_barrier(barrier, errflag);
+		ncells = wd.ncells;
+	} else if (prebinned) ncells = win[WIN_NCELLS];
+	else {
+		const Window wd = window_of(bbox, g, cellcap);
+		ncells = wd.ncells;
+		if (blockIdx.x == 0 && tid == 0) publish_window(win, wd, g);
 	}
-	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	// four consecutive cells per thread and pass (16-byte loads and stores: the table has 4 x the cells since the sort
-	// key carries x slices); chunk starts are multiples of 4 and the arrays come from cudaMalloc
-	for (int base = b0; base < b1; base += 4 * SCAN_TPB) {
-		const int i = base + 4 * (int)threadIdx.x;
-		const bool full = i + 3 < b1;
-		int4 v = make_int4(0, 0, 0, 0);
-		if (full) v = *reinterpret_cast<const int4 *>(count + i);
-		else {
-			if (i < b1) v.x = count[i];
-			if (i + 1 < b1) v.y = count[i + 1];
-			if (i + 2 < b1) v.z = count[i + 2];
-		}
-		const int sum4 = (v.x + v.y) + (v.z + v.w);
-		int inc = sum4;
+	if (blockIdx.x == 0 && tid == 0) {
+		if (ncells == 0) atomicOr(errflag, ERR_WINDOW_CAP);
+		if (win_next) publish_window(win_next, window_of(bbox, g, cellcap), g);
+	}
+	// ---- every block owns a contiguous chunk of tiles.  Pass 1: the chunk's total.  The block that arrives last (a ticket
+	// counter that only ever grows: every build all blocks take exactly one ticket) scans the gridDim.x totals and
+	// publishes one exclusive prefix per block, stamped with the build's epoch; a block polls nothing but its own word.
+	// Pass 2: the chunk again (L2-hot), scanned tile by tile from that prefix, written out, histogram zeroed.
+	const int T = (ncells + SCAN_TILE - 1) / SCAN_TILE;
+	const int tpb = (T + (int)gridDim.x - 1) / (int)gridDim.x;
+	const int t0 = min((int)blockIdx.x * tpb, T), t1 = min(t0 + tpb, T);
+	const unsigned long long ep = (unsigned long long)(epoch & 0x3fffffffu) << 34;
+	auto load8 = [&](int i, int (&v)[8]) {
+		if (i + 7 < ncells) {
+			const int4 a = *reinterpret_cast<const int4 *>(count + i), b = *reinterpret_cast<const int4 *>(count + i + 4);
+			v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+		} else {
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-			int t = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= o) inc += t;
+			for (int k = 0; k < 8; k++) v[k] = (i + k < ncells) ? count[i + k] : 0;
 		}
+	};
+	auto block_total = [&](int x) {   // sum over the block, returned to every thread
+		x = __reduce_add_sync(0xffffffffu, x);
+		__syncthreads();
+		if (lane == 0) sh[w] = x;
+		__syncthreads();
+		int tot = 0;
+#pragma unroll
+		for (int k = 0; k < SCAN_TPB / 32; k++) tot += sh[k];
+		return tot;
+	};
+	int mine = 0;
+	for (int t = t0; t < t1; t++) {
+		int v[8];
+		load8(t * SCAN_TILE + 8 * tid, v);
+#pragma unroll
+		for (int k = 0; k < 8; k++) mine += v[k];
+	}
+	const int chunk_total = block_total(mine);
+	__shared__ int s_last;
+	int *agg = reinterpret_cast<int *>(state + gridDim.x);   // [gridDim.x] chunk totals of this build, behind the prefix words
+	if (tid == 0) {
+		agg[blockIdx.x] = chunk_total;
+		__threadfence();
+		const unsigned ticket = atomicAdd(barrier + 1, 1u);
+		s_last = (ticket % gridDim.x) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (s_last) {   // (uniform per block) everybody's total is in: one block scans them
+		__threadfence();
+		int carry = 0;
+		for (int b0 = 0; b0 < (int)gridDim.x; b0 += SCAN_TPB) {
+			const int b = b0 + tid;
+			const int x = b < (int)gridDim.x ? *reinterpret_cast<volatile int *>(agg + b) : 0;
+			int inc = x;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+			__syncthreads();
+			if (lane == 31) sh[w] = inc;
+			__syncthreads();
+			int woff = 0, total = 0;
+#pragma unroll
+			for (int k = 0; k < SCAN_TPB / 32; k++) { const int y = sh[k]; if (k < w) woff += y; total += y; }
+			if (b < (int)gridDim.x) {
+				const unsigned long long word = ep | (SCAN_PREFIX << 32) | (unsigned)(carry + woff + inc - x);
+				asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(state + b), "l"(word) : "memory");
+			}
+			carry += total;
+		}
+	}
+	if (tid == 0) {   // this block's prefix (a word carries everything the reader needs: relaxed accesses)
+		unsigned long long word;
+		do {
+			asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(word) : "l"(state + blockIdx.x) : "memory");
+			if ((word >> 34) != (ep >> 34)) __nanosleep(200);
+		} while ((word >> 34) != (ep >> 34));
+		s_excl = (int)(unsigned)(word & 0xffffffffull);
+	}
+	__syncthreads();
+	int carry = s_excl;
+	for (int t = t0; t < t1; t++) {
+		const int i = t * SCAN_TILE + 8 * tid;
+		int v[8];
+		load8(i, v);
+		int sum8 = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) sum8 += v[k];
+		int inc = sum8;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+		__syncthreads();
 		if (lane == 31) sh[w] = inc;
 		__syncthreads();
 		int woff = 0, total = 0;
-		for (int k = 0; k < SCAN_TPB / 32; k++) {
-			int t = sh[k];
-			if (k < w) woff += t;
-			total += t;
-		}
-		int carry = carry_sh;
-		const int ex = carry + woff + inc - sum4;
-		const int4 e = make_int4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
-		if (full) {
-			*reinterpret_cast<int4 *>(start + i) = e;
-			*reinterpret_cast<int4 *>(cursor + i) = e;
-			*reinterpret_cast<int4 *>(count + i) = make_int4(0, 0, 0, 0);
+#pragma unroll
+		for (int k = 0; k < SCAN_TPB / 32; k++) { const int x = sh[k]; if (k < w) woff += x; total += x; }
+		int ex = carry + woff + inc - sum8;
+		int e[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) { e[k] = ex; ex += v[k]; }
+		if (i + 7 < ncells) {
+			const int4 a = make_int4(e[0], e[1], e[2], e[3]), b = make_int4(e[4], e[5], e[6], e[7]), z = make_int4(0, 0, 0, 0);
+			*reinterpret_cast<int4 *>(start + i) = a; *reinterpret_cast<int4 *>(start + i + 4) = b;
+			*reinterpret_cast<int4 *>(cursor + i) = a; *reinterpret_cast<int4 *>(cursor + i + 4) = b;
+			*reinterpret_cast<int4 *>(count + i) = z; *reinterpret_cast<int4 *>(count + i + 4) = z;
 		} else {
-			if (i < b1) { start[i] = e.x; cursor[i] = e.x; count[i] = 0; }
-			if (i + 1 < b1) { start[i + 1] = e.y; cursor[i + 1] = e.y; count[i + 1] = 0; }
-			if (i + 2 < b1) { start[i + 2] = e.z; cursor[i + 2] = e.z; count[i + 2] = 0; }
+#pragma unroll
+			for (int k = 0; k < 8; k++)
+				if (i + k < ncells) { start[i + k] = e[k]; cursor[i + k] = e[k]; count[i + k] = 0; }
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) carry_sh = carry + total;
-		__syncthreads();
+		carry += total;
+		if (t == T - 1 && tid == 0) {   // the carry behind the last tile = the number of binned particles
+			const int all = nlive ? carry : N;
+			start[ncells] = all;
+			if (nlive) *nlive = all;
+		}
 	}
-	__syncthreads();
-	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-		// the last block's carry after its chunk = number of binned particles (every block up to the end of the table
-		// has an empty or final chunk)
-		int total = nlive ? carry_sh : N;
-		start[ncells] = total;
-		if (nlive) *nlive = total;
-	}
+	if (T == 0 && blockIdx.x == 0 && tid == 0) { start[0] = nlive ? 0 : N; if (nlive) *nlive = 0; }
 }
 
 // pass 2: claim a position inside the cell's range (arbitrary order, fixed by k_reorder)
@@ -1910,7 +2044,8 @@ template <bool LAST>
 __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, int cap, const Particle *__restrict__ pos_in, Particle *__restrict__ pos_out,
                                                     double *vel, double *acc, double *unw, const int *__restrict__ gid,
                                                     const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag,
-                                                    BeadSet bs, int slot0, SlabComm comm, int seq, int *gid_w, const int *done, int epoch)
+                                                    BeadSet bs, int slot0, SlabComm comm, int seq, int *gid_w, const int *done, int epoch,
+                                                    BinArgs bin)
 {
 	// done != nullptr: launched as a programmatic dependent of the pair kernel -- this block may be resident while the
 	// tail of that grid is still running and only needs the accelerations of its own 128 slots, which pair block `blk`
@@ -1985,6 +2120,10 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 	if (valid) {
 		if (!live) p.cell = CELL_DEAD;   // slab ghost: replaced by the exchange (its index-table entry is given back by k_bin)
 		store_particle(pos_out + s, p);
+	}
+	if (bin.count) {   // the histogram of the build that follows
+		const int local = bin_particle(p, live, g, bin, errflag);
+		if (valid) bin.cellOfSlot[s] = local;
 	}
 	if (seq > 0) {
 		const bool wrote = slab_pack_one(live, s, p, gi, mvx, mvy, mvz, unw != nullptr, mux, muy, muz, gid_w, g, comm, seq, errflag);

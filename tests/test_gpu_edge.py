@@ -231,3 +231,30 @@ def test_hundred_beads_through_the_cell_grid(orc):
     xyz, _, vel = ctx.get_particles()
     assert np.abs(xyz - S.xyz).max() <= 1e-9 and np.abs(vel - S.vel).max() <= 1e-7
     ctx.close()
+
+
+def test_particles_that_outrun_the_occupied_window(orc):
+    """The kernel that moves the particles also fills the histogram of the next cell build, under a window published by the
+    previous build (occupied box + 1 cell).  Particles that leave that window in one step -- here a few fired at 150 sigma
+    per time unit out of a small cluster in a large box, some of them across the periodic faces -- mark it dirty and the
+    build redoes its histogram (k_scan's fallback): trajectory equal to the oracle's, cells bit-exact."""
+    rng = np.random.default_rng(5)
+    m = gas(21, 1500, (60.0, 60.0, 60.0), n_types=3, type0=0.0, chains=((100, 3),))
+    m["xyz"] = np.mod(m["xyz"] * 0.2 + np.array([1.0, 24.0, 47.5]), 60.0)     # a 12-sigma cluster touching the x = 0 face region
+    m["vel"][:] = rng.normal(0, 1.0, m["vel"].shape)
+    fast = rng.choice(1500, 12, replace=False)
+    m["vel"][fast] = rng.normal(0, 1.0, (12, 3)) * 150.0
+    ctx = sm.Context.from_dict(m)
+    S = orc.System(m, noise="philox")
+    S.init(3)
+    ctx.compute_forces(mask=sm.MASK_ALL, step=3)
+    for k in range(3):       # the fused multi-step path and the step_begin / step_end path
+        ctx.step(3 + 4 * k, 3)
+        ctx.step_begin(6 + 4 * k); ctx.step_end(6 + 4 * k)
+        for i in range(4):
+            S.step(3 + 4 * k + i)
+        xyz, _, vel = ctx.get_particles()
+        assert np.abs(xyz - S.xyz).max() <= 1e-9 and np.abs(vel - S.vel).max() <= 1e-8
+        _, key, _ = ctx.get_cell_ids()
+        assert np.array_equal(key, orc.cell_ids(xyz, m["size"], m["cutoff"]))
+    ctx.close()
