@@ -57,6 +57,9 @@ static cudaError_t launch_ex(bool pdl, void (*kernel)(KArgs...), int grid, int b
 	} while (0)
 
 static const int MAX_PARTIALS = 1 << 20;
+#ifndef SMD_PAIR3_MAX_DEFAULT
+#define SMD_PAIR3_MAX_DEFAULT 32000   // measured (profiles/r02b_pair3_ab.md): 15 000 particles 72 -> 47 us per step, 30 000 76 -> 67, 60 000 78 -> 102
+#endif
 #ifndef SMD_DEFAULT_PDL_CHAIN
 #define SMD_DEFAULT_PDL_CHAIN true
 #endif
@@ -186,7 +189,7 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 }
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
-static int pair_force_smem(smd_ctx *ctx, bool du = false);
+static int pair_force_smem(smd_ctx *ctx, bool du = false, bool split3 = false);
 static int drop_pending_histogram(smd_ctx *ctx);
 
 static int upload_acut(smd_ctx *ctx)
@@ -271,6 +274,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_ENERGY_ONEPHASE"); ctx->force_onephase_energy = e && *e == '1'; }
 	// SMD_NO_FUSE=1: every phase of the step in its own kernel (A/B and bit-identity tests).
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
+	{ const char *e = getenv("SMD_PAIR3"); ctx->pair3 = e ? atoi(e) : -1; }
+	{ const char *e = getenv("SMD_PAIR3_MAX"); ctx->pair3_max = e ? atoi(e) : SMD_PAIR3_MAX_DEFAULT; }
 	{ const char *e = getenv("SMD_NO_PREBIN"); ctx->prebin = !(e && *e == '1'); }
 	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }
@@ -1077,26 +1082,47 @@ static int ready(smd_ctx *ctx)
 	return SMD_OK;
 }
 
-static int pair_force_smem(smd_ctx *ctx, bool du)   // du: the force + dPotential instance (EMODE 3) stages a second table
+static int pair_force_smem(smd_ctx *ctx, bool du, bool split3)   // du: the force + dPotential instance (EMODE 3) stages a second table
 {
 	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
 	       (du ? (PTAB_STRIDE * ctx->nT * ctx->nT + PAIR_TPB) * (int)sizeof(double) : 0) +
-	       (PAIR_TPB / 32) * PAIR_CAP * 32 * (int)sizeof(unsigned short);
+	       (split3 ? (PAIR3_TPB / 32) * PAIR3_CAP : (PAIR_TPB / 32) * PAIR_CAP) * 32 * (int)sizeof(unsigned short);
 }
+
+// Three threads per particle (k_pair_force2<.., SPLIT = 3>): a third of the critical path per thread.  Worth it where the
+// grid of the one-thread engine does not fill the device, i.e. where the launch takes as long as its slowest thread.
+static bool use_pair3(const smd_ctx *ctx)
+{
+	if (!ctx->tables_symmetric) return false;
+	if (ctx->pair3 >= 0) return ctx->pair3 == 1;
+	return ctx->N <= ctx->pair3_max;
+}
+// particles per block of the pair force engine in use: the unit of the completion words (PairGeo::done) and of the
+// dPotential block sums of the force + dPotential pass
+static int pair_block_particles(const smd_ctx *ctx) { return use_pair3(ctx) ? PAIR3_TPB / 3 : PAIR_TPB; }
 
 // the pair force of all particles into acc[] (LANGEVIN: a = thermostat term + pair sum, else a += pair sum)
 template <bool LANGEVIN>
 static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
 {
 	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
+	const bool p3 = use_pair3(ctx);
+	const int nb3 = nblk(N, PAIR3_TPB / 3);
 	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
 		ctx->du_armed = false;
+		if (p3)
+			LAUNCHP((k_pair_force2<3, true, true, 3>), nb3, PAIR3_TPB, pair_force_smem(ctx, true, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16);
+		else
 		LAUNCHP((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16);
 		ctx->du_ready = true;
 		return SMD_OK;
 	}
-	if (ctx->tables_symmetric)
+	if (p3)
+		LAUNCHP((k_pair_force2<0, LANGEVIN, true, 3>), nb3, PAIR3_TPB, pair_force_smem(ctx, false, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
+	else if (ctx->tables_symmetric)
 		LAUNCHP((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
 	else
@@ -1300,8 +1326,8 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 		const bool pdl = ctx->pdl && scatter == 0 && ctx->prof_mask == 0 && ctx->tables_symmetric;
 		if (pdl) {
 			if (!ctx->pair_done) {
-				CK(cudaMalloc(&ctx->pair_done, (size_t)nblk(ctx->cap, PAIR_TPB) * sizeof(int)));
-				CK(cudaMemsetAsync(ctx->pair_done, 0, (size_t)nblk(ctx->cap, PAIR_TPB) * sizeof(int), ctx->stream));
+				CK(cudaMalloc(&ctx->pair_done, (size_t)nblk(ctx->cap, 32) * sizeof(int)));   // (one word per block of either pair engine)
+				CK(cudaMemsetAsync(ctx->pair_done, 0, (size_t)nblk(ctx->cap, 32) * sizeof(int), ctx->stream));
 			}
 			ctx->pgeo.done = ctx->pair_done;
 			ctx->pgeo.epoch = ++ctx->pair_epoch;
@@ -1312,16 +1338,17 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 		if (rc) return rc;
 		const int *done = pdl ? ctx->pair_done : nullptr;
 		const int epoch = ctx->pair_epoch;
+		const int done_per = TPB / pair_block_particles(ctx);   // completion words per seam block
 		ProfScope pf(ctx, SMD_PHASE_FUSED);
 		if (last && pdl) {
 			CK(launch_dependent(k_chain_kick<true>, nblk(N, TPB), TPB, ctx->stream, cnt_of(ctx), ctx->cap, (const Particle *)ctx->pos[ctx->pcur],
 			                    (Particle *)nullptr, ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], (const int *)ctx->gid[ctx->cur],
 			                    (const int *)ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr,
-			                    done, epoch, BinArgs{}));
+			                    done, epoch, BinArgs{}, done_per));
 			ctx->launches++;
 		} else if (last) {
 			LAUNCHP(k_chain_kick<true>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], (Particle *)nullptr, ctx->vel[ctx->cur],
-			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0, BinArgs{});
+			       ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0, SlabComm{}, 0, (int *)nullptr, (const int *)nullptr, 0, BinArgs{}, 1);
 		} else {
 			// slab mode: the seam kernel is also the send side of the exchange (migrants + halo packed as the particles get
 			// their new positions, written straight into the neighbours' buffers); SMD_NO_SEAM_PACK=1: separate pack kernel
@@ -1337,13 +1364,13 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 				                    ctx->pos[ctx->pcur ^ 1], ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], (const int *)ctx->gid[ctx->cur],
 				                    (const int *)ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox, ctx->errflag, bs, 0,
 				                    seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr,
-				                    done, epoch, bin));
+				                    done, epoch, bin, done_per));
 				ctx->launches++;
 			} else
 			LAUNCHP(k_chain_kick<false>, nblk(N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos[ctx->pcur ^ 1],
 			       ctx->vel[ctx->cur], ctx->acc, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->slot_of, ctx->geom, cs, ctx->desc.dt, ctx->bbox,
 			       ctx->errflag, bs, 0, seam_pack ? ctx->comm : SlabComm{}, seam_pack ? ctx->xseq : 0, seam_pack ? ctx->gid[ctx->cur] : (int *)nullptr,
-			       (const int *)nullptr, 0, bin);
+			       (const int *)nullptr, 0, bin, 1);
 			ctx->pcur ^= 1;
 			ctx->acc_live = false;
 			ctx->cells_valid = false;
@@ -1380,7 +1407,7 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 	if (MODE == 2 && ctx->du_ready && sx == ctx->du_en.sx && sy == ctx->du_en.sy && sz == ctx->du_en.sz) {
 		// the block sums of this very dPotential were left behind by the force kernel of the last step (smd_arm_dpotential)
 		ctx->du_ready = false;
-		LAUNCH(k_final_sum, 1, 256, 0, nblk(N, PAIR_TPB), ctx->du_partials, ctx->scalars, push(SMD_TERM_PAIR), 1.0);
+		LAUNCH(k_final_sum, 1, 256, 0, nblk(N, pair_block_particles(ctx)), ctx->du_partials, ctx->scalars, push(SMD_TERM_PAIR), 1.0);
 	} else if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
 		// two-phase kernel, every unordered pair once (see k_pair_force2)
 		int nb = nblk(N, PAIR_TPB);
@@ -1634,7 +1661,7 @@ extern "C" int smd_arm_dpotential(smd_ctx *ctx, const double scale[3])
 	                  !ctx->no_du_fuse && ctx->desc.noise != SMD_NOISE_EXTERNAL;
 	if (!fuse) return SMD_OK;
 	CK(cudaSetDevice(ctx->device));
-	const size_t need = (size_t)nblk(ctx->N, PAIR_TPB);
+	const size_t need = (size_t)nblk(ctx->N, PAIR3_TPB / 3);   // (either pair engine: the smaller block)
 	if (ctx->du_partials_n < need) {   // block sums of its own: nothing else may overwrite them before they are used
 		if (ctx->du_partials) cudaFree(ctx->du_partials);
 		ctx->du_partials = nullptr; ctx->du_partials_n = 0;

@@ -1064,6 +1064,14 @@ constexpr int PAIR_TPB = 128;
 #define SMD_PAIR_BLOCKS 4
 #endif
 constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 128 x 32 x 2 B = 32 KiB per block
+// k_pair_force2<.., SPLIT = 3>: 32 particles per block, three threads each (one per z plane of the stencil)
+#ifndef SMD_PAIR3_BLOCKS
+#define SMD_PAIR3_BLOCKS 4
+#endif
+#ifndef SMD_PAIR3_CAP
+#define SMD_PAIR3_CAP 64
+#endif
+constexpr int PAIR3_TPB = 96, PAIR3_BLOCKS = SMD_PAIR3_BLOCKS, PAIR3_CAP = SMD_PAIR3_CAP;
 constexpr int PAIR_SEGBITS = 12;   // entry = (range index << 12) | offset inside the range
 
 struct LangevinArgs { double gamma, sigma; uint64_t seed, step; const double *vel; const int *gid; const double *ext_noise; };
@@ -1200,8 +1208,8 @@ struct PairSmem {
 // other half comes from the other end of the pair.  Forces stay bit-identical to EMODE 0 (same pairs, same order).
 // (EnergyArgs: smd_internal.cuh)
 
-template <int EMODE, bool LANGEVIN, bool SYMM>
-__global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
+template <int EMODE, bool LANGEVIN, bool SYMM, int SPLIT = 1>
+__global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 ? PAIR3_BLOCKS : SMD_PAIR_BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
                                                             const int *__restrict__ win, Geom g, int nT,
                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
@@ -1213,9 +1221,18 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	static_assert(EMODE != 3 || SYMM, "forces + dPotential in one pass: symmetric tables only");
 	constexpr bool ENERGY_ONLY = (EMODE == 1 || EMODE == 2);   // no forces; every unordered pair once
 	constexpr bool DU = (EMODE == 3);                          // forces + dPotential
+	// SPLIT = 3: three threads per particle, one per z plane of the stencil (warp w of the block's three takes the rows
+	// oz = w - 1 of the same 32 particles): a third of the critical path per thread -- a block of a small system, or of the
+	// last, sparse round of blocks of a large one, is done in a third of the time -- and three partial sums per particle,
+	// added in plane order by the first warp.  Forces only.
+	static_assert(SPLIT == 1 || (SPLIT == 3 && !ENERGY_ONLY), "the split engine evaluates forces");
+	constexpr int BT = SPLIT == 3 ? PAIR3_TPB : PAIR_TPB;      // threads per block
+	constexpr int NP = BT / SPLIT;                             // particles per block
+	constexpr int CAP = SPLIT == 3 ? PAIR3_CAP : PAIR_CAP;     // list entries per thread
+	constexpr int NROW = PAIR_NSEG / SPLIT;                    // stencil rows per thread
 	const int N = cnt.get();
 	const int bid = (int)blockIdx.x;
-	if (bid * PAIR_TPB >= N) {
+	if (bid * NP >= N) {
 		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
 		return;
 	}
@@ -1232,10 +1249,11 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	double *s_utab = s_ptab + nptab;
 	double *s_dup = s_utab + nptab;
 	unsigned short *s_lists = reinterpret_cast<unsigned short *>(DU ? s_dup + PAIR_TPB : s_ptab + nptab);
+	const int row0 = SPLIT == 3 ? 3 * (int)(threadIdx.x >> 5) : 0;   // first stencil row of this thread
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	for (int k = tid; k < nptab; k += PAIR_TPB) s_ptab[k] = ptab[k];
-	if (DU) for (int k = tid; k < nptab; k += PAIR_TPB) s_utab[k] = en.utab[k];
-	for (int k = tid; k < PAIR_CAP + 2; k += PAIR_TPB) sm.hist[k] = 0;
+	for (int k = tid; k < nptab; k += BT) s_ptab[k] = ptab[k];
+	if (DU) for (int k = tid; k < nptab; k += BT) s_utab[k] = en.utab[k];
+	for (int k = tid; k < CAP + 2; k += BT) sm.hist[k] = 0;
 	const int w0 = win[WIN_ORG], w1 = win[WIN_ORG + 1], w2 = win[WIN_ORG + 2];
 	const int d0 = win[WIN_DIM], d1 = win[WIN_DIM + 1], d2 = win[WIN_DIM + 2];
 	const int fd0 = win[WIN_FD0], xs = g.xs;
@@ -1243,20 +1261,21 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 
 	// ---- deal the block's particles to threads by class
 	{
-		const int i0 = bid * PAIR_TPB + tid;
+		const int pt = SPLIT == 3 ? lane : tid;   // (SPLIT = 3: every warp holds the same 32 particles)
+		const int i0 = bid * NP + pt;
 		const bool heavy = (i0 < N) && pos32[i0].w >= pg.thr32;
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
 		if (lane == 0) sm.wcnt[wid] = __popc(bal);
 		__syncthreads();
 		int before = 0, total = 0;
 #pragma unroll
-		for (int k = 0; k < PAIR_TPB / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < wid) before += c; }
+		for (int k = 0; k < NP / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < (SPLIT == 3 ? 0 : wid)) before += c; }
 		const int below = __popc(bal & ((1u << lane) - 1u));
-		const int rank = heavy ? before + below : total + (tid - before - below);
-		sm.perm[rank] = i0;
+		const int rank = heavy ? before + below : total + (pt - before - below);
+		if (SPLIT == 1 || wid == 0) sm.perm[rank] = i0;
 		__syncthreads();
 	}
-	const int i = sm.perm[tid];
+	const int i = sm.perm[SPLIT == 3 ? lane : tid];
 	// slab mode: ghosts are only neighbours, nobody gathers for them
 	const bool live = i < N && !(g.slab && (gid[i] & GID_GHOST));
 	Particle pi;
@@ -1271,7 +1290,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const double rc2 = g.rc2;
 	const float ai = p32.w;
 	// entries of thread t's list sit 64 B apart (one 16-bit column per lane)
-	auto list_base = [&](int t) { return (unsigned)__cvta_generic_to_shared(s_lists + (t >> 5) * (PAIR_CAP * 32) + (t & 31)); };
+	auto list_base = [&](int t) { return (unsigned)__cvta_generic_to_shared(s_lists + (t >> 5) * (CAP * 32) + (t & 31)); };
 	const unsigned segb_base = (unsigned)__cvta_generic_to_shared(&sm.seg_b[0][0]);
 
 	double du = 0.0;   // EMODE 3: this thread's share of the dPotential
@@ -1411,7 +1430,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		asm volatile("st.shared.u16 [%0], %1;" ::"r"(wp), "h"((unsigned short)v) : "memory");
 		wp += 64u;
 	};
-	unsigned wlim = lbase + 64u * (PAIR_CAP - 8);    // checked once per two groups of four
+	unsigned wlim = lbase + 64u * (CAP - 8);    // checked once per two groups of four
 	asm volatile("" : "+r"(wlim));               // opaque: rematerialising the shared-window address cost 8 instructions per group
 
 	// ---- the particle's candidate ranges: one per (y,z) row of the stencil, pruned by geometry
@@ -1431,10 +1450,11 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	const float amax = fminf(ai, pg.thr32) + ext;
 	int nseg = 0;
 	bool shifted_rows = false;
-	int rjb[PAIR_NSEG], rje[PAIR_NSEG];
-	// all eighteen look-ups of start[] are issued before any of them is used (one trip to L2 instead of nine)
+	int rjb[NROW], rje[NROW];
+	// all the look-ups of start[] are issued before any of them is used (one trip to L2 instead of nine)
 #pragma unroll
-	for (int r = 0; r < PAIR_NSEG; r++) {
+	for (int rr = 0; rr < NROW; rr++) {
+		const int r = row0 + rr;
 		const int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
 		int nz = cz + oz, ny = cy + oy;
 		bool wrapyz = nz < 0 || nz >= g.nc[2] || ny < 0 || ny >= g.nc[1];
@@ -1453,7 +1473,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		} else {
 			xlo = max(max(cx - (keep_lo ? 1 : 0), 0) - w0, 0); xhi = min(min(cx + (keep_hi ? 1 : 0), g.nc[0] - 1) - w0, d0 - 1);
 		}
-		rjb[r] = 0; rje[r] = 0;
+		rjb[rr] = 0; rje[rr] = 0;
 		// x slices: the row is sorted by x to cs / xs, read only the slices within reach of this particle in this row
 		// (conservative: the FP32 errors of the slice coordinate are ~1e-4 of a slice, the slack is 0.02)
 		int flo = xlo * xs, fhi = xhi * xs + (xs - 1);
@@ -1466,13 +1486,14 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		}
 		if (row_ok && flo <= fhi) {
 			int rowbase = fd0 * (ly + d1 * lz);
-			rjb[r] = start[rowbase + flo]; rje[r] = start[rowbase + fhi + 1];
+			rjb[rr] = start[rowbase + flo]; rje[rr] = start[rowbase + fhi + 1];
 		}
 	}
 #pragma unroll
-	for (int r = 0; r < PAIR_NSEG; r++) {
-		int jb = rjb[r];
-		const int je = rje[r];
+	for (int rr = 0; rr < NROW; rr++) {
+		const int r = row0 + rr;
+		int jb = rjb[rr];
+		const int je = rje[rr];
 		if (ENERGY_ONLY && r == 4) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
 		const int lim = (1 << PAIR_SEGBITS) - 4;
 		sm.seg_b[r][tid] = jb;
@@ -1492,7 +1513,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 				}
 			}
 		}
-		nseg = (je > jb) ? r + 1 : nseg;
+		nseg = (je > jb) ? rr + 1 : nseg;
 	}
 
 	// ---- phase 1: prefilter along the thread's own stream of ranges over the 8-byte candidate records (16-bit
@@ -1513,7 +1534,8 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		extq = (ext * ir) * ir * (1.000001f + 1.75f / (pg.rmin32 * ir));
 	}
 	const int aiqi = __float_as_int(aiq);
-	for (int sg = 0; sg < nseg; sg++) {
+	for (int sq = 0; sq < nseg; sq++) {
+		const int sg = row0 + sq;
 		const int n = sm.seg_n[sg][tid];
 		if (n == 0) continue;
 		const uint2 *cp = pos16 + sm.seg_b[sg][tid];
@@ -1562,7 +1584,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	// ---- rows and end cells seen through a periodic image (particles in the outermost cell layers only)
 	if (shifted_rows) {
 #pragma unroll 1
-		for (int s = 0; s < 27; s++) {
+		for (int s = 3 * row0; s < 3 * (row0 + NROW); s++) {
 			int r = s / 3, sub = s - 3 * r;
 			int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
 			int nz = cz + oz, ny = cy + oy;
@@ -1619,17 +1641,17 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 	if (DU) s_dup[tid] = du;   // energy terms that bypassed the list (periodic images, early drains): they travel with it
 	atomicAdd(&sm.hist[lcnt], 1);
 	__syncthreads();
-	if (tid < 32) {   // exclusive prefix over descending length (PAIR_CAP + 1 bins)
-		constexpr int PER = (PAIR_CAP + 1 + 31) / 32;
+	if (tid < 32) {   // exclusive prefix over descending length (CAP + 1 bins)
+		constexpr int PER = (CAP + 1 + 31) / 32;
 		int h[PER], sum = 0;
 #pragma unroll
-		for (int k = 0; k < PER; k++) { int c = PAIR_CAP - (tid * PER + k); h[k] = c >= 0 ? sm.hist[c] : 0; sum += h[k]; }
+		for (int k = 0; k < PER; k++) { int c = CAP - (tid * PER + k); h[k] = c >= 0 ? sm.hist[c] : 0; sum += h[k]; }
 		int inc = sum;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, d); if (tid >= d) inc += v; }
 		int run = inc - sum;
 #pragma unroll
-		for (int k = 0; k < PER; k++) { int c = PAIR_CAP - (tid * PER + k); if (c >= 0) sm.hist[c] = run; run += h[k]; }
+		for (int k = 0; k < PER; k++) { int c = CAP - (tid * PER + k); if (c >= 0) sm.hist[c] = run; run += h[k]; }
 	}
 	__syncthreads();
 	sm.order[atomicAdd(&sm.hist[lcnt], 1)] = tid;
@@ -1637,9 +1659,9 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];
-	const int io = sm.perm[o];
+	const int io = sm.perm[SPLIT == 3 ? (o & 31) : o];
 	const bool act = io < N && !(g.slab && (gid[io] & GID_GHOST));
-	if (EMODE == 0 && !act && !pg.done) return;
+	if (SPLIT == 1 && EMODE == 0 && !act && !pg.done) return;
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
 	if (DU) du = s_dup[o];
 	if (act) {
@@ -1653,7 +1675,7 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		__syncthreads();
 		double tot = block_sum(sm.part[0][tid]);
 		if (tid == 0) en.partials[blockIdx.x] = tot;
-		if (!act && !pg.done) return;
+		if (SPLIT == 1 && !act && !pg.done) return;
 	}
 	if (ENERGY_ONLY) {   // one partial sum per block, reduced deterministically by k_final_sum
 		// summed in particle order, not in the (arrival-dependent) order the lists were handed out in: the energy is
@@ -1665,22 +1687,37 @@ __global__ void __launch_bounds__(PAIR_TPB, SMD_PAIR_BLOCKS) k_pair_force2(Cnt c
 		if (tid == 0) en.partials[blockIdx.x] = tot;
 		return;
 	}
-	if (!act) {
+	int iw = io;        // the particle whose acceleration this thread writes
+	bool actw = act;
+	if (SPLIT == 3) {   // the three partial sums of a particle, added in plane order by the first warp
+		__syncthreads();
+		sm.part[0][o] = act ? ax : 0.0; sm.part[1][o] = act ? ay : 0.0; sm.part[2][o] = act ? az : 0.0;
+		__syncthreads();
+		iw = sm.perm[lane];
+		actw = wid == 0 && iw < N && !(g.slab && (gid[iw] & GID_GHOST));
+		if (!actw && !pg.done) return;
+		if (actw) {
+			ax = (sm.part[0][lane] + sm.part[0][32 + lane]) + sm.part[0][64 + lane];
+			ay = (sm.part[1][lane] + sm.part[1][32 + lane]) + sm.part[1][64 + lane];
+			az = (sm.part[2][lane] + sm.part[2][32 + lane]) + sm.part[2][64 + lane];
+		}
+	}
+	if (!actw) {
 		// (only reached with pg.done: every thread of the block takes part in the hand-over below)
 	} else if (LANGEVIN) {
-		int id = lg.gid[io] & GID_MASK;
+		int id = lg.gid[iw] & GID_MASK;
 		double u[3];
 		if (lg.ext_noise) {
 			u[0] = lg.ext_noise[3 * id]; u[1] = lg.ext_noise[3 * id + 1]; u[2] = lg.ext_noise[3 * id + 2];
 		} else {
 			philox_uniform3(lg.seed, lg.step, (uint32_t)id, u);
 		}
-		double lx = -lg.gamma * lg.vel[io] + lg.sigma * (2.0 * u[0] - 1.0);
-		double ly = -lg.gamma * lg.vel[cap + io] + lg.sigma * (2.0 * u[1] - 1.0);
-		double lz = -lg.gamma * lg.vel[2 * cap + io] + lg.sigma * (2.0 * u[2] - 1.0);
-		acc[io] = lx + ax; acc[cap + io] = ly + ay; acc[2 * cap + io] = lz + az;
+		double lx = -lg.gamma * lg.vel[iw] + lg.sigma * (2.0 * u[0] - 1.0);
+		double ly = -lg.gamma * lg.vel[cap + iw] + lg.sigma * (2.0 * u[1] - 1.0);
+		double lz = -lg.gamma * lg.vel[2 * cap + iw] + lg.sigma * (2.0 * u[2] - 1.0);
+		acc[iw] = lx + ax; acc[cap + iw] = ly + ay; acc[2 * cap + iw] = lz + az;
 	} else {
-		acc[io] += ax; acc[cap + io] += ay; acc[2 * cap + io] += az;
+		acc[iw] += ax; acc[cap + iw] += ay; acc[2 * cap + iw] += az;
 	}
 	if (pg.done) {   // this block's accelerations are complete: release its seam block
 		__threadfence();
@@ -2045,7 +2082,7 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
                                                     double *vel, double *acc, double *unw, const int *__restrict__ gid,
                                                     const int *__restrict__ slot_of, Geom g, ChainSet cs, double dt, int *bbox, int *errflag,
                                                     BeadSet bs, int slot0, SlabComm comm, int seq, int *gid_w, const int *done, int epoch,
-                                                    BinArgs bin)
+                                                    BinArgs bin, int done_per = 1)
 {
 	// done != nullptr: launched as a programmatic dependent of the pair kernel -- this block may be resident while the
 	// tail of that grid is still running and only needs the accelerations of its own 128 slots, which pair block `blk`
@@ -2056,10 +2093,12 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 	if (done) {
 		const int blk = slot0 / TPB + (int)blockIdx.x;
 		if (blk * TPB < cnt.get()) {
-			if (threadIdx.x == 0) {
+			// done_per pair blocks cover this block's slots (4 when the pair kernel runs 32 particles per block)
+			const int sub = TPB / done_per;
+			if ((int)threadIdx.x < done_per && blk * TPB + (int)threadIdx.x * sub < cnt.get()) {
 				int v;
 				do {
-					asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + blk) : "memory");
+					asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done + blk * done_per + threadIdx.x) : "memory");
 				} while (v != epoch);
 			}
 			__syncthreads();
