@@ -127,6 +127,9 @@ int smd_add_floating_base(smd_ctx *ctx, int32_t n, const int32_t *idx, const dou
 int smd_add_ztorque(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[4]);
 int smd_add_zpower(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[2]);
 int smd_add_nanocore(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C);
+/* SOLID / OFFSET_BOUNDARY / RIGIDBEND / PULLBEAD: `MD` parses and ignores them (default case of MD.cpp:414-478); registering
+ * one keeps the molecule numbering of smd_observe equal to the file's */
+int smd_add_inert(smd_ctx *ctx, int32_t kind);
 
 /* Per-type friction, the `gammaType` command (MD.cpp:134-138, Langevin::compute algorithms/langevin.h:236-281).  What the
  * reference does with it, reproduced: the type lookup is commented out (`int type=0;//p[i].type;`), so EVERY particle
@@ -200,6 +203,36 @@ int smd_arm_dpotential(smd_ctx *ctx, const double scale[3]);
  * does not apply (asymmetric tables, external noise, ...).  = smd_mc_propose + smd_arm_dpotential + smd_step + the trial. */
 int smd_step_mc(smd_ctx *ctx, int64_t first_step, int32_t nsteps, double deltaLXY, double tension, double u_fluct,
                 double u_accept, int32_t *accepted, double *dU_total, double box_out[3]);
+
+/* ---- dataExtraction::compute's geometric observables, reduced on the device (dataExtraction.h:827-1693, default build: no
+ * ANCHOR_DATA / FLAT_MEMBRANE / NANOPARTICLE blocks).  The reference walks the host arrays once per measureInterval; here the
+ * particles never leave the GPU: one call = a few short kernels + one read-back of < 1 KB.
+ *   SMD_OBS_BONDS    sums of the bond length over every BOND record (:861-893) and of cos(theta) and the two arm lengths
+ *                    over every BEND record (:895-935), with the reference's inclusive image rule
+ *   SMD_OBS_EXTENT   lo = min(size, min position), hi = max(0, max position) per axis: flicker = hi - lo (:1457-1487)
+ *   SMD_OBS_KE_HIST  adds every particle to the kinetic-energy histogram, bin = int(0.5 v^2 / 0.0001) (:1511-1520); the
+ *                    histogram lives on the device and accumulates over calls; smd_ke_histogram reads it
+ *   SMD_OBS_MSD      msd_sum[k] = sum of |unwrapped - start|^2 over the particles of molecule k, msd_count[k] their number
+ *                    (:1525-1663: BOND / BEND / BEAD records entry by entry, CHAIN blocks as index ranges, 0 for every
+ *                    other kind), k in the order of the smd_add_* calls; needs track_unwrapped and smd_msd_start
+ * Not in slab mode. */
+#define SMD_OBS_BONDS 1u
+#define SMD_OBS_EXTENT 2u
+#define SMD_OBS_KE_HIST 4u
+#define SMD_OBS_MSD 8u
+typedef struct smd_observables {
+	double lbond_sum;
+	int64_t n_bond;
+	double cos_bend_sum, lbend_sum[2];
+	int64_t n_bend;
+	double lo[3], hi[3];
+	int32_t n_molecules;     /* entries written to msd_sum / msd_count */
+} smd_observables;
+int smd_observe(smd_ctx *ctx, uint32_t what, smd_observables *out, double *msd_sum, int64_t *msd_count, int32_t msd_cap);
+/* aPStart of the reference (MD.cpp:96-105, dataExtraction.h:790-803): remember the unwrapped positions of this moment */
+int smd_msd_start(smd_ctx *ctx);
+/* kEnergyDensity (dataExtraction.h:1680-1693): *n_bins = highest populated bin + 1; counts[0 .. min(cap, *n_bins)) if not NULL */
+int smd_ke_histogram(smd_ctx *ctx, int64_t *counts, int64_t cap, int64_t *n_bins);
 
 /* read back (original particle order).  Any pointer may be NULL. */
 int smd_get_particles(smd_ctx *ctx, double *xyz, int32_t *type, double *vel);

@@ -39,13 +39,20 @@ SYMBOLS = [
     "smd_slab_connect_ptr", "smd_slab_exchange_send", "smd_slab_exchange_recv", "smd_slab_counts", "smd_slab_capacity",
     "smd_slab_get_local", "smd_slab_set_local", "smd_mc_propose", "smd_mc_accept",
     "smd_host_alloc", "smd_host_free", "smd_snapshot", "smd_snapshot_wait",
+    "smd_add_inert", "smd_observe", "smd_msd_start", "smd_ke_histogram",
 ]
+OBS_BONDS, OBS_EXTENT, OBS_KE_HIST, OBS_MSD = 1, 2, 4, 8
 
 
 class SoftMoldError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"softmold_b200 error {code}: {msg}")
         self.code = code
+
+
+class Observables(C.Structure):
+    _fields_ = [("lbond_sum", C.c_double), ("n_bond", C.c_int64), ("cos_bend_sum", C.c_double), ("lbend_sum", C.c_double * 2),
+                ("n_bend", C.c_int64), ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("n_molecules", C.c_int32)]
 
 
 class Desc(C.Structure):
@@ -143,6 +150,10 @@ def lib():
         L.smd_slab_set_local.argtypes = [vp, i32, vp, vp, vp, vp]
         L.smd_mc_propose.argtypes = [vp, dbl, dbl, vp, vp]
         L.smd_mc_accept.argtypes = [dbl, dbl, vp, vp, dbl, dbl, ip, dp]
+        L.smd_add_inert.argtypes = [vp, i32]
+        L.smd_observe.argtypes = [vp, C.c_uint32, C.POINTER(Observables), vp, vp, i32]
+        L.smd_msd_start.argtypes = [vp]
+        L.smd_ke_histogram.argtypes = [vp, vp, i64, C.POINTER(i64)]
         _lib = L
     return _lib
 
@@ -278,10 +289,13 @@ class Context:
              MOL_FLOATING_BASE: self.L.smd_add_floating_base, MOL_ZTORQUE: self.L.smd_add_ztorque,
              MOL_ZPOWERPOTENTIAL: self.L.smd_add_zpower, MOL_NANOCORE: self.L.smd_add_nanocore}.get(int(mtype))
         if int(mtype) in MOL_IGNORED:
+            self._ck(self.L.smd_add_inert(self.h, int(mtype)))
+            self.n_molecules = getattr(self, "n_molecules", 0) + 1
             return
         if f is None:
             raise SoftMoldError(SMD_ERR_UNSUPPORTED, f"molecule type {mtype} is outside the hot path")
         self._ck(f(self.h, n, _ptr(r), _ptr(c)))
+        self.n_molecules = getattr(self, "n_molecules", 0) + 1
 
     def set_gamma_type(self, gamma_type):
         g = _f64(gamma_type)
@@ -324,6 +338,26 @@ class Context:
         v = C.c_double()
         self._ck(self.L.smd_kinetic(self.h, C.byref(v)))
         return v.value
+
+    def msd_start(self):
+        self._ck(self.L.smd_msd_start(self.h))
+
+    def observe(self, what=OBS_BONDS | OBS_EXTENT):
+        """dataExtraction::compute's geometric observables reduced on the device (smd_observe): a dict with lbond_sum, n_bond,
+        cos_bend_sum, lbend_sum[2], n_bend, lo[3], hi[3] and, with OBS_MSD, msd_sum / msd_count per molecule"""
+        o = Observables()
+        nm = getattr(self, "n_molecules", 0)
+        msd, cnt = np.zeros(max(nm, 1)), np.zeros(max(nm, 1), dtype=np.int64)
+        self._ck(self.L.smd_observe(self.h, int(what), C.byref(o), _ptr(msd), _ptr(cnt), nm))
+        return {"lbond_sum": o.lbond_sum, "n_bond": o.n_bond, "cos_bend_sum": o.cos_bend_sum, "lbend_sum": np.array(o.lbend_sum[:]),
+                "n_bend": o.n_bend, "lo": np.array(o.lo[:]), "hi": np.array(o.hi[:]), "msd_sum": msd[:nm], "msd_count": cnt[:nm]}
+
+    def ke_histogram(self):
+        n = C.c_int64()
+        self._ck(self.L.smd_ke_histogram(self.h, None, 0, C.byref(n)))
+        h = np.zeros(max(n.value, 1), dtype=np.int64)
+        self._ck(self.L.smd_ke_histogram(self.h, _ptr(h), n.value, C.byref(n)))
+        return h[:n.value]
 
     def dpotential(self, scale):
         out, s = np.zeros(NTERMS), _f64(scale)

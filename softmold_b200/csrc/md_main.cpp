@@ -84,6 +84,10 @@ struct Job {
 	double time_now, temperature, box[3], terms[SMD_NTERMS], kinetic;
 	int slot;
 	int64_t ticket;
+	// kind 1: the geometric observables, already reduced on the device (smd_observe)
+	smd_observables obs;
+	std::vector<double> msd_sum;
+	std::vector<int64_t> msd_count;
 };
 
 struct Driver {
@@ -94,9 +98,7 @@ struct Driver {
 	double *xyz = nullptr, *vel = nullptr;   // borrowed from the mpd object; written by the worker only
 	int32_t *type = nullptr;
 	std::vector<Mol> mols;
-	std::vector<double> unw_start;           // aPStart of the reference (MD.cpp:96-105, dataExtraction.h:790-803)
-	bool diffusion_started = false;
-	std::vector<long> ke_hist;
+	bool diffusion_started = false;          // aPStart of the reference (MD.cpp:96-105, dataExtraction.h:790-803): smd_msd_start
 	double temperature = 0, time_now = 0;
 
 	// snapshots in flight: two page-locked buffer sets, one FIFO of jobs, one worker
@@ -124,7 +126,6 @@ struct Driver {
 		for (Slot &s : slots) {
 			ck(smd_host_alloc((void **)&s.xyz, 3 * (size_t)n * sizeof(double)), "smd_host_alloc");
 			ck(smd_host_alloc((void **)&s.vel, 3 * (size_t)n * sizeof(double)), "smd_host_alloc");
-			ck(smd_host_alloc((void **)&s.unw, 3 * (size_t)n * sizeof(double)), "smd_host_alloc");
 		}
 		if (!sync_io) worker = std::thread([this] { work(); });
 	}
@@ -136,7 +137,7 @@ struct Driver {
 			cv_job.notify_all();
 			worker.join();
 		}
-		for (Slot &s : slots) { smd_host_free(s.xyz); smd_host_free(s.vel); smd_host_free(s.unw); }
+		for (Slot &s : slots) { smd_host_free(s.xyz); smd_host_free(s.vel); }
 	}
 
 	void work()
@@ -151,14 +152,23 @@ struct Driver {
 				jobs.pop_front();
 			}
 			run(j);
-			{ std::lock_guard<std::mutex> l(mu); slots[j.slot].busy = false; }
-			cv_free.notify_all();
+			if (j.kind == 0) {
+				{ std::lock_guard<std::mutex> l(mu); slots[j.slot].busy = false; }
+				cv_free.notify_all();
+			}
 		}
 	}
 
-	// snapshot of the current state into a free buffer set + the job that consumes it
-	void submit(Job j, bool want_unw)
+	// a store job: snapshot of the current state into a free buffer set + the job that consumes it; a measure job carries
+	// its numbers with it.  One FIFO, so the files are appended in the reference's order.
+	void submit(Job j)
 	{
+		if (j.kind == 1) {
+			if (sync_io) { run(j); return; }
+			{ std::lock_guard<std::mutex> l(mu); jobs.push_back(std::move(j)); }
+			cv_job.notify_all();
+			return;
+		}
 		{
 			std::unique_lock<std::mutex> l(mu);
 			cv_free.wait(l, [this] { return !slots[0].busy || !slots[1].busy; });
@@ -166,7 +176,7 @@ struct Driver {
 			slots[j.slot].busy = true;
 		}
 		Slot &s = slots[j.slot];
-		ck(smd_snapshot(ctx, s.xyz, s.vel, want_unw ? s.unw : nullptr, &j.ticket), "smd_snapshot");
+		ck(smd_snapshot(ctx, s.xyz, s.vel, nullptr, &j.ticket), "smd_snapshot");
 		if (sync_io) {
 			run(j);
 			slots[j.slot].busy = false;
@@ -178,9 +188,9 @@ struct Driver {
 
 	void run(const Job &j)
 	{
+		if (j.kind == 1) { do_measure(j); return; }
 		ck(smd_snapshot_wait(ctx, j.ticket), "smd_snapshot_wait");
-		if (j.kind == 0) do_store(j, slots[j.slot]);
-		else do_measure(j, slots[j.slot]);
+		do_store(j, slots[j.slot]);
 	}
 
 	// Script::write + xyzFormat::store at a store step (MD.cpp:373-381)
@@ -192,7 +202,7 @@ struct Driver {
 		// has already raised one must not replace the last good checkpoint
 		if (write_mpd) ck(smd_synchronize(ctx), "state check before the checkpoint");
 		smd_get_box(ctx, j.box);
-		submit(j, false);
+		submit(j);
 	}
 
 	void do_store(const Job &j, const Slot &s)
@@ -246,7 +256,9 @@ struct Driver {
 	}
 
 	// dataExtraction::compute (dataExtraction.h:827-1693, default build: no ANCHOR_DATA / FLAT_MEMBRANE / NANOPARTICLE):
-	// the energies are reduced on the device, the geometric observables by the worker from a snapshot
+	// everything is reduced on the device -- the energies by smd_potential / smd_kinetic, the bond and bend means, the extent
+	// of the particles (flicker), the kinetic-energy histogram and the mean square displacements by smd_observe -- so a
+	// measurement moves < 1 KB to the host; the worker only appends the lines
 	void measure()
 	{
 		Job j = {};
@@ -254,98 +266,41 @@ struct Driver {
 		ck(smd_potential(ctx, j.terms), "smd_potential");
 		ck(smd_kinetic(ctx, &j.kinetic), "smd_kinetic");
 		smd_get_box(ctx, j.box);
-		submit(j, diffusion_started);
+		j.msd_sum.assign(mols.size() + 1, 0.0);
+		j.msd_count.assign(mols.size() + 1, 0);
+		ck(smd_observe(ctx, SMD_OBS_BONDS | SMD_OBS_EXTENT | SMD_OBS_KE_HIST | (diffusion_started ? SMD_OBS_MSD : 0u), &j.obs,
+		               j.msd_sum.data(), j.msd_count.data(), (int32_t)mols.size()), "smd_observe");
+		submit(std::move(j));
 	}
 
-	void do_measure(const Job &j, const Slot &sl)
+	void do_measure(const Job &j)
 	{
-		const double *xyz = sl.xyz, *vel = sl.vel, *unw = sl.unw;
 		const double *terms = j.terms, *s = j.box;
 		const double kinetic = j.kinetic, temperature = j.temperature, time_now = j.time_now;
 		double potential = 0;
 		for (int t = 0; t < SMD_NTERMS; t++) potential += terms[t];
-
-		double lBond = 0, costhetaBend = 0, lBend[2] = {0, 0};
-		int nBond = 0, nBend = 0, nBeads = 0;
-		auto image = [&](double d[3]) {
-			for (int a = 0; a < 3; a++) {
-				if (d[a] >= s[a] / 2.0) d[a] -= s[a];
-				if (d[a] <= -s[a] / 2.0) d[a] += s[a];
-			}
-		};
-		for (const Mol &m : mols) {
-			if (m.type == SMD_MOL_BOND) {
-				for (int l = 0; l < m.n; l++) {
-					int a = m.rec[2 * l], b = m.rec[2 * l + 1];
-					double d[3] = {xyz[3 * a] - xyz[3 * b], xyz[3 * a + 1] - xyz[3 * b + 1], xyz[3 * a + 2] - xyz[3 * b + 2]};
-					image(d);
-					lBond += std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-				}
-				nBond += m.n;
-			} else if (m.type == SMD_MOL_BEND) {
-				for (int l = 0; l < m.n; l++) {
-					int a = m.rec[3 * l], b = m.rec[3 * l + 1], c = m.rec[3 * l + 2];
-					double da[3] = {xyz[3 * a] - xyz[3 * b], xyz[3 * a + 1] - xyz[3 * b + 1], xyz[3 * a + 2] - xyz[3 * b + 2]};
-					double db[3] = {xyz[3 * b] - xyz[3 * c], xyz[3 * b + 1] - xyz[3 * c + 1], xyz[3 * b + 2] - xyz[3 * c + 2]};
-					image(da);
-					image(db);
-					double ra = std::sqrt(da[0] * da[0] + da[1] * da[1] + da[2] * da[2]);
-					double rb = std::sqrt(db[0] * db[0] + db[1] * db[1] + db[2] * db[2]);
-					lBend[0] += ra;
-					lBend[1] += rb;
-					costhetaBend += (da[0] * db[0] + da[1] * db[1] + da[2] * db[2]) / (ra * rb);
-				}
-				nBend += m.n;
-			} else if (m.type == SMD_MOL_BEAD || m.type == SMD_MOL_NANOCORE) {   // dataExtraction.h:936-942, :971-978
-				nBeads++;
-			}
-		}
+		const smd_observables &o = j.obs;
+		double costhetaBend = o.cos_bend_sum, lBend[2] = {o.lbend_sum[0], o.lbend_sum[1]};
+		const long long nBond = o.n_bond, nBend = o.n_bend;
+		int nBeads = 0;
+		for (const Mol &m : mols)
+			if (m.type == SMD_MOL_BEAD || m.type == SMD_MOL_NANOCORE) nBeads++;   // dataExtraction.h:936-942, :971-978
 		line(time_now, "potential_", potential);
 		line(time_now, "size_", s[0], s[1], s[2]);
-		line(time_now, "lBond_", lBond / (double)nBond);
+		line(time_now, "lBond_", o.lbond_sum / (double)nBond);
 		if (nBend > 1) { costhetaBend /= nBend; lBend[0] /= nBend; lBend[1] /= nBend; }
 		line(time_now, "bend_", costhetaBend, lBend[0], lBend[1]);
 		if (nBeads > 0) line(time_now, "beadPotential_", terms[SMD_TERM_BEAD] + terms[SMD_TERM_NANOCORE]);
 		line(time_now, "temp_", temperature);
 		line(time_now, "kinetic_", kinetic);
-
-		double lo[3] = {s[0], s[1], s[2]}, hi[3] = {0, 0, 0};
-		for (int i = 0; i < n; i++)
-			for (int a = 0; a < 3; a++) {
-				if (xyz[3 * i + a] < lo[a]) lo[a] = xyz[3 * i + a];
-				if (xyz[3 * i + a] > hi[a]) hi[a] = xyz[3 * i + a];
-			}
-		line(time_now, "flicker_", hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
-
-		const double part = 0.0001;   // kEnergyDensityPartition, dataExtraction.h:390
-		for (int i = 0; i < n; i++) {
-			size_t b = (size_t)(0.5 * (vel[3 * i] * vel[3 * i] + vel[3 * i + 1] * vel[3 * i + 1] + vel[3 * i + 2] * vel[3 * i + 2]) / part);
-			if (b >= ke_hist.size()) ke_hist.resize(b + 1, 0);
-			ke_hist[b]++;
-		}
-
-		if (j.diffusion) {   // dataExtraction.h:1525-1663
+		line(time_now, "flicker_", o.hi[0] - o.lo[0], o.hi[1] - o.lo[1], o.hi[2] - o.lo[2]);
+		if (j.diffusion) {   // dataExtraction.h:1525-1663: one column per BOND / BEND / BEAD / CHAIN molecule with particles
 			std::ofstream f("meanSquareDisplacement_" + name + ".dat", std::ios::app | std::ios::out);
 			f << time_now;
-			auto sq = [&](int k) {
-				double d0 = unw[3 * k] - unw_start[3 * k], d1 = unw[3 * k + 1] - unw_start[3 * k + 1], d2 = unw[3 * k + 2] - unw_start[3 * k + 2];
-				return d0 * d0 + d1 * d1 + d2 * d2;
-			};
-			for (const Mol &m : mols) {
-				double msd = 0;
-				int np = 0;
-				if (m.type == SMD_MOL_BOND || m.type == SMD_MOL_BEND || m.type == SMD_MOL_BEAD) {
-					for (int l = 0; l < m.n; l++)
-						for (int k = 0; k < m.width; k++) msd += sq(m.rec[m.width * l + k]);
-					np = m.n * m.width;
-				} else if (m.type == SMD_MOL_CHAIN) {
-					for (int l = 0; l < m.n; l++) {
-						int st = m.rec[3 * l], nch = m.rec[3 * l + 1], len = m.rec[3 * l + 2];
-						for (int k = st; k < st + len * nch; k++) msd += sq(k);
-						np += len * nch;
-					}
-				}
-				if (np != 0) f << '\t' << (msd / (double)np);
+			for (size_t k = 0; k < mols.size(); k++) {
+				const int t = mols[k].type;
+				if (t != SMD_MOL_BOND && t != SMD_MOL_BEND && t != SMD_MOL_BEAD && t != SMD_MOL_CHAIN) continue;
+				if (j.msd_count[k] != 0) f << '\t' << (j.msd_sum[k] / (double)j.msd_count[k]);
 			}
 			f << '\n';
 		}
@@ -354,14 +309,17 @@ struct Driver {
 	void start_diffusion()
 	{
 		if (diffusion_started) return;
-		unw_start.resize(3 * (size_t)n);
-		ck(smd_get_unwrapped(ctx, unw_start.data()), "smd_get_unwrapped");
+		ck(smd_msd_start(ctx), "smd_msd_start");
 		diffusion_started = true;
 	}
 
 	void finish()
 	{
 		std::ofstream f("kEnergyDensity_" + name + ".dat", std::ios::out);
+		int64_t nb = 0;
+		ck(smd_ke_histogram(ctx, nullptr, 0, &nb), "smd_ke_histogram");
+		std::vector<int64_t> ke_hist((size_t)nb);
+		if (nb) ck(smd_ke_histogram(ctx, ke_hist.data(), nb, &nb), "smd_ke_histogram");
 		long sum = 0;
 		for (long c : ke_hist) sum += c;
 		for (size_t i = 0; i < ke_hist.size(); i++)

@@ -573,7 +573,7 @@ extern "C" int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, in
 		case SMD_MOL_ZPOWERPOTENTIAL: rc = smd_add_zpower(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
 		case SMD_MOL_NANOCORE: rc = smd_add_nanocore(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
 		// parsed and written back by the reference, but `MD` does nothing with them (default case of MD.cpp:414-478)
-		case SMD_MOL_SOLID: case SMD_MOL_OFFSET_BOUNDARY: case SMD_MOL_RIGIDBEND: case SMD_MOL_PULLBEAD: rc = SMD_OK; break;
+		case SMD_MOL_SOLID: case SMD_MOL_OFFSET_BOUNDARY: case SMD_MOL_RIGIDBEND: case SMD_MOL_PULLBEAD: rc = smd_add_inert(ctx, mol.type); break;
 		default: rc = SMD_ERR_UNSUPPORTED;
 		}
 		if (rc) return rc;

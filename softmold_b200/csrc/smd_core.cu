@@ -434,6 +434,11 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
 	if (ctx->pair_done) cudaFree(ctx->pair_done);
 	if (ctx->du_partials) cudaFree(ctx->du_partials);
+	if (ctx->obs_buf) cudaFree(ctx->obs_buf);
+	if (ctx->obs_host) cudaFreeHost(ctx->obs_host);
+	if (ctx->ke_bins) cudaFree(ctx->ke_bins);
+	if (ctx->ke_overflow) cudaFree(ctx->ke_overflow);
+	if (ctx->msd_start) cudaFree(ctx->msd_start);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 	return SMD_OK;
@@ -648,6 +653,7 @@ extern "C" int smd_add_chain(smd_ctx *ctx, int32_t n_blocks, const int32_t *bloc
 		for (int k = 0; k < 4; k++) cb.c[k] = c[k];
 		ctx->chains.push_back(cb);
 	}
+	ctx->mol_order.push_back({SMD_MOL_CHAIN, (int)ctx->chains.size() - n_blocks, n_blocks});
 	ctx->n_molecules++;
 	return SMD_OK;
 }
@@ -675,6 +681,7 @@ extern "C" int smd_add_bonds(smd_ctx *ctx, int32_t n, const int32_t *ij, const d
 	rc = upload_list<int>(ctx, ij, 2 * (size_t)n, &b.d_ij);
 	if (rc) return rc;
 	ctx->bonds.push_back(b);
+	ctx->mol_order.push_back({SMD_MOL_BOND, (int)ctx->bonds.size() - 1, 1});
 	ctx->n_molecules++;
 	return SMD_OK;
 }
@@ -691,6 +698,7 @@ extern "C" int smd_add_bends(smd_ctx *ctx, int32_t n, const int32_t *ijk, const 
 	rc = upload_list<int>(ctx, ijk, 3 * (size_t)n, &b.d_ijk);
 	if (rc) return rc;
 	ctx->bends.push_back(b);
+	ctx->mol_order.push_back({SMD_MOL_BEND, (int)ctx->bends.size() - 1, 1});
 	ctx->n_molecules++;
 	return SMD_OK;
 }
@@ -707,6 +715,7 @@ extern "C" int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const do
 	rc = upload_list<int>(ctx, cj, 2 * (size_t)n, &b.d_cj);
 	if (rc) return rc;
 	ctx->balls.push_back(b);
+	ctx->mol_order.push_back({SMD_MOL_BALL, (int)ctx->balls.size() - 1, 1});
 	ctx->n_molecules++;
 	return SMD_OK;
 }
@@ -734,6 +743,7 @@ static int add_field(smd_ctx *ctx, int kind, int32_t n, const int32_t *idx, cons
 		CK(cudaMemcpy(f.d_C, C, nC * sizeof(double), cudaMemcpyHostToDevice));
 	}
 	ctx->fields.push_back(f);
+	ctx->mol_order.push_back({kind, (int)ctx->fields.size() - 1, 1});
 	ctx->n_molecules++;
 	return SMD_OK;
 }
@@ -858,6 +868,7 @@ extern "C" int smd_add_beads(smd_ctx *ctx, int32_t n, const int32_t *idx, const 
 	CK(cudaMalloc(&b.d_C, nc * sizeof(double)));
 	CK(cudaMemcpy(b.d_C, C, nc * sizeof(double), cudaMemcpyHostToDevice));
 	ctx->beads.push_back(b);
+	ctx->mol_order.push_back({SMD_MOL_BEAD, (int)ctx->beads.size() - 1, 1});
 	ctx->n_molecules++;
 	return rebuild_bead_lists(ctx);
 }
@@ -1724,6 +1735,191 @@ extern "C" int smd_get_forces(smd_ctx *ctx, double *acc)
 	LAUNCH(k_export_soa3, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->acc, ctx->gid[ctx->cur], ctx->stage);
 	CK(cudaMemcpyAsync(acc, ctx->stage, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	return check_device_errors(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ observables
+// SOLID / OFFSET_BOUNDARY / RIGIDBEND / PULLBEAD: parsed and ignored by `MD` (default case of MD.cpp:414-478); registered so
+// that molecule k of smd_observe is molecule k of the file
+extern "C" int smd_add_inert(smd_ctx *ctx, int32_t kind)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(kind == SMD_MOL_SOLID || kind == SMD_MOL_OFFSET_BOUNDARY || kind == SMD_MOL_RIGIDBEND || kind == SMD_MOL_PULLBEAD,
+	        "smd_add_inert: only the kinds MD itself ignores");
+	ctx->mol_order.push_back({kind, 0, 0});
+	ctx->n_molecules++;
+	return SMD_OK;
+}
+
+static const long long KE_BINS = 1ll << 21;      // 0.0001 per bin: kinetic energies up to 209 (|v| = 20 at unit mass)
+static const int KE_OVERFLOW = 4096;
+static const double KE_PARTITION = 0.0001;       // kEnergyDensityPartition, dataExtraction.h:390
+
+static int obs_alloc(smd_ctx *ctx, int words)
+{
+	if (ctx->obs_words >= words) return SMD_OK;
+	if (ctx->obs_buf) cudaFree(ctx->obs_buf);
+	if (ctx->obs_host) cudaFreeHost(ctx->obs_host);
+	ctx->obs_buf = nullptr; ctx->obs_host = nullptr; ctx->obs_words = 0;
+	CK(cudaMalloc(&ctx->obs_buf, (size_t)words * 8));
+	CK(cudaMemsetAsync(ctx->obs_buf, 0, (size_t)words * 8, ctx->stream));
+	CK(cudaMallocHost(&ctx->obs_host, (size_t)words * 8));
+	ctx->obs_words = words;
+	return SMD_OK;
+}
+
+extern "C" int smd_msd_start(smd_ctx *ctx)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(ctx->particles_set && ctx->unw[0], "unwrapped positions are not tracked");
+	REQUIRE(!ctx->slab, "slab: observables are not reduced per rank");
+	CK(cudaSetDevice(ctx->device));
+	const int N = ctx->N;
+	if (!ctx->msd_start) CK(cudaMalloc(&ctx->msd_start, 3 * (size_t)N * sizeof(double)));
+	LAUNCH(k_obs_msd_start, nblk(N, TPB), TPB, 0, N, ctx->cap, ctx->unw[ctx->cur], ctx->gid[ctx->cur], ctx->msd_start);
+	return SMD_OK;
+}
+
+extern "C" int smd_observe(smd_ctx *ctx, uint32_t what, smd_observables *out, double *msd_sum, int64_t *msd_count, int32_t msd_cap)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(out && ctx->particles_set, "bad call");
+	REQUIRE(!ctx->slab, "slab: observables are not reduced per rank");
+	const bool msd = (what & SMD_OBS_MSD) != 0;
+	REQUIRE(!msd || (ctx->msd_start && ctx->unw[0]), "SMD_OBS_MSD: smd_msd_start first (and track_unwrapped)");
+	REQUIRE(!msd || (msd_sum && msd_count && msd_cap >= ctx->n_molecules), "SMD_OBS_MSD: one entry per molecule");
+	CK(cudaSetDevice(ctx->device));
+	const int N = ctx->N;
+	const Particle *pos = ctx->pos[ctx->pcur];
+	// slots of 8 bytes: [0..5] extent keys, [6] histogram overflow count, [8 ..] sums (one per launch below)
+	int nsum = 0;
+	nsum += (int)ctx->bonds.size() + 3 * (int)ctx->bends.size();
+	nsum += (int)ctx->chains.size() + (int)ctx->bonds.size() + (int)ctx->bends.size() + (int)ctx->beads.size();
+	int rc = obs_alloc(ctx, 8 + nsum + 8);
+	if (rc) return rc;
+	double *sums = reinterpret_cast<double *>(ctx->obs_buf + 8);
+	int slot = 0;
+	memset(out, 0, sizeof *out);
+
+	std::vector<int> bond_slots, bend_slots;
+	if (what & SMD_OBS_BONDS) {
+		for (auto &b : ctx->bonds) {
+			if (b.n <= 0) continue;
+			const int nb = nblk(b.n, TPB);
+			LAUNCH(k_obs_bond, nb, TPB, 0, b.n, b.d_ij, pos, ctx->slot_of, ctx->geom, ctx->partials);
+			LAUNCH(k_final_sum, 1, 256, 0, nb, ctx->partials, sums, slot, 1.0);
+			bond_slots.push_back(slot++);
+			out->n_bond += b.n;
+		}
+		for (auto &b : ctx->bends) {
+			if (b.n <= 0) continue;
+			const int nb = nblk(b.n, TPB);
+			REQUIRE(3 * (long long)nb <= MAX_PARTIALS, "BEND list too long for the partial-sum buffer");
+			LAUNCH(k_obs_bend, nb, TPB, 0, b.n, b.d_ijk, pos, ctx->slot_of, ctx->geom, ctx->partials);
+			for (int q = 0; q < 3; q++) LAUNCH(k_final_sum, 1, 256, 0, nb, ctx->partials + (size_t)q * nb, sums, slot + q, 1.0);
+			bend_slots.push_back(slot);
+			slot += 3;
+			out->n_bend += b.n;
+		}
+	}
+	if (what & (SMD_OBS_EXTENT | SMD_OBS_KE_HIST)) {
+		ObsHist h = {nullptr, 0, nullptr, 0, nullptr};
+		if (what & SMD_OBS_KE_HIST) {
+			if (!ctx->ke_bins) {
+				CK(cudaMalloc(&ctx->ke_bins, (size_t)KE_BINS * 8));
+				CK(cudaMemsetAsync(ctx->ke_bins, 0, (size_t)KE_BINS * 8, ctx->stream));
+				CK(cudaMalloc(&ctx->ke_overflow, (size_t)KE_OVERFLOW * 8));
+			}
+			CK(cudaMemsetAsync(ctx->obs_buf + 6, 0, 8, ctx->stream));
+			h.bins = ctx->ke_bins; h.cap = KE_BINS; h.overflow = ctx->ke_overflow; h.overflow_cap = KE_OVERFLOW;
+			h.n_overflow = reinterpret_cast<int *>(ctx->obs_buf + 6);
+		}
+		LAUNCH(k_obs_init, 1, 1, 0, ctx->obs_buf, ctx->geom.box[0], ctx->geom.box[1], ctx->geom.box[2]);
+		LAUNCH(k_obs_particles, std::min(nblk(N, 256), 1184), 256, 0, cnt_of(ctx), ctx->cap, pos, ctx->vel[ctx->cur], ctx->gid[ctx->cur],
+		       ctx->obs_buf, h, KE_PARTITION);
+	}
+	struct MsdSlot { int mol, slot; };
+	std::vector<MsdSlot> msd_slots;
+	if (msd) {
+		const double *unw = ctx->unw[ctx->cur];
+		for (int k = 0; k < ctx->n_molecules; k++) {
+			msd_sum[k] = 0.0; msd_count[k] = 0;
+			const smd_ctx::MolRef &r = ctx->mol_order[k];
+			auto run = [&](int n, const int *idx, int first) -> int {
+				if (n <= 0) return SMD_OK;
+				const int nb = nblk(n, TPB);
+				LAUNCH(k_obs_msd, nb, TPB, 0, n, idx, first, N, ctx->cap, unw, ctx->slot_of, ctx->msd_start, ctx->partials);
+				LAUNCH(k_final_sum, 1, 256, 0, nb, ctx->partials, sums, slot, 1.0);
+				msd_slots.push_back({k, slot++});
+				msd_count[k] += n;
+				return SMD_OK;
+			};
+			if (r.kind == SMD_MOL_CHAIN) {
+				for (int j = r.first; j < r.first + r.count; j++)
+					if ((rc = run(ctx->chains[j].nChains * ctx->chains[j].len, nullptr, ctx->chains[j].start))) return rc;
+			} else if (r.kind == SMD_MOL_BOND) {
+				if ((rc = run(2 * ctx->bonds[r.first].n, ctx->bonds[r.first].d_ij, 0))) return rc;
+			} else if (r.kind == SMD_MOL_BEND) {
+				if ((rc = run(3 * ctx->bends[r.first].n, ctx->bends[r.first].d_ijk, 0))) return rc;
+			} else if (r.kind == SMD_MOL_BEAD) {
+				if ((rc = run(ctx->beads[r.first].nOwn, ctx->beads[r.first].d_beads, 0))) return rc;
+			}
+		}
+	}
+	CK(cudaMemcpyAsync(ctx->obs_host, ctx->obs_buf, (size_t)(8 + slot) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	int novf = 0;
+	if (what & SMD_OBS_KE_HIST) {
+		// (the overflow list is read only when it is not empty: one more small copy, practically never)
+	}
+	rc = check_device_errors(ctx);   // synchronises
+	if (rc) return rc;
+	const double *hs = reinterpret_cast<const double *>(ctx->obs_host + 8);
+	for (int sl : bond_slots) out->lbond_sum += hs[sl];
+	for (int sl : bend_slots) { out->cos_bend_sum += hs[sl]; out->lbend_sum[0] += hs[sl + 1]; out->lbend_sum[1] += hs[sl + 2]; }
+	if (what & (SMD_OBS_EXTENT | SMD_OBS_KE_HIST)) {
+		auto unkey = [](unsigned long long k) {
+			unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+			double v; memcpy(&v, &b, 8); return v;
+		};
+		for (int a = 0; a < 3; a++) { out->lo[a] = unkey(ctx->obs_host[a]); out->hi[a] = unkey(ctx->obs_host[3 + a]); }
+	}
+	if (what & SMD_OBS_KE_HIST) {
+		novf = (int)(ctx->obs_host[6] & 0xffffffffull);
+		REQUIRE(novf <= KE_OVERFLOW, "kinetic-energy histogram: more than 4096 particles beyond 0.5 v^2 = 209 (diverged?)");
+		if (novf > 0) {
+			std::vector<unsigned long long> ov((size_t)novf);
+			CK(cudaMemcpy(ov.data(), ctx->ke_overflow, (size_t)novf * 8, cudaMemcpyDeviceToHost));
+			for (unsigned long long b : ov) {
+				bool found = false;
+				for (auto &pr : ctx->ke_spill) if (pr.first == (long long)b) { pr.second++; found = true; break; }
+				if (!found) ctx->ke_spill.push_back({(long long)b, 1});
+			}
+		}
+	}
+	for (auto &ms : msd_slots) msd_sum[ms.mol] += hs[ms.slot];
+	out->n_molecules = msd ? ctx->n_molecules : 0;
+	return SMD_OK;
+}
+
+extern "C" int smd_ke_histogram(smd_ctx *ctx, int64_t *counts, int64_t cap, int64_t *n_bins)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n_bins, "bad call");
+	*n_bins = 0;
+	if (!ctx->ke_bins) return SMD_OK;   // nothing observed yet
+	CK(cudaSetDevice(ctx->device));
+	std::vector<unsigned long long> h((size_t)KE_BINS);
+	CK(cudaMemcpyAsync(h.data(), ctx->ke_bins, (size_t)KE_BINS * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	long long top = -1;
+	for (long long b = KE_BINS - 1; b >= 0; b--) if (h[(size_t)b]) { top = b; break; }
+	for (auto &pr : ctx->ke_spill) top = std::max(top, pr.first);
+	*n_bins = top + 1;
+	if (counts) {
+		const long long n = std::min<long long>(cap, top + 1);
+		for (long long b = 0; b < n; b++) counts[b] = b < KE_BINS ? (int64_t)h[(size_t)b] : 0;
+		for (auto &pr : ctx->ke_spill) if (pr.first < n) counts[pr.first] += pr.second;
+	}
+	return SMD_OK;
 }
 
 extern "C" int smd_get_unwrapped(smd_ctx *ctx, double *xyz)

@@ -201,6 +201,16 @@ struct smd_ctx {
 	std::vector<smd::BeadMol> beads;
 	std::vector<smd::FieldMol> fields;
 	int n_molecules;
+	struct MolRef { int kind, first, count; };   // molecule k of the smd_add_* order: kind + its entries in the vector of that kind
+	std::vector<MolRef> mol_order;
+
+	// device-side observables (smd_observe)
+	unsigned long long *obs_buf = nullptr;   // [0..5] extent keys, [6] overflow count, [8 ..] sums
+	unsigned long long *obs_host = nullptr;  // pinned mirror
+	int obs_words = 0;
+	unsigned long long *ke_bins = nullptr, *ke_overflow = nullptr;
+	std::vector<std::pair<long long, long long>> ke_spill;   // (bin, count) beyond the device table
+	double *msd_start = nullptr;             // [3][N] by original index
 
 	// noise
 	bool sigma_frozen = false;          // per-type friction path: noise amplitude fixed at its first temperature

@@ -2762,4 +2762,134 @@ __global__ void __launch_bounds__(TPB) k_export_cells(int N, const Particle *pos
 	rank[id] = r;
 }
 
+// ------------------------------------------------------------------------------------------------ observables
+// dataExtraction::compute's geometric observables reduced on the device: bond / bend means
+// (dataExtraction.h:861-937), flicker = extent of the particles (:1457-1487), the kinetic-energy histogram (:1511-1520),
+// the mean square displacement per molecule (:1525-1663).  Sums: one partial per block, then k_final_sum (deterministic).
+
+// order-preserving map double -> unsigned 64-bit, so that atomicMin / atomicMax do the comparison
+__device__ __forceinline__ unsigned long long obs_key(double v)
+{
+	unsigned long long b = (unsigned long long)__double_as_longlong(v);
+	return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+struct ObsHist { unsigned long long *bins; long long cap; unsigned long long *overflow; int overflow_cap; int *n_overflow; };
+
+// ext[0..2] start at the box size, ext[3..5] at 0: the reference's initial values (dataExtraction.h:1457-1460)
+__global__ void k_obs_init(unsigned long long *ext, double bx, double by, double bz)
+{
+	ext[0] = obs_key(bx); ext[1] = obs_key(by); ext[2] = obs_key(bz);
+	ext[3] = ext[4] = ext[5] = obs_key(0.0);
+}
+
+// one pass over the particles: extent (min / max per axis) and, if hist.bins, the kinetic-energy histogram
+// bin = int(0.5 v^2 / partition); a bin beyond the table goes to a short overflow list the host merges
+__global__ void __launch_bounds__(256) k_obs_particles(Cnt cnt, int cap, const Particle *__restrict__ pos, const double *__restrict__ vel,
+                                                        const int *__restrict__ gid, unsigned long long *ext, ObsHist hist, double partition)
+{
+	const int N = cnt.get();
+	unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
+	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < N; s += gridDim.x * blockDim.x) {
+		if (gid[s] & GID_GHOST) continue;
+		const Particle p = load_particle(pos + s);
+		const double c[3] = {p.x, p.y, p.z};
+#pragma unroll
+		for (int a = 0; a < 3; a++) { unsigned long long k = obs_key(c[a]); lo[a] = min(lo[a], k); hi[a] = max(hi[a], k); }
+		if (hist.bins) {
+			const double vx = vel[s], vy = vel[cap + s], vz = vel[2 * cap + s];
+			const long long b = (long long)(0.5 * (vx * vx + vy * vy + vz * vz) / partition);
+			if (b >= 0 && b < hist.cap) atomicAdd(hist.bins + b, 1ull);
+			else {
+				int k = atomicAdd(hist.n_overflow, 1);
+				if (k < hist.overflow_cap) hist.overflow[k] = (unsigned long long)b;
+			}
+		}
+	}
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+			hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+		}
+		if ((threadIdx.x & 31) == 0) {
+			if (lo[a] != ~0ull) atomicMin(ext + a, lo[a]);
+			if (hi[a] != 0ull) atomicMax(ext + 3 + a, hi[a]);
+		}
+	}
+}
+
+// the reference's image rule for its bond statistics (dataExtraction.h:876-884): both comparisons inclusive
+__device__ __forceinline__ double obs_image(double d, double L)
+{
+	if (d >= L / 2.0) d -= L;
+	if (d <= -L / 2.0) d += L;
+	return d;
+}
+
+// BOND records: sum of the bond lengths (dataExtraction.h:861-893)
+__global__ void __launch_bounds__(TPB) k_obs_bond(int n, const int *__restrict__ ij, const Particle *__restrict__ pos,
+                                                  const int *__restrict__ slot_of, Geom g, double *partials)
+{
+	const int l = blockIdx.x * blockDim.x + threadIdx.x;
+	double r = 0.0;
+	if (l < n) {
+		const Particle a = load_particle(pos + slot_of[ij[2 * l]]), b = load_particle(pos + slot_of[ij[2 * l + 1]]);
+		const double dx = obs_image(a.x - b.x, g.box[0]), dy = obs_image(a.y - b.y, g.box[1]), dz = obs_image(a.z - b.z, g.box[2]);
+		r = sqrt(dx * dx + dy * dy + dz * dz);
+	}
+	r = block_sum(r);
+	if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+
+// BEND records: sums of cos(theta) and of the two arm lengths (dataExtraction.h:895-935); partials[q * gridDim.x + block]
+__global__ void __launch_bounds__(TPB) k_obs_bend(int n, const int *__restrict__ ijk, const Particle *__restrict__ pos,
+                                                  const int *__restrict__ slot_of, Geom g, double *partials)
+{
+	const int l = blockIdx.x * blockDim.x + threadIdx.x;
+	double ct = 0.0, ra = 0.0, rb = 0.0;
+	if (l < n) {
+		const Particle a = load_particle(pos + slot_of[ijk[3 * l]]), b = load_particle(pos + slot_of[ijk[3 * l + 1]]),
+		               c = load_particle(pos + slot_of[ijk[3 * l + 2]]);
+		const double ax = obs_image(a.x - b.x, g.box[0]), ay = obs_image(a.y - b.y, g.box[1]), az = obs_image(a.z - b.z, g.box[2]);
+		const double bx = obs_image(b.x - c.x, g.box[0]), by = obs_image(b.y - c.y, g.box[1]), bz = obs_image(b.z - c.z, g.box[2]);
+		ra = sqrt(ax * ax + ay * ay + az * az);
+		rb = sqrt(bx * bx + by * by + bz * bz);
+		ct = (ax * bx + ay * by + az * bz) / (ra * rb);
+	}
+	ct = block_sum(ct);
+	if (threadIdx.x == 0) partials[blockIdx.x] = ct;
+	ra = block_sum(ra);
+	if (threadIdx.x == 0) partials[gridDim.x + blockIdx.x] = ra;
+	rb = block_sum(rb);
+	if (threadIdx.x == 0) partials[2 * gridDim.x + blockIdx.x] = rb;
+}
+
+// aPStart (MD.cpp:96-105): the unwrapped positions at the start of the diffusion measurement, by original index, SoA [3][N]
+__global__ void __launch_bounds__(TPB) k_obs_msd_start(int N, int cap, const double *__restrict__ unw, const int *__restrict__ gid, double *start)
+{
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= N) return;
+	const int id = gid[s] & GID_MASK;
+	start[id] = unw[s]; start[N + id] = unw[cap + s]; start[2 * N + id] = unw[2 * cap + s];
+}
+
+// sum of |unwrapped - start|^2 over the entries of one molecule: idx != null: the list idx[0 .. n) of original indices (an
+// index listed twice counts twice, as in the reference's loop over the records); else the range first .. first + n
+__global__ void __launch_bounds__(TPB) k_obs_msd(int n, const int *__restrict__ idx, int first, int N, int cap, const double *__restrict__ unw,
+                                                 const int *__restrict__ slot_of, const double *__restrict__ start, double *partials)
+{
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	double r = 0.0;
+	if (e < n) {
+		const int id = idx ? idx[e] : first + e;
+		const int s = slot_of[id];
+		const double d0 = unw[s] - start[id], d1 = unw[cap + s] - start[N + id], d2 = unw[2 * cap + s] - start[2 * N + id];
+		r = d0 * d0 + d1 * d1 + d2 * d2;
+	}
+	r = block_sum(r);
+	if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+
 } // namespace smd
