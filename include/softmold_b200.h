@@ -177,6 +177,11 @@ int smd_kinetic(smd_ctx *ctx, double *out);
 /* CellOpt::computeDPotential (cellOpt.h:1043-1180) + Blob::do*DPotential (system.h:3280-3757) for the proposed
  * component-wise scaling of the box (MD.cpp:608-675).  out_terms[SMD_NTERMS]. */
 int smd_dpotential(smd_ctx *ctx, const double scale[3], double *out_terms);
+/* the same sums left ON THE DEVICE: *d_terms = device pointer to SMD_NTERMS doubles, valid until the next energy call of this
+ * context, written in stream order on smd_stream() -- nothing is copied and nothing waits.  For multi-GPU box moves: the
+ * slab driver all-reduces this buffer in place (NCCL, ordered on the same stream) and reads the total back once, instead of
+ * one device-to-host copy per rank followed by a host-staged all-reduce (MD.cpp:617-669 across ranks). */
+int smd_dpotential_device(smd_ctx *ctx, const double scale[3], double **d_terms);
 
 /* accepted box move: p *= scale, CellOpt::resize / Verlet::resize / setSize (MD.cpp:697-712, cellOpt.h:1525-1570) */
 int smd_rescale(smd_ctx *ctx, const double scale[3], const double new_box[3]);

@@ -39,7 +39,7 @@ SYMBOLS = [
     "smd_slab_connect_ptr", "smd_slab_exchange_send", "smd_slab_exchange_recv", "smd_slab_counts", "smd_slab_capacity",
     "smd_slab_get_local", "smd_slab_set_local", "smd_mc_propose", "smd_mc_accept",
     "smd_host_alloc", "smd_host_free", "smd_snapshot", "smd_snapshot_wait",
-    "smd_add_inert", "smd_observe", "smd_msd_start", "smd_ke_histogram",
+    "smd_add_inert", "smd_observe", "smd_msd_start", "smd_ke_histogram", "smd_dpotential_device",
 ]
 OBS_BONDS, OBS_EXTENT, OBS_KE_HIST, OBS_MSD = 1, 2, 4, 8
 
@@ -150,6 +150,7 @@ def lib():
         L.smd_slab_set_local.argtypes = [vp, i32, vp, vp, vp, vp]
         L.smd_mc_propose.argtypes = [vp, dbl, dbl, vp, vp]
         L.smd_mc_accept.argtypes = [dbl, dbl, vp, vp, dbl, dbl, ip, dp]
+        L.smd_dpotential_device.argtypes = [vp, vp, C.POINTER(vp)]
         L.smd_add_inert.argtypes = [vp, i32]
         L.smd_observe.argtypes = [vp, C.c_uint32, C.POINTER(Observables), vp, vp, i32]
         L.smd_msd_start.argtypes = [vp]
@@ -338,6 +339,13 @@ class Context:
         v = C.c_double()
         self._ck(self.L.smd_kinetic(self.h, C.byref(v)))
         return v.value
+
+    def dpotential_device(self, scale):
+        """smd_dpotential_device: the dPotential terms stay on the device; returns the device address of NTERMS doubles
+        (written in stream order on self.stream(), nothing waits)"""
+        s, p = _f64(scale), C.c_void_p()
+        self._ck(self.L.smd_dpotential_device(self.h, _ptr(s), C.byref(p)))
+        return p.value
 
     def msd_start(self):
         self._ck(self.L.smd_msd_start(self.h))

@@ -434,6 +434,7 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	for (auto e : ctx->prof_free) cudaEventDestroy(e);
 	if (ctx->pair_done) cudaFree(ctx->pair_done);
 	if (ctx->du_partials) cudaFree(ctx->du_partials);
+	if (ctx->terms_dev) cudaFree(ctx->terms_dev);
 	if (ctx->obs_buf) cudaFree(ctx->obs_buf);
 	if (ctx->obs_host) cudaFreeHost(ctx->obs_host);
 	if (ctx->ke_bins) cudaFree(ctx->ke_bins);
@@ -1401,7 +1402,7 @@ static int finish_sum(smd_ctx *ctx, int nparts, int slot, double factor)
 
 // MODE 1 potential, 2 dPotential; results accumulate on the host per term
 template <int MODE>
-static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
+static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms, bool on_device = false)
 {
 	int rc = ready(ctx);
 	if (rc) return rc;
@@ -1484,6 +1485,14 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms)
 			if (frc) return frc;
 		}
 	}
+	if (on_device) {   // the terms stay on the device (ctx->terms_dev), nothing waits: smd_dpotential_device
+		SlotTerms st;
+		st.n = slot;
+		for (int k = 0; k < slot; k++) st.term[k] = (signed char)term_of_slot[k];
+		if (!ctx->terms_dev) CK(cudaMalloc(&ctx->terms_dev, SMD_NTERMS * sizeof(double)));
+		LAUNCH(k_fold_terms, 1, 32, 0, st, ctx->scalars, ctx->terms_dev, SMD_NTERMS);
+		return SMD_OK;
+	}
 	CK(cudaMemcpyAsync(ctx->h_pinned, ctx->scalars, slot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	rc = check_device_errors(ctx);
 	if (rc) return rc;
@@ -1504,6 +1513,15 @@ extern "C" int smd_dpotential(smd_ctx *ctx, const double scale[3], double *out_t
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(out_terms && scale, "null argument");
 	return energy_terms<2>(ctx, scale, out_terms);
+}
+
+extern "C" int smd_dpotential_device(smd_ctx *ctx, const double scale[3], double **d_terms)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(d_terms && scale, "null argument");
+	int rc = energy_terms<2>(ctx, scale, nullptr, true);
+	*d_terms = ctx->terms_dev;
+	return rc;
 }
 
 extern "C" int smd_kinetic(smd_ctx *ctx, double *out)
@@ -1757,6 +1775,7 @@ static const double KE_PARTITION = 0.0001;       // kEnergyDensityPartition, dat
 static int obs_alloc(smd_ctx *ctx, int words)
 {
 	if (ctx->obs_words >= words) return SMD_OK;
+	if (ctx->terms_dev) cudaFree(ctx->terms_dev);
 	if (ctx->obs_buf) cudaFree(ctx->obs_buf);
 	if (ctx->obs_host) cudaFreeHost(ctx->obs_host);
 	ctx->obs_buf = nullptr; ctx->obs_host = nullptr; ctx->obs_words = 0;

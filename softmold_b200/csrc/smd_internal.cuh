@@ -225,6 +225,7 @@ struct smd_ctx {
 	double *stage;     // [N][3] staging in original order
 	int *istage;       // [N]
 	double *h_pinned;  // pinned host scratch (scalars)
+	double *terms_dev = nullptr;   // [SMD_NTERMS] result of smd_dpotential_device
 
 	long long launches, rebuilds;
 

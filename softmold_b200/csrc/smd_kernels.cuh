@@ -203,6 +203,15 @@ __global__ void __launch_bounds__(256) k_final_sum(int n, const double *partials
 	if (threadIdx.x == 0) out[slot] = e * factor;
 }
 
+// smd_dpotential_device: the per-launch sums of an energy evaluation folded into one value per term, on the device
+struct SlotTerms { int n; signed char term[64]; };
+__global__ void k_fold_terms(SlotTerms st, const double *scalars, double *terms, int nterms)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	for (int t = 0; t < nterms; t++) terms[t] = 0.0;
+	for (int k = 0; k < st.n; k++) terms[st.term[k]] += scalars[k];   // the host's order (energy_terms): bit-identical sums
+}
+
 // accepted box move: p *= aSize (MD.cpp:697-707)
 __global__ void __launch_bounds__(TPB) k_rescale(Cnt cnt, Particle *pos, double sx, double sy, double sz)
 {

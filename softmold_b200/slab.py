@@ -20,6 +20,13 @@ from . import capi
 from .capi import Context, NTERMS
 
 
+class _DeviceDoubles:
+    """__cuda_array_interface__ of n doubles at a device address the library owns"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
 def neighbours(rank, nranks):
     """(left, right) ranks of a slab in the periodic ring along x"""
     return (rank - 1) % nranks, (rank + 1) % nranks
@@ -177,6 +184,21 @@ class DistSlab(_SlabBase):
 
     def _local_terms(self, f):
         return f(self.c)
+
+    def dpotential(self, scale):
+        """NCCL: the terms never visit the host before they are reduced -- smd_dpotential_device leaves them in device memory,
+        the all-reduce runs in place on that buffer, ordered on the library's stream, and ONE device-to-host copy of the
+        total is the trial's only host wait (was: a copy + wait per rank, a staged upload, the all-reduce, a second copy)"""
+        if self.dist.get_backend(self.group) != "nccl":
+            return super().dpotential(scale)
+        import torch
+        dev = torch.device("cuda", self.device)
+        ptr = self.c.dpotential_device(scale)
+        t = torch.as_tensor(_DeviceDoubles(ptr, NTERMS), device=dev)      # zero-copy view of the library's buffer
+        with torch.cuda.stream(torch.cuda.ExternalStream(self.c.stream(), device=dev)):
+            self.dist.all_reduce(t, group=self.group)
+            out = t.cpu()
+        return out.numpy()
 
     def _allreduce(self, part):
         import torch

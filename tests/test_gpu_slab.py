@@ -251,3 +251,22 @@ def test_slab_restart_from_per_rank_particles(bilayer):
         assert np.array_equal(u, w)
     grp.step(9, 3)
     grp.close()
+
+
+def test_dpotential_left_on_the_device_equals_the_host_read_back(orc):
+    """smd_dpotential_device (the buffer the multi-GPU driver all-reduces in place with NCCL): the same terms, bit for bit,
+    as smd_dpotential's host read-back; nothing is copied by the call itself"""
+    import torch
+    from softmold_b200.slab import _DeviceDoubles
+    for case in ("bilayer_eq", "lipocyto_eq", "fields"):
+        m, _ = orc.load_golden(golden_path(case))
+        ctx = sm.Context.from_dict(m)
+        ctx.compute_forces(step=0)
+        ctx.step(0, 4)
+        scale = [1.002, 1.002, 1.0 / 1.002 ** 2]
+        host = ctx.dpotential(scale)
+        ptr = ctx.dpotential_device(scale)
+        ctx.synchronize()
+        dev = torch.as_tensor(_DeviceDoubles(ptr, sm.NTERMS), device="cuda").cpu().numpy()
+        assert np.array_equal(dev, host), (dev, host)
+        ctx.close()
