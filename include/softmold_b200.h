@@ -127,8 +127,17 @@ int smd_add_floating_base(smd_ctx *ctx, int32_t n, const int32_t *idx, const dou
 int smd_add_ztorque(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[4]);
 int smd_add_zpower(smd_ctx *ctx, int32_t n_blocks, const int32_t *blocks, const double c[2]);
 int smd_add_nanocore(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C);
-/* SOLID / OFFSET_BOUNDARY / RIGIDBEND / PULLBEAD: `MD` parses and ignores them (default case of MD.cpp:414-478); registering
- * one keeps the molecule numbering of smd_observe equal to the file's */
+/* The three kinds only MDsubstrate.cpp's molecule switch evaluates (MDsubstrate.cpp:245-259 and :476-490; `MD` ignores them).
+ * Forces only: neither dataExtraction::compute nor that driver's Metropolis sum has a term for them.
+ *   OFFSET_BOUNDARY  doOffsetBoundaryForce system.h:2351-2363, offsetBoundaryF MD.h:502-527; idx[n]; c = {dim, centre, offset, k}
+ *   RIGIDBEND        doRigidBendForce system.h:2366-2400, kmaxTorqueF MD.h:1073-1113; ij[n][2]; c = {zx, zy, zz, k, thetaD}
+ *   PULLBEAD         doPullBeadForce system.h:2449-2486, harmonicFZ MD.h:434-447; idx[n]; c = {x0, y0, z0, k} */
+int smd_add_offset_boundary(smd_ctx *ctx, int32_t n, const int32_t *idx, const double c[4]);
+int smd_add_rigidbend(smd_ctx *ctx, int32_t n, const int32_t *ij, const double c[5]);
+int smd_add_pullbead(smd_ctx *ctx, int32_t n, const int32_t *idx, const double c[4]);
+/* a molecule the driver in charge parses and ignores (default case of MD.cpp:414-478: SOLID, OFFSET_BOUNDARY, RIGIDBEND,
+ * PULLBEAD; of MDsubstrate.cpp:213-262: SOLID, BALL, FLOATING_BASE, ZTORQUE, ZPOWERPOTENTIAL, NANOCORE); registering it
+ * keeps the molecule numbering of smd_observe equal to the file's */
 int smd_add_inert(smd_ctx *ctx, int32_t kind);
 
 /* Per-type friction, the `gammaType` command (MD.cpp:134-138, Langevin::compute algorithms/langevin.h:236-281).  What the
@@ -390,6 +399,14 @@ int smd_mpd_molecule(smd_mpd *m, int32_t k, int32_t *type, int32_t *n_records, i
 
 /* convenience: create a context from a parsed file (tables, particles, molecules all set) */
 int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, int32_t track_unwrapped, smd_ctx **out);
+/* the same with the molecule switch of a named driver of the reference:
+ *   SMD_DRIVER_MD         MD.cpp:414-478 (and MDanneal.cpp, same switch): BALL, FLOATING_BASE, ZTORQUE, ZPOWERPOTENTIAL, NANOCORE
+ *                         act; OFFSET_BOUNDARY, RIGIDBEND, PULLBEAD are parsed and ignored
+ *   SMD_DRIVER_SUBSTRATE  MDsubstrate.cpp:213-262: the other way round (and no NANOCORE mass division)
+ * CHAIN, BOND, BEND, BEAD, BOUNDARY act under both; SOLID under neither. */
+#define SMD_DRIVER_MD 0
+#define SMD_DRIVER_SUBSTRATE 1
+int smd_create_from_mpd_driver(smd_mpd *m, int32_t device, int32_t noise, int32_t track_unwrapped, int32_t driver, smd_ctx **out);
 
 #ifdef __cplusplus
 }

@@ -51,10 +51,12 @@ def run_md(cwd, m, name, nsteps):
     return orc.read_mpd(os.path.join(cwd, name + ".mpd"))
 
 
-def harness(cwd, name, scale=None):
+def harness(cwd, name, scale=None, substrate=False):
     cmd = [os.path.join(REF, "ref_harness"), "dump", name, name + ".bin"]
     if scale is not None:
         cmd += [repr(float(s)) for s in scale]
+    if substrate:
+        cmd += ["substrate"]     # (after an explicit scale) the molecule switch of MDsubstrate.cpp instead of MD.cpp's
     run(cmd, cwd)
     return orc.read_dump(os.path.join(cwd, name + ".bin"))
 
@@ -259,6 +261,47 @@ def fields():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def substrate():
+    """The molecule kinds only MDsubstrate.cpp's switch evaluates (MDsubstrate.cpp:213-262): OFFSET_BOUNDARY, RIGIDBEND,
+    PULLBEAD, next to CHAIN and BOUNDARY, on the equilibrated periodic bilayer of bilayer_eq.  MDsubstrate.cpp does not
+    compile in the reference tree (it includes include/fileFormats/vmdOutput.h, which is not there), so there is no
+    trajectory: the per-molecule forces come from the unmodified Blob::do*Force members through ref_harness."""
+    tmp = tempfile.mkdtemp(prefix="golden_substrate_")
+    try:
+        m, _ = orc.load_golden(os.path.join(OUT, "bilayer_eq.npz"))
+        m = dict(m)
+        n = m["nParticles"]
+        xyz, typ = m["xyz"], m["type"]
+        z = xyz[:, 2]
+        heads = np.where(typ == 2)[0]
+        low = heads[np.argsort(z[heads])[:150]]
+        wall = float(z[low].min()) - 2.05                 # |d| - offset from 1.05 upwards: some inside sqrt(2), none near 0
+        ch = m["molecules"][0]
+        st, nch, ln = [int(v) for v in ch["bonds"][0]]
+        first = st + ln * np.arange(0, nch, 3)            # head and tail end of every third lipid
+        pairs = np.stack([first, first + ln - 1], axis=1).astype(np.int32)
+        mols = list(m["molecules"])
+        mols.append({"type": orc.BOUNDARY, "constants": np.array([2.0, wall + 1.0, 0.0, 0.35]), "bonds": low[:40].reshape(-1, 1).astype(np.int32)})
+        mols.append({"type": orc.OFFSET_BOUNDARY, "constants": np.array([2.0, wall, 1.0, 0.35]), "bonds": low.reshape(-1, 1).astype(np.int32)})
+        # preferred direction z, onset angle 0.6 rad: lipids of both leaflets, some below and some beyond the onset
+        mols.append({"type": orc.RIGIDBEND, "constants": np.array([0.0, 0.0, 1.0, 2.5, 0.6]), "bonds": pairs})
+        mols.append({"type": orc.RIGIDBEND, "constants": np.array([0.6, 0.0, 0.8, 1.5, -0.4]), "bonds": pairs[::5]})
+        mols.append({"type": orc.PULLBEAD, "constants": np.array([m["size"][0] * 0.95, 2.0, float(np.median(z)) + 4.0, 0.75]),
+                     "bonds": np.array([[int(heads[5])], [int(heads[77])]], np.int32)})
+        # kinds MDsubstrate ignores
+        mols.append({"type": orc.ZPOWER, "constants": np.array([-0.0001, 2.1]), "bonds": np.array([[0, 150]], np.int32)})
+        mols.append({"type": orc.BALL, "constants": np.array([4.0, 15.0]), "bonds": np.array([[0, int(j)] for j in heads[:9]], np.int32)})
+        m["molecules"] = mols
+        m["nMolecules"] = len(mols)
+        orc.write_mpd(os.path.join(tmp, "substrate.mpd"), m)
+        g = harness(tmp, "substrate", (1.0004, 1.0004, 1.0 / 1.0004 ** 2), substrate=True)
+        for k, mol in enumerate(mols):
+            print(k, mol["type"], "U", g["U_mol"][k], "dU", g["dU_mol"][k], "max|a|", np.abs(g[f"a_mol{k}"]).max())
+        save("substrate", pack(m, g))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def stats():
     """long-run observables of the reference `MD` executable itself: a tensionless flat bilayer with box moves, 20 000
     steps, two independent runs (seeds 99 / 100, 8 OpenMP threads).  tests/golden/stat_bilayer.npz holds the input
@@ -351,4 +394,4 @@ def kat():
 
 
 if __name__ == "__main__":
-    {"stats": stats, "ball": ball, "fields": fields, "kat": kat, "bead24": bead24}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()
+    {"stats": stats, "ball": ball, "fields": fields, "substrate": substrate, "kat": kat, "bead24": bead24}.get(sys.argv[1] if len(sys.argv) > 1 else "", main)()

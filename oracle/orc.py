@@ -56,6 +56,9 @@ def lib():
             getattr(L, f"orc_{nm}_dpotential").argtypes = [_dp, d3, C.c_int, _ip, d2, d3]
             getattr(L, f"orc_{nm}_dpotential").restype = C.c_double
         L.orc_boundary_force.argtypes = [_dp, d3, C.c_int, _ip, d4, _dp]
+        L.orc_offset_boundary_force.argtypes = [_dp, d3, C.c_int, _ip, d4, _dp]
+        L.orc_rigidbend_force.argtypes = [_dp, d3, C.c_int, _ip, C.c_double * 5, _dp]
+        L.orc_pullbead_force.argtypes = [C.c_int, _dp, d3, C.c_int, _ip, d4, _dp]
         L.orc_boundary_potential.argtypes = [_dp, d3, C.c_int, _ip, d4]
         L.orc_boundary_potential.restype = C.c_double
         L.orc_floating_base_force.argtypes = [_dp, _ip, C.c_int, _ip, _dp, _dp]

@@ -69,6 +69,9 @@ static int cmd_dump(int argc, char **argv)
 	threeVector<double> scale;
 	scale.x = 1.0005; scale.y = 1.0005; scale.z = 1.0 / (1.0005 * 1.0005);
 	if (argc >= 7) { scale.x = atof(argv[4]); scale.y = atof(argv[5]); scale.z = atof(argv[6]); }
+	// 8th argument "substrate": the molecule switch of MDsubstrate.cpp:213-262 instead of MD.cpp:414-478 (OFFSET_BOUNDARY,
+	// RIGIDBEND, PULLBEAD act; FLOATING_BASE, ZTORQUE, ZPOWERPOTENTIAL, NANOCORE, BALL are ignored)
+	const bool substrate = argc >= 8 && !strcmp(argv[7], "substrate");
 
 	Blob<double> S;
 	Script<double, Blob<double> > io(name, std::ios::in, &S);
@@ -131,6 +134,19 @@ static int cmd_dump(int argc, char **argv)
 		molType[k] = S.getMolecule()[k].readType();
 		zero_acc(S);
 		char nm[32];
+		if (substrate) {
+			switch (molType[k]) {
+			case BOND:  S.doBondForce(k);  U[k] = S.doBondPotential(k);  dU[k] = S.doBondDPotential(k, scale);  break;
+			case BEND:  S.doBendForce(k);  U[k] = S.doBendPotential(k);  dU[k] = S.doBendDPotential(k, scale);  break;
+			case CHAIN: S.doChainForce(k); U[k] = S.doChainPotential(k); dU[k] = S.doChainDPotential(k, scale); break;
+			case BEAD:  S.doBeadForce(k);  U[k] = S.doBeadPotential(k);  dU[k] = S.doBeadDPotential(k, scale);  break;
+			case BOUNDARY:        S.doBoundaryForce(k);       U[k] = S.doBoundaryPotential(k); break;
+			case OFFSET_BOUNDARY: S.doOffsetBoundaryForce(k); break;
+			case RIGIDBEND:       S.doRigidBendForce(k);      break;
+			case PULLBEAD:        S.doPullBeadForce(k);       dU[k] = S.doPullBeadDPotential(k, scale); break;
+			default: break;
+			}
+		} else
 		switch (molType[k]) {
 		case BOND:  S.doBondForce(k);  U[k] = S.doBondPotential(k);  dU[k] = S.doBondDPotential(k, scale);  break;
 		case BEND:  S.doBendForce(k);  U[k] = S.doBendPotential(k);  dU[k] = S.doBendDPotential(k, scale);  break;

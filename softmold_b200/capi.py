@@ -39,6 +39,7 @@ SYMBOLS = [
     "smd_slab_connect_ptr", "smd_slab_exchange_send", "smd_slab_exchange_recv", "smd_slab_counts", "smd_slab_capacity",
     "smd_slab_get_local", "smd_slab_set_local", "smd_mc_propose", "smd_mc_accept",
     "smd_host_alloc", "smd_host_free", "smd_snapshot", "smd_snapshot_wait",
+    "smd_add_offset_boundary", "smd_add_rigidbend", "smd_add_pullbead", "smd_create_from_mpd_driver",
     "smd_add_inert", "smd_observe", "smd_msd_start", "smd_ke_histogram", "smd_dpotential_device",
 ]
 OBS_BONDS, OBS_EXTENT, OBS_KE_HIST, OBS_MSD = 1, 2, 4, 8
@@ -151,6 +152,9 @@ def lib():
         L.smd_mc_propose.argtypes = [vp, dbl, dbl, vp, vp]
         L.smd_mc_accept.argtypes = [dbl, dbl, vp, vp, dbl, dbl, ip, dp]
         L.smd_dpotential_device.argtypes = [vp, vp, C.POINTER(vp)]
+        for nm in ("offset_boundary", "rigidbend", "pullbead"):
+            getattr(L, "smd_add_" + nm).argtypes = [vp, i32, vp, vp]
+        L.smd_create_from_mpd_driver.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp)]
         L.smd_add_inert.argtypes = [vp, i32]
         L.smd_observe.argtypes = [vp, C.c_uint32, C.POINTER(Observables), vp, vp, i32]
         L.smd_msd_start.argtypes = [vp]
@@ -216,7 +220,7 @@ class Context:
             raise SoftMoldError(rc, self.L.smd_last_error(self.h).decode())
 
     @classmethod
-    def from_dict(cls, m, device=0, noise=NOISE_PHILOX, track_unwrapped=False, **slab):
+    def from_dict(cls, m, device=0, noise=NOISE_PHILOX, track_unwrapped=False, driver="md", **slab):
         """m: dict with the .mpd fields (as oracle.orc.read_mpd / load_golden produce them); slab: rank, nranks,
         capacity, msg_capacity for a slab rank of a multi-GPU run (m is always the GLOBAL system)"""
         ctx = cls(m["nParticles"], m["nTypes"], m["size"], m["cutoff"], m["deltaT"], m["gamma"], m["initialTemp"],
@@ -224,7 +228,7 @@ class Context:
         ctx.set_pair_tables(m["twoBodyFconst"], m["twoBodyUconst"])
         ctx.set_particles(m["xyz"], m["type"], m["vel"])
         for mol in m["molecules"]:
-            ctx.add_molecule(mol["type"], mol["bonds"], mol["constants"])
+            ctx.add_molecule(mol["type"], mol["bonds"], mol["constants"], driver=driver)
         return ctx
 
     # -- setup
@@ -282,21 +286,27 @@ class Context:
         k = n.value
         return gid[:k], xyz[:k], typ[:k], vel[:k], acc[:k]
 
-    def add_molecule(self, mtype, records, constants):
+    def add_molecule(self, mtype, records, constants, driver="md"):
+        """driver: whose molecule switch decides what acts -- "md" (MD.cpp:414-478) or "substrate" (MDsubstrate.cpp:213-262);
+        the same rule as smd_create_from_mpd_driver"""
         r, c = _i32(records), _f64(constants)
         n = len(r)
-        f = {MOL_CHAIN: self.L.smd_add_chain, MOL_BOND: self.L.smd_add_bonds, MOL_BEND: self.L.smd_add_bends,
-             MOL_BEAD: self.L.smd_add_beads, MOL_BALL: self.L.smd_add_ball, MOL_BOUNDARY: self.L.smd_add_boundary,
-             MOL_FLOATING_BASE: self.L.smd_add_floating_base, MOL_ZTORQUE: self.L.smd_add_ztorque,
-             MOL_ZPOWERPOTENTIAL: self.L.smd_add_zpower, MOL_NANOCORE: self.L.smd_add_nanocore}.get(int(mtype))
-        if int(mtype) in MOL_IGNORED:
-            self._ck(self.L.smd_add_inert(self.h, int(mtype)))
-            self.n_molecules = getattr(self, "n_molecules", 0) + 1
-            return
+        both = {MOL_CHAIN: self.L.smd_add_chain, MOL_BOND: self.L.smd_add_bonds, MOL_BEND: self.L.smd_add_bends,
+                MOL_BEAD: self.L.smd_add_beads, MOL_BOUNDARY: self.L.smd_add_boundary}
+        md_only = {MOL_BALL: self.L.smd_add_ball, MOL_FLOATING_BASE: self.L.smd_add_floating_base, MOL_ZTORQUE: self.L.smd_add_ztorque,
+                   MOL_ZPOWERPOTENTIAL: self.L.smd_add_zpower, MOL_NANOCORE: self.L.smd_add_nanocore}
+        sub_only = {MOL_OFFSET_BOUNDARY: self.L.smd_add_offset_boundary, MOL_RIGIDBEND: self.L.smd_add_rigidbend,
+                    MOL_PULLBEAD: self.L.smd_add_pullbead}
+        assert driver in ("md", "substrate")
+        t = int(mtype)
+        f = both.get(t) or (md_only if driver == "md" else sub_only).get(t)
+        self.n_molecules = getattr(self, "n_molecules", 0) + 1
         if f is None:
+            if t == MOL_SOLID or t in md_only or t in sub_only:     # parsed and ignored by this driver
+                self._ck(self.L.smd_add_inert(self.h, t))
+                return
             raise SoftMoldError(SMD_ERR_UNSUPPORTED, f"molecule type {mtype} is outside the hot path")
         self._ck(f(self.h, n, _ptr(r), _ptr(c)))
-        self.n_molecules = getattr(self, "n_molecules", 0) + 1
 
     def set_gamma_type(self, gamma_type):
         g = _f64(gamma_type)

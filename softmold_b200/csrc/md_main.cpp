@@ -355,8 +355,18 @@ int main(int argc, char *argv[])
 	const double gamma = scalar(M, "gamma"), dt = scalar(M, "deltaT");
 	bool has_gamma_type = false;
 	scalar(M, "gammaType", &has_gamma_type);
+	// SMD_DRIVER: which of the reference's drivers this run stands in for -- "md" (MD.cpp, default), "anneal" (MDanneal.cpp: the
+	// same loop with a box-move trial every 4th step, MDanneal.cpp:67) or "substrate" (MDsubstrate.cpp: its molecule switch,
+	// :213-262, and its per-trial dAcceptFile.dat / dRejectFile.dat, :710-734)
+	const char *drv = std::getenv("SMD_DRIVER");
+	const std::string driver = drv ? drv : "md";
+	if (driver != "md" && driver != "anneal" && driver != "substrate") {
+		std::cerr << "MD_b200: SMD_DRIVER must be md, anneal or substrate\n";
+		return 1;
+	}
+	const bool substrate = driver == "substrate";
 	if (!(gamma > 0) && !has_gamma_type) {   // MD.cpp:129-143: gamma, else gammaType (smd_set_gamma_type), else give up
-		std::cout << "Error(main): No gamma available!\n";
+		(substrate ? std::cerr : std::cout) << "Error(main): No gamma available!\n";   // (MDsubstrate.cpp:143 writes it to stderr)
 		return 0;
 	}
 	const uint32_t seed = (uint32_t)scalar(M, "seed");
@@ -372,7 +382,7 @@ int main(int argc, char *argv[])
 		D.mols.push_back(m);
 	}
 	const char *dev = std::getenv("SMD_DEVICE");
-	int rc = smd_create_from_mpd(M, dev ? std::atoi(dev) : 0, SMD_NOISE_PHILOX, 1, &D.ctx);
+	int rc = smd_create_from_mpd_driver(M, dev ? std::atoi(dev) : 0, SMD_NOISE_PHILOX, 1, substrate ? SMD_DRIVER_SUBSTRATE : SMD_DRIVER_MD, &D.ctx);
 	if (rc) {
 		std::cerr << "MD_b200: " << smd_last_error(D.ctx) << " (code " << rc << ")\n";
 		return 1;
@@ -392,7 +402,7 @@ int main(int argc, char *argv[])
 	}
 	// MD.cpp:67 `#define resizeRate 8`; the driver variant MDanneal.cpp:67 is the same loop with `resizeRate 4` (its temperature
 	// ramp is the tempStepInterval command, handled below for every run): SMD_RESIZE_RATE=4 makes this executable that variant
-	int resizeRate = 8;
+	int resizeRate = driver == "anneal" ? 4 : 8;
 	if (const char *e = std::getenv("SMD_RESIZE_RATE")) { int v = std::atoi(e); if (v >= 1) resizeRate = v; }
 
 	double resizeHistInterval = 0.00001;
@@ -426,7 +436,7 @@ int main(int argc, char *argv[])
 
 	// one Metropolis box-move trial, MD.cpp:589-721: the two draws of MTRand randNum(seed), the trial itself (`run`), the
 	// histograms of resizeHist_<name>.dat
-	auto mc_trial_bookkeeping = [&](auto run) {
+	auto mc_trial_bookkeeping = [&](int at_step, auto run) {
 		double u_fluct = randNum.rand53(), u_accept = randNum.rand53();
 		double fluct = deltaLXY * (2.0 * u_fluct - 1.0);
 		int32_t acc = 0;
@@ -436,6 +446,10 @@ int main(int argc, char *argv[])
 		if (bin < resizeHist.size()) (acc ? resizeHist : rejectHist)[bin] += 1.0;   // 0.5 for x + 0.5 for y
 		if (acc) accepted++;
 		trial++;
+		if (substrate) {   // MDsubstrate.cpp:710-734
+			std::ofstream f(acc ? "dAcceptFile.dat" : "dRejectFile.dat", std::ios::out | std::ios::app);
+			f << (double)at_step * dt << '\t' << dU << std::endl;
+		}
 	};
 
 	std::cerr << "starting main loop: \n";
@@ -449,7 +463,7 @@ int main(int argc, char *argv[])
 		// of that step sum the dPotential of the proposed move along with its forces
 		const int j = i + nplain;
 		if (j <= endInt && mc_at(j) && !store_at(j) && !measure_at(j) && !ramp_at(j)) {
-			mc_trial_bookkeeping([&](double u_fluct, double u_accept, int32_t *acc, double *dU, double *box) {
+			mc_trial_bookkeeping(j, [&](double u_fluct, double u_accept, int32_t *acc, double *dU, double *box) {
 				D.ck(smd_step_mc(ctx, i, nplain + 1, deltaLXY, tension, u_fluct, u_accept, acc, dU, box), "smd_step_mc");
 			});
 			i = j + 1;
@@ -477,7 +491,7 @@ int main(int argc, char *argv[])
 			current = time(NULL);
 		}
 		if (mc_at(i))
-			mc_trial_bookkeeping([&](double u_fluct, double u_accept, int32_t *acc, double *dU, double *box) {
+			mc_trial_bookkeeping(i, [&](double u_fluct, double u_accept, int32_t *acc, double *dU, double *box) {
 				D.ck(smd_mc_box_move(ctx, deltaLXY, tension, u_fluct, u_accept, acc, dU, box), "smd_mc_box_move");
 			});
 		i++;
@@ -492,7 +506,7 @@ int main(int argc, char *argv[])
 	}
 
 	if (deltaLXY != 0) {
-		std::ofstream f("resizeHist_" + D.name + ".dat", std::ios::out);
+		std::ofstream f(substrate ? std::string("resizeHist.dat") : "resizeHist_" + D.name + ".dat", std::ios::out);   // MDsubstrate.cpp:753
 		for (size_t k = 0; k < resizeHist.size(); k++)
 			f << (static_cast<double>(k) * resizeHistInterval) - deltaLXY << '\t' << resizeHist[k] << '\t' << rejectHist[k] << std::endl;
 	}

@@ -535,7 +535,14 @@ extern "C" int smd_mpd_molecule(smd_mpd *m, int32_t k, int32_t *type, int32_t *n
 
 extern "C" int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, int32_t track_unwrapped, smd_ctx **out)
 {
+	return smd_create_from_mpd_driver(m, device, noise, track_unwrapped, SMD_DRIVER_MD, out);
+}
+
+extern "C" int smd_create_from_mpd_driver(smd_mpd *m, int32_t device, int32_t noise, int32_t track_unwrapped, int32_t driver, smd_ctx **out)
+{
 	if (!m || !out) return SMD_ERR_ARG;
+	if (driver != SMD_DRIVER_MD && driver != SMD_DRIVER_SUBSTRATE) return SMD_ERR_ARG;
+	const bool sub = driver == SMD_DRIVER_SUBSTRATE;
 	smd_desc d;
 	memset(&d, 0, sizeof d);
 	d.abi_version = SMD_ABI_VERSION;
@@ -561,19 +568,25 @@ extern "C" int smd_create_from_mpd(smd_mpd *m, int32_t device, int32_t noise, in
 	if (per_type && (rc = smd_set_gamma_type(ctx, (int32_t)m->gammaType.size(), m->gammaType.data()))) return rc;
 	if ((rc = smd_set_particles(ctx, m->xyz.data(), m->type.data(), m->vel.data()))) return rc;
 	for (auto &mol : m->mol) {
+		const int32_t *rec = mol.records.data();
+		const double *con = mol.constants.data();
 		switch (mol.type) {
-		case SMD_MOL_CHAIN: rc = smd_add_chain(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_BOND: rc = smd_add_bonds(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_BEND: rc = smd_add_bends(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_BEAD: rc = smd_add_beads(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_BALL: rc = smd_add_ball(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_BOUNDARY: rc = smd_add_boundary(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_FLOATING_BASE: rc = smd_add_floating_base(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_ZTORQUE: rc = smd_add_ztorque(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_ZPOWERPOTENTIAL: rc = smd_add_zpower(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		case SMD_MOL_NANOCORE: rc = smd_add_nanocore(ctx, mol.n(), mol.records.data(), mol.constants.data()); break;
-		// parsed and written back by the reference, but `MD` does nothing with them (default case of MD.cpp:414-478)
-		case SMD_MOL_SOLID: case SMD_MOL_OFFSET_BOUNDARY: case SMD_MOL_RIGIDBEND: case SMD_MOL_PULLBEAD: rc = smd_add_inert(ctx, mol.type); break;
+		case SMD_MOL_CHAIN: rc = smd_add_chain(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_BOND: rc = smd_add_bonds(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_BEND: rc = smd_add_bends(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_BEAD: rc = smd_add_beads(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_BOUNDARY: rc = smd_add_boundary(ctx, mol.n(), rec, con); break;
+		// MD.cpp:414-478 evaluates these five and ignores the next three; MDsubstrate.cpp:213-262 does the opposite
+		case SMD_MOL_BALL: rc = sub ? smd_add_inert(ctx, mol.type) : smd_add_ball(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_FLOATING_BASE: rc = sub ? smd_add_inert(ctx, mol.type) : smd_add_floating_base(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_ZTORQUE: rc = sub ? smd_add_inert(ctx, mol.type) : smd_add_ztorque(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_ZPOWERPOTENTIAL: rc = sub ? smd_add_inert(ctx, mol.type) : smd_add_zpower(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_NANOCORE: rc = sub ? smd_add_inert(ctx, mol.type) : smd_add_nanocore(ctx, mol.n(), rec, con); break;
+		case SMD_MOL_OFFSET_BOUNDARY: rc = sub ? smd_add_offset_boundary(ctx, mol.n(), rec, con) : smd_add_inert(ctx, mol.type); break;
+		case SMD_MOL_RIGIDBEND: rc = sub ? smd_add_rigidbend(ctx, mol.n(), rec, con) : smd_add_inert(ctx, mol.type); break;
+		case SMD_MOL_PULLBEAD: rc = sub ? smd_add_pullbead(ctx, mol.n(), rec, con) : smd_add_inert(ctx, mol.type); break;
+		// parsed and written back by the reference, but neither driver does anything with it ("Holy crap this doesn't work right now")
+		case SMD_MOL_SOLID: rc = smd_add_inert(ctx, mol.type); break;
 		default: rc = SMD_ERR_UNSUPPORTED;
 		}
 		if (rc) return rc;

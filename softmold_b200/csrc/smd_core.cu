@@ -787,6 +787,38 @@ extern "C" int smd_add_zpower(smd_ctx *ctx, int32_t n_blocks, const int32_t *blo
 	return add_field(ctx, SMD_MOL_ZPOWERPOTENTIAL, n_blocks, nullptr, c, 2, nullptr, 0, blocks, 2, "ZPOWERPOTENTIAL Molecule");
 }
 
+// ---- the kinds of MDsubstrate.cpp's switch (MDsubstrate.cpp:245-259): the caller decides which driver's switch it follows
+extern "C" int smd_add_offset_boundary(smd_ctx *ctx, int32_t n, const int32_t *idx, const double c[4])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (idx || n == 0) && c, "bad OFFSET_BOUNDARY arguments");
+	int dim = (int)c[0];   // static_cast<int>(constants[0]), MD.h:512
+	REQUIRE(dim >= 0 && dim <= 2, "OFFSET_BOUNDARY: constants[0] must name an axis (0, 1 or 2)");
+	return add_field(ctx, SMD_MOL_OFFSET_BOUNDARY, n, idx, c, 4, nullptr, 0, nullptr, 0, "OFFSET_BOUNDARY Molecule");
+}
+
+extern "C" int smd_add_rigidbend(smd_ctx *ctx, int32_t n, const int32_t *ij, const double c[5])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (ij || n == 0) && c, "bad RIGIDBEND arguments");
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
+	int rc = check_index(ctx, ij, 2 * (size_t)n, "RIGIDBEND Molecule");
+	if (rc) return rc;
+	// records of two indices: uploaded as a flat list; the fifth constant travels in host_radius
+	rc = add_field(ctx, SMD_MOL_RIGIDBEND, 2 * n, ij, c, 4, nullptr, 0, nullptr, 0, "RIGIDBEND Molecule");
+	if (rc) return rc;
+	ctx->fields.back().n = n;
+	ctx->fields.back().host_radius.assign(1, c[4]);
+	return SMD_OK;
+}
+
+extern "C" int smd_add_pullbead(smd_ctx *ctx, int32_t n, const int32_t *idx, const double c[4])
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(n >= 0 && (idx || n == 0) && c, "bad PULLBEAD arguments");
+	return add_field(ctx, SMD_MOL_PULLBEAD, n, idx, c, 4, nullptr, 0, nullptr, 0, "PULLBEAD Molecule");
+}
+
 extern "C" int smd_add_nanocore(smd_ctx *ctx, int32_t n, const int32_t *idx, const double *C)
 {
 	if (!ctx) return SMD_ERR_ARG;
@@ -827,6 +859,20 @@ static int launch_field(smd_ctx *ctx, const FieldMol &f, const Particle *pos, Do
 			LAUNCHP(k_zpower<MODE>, nblk(cnt, TPB), TPB, 0, cnt, ctx->cap, pos, ctx->slot_of, start, f.c[0], f.c[1], acc, part);
 			done(nblk(cnt, TPB), SMD_TERM_FIELD);
 		}
+		break;
+	case SMD_MOL_OFFSET_BOUNDARY:
+		if (f.n <= 0 || MODE != 0) break;
+		LAUNCHP(k_offset_boundary, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, ctx->geom, f.d_idx, (int)f.c[0], f.c[1], f.c[2], f.c[3], acc);
+		break;
+	case SMD_MOL_RIGIDBEND:
+		if (f.n <= 0 || MODE != 0) break;
+		LAUNCHP(k_rigidbend, nblk(f.n, TPB), TPB, 0, f.n, ctx->cap, pos, ctx->slot_of, ctx->geom, f.d_idx, f.c[0], f.c[1], f.c[2], f.c[3],
+		        f.host_radius[0], acc);
+		break;
+	case SMD_MOL_PULLBEAD:
+		if (f.n <= 0 || MODE != 0) break;
+		LAUNCHP(k_pullbead, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->N, f.n, ctx->cap, pos, ctx->slot_of, ctx->geom, f.d_idx, f.c[0], f.c[1], f.c[2],
+		        f.c[3], acc);
 		break;
 	default: break;
 	}
@@ -1756,13 +1802,15 @@ extern "C" int smd_get_forces(smd_ctx *ctx, double *acc)
 }
 
 // ------------------------------------------------------------------------------------------------ observables
-// SOLID / OFFSET_BOUNDARY / RIGIDBEND / PULLBEAD: parsed and ignored by `MD` (default case of MD.cpp:414-478); registered so
-// that molecule k of smd_observe is molecule k of the file
+// a molecule the driver in charge parses and ignores (default case of MD.cpp:414-478: SOLID, OFFSET_BOUNDARY, RIGIDBEND,
+// PULLBEAD; of MDsubstrate.cpp:213-262: SOLID, BALL, FLOATING_BASE, ZTORQUE, ZPOWERPOTENTIAL, NANOCORE); registered so that
+// molecule k of smd_observe is molecule k of the file
 extern "C" int smd_add_inert(smd_ctx *ctx, int32_t kind)
 {
 	if (!ctx) return SMD_ERR_ARG;
-	REQUIRE(kind == SMD_MOL_SOLID || kind == SMD_MOL_OFFSET_BOUNDARY || kind == SMD_MOL_RIGIDBEND || kind == SMD_MOL_PULLBEAD,
-	        "smd_add_inert: only the kinds MD itself ignores");
+	REQUIRE(kind == SMD_MOL_SOLID || kind == SMD_MOL_OFFSET_BOUNDARY || kind == SMD_MOL_RIGIDBEND || kind == SMD_MOL_PULLBEAD ||
+	        kind == SMD_MOL_BALL || kind == SMD_MOL_FLOATING_BASE || kind == SMD_MOL_ZTORQUE || kind == SMD_MOL_ZPOWERPOTENTIAL ||
+	        kind == SMD_MOL_NANOCORE, "smd_add_inert: only kinds one of the reference's drivers ignores");
 	ctx->mol_order.push_back({kind, 0, 0});
 	ctx->n_molecules++;
 	return SMD_OK;

@@ -2562,6 +2562,94 @@ __global__ void __launch_bounds__(TPB) k_boundary(int nb, int cap, const Particl
 	}
 }
 
+// ---- the kinds only MDsubstrate.cpp's switch evaluates (MDsubstrate.cpp:213-262, :476-490); forces only: neither
+// dataExtraction::compute nor that driver's Metropolis sum has a term for them (doPullBeadDPotential returns 0)
+
+// OFFSET_BOUNDARY (doOffsetBoundaryForce system.h:2351-2363; offsetBoundaryF MD.h:502-527): the BOUNDARY wall displaced by an
+// offset, d = |x - centre| - offset; c = {dim, centre, offset, k}
+__global__ void __launch_bounds__(TPB) k_offset_boundary(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                                         const int *__restrict__ idx, int dim, double centre, double offset, double kk, double *acc)
+{
+	pdl_prologue();
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nb) return;
+	int s = slot_of[idx[b]];
+	Particle p = load_particle(pos + s);
+	double L = g.box[dim];
+	double d = (dim == 0 ? p.x : dim == 1 ? p.y : p.z) - centre;
+	d -= (d > L / 2.0) ? L : 0;
+	d += (d < -L / 2.0) ? L : 0;
+	double dir = (d < 0) ? -1.0 : 1.0;   // MD.h:81 #define sign(v)
+	d = fabs(d) - offset;
+	double d2 = d * d;
+	double magnitude = 0;
+	if (d2 <= 2.0) magnitude = kk * (4.0 / (d2 * d2 * d) - 2.0 / (d2 * d));
+	atomicAdd(acc + dim * cap + s, magnitude * dir);
+}
+
+// RIGIDBEND (doRigidBendForce system.h:2366-2400; kmaxTorqueF MD.h:1073-1113): a torque that turns the bond first -> second
+// towards a preferred direction z; c = {zx, zy, zz, k, thetaD}.  asin / pow are the CUDA library's (<= 2 ulp from glibc's).
+__global__ void __launch_bounds__(TPB) k_rigidbend(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
+                                                   const int *__restrict__ ij, double zx, double zy, double zz, double kk, double thetaD, double *acc)
+{
+	pdl_prologue();
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nb) return;
+	const int s1 = slot_of[ij[2 * b]], s2 = slot_of[ij[2 * b + 1]];
+	const Particle p1 = load_particle(pos + s1), p2 = load_particle(pos + s2);
+	double r[3] = {p1.x - p2.x, p1.y - p2.y, p1.z - p2.z};
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		if (r[a] > g.box[a] / 2.0) r[a] -= g.box[a];
+		if (r[a] < -g.box[a] / 2.0) r[a] += g.box[a];
+	}
+	double dr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+	r[0] /= dr; r[1] /= dr; r[2] /= dr;
+	const double theta = asin(-((r[0] * zx) + (r[1] * zy) + (r[2] * zz)));
+	const double thetaSqr = theta * theta;
+	const double hp = M_PI / 2.0;
+	double magnitude;
+	if (theta < thetaD)
+		magnitude = kk;
+	else
+		magnitude = kk * (-2.0 * theta * thetaSqr + 3.0 * (hp + thetaD) * thetaSqr - 6.0 * hp * thetaD * theta + (M_PI * M_PI / 4.0) * (3.0 * thetaD - hp)) /
+		            pow(thetaD - hp, 3.0);
+	double cp[3] = {(r[1] * zz - r[2] * zy), -(r[0] * zz - r[2] * zx), (r[0] * zy - r[1] * zx)};
+	dr = sqrt(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]);
+	cp[0] /= dr; cp[1] /= dr; cp[2] /= dr;
+	const double f[3] = {(cp[1] * r[2] - cp[2] * r[1]) * magnitude, -(cp[0] * r[2] - cp[2] * r[0]) * magnitude, (cp[0] * r[1] - cp[1] * r[0]) * magnitude};
+#pragma unroll
+	for (int a = 0; a < 3; a++) { atomicAdd(acc + a * cap + s1, f[a]); atomicAdd(acc + a * cap + s2, -f[a]); }
+}
+
+// PULLBEAD (doPullBeadForce system.h:2449-2486; harmonicFZ MD.h:434-447): a spring between a particle and a fixed point whose
+// reaction is spread over EVERY particle (the pulled one included); c = {x0, y0, z0, k}.  One thread per particle walks the
+// records in order -- the record count is a handful --, so a particle's terms are added in the reference's order.
+__global__ void __launch_bounds__(TPB) k_pullbead(Cnt cnt, int nTotal, int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of,
+                                                  Geom g, const int *__restrict__ idx, double x0, double y0, double z0, double kk, double *acc)
+{
+	pdl_prologue();
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= cnt.get()) return;
+	double a[3] = {0.0, 0.0, 0.0};
+	const double c[3] = {x0, y0, z0};
+	for (int j = 0; j < nb; j++) {
+		const int sp = slot_of[idx[j]];
+		const Particle p = load_particle(pos + sp);
+		double d[3] = {p.x - c[0], p.y - c[1], p.z - c[2]};
+#pragma unroll
+		for (int q = 0; q < 3; q++) {
+			if (d[q] > g.box[q] / 2.0) d[q] -= g.box[q];
+			if (d[q] < -g.box[q] / 2.0) d[q] += g.box[q];
+			d[q] *= kk;
+			if (sp == s) a[q] -= d[q];
+			a[q] += (0.0 + d[q]) / (double)(nTotal - 1);
+		}
+	}
+	// (this kernel is the only writer of a[] while it runs: launches on one stream are ordered)
+	acc[s] += a[0]; acc[cap + s] += a[1]; acc[2 * cap + s] += a[2];
+}
+
 // FLOATING_BASE (doFloatingBaseForce system.h:2402-2422, doFloatingBasePotential :2424-2446; floatingBaseForce MD.h:457-472,
 // floatingBasePotential :475-494): a polynomial wall in z, constants row 6 * type.  Quirk reproduced: the force takes z
 // itself, the potential z - C[0] of ROW 0.
