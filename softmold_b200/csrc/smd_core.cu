@@ -189,7 +189,7 @@ static void set_geom(smd_ctx *ctx, const double box[3])
 }
 
 // per-type phase-1 cutoff = raw + the current FP32 margin (changes with the box), capped at rc^2 + margin
-static int pair_force_smem(smd_ctx *ctx, bool du = false, bool split3 = false);
+static int pair_force_smem(smd_ctx *ctx, bool du);
 static int drop_pending_histogram(smd_ctx *ctx);
 
 static int upload_acut(smd_ctx *ctx)
@@ -373,7 +373,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 		// the opt-in shared-memory size is a property of the FUNCTION on this device, shared by every context of the
 		// process: only ever raise it (a later context with fewer particle types must not shrink it under an earlier one)
 		static int smem_set[64] = {0};
-		int smem = pair_force_smem(ctx);
+		int smem = pair_force_smem(ctx, false);
 		int &have = smem_set[ctx->device & 63];
 		cudaError_t e1 = cudaSuccess;
 		if (smem > have) {
@@ -1140,51 +1140,67 @@ static int ready(smd_ctx *ctx)
 	return SMD_OK;
 }
 
-static int pair_force_smem(smd_ctx *ctx, bool du, bool split3)   // du: the force + dPotential instance (EMODE 3) stages a second table
+template <int SPLIT>
+static int pair_force_smem_t(smd_ctx *ctx, bool du)   // du: the force + dPotential instance (EMODE 3) stages a second table
 {
-	return (int)((sizeof(PairSmem) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
-	       (du ? (PTAB_STRIDE * ctx->nT * ctx->nT + PAIR_TPB) * (int)sizeof(double) : 0) +
-	       (split3 ? (PAIR3_TPB / 32) * PAIR3_CAP : (PAIR_TPB / 32) * PAIR_CAP) * 32 * (int)sizeof(unsigned short);
+	typedef PairCfg<SPLIT> Cfg;
+	return (int)((sizeof(PairSmemT<Cfg::BT>) + 15) & ~size_t(15)) + PTAB_STRIDE * ctx->nT * ctx->nT * (int)sizeof(double) +
+	       (du ? (PTAB_STRIDE * ctx->nT * ctx->nT + Cfg::BT) * (int)sizeof(double) : 0) +
+	       (Cfg::BT / 32) * Cfg::CAP * 32 * (int)sizeof(unsigned short);
 }
+static int pair_force_smem(smd_ctx *ctx, bool du) { return pair_force_smem_t<1>(ctx, du); }
 
-// Three threads per particle (k_pair_force2<.., SPLIT = 3>): a third of the critical path per thread.  Worth it where the
-// grid of the one-thread engine does not fill the device, i.e. where the launch takes as long as its slowest thread.
-static bool use_pair3(const smd_ctx *ctx)
+// Three threads per particle (k_pair_force2<.., SPLIT = 3>): a third of the critical path per thread.  Worth it where the grid
+// of the one-thread engine does not fill the device, i.e. where the launch takes as long as its slowest thread
+// (profiles/r02b_pair3_ab.md, profiles/r02d_timeline.md).
+static int pair_split(const smd_ctx *ctx)
 {
-	if (!ctx->tables_symmetric) return false;
-	if (ctx->pair3 >= 0) return ctx->pair3 == 1;
-	return ctx->N <= ctx->pair3_max;
+	if (!ctx->tables_symmetric) return 1;
+	if (ctx->pair3 >= 0) return ctx->pair3 ? 3 : 1;   // SMD_PAIR3 = 0 | 1
+	return ctx->N <= ctx->pair3_max ? 3 : 1;
 }
 // particles per block of the pair force engine in use: the unit of the completion words (PairGeo::done) and of the
 // dPotential block sums of the force + dPotential pass
-static int pair_block_particles(const smd_ctx *ctx) { return use_pair3(ctx) ? PAIR3_TPB / 3 : PAIR_TPB; }
+static int pair_block_particles(const smd_ctx *ctx) { return pair_split(ctx) > 1 ? PAIR_SPLIT_NP : PAIR_TPB; }
+
+template <int EMODE, bool LANGEVIN, int SPLIT>
+static int launch_pair_split(smd_ctx *ctx, const LangevinArgs &lg, const EnergyArgs &en)
+{
+	typedef PairCfg<SPLIT> Cfg;
+	static bool attr_done = false;   // > 48 KB of dynamic shared memory needs the opt-in (SPLIT = 9 with many types)
+	const int smem = pair_force_smem_t<SPLIT>(ctx, EMODE == 3);
+	if (smem > 48 * 1024 && !attr_done) {
+		CK(cudaFuncSetAttribute(k_pair_force2<EMODE, LANGEVIN, true, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+		attr_done = true;
+	}
+	LAUNCHP((k_pair_force2<EMODE, LANGEVIN, true, SPLIT>), nblk(ctx->N, Cfg::NP), Cfg::BT, smem, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+	       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], en, ctx->pos16);
+	return SMD_OK;
+}
 
 // the pair force of all particles into acc[] (LANGEVIN: a = thermostat term + pair sum, else a += pair sum)
 template <bool LANGEVIN>
 static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
 {
 	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
-	const bool p3 = use_pair3(ctx);
-	const int nb3 = nblk(N, PAIR3_TPB / 3);
+	const int split = pair_split(ctx);
 	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
 		ctx->du_armed = false;
-		if (p3)
-			LAUNCHP((k_pair_force2<3, true, true, 3>), nb3, PAIR3_TPB, pair_force_smem(ctx, true, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16);
+		int rc = SMD_OK;
+		if (split == 3) rc = launch_pair_split<3, true, 3>(ctx, lg, ctx->du_en);
 		else
 		LAUNCHP((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16);
+		if (rc) return rc;
 		ctx->du_ready = true;
 		return SMD_OK;
 	}
-	if (p3)
-		LAUNCHP((k_pair_force2<0, LANGEVIN, true, 3>), nb3, PAIR3_TPB, pair_force_smem(ctx, false, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
-	else if (ctx->tables_symmetric)
-		LAUNCHP((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+	if (split == 3) return launch_pair_split<0, LANGEVIN, 3>(ctx, lg, EnergyArgs{});
+	if (ctx->tables_symmetric)
+		LAUNCHP((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
 	else
-		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
 	return SMD_OK;
 }
@@ -1377,6 +1393,10 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	for (int k = 0; k < nsteps; k++) {
 		ProfScope ps(ctx, SMD_PHASE_STEP);
 		const bool last = (k == nsteps - 1);
+#ifdef SMD_TIMELINE
+		if (k == nsteps - 2) k_tl_set<<<1, 1, 0, ctx->stream>>>(1);   // stamps of step nsteps - 2: build, pair and a seam that is not the last
+		if (last) k_tl_set<<<1, 1, 0, ctx->stream>>>(0);
+#endif
 		ctx->du_armed = last && ctx->du_for_last;
 		// The seam as a programmatic dependent of the pair kernel (CHAIN-only systems, nothing recorded in between): its
 		// blocks move in where the tail of the pair grid has left SMs empty and start on their 128 slots as soon as the
@@ -1474,7 +1494,7 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms, 
 		double grow = 0;   // the most a component-wise scaling moves r^2 across a cutoff, relative
 		for (double sc : {sx, sy, sz}) grow = std::max(grow, std::max(fabs(sc * sc - 1.0), fabs(1.0 / (sc * sc) - 1.0)));
 		en.extra32 = MODE == 1 ? 0.0f : nextafterf((float)(1.01 * grow * ctx->geom.rc2 + 1e-7), INFINITY);
-		LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
+		LAUNCH((k_pair_force2<MODE, false, true>), nb, PAIR_TPB, pair_force_smem(ctx, false), cnt_of(ctx), ctx->cap, pos, ctx->pos32, ctx->start,
 		       cur_win(ctx), ctx->geom, ctx->nT, ctx->uC, ctx->utab, ctx->pgeo, nullptr, LangevinArgs{}, ctx->gid[ctx->cur], en, ctx->pos16);
 		finish_sum(ctx, nb, push(SMD_TERM_PAIR), 1.0);
 	} else {
@@ -1736,7 +1756,7 @@ extern "C" int smd_arm_dpotential(smd_ctx *ctx, const double scale[3])
 	                  !ctx->no_du_fuse && ctx->desc.noise != SMD_NOISE_EXTERNAL;
 	if (!fuse) return SMD_OK;
 	CK(cudaSetDevice(ctx->device));
-	const size_t need = (size_t)nblk(ctx->N, PAIR3_TPB / 3);   // (either pair engine: the smaller block)
+	const size_t need = (size_t)nblk(ctx->N, PAIR_SPLIT_NP);   // (either pair engine: the smaller block)
 	if (ctx->du_partials_n < need) {   // block sums of its own: nothing else may overwrite them before they are used
 		if (ctx->du_partials) cudaFree(ctx->du_partials);
 		ctx->du_partials = nullptr; ctx->du_partials_n = 0;
@@ -1800,6 +1820,17 @@ extern "C" int smd_get_forces(smd_ctx *ctx, double *acc)
 	CK(cudaMemcpyAsync(acc, ctx->stage, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	return check_device_errors(ctx);
 }
+
+#ifdef SMD_TIMELINE
+// debug builds only (tools/timeline.py): the stamps of the last instrumented step, ns: [kernel][first start, last start, last end]
+extern "C" int smd_timeline_read(smd_ctx *ctx, unsigned long long *out48)
+{
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpyFromSymbol(out48, g_tl, 48 * sizeof(unsigned long long)));
+	return SMD_OK;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------ observables
 // a molecule the driver in charge parses and ignores (default case of MD.cpp:414-478: SOLID, OFFSET_BOUNDARY, RIGIDBEND,

@@ -44,6 +44,36 @@ __device__ __forceinline__ void pdl_prologue()
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// -DSMD_TIMELINE: device-side time stamps (%globaltimer) of the step's kernels -- when the first block of a kernel starts, when
+// its last block starts and when its last block ends -- for tools/timeline.py.  Under programmatic dependent launches the
+// kernels of a step overlap, which no event pair can show.  Not compiled into the product library.
+#ifdef SMD_TIMELINE
+__device__ unsigned long long g_tl[48];
+__device__ int g_tl_on;
+__device__ __forceinline__ unsigned long long tl_now()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+struct TlScope {
+	int id;
+	__device__ __forceinline__ TlScope(int i) : id(i)
+	{
+		if (g_tl_on && threadIdx.x == 0) { const unsigned long long t = tl_now(); atomicMin(&g_tl[3 * id], t); atomicMax(&g_tl[3 * id + 1], t); }
+	}
+	__device__ __forceinline__ ~TlScope() { if (g_tl_on && threadIdx.x == 0) atomicMax(&g_tl[3 * id + 2], tl_now()); }
+};
+__global__ void k_tl_set(int on)
+{
+	if (on) for (int k = 0; k < 16; k++) { g_tl[3 * k] = ~0ull; g_tl[3 * k + 1] = 0ull; g_tl[3 * k + 2] = 0ull; }
+	g_tl_on = on;
+}
+#define SMD_TL(id) TlScope tl_scope_(id)
+#else
+#define SMD_TL(id)
+#endif
+
 __device__ __forceinline__ Particle load_particle(const Particle *p)
 {
 	// two 16-byte loads of one aligned 32-byte record (one sector)
@@ -483,6 +513,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan(int *count, const int *bbox, 
                                                    unsigned long long *state, unsigned epoch, const Particle *pos, int *cellOfSlot,
                                                    unsigned *barrier)
 {
+	SMD_TL(0);
 	pdl_prologue();
 	__shared__ int sh[SCAN_TPB / 32];
 	__shared__ int s_excl;
@@ -647,6 +678,7 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan(int *count, const int *bbox, 
 // pass 2: claim a position inside the cell's range (arbitrary order, fixed by k_reorder)
 __global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int2 *order, const int *__restrict__ gid)
 {
+	SMD_TL(1);
 	pdl_prologue();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= cnt.get()) return;
@@ -665,6 +697,7 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *_
                                                  const float *__restrict__ acut, int *bbox, int rearm, uint2 *pos16_out,
                                                  const float *__restrict__ arad, const int *__restrict__ win, Geom geo)
 {
+	SMD_TL(2);
 	pdl_prologue();
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	// rearm: every few hundred builds the occupied-cell extremes start from scratch, to follow a drifting object (nobody
@@ -1073,14 +1106,24 @@ constexpr int PAIR_TPB = 128;
 #define SMD_PAIR_BLOCKS 4
 #endif
 constexpr int PAIR_CAP = SMD_PAIR_CAP;   // list entries per lane, 16 bit each: 4 warps x 128 x 32 x 2 B = 32 KiB per block
-// k_pair_force2<.., SPLIT = 3>: 32 particles per block, three threads each (one per z plane of the stencil)
+// k_pair_force2<.., SPLIT>: SPLIT = 1: 128 particles per block, one thread each.  SPLIT = 3: 32 particles per block, three
+// threads each (one per z plane of the stencil) -- a shorter critical path for systems that do not fill the device.  (Nine
+// threads each, one per (y,z) row, was built and measured: 58 against 25 us per launch on 15 000 particles -- the per-thread
+// set-up and the block-wide hand-over are repeated nine times; profiles/r02b_pair3_ab.md.)
 #ifndef SMD_PAIR3_BLOCKS
 #define SMD_PAIR3_BLOCKS 4
 #endif
 #ifndef SMD_PAIR3_CAP
 #define SMD_PAIR3_CAP 64
 #endif
-constexpr int PAIR3_TPB = 96, PAIR3_BLOCKS = SMD_PAIR3_BLOCKS, PAIR3_CAP = SMD_PAIR3_CAP;
+template <int SPLIT> struct PairCfg {
+	static constexpr int NP = SPLIT == 1 ? 128 : 32;                                   // particles per block
+	static constexpr int BT = NP * SPLIT;                                              // threads per block
+	static constexpr int CAP = SPLIT == 1 ? SMD_PAIR_CAP : SMD_PAIR3_CAP;   // list entries per thread
+	static constexpr int BLOCKS = SPLIT == 1 ? SMD_PAIR_BLOCKS : SMD_PAIR3_BLOCKS;   // resident blocks per SM (register budget)
+	static constexpr int NROW = 9 / SPLIT;                                             // stencil rows per thread
+};
+constexpr int PAIR_SPLIT_NP = 32;   // particles per block of the split engine (the unit of its completion words)
 constexpr int PAIR_SEGBITS = 12;   // entry = (range index << 12) | offset inside the range
 
 struct LangevinArgs { double gamma, sigma; uint64_t seed, step; const double *vel; const int *gid; const double *ext_noise; };
@@ -1193,16 +1236,18 @@ constexpr int PTAB_STRIDE = 10;
 // cell layers only) go straight to the general routine from a separate, plain loop.
 constexpr int PAIR_NSEG = 9;
 
-struct PairSmem {
+template <int BT>
+struct PairSmemT {
 	int perm[PAIR_TPB];                 // particle (slot) taken by each thread in phase 1
-	int cnt[PAIR_TPB];                  // list length per phase-1 thread
-	int order[PAIR_TPB];                // phase-2 thread -> phase-1 thread whose list it drains
-	double part[3][PAIR_TPB];           // sums that do not go through the list (early drains, periodic images)
-	int seg_b[PAIR_NSEG][PAIR_TPB];     // candidate ranges of each thread: first index ...
-	unsigned short seg_n[PAIR_NSEG][PAIR_TPB];   // ... and length (< 4096)
+	int cnt[BT];                        // list length per phase-1 thread
+	int order[BT];                      // phase-2 thread -> phase-1 thread whose list it drains
+	double part[3][BT];                 // sums that do not go through the list (early drains, periodic images)
+	int seg_b[PAIR_NSEG][BT];           // candidate ranges of each thread: first index ...
+	unsigned short seg_n[PAIR_NSEG][BT];   // ... and length (< 4096)
 	int hist[PAIR_CAP + 2];
 	int wcnt[PAIR_TPB / 32];
 };
+typedef PairSmemT<PAIR_TPB> PairSmem;
 
 //
 // EMODE 0: forces.  EMODE 1 / 2: the same two-phase machinery evaluates the pair potential / the dPotential of a box
@@ -1218,7 +1263,7 @@ struct PairSmem {
 // (EnergyArgs: smd_internal.cuh)
 
 template <int EMODE, bool LANGEVIN, bool SYMM, int SPLIT = 1>
-__global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 ? PAIR3_BLOCKS : SMD_PAIR_BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
+__global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_pair_force2(Cnt cnt, int cap, const Particle *__restrict__ pos,
                                                             const float4 *__restrict__ pos32, const int *__restrict__ start,
                                                             const int *__restrict__ win, Geom g, int nT,
                                                             const double *__restrict__ tab, const double *__restrict__ ptab,
@@ -1226,6 +1271,7 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
                                                             const int *__restrict__ gid, EnergyArgs en,
                                                             const uint2 *__restrict__ pos16)
 {
+	SMD_TL(3);
 	asm volatile("griddepcontrol.wait;" ::: "memory");   // (its dependents are released further down, see pg.done)
 	static_assert(EMODE != 3 || SYMM, "forces + dPotential in one pass: symmetric tables only");
 	constexpr bool ENERGY_ONLY = (EMODE == 1 || EMODE == 2);   // no forces; every unordered pair once
@@ -1235,10 +1281,11 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 	// last, sparse round of blocks of a large one, is done in a third of the time -- and three partial sums per particle,
 	// added in plane order by the first warp.  Forces only.
 	static_assert(SPLIT == 1 || (SPLIT == 3 && !ENERGY_ONLY), "the split engine evaluates forces");
-	constexpr int BT = SPLIT == 3 ? PAIR3_TPB : PAIR_TPB;      // threads per block
-	constexpr int NP = BT / SPLIT;                             // particles per block
-	constexpr int CAP = SPLIT == 3 ? PAIR3_CAP : PAIR_CAP;     // list entries per thread
-	constexpr int NROW = PAIR_NSEG / SPLIT;                    // stencil rows per thread
+	constexpr int BT = PairCfg<SPLIT>::BT;        // threads per block
+	constexpr int NP = PairCfg<SPLIT>::NP;        // particles per block
+	constexpr int CAP = PairCfg<SPLIT>::CAP;      // list entries per thread
+	constexpr int NROW = PairCfg<SPLIT>::NROW;    // stencil rows per thread
+	static_assert(CAP <= PAIR_CAP, "hist[] is sized for the one-thread engine");
 	const int N = cnt.get();
 	const int bid = (int)blockIdx.x;
 	if (bid * NP >= N) {
@@ -1250,15 +1297,16 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 	// block b then waits for done[b] == epoch, which block b of this grid sets when its accelerations are written.
 	if (pg.done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	extern __shared__ __align__(128) unsigned char s_raw[];
-	PairSmem &sm = *reinterpret_cast<PairSmem *>(s_raw);
-	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(PairSmem) + 15) & ~size_t(15)));
+	typedef PairSmemT<BT> Smem;
+	Smem &sm = *reinterpret_cast<Smem *>(s_raw);
+	double *s_ptab = reinterpret_cast<double *>(s_raw + ((sizeof(Smem) + 15) & ~size_t(15)));
 	const int nptab = PTAB_STRIDE * nT * nT;
 	// EMODE 3 only (its launches reserve the room; every byte of shared memory is L1 the other instances want): the
 	// potential's padded table next to the force's, and the dPotential terms that bypass the lists
 	double *s_utab = s_ptab + nptab;
 	double *s_dup = s_utab + nptab;
-	unsigned short *s_lists = reinterpret_cast<unsigned short *>(DU ? s_dup + PAIR_TPB : s_ptab + nptab);
-	const int row0 = SPLIT == 3 ? 3 * (int)(threadIdx.x >> 5) : 0;   // first stencil row of this thread
+	unsigned short *s_lists = reinterpret_cast<unsigned short *>(DU ? s_dup + BT : s_ptab + nptab);
+	const int row0 = SPLIT > 1 ? NROW * (int)(threadIdx.x >> 5) : 0;   // first stencil row of this thread
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int k = tid; k < nptab; k += BT) s_ptab[k] = ptab[k];
 	if (DU) for (int k = tid; k < nptab; k += BT) s_utab[k] = en.utab[k];
@@ -1270,7 +1318,7 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 
 	// ---- deal the block's particles to threads by class
 	{
-		const int pt = SPLIT == 3 ? lane : tid;   // (SPLIT = 3: every warp holds the same 32 particles)
+		const int pt = SPLIT > 1 ? lane : tid;   // (split engines: every warp holds the same 32 particles)
 		const int i0 = bid * NP + pt;
 		const bool heavy = (i0 < N) && pos32[i0].w >= pg.thr32;
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
@@ -1278,13 +1326,13 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 		__syncthreads();
 		int before = 0, total = 0;
 #pragma unroll
-		for (int k = 0; k < NP / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < (SPLIT == 3 ? 0 : wid)) before += c; }
+		for (int k = 0; k < NP / 32; k++) { int c = sm.wcnt[k]; total += c; if (k < (SPLIT > 1 ? 0 : wid)) before += c; }
 		const int below = __popc(bal & ((1u << lane) - 1u));
 		const int rank = heavy ? before + below : total + (pt - before - below);
 		if (SPLIT == 1 || wid == 0) sm.perm[rank] = i0;
 		__syncthreads();
 	}
-	const int i = sm.perm[SPLIT == 3 ? lane : tid];
+	const int i = sm.perm[SPLIT > 1 ? lane : tid];
 	// slab mode: ghosts are only neighbours, nobody gathers for them
 	const bool live = i < N && !(g.slab && (gid[i] & GID_GHOST));
 	Particle pi;
@@ -1315,7 +1363,7 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 			unsigned short e;
 			asm volatile("ld.shared.u16 %0, [%1];" : "=h"(e) : "r"(a) : "memory");
 			int b;
-			asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(tb + (unsigned)(e >> PAIR_SEGBITS) * (4u * PAIR_TPB)) : "memory");
+			asm volatile("ld.shared.s32 %0, [%1];" : "=r"(b) : "r"(tb + (unsigned)(e >> PAIR_SEGBITS) * (4u * BT)) : "memory");
 			j = b + (int)(e & ((1u << PAIR_SEGBITS) - 1u));
 			return load_particle(pos + j);
 		};
@@ -1668,7 +1716,7 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];
-	const int io = sm.perm[SPLIT == 3 ? (o & 31) : o];
+	const int io = sm.perm[SPLIT > 1 ? (o & 31) : o];
 	const bool act = io < N && !(g.slab && (gid[io] & GID_GHOST));
 	if (SPLIT == 1 && EMODE == 0 && !act && !pg.done) return;
 	double ax = sm.part[0][o], ay = sm.part[1][o], az = sm.part[2][o];
@@ -1698,7 +1746,7 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 	}
 	int iw = io;        // the particle whose acceleration this thread writes
 	bool actw = act;
-	if (SPLIT == 3) {   // the three partial sums of a particle, added in plane order by the first warp
+	if (SPLIT > 1) {   // the partial sums of a particle, added in row order by the first warp
 		__syncthreads();
 		sm.part[0][o] = act ? ax : 0.0; sm.part[1][o] = act ? ay : 0.0; sm.part[2][o] = act ? az : 0.0;
 		__syncthreads();
@@ -1706,9 +1754,9 @@ __global__ void __launch_bounds__(SPLIT == 3 ? PAIR3_TPB : PAIR_TPB, SPLIT == 3 
 		actw = wid == 0 && iw < N && !(g.slab && (gid[iw] & GID_GHOST));
 		if (!actw && !pg.done) return;
 		if (actw) {
-			ax = (sm.part[0][lane] + sm.part[0][32 + lane]) + sm.part[0][64 + lane];
-			ay = (sm.part[1][lane] + sm.part[1][32 + lane]) + sm.part[1][64 + lane];
-			az = (sm.part[2][lane] + sm.part[2][32 + lane]) + sm.part[2][64 + lane];
+			ax = sm.part[0][lane]; ay = sm.part[1][lane]; az = sm.part[2][lane];
+#pragma unroll
+			for (int k = 1; k < SPLIT; k++) { ax += sm.part[0][32 * k + lane]; ay += sm.part[1][32 * k + lane]; az += sm.part[2][32 * k + lane]; }
 		}
 	}
 	if (!actw) {
@@ -2093,6 +2141,7 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
                                                     BeadSet bs, int slot0, SlabComm comm, int seq, int *gid_w, const int *done, int epoch,
                                                     BinArgs bin, int done_per = 1)
 {
+	SMD_TL(4);
 	// done != nullptr: launched as a programmatic dependent of the pair kernel -- this block may be resident while the
 	// tail of that grid is still running and only needs the accelerations of its own 128 slots, which pair block `blk`
 	// signals with done[blk] = epoch (everything else it reads was final before the pair kernel started)

@@ -450,7 +450,7 @@ def test_async_snapshot_equals_blocking_readback(orc):
 
 
 @pytest.mark.parametrize("case", ["lipo_eq", "bilayer_eq", "lipocyto_eq", "bead24", "fields", "gas"])
-def test_three_thread_pair_engine_changes_nothing_but_the_summation_order(orc, case):
+def test_split_pair_engine_changes_nothing_but_the_summation_order(orc, case):
     """k_pair_force2<.., SPLIT = 3> (SMD_PAIR3=1; the default for systems of at most SMD_PAIR3_MAX particles): three threads
     per particle, one per z plane of the stencil, three partial sums added in plane order.  Against the one-thread engine
     (SMD_PAIR3=0): the same pairs -- forces equal to rounding --, the same Metropolis decisions and dU (the force + dPotential
@@ -478,9 +478,10 @@ def test_three_thread_pair_engine_changes_nothing_but_the_summation_order(orc, c
             log.append(ctx.step_mc(nst * t, nst, 0.01, 0.4, mc[2 * t], mc[2 * t + 1]))
         runs.append((a_first, log, ctx.get_particles()[0], ctx.get_forces(), abs(ctx.potential()[sm.TERM_PAIR])))
         ctx.close()
-    (f0, l0, x0, a0, U0), (f1, l1, x1, a1, _) = runs
-    assert rel_force_err(f1, f0) <= 1e-13
-    assert [x[0] for x in l0] == [x[0] for x in l1]
-    for (_, d0, b0), (_, d1, b1) in zip(l0, l1):
-        assert abs(d0 - d1) <= 1e-12 * U0 and np.allclose(b0, b1, rtol=1e-15)
-    assert np.abs(x1 - x0).max() <= 1e-9 and rel_force_err(a1, a0) <= 1e-8
+    f0, l0, x0, a0, U0 = runs[0]
+    for f1, l1, x1, a1, _ in runs[1:]:
+        assert rel_force_err(f1, f0) <= 1e-13
+        assert [x[0] for x in l0] == [x[0] for x in l1]
+        for (_, d0, b0), (_, d1, b1) in zip(l0, l1):
+            assert abs(d0 - d1) <= 1e-12 * U0 and np.allclose(b0, b1, rtol=1e-15)
+        assert np.abs(x1 - x0).max() <= 1e-9 and rel_force_err(a1, a0) <= 1e-8
