@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <nvtx3/nvToolsExt.h>
 
 #include "smd_kernels.cuh"
 
@@ -57,6 +58,7 @@ static cudaError_t launch_ex(bool pdl, void (*kernel)(KArgs...), int grid, int b
 	} while (0)
 
 static const int MAX_PARTIALS = 1 << 20;
+static int g_slab_ctx_on_device[64] = {0};   // live slab contexts of this process per device (see smd_slab_exchange_recv)
 #ifndef SMD_PAIR3_MAX_DEFAULT
 #define SMD_PAIR3_MAX_DEFAULT 32000   // measured (profiles/r02b_pair3_ab.md): 15 000 particles 72 -> 47 us per step, 30 000 76 -> 67, 60 000 78 -> 102
 #endif
@@ -91,10 +93,29 @@ static void prof_drain(smd_ctx *ctx)
 	ctx->prof_pending.clear();
 }
 
+// NVTX ranges (tracing): SMD_NVTX=1 names every phase of the step on the host time line a profiler shows (Nsight
+// Systems, ncu --nvtx); the ranges bracket the ENQUEUE of the phase's launches.  Header-only NVTX v3: without a tool attached
+// the calls are a null function-pointer check.
+static const char *const PHASE_NAMES[SMD_NPHASES] = {"smd:integrate1", "smd:build", "smd:pair", "smd:molecules", "smd:langevin", "smd:integrate2",
+	"smd:step", "smd:exchange", "smd:fused_seam", "smd:pair+dU", "smd:build.hist", "smd:build.scan", "smd:build.place", "smd:build.reorder",
+	"smd:phase14", "smd:phase15"};
+static bool nvtx_on()
+{
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("SMD_NVTX"); v = (e && *e == '1') ? 1 : 0; }
+	return v == 1;
+}
+struct NvtxRange {
+	bool on;
+	explicit NvtxRange(const char *name) : on(nvtx_on()) { if (on) nvtxRangePushA(name); }
+	~NvtxRange() { if (on) nvtxRangePop(); }
+};
+
 // RAII bracket: records an event pair around the launches of one phase when that phase is enabled
 struct ProfScope {
 	smd_ctx *ctx; int phase; cudaEvent_t e0; bool on;
-	ProfScope(smd_ctx *c, int ph) : ctx(c), phase(ph), e0(nullptr), on((c->prof_mask >> ph) & 1u)
+	NvtxRange nv;
+	ProfScope(smd_ctx *c, int ph) : ctx(c), phase(ph), e0(nullptr), on((c->prof_mask >> ph) & 1u), nv(PHASE_NAMES[ph])
 	{
 		if (on) { e0 = prof_event(ctx); cudaEventRecord(e0, ctx->stream); }
 	}
@@ -250,6 +271,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->nT = desc->n_types;
 	ctx->cap = ((std::max(ctx->N, 1) + 255) / 256) * 256;
 	ctx->slab = desc->nranks > 1;
+	if (ctx->slab) g_slab_ctx_on_device[desc->device & 63]++;
 	memset(&ctx->comm, 0, sizeof ctx->comm);
 	if (ctx->slab) {
 		if (desc->rank < 0 || desc->rank >= desc->nranks) { g_create_error = "rank outside [0, nranks)"; delete ctx; return SMD_ERR_ARG; }
@@ -277,6 +299,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_PAIR3"); ctx->pair3 = e ? atoi(e) : -1; }
 	{ const char *e = getenv("SMD_PAIR3_MAX"); ctx->pair3_max = e ? atoi(e) : SMD_PAIR3_MAX_DEFAULT; }
 	{ const char *e = getenv("SMD_NO_PREBIN"); ctx->prebin = !(e && *e == '1'); }
+	{ const char *e = getenv("SMD_NO_SLAB_PREBIN"); ctx->no_slab_prebin = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_SEAM_PACK"); ctx->no_seam_pack = e && *e == '1'; }
 	// SMD_PDL=0: plain stream order everywhere; 1: only the step seam is a programmatic dependent (of the pair kernel);
@@ -404,6 +427,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 extern "C" int smd_destroy(smd_ctx *ctx)
 {
 	if (!ctx) return SMD_OK;
+	if (ctx->slab) g_slab_ctx_on_device[ctx->device & 63]--;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	for (int b = 0; b < 2; b++) {
@@ -952,7 +976,7 @@ static BinArgs bin_args(smd_ctx *ctx)
 {
 	BinArgs b = {nullptr, nullptr, nullptr};
 	if (ctx->hist_pending) drop_pending_histogram(ctx);   // a second pass without a build in between: that histogram is stale
-	if (!ctx->prebin || ctx->slab || !ctx->next_win_valid || !ctx->cells_valid) return b;
+	if (!ctx->prebin || (ctx->slab && ctx->no_slab_prebin) || !ctx->next_win_valid || !ctx->cells_valid) return b;
 	b.win = next_win(ctx); b.count = ctx->count; b.cellOfSlot = ctx->cellOfSlot;
 	ctx->hist_pending = true;
 	return b;
@@ -984,14 +1008,15 @@ static int build_cells(smd_ctx *ctx)
 	}
 	{
 		ProfScope ps(ctx, SMD_PHASE_BUILD_SCAN);
-		LAUNCHP(k_scan, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, cur_win(ctx), ctx->slab ? (int *)nullptr : next_win(ctx),
+		LAUNCHP(k_scan, SCAN_BLOCKS, SCAN_TPB, 0, ctx->count, ctx->bbox, ctx->geom, ctx->cellcap, cur_win(ctx), next_win(ctx),
 		       prebinned ? 1 : 0, ctx->start, ctx->cursor, N, ctx->slab ? ctx->dN : nullptr, ctx->errflag, ctx->scan_state, (unsigned)(ctx->rebuilds + 1),
 		       (const Particle *)ctx->pos[pcur], ctx->cellOfSlot, ctx->scan_barrier);
-		ctx->next_win_valid = !ctx->slab;
+		ctx->next_win_valid = true;
 	}
 	{
 		ProfScope ps(ctx, SMD_PHASE_BUILD_PLACE);
-		LAUNCHP(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order, ctx->gid[cur]);
+		LAUNCHP(k_place, nblk(N, TPB), TPB, 0, cnt_ext(ctx), ctx->cellOfSlot, ctx->cursor, ctx->order, ctx->gid[cur],
+		        (ctx->slab && prebinned) ? ctx->slot_of : (int *)nullptr);
 	}
 	{
 		ProfScope ps(ctx, SMD_PHASE_BUILD_REORDER);
@@ -1367,6 +1392,7 @@ static ChainSet chain_set(const smd_ctx *ctx)
 extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 {
 	if (!ctx) return SMD_ERR_ARG;
+	NvtxRange nv("smd_step");
 	REQUIRE(ctx->desc.noise != SMD_NOISE_EXTERNAL || nsteps <= 1, "external noise: one step per smd_set_noise");
 	if (nsteps <= 0) return SMD_OK;
 	struct Disarm { smd_ctx *c; ~Disarm() { c->du_for_last = false; c->du_armed = false; } } disarm{ctx};   // one call only
@@ -1585,6 +1611,7 @@ extern "C" int smd_dpotential_device(smd_ctx *ctx, const double scale[3], double
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(d_terms && scale, "null argument");
+	NvtxRange nv("smd_dpotential_device");
 	int rc = energy_terms<2>(ctx, scale, nullptr, true);
 	*d_terms = ctx->terms_dev;
 	return rc;
@@ -2276,10 +2303,14 @@ extern "C" int smd_slab_exchange_recv(smd_ctx *ctx)
 	// A few blocks only (grid-stride over <= 2 * capmsg entries): the kernel SPINS on the neighbours' headers, and when
 	// several ranks share one device (the single-process test harness) their waiting kernels must never fill the machine
 	// and starve the pack kernel they wait for (four ranks x 296 blocks x 256 threads did exactly that, intermittently).
-	int blocks = std::min(nblk(2ll * ctx->comm.capmsg, 256), 24);
+	// One slab context on this device (the production layout: one process per GPU): nothing else can be starved, one block
+	// per SM takes the entries in one trip.
+	const bool alone = g_slab_ctx_on_device[ctx->device & 63] <= 1;
+	int blocks = std::min(nblk(2ll * ctx->comm.capmsg, 256), alone ? 148 : 24);
 	long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a neighbour that never sends is reported, not waited for
 	LAUNCHP(k_slab_unpack, blocks, 256, 0, cnt_of(ctx), ctx->dN + 1, ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->unw[ctx->cur],
-	       ctx->gid[ctx->cur], ctx->comm, ctx->xseq, ctx->errflag, spin_limit);
+	       ctx->gid[ctx->cur], ctx->comm, ctx->xseq, ctx->errflag, spin_limit, ctx->geom,
+	       ctx->hist_pending ? BinArgs{next_win(ctx), ctx->count, ctx->cellOfSlot} : BinArgs{nullptr, nullptr, nullptr});
 	ctx->exch_pending = false;
 	ctx->ext_valid = true;
 	return SMD_OK;

@@ -181,6 +181,7 @@ struct smd_ctx {
 	int *win;         // [2][WIN_WORDS] window descriptors (device): [wcur] of the current sorted order, [wcur ^ 1] the one the next
 	                  // tagging pass bins into (published by every build: occupied box + 1 cell)
 	int wcur = 0;
+	bool no_slab_prebin = false;   // SMD_NO_SLAB_PREBIN=1: slab mode keeps the histogram pass of its own (k_bin) in every build (A/B)
 	bool prebin = true;         // SMD_NO_PREBIN=1: the histogram of the build is always a pass of its own (k_bin)
 	bool hist_pending = false;  // count[] holds the histogram of the current positions under win[wcur ^ 1] (a tagging pass filled it)
 	bool next_win_valid = false; // win[wcur ^ 1] was published by the last build and nothing has changed the geometry since

@@ -367,10 +367,14 @@ __device__ __forceinline__ int bin_particle(const Particle &p, bool live, const 
 	if (live) {
 		int cx, cy, cz;
 		unpack_cell(p.cell, cx, cy, cz);
-		const int lx = cx - b.win[WIN_ORG], ly = cy - b.win[WIN_ORG + 1], lz = cz - b.win[WIN_ORG + 2];
+		// (a slab's window is fixed -- its columns + halo, wrapping across the periodic seam: a particle outside it has moved
+		// further than the halo in one step, which is an error there, not a reason to re-bin)
+		const int lx = g.slab ? win_x(cx, b.win[WIN_ORG], g.nc[0]) : cx - b.win[WIN_ORG], ly = cy - b.win[WIN_ORG + 1], lz = cz - b.win[WIN_ORG + 2];
 		const int d0 = b.win[WIN_DIM], d1 = b.win[WIN_DIM + 1], d2 = b.win[WIN_DIM + 2];
-		if (b.win[WIN_NCELLS] == 0 || lx < 0 || lx >= d0 || ly < 0 || ly >= d1 || lz < 0 || lz >= d2) b.win[WIN_DIRTY] = 1;
-		else {
+		if (b.win[WIN_NCELLS] == 0 || lx < 0 || lx >= d0 || ly < 0 || ly >= d1 || lz < 0 || lz >= d2) {
+			if (g.slab) atomicOr(errflag, ERR_SLAB_MIGRATION);
+			else b.win[WIN_DIRTY] = 1;
+		} else {
 			int sub = 0;
 			if (g.xs > 1) sub = min(max((int)((p.x - (double)cx * g.cs[0]) * g.finv), 0), g.xs - 1);
 			local = (lx * g.xs + sub) + b.win[WIN_FD0] * (ly + d1 * lz);
@@ -676,14 +680,21 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan(int *count, const int *bbox, 
 }
 
 // pass 2: claim a position inside the cell's range (arbitrary order, fixed by k_reorder)
-__global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int2 *order, const int *__restrict__ gid)
+__global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int2 *order, const int *__restrict__ gid,
+                                               int *giveback)
 {
 	SMD_TL(1);
 	pdl_prologue();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= cnt.get()) return;
 	int c = cellOfSlot[s];
-	if (c < 0) return;
+	if (c < 0) {
+		// slab mode, histogram filled by the seam / the unpack (no k_bin in this build): a record that was not binned is a
+		// ghost the exchange dropped; its entry of the index table is given back here (see k_bin), before k_reorder re-enters
+		// the particle if it has just been received again
+		if (giveback) giveback[gid[s] & GID_MASK] = -1;
+		return;
+	}
 	int q = atomicAdd(cursor + c, 1);
 	order[q] = make_int2(s, gid[s] & GID_MASK);   // the original index travels along: k_reorder ranks a cell without a second gather
 }
@@ -2065,9 +2076,12 @@ __global__ void __launch_bounds__(TPB) k_slab_pack(Cnt cnt, int cap, Particle *p
 }
 
 __global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int cap, Particle *pos, double *vel, double *unw, int *gid,
-                                                     SlabComm c, int seq, int *errflag, long long spin_limit)
+                                                     SlabComm c, int seq, int *errflag, long long spin_limit, Geom g, BinArgs bin)
 {
-	pdl_prologue();
+	// (not pdl_prologue(): this kernel SPINS on its neighbours' headers.  Its dependents -- the persistent grid of k_scan is
+	// next -- are released only once the messages are in: waiting blocks of several ranks that share one device (the
+	// single-process test harness) could otherwise fill every SM while the kernel that sends the message finds no room)
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	__shared__ int n_s[2];
 	if (threadIdx.x < 2) {
 		const char *buf = c.recv[threadIdx.x] + (size_t)(seq & 1) * c.parity_stride;
@@ -2082,6 +2096,7 @@ __global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int ca
 		n_s[threadIdx.x] = n;
 	}
 	__syncthreads();
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	const int N0 = cnt.get(), nL = n_s[0], nR = n_s[1], total = nL + nR;
 	for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
 		int side = e >= nL, k = e - (side ? nL : 0);
@@ -2097,6 +2112,21 @@ __global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int ca
 		if (unw) {
 			double2 u0 = __ldcg(q + 4), u1 = __ldcg(q + 5);
 			unw[slot] = u0.x; unw[cap + slot] = u0.y; unw[2 * cap + slot] = u1.x;
+		}
+		if (bin.count) {   // the histogram of the build that follows: the seam binned what stayed, this bins what arrived
+			// (the record carries the sender's cell tag: the reference grid is the same on every rank)
+			int cx, cy, cz;
+			unpack_cell((unsigned)((unsigned long long)__double_as_longlong(b.y) >> 32), cx, cy, cz);
+			const int lx = win_x(cx, bin.win[WIN_ORG], g.nc[0]);
+			int local = -1;
+			if (lx >= bin.win[WIN_DIM]) atomicOr(errflag, ERR_SLAB_MIGRATION);
+			else {
+				int sub = 0;
+				if (g.xs > 1) sub = min(max((int)((a.x - (double)cx * g.cs[0]) * g.finv), 0), g.xs - 1);
+				local = (lx * g.xs + sub) + bin.win[WIN_FD0] * ((cy - bin.win[WIN_ORG + 1]) + bin.win[WIN_DIM + 1] * (cz - bin.win[WIN_ORG + 2]));
+				atomicAdd(bin.count + local, 1);
+			}
+			bin.cellOfSlot[slot] = local;
 		}
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) *dNext = min(N0 + total, cap);

@@ -270,3 +270,35 @@ def test_dpotential_left_on_the_device_equals_the_host_read_back(orc):
         dev = torch.as_tensor(_DeviceDoubles(ptr, sm.NTERMS), device="cuda").cpu().numpy()
         assert np.array_equal(dev, host), (dev, host)
         ctx.close()
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_slab_histogram_filled_by_the_seam_and_the_unpack_is_bit_identical(bilayer, batched):
+    """slab mode: the histogram of the cell build is filled by the kernel that moves the particles (owned particles and the
+    migrants that stay behind as ghosts) and by the unpack kernel (what arrives), instead of a pass of its own over every
+    slot (k_bin; SMD_NO_SLAB_PREBIN=1 keeps it).  Same sort, same forces: trajectories with box moves identical bit for bit,
+    and the index-table entries of dropped ghosts are still given back (gather finds every particle exactly once)."""
+    import os
+    m = bilayer
+    n = m["nParticles"]
+    mc = np.random.RandomState(5).random_sample(16)
+    out = []
+    for env in ("1", "0"):
+        os.environ["SMD_NO_SLAB_PREBIN"] = env
+        try:
+            grp = LocalSlabGroup(m, 3)
+        finally:
+            del os.environ["SMD_NO_SLAB_PREBIN"]
+        grp.batched_default = batched
+        grp.compute_forces(mask=sm.MASK_ALL, step=0)
+        boxes = []
+        for t in range(4):
+            boxes.append(grp.step_mc(8 * t, 8, 0.01, 0.4, mc[2 * t], mc[2 * t + 1])[2]) if batched else \
+                (grp.step(8 * t, 8), boxes.append(grp.mc_box_move(0.01, 0.4, mc[2 * t], mc[2 * t + 1])[2]))
+        xyz, typ, vel, acc, owner = grp.gather(n)
+        launches = sum(c.stats()[0] for c in grp.ctx)
+        out.append((xyz, vel, acc, np.array(boxes), launches))
+        grp.close()
+    (x0, v0, a0, b0, l0), (x1, v1, a1, b1, l1) = out
+    assert np.array_equal(b0, b1) and np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(a0, a1)
+    assert l1 < l0          # the histogram passes are gone
