@@ -361,6 +361,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 			CKC(cudaMemset(ctx->recv_base[sd], 0, ctx->recv_bytes));
 			ctx->comm.recv[sd] = ctx->recv_base[sd];
 		}
+		{ const char *e = getenv("SMD_SLAB_PULL"); ctx->comm.pull = (e && *e == '1') ? 1 : 0; }
 		CKC(cudaMalloc(&ctx->comm.counters, 4 * sizeof(int)));
 		CKC(cudaMemset(ctx->comm.counters, 0, 4 * sizeof(int)));
 	}

@@ -78,11 +78,20 @@ struct __align__(32) SlabMsgEntry {    // 96 B
 	double ux, uy, uz; double pad1;              // unwrapped position (migrants, when tracked)
 };
 struct SlabComm {
-	char *send[2];          // receive buffer AT the left / right neighbour that this rank fills (parity 0; parity 1 follows)
-	char *recv[2];          // own receive buffers: [0] filled by the left neighbour, [1] by the right one
+	char *send[2];          // peer pointers: the left / right neighbour's message buffer that faces this rank (parity 0; parity 1 follows)
+	char *recv[2];          // own message buffers: [0] shared with the left neighbour, [1] with the right one
 	int *counters;          // [0..1] entries claimed per direction, [2] blocks done
 	size_t parity_stride;   // bytes between the two parity copies of a buffer
 	int capmsg;             // entries per message
+	// Who crosses the link.  pull = 0 (default): the sender writes through peer memory into the neighbour's buffer send[d];
+	// every writing thread needs a system-scope fence before its block may be counted, and since the boundary columns are
+	// spread over every block of a cell-sorted array, every block of the step seam pays that NVLink round trip.
+	// pull = 1 (SMD_SLAB_PULL=1): the sender packs into ITS OWN buffer recv[d] -- local stores, a device-scope fence -- and the
+	// receiver's unpack kernel reads the neighbour's buffer send[side] through the link after acquiring its header at system
+	// scope.  Measured on 2 x B200 (C5 tile, profiles/r02h_slab_transport.md): the seam gets 11.6 us cheaper (96.1 -> 84.5),
+	// the unpack 14.1 us dearer (16.0 -> 30.1: remote reads on the critical path of the step): 860.8 -> 870.0 us per step.
+	// Same messages, bit-identical results; push stays.
+	int pull;
 };
 
 struct PairGeo {            // phase-1 constants of k_pair_force2

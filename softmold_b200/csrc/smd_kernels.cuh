@@ -2010,7 +2010,7 @@ __device__ __forceinline__ bool slab_pack_one(bool own, int s, const Particle &p
 			if (idx >= c.capmsg) {
 				atomicOr(errflag, ERR_SLAB_MSG_CAP);
 			} else {
-				char *buf = c.send[d] + (size_t)(seq & 1) * c.parity_stride;
+				char *buf = (c.pull ? c.recv[d] : c.send[d]) + (size_t)(seq & 1) * c.parity_stride;
 				SlabMsgEntry *e = reinterpret_cast<SlabMsgEntry *>(buf + sizeof(SlabMsgHeader)) + idx;
 				st_entry(e, p, migrant ? vx : 0.0, migrant ? vy : 0.0, migrant ? vz : 0.0, migrant ? gi : (gi | GID_GHOST));
 				if (migrant && has_unw) {
@@ -2031,7 +2031,10 @@ __device__ __forceinline__ bool slab_pack_one(bool own, int s, const Particle &p
 // arrive writes the two headers
 __device__ __forceinline__ void slab_publish(const SlabComm &c, int seq, bool wrote)
 {
-	if (wrote) __threadfence_system();
+	// pull: the entries are in this device's own memory: a device-scope fence orders them before the arrival below, the last
+	// block observes every arrival and then releases the headers at system scope (release is cumulative: what the releasing
+	// thread has observed is visible to whoever acquires the header).  push: the entries crossed the link, see SlabComm.
+	if (wrote) { if (c.pull) __threadfence(); else __threadfence_system(); }
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		int t = atomicAdd(c.counters + 2, 1);
@@ -2040,8 +2043,8 @@ __device__ __forceinline__ void slab_publish(const SlabComm &c, int seq, bool wr
 			int n0 = min(atomicExch(c.counters + 0, 0), c.capmsg), n1 = min(atomicExch(c.counters + 1, 0), c.capmsg);
 			c.counters[2] = 0;
 			__threadfence_system();
-			volatile int2 *h0 = reinterpret_cast<volatile int2 *>(c.send[0] + (size_t)(seq & 1) * c.parity_stride);
-			volatile int2 *h1 = reinterpret_cast<volatile int2 *>(c.send[1] + (size_t)(seq & 1) * c.parity_stride);
+			volatile int2 *h0 = reinterpret_cast<volatile int2 *>((c.pull ? c.recv[0] : c.send[0]) + (size_t)(seq & 1) * c.parity_stride);
+			volatile int2 *h1 = reinterpret_cast<volatile int2 *>((c.pull ? c.recv[1] : c.send[1]) + (size_t)(seq & 1) * c.parity_stride);
 			int2 v0 = make_int2(n0, seq), v1 = make_int2(n1, seq);
 			asm volatile("st.release.sys.global.v2.s32 [%0], {%1, %2};" ::"l"(h0), "r"(v0.x), "r"(v0.y) : "memory");
 			asm volatile("st.release.sys.global.v2.s32 [%0], {%1, %2};" ::"l"(h1), "r"(v1.x), "r"(v1.y) : "memory");
@@ -2084,7 +2087,7 @@ __global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int ca
 	asm volatile("griddepcontrol.wait;" ::: "memory");
 	__shared__ int n_s[2];
 	if (threadIdx.x < 2) {
-		const char *buf = c.recv[threadIdx.x] + (size_t)(seq & 1) * c.parity_stride;
+		const char *buf = (c.pull ? c.send[threadIdx.x] : c.recv[threadIdx.x]) + (size_t)(seq & 1) * c.parity_stride;
 		int n = 0, sq = seq - 1;
 		long long t0 = clock64();
 		while (true) {
@@ -2100,10 +2103,11 @@ __global__ void __launch_bounds__(256) k_slab_unpack(Cnt cnt, int *dNext, int ca
 	const int N0 = cnt.get(), nL = n_s[0], nR = n_s[1], total = nL + nR;
 	for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
 		int side = e >= nL, k = e - (side ? nL : 0);
-		const char *buf = c.recv[side] + (size_t)(seq & 1) * c.parity_stride;
+		const char *buf = (c.pull ? c.send[side] : c.recv[side]) + (size_t)(seq & 1) * c.parity_stride;
 		const double2 *q = reinterpret_cast<const double2 *>(reinterpret_cast<const SlabMsgEntry *>(buf + sizeof(SlabMsgHeader)) + k);
 		int slot = N0 + e;
 		if (slot >= cap) { atomicOr(errflag, ERR_SLAB_CAPACITY); continue; }
+		// (pull: the neighbour's memory, read through the link: L2-only loads, nothing of an earlier exchange can sit in an L1)
 		double2 a = __ldcg(q), b = __ldcg(q + 1), v0 = __ldcg(q + 2), v1 = __ldcg(q + 3);
 		double2 *o = reinterpret_cast<double2 *>(pos + slot);
 		o[0] = a; o[1] = b;

@@ -283,12 +283,14 @@ def test_slab_histogram_filled_by_the_seam_and_the_unpack_is_bit_identical(bilay
     n = m["nParticles"]
     mc = np.random.RandomState(5).random_sample(16)
     out = []
-    for env in ("1", "0"):
-        os.environ["SMD_NO_SLAB_PREBIN"] = env
+    for env, push in (("1", "0"), ("0", "0"), ("0", "1")):
+        # (third run: SMD_SLAB_PULL=1 -- the receiver reads the sender's buffer through the link -- against the default, where
+        # the sender writes into the neighbour's buffer: same messages, same results; measured slower, kept for A/B)
+        os.environ["SMD_NO_SLAB_PREBIN"], os.environ["SMD_SLAB_PULL"] = env, push
         try:
             grp = LocalSlabGroup(m, 3)
         finally:
-            del os.environ["SMD_NO_SLAB_PREBIN"]
+            del os.environ["SMD_NO_SLAB_PREBIN"], os.environ["SMD_SLAB_PULL"]
         grp.batched_default = batched
         grp.compute_forces(mask=sm.MASK_ALL, step=0)
         boxes = []
@@ -299,6 +301,7 @@ def test_slab_histogram_filled_by_the_seam_and_the_unpack_is_bit_identical(bilay
         launches = sum(c.stats()[0] for c in grp.ctx)
         out.append((xyz, vel, acc, np.array(boxes), launches))
         grp.close()
-    (x0, v0, a0, b0, l0), (x1, v1, a1, b1, l1) = out
+    (x0, v0, a0, b0, l0), (x1, v1, a1, b1, l1), (x2, v2, a2, b2, l2) = out
     assert np.array_equal(b0, b1) and np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(a0, a1)
-    assert l1 < l0          # the histogram passes are gone
+    assert np.array_equal(b0, b2) and np.array_equal(x0, x2) and np.array_equal(v0, v2) and np.array_equal(a0, a2)
+    assert l1 < l0 and l2 == l1          # the histogram passes are gone
