@@ -1049,6 +1049,9 @@ static int pair_smem(smd_ctx *ctx) { return 6 * ctx->nT * ctx->nT * (int)sizeof(
 
 // NOTE on acc[]: a build permutes pos / vel / gid but not acc (it is zeroed or recomputed right after every
 // build in the reference's loop order), so forces are always evaluated as: [build] -> zero -> terms.
+// blocks per bead of k_bead: a few beads are spread over the device row by row, many beads take a block each
+static int bead_parts(int nbeads) { return std::max(1, std::min(32, 296 / std::max(nbeads, 1))); }
+
 static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 {
 	const Particle *pos = ctx->pos[ctx->pcur];
@@ -1078,8 +1081,8 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 			if (b.nOwn <= 0) continue;
 			LAUNCHP(k_beadbead<0>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius,
 			       ctx->acc, nullptr, 1.0, 1.0, 1.0);
-			LAUNCHP(k_bead<0>, b.nOwn, TPB, 0, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
-			       b.d_beads, b.d_C, b.nOwn <= 20 ? 1 : 0, 0, ctx->acc, nullptr, 1.0, 1.0, 1.0);
+			LAUNCHP(k_bead<0>, b.nOwn * bead_parts(b.nOwn), TPB, 0, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
+			       b.d_beads, b.d_C, b.nOwn <= 20 ? 1 : 0, 0, ctx->acc, nullptr, 1.0, 1.0, 1.0, bead_parts(b.nOwn));
 		}
 	if (mask & SMD_MASK(SMD_TERM_FIELD))
 		for (auto &f : ctx->fields) {
@@ -1089,8 +1092,8 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 	if (mask & SMD_MASK(SMD_TERM_NANOCORE))
 		for (auto &f : ctx->fields)
 			if (f.kind == SMD_MOL_NANOCORE && f.n > 0)
-				LAUNCHP(k_bead<0>, f.n, TPB, 0, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
-				       f.d_idx, f.d_C, 0, 1, ctx->acc, nullptr, 1.0, 1.0, 1.0);
+				LAUNCHP(k_bead<0>, f.n * bead_parts(f.n), TPB, 0, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT,
+				       f.d_idx, f.d_C, 0, 1, ctx->acc, nullptr, 1.0, 1.0, 1.0, bead_parts(f.n));
 	return SMD_OK;
 }
 
@@ -1563,16 +1566,16 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms, 
 		LAUNCH(k_beadbead<MODE>, 1, TPB, 0, b.nOwn, b.nAll, ctx->cap, pos, ctx->slot_of, ctx->geom, ctx->nT, b.d_beads, b.d_C, b.radius, nullptr,
 		       ctx->partials, sx, sy, sz);
 		finish_sum(ctx, 1, push(SMD_TERM_BEAD), 1.0);
-		LAUNCH(k_bead<MODE>, b.nOwn, TPB, 0, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, b.d_beads, b.d_C, 0, 0,
-		       nullptr, ctx->partials, sx, sy, sz);
-		finish_sum(ctx, b.nOwn, push(SMD_TERM_BEAD), 1.0);
+		LAUNCH(k_bead<MODE>, b.nOwn * bead_parts(b.nOwn), TPB, 0, b.nOwn, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, b.d_beads, b.d_C, 0, 0,
+		       nullptr, ctx->partials, sx, sy, sz, bead_parts(b.nOwn));
+		finish_sum(ctx, b.nOwn * bead_parts(b.nOwn), push(SMD_TERM_BEAD), 1.0);
 	}
 	for (auto &f : ctx->fields) {
 		if (f.kind == SMD_MOL_NANOCORE) {
 			if (f.n <= 0) continue;
-			LAUNCH(k_bead<MODE>, f.n, TPB, 0, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, f.d_idx, f.d_C, 0, 1,
-			       nullptr, ctx->partials, sx, sy, sz);
-			finish_sum(ctx, f.n, push(SMD_TERM_NANOCORE), 1.0);
+			LAUNCH(k_bead<MODE>, f.n * bead_parts(f.n), TPB, 0, f.n, ctx->cap, pos, ctx->gid[ctx->cur], ctx->slot_of, ctx->start, cur_win(ctx), ctx->geom, ctx->nT, f.d_idx, f.d_C, 0, 1,
+			       nullptr, ctx->partials, sx, sy, sz, bead_parts(f.n));
+			finish_sum(ctx, f.n * bead_parts(f.n), push(SMD_TERM_NANOCORE), 1.0);
 		} else if (MODE == 1) {   // the one-body fields have no dPotential (MD.cpp:642-669)
 			int frc = launch_field<1>(ctx, f, pos, [&](int nb, int term) { finish_sum(ctx, nb, push(term), 1.0); });
 			if (frc) return frc;

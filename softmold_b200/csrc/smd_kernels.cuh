@@ -2507,11 +2507,13 @@ template <int MODE>
 __global__ void __launch_bounds__(TPB) k_bead(int nOwn, int cap, const Particle *__restrict__ pos, const int *__restrict__ gid,
                                               const int *__restrict__ slot_of, const int *__restrict__ start, const int *__restrict__ win,
                                               Geom g, int nT, const int *__restrict__ beads, const double *__restrict__ C, int excl_all,
-                                              int nano, double *acc, double *partials, double sx, double sy, double sz)
+                                              int nano, double *acc, double *partials, double sx, double sy, double sz, int nparts)
 {
 	pdl_prologue();
 	__shared__ int seg_b[BEAD_SEGS], seg_e[BEAD_SEGS];
-	const int j = blockIdx.x;
+	// nparts blocks per bead: block (j, part) takes the rows part, part + nparts, ... of the bead's cube, so that ONE large
+	// bead (C3: a sphere of radius 5.88 against 3 000 particles) is not one block's serial loop; grid = nOwn * nparts
+	const int j = blockIdx.x / nparts, part = blockIdx.x % nparts;
 	const int bs = slot_of[beads[j]];
 	const Particle pb = load_particle(pos + bs);
 	const double cutR = nano ? C[22 * j] : C[0];   // R + rc (BEAD: row 0, system.h:2100-2101; NANOCORE: the bead's own row)
@@ -2539,12 +2541,14 @@ __global__ void __launch_bounds__(TPB) k_bead(int nOwn, int cap, const Particle 
 	};
 	double usum = 0, rx = 0, ry = 0, rz = 0;
 	const int nrows = cnt[1] * cnt[2];
-	for (int r0 = 0; r0 < nrows; r0 += BEAD_SEGS / 2) {
+	const int nmine = part < nrows ? (nrows - part + nparts - 1) / nparts : 0;   // rows of this block
+	for (int r0 = 0; r0 < nmine; r0 += BEAD_SEGS / 2) {
 		// ---- the slot ranges of up to BEAD_SEGS / 2 rows, two x segments each
+		const int nq = min(BEAD_SEGS / 2, nmine - r0);
 		__syncthreads();
-		for (int q = threadIdx.x; q < BEAD_SEGS / 2; q += blockDim.x) {
+		for (int q = threadIdx.x; q < nq; q += blockDim.x) {
 			int b0 = 0, e0 = 0, b1 = 0, e1 = 0;
-			const int r = r0 + q;
+			const int r = part + nparts * (r0 + q);
 			if (r < nrows) {
 				const int ly = axis_cell(1, r % cnt[1]) - w[1], lz = axis_cell(2, r / cnt[1]) - w[2];
 				if (ly >= 0 && ly < dm[1] && lz >= 0 && lz < dm[2]) {
@@ -2566,7 +2570,7 @@ __global__ void __launch_bounds__(TPB) k_bead(int nOwn, int cap, const Particle 
 		}
 		__syncthreads();
 		// ---- the particles of those ranges
-		for (int sgm = 0; sgm < BEAD_SEGS; sgm++) {
+		for (int sgm = 0; sgm < 2 * nq; sgm++) {
 			const int e = seg_e[sgm];
 			for (int s = seg_b[sgm] + threadIdx.x; s < e; s += blockDim.x) {
 				if (s == bs) continue;

@@ -86,7 +86,7 @@ def test_documented_switches_exist_in_the_sources():
     import re
     readme = open(os.path.join(ROOT, "README.md")).read()
     table = readme[readme.index("Run-time switches"):]
-    names = set(re.findall(r"`(SMD_[A-Z_]+)", table))
+    names = set(re.findall(r"`(SMD_[A-Z0-9_]+)", table))
     assert len(names) >= 10
     src = ""
     for f in ("smd_core.cu", "md_main.cpp", "smd_kernels.cuh"):
