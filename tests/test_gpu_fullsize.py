@@ -6,6 +6,7 @@ and oracle/_ref/ref_harness -- the reference's CellOpt / Blob::do* routines -- d
 precision:  cell ids bit-exact; per-particle forces <= 1e-5 (asserted: 1e-11) of max|F|; energies <= 1e-7 (asserted: 1e-11).
    C2  liposome 80 000 lipids              N = 240 000   at t = 0 and after 150 timesteps on the GPU (thermal occupancy)
    C4  lipoCyto 20 000 lipids + network    N =  64 962   (2 x CHAIN + BOND), with SURVEY.md 8(c)'s known answers
+   C3  continuumSphereAndLiposome          N =  15 001   (CHAIN + one BEAD of radius 5.88), at t = 0 and after 60 timesteps
    C5  flat bilayer tile 333 334 lipids    N = 998 784   after 40 timesteps
    +   SURVEY.md 8(c)'s bilayer KAT (`bilayer flat 99 20000 3.11`)
 Skipped where oracle/_ref was not built (a checkout without /root/reference)."""
@@ -113,6 +114,31 @@ def test_c4_lipocyto_64962_particles_and_its_known_answers(orc, tmp_path):
     assert near(U[sm.TERM_PAIR], -1.531856948987063e+06) and near(U[sm.TERM_BOND], 9.471083372961848e+03)
     ctx.close()
     evolve_and_compare(orc, tmp, m, "lc_eq", 100)
+
+
+def test_c3_continuum_sphere_and_liposome_15001_particles(orc, tmp_path):
+    """BASELINE config C3 from the reference's own generator: the bead - particle terms through the cell grid (k_bead, one
+    large bead dealt to several blocks) and the bead mass quirk's system, against Blob::doBeadForce / Potential / DPotential"""
+    tmp = str(tmp_path)
+    m = generate(orc, tmp, "continuumSphereAndLiposome", "csl", 1234, 5000, 3.45, 4, -6, 40, 5.88, 0, 1, 0, 2.0)
+    assert m["nParticles"] == 15001 and [mol["type"] for mol in m["molecules"]] == [sm.MOL_CHAIN, sm.MOL_BEAD]
+    # the generator leaves the sphere out of reach of the vesicle: press it against the outer leaflet (gap 0.9 below the
+    # outermost particle along x), so that the bead terms are not all zero
+    bead = int(m["molecules"][1]["bonds"][0][0])
+    lip = np.delete(np.arange(m["nParticles"]), bead)
+    com = m["xyz"][lip].mean(axis=0)
+    rmax = np.sqrt(((m["xyz"][lip] - com) ** 2).sum(axis=1)).max()
+    xyz = m["xyz"].copy()
+    xyz[bead] = com + np.array([rmax + 5.88 - 0.9, 0.0, 0.0])
+    assert np.all(xyz[bead] > 0) and np.all(xyz[bead] < np.array(m["size"]))
+    m = dict(m, xyz=xyz)
+    orc.write_mpd(os.path.join(tmp, "csl.mpd"), m)
+    g = reference_dump(orc, tmp, "csl")
+    assert np.abs(g["a_mol1"]).max() > 0 and g["U_mol"][1] != 0          # the sphere touches the membrane
+    ctx = sm.Context.from_dict(m)
+    compare(ctx, m, g)
+    ctx.close()
+    evolve_and_compare(orc, tmp, m, "csl_eq", 6)      # (a few steps: a sphere pressed in like this leaves again quickly)
 
 
 def test_c5_bilayer_tile_998784_particles(orc, tmp_path):
