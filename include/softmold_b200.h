@@ -326,7 +326,8 @@ int smd_fp64_peak(smd_ctx *ctx, double *fma_tflops, double *muladd_tflops);
  *   - desc.n_particles is the GLOBAL particle count, desc.box the global box; desc.reserved[0] = local capacity in
  *     particles (0: 1.25 * n/nranks + halo allowance), desc.reserved[1] = entries per halo message (0: default);
  *   - smd_set_particles takes the GLOBAL arrays (every rank passes the same data) and keeps what this rank owns plus
- *     its ghost columns; molecule records use global particle indices; only CHAIN molecules are supported;
+ *     its ghost columns; molecule records use global particle indices; CHAIN, BOND and BEND molecules are supported (the
+ *     members of a record must lie within SMD_SLAB_HALO cell columns of each other, else the run stops with SMD_ERR_CELL);
  *   - every step the ranks exchange migrating particles and the ghost-column halo (SMD_SLAB_HALO cell columns) by
  *     writing straight into the neighbour's receive buffer through peer memory (NVLink), inside smd_step_begin
  *     (send) and smd_step_end (receive): wire the buffers once with smd_slab_ipc_handle / smd_slab_connect_ipc

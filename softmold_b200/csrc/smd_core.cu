@@ -484,7 +484,7 @@ static int check_device_errors(smd_ctx *ctx)
 		if (flag & ERR_SLAB_MSG_CAP) ctx->err += " slab: halo message capacity exceeded (desc.reserved[1])";
 		if (flag & ERR_SLAB_CAPACITY) ctx->err += " slab: local particle capacity exceeded (desc.reserved[0])";
 		if (flag & ERR_SLAB_TIMEOUT) ctx->err += " slab: timed out waiting for a neighbour's halo message";
-		if (flag & ERR_SLAB_MISSING) ctx->err += " slab: a chain member is neither owned nor inside the halo";
+		if (flag & ERR_SLAB_MISSING) ctx->err += " slab: a member of a chain / bond / bend record is neither owned nor inside the halo";
 		return SMD_ERR_CELL;
 	}
 	return SMD_OK;
@@ -699,7 +699,6 @@ extern "C" int smd_add_bonds(smd_ctx *ctx, int32_t n, const int32_t *ij, const d
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (ij || n == 0) && c, "bad BOND arguments");
-	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, ij, 2 * (size_t)n, "BOND Molecule");
 	if (rc) return rc;
 	BondList b;
@@ -716,7 +715,6 @@ extern "C" int smd_add_bends(smd_ctx *ctx, int32_t n, const int32_t *ijk, const 
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (ijk || n == 0) && c, "bad BEND arguments");
-	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, ijk, 3 * (size_t)n, "BEND Molecule");
 	if (rc) return rc;
 	BendList b;
@@ -733,7 +731,7 @@ extern "C" int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const do
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (cj || n == 0) && c, "bad BALL arguments");
-	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN, BOND and BEND molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, cj, 2 * (size_t)n, "BALL Molecule");
 	if (rc) return rc;
 	BallList b;
@@ -750,7 +748,7 @@ extern "C" int smd_add_ball(smd_ctx *ctx, int32_t n, const int32_t *cj, const do
 static int add_field(smd_ctx *ctx, int kind, int32_t n, const int32_t *idx, const double *c, int nc_host, const double *C, size_t nC,
                      const int32_t *blocks, int width, const char *what)
 {
-	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN, BOND and BEND molecules only"; return SMD_ERR_UNSUPPORTED; }
 	CK(cudaSetDevice(ctx->device));
 	FieldMol f;
 	f.kind = kind; f.n = n; f.d_idx = nullptr; f.d_C = nullptr;
@@ -826,7 +824,7 @@ extern "C" int smd_add_rigidbend(smd_ctx *ctx, int32_t n, const int32_t *ij, con
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (ij || n == 0) && c, "bad RIGIDBEND arguments");
-	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN, BOND and BEND molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, ij, 2 * (size_t)n, "RIGIDBEND Molecule");
 	if (rc) return rc;
 	// records of two indices: uploaded as a flat list; the fifth constant travels in host_radius
@@ -927,7 +925,7 @@ extern "C" int smd_add_beads(smd_ctx *ctx, int32_t n, const int32_t *idx, const 
 {
 	if (!ctx) return SMD_ERR_ARG;
 	REQUIRE(n >= 0 && (idx || n == 0) && C, "bad BEAD arguments");
-	if (ctx->slab) { ctx->err = "slab mode supports CHAIN molecules only"; return SMD_ERR_UNSUPPORTED; }
+	if (ctx->slab) { ctx->err = "slab mode supports CHAIN, BOND and BEND molecules only"; return SMD_ERR_UNSUPPORTED; }
 	int rc = check_index(ctx, idx, (size_t)n, "BEAD Molecule");
 	if (rc) return rc;
 	CK(cudaSetDevice(ctx->device));
@@ -1067,11 +1065,11 @@ static int add_molecule_forces(smd_ctx *ctx, uint32_t mask)
 	if (mask & SMD_MASK(SMD_TERM_BOND))
 		for (auto &b : ctx->bonds)
 			if (b.n > 0)
-				LAUNCHP(k_bond<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+				LAUNCHP(k_bond<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0, ctx->gid[ctx->cur], ctx->errflag);
 	if (mask & SMD_MASK(SMD_TERM_BEND))
 		for (auto &b : ctx->bends)
 			if (b.n > 0)
-				LAUNCHP(k_bend<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0);
+				LAUNCHP(k_bend<0>, nblk(b.n, TPB), TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], ctx->acc, nullptr, 1.0, 1.0, 1.0, ctx->gid[ctx->cur], ctx->errflag);
 	if (mask & SMD_MASK(SMD_TERM_BALL))
 		for (auto &b : ctx->balls)
 			if (b.n > 0)
@@ -1546,13 +1544,13 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms, 
 	for (auto &b : ctx->bonds) {
 		if (b.n <= 0) continue;
 		int nb = nblk(b.n, TPB);
-		LAUNCH(k_bond<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz);
+		LAUNCH(k_bond<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ij, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz, ctx->gid[ctx->cur], ctx->errflag);
 		finish_sum(ctx, nb, push(SMD_TERM_BOND), 1.0);
 	}
 	for (auto &b : ctx->bends) {
 		if (b.n <= 0) continue;
 		int nb = nblk(b.n, TPB);
-		LAUNCH(k_bend<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz);
+		LAUNCH(k_bend<MODE>, nb, TPB, 0, b.n, ctx->cap, pos, ctx->slot_of, ctx->geom, b.d_ijk, b.c[0], b.c[1], nullptr, ctx->partials, sx, sy, sz, ctx->gid[ctx->cur], ctx->errflag);
 		finish_sum(ctx, nb, push(SMD_TERM_BEND), 1.0);
 	}
 	for (auto &b : ctx->balls) {

@@ -2263,21 +2263,35 @@ __global__ void __launch_bounds__(TPB, SMD_KICK_BLOCKS) k_chain_kick(Cnt cnt, in
 }
 
 // explicit BOND list (system.h:1880-1934, :2717-2747, :3398-3435); one thread per bond, FP64 atomics for the force
+// Slab mode (records carry global indices; every rank walks the whole list): a record is evaluated by every rank that OWNS
+// one of its members -- the others must then be inside its halo, else ERR_SLAB_MISSING --, forces go to owned members only,
+// and the energy terms are counted by the rank that owns the FIRST member, so every record is counted exactly once.
+__device__ __forceinline__ bool slab_owned(int s, const int *__restrict__ gid) { return s >= 0 && !(gid[s] & GID_GHOST); }
+
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_bond(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
                                               const int *__restrict__ ij, double r0, double kk, double *acc, double *partials,
-                                              double sx, double sy, double sz)
+                                              double sx, double sy, double sz, const int *__restrict__ gid, int *errflag)
 {
 	pdl_prologue();
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0;
-	if (b < nb) {
-		int s1 = slot_of[ij[2 * b]], s2 = slot_of[ij[2 * b + 1]];
+	bool o1 = true, o2 = true, go = b < nb;
+	int s1 = 0, s2 = 0;
+	if (go) {
+		s1 = slot_of[ij[2 * b]]; s2 = slot_of[ij[2 * b + 1]];
+		if (g.slab) {
+			o1 = slab_owned(s1, gid); o2 = slab_owned(s2, gid);
+			go = MODE == 0 ? (o1 || o2) : o1;
+			if (go && (s1 < 0 || s2 < 0)) { atomicOr(errflag, ERR_SLAB_MISSING); go = false; }
+		}
+	}
+	if (go) {
 		V3 d = diff_mi(load_particle(pos + s1), load_particle(pos + s2), g);
 		if (MODE == 0) {
 			V3 f = harmonic_f(d, r0, kk);
-			atomicAdd(acc + s1, f.x); atomicAdd(acc + cap + s1, f.y); atomicAdd(acc + 2 * cap + s1, f.z);
-			atomicAdd(acc + s2, -f.x); atomicAdd(acc + cap + s2, -f.y); atomicAdd(acc + 2 * cap + s2, -f.z);
+			if (o1) { atomicAdd(acc + s1, f.x); atomicAdd(acc + cap + s1, f.y); atomicAdd(acc + 2 * cap + s1, f.z); }
+			if (o2) { atomicAdd(acc + s2, -f.x); atomicAdd(acc + cap + s2, -f.y); atomicAdd(acc + 2 * cap + s2, -f.z); }
 		} else if (MODE == 1) {
 			usum = harmonic_p(d, r0, kk);
 		} else {
@@ -2346,21 +2360,30 @@ __global__ void __launch_bounds__(TPB) k_ball(int nb, int cap, const Particle *_
 template <int MODE>
 __global__ void __launch_bounds__(TPB) k_bend(int nb, int cap, const Particle *__restrict__ pos, const int *__restrict__ slot_of, Geom g,
                                               const int *__restrict__ ijk, double c0, double kk, double *acc, double *partials,
-                                              double sx, double sy, double sz)
+                                              double sx, double sy, double sz, const int *__restrict__ gid, int *errflag)
 {
 	pdl_prologue();
 	int b = blockIdx.x * blockDim.x + threadIdx.x;
 	double usum = 0;
-	if (b < nb) {
-		int s1 = slot_of[ijk[3 * b]], s2 = slot_of[ijk[3 * b + 1]], s3 = slot_of[ijk[3 * b + 2]];
+	bool o1 = true, o2 = true, o3 = true, go = b < nb;
+	int s1 = 0, s2 = 0, s3 = 0;
+	if (go) {
+		s1 = slot_of[ijk[3 * b]]; s2 = slot_of[ijk[3 * b + 1]]; s3 = slot_of[ijk[3 * b + 2]];
+		if (g.slab) {   // (see k_bond)
+			o1 = slab_owned(s1, gid); o2 = slab_owned(s2, gid); o3 = slab_owned(s3, gid);
+			go = MODE == 0 ? (o1 || o2 || o3) : o1;
+			if (go && (s1 < 0 || s2 < 0 || s3 < 0)) { atomicOr(errflag, ERR_SLAB_MISSING); go = false; }
+		}
+	}
+	if (go) {
 		Particle p2 = load_particle(pos + s2);
 		V3 da = diff_mi(load_particle(pos + s1), p2, g), db = diff_mi(p2, load_particle(pos + s3), g);
 		if (MODE == 0) {
 			V3 fa, fb;
 			bend_f(da, db, c0, kk, fa, fb);
-			atomicAdd(acc + s1, fa.x); atomicAdd(acc + cap + s1, fa.y); atomicAdd(acc + 2 * cap + s1, fa.z);
-			atomicAdd(acc + s2, fb.x - fa.x); atomicAdd(acc + cap + s2, fb.y - fa.y); atomicAdd(acc + 2 * cap + s2, fb.z - fa.z);
-			atomicAdd(acc + s3, -fb.x); atomicAdd(acc + cap + s3, -fb.y); atomicAdd(acc + 2 * cap + s3, -fb.z);
+			if (o1) { atomicAdd(acc + s1, fa.x); atomicAdd(acc + cap + s1, fa.y); atomicAdd(acc + 2 * cap + s1, fa.z); }
+			if (o2) { atomicAdd(acc + s2, fb.x - fa.x); atomicAdd(acc + cap + s2, fb.y - fa.y); atomicAdd(acc + 2 * cap + s2, fb.z - fa.z); }
+			if (o3) { atomicAdd(acc + s3, -fb.x); atomicAdd(acc + cap + s3, -fb.y); atomicAdd(acc + 2 * cap + s3, -fb.z); }
 		} else if (MODE == 1) {
 			usum = bend_p(da, db, c0, kk);
 		} else {

@@ -217,8 +217,8 @@ def test_slab_errors_are_loud(bilayer):
         c.close()
     # slab contexts refuse what they do not support instead of computing something else
     ctx = sm.Context.from_dict(m, rank=0, nranks=2)
-    with pytest.raises(sm.SoftMoldError, match="CHAIN molecules only"):
-        ctx.add_molecule(sm.MOL_BOND, np.array([[0, 1]], np.int32), [1.0, 1.0])
+    with pytest.raises(sm.SoftMoldError, match="CHAIN, BOND and BEND molecules only"):
+        ctx.add_molecule(sm.MOL_BEAD, np.array([[0]], np.int32), np.zeros(22 * m["nTypes"] ** 2))
     with pytest.raises(sm.SoftMoldError, match="connect both neighbours"):
         ctx.step(0, 1)
     ctx.close()
@@ -305,3 +305,78 @@ def test_slab_histogram_filled_by_the_seam_and_the_unpack_is_bit_identical(bilay
     assert np.array_equal(b0, b1) and np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(a0, a1)
     assert np.array_equal(b0, b2) and np.array_equal(x0, x2) and np.array_equal(v0, v2) and np.array_equal(a0, a2)
     assert l1 < l0 and l2 == l1          # the histogram passes are gone
+
+
+def _with_bond_and_bend_lists(m, seed=3):
+    """the bilayer plus a BOND list between head groups of neighbouring lipids (a cytoskeleton-like mesh, bonds up to ~2 sigma:
+    well inside the two-column halo) and a BEND list over the lipids' own triplets"""
+    rng = np.random.RandomState(seed)
+    xyz, typ, box = m["xyz"], m["type"], np.array(m["size"])
+    st, nch, ln = [int(v) for v in m["molecules"][0]["bonds"][0]]
+    heads = st + ln * np.arange(nch)
+    # nearest head in +x direction within 2 sigma (minimum image), brute force on a subset
+    pick = heads[rng.choice(len(heads), 600, replace=False)]
+    bonds = []
+    for i in pick:
+        d = xyz[heads] - xyz[i]
+        d -= box * np.round(d / box)
+        r = np.sqrt((d * d).sum(axis=1))
+        j = heads[np.argsort(r)[1]]            # nearest other head
+        if r[np.argsort(r)[1]] < 2.0:
+            bonds.append((int(i), int(j)))
+    bends = [(int(h), int(h) + 1, int(h) + 2) for h in heads[::5]]
+    mols = list(m["molecules"]) + [
+        {"type": sm.MOL_BOND, "constants": np.array([1.1, 40.0]), "bonds": np.array(bonds, np.int32)},
+        {"type": sm.MOL_BEND, "constants": np.array([-0.7, 30.0]), "bonds": np.array(bends, np.int32)}]
+    return dict(m, molecules=mols, nMolecules=len(mols))
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slab_bond_and_bend_lists_match_single_gpu(bilayer, nranks):
+    """BOND / BEND lists in slab mode (round 2): every rank walks the whole list with global indices, evaluates the records
+    that have an owned member (the partners sit in its halo), adds forces to owned members only and counts the energy of a
+    record where its first member is owned.  Against one GPU: forces <= 1e-12, every energy term, dPotential, a trajectory with
+    box moves; a bond longer than the halo is reported, not skipped."""
+    m = _with_bond_and_bend_lists(bilayer)
+    n = m["nParticles"]
+    assert len(m["molecules"][1]["bonds"]) > 300
+    scale = [1.0005, 1.0005, 1.0 / (1.0005 * 1.0005)]
+    mc = np.random.RandomState(9).random_sample(8)
+
+    def run(sim, gather):
+        sim.compute_forces(mask=sm.MASK_ALL, step=5)
+        a = gather(sim)[3]
+        U, dU = sim.potential(), sim.dpotential(scale)
+        boxes = []
+        for t in range(3):
+            sim.step(8 * t, 8)
+            boxes.append(sim.mc_box_move(0.01, 0.4, mc[2 * t], mc[2 * t + 1])[2])
+        x = gather(sim)[0]
+        return a, U, dU, np.array(boxes), x
+
+    one = sm.Context.from_dict(m)
+    a1, U1, dU1, b1, x1 = run(one, lambda c: (c.get_particles()[0], None, None, c.get_forces()))
+    one.close()
+    grp = LocalSlabGroup(m, nranks)
+    a2, U2, dU2, b2, x2 = run(grp, lambda g: g.gather(n))
+    grp.close()
+    assert rel_err(a2, a1) <= 1e-12
+    for t in (sm.TERM_PAIR, sm.TERM_CHAIN, sm.TERM_BOND, sm.TERM_BEND):
+        assert U1[t] != 0 and abs(U2[t] - U1[t]) <= 1e-12 * abs(U1[t]), t
+        assert abs(dU2[t] - dU1[t]) <= 1e-12 * abs(U1[t]) + 1e-9 * abs(dU1[t]), t
+    assert np.allclose(b2, b1, rtol=1e-13) and np.abs(x2 - x1).max() <= 1e-9
+
+    # a bond across half the box: its partner is in nobody's halo
+    dx = m["xyz"][:, 0] - m["xyz"][0, 0]
+    dx -= m["size"][0] * np.round(dx / m["size"][0])
+    far_j = int(np.argmax(np.abs(dx)))          # half a box away along x: ten cell columns
+    far = dict(m)
+    far["molecules"] = list(m["molecules"][:1]) + [{"type": sm.MOL_BOND, "constants": np.array([1.0, 1.0]),
+                                                    "bonds": np.array([[0, far_j]], np.int32)}]
+    far["nMolecules"] = 2
+    grp = LocalSlabGroup(far, 4)
+    with pytest.raises(sm.SoftMoldError, match="neither owned nor inside the halo"):
+        grp.compute_forces(mask=sm.MASK_ALL, step=0)
+        grp.synchronize()
+    for c in grp.ctx:
+        c.close()
