@@ -314,6 +314,15 @@ enum { SMD_PHASE_INTEGRATE1 = 0,  /* bead mass, Verlet::first (+ cell tagging), 
 int smd_profile(smd_ctx *ctx, uint32_t phase_mask);
 int smd_profile_read(smd_ctx *ctx, double ms[SMD_NPHASES], int64_t count[SMD_NPHASES]);
 
+/* The step on the device's own clock.  With programmatic dependent launches the kernels of a step overlap -- a block of the
+ * next kernel becomes resident as soon as one of this kernel's leaves --, which event pairs cannot show (and switch off).
+ * smd_timeline(ctx, 1): every smd_step call of >= 3 steps stamps %globaltimer in the kernels of its second-to-last step;
+ * smd_timeline_read: us15[3 k + {0, 1, 2}] = microseconds after the first block of the scan at which kernel k (0 k_scan,
+ * 1 k_place, 2 k_reorder, 3 k_pair_force2, 4 k_chain_kick) saw its first block start working, its last block start, and its
+ * last block end; -1: that kernel did not run.  Off by default (costs one cached load per block when off). */
+int smd_timeline(smd_ctx *ctx, int32_t enable);
+int smd_timeline_read(smd_ctx *ctx, double *us15);
+
 /* FP64 pipe peak of the context's device in TFLOP/s, measured with a dependency-chain micro-kernel: with fused
  * multiply-add, and with separate multiply + add (what this library issues: it is compiled without contraction to
  * stay bit-exact with the reference's x86-64 build).  Roofline denominator for the pair kernel. */

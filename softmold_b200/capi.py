@@ -40,6 +40,7 @@ SYMBOLS = [
     "smd_slab_get_local", "smd_slab_set_local", "smd_mc_propose", "smd_mc_accept",
     "smd_host_alloc", "smd_host_free", "smd_snapshot", "smd_snapshot_wait",
     "smd_add_offset_boundary", "smd_add_rigidbend", "smd_add_pullbead", "smd_create_from_mpd_driver",
+    "smd_timeline", "smd_timeline_read",
     "smd_add_inert", "smd_observe", "smd_msd_start", "smd_ke_histogram", "smd_dpotential_device",
 ]
 OBS_BONDS, OBS_EXTENT, OBS_KE_HIST, OBS_MSD = 1, 2, 4, 8
@@ -155,6 +156,8 @@ def lib():
         for nm in ("offset_boundary", "rigidbend", "pullbead"):
             getattr(L, "smd_add_" + nm).argtypes = [vp, i32, vp, vp]
         L.smd_create_from_mpd_driver.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp)]
+        L.smd_timeline.argtypes = [vp, i32]
+        L.smd_timeline_read.argtypes = [vp, vp]
         L.smd_add_inert.argtypes = [vp, i32]
         L.smd_observe.argtypes = [vp, C.c_uint32, C.POINTER(Observables), vp, vp, i32]
         L.smd_msd_start.argtypes = [vp]
@@ -356,6 +359,17 @@ class Context:
         s, p = _f64(scale), C.c_void_p()
         self._ck(self.L.smd_dpotential_device(self.h, _ptr(s), C.byref(p)))
         return p.value
+
+    TIMELINE_KERNELS = ("k_scan", "k_place", "k_reorder", "k_pair_force2", "k_chain_kick")
+
+    def timeline(self, enable=True):
+        self._ck(self.L.smd_timeline(self.h, 1 if enable else 0))
+
+    def timeline_read(self):
+        """{kernel: (first block starts working, last block starts, last block ends)} in us after the scan's first block"""
+        t = np.zeros(15)
+        self._ck(self.L.smd_timeline_read(self.h, _ptr(t)))
+        return {k: tuple(float(x) for x in t[3 * i:3 * i + 3]) for i, k in enumerate(self.TIMELINE_KERNELS)}
 
     def msd_start(self):
         self._ck(self.L.smd_msd_start(self.h))

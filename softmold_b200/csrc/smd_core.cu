@@ -1421,10 +1421,14 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 	for (int k = 0; k < nsteps; k++) {
 		ProfScope ps(ctx, SMD_PHASE_STEP);
 		const bool last = (k == nsteps - 1);
-#ifdef SMD_TIMELINE
-		if (k == nsteps - 2) k_tl_set<<<1, 1, 0, ctx->stream>>>(1);   // stamps of step nsteps - 2: build, pair and a seam that is not the last
-		if (last) k_tl_set<<<1, 1, 0, ctx->stream>>>(0);
-#endif
+		if (ctx->timeline) {   // smd_timeline: stamps of step nsteps - 2 (build, pair and a seam that is not the last of the call)
+			static const int tl_on = 1, tl_off = 0;   // (stream-ordered copies into constant memory: the kernels launched after them see the new value)
+			if (k == nsteps - 2) {
+				k_tl_reset<<<1, 1, 0, ctx->stream>>>();
+				CK(cudaMemcpyToSymbolAsync(c_tl_on, &tl_on, sizeof(int), 0, cudaMemcpyHostToDevice, ctx->stream));
+			}
+			if (last) CK(cudaMemcpyToSymbolAsync(c_tl_on, &tl_off, sizeof(int), 0, cudaMemcpyHostToDevice, ctx->stream));
+		}
 		ctx->du_armed = last && ctx->du_for_last;
 		// The seam as a programmatic dependent of the pair kernel (CHAIN-only systems, nothing recorded in between): its
 		// blocks move in where the tail of the pair grid has left SMs empty and start on their 128 slots as soon as the
@@ -1850,16 +1854,26 @@ extern "C" int smd_get_forces(smd_ctx *ctx, double *acc)
 	return check_device_errors(ctx);
 }
 
-#ifdef SMD_TIMELINE
-// debug builds only (tools/timeline.py): the stamps of the last instrumented step, ns: [kernel][first start, last start, last end]
-extern "C" int smd_timeline_read(smd_ctx *ctx, unsigned long long *out48)
+// smd_timeline: device-side time stamps of the kernels of one MD step (see TlScope)
+extern "C" int smd_timeline(smd_ctx *ctx, int32_t enable)
 {
-	CK(cudaSetDevice(ctx->device));
-	CK(cudaStreamSynchronize(ctx->stream));
-	CK(cudaMemcpyFromSymbol(out48, g_tl, 48 * sizeof(unsigned long long)));
+	if (!ctx) return SMD_ERR_ARG;
+	ctx->timeline = enable != 0;
 	return SMD_OK;
 }
-#endif
+
+extern "C" int smd_timeline_read(smd_ctx *ctx, double *us15)
+{
+	if (!ctx) return SMD_ERR_ARG;
+	REQUIRE(us15, "null argument");
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	unsigned long long t[48];
+	CK(cudaMemcpyFromSymbol(t, g_tl, sizeof t));
+	REQUIRE(t[0] != ~0ull && t[2] != 0ull, "smd_timeline_read: no instrumented step yet (smd_timeline(ctx, 1), then smd_step with nsteps >= 3 on a CHAIN-only system)");
+	for (int k = 0; k < 15; k++) us15[k] = t[k] == ~0ull || t[k] == 0ull ? -1.0 : (double)(long long)(t[k] - t[0]) * 1e-3;
+	return SMD_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ observables
 // a molecule the driver in charge parses and ignores (default case of MD.cpp:414-478: SOLID, OFFSET_BOUNDARY, RIGIDBEND,

@@ -170,6 +170,7 @@ struct smd_ctx {
 	smd::EnergyArgs du_en;
 	double *du_partials = nullptr;   // block sums of the armed dPotential (their own buffer: nothing else writes it)
 	size_t du_partials_n = 0;
+	bool timeline = false;   // smd_timeline: stamp the kernels of the second-to-last step of every smd_step call
 	int pair3 = -1;         // SMD_PAIR3: the three-threads-per-particle pair engine: 0 never, 1 always, default: systems of at most pair3_max particles
 	int pair3_max = 0;
 	bool no_fuse = false;   // SMD_NO_FUSE=1: always run the separate chain / Verlet kernels (A/B checks)

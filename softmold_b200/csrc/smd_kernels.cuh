@@ -44,12 +44,13 @@ __device__ __forceinline__ void pdl_prologue()
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-// -DSMD_TIMELINE: device-side time stamps (%globaltimer) of the step's kernels -- when the first block of a kernel starts, when
-// its last block starts and when its last block ends -- for tools/timeline.py.  Under programmatic dependent launches the
-// kernels of a step overlap, which no event pair can show.  Not compiled into the product library.
-#ifdef SMD_TIMELINE
+// Device-side time stamps (%globaltimer) of the step's kernels -- when the first block of a kernel starts working (after its
+// griddepcontrol.wait), when its last block starts and when its last block ends -- for smd_timeline / bench.py's
+// `device_timeline_us` / tools/timeline.py.  Under programmatic dependent launches the kernels of a step overlap, which no
+// event pair can show (and event pairs switch the overlap off).  The switch lives in constant memory: off, it costs one
+// uniform constant load and a predicate per block.
 __device__ unsigned long long g_tl[48];
-__device__ int g_tl_on;
+__constant__ int c_tl_on;
 __device__ __forceinline__ unsigned long long tl_now()
 {
 	unsigned long long t;
@@ -58,21 +59,18 @@ __device__ __forceinline__ unsigned long long tl_now()
 }
 struct TlScope {
 	int id;
-	__device__ __forceinline__ TlScope(int i) : id(i)
+	bool on;
+	__device__ __forceinline__ TlScope(int i) : id(i), on(threadIdx.x == 0 && c_tl_on != 0)
 	{
-		if (g_tl_on && threadIdx.x == 0) { const unsigned long long t = tl_now(); atomicMin(&g_tl[3 * id], t); atomicMax(&g_tl[3 * id + 1], t); }
+		if (on) { const unsigned long long t = tl_now(); atomicMin(&g_tl[3 * id], t); atomicMax(&g_tl[3 * id + 1], t); }
 	}
-	__device__ __forceinline__ ~TlScope() { if (g_tl_on && threadIdx.x == 0) atomicMax(&g_tl[3 * id + 2], tl_now()); }
+	__device__ __forceinline__ ~TlScope() { if (on) atomicMax(&g_tl[3 * id + 2], tl_now()); }
 };
-__global__ void k_tl_set(int on)
+__global__ void k_tl_reset()
 {
-	if (on) for (int k = 0; k < 16; k++) { g_tl[3 * k] = ~0ull; g_tl[3 * k + 1] = 0ull; g_tl[3 * k + 2] = 0ull; }
-	g_tl_on = on;
+	for (int k = 0; k < 16; k++) { g_tl[3 * k] = ~0ull; g_tl[3 * k + 1] = 0ull; g_tl[3 * k + 2] = 0ull; }
 }
 #define SMD_TL(id) TlScope tl_scope_(id)
-#else
-#define SMD_TL(id)
-#endif
 
 __device__ __forceinline__ Particle load_particle(const Particle *p)
 {
@@ -517,8 +515,8 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan(int *count, const int *bbox, 
                                                    unsigned long long *state, unsigned epoch, const Particle *pos, int *cellOfSlot,
                                                    unsigned *barrier)
 {
-	SMD_TL(0);
 	pdl_prologue();
+	SMD_TL(0);
 	__shared__ int sh[SCAN_TPB / 32];
 	__shared__ int s_excl;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -683,8 +681,8 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan(int *count, const int *bbox, 
 __global__ void __launch_bounds__(TPB) k_place(Cnt cnt, const int *cellOfSlot, int *cursor, int2 *order, const int *__restrict__ gid,
                                                int *giveback)
 {
-	SMD_TL(1);
 	pdl_prologue();
+	SMD_TL(1);
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= cnt.get()) return;
 	int c = cellOfSlot[s];
@@ -708,8 +706,8 @@ __global__ void __launch_bounds__(TPB) k_reorder(Cnt cnt, int cap, const int2 *_
                                                  const float *__restrict__ acut, int *bbox, int rearm, uint2 *pos16_out,
                                                  const float *__restrict__ arad, const int *__restrict__ win, Geom geo)
 {
-	SMD_TL(2);
 	pdl_prologue();
+	SMD_TL(2);
 	int q = blockIdx.x * blockDim.x + threadIdx.x;
 	// rearm: every few hundred builds the occupied-cell extremes start from scratch, to follow a drifting object (nobody
 	// reads them between the scan and the next tagging pass)
@@ -1282,8 +1280,8 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
                                                             const int *__restrict__ gid, EnergyArgs en,
                                                             const uint2 *__restrict__ pos16)
 {
-	SMD_TL(3);
 	asm volatile("griddepcontrol.wait;" ::: "memory");   // (its dependents are released further down, see pg.done)
+	SMD_TL(3);
 	static_assert(EMODE != 3 || SYMM, "forces + dPotential in one pass: symmetric tables only");
 	constexpr bool ENERGY_ONLY = (EMODE == 1 || EMODE == 2);   // no forces; every unordered pair once
 	constexpr bool DU = (EMODE == 3);                          // forces + dPotential

@@ -258,3 +258,25 @@ def test_particles_that_outrun_the_occupied_window(orc):
         _, key, _ = ctx.get_cell_ids()
         assert np.array_equal(key, orc.cell_ids(xyz, m["size"], m["cutoff"]))
     ctx.close()
+
+
+def test_device_timeline_of_a_step(orc):
+    """smd_timeline / smd_timeline_read: %globaltimer stamps inside the kernels of one step.  The order of the build kernels, the
+    pair kernel starting after the reorder ended, the seam ending last; switching it off again stamps nothing new."""
+    from softmold_b200 import workloads
+    m = workloads.liposome(3000, 3.45, 2)
+    ctx = sm.Context.from_dict(m)
+    ctx.compute_forces(step=0)
+    ctx.step(0, 20)
+    ctx.timeline(True)
+    ctx.step(20, 6)
+    t = ctx.timeline_read()
+    assert t["k_scan"][0] == 0.0
+    for k in t:
+        assert 0.0 <= t[k][0] <= t[k][1] <= t[k][2] < 1e4, (k, t[k])
+    assert t["k_scan"][2] <= t["k_place"][2] <= t["k_reorder"][2] <= t["k_pair_force2"][2] <= t["k_chain_kick"][2]
+    assert t["k_pair_force2"][0] >= t["k_reorder"][2] - 0.5           # (stamped after its griddepcontrol.wait)
+    ctx.timeline(False)
+    ctx.step(26, 6)
+    assert ctx.timeline_read() == t
+    ctx.close()
