@@ -237,6 +237,7 @@ struct smd_ctx {
 	int *istage;       // [N]
 	double *h_pinned;  // pinned host scratch (scalars)
 	double *terms_dev = nullptr;   // [SMD_NTERMS] result of smd_dpotential_device
+	int *import_bad = nullptr;     // first out-of-box / out-of-range particle found by the import kernel (smd_set_particles)
 
 	long long launches, rebuilds;
 

@@ -2933,7 +2933,7 @@ __global__ void __launch_bounds__(TPB) k_export_int(int N, const int *v, const i
 // gid_in: slab mode -- global index (+ ghost flag) of each uploaded particle; single GPU: slot s holds particle s
 __global__ void __launch_bounds__(TPB) k_import_particles(int N, int cap, const double *xyz, const int *type, const double *v,
                                                           Particle *pos, double *vel, double *unw, int *gid, int *slot_of,
-                                                          const int *gid_in)
+                                                          const int *gid_in, Geom g, int nT, int *bad)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= N) return;
@@ -2941,6 +2941,13 @@ __global__ void __launch_bounds__(TPB) k_import_particles(int N, int cap, const 
 	p.x = xyz[3 * s]; p.y = xyz[3 * s + 1]; p.z = xyz[3 * s + 2];
 	p.type = type[s];
 	p.cell = 0;
+	if (bad) {   // what the reference refuses at load (system.h:452-469): the first offender by (particle, axis); 3: its type
+		const double c[3] = {p.x, p.y, p.z};
+		int code = INT_MAX;
+		for (int d = 2; d >= 0; d--) if (!(c[d] >= 0 && c[d] <= g.box[d])) code = 4 * s + d;
+		if (code == INT_MAX && (p.type < 0 || p.type >= nT)) code = 4 * s + 3;
+		if (code != INT_MAX) atomicMin(bad, code);
+	}
 	store_particle(pos + s, p);
 	vel[s] = v ? v[3 * s] : 0.0; vel[cap + s] = v ? v[3 * s + 1] : 0.0; vel[2 * cap + s] = v ? v[3 * s + 2] : 0.0;
 	if (unw) { unw[s] = p.x; unw[cap + s] = p.y; unw[2 * cap + s] = p.z; }

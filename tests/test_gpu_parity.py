@@ -241,6 +241,20 @@ def test_errors_are_loud(orc):
     with pytest.raises(sm.SoftMoldError, match="X position of particle 5 is out of bounds"):
         sm.Context.from_dict(bad)
     ctx = sm.Context.from_dict(m)
+    # (the load-time checks run inside the import kernel: the FIRST offender is named, a refused upload leaves the context
+    # usable, and the next good upload works)
+    bad["xyz"][2, 2] = float("nan")
+    with pytest.raises(sm.SoftMoldError, match="Z position of particle 2 is out of bounds"):
+        ctx.set_particles(bad["xyz"], m["type"], m["vel"])
+    t = m["type"].copy()
+    t[7] = m["nTypes"]
+    with pytest.raises(sm.SoftMoldError, match="particle type out of range"):
+        ctx.set_particles(m["xyz"], t, m["vel"])
+    with pytest.raises(sm.SoftMoldError, match="smd_set_particles first"):
+        ctx.compute_forces()
+    ctx.set_particles(m["xyz"], m["type"], m["vel"])
+    ctx.compute_forces()
+    ctx.synchronize()
     with pytest.raises(sm.SoftMoldError):
         ctx.add_molecule(sm.MOL_BOND, np.array([[0, 10 ** 6]], np.int32), [1.0, 1.0])
     # a particle crossing many cells in one step is fine (cells are rebuilt from scratch, as in the reference) ...
