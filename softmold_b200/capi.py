@@ -279,14 +279,20 @@ class Context:
         vel = None if vel is None else _f64(vel)
         self._ck(self.L.smd_slab_set_local(self.h, len(gid), _ptr(gid), _ptr(xyz), _ptr(typ), _ptr(vel)))
 
-    def slab_get_local(self):
-        """owned particles of this rank: (gid, xyz, type, vel, acc), arbitrary order"""
+    def slab_get_local(self, out=None):
+        """owned particles of this rank: (gid, xyz, type, vel, acc), arbitrary order.  out: optional preallocated
+        (gid[cap], xyz[cap][3], type[cap], vel[cap][3], acc[cap][3] or None) arrays, e.g. page-locked ones"""
         cap = self.slab_capacity()
         n = C.c_int32()
-        gid, typ = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
-        xyz, vel, acc = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3))
+        if out is None:
+            gid, typ = np.empty(cap, np.int32), np.empty(cap, np.int32)
+            xyz, vel, acc = np.empty((cap, 3)), np.empty((cap, 3)), np.empty((cap, 3))
+        else:
+            gid, xyz, typ, vel, acc = out
         self._ck(self.L.smd_slab_get_local(self.h, C.byref(n), _ptr(gid), _ptr(xyz), _ptr(typ), _ptr(vel), _ptr(acc)))
         k = n.value
+        if acc is None:
+            return gid[:k], xyz[:k], typ[:k], vel[:k], None
         return gid[:k], xyz[:k], typ[:k], vel[:k], acc[:k]
 
     def add_molecule(self, mtype, records, constants, driver="md"):

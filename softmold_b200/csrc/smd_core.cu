@@ -461,6 +461,8 @@ extern "C" int smd_destroy(smd_ctx *ctx)
 	if (ctx->du_partials) cudaFree(ctx->du_partials);
 	if (ctx->terms_dev) cudaFree(ctx->terms_dev);
 	if (ctx->import_bad) cudaFree(ctx->import_bad);
+	if (ctx->export_i) cudaFree(ctx->export_i);
+	if (ctx->export_d) cudaFree(ctx->export_d);
 	if (ctx->obs_buf) cudaFree(ctx->obs_buf);
 	if (ctx->obs_host) cudaFreeHost(ctx->obs_host);
 	if (ctx->ke_bins) cudaFree(ctx->ke_bins);
@@ -649,13 +651,13 @@ extern "C" int smd_set_particles(smd_ctx *ctx, const double *xyz, const int32_t 
 	ctx->pcur = 0;
 	int *bad = nullptr, *h_bad = reinterpret_cast<int *>(ctx->h_pinned + 60);
 	if (device_check) {
-		if (!ctx->import_bad) CK(cudaMalloc(&ctx->import_bad, sizeof(int)));
+		if (!ctx->import_bad) CK(cudaMalloc(&ctx->import_bad, 2 * sizeof(int)));
 		bad = ctx->import_bad;
-		CK(cudaMemsetAsync(bad, 0x7f, sizeof(int), ctx->stream));   // 0x7f7f7f7f: larger than any code
+		CK(cudaMemsetAsync(bad, 0x7f, 2 * sizeof(int), ctx->stream));   // 0x7f7f7f7f: larger than any code
 	}
 	if (N > 0)
 		LAUNCH(k_import_particles, nblk(N, TPB), TPB, 0, N, ctx->cap, sx, ctx->istage, vel ? sv : nullptr, ctx->pos[0], ctx->vel[0],
-		       ctx->unw[0], ctx->gid[0], ctx->slot_of, gid_in, ctx->geom, ctx->nT, bad);
+		       ctx->unw[0], ctx->gid[0], ctx->slot_of, gid_in, ctx->geom, ctx->nT, bad, ctx->n_global);
 	if (bad) CK(cudaMemcpyAsync(h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaMemsetAsync(ctx->acc, 0, 3 * (size_t)ctx->cap * sizeof(double), ctx->stream));
 	ctx->acc_live = false;
@@ -1919,6 +1921,8 @@ static int obs_alloc(smd_ctx *ctx, int words)
 	if (ctx->obs_words >= words) return SMD_OK;
 	if (ctx->terms_dev) cudaFree(ctx->terms_dev);
 	if (ctx->import_bad) cudaFree(ctx->import_bad);
+	if (ctx->export_i) cudaFree(ctx->export_i);
+	if (ctx->export_d) cudaFree(ctx->export_d);
 	if (ctx->obs_buf) cudaFree(ctx->obs_buf);
 	if (ctx->obs_host) cudaFreeHost(ctx->obs_host);
 	ctx->obs_buf = nullptr; ctx->obs_host = nullptr; ctx->obs_words = 0;
@@ -2363,16 +2367,12 @@ extern "C" int smd_slab_set_local(smd_ctx *ctx, int32_t n, const int32_t *gid, c
 	REQUIRE(ctx->peer_set[0] && ctx->peer_set[1], "slab: connect both neighbours first (smd_slab_connect_*)");
 	REQUIRE(!ctx->exch_pending, "slab: previous exchange not received yet");
 	CK(cudaSetDevice(ctx->device));
-	for (int i = 0; i < n; i++) {
-		if (gid[i] < 0 || gid[i] >= ctx->n_global) { ctx->err = "global particle index out of range"; return SMD_ERR_ARG; }
-		if (type[i] < 0 || type[i] >= ctx->nT) { ctx->err = "particle type out of range"; return SMD_ERR_ARG; }
-		for (int d = 0; d < 3; d++) {
-			double x = xyz[3 * (size_t)i + d];
-			if (!(x >= 0 && x <= ctx->geom.box[d])) { ctx->err = "position of a particle is out of bounds."; return SMD_ERR_CELL; }   // system.h:452-469
-		}
-	}
+	// (global index, type and position of every particle are checked by the import kernel -- a host loop over 10^6 particles
+	// cost milliseconds on the end-to-end path of every per-rank upload)
 	double *sx = ctx->stage, *sv = ctx->stage + 3 * (size_t)ctx->cap;
 	int *dg = ctx->istage + ctx->cap;
+	if (!ctx->import_bad) CK(cudaMalloc(&ctx->import_bad, 2 * sizeof(int)));
+	CK(cudaMemsetAsync(ctx->import_bad, 0x7f, 2 * sizeof(int), ctx->stream));
 	CK(cudaMemcpyAsync(sx, xyz, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->istage, type, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(dg, gid, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -2385,11 +2385,21 @@ extern "C" int smd_slab_set_local(smd_ctx *ctx, int32_t n, const int32_t *gid, c
 	ctx->ext_valid = false;
 	if (n > 0)
 		LAUNCH(k_import_particles, nblk(n, TPB), TPB, 0, n, ctx->cap, sx, ctx->istage, vel ? sv : nullptr, ctx->pos[0], ctx->vel[0], ctx->unw[0],
-		       ctx->gid[0], ctx->slot_of, dg, ctx->geom, ctx->nT, (int *)nullptr);
+		       ctx->gid[0], ctx->slot_of, dg, ctx->geom, ctx->nT, ctx->import_bad, ctx->n_global);
+	int *h_bad = reinterpret_cast<int *>(ctx->h_pinned + 60);
+	CK(cudaMemcpyAsync(h_bad, ctx->import_bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaMemsetAsync(ctx->acc, 0, 3 * (size_t)ctx->cap * sizeof(double), ctx->stream));
 	ctx->acc_live = false;
 	retag_cells(ctx);
 	CK(cudaStreamSynchronize(ctx->stream));   // host buffers may be reused by the caller
+	if (h_bad[0] != 0x7f7f7f7f || h_bad[1] != 0x7f7f7f7f) {
+		ctx->particles_set = false;
+		CK(cudaMemsetAsync(ctx->errflag, 0, sizeof(int), ctx->stream));
+		if (h_bad[1] != 0x7f7f7f7f) { ctx->err = "global particle index out of range"; return SMD_ERR_ARG; }
+		if (h_bad[0] % 4 == 3) { ctx->err = "particle type out of range"; return SMD_ERR_ARG; }
+		ctx->err = "position of a particle is out of bounds.";   // system.h:452-469
+		return SMD_ERR_CELL;
+	}
 	ctx->particles_set = true;
 	// ghosts come from the neighbours (and strays go to them) through the ordinary exchange; received by the next
 	// force evaluation
@@ -2411,24 +2421,25 @@ extern "C" int smd_slab_get_local(smd_ctx *ctx, int32_t *n, int32_t *gid, double
 	REQUIRE(!ctx->exch_pending, "slab: read-back between smd_step_begin and smd_step_end");
 	CK(cudaSetDevice(ctx->device));
 	size_t cap = ctx->cap;
-	int *d_i = nullptr;
-	double *d_d = nullptr;
-	CK(cudaMalloc(&d_i, 2 * cap * sizeof(int)));
-	CK(cudaMalloc(&d_d, 9 * cap * sizeof(double)));
+	if (!ctx->export_i) {   // export buffers: allocated once (cudaMalloc / cudaFree per read-back cost milliseconds and a device-wide wait)
+		CK(cudaMalloc(&ctx->export_i, 2 * cap * sizeof(int)));
+		CK(cudaMalloc(&ctx->export_d, 9 * cap * sizeof(double)));
+	}
+	int *d_i = ctx->export_i;
+	double *d_d = ctx->export_d;
 	CK(cudaMemsetAsync(ctx->d_export_counter, 0, sizeof(int), ctx->stream));
 	LAUNCH(k_slab_export, nblk(ctx->N, TPB), TPB, 0, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->vel[ctx->cur], ctx->acc, ctx->gid[ctx->cur],
 	       ctx->d_export_counter, d_i, d_d, d_d + 3 * cap, d_d + 6 * cap, d_i + cap);
-	int cnt = 0;
-	cudaError_t e = cudaMemcpyAsync(&cnt, ctx->d_export_counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	if (e == cudaSuccess && gid) e = cudaMemcpy(gid, d_i, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost);
-	if (e == cudaSuccess && type) e = cudaMemcpy(type, d_i + cap, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost);
-	if (e == cudaSuccess && xyz) e = cudaMemcpy(xyz, d_d, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost);
-	if (e == cudaSuccess && vel) e = cudaMemcpy(vel, d_d + 3 * cap, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost);
-	if (e == cudaSuccess && acc) e = cudaMemcpy(acc, d_d + 6 * cap, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost);
-	cudaFree(d_i);
-	cudaFree(d_d);
-	if (e != cudaSuccess) { ctx->err = std::string("smd_slab_get_local: ") + cudaGetErrorString(e); return SMD_ERR_CUDA; }
+	int *h_cnt = reinterpret_cast<int *>(ctx->h_pinned + 62);
+	CK(cudaMemcpyAsync(h_cnt, ctx->d_export_counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	const int cnt = *h_cnt;
+	// (asynchronous on the stream: with page-locked destinations the five copies overlap their set-up, one wait at the end)
+	if (gid) CK(cudaMemcpyAsync(gid, d_i, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	if (type) CK(cudaMemcpyAsync(type, d_i + cap, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	if (xyz) CK(cudaMemcpyAsync(xyz, d_d, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	if (vel) CK(cudaMemcpyAsync(vel, d_d + 3 * cap, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	if (acc) CK(cudaMemcpyAsync(acc, d_d + 6 * cap, 3 * (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	*n = cnt;
 	return check_device_errors(ctx);
 }

@@ -237,6 +237,8 @@ struct smd_ctx {
 	int *istage;       // [N]
 	double *h_pinned;  // pinned host scratch (scalars)
 	double *terms_dev = nullptr;   // [SMD_NTERMS] result of smd_dpotential_device
+	int *export_i = nullptr;       // smd_slab_get_local: compacted gid / type [2][cap]
+	double *export_d = nullptr;    //                     compacted xyz / vel / acc [9][cap]
 	int *import_bad = nullptr;     // first out-of-box / out-of-range particle found by the import kernel (smd_set_particles)
 
 	long long launches, rebuilds;

@@ -2933,7 +2933,7 @@ __global__ void __launch_bounds__(TPB) k_export_int(int N, const int *v, const i
 // gid_in: slab mode -- global index (+ ghost flag) of each uploaded particle; single GPU: slot s holds particle s
 __global__ void __launch_bounds__(TPB) k_import_particles(int N, int cap, const double *xyz, const int *type, const double *v,
                                                           Particle *pos, double *vel, double *unw, int *gid, int *slot_of,
-                                                          const int *gid_in, Geom g, int nT, int *bad)
+                                                          const int *gid_in, Geom g, int nT, int *bad, int n_global)
 {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= N) return;
@@ -2947,13 +2947,14 @@ __global__ void __launch_bounds__(TPB) k_import_particles(int N, int cap, const 
 		for (int d = 2; d >= 0; d--) if (!(c[d] >= 0 && c[d] <= g.box[d])) code = 4 * s + d;
 		if (code == INT_MAX && (p.type < 0 || p.type >= nT)) code = 4 * s + 3;
 		if (code != INT_MAX) atomicMin(bad, code);
+		if (gid_in && ((gid_in[s] & GID_MASK) < 0 || (gid_in[s] & GID_MASK) >= n_global)) atomicMin(bad + 1, s);   // slab: global index out of range
 	}
 	store_particle(pos + s, p);
 	vel[s] = v ? v[3 * s] : 0.0; vel[cap + s] = v ? v[3 * s + 1] : 0.0; vel[2 * cap + s] = v ? v[3 * s + 2] : 0.0;
 	if (unw) { unw[s] = p.x; unw[cap + s] = p.y; unw[2 * cap + s] = p.z; }
 	int gi = gid_in ? gid_in[s] : s;
 	gid[s] = gi;
-	slot_of[gi & GID_MASK] = s;
+	if ((gi & GID_MASK) >= 0 && (gi & GID_MASK) < n_global) slot_of[gi & GID_MASK] = s;
 }
 
 // reference cell key and rank inside the cell's list, per original index

@@ -380,3 +380,32 @@ def test_slab_bond_and_bend_lists_match_single_gpu(bilayer, nranks):
         grp.synchronize()
     for c in grp.ctx:
         c.close()
+
+
+def test_slab_set_local_checks_run_on_the_device_and_name_the_fault(bilayer):
+    """smd_slab_set_local: global index, type and position of every uploaded particle are checked by the import kernel (no
+    host loop on the upload path); a refused upload leaves the rank usable"""
+    m = bilayer
+    grp = LocalSlabGroup(m, 2)
+    grp.compute_forces()
+    c = grp.ctx[0]
+    g, x, t, v, _ = c.slab_get_local()
+    g, x, t, v = g.copy(), x.copy(), t.copy(), v.copy()
+    for what, match in (("gid", "global particle index out of range"), ("type", "particle type out of range"),
+                        ("pos", "out of bounds")):
+        g2, x2, t2 = g.copy(), x.copy(), t.copy()
+        if what == "gid":
+            g2[3] = m["nParticles"] + 5
+        elif what == "type":
+            t2[4] = m["nTypes"]
+        else:
+            x2[5, 1] = -0.5
+        with pytest.raises(sm.SoftMoldError, match=match):
+            c.slab_set_local(g2, x2, t2, v)
+    for r, cc in enumerate(grp.ctx):                  # reload every rank with its own particles: the run goes on
+        gg, xx, tt, vv, _ = (g, x, t, v, None) if r == 0 else cc.slab_get_local()
+        cc.slab_set_local(gg.copy(), xx.copy(), tt.copy(), vv.copy())
+    grp.compute_forces()
+    grp.step(0, 4)
+    grp.gather(m["nParticles"])
+    grp.close()
