@@ -362,6 +362,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 			ctx->comm.recv[sd] = ctx->recv_base[sd];
 		}
 		{ const char *e = getenv("SMD_SLAB_PULL"); ctx->comm.pull = (e && *e == '1') ? 1 : 0; }
+		{ const char *e = getenv("SMD_SLAB_FENCE_GPU"); ctx->comm.gpu_fence = (e && *e == '1') ? 1 : 0; }
 		CKC(cudaMalloc(&ctx->comm.counters, 4 * sizeof(int)));
 		CKC(cudaMemset(ctx->comm.counters, 0, 4 * sizeof(int)));
 	}

@@ -92,6 +92,7 @@ struct SlabComm {
 	// the unpack 14.1 us dearer (16.0 -> 30.1: remote reads on the critical path of the step): 860.8 -> 870.0 us per step.
 	// Same messages, bit-identical results; push stays.
 	int pull;
+	int gpu_fence;          // EXPERIMENT (SMD_SLAB_FENCE_GPU=1): writers of the push transport fence at device scope only, see slab_publish
 };
 
 struct PairGeo {            // phase-1 constants of k_pair_force2

@@ -2032,9 +2032,15 @@ __device__ __forceinline__ void slab_publish(const SlabComm &c, int seq, bool wr
 	// pull: the entries are in this device's own memory: a device-scope fence orders them before the arrival below, the last
 	// block observes every arrival and then releases the headers at system scope (release is cumulative: what the releasing
 	// thread has observed is visible to whoever acquires the header).  push: the entries crossed the link, see SlabComm.
-	if (wrote) { if (c.pull) __threadfence(); else __threadfence_system(); }
+	// SMD_SLAB_FENCE_GPU=1 (experiment, push): writers fence at device scope only and thread 0 releases the block's arrival with a
+	// device-scope fence of its own; by the PTX model's cumulativity the last block's system-scope release then covers every
+	// entry (writer -> barrier -> release / acquire chain on the counter -> system fence -> header).  2 x B200: seam 98 -> 86 us,
+	// 860.4 -> 856.4 us per step, trajectories bit-identical over 2 100 steps.  NOT the default: it leans on a system fence of one SM
+	// completing peer writes that other SMs still have in flight, which the model promises and no test here can prove.
+	if (wrote) { if (c.pull || c.gpu_fence) __threadfence(); else __threadfence_system(); }
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		if (c.gpu_fence) __threadfence();
 		int t = atomicAdd(c.counters + 2, 1);
 		if (t == (int)gridDim.x - 1) {
 			__threadfence_system();
