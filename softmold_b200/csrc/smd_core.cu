@@ -1217,11 +1217,12 @@ template <int EMODE, bool LANGEVIN, int SPLIT>
 static int launch_pair_split(smd_ctx *ctx, const LangevinArgs &lg, const EnergyArgs &en)
 {
 	typedef PairCfg<SPLIT> Cfg;
-	static bool attr_done = false;   // > 48 KB of dynamic shared memory needs the opt-in (SPLIT = 9 with many types)
+	// > 48 KB of dynamic shared memory (many particle types) needs the opt-in: a property of the function ON A DEVICE, raised once
+	static bool attr_done[64] = {false};
 	const int smem = pair_force_smem_t<SPLIT>(ctx, EMODE == 3);
-	if (smem > 48 * 1024 && !attr_done) {
+	if (smem > 48 * 1024 && !attr_done[ctx->device & 63]) {
 		CK(cudaFuncSetAttribute(k_pair_force2<EMODE, LANGEVIN, true, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-		attr_done = true;
+		attr_done[ctx->device & 63] = true;
 	}
 	LAUNCHP((k_pair_force2<EMODE, LANGEVIN, true, SPLIT>), nblk(ctx->N, Cfg::NP), Cfg::BT, smem, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
 	       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], en, ctx->pos16);
