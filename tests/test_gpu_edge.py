@@ -280,3 +280,17 @@ def test_device_timeline_of_a_step(orc):
     ctx.step(26, 6)
     assert ctx.timeline_read() == t
     ctx.close()
+
+
+@pytest.mark.parametrize("engine", ["0", "1"])
+def test_many_particle_types_need_the_shared_memory_opt_in(orc, engine):
+    """26 particle types: the staged pair tables (80 B per ordered type pair) push the dynamic shared memory of both pair
+    engines past 48 KB, the size that needs cudaFuncAttributeMaxDynamicSharedMemorySize -- with one (SMD_PAIR3=0) and with
+    three threads per particle"""
+    import os
+    m = gas(23, 2500, (14.3, 11.1, 12.7), n_types=26, chains=((100, 3),))
+    os.environ["SMD_PAIR3"] = engine
+    try:
+        check_against_oracle(orc, m, steps=4)
+    finally:
+        del os.environ["SMD_PAIR3"]
