@@ -1378,6 +1378,16 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 		};
 		// Potential<T>, MD.h:895-930, on r^2 (x normal and positive): correctly rounded sqrt as above, both branches
 		// evaluated and selected
+		auto upoly = [&](double dr, const char *c) {   // the potential at distance dr (= the correctly rounded sqrt of r^2)
+			double2 c01 = *reinterpret_cast<const double2 *>(c + 16);
+			double c2 = *reinterpret_cast<const double *>(c + 32);
+			double2 c34 = *reinterpret_cast<const double2 *>(c + 48);
+			double c5 = *reinterpret_cast<const double *>(c + 64);
+			double tc = c01.x - dr, tt = c34.x - dr;
+			double ucore = c01.y * tc * tc + c2;
+			double utail = tt * tt * (c34.y - tt * c5);
+			return (dr <= c01.x) ? ucore : utail;
+		};
 		auto upot = [&](double x, const char *c) {
 			double y = rsqrt43(x);
 			double dr = x * y;
@@ -1414,7 +1424,9 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 			ax += dx * q; ay += dy * q; az += dz * q;
 			if (DU && !(in && !ok)) {   // (pairs handed to the general routine take their energy term there)
 				const char *cu = rowu + (PTAB_STRIDE * 8) * pj.type;
-				double uo = upot(in ? dr2 : 1.0, cu);
+				// (here the pair is either out of range or took the fast path: dr above IS sqrt(dr2), the very value upot would
+				// compute again -- same operations on the same operand)
+				double uo = upoly(dr, cu);
 				uo = in ? uo : 0.0;
 				double ex = po.x * en.sx - pj.x * en.sx, ey = po.y * en.sy - pj.y * en.sy, ez = po.z * en.sz - pj.z * en.sz;
 				double er2 = ex * ex + ey * ey + ez * ez;
