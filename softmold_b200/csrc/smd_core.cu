@@ -1878,6 +1878,17 @@ extern "C" int smd_get_forces(smd_ctx *ctx, double *acc)
 	return check_device_errors(ctx);
 }
 
+#ifdef SMD_PHASE_CLOCKS
+extern "C" int smd_phase_clocks(smd_ctx *ctx, unsigned long long *out16, int reset)
+{
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaMemcpyFromSymbol(out16, g_pc, 16 * sizeof(unsigned long long)));
+	if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_pc, z, sizeof z)); }
+	return SMD_OK;
+}
+#endif
+
 // smd_timeline: device-side time stamps of the kernels of one MD step (see TlScope)
 extern "C" int smd_timeline(smd_ctx *ctx, int32_t enable)
 {

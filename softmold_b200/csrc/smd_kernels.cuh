@@ -71,6 +71,15 @@ __global__ void k_tl_reset()
 	for (int k = 0; k < 16; k++) { g_tl[3 * k] = ~0ull; g_tl[3 * k + 1] = 0ull; g_tl[3 * k + 2] = 0ull; }
 }
 #define SMD_TL(id) TlScope tl_scope_(id)
+#ifdef SMD_PHASE_CLOCKS
+// debug builds only (tools/phase_clocks.py): cycles per warp between the phase marks of k_pair_force2, summed over warps
+__device__ unsigned long long g_pc[16];
+#define SMD_PC(k) do { if ((threadIdx.x & 31) == 0) { const long long t_ = clock64(); atomicAdd(&g_pc[k], (unsigned long long)(t_ - pc_t)); pc_t = t_; } } while (0)
+#define SMD_PC_INIT long long pc_t = clock64(); if (threadIdx.x == 0) atomicAdd(&g_pc[15], 1ull)
+#else
+#define SMD_PC(k)
+#define SMD_PC_INIT
+#endif
 
 __device__ __forceinline__ Particle load_particle(const Particle *p)
 {
@@ -1325,6 +1334,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	const int fd0 = win[WIN_FD0], xs = g.xs;
 
 
+	SMD_PC_INIT;
 	// ---- deal the block's particles to threads by class
 	{
 		const int pt = SPLIT > 1 ? lane : tid;   // (split engines: every warp holds the same 32 particles)
@@ -1511,6 +1521,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	unsigned wlim = lbase + 64u * (CAP - 8);    // checked once per two groups of four
 	asm volatile("" : "+r"(wlim));               // opaque: rematerialising the shared-window address cost 8 instructions per group
 
+	SMD_PC(0);   // entry: table staging, dealing, own record
 	// ---- the particle's candidate ranges: one per (y,z) row of the stencil, pruned by geometry
 	// conservative FP32 distances to the faces of the own cell: a neighbour cell at offset -1 / +1 along an axis holds
 	// no point closer than that along the axis
@@ -1594,6 +1605,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 		nseg = (je > jb) ? rr + 1 : nseg;
 	}
 
+	SMD_PC(1);   // range set-up
 	// ---- phase 1: prefilter along the thread's own stream of ranges over the 8-byte candidate records (16-bit
 	// window-relative coordinates, see quantize16) -- from the block's staged copy in shared memory where the range was
 	// staged, else from global memory; four candidates per step, the next four already in flight.  The coordinates are
@@ -1659,6 +1671,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	}
 
 
+	SMD_PC(2);   // phase 1
 	// ---- rows and end cells seen through a periodic image (particles in the outermost cell layers only)
 	if (shifted_rows) {
 #pragma unroll 1
@@ -1712,6 +1725,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 		}
 	}
 
+	SMD_PC(3);   // periodic-image rows
 	// ---- hand the lists out again, longest first
 	const int lcnt = (int)((wp - lbase) >> 6);
 	sm.cnt[tid] = lcnt;
@@ -1735,6 +1749,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	sm.order[atomicAdd(&sm.hist[lcnt], 1)] = tid;
 	__syncthreads();
 
+	SMD_PC(4);   // hand-over: histogram, prefix, order (three barriers: includes waiting for the block's slowest warp)
 	// ---- phase 2: drain one list, FP64
 	const int o = sm.order[tid];
 	const int io = sm.perm[SPLIT > 1 ? (o & 31) : o];
@@ -1797,6 +1812,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	} else {
 		acc[iw] += ax; acc[cap + iw] += ay; acc[2 * cap + iw] += az;
 	}
+	SMD_PC(5);   // phase 2 + epilogue (warps that returned early are not counted)
 	if (pg.done) {   // this block's accelerations are complete: release its seam block
 		__threadfence();
 		__syncthreads();
