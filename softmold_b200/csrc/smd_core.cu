@@ -1932,10 +1932,6 @@ static const double KE_PARTITION = 0.0001;       // kEnergyDensityPartition, dat
 static int obs_alloc(smd_ctx *ctx, int words)
 {
 	if (ctx->obs_words >= words) return SMD_OK;
-	if (ctx->terms_dev) cudaFree(ctx->terms_dev);
-	if (ctx->import_bad) cudaFree(ctx->import_bad);
-	if (ctx->export_i) cudaFree(ctx->export_i);
-	if (ctx->export_d) cudaFree(ctx->export_d);
 	if (ctx->obs_buf) cudaFree(ctx->obs_buf);
 	if (ctx->obs_host) cudaFreeHost(ctx->obs_host);
 	ctx->obs_buf = nullptr; ctx->obs_host = nullptr; ctx->obs_words = 0;
