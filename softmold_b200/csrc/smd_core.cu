@@ -298,6 +298,8 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	{ const char *e = getenv("SMD_NO_FUSE"); ctx->no_fuse = e && *e == '1'; }
 	{ const char *e = getenv("SMD_PAIR3"); ctx->pair3 = e ? atoi(e) : -1; }
 	{ const char *e = getenv("SMD_PAIR3_MAX"); ctx->pair3_max = e ? atoi(e) : SMD_PAIR3_MAX_DEFAULT; }
+	{ const char *e = getenv("SMD_PAIR_TAIL"); ctx->pair_tail = (e && *e == '1') ? 1 : 0; }
+	{ cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.multiProcessorCount > 0) ctx->sm_count = prop.multiProcessorCount; }
 	{ const char *e = getenv("SMD_NO_PREBIN"); ctx->prebin = !(e && *e == '1'); }
 	{ const char *e = getenv("SMD_NO_SLAB_PREBIN"); ctx->no_slab_prebin = e && *e == '1'; }
 	{ const char *e = getenv("SMD_NO_DU_FUSE"); ctx->no_du_fuse = e && *e == '1'; }
@@ -310,7 +312,7 @@ extern "C" int smd_create(const smd_desc *desc, smd_ctx **out)
 	ctx->pcur = 0;
 	set_geom(ctx, desc->box);
 	ctx->pgeo.rmin32 = (float)desc->cutoff;
-	ctx->pgeo.done = nullptr; ctx->pgeo.epoch = 0;
+	ctx->pgeo.done = nullptr; ctx->pgeo.epoch = 0; ctx->pgeo.first = 0; ctx->pgeo.part0 = 0; ctx->pgeo.nowait = 0;
 	int rc = check_geom(ctx);
 	if (rc) { g_create_error = ctx->err; delete ctx; return rc; }
 
@@ -1209,12 +1211,30 @@ static int pair_split(const smd_ctx *ctx)
 	if (ctx->pair3 >= 0) return ctx->pair3 ? 3 : 1;   // SMD_PAIR3 = 0 | 1
 	return ctx->N <= ctx->pair3_max ? 3 : 1;
 }
-// particles per block of the pair force engine in use: the unit of the completion words (PairGeo::done) and of the
-// dPotential block sums of the force + dPotential pass
-static int pair_block_particles(const smd_ctx *ctx) { return pair_split(ctx) > 1 ? PAIR_SPLIT_NP : PAIR_TPB; }
+// Which blocks of particles go to which engine.  Small systems: everything to the three-thread engine.  Large ones: the
+// one-thread engine -- and, as an experiment (SMD_PAIR_TAIL=1, see launch_pair_force), in whole rounds of (resident blocks
+// per SM x SMs) blocks with the particles of a last round that would be less than half full handed to the three-thread engine
+// in a second launch behind the first.
+struct PairPlan { int nb_main, first_tail, nb_tail; };
+static PairPlan pair_plan(const smd_ctx *ctx)
+{
+	const int N = ctx->N;
+	PairPlan p = {nblk(N, PAIR_TPB), 0, 0};
+	const int split = pair_split(ctx);
+	if (split == 3) { p.nb_main = 0; p.first_tail = 0; p.nb_tail = nblk(N, PAIR_SPLIT_NP); return p; }
+	if (!ctx->tables_symmetric || !ctx->pair_tail || ctx->slab) return p;
+	const int slots = ctx->sm_count * SMD_PAIR_BLOCKS;
+	const int rem = p.nb_main % slots;
+	if (p.nb_main > slots && rem > 0 && 2 * rem < slots) {
+		p.nb_main -= rem;
+		p.first_tail = p.nb_main * PAIR_TPB;
+		p.nb_tail = nblk(N - p.first_tail, PAIR_SPLIT_NP);
+	}
+	return p;
+}
 
 template <int EMODE, bool LANGEVIN, int SPLIT>
-static int launch_pair_split(smd_ctx *ctx, const LangevinArgs &lg, const EnergyArgs &en)
+static int launch_pair_split(smd_ctx *ctx, const LangevinArgs &lg, const EnergyArgs &en, int first, int nb, int part0, int nowait = 0)
 {
 	typedef PairCfg<SPLIT> Cfg;
 	// > 48 KB of dynamic shared memory (many particle types) needs the opt-in: a property of the function ON A DEVICE, raised once
@@ -1224,8 +1244,10 @@ static int launch_pair_split(smd_ctx *ctx, const LangevinArgs &lg, const EnergyA
 		CK(cudaFuncSetAttribute(k_pair_force2<EMODE, LANGEVIN, true, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 		attr_done[ctx->device & 63] = true;
 	}
-	LAUNCHP((k_pair_force2<EMODE, LANGEVIN, true, SPLIT>), nblk(ctx->N, Cfg::NP), Cfg::BT, smem, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-	       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], en, ctx->pos16);
+	PairGeo pg = ctx->pgeo;
+	pg.first = first; pg.part0 = part0; pg.nowait = nowait;
+	LAUNCHP((k_pair_force2<EMODE, LANGEVIN, true, SPLIT>), nb, Cfg::BT, smem, cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+	       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], en, ctx->pos16);
 	return SMD_OK;
 }
 
@@ -1233,27 +1255,39 @@ static int launch_pair_split(smd_ctx *ctx, const LangevinArgs &lg, const EnergyA
 template <bool LANGEVIN>
 static int launch_pair_force(smd_ctx *ctx, const LangevinArgs &lg)
 {
-	const int N = ctx->N, nb = nblk(N, PAIR_TPB);
-	const int split = pair_split(ctx);
+	const PairPlan pl = pair_plan(ctx);
+	PairGeo pg = ctx->pgeo;
+	pg.first = 0; pg.part0 = 0;
+	int rc = SMD_OK;
+	// Hybrid (EXPERIMENT, SMD_PAIR_TAIL=1): the main launch in whole rounds, then a small three-thread launch for what would have
+	// been the partial last round.  The small launch is a programmatic dependent of the main one, whose results it does not
+	// need -- it needs the cell build, which had completed and flushed before the first main block got past its
+	// griddepcontrol.wait, and no small block is resident before every main block has started -- so it does not wait
+	// (PairGeo::nowait) and its blocks move in as main blocks leave.  Measured on C2: the pair kernels end at 178.0 instead of
+	// 184.0 us of the step, 203.6 -> 200.4 us per MD step (the other order, small launch first: 201.5).  Off by default: 1.6 % do
+	// not pay for a grid that reads the build's output without having waited on anything -- the read-only data path may keep
+	// lines of the previous step that only a completed dependency is documented to invalidate.
+	const int hybrid_nowait = (pl.nb_tail > 0 && pl.nb_main > 0 && pg.done != nullptr) ? 1 : 0;
 	if (LANGEVIN && ctx->du_armed && ctx->tables_symmetric) {   // forces + Langevin + the dPotential of the box move proposed for this configuration (smd_step_mc)
 		ctx->du_armed = false;
-		int rc = SMD_OK;
-		if (split == 3) rc = launch_pair_split<3, true, 3>(ctx, lg, ctx->du_en);
-		else
-		LAUNCHP((k_pair_force2<3, true, true>), nb, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16);
-		if (rc) return rc;
+		if (pl.nb_main > 0)
+			LAUNCHP((k_pair_force2<3, true, true>), pl.nb_main, PAIR_TPB, pair_force_smem(ctx, true), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+			       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], ctx->du_en, ctx->pos16);
+		if (pl.nb_tail > 0 && (rc = launch_pair_split<3, true, 3>(ctx, lg, ctx->du_en, pl.first_tail, pl.nb_tail, pl.nb_main, hybrid_nowait))) return rc;
+		ctx->du_nparts = pl.nb_main + pl.nb_tail;
 		ctx->du_ready = true;
 		return SMD_OK;
 	}
-	if (split == 3) return launch_pair_split<0, LANGEVIN, 3>(ctx, lg, EnergyArgs{});
-	if (ctx->tables_symmetric)
-		LAUNCHP((k_pair_force2<0, LANGEVIN, true>), nb, PAIR_TPB, pair_force_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
-	else
-		LAUNCH((k_pair_force2<0, LANGEVIN, false>), nb, PAIR_TPB, pair_force_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
-		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, ctx->pgeo, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
-	return SMD_OK;
+	if (!ctx->tables_symmetric) {
+		LAUNCH((k_pair_force2<0, LANGEVIN, false>), pl.nb_main, PAIR_TPB, pair_force_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
+		return SMD_OK;
+	}
+	if (pl.nb_main > 0)
+		LAUNCHP((k_pair_force2<0, LANGEVIN, true>), pl.nb_main, PAIR_TPB, pair_force_smem(ctx, false), cnt_of(ctx), ctx->cap, ctx->pos[ctx->pcur], ctx->pos32,
+		       ctx->start, cur_win(ctx), ctx->geom, ctx->nT, ctx->fC, ctx->ptab, pg, ctx->acc, lg, ctx->gid[ctx->cur], EnergyArgs{}, ctx->pos16);
+	if (pl.nb_tail > 0) rc = launch_pair_split<0, LANGEVIN, 3>(ctx, lg, EnergyArgs{}, pl.first_tail, pl.nb_tail, pl.nb_main, hybrid_nowait);
+	return rc;
 }
 
 static int forces(smd_ctx *ctx, uint32_t mask, int64_t step, bool langevin_first)
@@ -1472,7 +1506,7 @@ extern "C" int smd_step(smd_ctx *ctx, int64_t first_step, int32_t nsteps)
 		if (rc) return rc;
 		const int *done = pdl ? ctx->pair_done : nullptr;
 		const int epoch = ctx->pair_epoch;
-		const int done_per = TPB / pair_block_particles(ctx);   // completion words per seam block
+		const int done_per = TPB / PAIR_SPLIT_NP;   // completion words per seam block: one per 32 slots, whatever the pair engine
 		ProfScope pf(ctx, SMD_PHASE_FUSED);
 		if (last && pdl) {
 			CK(launch_dependent(k_chain_kick<true>, nblk(N, TPB), TPB, ctx->stream, cnt_of(ctx), ctx->cap, (const Particle *)ctx->pos[ctx->pcur],
@@ -1541,7 +1575,7 @@ static int energy_terms(smd_ctx *ctx, const double scale[3], double *out_terms, 
 	if (MODE == 2 && ctx->du_ready && sx == ctx->du_en.sx && sy == ctx->du_en.sy && sz == ctx->du_en.sz) {
 		// the block sums of this very dPotential were left behind by the force kernel of the last step (smd_arm_dpotential)
 		ctx->du_ready = false;
-		LAUNCH(k_final_sum, 1, 256, 0, nblk(N, pair_block_particles(ctx)), ctx->du_partials, ctx->scalars, push(SMD_TERM_PAIR), 1.0);
+		LAUNCH(k_final_sum, 1, 256, 0, ctx->du_nparts, ctx->du_partials, ctx->scalars, push(SMD_TERM_PAIR), 1.0);
 	} else if (ctx->tables_symmetric && !ctx->force_onephase_energy) {
 		// two-phase kernel, every unordered pair once (see k_pair_force2)
 		int nb = nblk(N, PAIR_TPB);

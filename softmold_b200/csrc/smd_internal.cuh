@@ -102,8 +102,11 @@ struct PairGeo {            // phase-1 constants of k_pair_force2
 	float cs32[3];          // cell size
 	float rmin32;           // smallest positive per-type phase-1 radius (pos16 path: widening of the energy modes' cutoffs)
 	float finv32;           // x slices per unit length (Geom::finv)
-	int *done;              // per-block completion words for a programmatic dependent launch of the step seam (else null)
+	int *done;              // completion words, one per 32 slots, for a programmatic dependent launch of the step seam (else null)
 	int epoch;              // value a block stores there
+	int first;              // first slot of this launch (the tail launch of a hybrid pair of launches starts past the main one's)
+	int part0;              // index of this launch's first block sum in EnergyArgs::partials
+	int nowait;             // tail launch of a hybrid pair: does not wait for the main launch, which it does not depend on (see k_pair_force2)
 };
 
 // energy modes of k_pair_force2: the proposed scaling, the widening of the phase-1 cutoffs, where the block sums go;
@@ -171,6 +174,9 @@ struct smd_ctx {
 	smd::EnergyArgs du_en;
 	double *du_partials = nullptr;   // block sums of the armed dPotential (their own buffer: nothing else writes it)
 	size_t du_partials_n = 0;
+	int sm_count = 148;      // SMs of the device
+	int pair_tail = 0;       // SMD_PAIR_TAIL=1 (experiment): hand the last, partial round of pair blocks to the three-thread engine
+	int du_nparts = 0;       // block sums the armed force + dPotential launch(es) leave in du_partials
 	bool timeline = false;   // smd_timeline: stamp the kernels of the second-to-last step of every smd_step call
 	int pair3 = -1;         // SMD_PAIR3: the three-threads-per-particle pair engine: 0 never, 1 always, default: systems of at most pair3_max particles
 	int pair3_max = 0;

@@ -1289,7 +1289,10 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
                                                             const int *__restrict__ gid, EnergyArgs en,
                                                             const uint2 *__restrict__ pos16)
 {
-	asm volatile("griddepcontrol.wait;" ::: "memory");   // (its dependents are released further down, see pg.done)
+	// (its dependents are released further down, see pg.done)  The tail launch of a hybrid pair is a programmatic dependent of
+	// the MAIN launch, whose results it does not need: it only needs the cell build, and that had completed and flushed before
+	// the first main block got past this very wait -- and no tail block is resident before every main block has started.
+	if (!pg.nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
 	SMD_TL(3);
 	static_assert(EMODE != 3 || SYMM, "forces + dPotential in one pass: symmetric tables only");
 	constexpr bool ENERGY_ONLY = (EMODE == 1 || EMODE == 2);   // no forces; every unordered pair once
@@ -1306,8 +1309,9 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	static_assert(CAP <= PAIR_CAP, "hist[] is sized for the one-thread engine");
 	const int N = cnt.get();
 	const int bid = (int)blockIdx.x;
-	if (bid * NP >= N) {
-		if (EMODE != 0 && threadIdx.x == 0) en.partials[blockIdx.x] = 0.0;
+	const int base = pg.first + bid * NP;   // first slot of this block
+	if (base >= N) {
+		if (EMODE != 0 && threadIdx.x == 0) en.partials[pg.part0 + blockIdx.x] = 0.0;
 		return;
 	}
 	// pg.done: the step seam is launched as a programmatic dependent of this kernel.  All its blocks may become resident as
@@ -1338,7 +1342,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	// ---- deal the block's particles to threads by class
 	{
 		const int pt = SPLIT > 1 ? lane : tid;   // (split engines: every warp holds the same 32 particles)
-		const int i0 = bid * NP + pt;
+		const int i0 = base + pt;
 		const bool heavy = (i0 < N) && pos32[i0].w >= pg.thr32;
 		const unsigned bal = __ballot_sync(0xffffffffu, heavy);
 		if (lane == 0) sm.wcnt[wid] = __popc(bal);
@@ -1767,7 +1771,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 		sm.part[0][o] = act ? du : 0.0;
 		__syncthreads();
 		double tot = block_sum(sm.part[0][tid]);
-		if (tid == 0) en.partials[blockIdx.x] = tot;
+		if (tid == 0) en.partials[pg.part0 + blockIdx.x] = tot;
 		if (SPLIT == 1 && !act && !pg.done) return;
 	}
 	if (ENERGY_ONLY) {   // one partial sum per block, reduced deterministically by k_final_sum
@@ -1777,7 +1781,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 		sm.part[0][o] = act ? ax : 0.0;
 		__syncthreads();
 		double tot = block_sum(sm.part[0][tid]);
-		if (tid == 0) en.partials[blockIdx.x] = tot;
+		if (tid == 0) en.partials[pg.part0 + blockIdx.x] = tot;
 		return;
 	}
 	int iw = io;        // the particle whose acceleration this thread writes
@@ -1816,7 +1820,8 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	if (pg.done) {   // this block's accelerations are complete: release its seam block
 		__threadfence();
 		__syncthreads();
-		if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(pg.done + bid), "r"(pg.epoch) : "memory");
+		// (one word per 32 slots, whatever the engine: the seam waits for the four words of its 128 slots)
+		if (tid < NP / 32) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(pg.done + base / 32 + tid), "r"(pg.epoch) : "memory");
 	}
 }
 
