@@ -1328,7 +1328,12 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	double *s_utab = s_ptab + nptab;
 	double *s_dup = s_utab + nptab;
 	unsigned short *s_lists = reinterpret_cast<unsigned short *>(DU ? s_dup + BT : s_ptab + nptab);
-	const int row0 = SPLIT > 1 ? NROW * (int)(threadIdx.x >> 5) : 0;   // first stencil row of this thread
+	const int row0 = SPLIT > 1 ? NROW * (int)(threadIdx.x >> 5) : 0;   // first stencil row of this thread (SPLIT = 1)
+	// SPLIT = 3: which three rows a warp walks.  By z plane the middle warp got the own row AND two face rows, 64 % of the
+	// candidates, and the other two waited for it at the hand-over (barrier stall 2.5 per issue, profiles/r02n_pair3_kernel.md);
+	// dealt by weight instead: own row + two corner rows / two face rows + a corner row / the same (r = 3 (oz + 1) + oy + 1).
+	const unsigned rowmap = SPLIT == 3 ? ((threadIdx.x >> 5) == 0 ? 0x804u : (threadIdx.x >> 5) == 1 ? 0x231u : 0x675u) : 0u;
+	auto row_of = [&](int rr) -> int { return SPLIT == 3 ? (int)((rowmap >> (4 * rr)) & 15u) : row0 + rr; };
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	for (int k = tid; k < nptab; k += BT) s_ptab[k] = ptab[k];
 	if (DU) for (int k = tid; k < nptab; k += BT) s_utab[k] = en.utab[k];
@@ -1547,7 +1552,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	// all the look-ups of start[] are issued before any of them is used (one trip to L2 instead of nine)
 #pragma unroll
 	for (int rr = 0; rr < NROW; rr++) {
-		const int r = row0 + rr;
+		const int r = row_of(rr);
 		const int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
 		int nz = cz + oz, ny = cy + oy;
 		bool wrapyz = nz < 0 || nz >= g.nc[2] || ny < 0 || ny >= g.nc[1];
@@ -1584,7 +1589,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	}
 #pragma unroll
 	for (int rr = 0; rr < NROW; rr++) {
-		const int r = row0 + rr;
+		const int r = row_of(rr);
 		int jb = rjb[rr];
 		const int je = rje[rr];
 		if (ENERGY_ONLY && r == 4) jb = min(max(jb, i + 1), je);   // own row: only the slots behind mine
@@ -1629,7 +1634,7 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	}
 	const int aiqi = __float_as_int(aiq);
 	for (int sq = 0; sq < nseg; sq++) {
-		const int sg = row0 + sq;
+		const int sg = row_of(sq);
 		const int n = sm.seg_n[sg][tid];
 		if (n == 0) continue;
 		const uint2 *cp = pos16 + sm.seg_b[sg][tid];
@@ -1679,8 +1684,8 @@ __global__ void __launch_bounds__(PairCfg<SPLIT>::BT, PairCfg<SPLIT>::BLOCKS) k_
 	// ---- rows and end cells seen through a periodic image (particles in the outermost cell layers only)
 	if (shifted_rows) {
 #pragma unroll 1
-		for (int s = 3 * row0; s < 3 * (row0 + NROW); s++) {
-			int r = s / 3, sub = s - 3 * r;
+		for (int s = 0; s < 3 * NROW; s++) {
+			int r = row_of(s / 3), sub = s - 3 * (s / 3);
 			int oz = r / 3 - 1, oy = r - 3 * (r / 3) - 1;
 			int nz = cz + oz, ny = cy + oy;
 			float sx = 0.f, sy = 0.f, sz = 0.f;
