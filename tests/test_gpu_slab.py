@@ -366,6 +366,20 @@ def test_slab_bond_and_bend_lists_match_single_gpu(bilayer, nranks):
         assert abs(dU2[t] - dU1[t]) <= 1e-12 * abs(U1[t]) + 1e-9 * abs(dU1[t]), t
     assert np.allclose(b2, b1, rtol=1e-13) and np.abs(x2 - x1).max() <= 1e-9
 
+    # the production call sequence: steps + trial in one call (smd_step_mc: fused seam, force + dPotential pass armed on every rank)
+    one = sm.Context.from_dict(m)
+    one.compute_forces(mask=sm.MASK_ALL, step=5)
+    grp = LocalSlabGroup(m, nranks)
+    grp.batched_default = True
+    grp.compute_forces(mask=sm.MASK_ALL, step=5)
+    for t in range(3):
+        r1 = one.step_mc(8 * t, 8, 0.01, 0.4, mc[2 * t], mc[2 * t + 1])
+        r2 = grp.step_mc(8 * t, 8, 0.01, 0.4, mc[2 * t], mc[2 * t + 1])
+        assert r1[0] == r2[0] and np.allclose(r1[2], r2[2], rtol=1e-13)
+    assert np.abs(grp.gather(n)[0] - one.get_particles()[0]).max() <= 1e-9
+    one.close()
+    grp.close()
+
     # a bond across half the box: its partner is in nobody's halo
     dx = m["xyz"][:, 0] - m["xyz"][0, 0]
     dx -= m["size"][0] * np.round(dx / m["size"][0])
